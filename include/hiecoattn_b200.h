@@ -1,0 +1,134 @@
+/*
+ * hiecoattn_b200 -- C ABI of the B200-native Hierarchical Co-Attention hot path.
+ *
+ * The reference (Axe--/Visual-Question-Answering) has no native code: its hot path is the ATen calls
+ * issued by four nn.Modules in model.py.  This header is therefore the boundary a maintainer of the
+ * reference would bind (ctypes stub in INTEGRATION.md); each entry point names the reference code it
+ * replaces.  The Python package visual-question-answering_b200 wraps these as torch.library custom
+ * ops (namespace "hiecoattn") behind modules with the reference's names and signatures.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the current CUDA device
+ *     unless stated otherwise; all matrices are dense row-major fp32 unless stated otherwise.
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the host, nothing runs on the
+ *     legacy default stream unless that is the stream passed in; safe under CUDA-graph capture.
+ *   - the library allocates nothing per call: outputs, saved tensors and scratch (`ws`, sized by the
+ *     matching *_workspace query, 256-byte aligned) are owned by the caller.
+ *   - return value 0 = ok; non-zero = error, message via hca_last_error() (thread-local).  Never
+ *     throws, never exits.
+ *   - there is NO CPU implementation behind this ABI.
+ */
+#ifndef HIECOATTN_B200_H_
+#define HIECOATTN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HCA_API __attribute__((visibility("default")))
+#else
+#define HCA_API
+#endif
+
+/* error codes */
+#define HCA_OK 0
+#define HCA_ERR_ARG 1      /* bad shape / null pointer / unsupported size */
+#define HCA_ERR_CUDA 2     /* CUDA runtime / driver error */
+#define HCA_ERR_WORKSPACE 3 /* workspace too small */
+
+HCA_API int hca_abi_version(void);
+HCA_API const char* hca_last_error(void);
+/* number of CUDA kernels this library has launched from the calling process so far (bench.py's
+ * gpu_launches is the difference across the timed region) */
+HCA_API int64_t hca_launch_count(void);
+/* runtime switches: name in {"gemm"}; value "tc" (tcgen05 tensor-core path, default on sm_100) or
+ * "ffma" (plain fp32 CUDA-core path, the bring-up / cross-check path).  Returns 0 or HCA_ERR_ARG. */
+HCA_API int hca_set_option(const char* name, const char* value);
+HCA_API const char* hca_get_option(const char* name);
+
+/* ---- question encoder: embedding gather (replaces nn.Embedding, model.py:263,282) -------------- */
+/* out[r,:] = table[tokens[r],:] for r < rows; tokens int64 in [0,vocab).  E % 4 == 0. */
+HCA_API int hca_embedding_fwd(const int64_t* tokens, const float* table, float* out,
+                      int64_t rows, int E, int64_t vocab, void* stream);
+/* dtable (pre-zeroed by this call) += scatter of dout rows; row 0 (padding_idx) stays zero. */
+HCA_API int hca_embedding_bwd(const int64_t* tokens, const float* dout, float* dtable,
+                      int64_t rows, int E, int64_t vocab, void* stream);
+
+/* ---- PhraseConvPool (replaces model.py:304-334) ------------------------------------------------ */
+/* x [B,T,E]; w{1,2,3} = Conv1d weights [E,E,k] (k=1,2,3), b{1,2,3} [E];
+ * lens: optional int64 [B] (device); when non-null rows t >= lens[b] of `out` are zeroed (the
+ * pack/pad step of model.py:287-292) and idx there is 0.
+ * out [B,T,E]; idx [B,T,E] uint8 = position (0..2) inside the consecutive channel triple of
+ * [uni|bi|tri] that attained the max, first index on ties (MaxPool2d((1,3)), model.py:311,329-332). */
+HCA_API size_t hca_phrase_conv_pool_workspace(int B, int T, int E);
+HCA_API int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const float* b1, const float* w2,
+                             const float* b2, const float* w3, const float* b3, const int64_t* lens,
+                             float* out, uint8_t* idx, int B, int T, int E,
+                             void* ws, size_t ws_bytes, void* stream);
+/* gradients of the above given dout [B,T,E]; dx may be null (input does not need grad). */
+HCA_API int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const float* w2, const float* w3,
+                             const float* out, const uint8_t* idx, const float* dout, const int64_t* lens,
+                             float* dx, float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3,
+                             int B, int T, int E, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- ParallelCoAttention, all three levels (replaces model.py:356-397) -------------------------- */
+/* V [B,N,d] with ELEMENT strides (v_sb, v_sn, v_sd) -- the reference hands a permuted VGG view
+ * (model.py:217); q0,q1,q2 = word / phrase / sentence features, each dense [B,T,d];
+ * Wv,Wq [d,d] (nn.Linear layout [out,in]), bv,bq [d], wv,wq [d], cv,cq device scalars [1].
+ * W_b is declared by the reference (model.py:347) but never used (model.py:377): it is not an input.
+ * outputs: vhat [3,B,d], qhat [3,B,d];
+ * saved for backward: PV [B,N,d], PQ [3,B,T,d], C [3,B,T,N], av [3,B,N], aq [3,B,T]. */
+HCA_API size_t hca_coattn_workspace(int B, int N, int T, int d, int need_dv);
+HCA_API int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_t v_sd,
+                   const float* q0, const float* q1, const float* q2,
+                   const float* Wv, const float* bv, const float* Wq, const float* bq,
+                   const float* wv, const float* cv, const float* wq, const float* cq,
+                   float* vhat, float* qhat, float* PV, float* PQ, float* C, float* av, float* aq,
+                   int B, int N, int T, int d, void* ws, size_t ws_bytes, void* stream);
+/* gvhat,gqhat [3,B,d] = dL/dvhat, dL/dqhat.  Outputs: dQ [3,B,T,d]; dWv,dWq [d,d]; dbv,dbq,dwv,dwq [d];
+ * dcv,dcq [1]; dV [B,N,d] dense or null when the image features need no gradient (frozen VGG,
+ * main.py:67).  Weight gradients are summed over batch and levels. */
+HCA_API int hca_coattn_bwd(const float* V, int64_t v_sb, int64_t v_sn, int64_t v_sd,
+                   const float* q0, const float* q1, const float* q2,
+                   const float* Wv, const float* Wq, const float* wv, const float* wq,
+                   const float* PV, const float* PQ, const float* C, const float* av, const float* aq,
+                   const float* gvhat, const float* gqhat,
+                   float* dV, float* dQ, float* dWv, float* dbv, float* dWq, float* dbq,
+                   float* dwv, float* dcv, float* dwq, float* dcq,
+                   int B, int N, int T, int d, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- MLPClassifier (replaces model.py:414-434) -------------------------------------------------- */
+/* vhat,qhat [3,B,d] (levels word, phrase, sentence); Ww [d,d], Wp [d,2d], Ws [mlp,2d], Wh [K,mlp].
+ * outputs: logits [B,K]; saved: xw [B,d], xp [B,2d] (= [q_p+v_p | h_w]), xs [B,2d] (= [q_s+v_s | h_p]),
+ * hs [B,mlp]. */
+HCA_API size_t hca_mlp_workspace(int B, int d, int mlp, int K);
+HCA_API int hca_mlp_fwd(const float* vhat, const float* qhat,
+                const float* Ww, const float* bw, const float* Wp, const float* bp,
+                const float* Ws, const float* bs, const float* Wh, const float* bh,
+                float* logits, float* xw, float* xp, float* xs, float* hs,
+                int B, int d, int mlp, int K, void* ws, size_t ws_bytes, void* stream);
+/* dlogits [B,K] -> g [3,B,d] (gradient of BOTH vhat and qhat of each level: they enter as q+v),
+ * and all weight / bias gradients. */
+HCA_API int hca_mlp_bwd(const float* dlogits, const float* Ww, const float* Wp, const float* Ws, const float* Wh,
+                const float* xw, const float* xp, const float* xs, const float* hs,
+                float* g, float* dWw, float* dbw, float* dWp, float* dbp, float* dWs, float* dbs,
+                float* dWh, float* dbh, int B, int d, int mlp, int K,
+                void* ws, size_t ws_bytes, void* stream);
+
+/* ---- building block exposed for tests and profiling: D[M,N] = A[M,K] . B[N,K]^T (+bias[N]) -------- */
+/* dense row-major fp32 in and out; `path` 0 = fp32 CUDA cores, 1 = tcgen05 with bf16x2 operand
+ * splitting (3 MMAs, ~2^-16 operand precision), 2 = tcgen05 bf16x3 (6 MMAs, fp32-grade). */
+HCA_API size_t hca_gemm_nt_workspace(int M, int N, int K, int path);
+HCA_API int hca_gemm_nt(const float* A, const float* B, const float* bias, float* D, int M, int N, int K,
+                int path, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIECOATTN_B200_H_ */

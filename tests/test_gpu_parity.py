@@ -1,0 +1,272 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI / custom ops / modules) against the numpy oracle
+and against the golden fixtures generated from the reference.  north_star tolerances: logits and
+gradients within 1e-3 relative, phrase max-pool indices bit exact (near-tie protocol of SURVEY H1b),
+argmax agreement >= 99.9 %."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import GOLDEN  # noqa: E402
+
+
+def _h():
+    import gpu_harness
+    return gpu_harness
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def test_library_loaded_and_cuda_only():
+    h = _h()
+    assert h.PKG._lib.lib().hca_abi_version() == 1
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        h.PKG.ops.embedding(torch.zeros(2, 3, dtype=torch.long), torch.zeros(4, 8))     # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("name", ["small_a", "small_b", "small_c"])
+def test_small_golden_full_step(name):
+    """CUDA path vs the reference's own fp64 outputs (tests/golden, from oracle/make_golden.py)."""
+    h = _h()
+    g = load_golden(name)
+    c = {k[4:]: g[k].item() for k in g if k.startswith("cfg.")}
+    p = {k[2:]: v for k, v in g.items() if k.startswith("p.")}
+    x = {k[2:]: v for k, v in g.items() if k.startswith("x.")}
+    net = h.build_net(p, c["d"], c["vocab"], c["K"], c["mlp_dim"])
+    ours = h.run_ours(net, x, feats_grad=True)
+    ref = dict(logits=g["f64.logits"], loss=g["f64.loss"], dfeats=g["f64.dfeats"],
+               grads={k[len("f64.grad."):]: v for k, v in g.items() if k.startswith("f64.grad.")})
+    errs = h.compare(ours, ref, tol=1e-3, check_dfeats=True)
+    for key in ("word", "phrase", "sent", "vhat", "qhat"):
+        assert h.rel(ours[key], g[f"f64.{key}"]) < 1e-4, key
+    print(name, {k: f"{v:.1e}" for k, v in errs.items()})
+
+
+@pytest.mark.parametrize("name", ["small_a", "small_b"])
+def test_phrase_conv_pool_module_and_indices(name):
+    h = _h()
+    g = load_golden(name)
+    c = {k[4:]: g[k].item() for k in g if k.startswith("cfg.")}
+    p = {k[2:]: v for k, v in g.items() if k.startswith("p.")}
+    net = h.build_net(p, c["d"], c["vocab"], c["K"], c["mlp_dim"])
+    word = torch.from_numpy(g["f64.word"].astype(np.float32)).cuda()
+    with torch.no_grad():
+        out, idx = net.question_encoder.phrase_conv_pool(word, None, return_indices=True)
+    assert h.rel(out.cpu().numpy(), g["f64.phrase_raw"]) < 1e-5
+    assert np.array_equal(idx.cpu().numpy(), g["idx"])          # bit exact
+
+
+def _near_tie_ok(p, x, idx_ours, orc, atol=4e-6):
+    """Index mismatches are tolerated only where the oracle's fp64 top-2 gap (of the tanh outputs) is within a
+    few fp32 ulps; returns (#mismatch, #mismatch outside the tie band)."""
+    import hiecoattn_oracle as O
+    bad = np.argwhere(idx_ours != orc["idx"])
+    if len(bad) == 0:
+        return 0, 0
+    c = orc["cache"]
+    w = [np.asarray(v, np.float64) for v in c["conv_w"]]
+    cat = np.tanh(O.phrase_conv_preact(np.asarray(c["word"], np.float64), *w))
+    B, T, E3 = cat.shape
+    grp = np.sort(cat.reshape(B, T, E3 // 3, 3), axis=3)
+    gap = grp[..., 2] - grp[..., 1]
+    valid = O.valid_mask(x["lens"], T)
+    outside = 0
+    for b, t, e in bad:
+        if not valid[b, t]:
+            outside += 1           # masked rows must report idx 0 on both sides
+        elif gap[b, t, e] > atol:
+            outside += 1
+    return len(bad), outside
+
+
+@pytest.mark.parametrize("B,dist,seed", [(8, "D1", 1), (6, "D2", 5), (1, "D1", 7)])
+def test_real_widths_full_step(B, dist, seed, syn):
+    """d=512, N=196, T=26, K=1001: logits + every gradient vs the fp64 oracle; pool indices bit exact."""
+    h = _h()
+    d, N, T, vocab, K, mlp = 512, 196, 26, 10000, 1001, 1024
+    p = syn.make_params(d, vocab, K, mlp, seed=0)
+    x = syn.make_inputs(B, N, T, d, vocab, K, seed=seed, dist=dist, min_len=1)
+    net = h.build_net(p, d, vocab, K, mlp)
+    ours = h.run_ours(net, x, feats_grad=True, lens_on="both")
+    orc = h.run_oracle(p, x, np.float64, need_dfeats=True)
+    errs = h.compare(ours, orc, tol=1e-3, check_dfeats=True)
+    print(f"B={B} {dist}", {k.split('.')[-2] + '.' + k.split('.')[-1] if '.' in k else k: f"{v:.1e}" for k, v in errs.items()})
+    with torch.no_grad():
+        word = torch.from_numpy(np.asarray(orc["cache"]["word"], np.float32)).cuda()
+        lens_dev = torch.from_numpy(x["lens"]).cuda()
+        _, idx = net.question_encoder.phrase_conv_pool(word, lens_dev, return_indices=True)
+    idx = idx.cpu().numpy()
+    orc_idx = np.where(h.O.valid_mask(x["lens"], T)[..., None], orc["idx"], 0)
+    nbad, outside = _near_tie_ok(p, x, idx, dict(orc, idx=orc_idx))
+    print("pool index mismatches:", nbad, "outside tie band:", outside)
+    assert outside == 0 and nbad <= 2
+
+
+@pytest.mark.parametrize("name", ["d512_D1", "d512_D2"])
+def test_real_widths_against_reference_golden(name, syn):
+    """Same widths, but against digests of the reference's own run (not the oracle)."""
+    h = _h()
+    g = load_golden(name)
+    c = {k[4:]: g[k].item() for k in g if k.startswith("cfg.")}
+    p = syn.make_params(c["d"], c["vocab"], c["K"], c["mlp_dim"], seed=0)
+    x = syn.make_inputs(c["B"], c["N"], c["T"], c["d"], c["vocab"], c["K"], seed=c["seed"], dist=str(c["dist"]), min_len=c["min_len"])
+    net = h.build_net(p, c["d"], c["vocab"], c["K"], c["mlp_dim"])
+    ours = h.run_ours(net, x, feats_grad=True)
+    assert h.rel(ours["logits"], g["f64.logits"]) < 1e-3
+    assert (ours["logits"].argmax(1) == g["f64.logits"].argmax(1)).all()
+    assert h.rel(ours["vhat"], g["f64.vhat"]) < 1e-3 and h.rel(ours["qhat"], g["f64.qhat"]) < 1e-3
+
+    def digest(a):
+        a = np.asarray(a, np.float64).reshape(-1)
+        stride = max(1, a.size // 64)
+        return np.concatenate([[np.sqrt((a * a).sum())], a[::stride][:64]])
+
+    for k, v in ours["grads"].items():
+        ref = g[f"f64.grad.{k}.digest"][1:]
+        if k in h.ZERO_BIASES:
+            continue
+        assert h.rel(digest(v)[:1], ref[:1]) < 1e-3, k             # gradient norm
+        assert np.linalg.norm(digest(v)[1:] - ref[1:]) <= 2e-3 * max(np.linalg.norm(ref[1:]), 1e-30) + 1e-9, k
+
+
+def test_edge_shapes_large_grid_long_question(syn):
+    """N=576 (24x24 grid), T=64, K=3001 (odd K: rows not 16-byte aligned), B=3."""
+    h = _h()
+    d, N, T, vocab, K, mlp = 512, 576, 64, 500, 3001, 1024
+    p = syn.make_params(d, vocab, K, mlp, seed=3)
+    x = syn.make_inputs(3, N, T, d, vocab, K, seed=11, dist="D2", min_len=1)
+    net = h.build_net(p, d, vocab, K, mlp)
+    ours = h.run_ours(net, x, feats_grad=False, lens_on="cuda")
+    orc = h.run_oracle(p, x, np.float64)
+    h.compare(ours, orc, tol=1e-3)
+
+
+def test_len_one_and_len_T(syn):
+    h = _h()
+    d, N, T, vocab, K, mlp = 64, 7, 5, 50, 9, 32
+    p = syn.make_params(d, vocab, K, mlp, seed=4)
+    x = syn.make_inputs(4, N, T, d, vocab, K, seed=2, min_len=1)
+    x["lens"][:] = [T, T, 1, 1]
+    x["tokens"][2:, 1:] = 0
+    x["tokens"][:2] = np.maximum(x["tokens"][:2], 1)
+    net = h.build_net(p, d, vocab, K, mlp)
+    ours = h.run_ours(net, x, feats_grad=True)
+    orc = h.run_oracle(p, x, np.float64, need_dfeats=True)
+    h.compare(ours, orc, tol=1e-3, check_dfeats=True)
+    # embedding row 0 (padding_idx) gets exactly zero gradient (model.py:263)
+    assert np.abs(ours["grads"]["question_encoder.word_embedding.weight"][0]).max() == 0.0
+    # pad rows are exactly zero at all three levels
+    m = ~h.O.valid_mask(x["lens"], T)
+    for key in ("word", "phrase", "sent"):
+        assert np.abs(ours[key][m]).max() == 0.0
+
+
+def test_permuted_feature_view_and_lens_devices(syn):
+    """x_img arrives as a non-contiguous [B,N,d] view (model.py:217); lens on CPU, on CUDA, or both."""
+    h = _h()
+    d, N, T, vocab, K, mlp = 128, 49, 9, 80, 21, 64
+    p = syn.make_params(d, vocab, K, mlp, seed=5)
+    x = syn.make_inputs(5, N, T, d, vocab, K, seed=3, min_len=1)
+    net = h.build_net(p, d, vocab, K, mlp)
+    orc = h.run_oracle(p, x, np.float64, need_dfeats=True)
+    for lens_on in ("cpu", "cuda", "both"):
+        ours = h.run_ours(net, x, feats_grad=True, lens_on=lens_on, feats_view="permuted")
+        h.compare(ours, orc, tol=1e-3, check_dfeats=True)
+
+
+def test_misuse_raises_like_the_reference(syn):
+    h = _h()
+    d, N, T, vocab, K, mlp = 64, 7, 5, 50, 9, 32
+    net = h.build_net(syn.make_params(d, vocab, K, mlp), d, vocab, K, mlp)
+    tokens = torch.ones(3, T, dtype=torch.long, device="cuda")
+    with pytest.raises(RuntimeError):
+        net.question_encoder(tokens, torch.tensor([2, 5, 3]))          # unsorted lengths (utils.py:33-45)
+    with pytest.raises(RuntimeError):
+        net.question_encoder(tokens, torch.tensor([3, 2, 0]))          # zero length
+
+
+def test_eval_no_grad_forward_matches_training_forward(syn):
+    """Validation path (main.py:301-327): eval() + no_grad(), no autograd graph."""
+    h = _h()
+    d, N, T, vocab, K, mlp = 512, 196, 26, 1000, 1001, 1024
+    p = syn.make_params(d, vocab, K, mlp, seed=0)
+    x = syn.make_inputs(16, N, T, d, vocab, K, seed=9)
+    net = h.build_net(p, d, vocab, K, mlp).eval()
+    feats = torch.from_numpy(x["feats"]).cuda()
+    tokens = torch.from_numpy(x["tokens"]).cuda()
+    lens = torch.from_numpy(x["lens"])
+    with torch.no_grad():
+        a = net(feats, tokens, lens)
+    b = net(feats, tokens, lens)
+    assert not a.requires_grad and b.requires_grad
+    assert torch.equal(a, b.detach())
+    import hiecoattn_oracle as O
+    ref = O.hiecoattn_forward({k: v.astype(np.float64) for k, v in p.items()}, x["feats"].astype(np.float64), x["tokens"], x["lens"])
+    assert h.rel(a.cpu().numpy(), ref) < 1e-3
+    assert (a.argmax(1).cpu().numpy() == ref.argmax(1)).all()
+
+
+def test_module_list_api_matches_reference_signatures(syn):
+    """ParallelCoAttention / MLPClassifier called the way the reference wrapper calls them (model.py:182-185)."""
+    h = _h()
+    d, N, T, vocab, K, mlp = 64, 12, 6, 50, 9, 32
+    p = syn.make_params(d, vocab, K, mlp, seed=6)
+    x = syn.make_inputs(4, N, T, d, vocab, K, seed=4, min_len=1)
+    net = h.build_net(p, d, vocab, K, mlp)
+    feats = torch.from_numpy(x["feats"]).cuda()
+    hier = net.question_encoder(torch.from_numpy(x["tokens"]).cuda(), torch.from_numpy(x["lens"]))
+    img_l, q_l = net.co_attention(feats, list(hier))
+    assert isinstance(img_l, list) and len(img_l) == 3 and img_l[0].shape == (4, d)
+    logits = net.mlp_classify(img_l, q_l)
+    logits.sum().backward()
+    ref = h.O.hiecoattn_forward({k: v.astype(np.float64) for k, v in p.items()}, x["feats"].astype(np.float64), x["tokens"], x["lens"])
+    assert h.rel(logits.detach().cpu().numpy(), ref) < 1e-3
+    assert net.co_attention.W_b.weight.grad is None and net.co_attention.W_v.weight.grad is not None
+
+
+def test_headline_batch_properties(syn):
+    """B=160 (BASELINE config 3): size-independent properties + argmax agreement with the fp32 oracle forward."""
+    h = _h()
+    d, N, T, vocab, K, mlp = 512, 196, 26, 10000, 1001, 1024
+    p = syn.make_params(d, vocab, K, mlp, seed=0)
+    x = syn.make_inputs(160, N, T, d, vocab, K, seed=1)
+    net = h.build_net(p, d, vocab, K, mlp)
+    ours = h.run_ours(net, x, lens_on="both")
+    assert np.isfinite(ours["logits"]).all() and all(np.isfinite(g).all() for g in ours["grads"].values())
+    # batch independence: the first 8 samples alone give the same logits (no cross-sample op in the path)
+    x8 = {k: v[:8] for k, v in x.items()}
+    ours8 = h.run_ours(net, x8, lens_on="both")
+    assert h.rel(ours8["logits"], ours["logits"][:8]) < 1e-5
+    # attention weights are a softmax: attended features are convex combinations of the rows
+    f = x["feats"]
+    assert (ours["vhat"] <= f.max(1)[None] + 1e-4).all() and (ours["vhat"] >= f.min(1)[None] - 1e-4).all()
+    ref = h.O.hiecoattn_forward({k: v.astype(np.float64) for k, v in p.items()}, x["feats"].astype(np.float64), x["tokens"], x["lens"])
+    assert h.rel(ours["logits"], ref) < 1e-3
+    agree = (ours["logits"].argmax(1) == ref.argmax(1)).mean()
+    print("argmax agreement", agree)
+    assert agree >= 0.999
+
+
+def test_opcheck_schemas():
+    """torch.library hygiene: schema, fake kernels and autograd registration of every custom op."""
+    h = _h()
+    ops = h.PKG.ops
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev)
+    B, N, T, d, K, m = 2, 5, 4, 32, 7, 16
+    tokens = torch.randint(0, 10, (B, T), generator=g).to(dev)
+    kinds = ("test_schema", "test_faketensor", "test_autograd_registration")
+    torch.library.opcheck(ops.embedding, (tokens, r(10, d).requires_grad_()), test_utils=kinds)
+    conv = [r(d, d, 1), r(d), r(d, d, 2), r(d), r(d, d, 3), r(d)]
+    torch.library.opcheck(ops.phrase_conv_pool, (r(B, T, d).requires_grad_(), *[c.requires_grad_() for c in conv], None), test_utils=kinds)
+    ca = [r(B, N, d), r(B, T, d).requires_grad_(), r(B, T, d), r(B, T, d), r(d, d).requires_grad_(), r(d), r(d, d), r(d), r(1, d), r(1), r(1, d), r(1)]
+    torch.library.opcheck(ops.coattn, tuple(ca), test_utils=kinds)
+    ml = [r(3, B, d).requires_grad_(), r(3, B, d), r(d, d), r(d), r(d, 2 * d), r(d), r(m, 2 * d), r(m), r(K, m).requires_grad_(), r(K)]
+    torch.library.opcheck(ops.mlp, tuple(ml), test_utils=kinds)

@@ -1,0 +1,86 @@
+// Shared helpers for the hiecoattn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <atomic>
+
+#include "../../include/hiecoattn_b200.h"
+
+namespace hca {
+
+// ---- error plumbing (thread-local message, C ABI never throws) -------------------------------------
+char* err_buf();
+int set_err(int code, const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define HCA_CHECK_ARG(cond, ...)                                    \
+  do {                                                              \
+    if (!(cond)) return ::hca::set_err(HCA_ERR_ARG, __VA_ARGS__);   \
+  } while (0)
+
+#define HCA_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return ::hca::set_err(HCA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                              \
+  } while (0)
+
+// call right after a <<<>>> launch
+#define HCA_LAUNCHED()                                                                         \
+  do {                                                                                         \
+    ::hca::g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
+    cudaError_t _e = cudaPeekAtLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                   \
+      cudaGetLastError();                                                                      \
+      return ::hca::set_err(HCA_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                  \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+    }                                                                                          \
+  } while (0)
+
+#define HCA_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+// grid size for grid-stride elementwise kernels: enough blocks to fill 148 SMs a few times over
+static inline int ew_grid(int64_t total) {
+  const int64_t g = (total + 255) / 256;
+  return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+// bump allocator over the caller's workspace
+struct Workspace {
+  char* base;
+  size_t cap, off;
+  Workspace(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0) {}
+  template <class T>
+  T* take(size_t n) {
+    size_t b = align_up(n * sizeof(T));
+    if (off + b > cap) return nullptr;
+    T* r = (T*)(base + off);
+    off += b;
+    return r;
+  }
+};
+
+// ---- device helpers ----------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// options
+bool use_tc();
+
+}  // namespace hca

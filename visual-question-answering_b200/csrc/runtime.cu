@@ -1,0 +1,57 @@
+// Error plumbing, launch counter and runtime options of the C ABI (include/hiecoattn_b200.h).
+#include "common.cuh"
+#include <cstring>
+#include <cstdlib>
+
+namespace hca {
+
+std::atomic<int64_t> g_launches{0};
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static std::atomic<int> g_gemm_mode{-1};  // -1 unset, 0 ffma, 1 tc
+
+bool use_tc() {
+  int m = g_gemm_mode.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("HCA_GEMM");
+    m = (e && strcmp(e, "ffma") == 0) ? 0 : 1;
+    g_gemm_mode.store(m);
+  }
+  return m == 1;
+}
+
+}  // namespace hca
+
+extern "C" {
+
+int hca_abi_version(void) { return HCA_ABI_VERSION; }
+const char* hca_last_error(void) { return hca::err_buf(); }
+int64_t hca_launch_count(void) { return hca::g_launches.load(); }
+
+int hca_set_option(const char* name, const char* value) {
+  if (!name || !value) return hca::set_err(HCA_ERR_ARG, "hca_set_option: null argument");
+  if (strcmp(name, "gemm") == 0) {
+    if (strcmp(value, "tc") == 0) { hca::g_gemm_mode.store(1); return 0; }
+    if (strcmp(value, "ffma") == 0) { hca::g_gemm_mode.store(0); return 0; }
+  }
+  return hca::set_err(HCA_ERR_ARG, "hca_set_option: unknown option %s=%s", name, value);
+}
+
+const char* hca_get_option(const char* name) {
+  if (name && strcmp(name, "gemm") == 0) return hca::use_tc() ? "tc" : "ffma";
+  return "";
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+"""Batch-sharded data parallelism for the co-attention path: one process per GPU, NCCL all-reduce of a
+flat gradient buffer over NVLink 5 / NVSwitch, issued bucket by bucket in reverse-backward order so the
+transfer of the early buckets overlaps the remaining backward.
+
+The reference has no multi-GPU support at all (a commented-out nn.DataParallel TODO, main.py:102-106);
+the path shards over the batch because no op in model.py:246-434 mixes samples -- the only cross-sample
+reductions are the weight-gradient sums and the mean of the loss (main.py:179).
+
+Design:
+  * every participating parameter's ``.grad`` is a VIEW into one flat fp32 buffer, laid out in the order
+    gradients become ready during backward (classifier -> co-attention -> LSTM / conv -> embedding), so
+    there is no gather copy before the collective and no scatter after it;
+  * ``co_attention.W_b`` never receives a gradient (reference model.py:347 vs :377) and frozen VGG weights
+    have ``requires_grad=False``: both are left out of the buffer (``skip`` / requires_grad);
+  * post-accumulate-grad hooks count down each bucket and launch its all-reduce (SUM) as soon as it is
+    complete; the mean over ranks is obtained by scaling the loss by 1/world_size before backward
+    (``loss_scale``), so no extra pass over the buffer is needed;
+  * ``finish()`` waits for the outstanding collectives before the optimizer step.
+Works with any backend torch.distributed offers (NCCL on the GPUs; gloo in the CPU unit tests).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+# parameter-name prefixes in the order their gradients are produced by backward
+BACKWARD_ORDER = ("mlp_classify.", "co_attention.", "question_encoder.sentence_lstm.", "question_encoder.phrase_conv_pool.",
+                  "question_encoder.word_embedding.")
+
+
+def shard_batch(n_items: int, rank: int, world: int) -> slice:
+    """Contiguous shard of a length-sorted global batch: every shard stays sorted (utils.py:33-45)."""
+    per = n_items // world
+    if per * world != n_items:
+        raise ValueError(f"global batch {n_items} is not divisible by world size {world}")
+    return slice(rank * per, (rank + 1) * per)
+
+
+class FlatGradAllReduce:
+    def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], process_group=None,
+                 skip: Sequence[str] = ("co_attention.W_b.",), bucket_bytes: int = 16 << 20, overlap: bool = True):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.loss_scale = 1.0 / self.world
+        self.overlap = overlap
+        items = [(n, p) for n, p in named_params if p.requires_grad and not any(n.startswith(s) for s in skip)]
+
+        def order(item):
+            for i, pre in enumerate(BACKWARD_ORDER):
+                if item[0].startswith(pre):
+                    return i
+            return len(BACKWARD_ORDER)
+
+        items.sort(key=order)                               # stable: keeps definition order inside a group
+        self.names = [n for n, _ in items]
+        self.params = [p for _, p in items]
+        if not self.params:
+            raise ValueError("no parameters to reduce")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=dt, device=dev)
+        # carve views and buckets
+        self.buckets: List[Tuple[int, int]] = []            # [start, end) element ranges of the flat buffer
+        self._bucket_of: List[int] = []
+        off, b_start, limit = 0, 0, max(1, bucket_bytes // self.flat.element_size())
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+            self._bucket_of.append(len(self.buckets))
+            if off - b_start >= limit:
+                self.buckets.append((b_start, off))
+                b_start = off
+        if off > b_start:
+            self.buckets.append((b_start, off))
+        self._bucket_of = [min(b, len(self.buckets) - 1) for b in self._bucket_of]
+        self._need = [0] * len(self.buckets)
+        for b in self._bucket_of:
+            self._need[b] += 1
+        self._left = list(self._need)
+        self._work = []
+        self._hooks = []
+        if self.world > 1 and overlap:
+            for i, p in enumerate(self.params):
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+
+    # ---------------------------------------------------------------------------------------------------
+    def _make_hook(self, i):
+        def hook(_param):
+            b = self._bucket_of[i]
+            self._left[b] -= 1
+            if self._left[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        s, e = self.buckets[b]
+        self._work.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def zero_grad(self):
+        """Clears the flat buffer in place (parameters keep their views) and re-arms the bucket counters."""
+        self.flat.zero_()
+        self._left = list(self._need)
+        self._work = []
+
+    def finish(self):
+        """Call after backward, before optimizer.step(): launches what the hooks did not and waits."""
+        if self.world > 1:
+            if not self.overlap:
+                for b in range(len(self.buckets)):
+                    self._launch(b)
+            else:
+                for b, left in enumerate(self._left):
+                    if left > 0:                            # a parameter received no gradient this step
+                        self._launch(b)
+            for w in self._work:
+                w.wait()
+        self._work = []
+        self._left = list(self._need)
+
+    def grad_bytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()

@@ -1,0 +1,260 @@
+"""nn.Module mirrors of the reference's Hierarchical Co-Attention model (reference model.py:157-434).
+
+Same class names, constructor arguments, ``forward`` signatures, sub-module attribute names and
+``state_dict`` keys as the reference, so ``from model import HierarchicalCoAttentionNet`` in the
+reference's main.py (main.py:15,164) picks these up unchanged and checkpoints interchange
+(main.py:168-176, 260-263).  The arithmetic of the hot path runs in the hand-written sm_100a kernels
+behind the ``hiecoattn::*`` custom ops (ops.py); parameters are held by stock ``nn.Linear`` /
+``nn.Conv1d`` / ``nn.Embedding`` containers only so that names, shapes and default initialisation match.
+
+Out of the hot path and therefore stock PyTorch here: the VGG11-bn trunk (torchvision), the sentence
+``nn.LSTM`` (cuDNN) and the GRU baseline network.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+
+from . import ops
+
+
+class QuestionLens:
+    """Sequence lengths held on both sides of the PCIe bus.
+
+    The reference moves ``ques_len`` to the GPU (main.py:207) and then hands it to
+    ``pack_padded_sequence`` (model.py:287), which needs it on the CPU: a device->host sync per step (and
+    an error on current PyTorch).  Passing a ``QuestionLens`` instead of a tensor gives the encoder both
+    copies up front, so the step stays free of host synchronisation and can be captured in a CUDA graph.
+    A plain tensor (CPU or CUDA) is still accepted everywhere.
+    """
+
+    def __init__(self, lens_cpu: Tensor, device=None, lens_dev: Optional[Tensor] = None):
+        self.cpu = lens_cpu.detach().to("cpu", torch.int64)
+        self.dev = lens_dev if lens_dev is not None else self.cpu.to(device, non_blocking=True)
+
+
+def _f32(t: Tensor) -> Tensor:
+    return t if t.dtype == torch.float32 else t.float()
+
+
+class PhraseConvPool(nn.Module):
+    """Unigram / bigram / trigram Conv1d + tanh, max over consecutive channel triples (model.py:301-334)."""
+
+    def __init__(self, emb_dim):
+        super().__init__()
+        # index 1 inside each Sequential keeps the reference's state_dict keys ("conv_unigram.1.weight", ...)
+        self.conv_unigram = nn.Sequential(nn.ConstantPad1d((0, 0), 0), nn.Conv1d(emb_dim, emb_dim, 1, 1), nn.Tanh())
+        self.conv_bigram = nn.Sequential(nn.ConstantPad1d((1, 0), 0), nn.Conv1d(emb_dim, emb_dim, 2, 1), nn.Tanh())
+        self.conv_trigram = nn.Sequential(nn.ConstantPad1d((1, 1), 0), nn.Conv1d(emb_dim, emb_dim, 3, 1), nn.Tanh())
+        self.max_pool = nn.MaxPool2d(kernel_size=(1, 3))        # parameter-free; kept for attribute parity
+
+    def forward(self, x_question: Tensor, lens_dev: Optional[Tensor] = None, return_indices: bool = False):
+        """x_question [B,T,E] -> [B,T,E].  ``lens_dev`` (optional, int64 on the GPU) zeroes rows t >= len."""
+        u, b, t = self.conv_unigram[1], self.conv_bigram[1], self.conv_trigram[1]
+        out, idx = ops.phrase_conv_pool(_f32(x_question), u.weight, u.bias, b.weight, b.bias, t.weight, t.bias, lens_dev)
+        return (out, idx) if return_indices else out
+
+
+class QuestionCoAttentionEncoder(nn.Module):
+    """Word embedding -> PhraseConvPool -> LSTM; returns (word, phrase, sentence) [B,T,d] (model.py:246-298)."""
+
+    def __init__(self, vocab_size, word_emb_dim, hidden_dim):
+        super().__init__()
+        self.vocab_size = vocab_size
+        self.embedding_dim = word_emb_dim
+        self.hidden_dim = hidden_dim
+        self.word_embedding = nn.Embedding(self.vocab_size, self.embedding_dim, padding_idx=0)
+        self.phrase_conv_pool = PhraseConvPool(self.embedding_dim)
+        self.sentence_lstm = nn.LSTM(self.embedding_dim, self.hidden_dim)
+
+    def forward(self, x: Tensor, x_lens) -> Tuple[Tensor, Tensor, Tensor]:
+        max_seq_len = x.shape[1]
+        if isinstance(x_lens, QuestionLens):
+            lens_cpu, lens_dev = x_lens.cpu, x_lens.dev
+        else:
+            lens_cpu = x_lens.cpu() if x_lens.is_cuda else x_lens          # the one D2H sync the reference also pays
+            lens_dev = x_lens if x_lens.is_cuda else x_lens.to(x.device)
+        x_word_emb = ops.embedding(x, self.word_embedding.weight)                       # model.py:282
+        # phrase level with the pad rows already zeroed (what pack -> pad does at model.py:287,292)
+        x_phrase_emb = self.phrase_conv_pool(x_word_emb, lens_dev)                      # model.py:284
+        packed = pack_padded_sequence(x_phrase_emb, lens_cpu, batch_first=True)         # raises on unsorted / zero lens
+        x_sentence_emb, _ = self.sentence_lstm(packed)                                  # model.py:289
+        x_sentence_emb = pad_packed_sequence(x_sentence_emb, batch_first=True, total_length=max_seq_len)[0]
+        return x_word_emb, x_phrase_emb, x_sentence_emb
+
+
+class ParallelCoAttention(nn.Module):
+    """Parallel co-attention applied at the word, phrase and sentence level (model.py:337-397)."""
+
+    def __init__(self, hidden_dim):
+        super().__init__()
+        self.hidden_dim = hidden_dim
+        self.W_b = nn.Linear(self.hidden_dim, self.hidden_dim)   # declared, never used by the reference (model.py:347,377)
+        self.W_v = nn.Linear(self.hidden_dim, self.hidden_dim)
+        self.W_q = nn.Linear(self.hidden_dim, self.hidden_dim)
+        self.w_v = nn.Linear(self.hidden_dim, 1)
+        self.w_q = nn.Linear(self.hidden_dim, 1)
+
+    def forward_stacked(self, x_img: Tensor, x_ques_hierarchy: Sequence[Tensor]) -> Tuple[Tensor, Tensor]:
+        """-> (vhat [3,B,d], qhat [3,B,d])"""
+        q0, q1, q2 = (_f32(q) for q in x_ques_hierarchy)
+        out = ops.coattn(_f32(x_img), q0, q1, q2, self.W_v.weight, self.W_v.bias, self.W_q.weight, self.W_q.bias,
+                         self.w_v.weight, self.w_v.bias, self.w_q.weight, self.w_q.bias)
+        return out[0], out[1]
+
+    def forward(self, x_img: Tensor, x_ques_hierarchy: Sequence[Tensor]) -> Tuple[List[Tensor], List[Tensor]]:
+        if len(x_ques_hierarchy) != 3:
+            raise ValueError("ParallelCoAttention expects the (word, phrase, sentence) hierarchy: 3 tensors")
+        vhat, qhat = self.forward_stacked(x_img, x_ques_hierarchy)
+        return list(vhat.unbind(0)), list(qhat.unbind(0))
+
+
+class MLPClassifier(nn.Module):
+    """Recursive MLP over the three levels of attended features (model.py:400-434)."""
+
+    def __init__(self, hidden_dim, mlp_dim, K):
+        super().__init__()
+        self.W_w = nn.Linear(hidden_dim, hidden_dim)
+        self.W_p = nn.Linear(2 * hidden_dim, hidden_dim)
+        self.W_s = nn.Linear(2 * hidden_dim, mlp_dim)
+        self.W_h = nn.Linear(mlp_dim, K)
+
+    def forward_stacked(self, vhat: Tensor, qhat: Tensor) -> Tensor:
+        return ops.mlp(vhat, qhat, self.W_w.weight, self.W_w.bias, self.W_p.weight, self.W_p.bias, self.W_s.weight,
+                       self.W_s.bias, self.W_h.weight, self.W_h.bias)[0]
+
+    def forward(self, x_img_feats: Sequence[Tensor], x_ques_feats: Sequence[Tensor]) -> Tensor:
+        vhat = torch.stack([_f32(t) for t in x_img_feats])
+        qhat = torch.stack([_f32(t) for t in x_ques_feats])
+        return self.forward_stacked(vhat, qhat)
+
+
+class ImageCoAttentionEncoder(nn.Module):
+    """VGG11-bn trunk, 448x448 -> [B, 196, 512] (model.py:190-243).  Stock torchvision: out of the hot path."""
+
+    def __init__(self, is_trainable, weights_path):
+        super().__init__()
+        self.is_trainable = is_trainable
+        self.weights_path = weights_path
+        self.vgg11_encoder = self.build_vgg_encoder()
+        self.flatten = nn.Flatten(start_dim=2, end_dim=3)
+
+    def forward(self, x_img):
+        return self.flatten(self.vgg11_encoder(x_img)).permute(0, 2, 1)      # non-contiguous [B, H*W, 512] view
+
+    def build_vgg_encoder(self):
+        import torchvision.models as models
+        vgg11 = models.vgg11_bn(weights=None if self.weights_path else "IMAGENET1K_V1")
+        if self.weights_path:
+            vgg11.load_state_dict(torch.load(self.weights_path))
+        enc = vgg11.features
+        if not self.is_trainable:
+            for p in enc.parameters():
+                p.requires_grad = False
+        return enc
+
+
+class HierarchicalCoAttentionNet(nn.Module):
+    """Drop-in for the reference's ``--model attention`` network (model.py:157-187)."""
+
+    def __init__(self, ques_enc_params, img_enc_params, K, mlp_dim=1024):
+        super().__init__()
+        self.hidden_dim = ques_enc_params["hidden_dim"]
+        self.image_encoder = ImageCoAttentionEncoder(**img_enc_params)
+        self.question_encoder = QuestionCoAttentionEncoder(**ques_enc_params)
+        self.co_attention = ParallelCoAttention(self.hidden_dim)
+        self.mlp_classify = MLPClassifier(self.hidden_dim, mlp_dim, K)
+
+    def forward(self, x_img, x_ques, x_ques_lens):
+        x_word, x_phrase, x_sentence = self.question_encoder(x_ques, x_ques_lens)
+        x_img_features = self.image_encoder(x_img)
+        return self.forward_features(x_img_features, (x_word, x_phrase, x_sentence))
+
+    def forward_features(self, x_img_features, x_ques_features):
+        """Co-attention + classifier on precomputed [B,N,d] image features (synthetic-feature entry point)."""
+        vhat, qhat = self.co_attention.forward_stacked(x_img_features, x_ques_features)
+        return self.mlp_classify.forward_stacked(vhat, qhat)
+
+
+class HieCoAttnHotPath(nn.Module):
+    """question encoder -> co-attention x3 -> MLP on precomputed image features.
+
+    This is the path BASELINE.json benchmarks (the VGG trunk is bypassed with synthetic 196x512 grids);
+    it shares its three sub-modules' names with HierarchicalCoAttentionNet so state_dicts interchange."""
+
+    def __init__(self, vocab_size=10000, hidden_dim=512, K=1001, mlp_dim=1024):
+        super().__init__()
+        self.question_encoder = QuestionCoAttentionEncoder(vocab_size, hidden_dim, hidden_dim)
+        self.co_attention = ParallelCoAttention(hidden_dim)
+        self.mlp_classify = MLPClassifier(hidden_dim, mlp_dim, K)
+
+    def forward(self, x_img_features, x_ques, x_ques_lens):
+        hier = self.question_encoder(x_ques, x_ques_lens)
+        vhat, qhat = self.co_attention.forward_stacked(x_img_features, hier)
+        return self.mlp_classify.forward_stacked(vhat, qhat)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Baseline network (reference model.py:10-151).  Not on the accelerated path (BASELINE.json config 2 only
+# times it for context); stock PyTorch layers with the reference's names so `from model import VQABaselineNet`
+# keeps working.
+
+
+class ImageBaselineEncoder(nn.Module):
+    def __init__(self, is_trainable, weights_path):
+        super().__init__()
+        self.is_trainable = is_trainable
+        self.weights_path = weights_path
+        self.vgg11_encoder = self.build_vgg_encoder()
+        self.embedding_layer = nn.Sequential(nn.Linear(4096, 1024), nn.Tanh())
+
+    def build_vgg_encoder(self):
+        import torchvision.models as models
+        vgg11 = models.vgg11_bn(weights=None if self.weights_path else "IMAGENET1K_V1")
+        if self.weights_path:
+            vgg11.load_state_dict(torch.load(self.weights_path))
+        fc = nn.Sequential(nn.Flatten(), *list(vgg11.classifier)[:-1])
+        enc = nn.Sequential(OrderedDict(conv_layers=vgg11.features, avgpool=vgg11.avgpool, fc_layers=fc))
+        if not self.is_trainable:
+            for p in enc.parameters():
+                p.requires_grad = False
+        return enc
+
+    def forward(self, x_img):
+        return self.embedding_layer(F.normalize(self.vgg11_encoder(x_img), dim=1, p=2))
+
+
+class QuestionBaselineEncoder(nn.Module):
+    def __init__(self, vocab_size, word_emb_dim, hidden_dim):
+        super().__init__()
+        self.hidden_dim, self.vocab_size, self.word_emb_dim = hidden_dim, vocab_size, word_emb_dim
+        self.word_embedding = nn.Sequential(nn.Embedding(vocab_size, word_emb_dim), nn.Tanh())
+        self.gru = nn.GRU(word_emb_dim, hidden_dim)
+        self.embedding_layer = nn.Sequential(nn.Linear(hidden_dim, 1024), nn.Tanh())
+
+    def forward(self, x, seq_lengths):
+        if isinstance(seq_lengths, QuestionLens):
+            seq_lengths = seq_lengths.cpu
+        elif seq_lengths.is_cuda:
+            seq_lengths = seq_lengths.cpu()
+        packed = pack_padded_sequence(self.word_embedding(x), seq_lengths, batch_first=True)
+        _, hidden = self.gru(packed)
+        return self.embedding_layer(hidden.squeeze(0))
+
+
+class VQABaselineNet(nn.Module):
+    def __init__(self, ques_enc_params, img_enc_params, K):
+        super().__init__()
+        self.image_encoder = ImageBaselineEncoder(**img_enc_params)
+        self.question_encoder = QuestionBaselineEncoder(**ques_enc_params)
+        self.mlp = nn.Sequential(nn.Linear(1024, 1000), nn.Dropout(0.5), nn.Tanh())
+        self.fc_final = nn.Linear(1000, K)
+
+    def forward(self, x_img, x_ques, x_ques_len):
+        return self.fc_final(self.mlp(self.image_encoder(x_img) * self.question_encoder(x_ques, x_ques_len)))

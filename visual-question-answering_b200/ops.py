@@ -1,0 +1,348 @@
+"""torch.library custom ops (namespace ``hiecoattn``) over the C ABI of libhiecoattn_b200.so.
+
+Each op is functional (no hidden mutation), has a fake kernel for shape inference, an autograd formula
+that calls the matching ``*_bwd`` op, and works under ``no_grad``.  All ops are CUDA-only: there is no
+CPU kernel behind them (a CPU tensor raises).  Tensors are fp32 at this boundary; callers that run
+under autocast hand in fp16/bf16 and are upcast by the module wrappers (modules.py).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+NS = "hiecoattn"
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda_f32(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("hiecoattn_b200 ops run on CUDA only (no CPU fallback); got a CPU tensor")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"hiecoattn_b200 ops take float32 tensors; got {t.dtype}")
+
+
+def _c(t: Tensor) -> Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ws(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------ embedding
+@torch.library.custom_op(f"{NS}::embedding", mutates_args=(), device_types="cuda")
+def embedding(tokens: Tensor, table: Tensor) -> Tensor:
+    """nn.Embedding(padding_idx=0) forward (reference model.py:263,282)."""
+    _cuda_f32(table)
+    tokens, table = _c(tokens), _c(table)
+    assert tokens.dtype == torch.int64
+    out = torch.empty(*tokens.shape, table.shape[1], dtype=torch.float32, device=table.device)
+    with torch.cuda.device(table.device):
+        _lib.check(_lib.lib().hca_embedding_fwd(_ptr(tokens), _ptr(table), _ptr(out), tokens.numel(), table.shape[1],
+                                                table.shape[0], _stream()), "embedding_fwd")
+    return out
+
+
+@embedding.register_fake
+def _(tokens, table):
+    return table.new_empty(*tokens.shape, table.shape[1])
+
+
+@torch.library.custom_op(f"{NS}::embedding_bwd", mutates_args=(), device_types="cuda")
+def embedding_bwd(tokens: Tensor, dout: Tensor, vocab: int) -> Tensor:
+    _cuda_f32(dout)
+    tokens, dout = _c(tokens), _c(dout)
+    E = dout.shape[-1]
+    dtable = torch.empty(vocab, E, dtype=torch.float32, device=dout.device)
+    with torch.cuda.device(dout.device):
+        _lib.check(_lib.lib().hca_embedding_bwd(_ptr(tokens), _ptr(dout), _ptr(dtable), tokens.numel(), E, vocab, _stream()),
+                   "embedding_bwd")
+    return dtable
+
+
+@embedding_bwd.register_fake
+def _(tokens, dout, vocab):
+    return dout.new_empty(vocab, dout.shape[-1])
+
+
+def _embedding_setup(ctx, inputs, output):
+    tokens, table = inputs
+    ctx.save_for_backward(tokens)
+    ctx.vocab = table.shape[0]
+
+
+def _embedding_backward(ctx, dout):
+    (tokens,) = ctx.saved_tensors
+    return None, embedding_bwd(tokens, dout, ctx.vocab)
+
+
+embedding.register_autograd(_embedding_backward, setup_context=_embedding_setup)
+
+
+# ------------------------------------------------------------------------------------------ phrase conv + pool
+@torch.library.custom_op(f"{NS}::phrase_conv_pool", mutates_args=(), device_types="cuda")
+def phrase_conv_pool(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, w3: Tensor, b3: Tensor,
+                     lens: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """PhraseConvPool forward (reference model.py:313-334) -> (out [B,T,E], idx uint8 [B,T,E]).
+
+    ``lens`` (int64, CUDA, optional) additionally zeroes rows t >= len (model.py:287-292)."""
+    _cuda_f32(x, w1, b1, w2, b2, w3, b3)
+    x, w1, b1, w2, b2, w3, b3 = map(_c, (x, w1, b1, w2, b2, w3, b3))
+    B, T, E = x.shape
+    out = torch.empty_like(x)
+    idx = torch.empty(B, T, E, dtype=torch.uint8, device=x.device)
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        nb = L.hca_phrase_conv_pool_workspace(B, T, E)
+        ws = _ws(nb, x.device)
+        _lib.check(L.hca_phrase_conv_pool_fwd(_ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(w3), _ptr(b3),
+                                              _ptr(None if lens is None else _c(lens)), _ptr(out), _ptr(idx), B, T, E,
+                                              _ptr(ws), ws.numel(), _stream()), "phrase_conv_pool_fwd")
+    return out, idx
+
+
+@phrase_conv_pool.register_fake
+def _(x, w1, b1, w2, b2, w3, b3, lens):
+    return torch.empty_like(x), x.new_empty(x.shape, dtype=torch.uint8)
+
+
+@torch.library.custom_op(f"{NS}::phrase_conv_pool_bwd", mutates_args=(), device_types="cuda")
+def phrase_conv_pool_bwd(x: Tensor, w1: Tensor, w2: Tensor, w3: Tensor, out: Tensor, idx: Tensor, dout: Tensor,
+                         lens: Optional[Tensor], need_dx: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    _cuda_f32(x, w1, w2, w3, out, dout)
+    x, w1, w2, w3, out, idx, dout = map(_c, (x, w1, w2, w3, out, idx, dout))
+    B, T, E = x.shape
+    dx = torch.empty_like(x) if need_dx else x.new_empty(0)
+    dw1, dw2, dw3 = torch.empty_like(w1), torch.empty_like(w2), torch.empty_like(w3)
+    db1, db2, db3 = (x.new_empty(E) for _ in range(3))
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        ws = _ws(L.hca_phrase_conv_pool_workspace(B, T, E), x.device)
+        _lib.check(L.hca_phrase_conv_pool_bwd(_ptr(x), _ptr(w1), _ptr(w2), _ptr(w3), _ptr(out), _ptr(idx), _ptr(dout),
+                                              _ptr(None if lens is None else _c(lens)), _ptr(dx) if need_dx else None,
+                                              _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _ptr(dw3), _ptr(db3), B, T, E,
+                                              _ptr(ws), ws.numel(), _stream()), "phrase_conv_pool_bwd")
+    return dx, dw1, db1, dw2, db2, dw3, db3
+
+
+@phrase_conv_pool_bwd.register_fake
+def _(x, w1, w2, w3, out, idx, dout, lens, need_dx):
+    E = x.shape[-1]
+    return (torch.empty_like(x) if need_dx else x.new_empty(0), torch.empty_like(w1), x.new_empty(E), torch.empty_like(w2),
+            x.new_empty(E), torch.empty_like(w3), x.new_empty(E))
+
+
+def _pcp_setup(ctx, inputs, output):
+    x, w1, b1, w2, b2, w3, b3, lens = inputs
+    out, idx = output
+    ctx.save_for_backward(x, w1, w2, w3, out, idx, lens)
+    ctx.set_materialize_grads(False)
+
+
+def _pcp_backward(ctx, dout, _didx):
+    x, w1, w2, w3, out, idx, lens = ctx.saved_tensors
+    if dout is None:
+        return (None,) * 8
+    need_dx = ctx.needs_input_grad[0]
+    dx, dw1, db1, dw2, db2, dw3, db3 = phrase_conv_pool_bwd(x, w1, w2, w3, out, idx, dout, lens, need_dx)
+    return (dx if need_dx else None), dw1, db1, dw2, db2, dw3, db3, None
+
+
+phrase_conv_pool.register_autograd(_pcp_backward, setup_context=_pcp_setup)
+
+
+# ------------------------------------------------------------------------------------------------ co-attention
+@torch.library.custom_op(f"{NS}::coattn", mutates_args=(), device_types="cuda")
+def coattn(V: Tensor, q0: Tensor, q1: Tensor, q2: Tensor, Wv: Tensor, bv: Tensor, Wq: Tensor, bq: Tensor, wv: Tensor,
+           cv: Tensor, wq: Tensor, cq: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """ParallelCoAttention over the three question levels (reference model.py:356-397).
+
+    Returns (vhat [3,B,d], qhat [3,B,d]) and the tensors saved for backward (PV, PQ, C, av, aq).
+    V may be any strided [B,N,d] view (the reference passes a permuted VGG feature map)."""
+    _cuda_f32(V, q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq)
+    q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq = map(_c, (q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq))
+    B, N, d = V.shape
+    T = q0.shape[1]
+    dev = V.device
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    vhat, qhat = f(3, B, d), f(3, B, d)
+    PV, PQ, Cm, av, aq = f(B, N, d), f(3, B, T, d), f(3, B, T, N), f(3, B, N), f(3, B, T)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = _ws(L.hca_coattn_workspace(B, N, T, d, 0), dev)
+        _lib.check(L.hca_coattn_fwd(_ptr(V), V.stride(0), V.stride(1), V.stride(2), _ptr(q0), _ptr(q1), _ptr(q2), _ptr(Wv), _ptr(bv),
+                                    _ptr(Wq), _ptr(bq), _ptr(wv), _ptr(cv), _ptr(wq), _ptr(cq), _ptr(vhat), _ptr(qhat), _ptr(PV),
+                                    _ptr(PQ), _ptr(Cm), _ptr(av), _ptr(aq), B, N, T, d, _ptr(ws), ws.numel(), _stream()), "coattn_fwd")
+    return vhat, qhat, PV, PQ, Cm, av, aq
+
+
+@coattn.register_fake
+def _(V, q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq):
+    B, N, d = V.shape
+    T = q0.shape[1]
+    f = lambda *s: V.new_empty(*s)
+    return f(3, B, d), f(3, B, d), f(B, N, d), f(3, B, T, d), f(3, B, T, N), f(3, B, N), f(3, B, T)
+
+
+@torch.library.custom_op(f"{NS}::coattn_bwd", mutates_args=(), device_types="cuda")
+def coattn_bwd(V: Tensor, q0: Tensor, q1: Tensor, q2: Tensor, Wv: Tensor, Wq: Tensor, wv: Tensor, wq: Tensor, PV: Tensor,
+               PQ: Tensor, Cm: Tensor, av: Tensor, aq: Tensor, gv: Tensor, gq: Tensor, need_dv: bool
+               ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    _cuda_f32(V, q0, q1, q2, Wv, Wq, wv, wq, PV, PQ, Cm, av, aq, gv, gq)
+    q0, q1, q2, Wv, Wq, wv, wq, gv, gq = map(_c, (q0, q1, q2, Wv, Wq, wv, wq, gv, gq))
+    B, N, d = V.shape
+    T = q0.shape[1]
+    dev = V.device
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    dV = f(B, N, d) if need_dv else f(0)
+    dQ = f(3, B, T, d)
+    dWv, dbv, dWq, dbq = f(d, d), f(d), f(d, d), f(d)
+    dwv, dcv, dwq, dcq = f(d), f(1), f(d), f(1)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = _ws(L.hca_coattn_workspace(B, N, T, d, int(need_dv)), dev)
+        _lib.check(L.hca_coattn_bwd(_ptr(V), V.stride(0), V.stride(1), V.stride(2), _ptr(q0), _ptr(q1), _ptr(q2), _ptr(Wv), _ptr(Wq),
+                                    _ptr(wv), _ptr(wq), _ptr(PV), _ptr(PQ), _ptr(Cm), _ptr(av), _ptr(aq), _ptr(gv), _ptr(gq),
+                                    _ptr(dV) if need_dv else None, _ptr(dQ), _ptr(dWv), _ptr(dbv), _ptr(dWq), _ptr(dbq), _ptr(dwv),
+                                    _ptr(dcv), _ptr(dwq), _ptr(dcq), B, N, T, d, _ptr(ws), ws.numel(), _stream()), "coattn_bwd")
+    return dV, dQ, dWv, dbv, dWq, dbq, dwv, dcv, dwq, dcq
+
+
+@coattn_bwd.register_fake
+def _(V, q0, q1, q2, Wv, Wq, wv, wq, PV, PQ, Cm, av, aq, gv, gq, need_dv):
+    B, N, d = V.shape
+    T = q0.shape[1]
+    f = lambda *s: V.new_empty(*s)
+    return (f(B, N, d) if need_dv else f(0), f(3, B, T, d), f(d, d), f(d), f(d, d), f(d), f(d), f(1), f(d), f(1))
+
+
+def _coattn_setup(ctx, inputs, output):
+    V, q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq = inputs
+    vhat, qhat, PV, PQ, Cm, av, aq = output
+    ctx.save_for_backward(V, q0, q1, q2, Wv, Wq, wv, wq, PV, PQ, Cm, av, aq)
+    ctx.shapes = (wv.shape, cv.shape, wq.shape, cq.shape)
+    ctx.set_materialize_grads(False)
+
+
+def _coattn_backward(ctx, gv, gq, *_unused):
+    V, q0, q1, q2, Wv, Wq, wv, wq, PV, PQ, Cm, av, aq = ctx.saved_tensors
+    if gv is None and gq is None:
+        return (None,) * 12
+    if gv is None:
+        gv = torch.zeros_like(gq)
+    if gq is None:
+        gq = torch.zeros_like(gv)
+    need_dv = ctx.needs_input_grad[0]
+    dV, dQ, dWv, dbv, dWq, dbq, dwv, dcv, dwq, dcq = coattn_bwd(V, q0, q1, q2, Wv, Wq, wv, wq, PV, PQ, Cm, av, aq, gv, gq, need_dv)
+    s_wv, s_cv, s_wq, s_cq = ctx.shapes
+    return ((dV if need_dv else None), dQ[0], dQ[1], dQ[2], dWv, dbv, dWq, dbq, dwv.view(s_wv), dcv.view(s_cv), dwq.view(s_wq),
+            dcq.view(s_cq))
+
+
+coattn.register_autograd(_coattn_backward, setup_context=_coattn_setup)
+
+
+# -------------------------------------------------------------------------------------------------------- MLP
+@torch.library.custom_op(f"{NS}::mlp", mutates_args=(), device_types="cuda")
+def mlp(vhat: Tensor, qhat: Tensor, Ww: Tensor, bw: Tensor, Wp: Tensor, bp: Tensor, Ws: Tensor, bs: Tensor, Wh: Tensor,
+        bh: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """MLPClassifier forward (reference model.py:414-434) on stacked [3,B,d] attended features.
+
+    Returns logits [B,K] and the tensors saved for backward (xw, xp, xs, hs)."""
+    _cuda_f32(vhat, qhat, Ww, bw, Wp, bp, Ws, bs, Wh, bh)
+    vhat, qhat, Ww, bw, Wp, bp, Ws, bs, Wh, bh = map(_c, (vhat, qhat, Ww, bw, Wp, bp, Ws, bs, Wh, bh))
+    _, B, d = vhat.shape
+    m, K = Ws.shape[0], Wh.shape[0]
+    dev = vhat.device
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    logits, xw, xp, xs, hs = f(B, K), f(B, d), f(B, 2 * d), f(B, 2 * d), f(B, m)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = _ws(L.hca_mlp_workspace(B, d, m, K), dev)
+        _lib.check(L.hca_mlp_fwd(_ptr(vhat), _ptr(qhat), _ptr(Ww), _ptr(bw), _ptr(Wp), _ptr(bp), _ptr(Ws), _ptr(bs), _ptr(Wh), _ptr(bh),
+                                 _ptr(logits), _ptr(xw), _ptr(xp), _ptr(xs), _ptr(hs), B, d, m, K, _ptr(ws), ws.numel(), _stream()),
+                   "mlp_fwd")
+    return logits, xw, xp, xs, hs
+
+
+@mlp.register_fake
+def _(vhat, qhat, Ww, bw, Wp, bp, Ws, bs, Wh, bh):
+    _, B, d = vhat.shape
+    f = lambda *s: vhat.new_empty(*s)
+    return f(B, Wh.shape[0]), f(B, d), f(B, 2 * d), f(B, 2 * d), f(B, Ws.shape[0])
+
+
+@torch.library.custom_op(f"{NS}::mlp_bwd", mutates_args=(), device_types="cuda")
+def mlp_bwd(dlogits: Tensor, Ww: Tensor, Wp: Tensor, Ws: Tensor, Wh: Tensor, xw: Tensor, xp: Tensor, xs: Tensor, hs: Tensor
+            ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    _cuda_f32(dlogits, Ww, Wp, Ws, Wh, xw, xp, xs, hs)
+    dlogits, Ww, Wp, Ws, Wh = map(_c, (dlogits, Ww, Wp, Ws, Wh))
+    B, d = xw.shape
+    m, K = Ws.shape[0], Wh.shape[0]
+    dev = dlogits.device
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    g = f(3, B, d)
+    dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh = f(d, d), f(d), f(d, 2 * d), f(d), f(m, 2 * d), f(m), f(K, m), f(K)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = _ws(L.hca_mlp_workspace(B, d, m, K), dev)
+        _lib.check(L.hca_mlp_bwd(_ptr(dlogits), _ptr(Ww), _ptr(Wp), _ptr(Ws), _ptr(Wh), _ptr(xw), _ptr(xp), _ptr(xs), _ptr(hs), _ptr(g),
+                                 _ptr(dWw), _ptr(dbw), _ptr(dWp), _ptr(dbp), _ptr(dWs), _ptr(dbs), _ptr(dWh), _ptr(dbh), B, d, m, K,
+                                 _ptr(ws), ws.numel(), _stream()), "mlp_bwd")
+    return g, dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh
+
+
+@mlp_bwd.register_fake
+def _(dlogits, Ww, Wp, Ws, Wh, xw, xp, xs, hs):
+    B, d = xw.shape
+    m, K = Ws.shape[0], Wh.shape[0]
+    f = lambda *s: dlogits.new_empty(*s)
+    return f(3, B, d), f(d, d), f(d), f(d, 2 * d), f(d), f(m, 2 * d), f(m), f(K, m), f(K)
+
+
+def _mlp_setup(ctx, inputs, output):
+    vhat, qhat, Ww, bw, Wp, bp, Ws, bs, Wh, bh = inputs
+    logits, xw, xp, xs, hs = output
+    ctx.save_for_backward(Ww, Wp, Ws, Wh, xw, xp, xs, hs)
+    ctx.set_materialize_grads(False)
+
+
+def _mlp_backward(ctx, dlogits, *_unused):
+    Ww, Wp, Ws, Wh, xw, xp, xs, hs = ctx.saved_tensors
+    if dlogits is None:
+        return (None,) * 10
+    g, dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh = mlp_bwd(dlogits, Ww, Wp, Ws, Wh, xw, xp, xs, hs)
+    return g, g, dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh      # q_l + v_l: both receive the same gradient
+
+
+mlp.register_autograd(_mlp_backward, setup_context=_mlp_setup)
+
+
+# ---------------------------------------------------------------------------------- raw GEMM (tests / profiling)
+def gemm_nt(A: Tensor, B: Tensor, bias: Optional[Tensor] = None, path: int = 1) -> Tensor:
+    """D = A . B^T (+ bias) through the library's dense kernels: path 0 fp32 CUDA cores, 1 tcgen05 bf16x2,
+    2 tcgen05 bf16x3.  Not differentiable; for tests, benchmarks and ncu captures."""
+    _cuda_f32(A, B, bias)
+    A, B = _c(A), _c(B)
+    M, K = A.shape
+    N = B.shape[0]
+    D = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    L = _lib.lib()
+    with torch.cuda.device(A.device):
+        ws = _ws(L.hca_gemm_nt_workspace(M, N, K, path), A.device)
+        _lib.check(L.hca_gemm_nt(_ptr(A), _ptr(B), _ptr(bias), _ptr(D), M, N, K, path, _ptr(ws), ws.numel(), _stream()), "gemm_nt")
+    return D
