@@ -121,12 +121,15 @@ HCA_API int hca_mlp_bwd(const float* dlogits, const float* Ww, const float* Wp, 
                 float* dWh, float* dbh, int B, int d, int mlp, int K,
                 void* ws, size_t ws_bytes, void* stream);
 
-/* ---- building block exposed for tests and profiling: D[M,N] = A[M,K] . B[N,K]^T (+bias[N]) -------- */
-/* dense row-major fp32 in and out; `path` 0 = fp32 CUDA cores, 1 = tcgen05 with bf16x2 operand
- * splitting (3 MMAs, ~2^-16 operand precision), 2 = tcgen05 bf16x3 (6 MMAs, fp32-grade). */
-HCA_API size_t hca_gemm_nt_workspace(int M, int N, int K, int path);
-HCA_API int hca_gemm_nt(const float* A, const float* B, const float* bias, float* D, int M, int N, int K,
-                int path, void* ws, size_t ws_bytes, void* stream);
+/* ---- building block exposed for tests and profiling: one dense contraction ------------------------- */
+/* fp32 row-major in and out.  layout 0 "nt": D[M,N] = A[M,K] . B[N,K]^T (+bias[N])   (nn.Linear forward)
+ *                            layout 1 "nn": D[M,N] = A[M,K] . B[K,N]     (+bias[N])   (data gradient)
+ *                            layout 2 "tn": D[M,N] = A[K,M]^T . B[K,N]                (weight gradient, split-K)
+ * path 0 = fp32 CUDA cores; 1 = tcgen05 with bf16x2 operand splitting (3 MMAs, ~2^-16 operand
+ * precision); 2 = tcgen05 bf16x3 (6 MMAs, fp32-grade). */
+HCA_API size_t hca_gemm_workspace(int M, int N, int K);
+HCA_API int hca_gemm(const float* A, const float* B, const float* bias, float* D, int M, int N, int K,
+                     int layout, int path, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

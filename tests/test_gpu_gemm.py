@@ -1,0 +1,60 @@
+"""-m gpu: the dense contraction kernels (fp32 CUDA-core path and the tcgen05 split-bf16 path) against fp64."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import gpu_harness
+    return gpu_harness.PKG.ops
+
+
+def _ref(A, B, bias, layout):
+    A, B = A.double().cpu(), B.double().cpu()
+    if layout == "nt":
+        D = A @ B.T
+    elif layout == "nn":
+        D = A @ B
+    else:
+        D = A.T @ B
+    if bias is not None:
+        D = D + bias.double().cpu()
+    return D
+
+
+SHAPES = [(128, 128, 64), (256, 512, 512), (1000, 512, 512), (160, 1001, 1024), (77, 40, 200), (4160, 1536, 512), (130, 136, 1001)]
+# expected normwise relative error per path: fp32 ~1e-6, bf16x2 split ~2^-16, bf16x3 split fp32-grade
+TOL = {0: 2e-6, 1: 3e-5, 2: 2e-6}
+
+
+@pytest.mark.parametrize("layout", ["nt", "nn", "tn"])
+@pytest.mark.parametrize("path", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_layouts_and_paths(layout, path, M, N, K):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    if layout == "nt":
+        A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    elif layout == "nn":
+        A, B = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g)
+    else:
+        A, B = torch.randn(K, M, generator=g), torch.randn(K, N, generator=g)
+    bias = torch.randn(N, generator=g) if layout != "tn" else None
+    D = ops.gemm(A.cuda(), B.cuda(), None if bias is None else bias.cuda(), layout=layout, path=path)
+    torch.cuda.synchronize()
+    ref = _ref(A, B, bias, layout)
+    err = float((D.double().cpu() - ref).norm() / ref.norm())
+    assert err < TOL[path], (layout, path, M, N, K, err)
+
+
+def test_gemm_tc_large_k_splitk_wgrad_shape():
+    """dW_v = dPV^T V at the headline size: M = N = 512, K = 160*196 (split-K with fp32 atomics)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    K, M, N = 160 * 196, 512, 512
+    A, B = torch.randn(K, M, generator=g), torch.randn(K, N, generator=g)
+    D = ops.gemm(A.cuda(), B.cuda(), None, layout="tn", path=1)
+    ref = A.double().T @ B.double()
+    assert float((D.double().cpu() - ref).norm() / ref.norm()) < 3e-5

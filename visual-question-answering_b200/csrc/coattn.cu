@@ -13,6 +13,7 @@
 //
 // This file is the orchestration + the warp-level glue kernels; the contractions go through dense.cuh
 // (large, tensor-core capable) and gemm_ffma.cuh (per-sample strided products with fused epilogues).
+#include <algorithm>
 #include "common.cuh"
 #include "dense.cuh"
 #include "gemm_ffma.cuh"
@@ -165,7 +166,11 @@ extern "C" size_t hca_coattn_workspace(int B, int N, int T, int d, int need_dv) 
   s += 2 * align_up(3 * b * T * d * 4);                        // dZq, dPQ
   s += align_up(b * N * d * 4);                                // dPV
   s += align_up(3 * b * T * N * 4);                            // dS
-  s += hca::dense_scratch_bytes((int)(b * N), d, d) + hca::dense_scratch_bytes((int)(3 * b * T), d, d);
+  size_t sc = hca::dense_scratch_bytes((int)(b * N), d, d);                    // PV, dV
+  sc = std::max(sc, hca::dense_scratch_bytes(d, d, (int)(b * N)));            // dWv (K = B*N)
+  sc = std::max(sc, hca::dense_scratch_bytes((int)(3 * b * T), d, d));        // dQ += dPQ Wq
+  sc = std::max(sc, hca::dense_scratch_bytes(d, d, (int)(b * T)));            // dWq
+  s += sc;
   return s + 1024;
 }
 

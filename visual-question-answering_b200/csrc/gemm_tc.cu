@@ -1,0 +1,404 @@
+// tcgen05 / TMEM / TMA split-bf16 GEMM (see gemm_tc.cuh for the scheme).  sm_100a only.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "gemm_tc.cuh"
+
+namespace hca {
+namespace {
+
+constexpr int BM = 128;               // UMMA M (cta_group::1): TMEM lane i <-> output row i
+constexpr int BK = 64;                // bf16 elements per k-block = 128 bytes = one SWIZZLE_128B span
+constexpr int UMMA_K = 16;            // bf16
+constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int MAX_STAGES = 6;
+constexpr int NUM_THREADS = 192;      // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct TcParams {
+  int M, N, K, P, a_mn, b_mn, stages, kb_total, kb_per_split;
+  float* D;
+  int64_t ldd;
+  const float* bias;
+  int act_tanh;
+  const float* mulx;
+  int64_t mulx_ld;
+  int accumulate, atomic;
+};
+
+// ----------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (an error the host sees), never as a hang.
+__device__ __noinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("hiecoattn gemm_tc: mbarrier wait timed out (tag %d, block %d,%d,%d, thread %d)\n", tag, blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
+//   [46,48) version = 1 | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Descriptor of the k-th 16-wide K slice of a tile.
+//   K-major tile  [rows][64 k] : rows are 128 B apart, 8-row groups 1024 B apart (SBO); a K slice is +32 B inside the row.
+//   MN-major tile [64 k][64 mn] per 64-wide MN chunk (one TMA box, 8192 B): k rows 128 B apart, 8-row groups 1024 B apart
+//                 (SBO), MN chunks 8192 B apart (LBO); a K slice of 16 rows is +2048 B.
+__device__ __forceinline__ uint64_t tile_desc(uint32_t tile_addr, int mn_major, int kslice) {
+  return mn_major ? umma_desc(tile_addr + kslice * 2048, 8192, 1024) : umma_desc(tile_addr + kslice * 32, 16, 1024);
+}
+
+__device__ __forceinline__ float tanh_acc(float x) { return tanhf(x); }
+
+// ------------------------------------------------------------------------------------------------------ kernel
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  constexpr int B_TILE_BYTES = BN * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t stage_bytes = p.P * (A_TILE_BYTES + B_TILE_BYTES);
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
+  __shared__ uint32_t tmem_ptr_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
+  const int num_kb = kb_end - kb_begin;
+
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[MAX_STAGES + s]); };
+  const uint32_t tmem_full_bar = smem_u32(&bars[2 * MAX_STAGES]);
+  auto a_tile = [&](int s, int pl) { return smem_base + s * stage_bytes + pl * A_TILE_BYTES; };
+  auto b_tile = [&](int s, int pl) { return smem_base + s * stage_bytes + p.P * A_TILE_BYTES + pl * B_TILE_BYTES; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr_smem), BN);       // BN fp32 accumulator columns (power of two >= 32)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (one lane)
+    if (lane == 0) {
+      for (int it = 0; it < num_kb; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1, 1);
+        mbar_expect_tx(full_bar(s), stage_bytes);
+        const int k0 = (kb_begin + it) * BK;
+        for (int pl = 0; pl < p.P; ++pl) {
+          if (!p.a_mn) {
+            tma_load_3d(a_tile(s, pl), &tmA, full_bar(s), k0, m0, pl);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_3d(a_tile(s, pl) + c * 8192, &tmA, full_bar(s), m0 + c * 64, k0, pl);
+          }
+          if (!p.b_mn) {
+            tma_load_3d(b_tile(s, pl), &tmB, full_bar(s), k0, n0, pl);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_3d(b_tile(s, pl) + c * 8192, &tmB, full_bar(s), n0 + c * 64, k0, pl);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one lane)
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6), a=bf16 [7,10), b=bf16 [10,13),
+      // a_major bit 15, b_major bit 16, N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t acc = 0;
+      for (int it = 0; it < num_kb; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(full_bar(s), ph, 2);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          for (int i = 0; i < p.P; ++i) {
+            const uint64_t ad = tile_desc(a_tile(s, i), p.a_mn, ks);
+            for (int j = 0; j < p.P - i; ++j) {
+              const uint64_t bd = tile_desc(b_tile(s, j), p.b_mn, ks);
+              umma_bf16(tmem_base, ad, bd, idesc, acc);
+              acc = 1;
+            }
+          }
+        }
+        umma_commit(empty_bar(s));          // frees the smem stage once the MMAs above have read it
+      }
+      umma_commit(tmem_full_bar);           // accumulator complete -> epilogue
+    }
+  } else {
+    // ===================================================================== epilogue: TMEM -> registers -> global
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0, 3);
+    tc_fence_after();
+    const bool row_ok = row < p.M;
+    float* drow = p.D + (int64_t)row * p.ldd;
+    const float* xrow = p.mulx ? p.mulx + (int64_t)row * p.mulx_ld : nullptr;
+    const bool vec_ok = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && !p.atomic;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      __syncwarp();                         // tcgen05.ld is warp-collective: reconverge after the guarded stores
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      if (num_kb == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      const int col0 = n0 + c * 32;
+      if (!row_ok || col0 >= p.N) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        const int col = col0 + j;
+        if (col < p.N) {
+          if (p.bias) x += __ldg(p.bias + col);
+          if (p.act_tanh) x = tanh_acc(x);
+          if (xrow) {
+            const float h = xrow[col];
+            x *= (1.f - h * h);
+          }
+        }
+        f[j] = x;
+      }
+      if (vec_ok && col0 + 32 <= p.N) {
+        float4* d4 = reinterpret_cast<float4*>(drow + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          if (p.accumulate) {
+            const float4 old = d4[j];
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          d4[j] = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col < p.N) {
+            if (p.atomic) atomicAdd(drow + col, f[j]);
+            else if (p.accumulate) drow[col] += f[j];
+            else drow[col] = f[j];
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// fp32 -> bf16 planes
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols,
+                                                           __nv_bfloat16* __restrict__ planes, int64_t ldp, int64_t plane_stride,
+                                                           int P) {
+  const int c4n = (cols + 3) / 4;
+  const int64_t total = rows * c4n;
+  const bool aligned = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c4n;
+    const int c = (int)(i - r * c4n) * 4;
+    float x[4];
+    if (aligned && c + 4 <= cols) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src + r * ld + c));
+      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = (c + j < cols) ? src[r * ld + c + j] : 0.f;
+    }
+    for (int pl = 0; pl < P; ++pl) {
+      __nv_bfloat16 h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = __float2bfloat16_rn(x[j]);
+        x[j] -= __bfloat162float(h[j]);
+      }
+      __nv_bfloat16* dst = planes + pl * plane_stride + r * ldp + c;     // ldp % 8 == 0 and c % 4 == 0: 8-byte aligned
+      *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(h);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// 3-D tensor map over [P][rows][ld] bf16: dims (cols, rows, P); box (64, box_rows, 1); 128-byte swizzle; OOB -> zeros
+int make_tmap(CUtensorMap* tm, const TcOperand& o, int P, int box_rows) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return set_err(HCA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[3] = {(cuuint64_t)o.cols, (cuuint64_t)o.rows, (cuuint64_t)P};
+  cuuint64_t gstr[2] = {(cuuint64_t)o.ld * 2, (cuuint64_t)o.plane_stride * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)o.planes, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_err(HCA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed (%d) cols=%d rows=%d ld=%lld P=%d", (int)r, o.cols, o.rows,
+                   (long long)o.ld, P);
+  return 0;
+}
+
+}  // namespace
+
+bool tc_available() { return get_encoder() != nullptr; }
+
+int launch_split_planes(const float* src, int64_t ld, int64_t rows, int cols, __nv_bfloat16* planes, int64_t ldp,
+                        int64_t plane_stride, int P, cudaStream_t s) {
+  HCA_CHECK_ARG(src && planes && rows > 0 && cols > 0 && P >= 1 && P <= 3 && (ldp % 8) == 0 && (plane_stride % 8) == 0,
+                "split_planes: bad arguments");
+  const int64_t total = rows * ((cols + 3) / 4);
+  split_planes_kernel<<<ew_grid(total), 256, 0, s>>>(src, ld, rows, cols, planes, ldp, plane_stride, P);
+  HCA_LAUNCHED();
+  return 0;
+}
+
+int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, int K, const TcEpilogue& e, int splitk,
+                   cudaStream_t s) {
+  constexpr int BN = 128;
+  HCA_CHECK_ARG(P >= 1 && P <= 3 && M > 0 && N > 0 && K > 0 && splitk >= 1, "gemm_tc: bad sizes");
+  HCA_CHECK_ARG((A.ld % 8) == 0 && (B.ld % 8) == 0 && (A.plane_stride % 8) == 0 && (B.plane_stride % 8) == 0,
+                "gemm_tc: plane leading dimensions must be multiples of 8 elements (TMA 16-byte strides)");
+  HCA_CHECK_ARG((reinterpret_cast<uintptr_t>(A.planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(B.planes) & 15) == 0,
+                "gemm_tc: planes must be 16-byte aligned");
+  CUtensorMap tmA, tmB;
+  HCA_TRY(make_tmap(&tmA, A, P, A.mn_major ? 64 : BM));
+  HCA_TRY(make_tmap(&tmB, B, P, B.mn_major ? 64 : BN));
+  TcParams p;
+  p.M = M; p.N = N; p.K = K; p.P = P;
+  p.a_mn = A.mn_major ? 1 : 0;
+  p.b_mn = B.mn_major ? 1 : 0;
+  const int stage_bytes = P * (A_TILE_BYTES + BN * BK * 2);
+  p.stages = SMEM_BUDGET / stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  HCA_CHECK_ARG(p.stages >= 2, "gemm_tc: tile does not fit two pipeline stages");
+  p.kb_total = (K + BK - 1) / BK;
+  if (splitk > p.kb_total) splitk = p.kb_total;
+  p.kb_per_split = (p.kb_total + splitk - 1) / splitk;
+  splitk = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;      // no empty split
+  p.D = e.D; p.ldd = e.ldd; p.bias = e.bias; p.act_tanh = e.act_tanh; p.mulx = e.mulx; p.mulx_ld = e.mulx_ld;
+  p.accumulate = e.accumulate;
+  p.atomic = splitk > 1 ? 1 : 0;
+  HCA_CHECK_ARG(!(p.atomic && (e.bias || e.act_tanh || e.mulx)), "gemm_tc: split-K needs a linear epilogue");
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HCA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048));
+    attr_set = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splitk);
+  HCA_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "gemm_tc: grid too large");
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, p);
+  HCA_LAUNCHED();
+  return 0;
+}
+
+}  // namespace hca

@@ -5,6 +5,8 @@
 // The concatenations are never materialised separately: h_w and h_p are written by the GEMM epilogues
 // straight into the right halves of the next layer's input rows (xp, xs), which are also the tensors
 // saved for backward.
+#include <algorithm>
+#include <initializer_list>
 #include "common.cuh"
 #include "dense.cuh"
 #include "util_kernels.cuh"
@@ -36,7 +38,12 @@ __global__ void __launch_bounds__(256) mlp_inputs_kernel(const float4* __restric
 extern "C" size_t hca_mlp_workspace(int B, int d, int mlp, int K) {
   using hca::align_up;
   size_t s = align_up((size_t)B * mlp * 4) + 2 * align_up((size_t)B * d * 4) + 1024;
-  s += hca::dense_scratch_bytes(B, K, mlp) + hca::dense_scratch_bytes(B, mlp, 2 * d);
+  size_t sc = 0;
+  for (size_t v : {hca::dense_scratch_bytes(B, K, mlp), hca::dense_scratch_bytes(K, mlp, B), hca::dense_scratch_bytes(B, mlp, K),
+                   hca::dense_scratch_bytes(mlp, 2 * d, B), hca::dense_scratch_bytes(B, mlp, 2 * d), hca::dense_scratch_bytes(B, 2 * d, mlp),
+                   hca::dense_scratch_bytes(d, 2 * d, B), hca::dense_scratch_bytes(B, 2 * d, d)})
+    sc = std::max(sc, v);
+  s += sc;
   return s;
 }
 

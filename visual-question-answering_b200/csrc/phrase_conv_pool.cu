@@ -12,6 +12,7 @@
 // The pre-activations must be fp32-grade: an argmax flip re-routes a gradient element,
 // so the forward products run on the exact-fp32 GEMM path.  The backward products (dgrad, wgrad) only
 // need the 1e-3 budget and may use the tensor-core path.
+#include <algorithm>
 #include "common.cuh"
 #include "gemm_ffma.cuh"
 #include "dense.cuh"
@@ -143,7 +144,7 @@ extern "C" size_t hca_phrase_conv_pool_workspace(int B, int T, int E) {
   using hca::align_up;
   const size_t R = (size_t)B * T;
   return 3 * align_up(R * 3 * E * 4) + 2 * (align_up((size_t)E * 2 * E * 4) + align_up((size_t)E * 3 * E * 4)) + 256 +
-         hca::dense_scratch_bytes((int)R, 3 * E, 3 * E);
+         std::max(hca::dense_scratch_bytes(E, 3 * E, (int)R), hca::dense_scratch_bytes((int)R, 3 * E, E));
 }
 
 extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,

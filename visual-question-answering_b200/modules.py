@@ -39,6 +39,20 @@ class QuestionLens:
         self.dev = lens_dev if lens_dev is not None else self.cpu.to(device, non_blocking=True)
 
 
+class _cudnn_fp32:
+    """cuDNN RNNs default to TF32 math (torch.backends.cudnn.allow_tf32 = True), which alone costs ~1e-3 of
+    relative error in the sentence features and their gradients -- the whole north_star budget.  The
+    sentence LSTM therefore runs with TF32 disabled, i.e. in the reference's fp32."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cudnn.allow_tf32 = self.prev
+        return False
+
+
 def _f32(t: Tensor) -> Tensor:
     return t if t.dtype == torch.float32 else t.float()
 
@@ -84,7 +98,8 @@ class QuestionCoAttentionEncoder(nn.Module):
         # phrase level with the pad rows already zeroed (what pack -> pad does at model.py:287,292)
         x_phrase_emb = self.phrase_conv_pool(x_word_emb, lens_dev)                      # model.py:284
         packed = pack_padded_sequence(x_phrase_emb, lens_cpu, batch_first=True)         # raises on unsorted / zero lens
-        x_sentence_emb, _ = self.sentence_lstm(packed)                                  # model.py:289
+        with _cudnn_fp32():
+            x_sentence_emb, _ = self.sentence_lstm(packed)                              # model.py:289
         x_sentence_emb = pad_packed_sequence(x_sentence_emb, batch_first=True, total_length=max_seq_len)[0]
         return x_word_emb, x_phrase_emb, x_sentence_emb
 

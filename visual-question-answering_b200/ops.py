@@ -333,16 +333,30 @@ mlp.register_autograd(_mlp_backward, setup_context=_mlp_setup)
 
 
 # ---------------------------------------------------------------------------------- raw GEMM (tests / profiling)
-def gemm_nt(A: Tensor, B: Tensor, bias: Optional[Tensor] = None, path: int = 1) -> Tensor:
-    """D = A . B^T (+ bias) through the library's dense kernels: path 0 fp32 CUDA cores, 1 tcgen05 bf16x2,
-    2 tcgen05 bf16x3.  Not differentiable; for tests, benchmarks and ncu captures."""
+_LAYOUTS = {"nt": 0, "nn": 1, "tn": 2}
+
+
+def gemm(A: Tensor, B: Tensor, bias: Optional[Tensor] = None, layout: str = "nt", path: int = 1) -> Tensor:
+    """One dense contraction through the library's kernels (not differentiable; tests, benchmarks, ncu).
+
+    layout "nt": A[M,K] . B[N,K]^T (+bias)   "nn": A[M,K] . B[K,N] (+bias)   "tn": A[K,M]^T . B[K,N]
+    path 0 = fp32 CUDA cores, 1 = tcgen05 bf16x2 split (3 MMAs), 2 = tcgen05 bf16x3 split (6 MMAs)."""
     _cuda_f32(A, B, bias)
     A, B = _c(A), _c(B)
-    M, K = A.shape
-    N = B.shape[0]
+    if layout == "nt":
+        (M, K), N = A.shape, B.shape[0]
+    elif layout == "nn":
+        (M, K), N = A.shape, B.shape[1]
+    else:
+        (K, M), N = A.shape, B.shape[1]
     D = torch.empty(M, N, dtype=torch.float32, device=A.device)
     L = _lib.lib()
     with torch.cuda.device(A.device):
-        ws = _ws(L.hca_gemm_nt_workspace(M, N, K, path), A.device)
-        _lib.check(L.hca_gemm_nt(_ptr(A), _ptr(B), _ptr(bias), _ptr(D), M, N, K, path, _ptr(ws), ws.numel(), _stream()), "gemm_nt")
+        ws = _ws(L.hca_gemm_workspace(M, N, K), A.device)
+        _lib.check(L.hca_gemm(_ptr(A), _ptr(B), _ptr(bias), _ptr(D), M, N, K, _LAYOUTS[layout], path, _ptr(ws), ws.numel(), _stream()),
+                   "gemm")
     return D
+
+
+def gemm_nt(A: Tensor, B: Tensor, bias: Optional[Tensor] = None, path: int = 1) -> Tensor:
+    return gemm(A, B, bias, "nt", path)
