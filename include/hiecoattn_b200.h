@@ -128,6 +128,10 @@ HCA_API int hca_mlp_bwd(const float* dlogits, const float* Ww, const float* Wp, 
  * path 0 = fp32 CUDA cores; 1 = tcgen05 with bf16x2 operand splitting (3 MMAs, ~2^-16 operand
  * precision); 2 = tcgen05 bf16x3 (6 MMAs, fp32-grade). */
 HCA_API size_t hca_gemm_workspace(int M, int N, int K);
+/* debug / profiling aid: subsequent tensor-core GEMM launches record per-CTA clock64() stamps into
+ * buf [nctas][64] int64 ([0..7]: start, setup done, first tile landed, MMAs issued, epilogue start,
+ * epilogue end, CTA end, SM id; [8+i], [24+i], [40+i]: per-k-block producer / landed / issued stamps); pass NULL to switch it off. */
+HCA_API int hca_debug_gemm_timeline(void* buf, int nctas);
 HCA_API int hca_gemm(const float* A, const float* B, const float* bias, float* D, int M, int N, int K,
                      int layout, int path, void* ws, size_t ws_bytes, void* stream);
 

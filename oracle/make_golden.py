@@ -161,5 +161,22 @@ def main():
         print("wrote", c["name"], "loss64", float(r64["loss"]), "idx flips f32 vs f64:", int((idx64 != idx32).sum()))
 
 
+def record_state_dict_keys():
+    """Key names and shapes of the reference modules' state_dicts (the checkpoint-compat contract, main.py:168-176)."""
+    import json
+    d, vocab, K, mlp = 512, 10000, 1001, 1024
+    out = {}
+    for prefix, m in (("question_encoder", ref.QuestionCoAttentionEncoder(vocab, d, d)), ("co_attention", ref.ParallelCoAttention(d)),
+                      ("mlp_classify", ref.MLPClassifier(d, mlp, K))):
+        for k, v in m.state_dict().items():
+            out[f"{prefix}.{k}"] = list(v.shape)
+    base_q = ref.QuestionBaselineEncoder(vocab, 300, 1024)
+    for k, v in base_q.state_dict().items():
+        out[f"baseline.question_encoder.{k}"] = list(v.shape)
+    json.dump(out, open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json"), "w"), indent=1, sort_keys=True)
+    print("wrote state_dict_keys.json", len(out))
+
+
 if __name__ == "__main__":
     main()
+    record_state_dict_keys()

@@ -1,6 +1,7 @@
 // tcgen05 / TMEM / TMA split-bf16 GEMM (see gemm_tc.cuh for the scheme).  sm_100a only.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "gemm_tc.cuh"
 
 namespace hca {
@@ -23,7 +24,14 @@ struct TcParams {
   const float* mulx;
   int64_t mulx_ld;
   int accumulate, atomic;
+  int tma_store;            // epilogue goes through smem + TMA tile store (D 16-byte aligned, ldd % 4 == 0)
+  int dbg;                  // debug bit flags (HCA_TC_DBG): 1 = no TMA (MMA on garbage), 2 = sleepy epilogue wait, 4 = no stores
+  long long* timeline;      // optional [ncta][64] clock64 stamps (debug / profiling), nullptr normally
+  int timeline_ctas;
 };
+
+long long* g_timeline = nullptr;
+int g_timeline_ctas = 0;
 
 // ----------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -63,6 +71,22 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// TMA tile store / reduce-add from shared memory (bulk async group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps only
+
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -82,6 +106,37 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Warp-converged variants: every lane of the MMA warp executes the loop (so ptxas keeps the descriptors in
+// uniform registers instead of electing + broadcasting them per instruction) and one elected lane issues.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// descriptors passed as 32-bit halves so that ptxas can build them on the uniform datapath
+__device__ __forceinline__ void umma_bf16_elect32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -120,17 +175,22 @@ __device__ __forceinline__ uint64_t tile_desc(uint32_t tile_addr, int mn_major, 
 __device__ __forceinline__ float tanh_acc(float x) { return tanhf(x); }
 
 // ------------------------------------------------------------------------------------------------------ kernel
-template <int BN>
+template <int BN, int P, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const TcParams p) {
   constexpr int B_TILE_BYTES = BN * BK * 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
-  const uint32_t stage_bytes = p.P * (A_TILE_BYTES + B_TILE_BYTES);
+  constexpr uint32_t stage_bytes = P * (A_TILE_BYTES + B_TILE_BYTES);
   __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
   __shared__ uint32_t tmem_ptr_smem;
+  __shared__ __align__(16) float bias_sm[BN];           // this tile's bias slice, staged once by the epilogue warps
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform for ptxas, so the role branches below are uniform control flow and
+  // the MMA descriptors live in uniform registers (otherwise every tcgen05.mma pays an ELECT + VOTEU + 4x R2UR.BROADCAST
+  // sequence, ~250 cycles per instruction, measured)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
@@ -140,8 +200,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto empty_bar = [&](int s) { return smem_u32(&bars[MAX_STAGES + s]); };
   const uint32_t tmem_full_bar = smem_u32(&bars[2 * MAX_STAGES]);
   auto a_tile = [&](int s, int pl) { return smem_base + s * stage_bytes + pl * A_TILE_BYTES; };
-  auto b_tile = [&](int s, int pl) { return smem_base + s * stage_bytes + p.P * A_TILE_BYTES + pl * B_TILE_BYTES; };
+  auto b_tile = [&](int s, int pl) { return smem_base + s * stage_bytes + P * A_TILE_BYTES + pl * B_TILE_BYTES; };
 
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  long long* tl = (p.timeline && cta_lin < p.timeline_ctas) ? p.timeline + (size_t)cta_lin * 64 : nullptr;
+  if (tl && threadIdx.x == 0) {
+    tl[0] = clock64();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tl[7] = smid;
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
@@ -151,128 +219,235 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr_smem), BN);       // BN fp32 accumulator columns (power of two >= 32)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_ptr_smem, 0);
+  if (tl && threadIdx.x == 0) tl[1] = clock64();
 
   if (warp == 0) {
     // ===================================================================== TMA producer (one lane)
-    if (lane == 0) {
+    if (lane == 0 && !(p.dbg & 1)) {
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < num_kb; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1, 1);
+        if (tl && it < 12) tl[8 + it] = clock64();          // producer: slot free, issuing TMA for k-block `it`
         mbar_expect_tx(full_bar(s), stage_bytes);
         const int k0 = (kb_begin + it) * BK;
-        for (int pl = 0; pl < p.P; ++pl) {
-          if (!p.a_mn) {
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl) {
+          if (!A_MN) {
             tma_load_3d(a_tile(s, pl), &tmA, full_bar(s), k0, m0, pl);
           } else {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c) tma_load_3d(a_tile(s, pl) + c * 8192, &tmA, full_bar(s), m0 + c * 64, k0, pl);
           }
-          if (!p.b_mn) {
+          if (!B_MN) {
             tma_load_3d(b_tile(s, pl), &tmB, full_bar(s), k0, n0, pl);
           } else {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c) tma_load_3d(b_tile(s, pl) + c * 8192, &tmB, full_bar(s), n0 + c * 64, k0, pl);
           }
         }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (one lane)
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (whole warp converged, one lane issues)
+    {
       // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6), a=bf16 [7,10), b=bf16 [10,13),
       // a_major bit 15, b_major bit 16, N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      uint32_t acc = 0;
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // smem descriptor halves (cute::UMMA::SmemDescriptor): hi = SBO(1024 B) | version 1 | SWIZZLE_128B, constant;
+      // lo = (addr >> 4) | (LBO >> 4) << 16.  K-major: LBO unused (16 B), K slice = +32 B.  MN-major: LBO = 8192 B
+      // between 64-wide MN chunks, K slice of 16 rows = +2048 B.  Everything below is warp-uniform integer arithmetic,
+      // so ptxas keeps it on the uniform datapath (no per-MMA ELECT / R2UR.BROADCAST sequence).
+      constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t a_lbo = (A_MN ? (8192u >> 4) : 1u) << 16, b_lbo = (B_MN ? (8192u >> 4) : 1u) << 16;
+      constexpr uint32_t a_kstep = A_MN ? (2048u >> 4) : (32u >> 4), b_kstep = B_MN ? (2048u >> 4) : (32u >> 4);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t a0 = ((smem_base & 0x3FFFFu) >> 4) | a_lbo;
+      uint32_t b0 = (((smem_base + P * A_TILE_BYTES) & 0x3FFFFu) >> 4) | b_lbo;
       for (int it = 0; it < num_kb; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(full_bar(s), ph, 2);
+        if (!(p.dbg & 1)) mbar_wait(full_bar(s), ph, 2);
         tc_fence_after();
+        if (tl && lane == 0 && it == 0) tl[2] = clock64();
+        if (tl && lane == 0 && it < 12) tl[24 + it] = clock64();         // MMA warp: k-block `it` landed
+        // shuffle-broadcast: tells ptxas the stage base is warp-uniform, so the 12 descriptor variants below are
+        // uniform-register adds of compile-time constants
+        const uint32_t au = __shfl_sync(0xffffffffu, a0, 0), bu = __shfl_sync(0xffffffffu, b0, 0);
+        const uint32_t first = __shfl_sync(0xffffffffu, it == 0 ? 0u : 1u, 0);
 #pragma unroll
         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-          for (int i = 0; i < p.P; ++i) {
-            const uint64_t ad = tile_desc(a_tile(s, i), p.a_mn, ks);
-            for (int j = 0; j < p.P - i; ++j) {
-              const uint64_t bd = tile_desc(b_tile(s, j), p.b_mn, ks);
-              umma_bf16(tmem_base, ad, bd, idesc, acc);
-              acc = 1;
+#pragma unroll
+          for (int i = 0; i < P; ++i) {
+#pragma unroll
+            for (int j = 0; j < P - i; ++j) {
+              umma_bf16_elect32(tmem_base, au + i * (A_TILE_BYTES >> 4) + ks * a_kstep, desc_hi,
+                                bu + j * (B_TILE_BYTES >> 4) + ks * b_kstep, desc_hi, idesc, (ks | i | j) != 0 ? 1u : first);
             }
           }
         }
-        umma_commit(empty_bar(s));          // frees the smem stage once the MMAs above have read it
+        umma_commit_elect(empty_bar(s));      // frees the smem stage once the MMAs above have read it
+        if (tl && lane == 0 && it < 12) tl[40 + it] = clock64();         // MMA warp: k-block `it` issued + committed
+        a0 += stage_bytes >> 4;
+        b0 += stage_bytes >> 4;
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
+          a0 -= p.stages * (stage_bytes >> 4);
+          b0 -= p.stages * (stage_bytes >> 4);
+        }
       }
-      umma_commit(tmem_full_bar);           // accumulator complete -> epilogue
+      umma_commit_elect(tmem_full_bar);       // accumulator complete -> epilogue
+      if (tl && lane == 0) tl[3] = clock64();
     }
   } else {
     // ===================================================================== epilogue: TMEM -> registers -> global
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = m0 + q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0, 3);
+    {                                       // stage the bias slice while the mainloop runs
+      const int t = threadIdx.x - 64;       // 0..127
+      for (int j = t; j < BN; j += 128) bias_sm[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      epi_barrier();
+    }
+    if (p.dbg & 2) {
+      while (!mbar_try_wait(tmem_full_bar, 0)) __nanosleep(500);
+    } else {
+      mbar_wait(tmem_full_bar, 0, 3);
+    }
     tc_fence_after();
+    if (tl && threadIdx.x == 64) tl[4] = clock64();
     const bool row_ok = row < p.M;
     float* drow = p.D + (int64_t)row * p.ldd;
     const float* xrow = p.mulx ? p.mulx + (int64_t)row * p.mulx_ld : nullptr;
-    const bool vec_ok = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && !p.atomic;
+    if (p.tma_store) {
+      // Each thread owns one output row; a 32-column chunk is staged in shared memory as a [128 rows][128 B] tile in the
+      // TMA 128-byte swizzle (16-byte chunk j of row r lives at chunk j ^ (r & 7): conflict-free float4 stores), then one
+      // thread hands it to the TMA engine as a tile store (or reduce-add for accumulate / split-K).  Two staging buffers
+      // alternate; the pipeline stages are free by now (tmem_full implies every MMA has consumed its smem operands).
+      const int r = q * 32 + lane;
+      const bool leader = (warp == 2 && lane == 0);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      __syncwarp();                         // tcgen05.ld is warp-collective: reconverge after the guarded stores
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      if (num_kb == 0) {
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;                                   // uniform across the CTA
+        const uint32_t stage_buf = smem_base + (uint32_t)(c & 1) * (BM * 128);
+        if (c >= 2) {                                             // buffer reuse: its previous TMA store must have read it
+          if (leader) tma_store_wait_read<1>();
+          epi_barrier();
+        }
+        if (tl && leader && c < 4) tl[52 + 3 * c] = clock64();
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        if (tl && leader && c < 4) tl[53 + 3 * c] = clock64();
+        float f[32];
+        {                                                         // bias slice of this chunk: 8 x LDS.128, no dependent chain
+          const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
-      const int col0 = n0 + c * 32;
-      if (!row_ok || col0 >= p.N) continue;
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        const int col = col0 + j;
-        if (col < p.N) {
-          if (p.bias) x += __ldg(p.bias + col);
-          if (p.act_tanh) x = tanh_acc(x);
-          if (xrow) {
-            const float h = xrow[col];
-            x *= (1.f - h * h);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            f[4 * j] = b.x; f[4 * j + 1] = b.y; f[4 * j + 2] = b.z; f[4 * j + 3] = b.w;
           }
         }
-        f[j] = x;
-      }
-      if (vec_ok && col0 + 32 <= p.N) {
-        float4* d4 = reinterpret_cast<float4*>(drow + col0);
+        if (num_kb != 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+        }
+        if (p.act_tanh) {                                         // uniform branches: no predicated-off code on the common path
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = tanh_acc(f[j]);
+        }
+        if (xrow) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (row_ok && col0 + j < p.N) {
+              const float h = xrow[col0 + j];
+              f[j] *= (1.f - h * h);
+            }
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          if (p.accumulate) {
-            const float4 old = d4[j];
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-          }
-          d4[j] = o;
+          const uint32_t dst = stage_buf + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) * 16);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(f[4 * j]), "f"(f[4 * j + 1]), "f"(f[4 * j + 2]),
+                       "f"(f[4 * j + 3])
+                       : "memory");
         }
-      } else {
-#pragma unroll
+        fence_proxy_async_smem();                                 // generic-proxy smem writes -> visible to the TMA engine
+        epi_barrier();
+        if (tl && leader && c < 4) tl[54 + 3 * c] = clock64();
+        if (leader) {
+          if (p.atomic || p.accumulate) tma_reduce_add_2d(&tmD, stage_buf, col0, m0);
+          else tma_store_2d(&tmD, stage_buf, col0, m0);
+          tma_store_commit();
+        }
+      }
+      if (leader) tma_store_wait_read<0>();                       // smem must stay valid until the engine has read it
+    } else {
+      const bool vec_ok = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && !p.atomic;
+  #pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        __syncwarp();                         // tcgen05.ld is warp-collective: reconverge after the guarded stores
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        if (num_kb == 0) {
+  #pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        const int col0 = n0 + c * 32;
+        if (!row_ok || col0 >= p.N || (p.dbg & 4)) continue;
+        float f[32];
+  #pragma unroll
         for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]);
           const int col = col0 + j;
           if (col < p.N) {
-            if (p.atomic) atomicAdd(drow + col, f[j]);
-            else if (p.accumulate) drow[col] += f[j];
-            else drow[col] = f[j];
+            x += bias_sm[c * 32 + j];
+            if (p.act_tanh) x = tanh_acc(x);
+            if (xrow) {
+              const float h = xrow[col];
+              x *= (1.f - h * h);
+            }
+          }
+          f[j] = x;
+        }
+        if (vec_ok && col0 + 32 <= p.N) {
+          float4* d4 = reinterpret_cast<float4*>(drow + col0);
+  #pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            if (p.accumulate) {
+              const float4 old = d4[j];
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            d4[j] = o;
+          }
+        } else {
+  #pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < p.N) {
+              if (p.atomic) atomicAdd(drow + col, f[j]);
+              else if (p.accumulate) drow[col] += f[j];
+              else drow[col] = f[j];
+            }
           }
         }
       }
     }
     tc_fence_before();
+    if (tl && threadIdx.x == 64) tl[5] = clock64();
   }
   __syncthreads();
+  if (tl && threadIdx.x == 0) tl[6] = clock64();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
@@ -339,17 +514,38 @@ int make_tmap(CUtensorMap* tm, const TcOperand& o, int P, int box_rows) {
   cuuint64_t gstr[2] = {(cuuint64_t)o.ld * 2, (cuuint64_t)o.plane_stride * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
+  static int promo = -1;
+  if (promo < 0) { const char* e = getenv("HCA_TC_L2PROMO"); promo = e ? atoi(e) : 3; }
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)o.planes, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_err(HCA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed (%d) cols=%d rows=%d ld=%lld P=%d", (int)r, o.cols, o.rows,
                    (long long)o.ld, P);
   return 0;
 }
 
+// 2-D fp32 map over D [M, N] (leading dim ldd): box = 32 columns (128 B) x 128 rows, 128-byte swizzle; stores clip at the edges
+int make_tmap_out(CUtensorMap* tm, float* D, int64_t ldd, int M, int N) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return set_err(HCA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  cuuint64_t gstr[1] = {(cuuint64_t)ldd * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)D, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(HCA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled (output) failed (%d) M=%d N=%d ldd=%lld", (int)r, M, N, (long long)ldd);
+  return 0;
+}
+
 }  // namespace
 
 bool tc_available() { return get_encoder() != nullptr; }
+
+void tc_set_timeline(long long* buf, int nctas) {
+  g_timeline = buf;
+  g_timeline_ctas = nctas;
+}
 
 int launch_split_planes(const float* src, int64_t ld, int64_t rows, int cols, __nv_bfloat16* planes, int64_t ldp,
                         int64_t plane_stride, int P, cudaStream_t s) {
@@ -369,9 +565,12 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
                 "gemm_tc: plane leading dimensions must be multiples of 8 elements (TMA 16-byte strides)");
   HCA_CHECK_ARG((reinterpret_cast<uintptr_t>(A.planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(B.planes) & 15) == 0,
                 "gemm_tc: planes must be 16-byte aligned");
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmD;
   HCA_TRY(make_tmap(&tmA, A, P, A.mn_major ? 64 : BM));
   HCA_TRY(make_tmap(&tmB, B, P, B.mn_major ? 64 : BN));
+  const bool tma_store = ((e.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.D) & 15) == 0);
+  if (tma_store) HCA_TRY(make_tmap_out(&tmD, e.D, e.ldd, M, N));
+  else tmD = tmA;                                                     // unused placeholder
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.P = P;
   p.a_mn = A.mn_major ? 1 : 0;
@@ -379,6 +578,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   const int stage_bytes = P * (A_TILE_BYTES + BN * BK * 2);
   p.stages = SMEM_BUDGET / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  { const char* e = getenv("HCA_TC_STAGES"); if (e && atoi(e) >= 1 && atoi(e) < p.stages) p.stages = atoi(e); }
   HCA_CHECK_ARG(p.stages >= 2, "gemm_tc: tile does not fit two pipeline stages");
   p.kb_total = (K + BK - 1) / BK;
   if (splitk > p.kb_total) splitk = p.kb_total;
@@ -387,16 +587,29 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   p.D = e.D; p.ldd = e.ldd; p.bias = e.bias; p.act_tanh = e.act_tanh; p.mulx = e.mulx; p.mulx_ld = e.mulx_ld;
   p.accumulate = e.accumulate;
   p.atomic = splitk > 1 ? 1 : 0;
+  p.tma_store = tma_store ? 1 : 0;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("HCA_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+  p.timeline = g_timeline;
+  p.timeline_ctas = g_timeline_ctas;
   HCA_CHECK_ARG(!(p.atomic && (e.bias || e.act_tanh || e.mulx)), "gemm_tc: split-K needs a linear epilogue");
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HCA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048));
-    attr_set = true;
-  }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splitk);
   HCA_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "gemm_tc: grid too large");
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, p);
+  HCA_CHECK_ARG(!(A.mn_major && !B.mn_major), "gemm_tc: (MN-major A, K-major B) is not instantiated");
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+  KernelFn fn = nullptr;
+  const int combo = (A.mn_major ? 2 : (B.mn_major ? 1 : 0));    // 0 = NT, 1 = NN, 2 = TN
+#define HCA_TC_CASE(PP, CC, AMN, BMN) if (P == PP && combo == CC) fn = gemm_tc_kernel<BN, PP, AMN, BMN>;
+  HCA_TC_CASE(1, 0, false, false) HCA_TC_CASE(1, 1, false, true) HCA_TC_CASE(1, 2, true, true)
+  HCA_TC_CASE(2, 0, false, false) HCA_TC_CASE(2, 1, false, true) HCA_TC_CASE(2, 2, true, true)
+  HCA_TC_CASE(3, 0, false, false) HCA_TC_CASE(3, 1, false, true) HCA_TC_CASE(3, 2, true, true)
+#undef HCA_TC_CASE
+  static bool attr_set[3][3] = {};
+  if (!attr_set[P - 1][combo]) {
+    HCA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048));
+    attr_set[P - 1][combo] = true;
+  }
+  fn<<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, tmD, p);
   HCA_LAUNCHED();
   return 0;
 }

@@ -45,6 +45,8 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
 int launch_split_planes(const float* src, int64_t ld, int64_t rows, int cols, __nv_bfloat16* planes, int64_t ldp,
                         int64_t plane_stride, int P, cudaStream_t s);
 
-bool tc_available();   // TMA descriptor encoder resolved from the driver
+bool tc_available();
+// debug: record per-CTA clock64 stamps of the next gemm_tc launches into buf [nctas][8] (nullptr disables)
+void tc_set_timeline(long long* buf, int nctas);   // TMA descriptor encoder resolved from the driver
 
 }  // namespace hca
