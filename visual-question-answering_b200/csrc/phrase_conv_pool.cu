@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "gemm_ffma.cuh"
 #include "dense.cuh"
+#include "gemm_tc.cuh"
 #include "util_kernels.cuh"
 
 namespace hca {
@@ -69,9 +70,15 @@ __global__ void __launch_bounds__(256) repack_conv_w_kernel(const float* __restr
   }
 }
 
-// cat [R, 3E] (post tanh) -> out [R, E], idx [R, E]; rows t >= len zeroed
+// Max-pool argmax must match the reference bit for bit, but the tensor-core conv (bf16x3 operand split, fp32 TMEM
+// accumulation) carries ~3e-6 of error.  So the pool kernel records every element whose top-2 gap is below TIE_TOL
+// (two orders of magnitude above that error) and fixup_ties_kernel recomputes just those elements in exact fp32.
+constexpr float TIE_TOL = 2e-4f;
+
+// cat [R, 3E] (post tanh) -> out [R, E], idx [R, E]; rows t >= len zeroed.  tie_list/tie_count may be null.
 __global__ void __launch_bounds__(256) pool3_fwd_kernel(const float* __restrict__ cat, const int64_t* __restrict__ lens,
-                                                        float* __restrict__ out, uint8_t* __restrict__ idx, int B, int T, int E) {
+                                                        float* __restrict__ out, uint8_t* __restrict__ idx, int B, int T, int E,
+                                                        int* __restrict__ tie_list, int* __restrict__ tie_count, int tie_cap) {
   const int64_t total = (int64_t)B * T * E;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / E;
@@ -86,9 +93,54 @@ __global__ void __launch_bounds__(256) pool3_fwd_kernel(const float* __restrict_
       // MaxPool2d semantics: a later element wins only if strictly greater, or is NaN
       if (v1 > best || v1 != v1) { best = v1; bi = 1; }
       if (v2 > best || v2 != v2) { best = v2; bi = 2; }
+      if (tie_list) {
+        const float lo = fminf(fminf(v0, v1), v2);
+        const float mid = v0 + v1 + v2 - best - lo;            // middle value (approximate is fine: only a trigger)
+        if (best - mid < TIE_TOL) {
+          const int slot = atomicAdd(tie_count, 1);
+          if (slot < tie_cap) tie_list[slot] = (int)i;
+        }
+      }
     }
     out[i] = best;
     idx[i] = (uint8_t)bi;
+  }
+}
+
+// one warp per listed element: the three pre-activations of its channel triple in plain fp32, then tanh and the max again
+__global__ void __launch_bounds__(256) fixup_ties_kernel(const int* __restrict__ tie_list, const int* __restrict__ tie_count, int tie_cap,
+                                                         const float* __restrict__ acat, const float* __restrict__ w1,
+                                                         const float* __restrict__ wr2, const float* __restrict__ wr3,
+                                                         const float* __restrict__ b1, const float* __restrict__ b2,
+                                                         const float* __restrict__ b3, float* __restrict__ out,
+                                                         uint8_t* __restrict__ idx, int E) {
+  const int n = min(*tie_count, tie_cap);
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += warps) {
+    const int i = tie_list[w];
+    const int64_t r = i / E;
+    const int e = i - (int)r * E;
+    float v[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int c = 3 * e + j;                    // channel of the concatenated [uni|bi|tri] axis
+      const int k = c / E + 1, o = c % E;         // which conv, which output channel
+      const float* wrow = (k == 1 ? w1 : (k == 2 ? wr2 : wr3)) + (int64_t)o * k * E;
+      const float* arow = acat + r * 3 * (int64_t)E + (k == 1 ? E : 0);
+      float acc = 0.f;
+      for (int kk = lane; kk < k * E; kk += 32) acc = fmaf(arow[kk], wrow[kk], acc);
+      acc = warp_sum(acc);
+      v[j] = tanhf(acc + (k == 1 ? b1 : (k == 2 ? b2 : b3))[o]);
+    }
+    float best = v[0];
+    int bi = 0;
+    if (v[1] > best || v[1] != v[1]) { best = v[1]; bi = 1; }
+    if (v[2] > best || v[2] != v[2]) { best = v[2]; bi = 2; }
+    if (lane == 0) {
+      out[i] = best;
+      idx[i] = (uint8_t)bi;
+    }
   }
 }
 
@@ -119,6 +171,8 @@ __global__ void __launch_bounds__(256) pool3_bwd_kernel(const float* __restrict_
 struct ConvWs {
   Workspace w;
   float *acat, *cat, *dA, *wr2, *wr3, *dwr2, *dwr3;
+  int *tie_count, *tie_list;
+  int tie_cap;
   bool ok;
   ConvWs(void* p, size_t bytes) : w(p, bytes) {}
 };
@@ -133,7 +187,10 @@ ConvWs carve(void* ws, size_t bytes, int B, int T, int E) {
   c.wr3 = w.take<float>((size_t)E * 3 * E);
   c.dwr2 = w.take<float>((size_t)E * 2 * E);
   c.dwr3 = w.take<float>((size_t)E * 3 * E);
-  c.ok = c.dwr3 != nullptr;
+  c.tie_cap = (int)(R * E / 8 + 1024);
+  c.tie_count = w.take<int>(64);
+  c.tie_list = w.take<int>((size_t)c.tie_cap);
+  c.ok = c.tie_list != nullptr;
   return c;
 }
 
@@ -143,7 +200,10 @@ ConvWs carve(void* ws, size_t bytes, int B, int T, int E) {
 extern "C" size_t hca_phrase_conv_pool_workspace(int B, int T, int E) {
   using hca::align_up;
   const size_t R = (size_t)B * T;
-  return 3 * align_up(R * 3 * E * 4) + 2 * (align_up((size_t)E * 2 * E * 4) + align_up((size_t)E * 3 * E * 4)) + 256 +
+  return 3 * align_up(R * 3 * E * 4) + 2 * (align_up((size_t)E * 2 * E * 4) + align_up((size_t)E * 3 * E * 4)) + 1024 +
+         align_up((R * E / 8 + 1024) * 4) +                                             // near-tie list
+         3 * 2 * (align_up(R * 3 * E) + 3 * align_up((size_t)E * 3 * E)) +               // bf16x3 planes of Acat and the weights
+
          std::max(hca::dense_scratch_bytes(E, 3 * E, (int)R), hca::dense_scratch_bytes((int)R, 3 * E, E));
 }
 
@@ -163,9 +223,37 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
   HCA_LAUNCHED();
   repack_conv_w_kernel<<<ew_grid((int64_t)E * E * 3), 256, 0, s>>>(w3, c.wr3, E, 3, false);
   HCA_LAUNCHED();
-  // three exact-fp32 GEMMs, bias + tanh fused, writing the column blocks of cat [R, 3E]
   const float* wr[3] = {w1, c.wr2, c.wr3};
   const float* bs[3] = {b1, b2, b3};
+  const bool tc = use_tc() && tc_available() && (E % 8 == 0);      // TMA needs 16-byte aligned plane windows
+  if (tc) {
+    // tensor cores, bf16x3 operand split (6 MMAs per product, fp32-grade): Acat is split once and the three convs read
+    // column windows of its planes; bias + tanh fused in the epilogue; near-ties are repaired exactly below
+    const int P = 3;
+    const int64_t lda = 3 * (int64_t)E, a_stride = (int64_t)R * lda;
+    __nv_bfloat16* ap = c.w.take<__nv_bfloat16>((size_t)P * a_stride);
+    if (!ap) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for operand planes");
+    HCA_TRY(launch_split_planes(c.acat, lda, R, 3 * E, ap, lda, a_stride, P, s));
+    for (int k = 1; k <= 3; ++k) {
+      const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
+      __nv_bfloat16* wp = c.w.take<__nv_bfloat16>((size_t)P * w_stride);
+      if (!wp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for weight planes");
+      HCA_TRY(launch_split_planes(wr[k - 1], ldw, E, k * E, wp, ldw, w_stride, P, s));
+      TcOperand A, Bw;
+      A.planes = ap + (k == 1 ? E : 0); A.ld = lda; A.plane_stride = a_stride; A.rows = R; A.cols = k * E;
+      Bw.planes = wp; Bw.ld = ldw; Bw.plane_stride = w_stride; Bw.rows = E; Bw.cols = k * E;
+      TcEpilogue ep;
+      ep.D = c.cat + (k - 1) * E; ep.ldd = lda; ep.bias = bs[k - 1]; ep.act_tanh = 1;
+      HCA_TRY(launch_gemm_tc(A, Bw, P, R, E, k * E, ep, 1, s));
+    }
+    HCA_TRY(zero_async(c.tie_count, sizeof(int), s));
+    pool3_fwd_kernel<<<ew_grid((int64_t)R * E), 256, 0, s>>>(c.cat, lens, out, idx, B, T, E, c.tie_list, c.tie_count, c.tie_cap);
+    HCA_LAUNCHED();
+    fixup_ties_kernel<<<148 * 2, 256, 0, s>>>(c.tie_list, c.tie_count, c.tie_cap, c.acat, w1, c.wr2, c.wr3, b1, b2, b3, out, idx, E);
+    HCA_LAUNCHED();
+    return 0;
+  }
+  // exact-fp32 CUDA-core path: three GEMMs, bias + tanh fused, writing the column blocks of cat [R, 3E]
   for (int k = 1; k <= 3; ++k) {
     GemmParams g;
     const int a_off = (k == 1) ? E : 0;
@@ -177,7 +265,7 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
     g.act_tanh = 1;
     HCA_TRY(launch_gemm_ffma(g, true, s));
   }
-  pool3_fwd_kernel<<<ew_grid((int64_t)R * E), 256, 0, s>>>(c.cat, lens, out, idx, B, T, E);
+  pool3_fwd_kernel<<<ew_grid((int64_t)R * E), 256, 0, s>>>(c.cat, lens, out, idx, B, T, E, nullptr, nullptr, 0);
   HCA_LAUNCHED();
   return 0;
 }
