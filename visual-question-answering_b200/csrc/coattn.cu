@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "dense.cuh"
 #include "gemm_ffma.cuh"
+#include "gemm_tc.cuh"
 #include "util_kernels.cuh"
 
 namespace hca {
@@ -150,6 +151,198 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const float* __restr
 }
 
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// tensor-core path: every contraction of the module on tcgen05 with bf16x2 operand planes (gemm_tc.cuh).  Per-sample
+// products are batched launches (grid.z = level * B + sample); image-side operands are shared across levels through
+// the batch modulo of the TMA batch coordinate.
+constexpr int TCP = 2;    // planes
+
+struct Planes {
+  __nv_bfloat16* p = nullptr;
+  int64_t ld = 0, plane_stride = 0;
+  int64_t rows = 0;
+  int cols = 0;
+};
+
+inline int64_t round8(int64_t x) { return (x + 7) / 8 * 8; }
+
+// allocate planes for an fp32 matrix [rows, cols] (rows may be filled by several split launches)
+int alloc_planes(Planes& pl, int64_t rows, int cols, Workspace& w) {
+  pl.ld = round8(cols);
+  pl.rows = rows;
+  pl.cols = cols;
+  pl.plane_stride = rows * pl.ld;
+  pl.p = w.take<__nv_bfloat16>((size_t)TCP * pl.plane_stride);
+  if (!pl.p) return set_err(HCA_ERR_WORKSPACE, "coattn: workspace too small for bf16 operand planes (%lld x %d)", (long long)rows, cols);
+  return 0;
+}
+int fill_planes(const Planes& pl, const float* src, int64_t ld, int64_t row0, int64_t rows, cudaStream_t s) {
+  return launch_split_planes(src, ld, rows, pl.cols, pl.p + row0 * pl.ld, pl.ld, pl.plane_stride, TCP, s);
+}
+int make_planes(Planes& pl, const float* src, int64_t ld, int64_t rows, int cols, Workspace& w, cudaStream_t s) {
+  HCA_TRY(alloc_planes(pl, rows, cols, w));
+  return fill_planes(pl, src, ld, 0, rows, s);
+}
+// batched view: entry z = rows [row0 + z * rows_per_batch, +rows_per_batch) of the plane matrix
+TcOperand view(const Planes& pl, int64_t row0, int rows_per_batch, int nbatch, bool mn_major) {
+  TcOperand o;
+  o.planes = pl.p + row0 * pl.ld;
+  o.ld = pl.ld;
+  o.plane_stride = pl.plane_stride;
+  o.batch_stride = (int64_t)rows_per_batch * pl.ld;
+  o.nbatch = nbatch;
+  o.rows = rows_per_batch;
+  o.cols = pl.cols;
+  o.mn_major = mn_major;
+  return o;
+}
+
+bool tc_path_ok(int N, int d) { return use_tc() && tc_available() && (d % 8 == 0) && (N % 4 == 0); }
+
+int tc_splitk(int M, int N, int K) {
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  if (tiles >= 96) return 1;
+  int sk = (148 + tiles - 1) / tiles;
+  const int maxk = (K + 255) / 256;
+  if (sk > maxk) sk = maxk;
+  return sk < 1 ? 1 : sk;
+}
+
+struct CoattnPlanes {
+  Planes V, Q, C, PV, PQ, Wv, Wq;
+};
+
+// planes every direction needs: V, the three question levels stacked [3*B*T, d], and the two projection weights
+int common_planes(CoattnPlanes& cp, const float* Vd, const float* const q[3], const float* Wv, const float* Wq, int B, int N, int T,
+                  int d, Workspace& w, cudaStream_t s) {
+  const int64_t BT = (int64_t)B * T;
+  HCA_TRY(make_planes(cp.V, Vd, d, (int64_t)B * N, d, w, s));
+  HCA_TRY(alloc_planes(cp.Q, 3 * BT, d, w));
+  for (int l = 0; l < 3; ++l) HCA_TRY(fill_planes(cp.Q, q[l], d, l * BT, BT, s));
+  HCA_TRY(make_planes(cp.Wv, Wv, d, d, d, w, s));
+  HCA_TRY(make_planes(cp.Wq, Wq, d, d, d, w, s));
+  return 0;
+}
+
+int coattn_fwd_tc(const float* Vd, const float* const q[3], const float* Wv, const float* bv, const float* Wq, const float* bq,
+                  const float* wv, const float* wq, float* PV, float* PQ, float* C, float* sv, float* sq, int B, int N, int T, int d,
+                  Workspace& w, cudaStream_t s) {
+  const int64_t BT = (int64_t)B * T, BN = (int64_t)B * N;
+  CoattnPlanes cp;
+  HCA_TRY(common_planes(cp, Vd, q, Wv, Wq, B, N, T, d, w, s));
+  {  // PV = V Wv^T + bv   (once per step: level independent)
+    TcEpilogue e; e.D = PV; e.ldd = d; e.bias = bv;
+    HCA_TRY(launch_gemm_tc(view(cp.V, 0, (int)BN, 1, false), view(cp.Wv, 0, d, 1, false), TCP, (int)BN, d, d, e, 1, s));
+  }
+  {  // PQ = Q Wq^T + bq   (the three levels in one launch)
+    TcEpilogue e; e.D = PQ; e.ldd = d; e.bias = bq;
+    HCA_TRY(launch_gemm_tc(view(cp.Q, 0, (int)(3 * BT), 1, false), view(cp.Wq, 0, d, 1, false), TCP, (int)(3 * BT), d, d, e, 1, s));
+  }
+  {  // C[z] = tanh(Q[z] V[b]^T)
+    TcEpilogue e; e.D = C; e.ldd = N; e.d_batch_stride = (int64_t)T * N; e.act_tanh = 1;
+    HCA_TRY(launch_gemm_tc(view(cp.Q, 0, T, 3 * B, false), view(cp.V, 0, N, B, false), TCP, T, N, d, e, 1, s, 3 * B));
+  }
+  HCA_TRY(make_planes(cp.C, C, N, 3 * BT, N, w, s));
+  HCA_TRY(make_planes(cp.PV, PV, d, BN, d, w, s));
+  HCA_TRY(make_planes(cp.PQ, PQ, d, 3 * BT, d, w, s));
+  {  // sq[z][t] = sum_j tanh(PQ + C PV)[t][j] wq[j]
+    TcEpilogue e; e.mode = TC_EPI_ROWDOT; e.act_tanh = 1; e.colv = wq; e.red_row = sq; e.red_row_batch_stride = T;
+    e.aux = PQ; e.aux_ld = d; e.aux_batch_stride = (int64_t)T * d; e.aux_nbatch = 3 * B; e.aux_mode = TC_AUX_ADD;
+    HCA_TRY(launch_gemm_tc(view(cp.C, 0, T, 3 * B, false), view(cp.PV, 0, N, B, true), TCP, T, d, N, e, 1, s, 3 * B));
+  }
+  {  // sv[z][n] = sum_j tanh(PV + C^T PQ)[n][j] wv[j]
+    TcEpilogue e; e.mode = TC_EPI_ROWDOT; e.act_tanh = 1; e.colv = wv; e.red_row = sv; e.red_row_batch_stride = N;
+    e.aux = PV; e.aux_ld = d; e.aux_batch_stride = (int64_t)N * d; e.aux_nbatch = B; e.aux_mode = TC_AUX_ADD;
+    HCA_TRY(launch_gemm_tc(view(cp.C, 0, T, 3 * B, true), view(cp.PQ, 0, T, 3 * B, true), TCP, N, d, T, e, 1, s, 3 * B));
+  }
+  return 0;
+}
+
+int coattn_bwd_tc(const float* Vd, const float* const q[3], const float* Wv, const float* Wq, const float* wv, const float* wq,
+                  const float* PV, const float* PQ, const float* C, const float* av, const float* aq, const float* gvhat,
+                  const float* gqhat, const float* dsv, const float* dsq, float* dZv, float* dZq, float* dPQ, float* dPV, float* dS,
+                  float* dV, float* dQ, float* dWv, float* dbv, float* dWq, float* dbq, float* dwv, float* dwq, int B, int N, int T,
+                  int d, Workspace& w, cudaStream_t s) {
+  const int64_t BT = (int64_t)B * T, BN = (int64_t)B * N;
+  CoattnPlanes cp;
+  HCA_TRY(common_planes(cp, Vd, q, Wv, Wq, B, N, T, d, w, s));
+  HCA_TRY(make_planes(cp.C, C, N, 3 * BT, N, w, s));
+  HCA_TRY(make_planes(cp.PV, PV, d, BN, d, w, s));
+  HCA_TRY(make_planes(cp.PQ, PQ, d, 3 * BT, d, w, s));
+  {  // dZv = (dsv x wv) * (1 - Hv^2), Hv = tanh(PV + C^T PQ) recomputed ; dwv += Hv^T dsv
+    TcEpilogue e; e.mode = TC_EPI_DZ; e.act_tanh = 1; e.colv = wv; e.rowv = dsv; e.rowv_batch_stride = N; e.red_col = dwv;
+    e.aux = PV; e.aux_ld = d; e.aux_batch_stride = (int64_t)N * d; e.aux_nbatch = B; e.aux_mode = TC_AUX_ADD;
+    e.D = dZv; e.ldd = d; e.d_batch_stride = (int64_t)N * d;
+    HCA_TRY(launch_gemm_tc(view(cp.C, 0, T, 3 * B, true), view(cp.PQ, 0, T, 3 * B, true), TCP, N, d, T, e, 1, s, 3 * B));
+  }
+  {  // dZq likewise from Hq = tanh(PQ + C PV)
+    TcEpilogue e; e.mode = TC_EPI_DZ; e.act_tanh = 1; e.colv = wq; e.rowv = dsq; e.rowv_batch_stride = T; e.red_col = dwq;
+    e.aux = PQ; e.aux_ld = d; e.aux_batch_stride = (int64_t)T * d; e.aux_nbatch = 3 * B; e.aux_mode = TC_AUX_ADD;
+    e.D = dZq; e.ldd = d; e.d_batch_stride = (int64_t)T * d;
+    HCA_TRY(launch_gemm_tc(view(cp.C, 0, T, 3 * B, false), view(cp.PV, 0, N, B, true), TCP, T, d, N, e, 1, s, 3 * B));
+  }
+  Planes pZv, pZq, pS, pPQg, pPVg;
+  HCA_TRY(make_planes(pZv, dZv, d, 3 * BN, d, w, s));
+  HCA_TRY(make_planes(pZq, dZq, d, 3 * BT, d, w, s));
+  {  // dPQ = dZq + C dZv
+    TcEpilogue e; e.D = dPQ; e.ldd = d; e.d_batch_stride = (int64_t)T * d;
+    e.aux = dZq; e.aux_ld = d; e.aux_batch_stride = (int64_t)T * d; e.aux_nbatch = 3 * B; e.aux_mode = TC_AUX_ADD;
+    HCA_TRY(launch_gemm_tc(view(cp.C, 0, T, 3 * B, false), view(pZv, 0, N, 3 * B, true), TCP, T, d, N, e, 1, s, 3 * B));
+  }
+  for (int l = 0; l < 3; ++l) {  // dPV = sum_l dZv_l + C_l^T dZq_l
+    TcEpilogue e; e.D = dPV; e.ldd = d; e.d_batch_stride = (int64_t)N * d; e.accumulate = (l > 0);
+    e.aux = dZv + l * BN * d; e.aux_ld = d; e.aux_batch_stride = (int64_t)N * d; e.aux_nbatch = B; e.aux_mode = TC_AUX_ADD;
+    HCA_TRY(launch_gemm_tc(view(cp.C, l * BT, T, B, true), view(pZq, l * BT, T, B, true), TCP, N, d, T, e, 1, s, B));
+  }
+  {  // dS = (PQ dZv^T + dZq PV^T) * (1 - C^2): two operand pairs chained along K in one accumulator
+    TcEpilogue e; e.D = dS; e.ldd = N; e.d_batch_stride = (int64_t)T * N;
+    e.aux = C; e.aux_ld = N; e.aux_batch_stride = (int64_t)T * N; e.aux_nbatch = 3 * B; e.aux_mode = TC_AUX_MUL_1MX2;
+    const TcOperand a2 = view(pZq, 0, T, 3 * B, false), b2 = view(cp.PV, 0, N, B, false);
+    HCA_TRY(launch_gemm_tc(view(cp.PQ, 0, T, 3 * B, false), view(pZv, 0, N, 3 * B, false), TCP, T, N, d, e, 1, s, 3 * B, &a2, &b2, d));
+  }
+  HCA_TRY(make_planes(pS, dS, N, 3 * BT, N, w, s));
+  {  // dQ = dS V + aq x gq
+    TcEpilogue e; e.D = dQ; e.ldd = d; e.d_batch_stride = (int64_t)T * d;
+    e.rowv = aq; e.rowv_batch_stride = T; e.r1col = gqhat; e.r1col_batch_stride = d;
+    HCA_TRY(launch_gemm_tc(view(pS, 0, T, 3 * B, false), view(cp.V, 0, N, B, true), TCP, T, d, N, e, 1, s, 3 * B));
+  }
+  HCA_TRY(make_planes(pPQg, dPQ, d, 3 * BT, d, w, s));
+  {  // dQ += dPQ Wq
+    TcEpilogue e; e.D = dQ; e.ldd = d; e.accumulate = 1;
+    HCA_TRY(launch_gemm_tc(view(pPQg, 0, (int)(3 * BT), 1, false), view(cp.Wq, 0, d, 1, true), TCP, (int)(3 * BT), d, d, e, 1, s));
+  }
+  {  // dWq = dPQ^T Q over batch, time and the three levels at once (K = 3*B*T, split-K)
+    const int sk = tc_splitk(d, d, (int)(3 * BT));
+    if (sk > 1) HCA_TRY(zero_async(dWq, (size_t)d * d * 4, s));
+    TcEpilogue e; e.D = dWq; e.ldd = d;
+    HCA_TRY(launch_gemm_tc(view(pPQg, 0, (int)(3 * BT), 1, true), view(cp.Q, 0, (int)(3 * BT), 1, true), TCP, d, d, (int)(3 * BT), e, sk, s));
+  }
+  HCA_TRY(zero_async(dbq, (size_t)d * 4, s));
+  HCA_TRY(launch_colsum(dPQ, d, 3 * BT, d, dbq, s));
+  HCA_TRY(make_planes(pPVg, dPV, d, BN, d, w, s));
+  {  // dWv = dPV^T V   (K = B*N, split-K)
+    const int sk = tc_splitk(d, d, (int)BN);
+    if (sk > 1) HCA_TRY(zero_async(dWv, (size_t)d * d * 4, s));
+    TcEpilogue e; e.D = dWv; e.ldd = d;
+    HCA_TRY(launch_gemm_tc(view(pPVg, 0, (int)BN, 1, true), view(cp.V, 0, (int)BN, 1, true), TCP, d, d, (int)BN, e, sk, s));
+  }
+  HCA_TRY(zero_async(dbv, (size_t)d * 4, s));
+  HCA_TRY(launch_colsum(dPV, d, BN, d, dbv, s));
+  if (dV) {  // only when the image features require grad (--vgg_train true)
+    {
+      TcEpilogue e; e.D = dV; e.ldd = d;
+      HCA_TRY(launch_gemm_tc(view(pPVg, 0, (int)BN, 1, false), view(cp.Wv, 0, d, 1, true), TCP, (int)BN, d, d, e, 1, s));
+    }
+    for (int l = 0; l < 3; ++l) {  // dV += dS_l^T Q_l + av_l x gv_l
+      TcEpilogue e; e.D = dV; e.ldd = d; e.d_batch_stride = (int64_t)N * d; e.accumulate = 1;
+      e.rowv = av + l * BN; e.rowv_batch_stride = N; e.r1col = gvhat + (int64_t)l * B * d; e.r1col_batch_stride = d;
+      HCA_TRY(launch_gemm_tc(view(pS, l * BT, T, B, true), view(cp.Q, l * BT, T, B, true), TCP, N, d, T, e, 1, s, B));
+    }
+  }
+  return 0;
+}
+
 bool v_is_dense(int64_t sb, int64_t sn, int64_t sd, int N, int d) { return sd == 1 && sn == d && sb == (int64_t)N * d; }
 
 }  // namespace
@@ -171,7 +364,9 @@ extern "C" size_t hca_coattn_workspace(int B, int N, int T, int d, int need_dv) 
   sc = std::max(sc, hca::dense_scratch_bytes((int)(3 * b * T), d, d));        // dQ += dPQ Wq
   sc = std::max(sc, hca::dense_scratch_bytes(d, d, (int)(b * T)));            // dWq
   s += sc;
-  return s + 1024;
+  // tensor-core path: bf16x2 planes of V, Q, C, PV, PQ, dZv, dZq, dS, dPQ, dPV and the two weights
+  const size_t pl = 2 * 2 * (6 * b * N * d + 12 * b * T * d + 6 * b * T * (N + 8) + 2 * (size_t)d * d) + 64 * 256;
+  return s + pl + 1024;
 }
 
 extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_t v_sd, const float* q0, const float* q1,
@@ -199,6 +394,15 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
   if (!sv || !sq) return set_err(HCA_ERR_WORKSPACE, "coattn_fwd: workspace too small");
   const float* q[3] = {q0, q1, q2};
   const int64_t BT = (int64_t)B * T, BN = (int64_t)B * N;
+  if (tc_path_ok(N, d)) {
+    HCA_TRY(zero_async(sv, (size_t)3 * B * N * 4, s));
+    HCA_TRY(zero_async(sq, (size_t)3 * B * T * 4, s));
+    HCA_TRY(coattn_fwd_tc(Vd, q, Wv, bv, Wq, bq, wv, wq, PV, PQ, C, sv, sq, B, N, T, d, w, s));
+    const size_t smem_tc = (64 + (size_t)max(N, T)) * sizeof(float);
+    attn_finish_kernel<<<3 * B, 256, smem_tc, s>>>(sv, sq, cv, cq, Vd, q0, q1, q2, av, aq, vhat, qhat, B, N, T, d);
+    HCA_LAUNCHED();
+    return 0;
+  }
 
   // projections
   {
@@ -286,6 +490,9 @@ extern "C" int hca_coattn_bwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
   const size_t smem = (64 + (size_t)max(N, T)) * sizeof(float);
   attn_bwd_prep_kernel<<<3 * B, 256, smem, s>>>(av, aq, Vd, q0, q1, q2, gvhat, gqhat, dsv, dsq, dcv, dcq, B, N, T, d);
   HCA_LAUNCHED();
+  if (tc_path_ok(N, d))
+    return coattn_bwd_tc(Vd, q, Wv, Wq, wv, wq, PV, PQ, C, av, aq, gvhat, gqhat, dsv, dsq, dZv, dZq, dPQ, dPV, dS, dV, dQ, dWv, dbv,
+                         dWq, dbq, dwv, dwq, B, N, T, d, w, s);
   {  // dZv = (dsv x wv) * (1 - Hv^2), Hv recomputed; dwv += Hv^T dsv
     GemmParams g;
     g.A = {C, (int64_t)T * N, 1, N, 0};

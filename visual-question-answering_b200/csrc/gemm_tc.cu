@@ -16,16 +16,23 @@ constexpr int NUM_THREADS = 192;      // warp 0 TMA, warp 1 MMA + TMEM alloc, wa
 constexpr int SMEM_BUDGET = 200 * 1024;
 
 struct TcParams {
-  int M, N, K, P, a_mn, b_mn, stages, kb_total, kb_per_split;
+  int M, N, K, stages, kb_total, kb_per_split, kb1, splitk;
+  // epilogue
   float* D;
-  int64_t ldd;
-  const float* bias;
+  int64_t ldd, d_sb;
+  const float* bias; int64_t bias_sb;
   int act_tanh;
-  const float* mulx;
-  int64_t mulx_ld;
+  const float* mulx; int64_t mulx_ld;
   int accumulate, atomic;
   int tma_store;            // epilogue goes through smem + TMA tile store (D 16-byte aligned, ldd % 4 == 0)
-  int dbg;                  // debug bit flags (HCA_TC_DBG): 1 = no TMA (MMA on garbage), 2 = sleepy epilogue wait, 4 = no stores
+  int mode, aux_mode, aux_nbatch;
+  const float* rowv; int64_t rowv_sb;
+  const float* colv;
+  const float* r1col; int64_t r1col_sb;
+  float* red_row; int64_t red_row_sb;
+  float* red_col;
+  int a_nb, b_nb, a2_nb, b2_nb;   // batch entries of each operand (entry = z % nb)
+  int dbg;                  // debug bit flags (HCA_TC_DBG): 1 = no TMA (MMA on garbage), 2 = sleepy epilogue wait
   long long* timeline;      // optional [ncta][64] clock64 stamps (debug / profiling), nullptr normally
   int timeline_ctas;
 };
@@ -71,14 +78,21 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // TMA tile store / reduce-add from shared memory (bulk async group completion)
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2)
                : "memory");
 }
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src),
-               "r"(c0), "r"(c1)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -175,30 +189,38 @@ __device__ __forceinline__ uint64_t tile_desc(uint32_t tile_addr, int mn_major, 
 __device__ __forceinline__ float tanh_acc(float x) { return tanhf(x); }
 
 // ------------------------------------------------------------------------------------------------------ kernel
+struct TcMaps {            // all TMA descriptors of one launch (operands 4-D: cols, rows, plane, batch; D / aux 3-D: N, M, batch)
+  CUtensorMap A, B, A2, B2, D, AUX;
+};
+
 template <int BN, int P, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmD, const TcParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   constexpr int B_TILE_BYTES = BN * BK * 2;
+  constexpr uint32_t stage_bytes = P * (A_TILE_BYTES + B_TILE_BYTES);
+  constexpr int CHUNKS = BN / 32;
+  constexpr uint32_t CHUNK_BYTES = BM * 128;           // one [128 rows][32 fp32] staging tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
-  constexpr uint32_t stage_bytes = P * (A_TILE_BYTES + B_TILE_BYTES);
-  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 2];
   __shared__ uint32_t tmem_ptr_smem;
-  __shared__ __align__(16) float bias_sm[BN];           // this tile's bias slice, staged once by the epilogue warps
+  __shared__ __align__(16) float bias_sm[BN];          // this tile's bias slice (per batch entry)
+  __shared__ __align__(16) float colv_sm[BN];          // colv (ROWDOT / DZ) or the rank-1 column vector
+  __shared__ float colred_sm[BN];                      // DZ: column partial sums of the four epilogue warps
 
   // warp index through a shuffle: provably warp-uniform for ptxas, so the role branches below are uniform control flow and
   // the MMA descriptors live in uniform registers (otherwise every tcgen05.mma pays an ELECT + VOTEU + 4x R2UR.BROADCAST
   // sequence, ~250 cycles per instruction, measured)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int z = blockIdx.z / p.splitk, ksplit = blockIdx.z - z * p.splitk;
+  const int kb_begin = ksplit * p.kb_per_split;
   const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
   const int num_kb = kb_end - kb_begin;
 
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[MAX_STAGES + s]); };
   const uint32_t tmem_full_bar = smem_u32(&bars[2 * MAX_STAGES]);
+  const uint32_t aux_bar = smem_u32(&bars[2 * MAX_STAGES + 1]);
   auto a_tile = [&](int s, int pl) { return smem_base + s * stage_bytes + pl * A_TILE_BYTES; };
   auto b_tile = [&](int s, int pl) { return smem_base + s * stage_bytes + P * A_TILE_BYTES + pl * B_TILE_BYTES; };
 
@@ -216,10 +238,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(aux_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.A) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.B) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.D) : "memory");
+    if (p.aux_mode) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.AUX) : "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr_smem), BN);       // BN fp32 accumulator columns (power of two >= 32)
   tc_fence_before();
@@ -237,20 +261,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(empty_bar(s), ph ^ 1, 1);
         if (tl && it < 12) tl[8 + it] = clock64();          // producer: slot free, issuing TMA for k-block `it`
         mbar_expect_tx(full_bar(s), stage_bytes);
-        const int k0 = (kb_begin + it) * BK;
+        const int kb = kb_begin + it;
+        const bool second = kb >= p.kb1;                    // chained second operand pair
+        const CUtensorMap* ma = second ? &maps.A2 : &maps.A;
+        const CUtensorMap* mb = second ? &maps.B2 : &maps.B;
+        const int za = z % (second ? p.a2_nb : p.a_nb), zb = z % (second ? p.b2_nb : p.b_nb);
+        const int k0 = (second ? kb - p.kb1 : kb) * BK;
 #pragma unroll
         for (int pl = 0; pl < P; ++pl) {
           if (!A_MN) {
-            tma_load_3d(a_tile(s, pl), &tmA, full_bar(s), k0, m0, pl);
+            tma_load_4d(a_tile(s, pl), ma, full_bar(s), k0, m0, pl, za);
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_3d(a_tile(s, pl) + c * 8192, &tmA, full_bar(s), m0 + c * 64, k0, pl);
+            for (int c = 0; c < BM / 64; ++c) tma_load_4d(a_tile(s, pl) + c * 8192, ma, full_bar(s), m0 + c * 64, k0, pl, za);
           }
           if (!B_MN) {
-            tma_load_3d(b_tile(s, pl), &tmB, full_bar(s), k0, n0, pl);
+            tma_load_4d(b_tile(s, pl), mb, full_bar(s), k0, n0, pl, zb);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_3d(b_tile(s, pl) + c * 8192, &tmB, full_bar(s), n0 + c * 64, k0, pl);
+            for (int c = 0; c < BN / 64; ++c) tma_load_4d(b_tile(s, pl) + c * 8192, mb, full_bar(s), n0 + c * 64, k0, pl, zb);
           }
         }
         if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -279,7 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         if (tl && lane == 0 && it == 0) tl[2] = clock64();
         if (tl && lane == 0 && it < 12) tl[24 + it] = clock64();         // MMA warp: k-block `it` landed
-        // shuffle-broadcast: tells ptxas the stage base is warp-uniform, so the 12 descriptor variants below are
+        // shuffle-broadcast: tells ptxas the stage base is warp-uniform, so the descriptor variants below are
         // uniform-register adds of compile-time constants
         const uint32_t au = __shfl_sync(0xffffffffu, a0, 0), bu = __shfl_sync(0xffffffffu, b0, 0);
         const uint32_t first = __shfl_sync(0xffffffffu, it == 0 ? 0u : 1u, 0);
@@ -309,14 +338,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (tl && lane == 0) tl[3] = clock64();
     }
   } else {
-    // ===================================================================== epilogue: TMEM -> registers -> global
+    // ===================================================================== epilogue: TMEM -> registers -> (smem -> TMA) global
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int row = m0 + q * 32 + lane;
-    {                                       // stage the bias slice while the mainloop runs
-      const int t = threadIdx.x - 64;       // 0..127
-      for (int j = t; j < BN; j += 128) bias_sm[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+    const int r = q * 32 + lane;            // row inside the tile
+    const int row = m0 + r;
+    const bool row_ok = row < p.M;
+    const int et = threadIdx.x - 64;        // 0..127
+    {                                       // stage the per-column vectors while the mainloop runs
+      const float* bias = p.bias ? p.bias + (int64_t)z * p.bias_sb : nullptr;
+      const float* cvec = p.r1col ? p.r1col + (int64_t)z * p.r1col_sb : p.colv;
+      for (int j = et; j < BN; j += 128) {
+        const bool ok = n0 + j < p.N;
+        bias_sm[j] = (bias && ok) ? __ldg(bias + n0 + j) : 0.f;
+        colv_sm[j] = (cvec && ok) ? __ldg(cvec + n0 + j) : 0.f;
+        colred_sm[j] = 0.f;
+      }
       epi_barrier();
     }
+    const float rv = (p.rowv && row_ok) ? __ldg(p.rowv + (int64_t)z * p.rowv_sb + row) : 0.f;
     if (p.dbg & 2) {
       while (!mbar_try_wait(tmem_full_bar, 0)) __nanosleep(500);
     } else {
@@ -324,56 +363,97 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_after();
     if (tl && threadIdx.x == 64) tl[4] = clock64();
-    const bool row_ok = row < p.M;
-    float* drow = p.D + (int64_t)row * p.ldd;
+    const bool leader = (warp == 2 && lane == 0);
+    const int nchunks = min(CHUNKS, (p.N - n0 + 31) / 32);           // uniform across the CTA
+    // staging layout inside the (now idle) pipeline stages: [0, 2*CHUNK) store tiles, then one aux tile per chunk
+    const uint32_t store_buf0 = smem_base, aux_buf0 = smem_base + 2 * CHUNK_BYTES;
+    if (p.aux_mode) {                       // fetch the aux tile (pre-activation addend or (1 - x^2) factor) for all chunks at once
+      if (leader) {
+        mbar_expect_tx(aux_bar, (uint32_t)nchunks * CHUNK_BYTES);
+        for (int c = 0; c < nchunks; ++c) tma_load_3d(aux_buf0 + c * CHUNK_BYTES, &maps.AUX, aux_bar, n0 + c * 32, m0, z % p.aux_nbatch);
+      }
+      mbar_wait(aux_bar, 0, 4);
+    }
+    float* drow = p.D ? p.D + (int64_t)z * p.d_sb + (int64_t)row * p.ldd : nullptr;
     const float* xrow = p.mulx ? p.mulx + (int64_t)row * p.mulx_ld : nullptr;
-    if (p.tma_store) {
-      // Each thread owns one output row; a 32-column chunk is staged in shared memory as a [128 rows][128 B] tile in the
-      // TMA 128-byte swizzle (16-byte chunk j of row r lives at chunk j ^ (r & 7): conflict-free float4 stores), then one
-      // thread hands it to the TMA engine as a tile store (or reduce-add for accumulate / split-K).  Two staging buffers
-      // alternate; the pipeline stages are free by now (tmem_full implies every MMA has consumed its smem operands).
-      const int r = q * 32 + lane;
-      const bool leader = (warp == 2 && lane == 0);
+    float rowdot = 0.f;
+    const bool do_store = (p.mode != TC_EPI_ROWDOT);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;                                   // uniform across the CTA
-        const uint32_t stage_buf = smem_base + (uint32_t)(c & 1) * (BM * 128);
-        if (c >= 2) {                                             // buffer reuse: its previous TMA store must have read it
-          if (leader) tma_store_wait_read<1>();
-          epi_barrier();
-        }
-        if (tl && leader && c < 4) tl[52 + 3 * c] = clock64();
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        if (tl && leader && c < 4) tl[53 + 3 * c] = clock64();
-        float f[32];
-        {                                                         // bias slice of this chunk: 8 x LDS.128, no dependent chain
-          const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c * 32);
+    for (int c = 0; c < nchunks; ++c) {
+      const int col0 = n0 + c * 32;
+      const uint32_t stage_buf = store_buf0 + (uint32_t)(c & 1) * CHUNK_BYTES;
+      if (do_store && p.tma_store && c >= 2) {                    // staging buffer reuse: its previous TMA store must have read it
+        if (leader) tma_store_wait_read<1>();
+        epi_barrier();
+      }
+      uint32_t v[32];
+      __syncwarp();                                               // tcgen05.ld is warp-collective
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      float f[32];
+      {                                                           // bias slice of this chunk: 8 x LDS.128
+        const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = b4[j];
-            f[4 * j] = b.x; f[4 * j + 1] = b.y; f[4 * j + 2] = b.z; f[4 * j + 3] = b.w;
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = b4[j];
+          f[4 * j] = b.x; f[4 * j + 1] = b.y; f[4 * j + 2] = b.z; f[4 * j + 3] = b.w;
+        }
+      }
+      if (num_kb != 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+      }
+      float ax[32];
+      if (p.aux_mode) {                                           // this thread's row of the aux tile (same swizzle as the stores)
+        const uint32_t src = aux_buf0 + (uint32_t)c * CHUNK_BYTES + (uint32_t)r * 128u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(ax[4 * j]), "=f"(ax[4 * j + 1]), "=f"(ax[4 * j + 2]), "=f"(ax[4 * j + 3])
+                       : "r"(src + (uint32_t)((j ^ (r & 7)) * 16)));
+        }
+        if (p.aux_mode == TC_AUX_ADD) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += ax[j];
+        }
+      }
+      if (p.act_tanh) {                                           // uniform branches: no predicated-off code on the common path
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = tanh_acc(f[j]);
+      }
+      if (p.r1col) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaf(rv, colv_sm[c * 32 + j], f[j]);
+      }
+      if (p.aux_mode == TC_AUX_MUL_1MX2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= (1.f - ax[j] * ax[j]);
+      }
+      if (xrow) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (row_ok && col0 + j < p.N) {
+            const float h = xrow[col0 + j];
+            f[j] *= (1.f - h * h);
           }
         }
-        if (num_kb != 0) {
+      }
+      if (p.mode == TC_EPI_ROWDOT) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
-        }
-        if (p.act_tanh) {                                         // uniform branches: no predicated-off code on the common path
+        for (int j = 0; j < 32; ++j) rowdot = fmaf(f[j], colv_sm[c * 32 + j], rowdot);   // colv_sm is 0 beyond N
+        continue;
+      }
+      if (p.mode == TC_EPI_DZ) {
+        // column partials of h * rowv over this warp's 32 rows, then dz = rowv * colv * (1 - h^2)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = tanh_acc(f[j]);
+        for (int j = 0; j < 32; ++j) {
+          const float part = warp_sum(f[j] * rv);
+          if (lane == j) atomicAdd(&colred_sm[c * 32 + j], part);
+          f[j] = rv * colv_sm[c * 32 + j] * (1.f - f[j] * f[j]);
         }
-        if (xrow) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (row_ok && col0 + j < p.N) {
-              const float h = xrow[col0 + j];
-              f[j] *= (1.f - h * h);
-            }
-          }
-        }
+      }
+      if (p.tma_store) {
+        // Each thread owns one output row; the 32-column chunk is staged as a [128 rows][128 B] tile in the TMA 128-byte
+        // swizzle (16-byte chunk j of row r at chunk j ^ (r & 7): conflict-free float4 stores) and handed to the TMA engine.
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t dst = stage_buf + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) * 16);
@@ -383,65 +463,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_proxy_async_smem();                                 // generic-proxy smem writes -> visible to the TMA engine
         epi_barrier();
-        if (tl && leader && c < 4) tl[54 + 3 * c] = clock64();
         if (leader) {
-          if (p.atomic || p.accumulate) tma_reduce_add_2d(&tmD, stage_buf, col0, m0);
-          else tma_store_2d(&tmD, stage_buf, col0, m0);
+          if (p.atomic || p.accumulate) tma_reduce_add_3d(&maps.D, stage_buf, col0, m0, z);
+          else tma_store_3d(&maps.D, stage_buf, col0, m0, z);
           tma_store_commit();
         }
-      }
-      if (leader) tma_store_wait_read<0>();                       // smem must stay valid until the engine has read it
-    } else {
-      const bool vec_ok = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && !p.atomic;
-  #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        __syncwarp();                         // tcgen05.ld is warp-collective: reconverge after the guarded stores
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        if (num_kb == 0) {
-  #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0u;
-        }
-        const int col0 = n0 + c * 32;
-        if (!row_ok || col0 >= p.N || (p.dbg & 4)) continue;
-        float f[32];
-  #pragma unroll
+      } else if (row_ok) {                                        // unaligned output (e.g. K = 1001 logits): direct stores
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]);
           const int col = col0 + j;
           if (col < p.N) {
-            x += bias_sm[c * 32 + j];
-            if (p.act_tanh) x = tanh_acc(x);
-            if (xrow) {
-              const float h = xrow[col];
-              x *= (1.f - h * h);
-            }
-          }
-          f[j] = x;
-        }
-        if (vec_ok && col0 + 32 <= p.N) {
-          float4* d4 = reinterpret_cast<float4*>(drow + col0);
-  #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            if (p.accumulate) {
-              const float4 old = d4[j];
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            d4[j] = o;
-          }
-        } else {
-  #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col < p.N) {
-              if (p.atomic) atomicAdd(drow + col, f[j]);
-              else if (p.accumulate) drow[col] += f[j];
-              else drow[col] = f[j];
-            }
+            if (p.atomic) atomicAdd(drow + col, f[j]);
+            else if (p.accumulate) drow[col] += f[j];
+            else drow[col] = f[j];
           }
         }
       }
+    }
+    if (do_store && p.tma_store && leader) tma_store_wait_read<0>();   // smem must stay valid until the engine has read it
+    if (p.mode == TC_EPI_ROWDOT && row_ok) atomicAdd(p.red_row + (int64_t)z * p.red_row_sb + row, rowdot);
+    if (p.mode == TC_EPI_DZ) {
+      epi_barrier();
+      for (int j = et; j < BN; j += 128)
+        if (n0 + j < p.N) atomicAdd(p.red_col + n0 + j, colred_sm[j]);
     }
     tc_fence_before();
     if (tl && threadIdx.x == 64) tl[5] = clock64();
@@ -506,36 +550,43 @@ EncodeTiledFn get_encoder() {
   return fn;
 }
 
-// 3-D tensor map over [P][rows][ld] bf16: dims (cols, rows, P); box (64, box_rows, 1); 128-byte swizzle; OOB -> zeros
+// 4-D map over bf16 planes: dims (cols, rows, P, batch); box (64, box_rows, 1, 1); 128-byte swizzle; OOB -> zeros
 int make_tmap(CUtensorMap* tm, const TcOperand& o, int P, int box_rows) {
   EncodeTiledFn enc = get_encoder();
   if (!enc) return set_err(HCA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t gdim[3] = {(cuuint64_t)o.cols, (cuuint64_t)o.rows, (cuuint64_t)P};
-  cuuint64_t gstr[2] = {(cuuint64_t)o.ld * 2, (cuuint64_t)o.plane_stride * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  static int promo = -1;
-  if (promo < 0) { const char* e = getenv("HCA_TC_L2PROMO"); promo = e ? atoi(e) : 3; }
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)o.planes, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const int nb = o.nbatch > 0 ? o.nbatch : 1;
+  cuuint64_t gdim[4] = {(cuuint64_t)o.cols, (cuuint64_t)o.rows, (cuuint64_t)P, (cuuint64_t)nb};
+  cuuint64_t gstr[3] = {(cuuint64_t)o.ld * 2, (cuuint64_t)o.plane_stride * 2,
+                        (cuuint64_t)(nb > 1 ? o.batch_stride : o.plane_stride * P) * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)o.planes, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return set_err(HCA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed (%d) cols=%d rows=%d ld=%lld P=%d", (int)r, o.cols, o.rows,
-                   (long long)o.ld, P);
+    return set_err(HCA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed (%d) cols=%d rows=%d ld=%lld P=%d nb=%d", (int)r, o.cols, o.rows,
+                   (long long)o.ld, P, nb);
   return 0;
 }
 
-// 2-D fp32 map over D [M, N] (leading dim ldd): box = 32 columns (128 B) x 128 rows, 128-byte swizzle; stores clip at the edges
-int make_tmap_out(CUtensorMap* tm, float* D, int64_t ldd, int M, int N) {
+// 3-D fp32 map over X [batch][M, N] (leading dim ld): box = 32 columns (128 B) x 128 rows x 1, 128-byte swizzle
+int make_tmap_f32(CUtensorMap* tm, const float* X, int64_t ld, int64_t batch_stride, int nbatch, int M, int N) {
   EncodeTiledFn enc = get_encoder();
   if (!enc) return set_err(HCA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
-  cuuint64_t gstr[1] = {(cuuint64_t)ldd * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)BM};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)D, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const int nb = nbatch > 0 ? nbatch : 1;
+  cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)nb};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(nb > 1 ? batch_stride : (int64_t)M * ld) * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)X, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_err(HCA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled (output) failed (%d) M=%d N=%d ldd=%lld", (int)r, M, N, (long long)ldd);
+  if (r != CUDA_SUCCESS)
+    return set_err(HCA_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled (fp32 tile) failed (%d) M=%d N=%d ld=%lld nb=%d", (int)r, M, N,
+                   (long long)ld, nb);
   return 0;
+}
+
+bool f32_tma_ok(const float* p, int64_t ld, int64_t batch_stride) {
+  return ((ld & 3) == 0) && ((batch_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 }
 
 }  // namespace
@@ -558,45 +609,81 @@ int launch_split_planes(const float* src, int64_t ld, int64_t rows, int cols, __
 }
 
 int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, int K, const TcEpilogue& e, int splitk,
-                   cudaStream_t s) {
+                   cudaStream_t s, int batch, const TcOperand* A2, const TcOperand* B2, int K2) {
   constexpr int BN = 128;
-  HCA_CHECK_ARG(P >= 1 && P <= 3 && M > 0 && N > 0 && K > 0 && splitk >= 1, "gemm_tc: bad sizes");
-  HCA_CHECK_ARG((A.ld % 8) == 0 && (B.ld % 8) == 0 && (A.plane_stride % 8) == 0 && (B.plane_stride % 8) == 0,
-                "gemm_tc: plane leading dimensions must be multiples of 8 elements (TMA 16-byte strides)");
-  HCA_CHECK_ARG((reinterpret_cast<uintptr_t>(A.planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(B.planes) & 15) == 0,
-                "gemm_tc: planes must be 16-byte aligned");
-  CUtensorMap tmA, tmB, tmD;
-  HCA_TRY(make_tmap(&tmA, A, P, A.mn_major ? 64 : BM));
-  HCA_TRY(make_tmap(&tmB, B, P, B.mn_major ? 64 : BN));
-  const bool tma_store = ((e.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.D) & 15) == 0);
-  if (tma_store) HCA_TRY(make_tmap_out(&tmD, e.D, e.ldd, M, N));
-  else tmD = tmA;                                                     // unused placeholder
+  HCA_CHECK_ARG(P >= 1 && P <= 3 && M > 0 && N > 0 && K > 0 && splitk >= 1 && batch >= 1, "gemm_tc: bad sizes");
+  HCA_CHECK_ARG(batch == 1 || splitk == 1, "gemm_tc: split-K is for un-batched products");
+  HCA_CHECK_ARG((A2 == nullptr) == (B2 == nullptr), "gemm_tc: the chained operand pair needs both A2 and B2");
+  const TcOperand* ops[4] = {&A, &B, A2, B2};
+  for (const TcOperand* o : ops) {
+    if (!o) continue;
+    HCA_CHECK_ARG((o->ld % 8) == 0 && (o->plane_stride % 8) == 0 && (o->batch_stride % 8) == 0,
+                  "gemm_tc: plane leading dimensions / strides must be multiples of 8 elements (TMA 16-byte strides)");
+    HCA_CHECK_ARG((reinterpret_cast<uintptr_t>(o->planes) & 15) == 0, "gemm_tc: planes must be 16-byte aligned");
+  }
+  HCA_CHECK_ARG(!(A.mn_major && !B.mn_major), "gemm_tc: (MN-major A, K-major B) is not instantiated");
+  if (A2) HCA_CHECK_ARG(A2->mn_major == A.mn_major && B2->mn_major == B.mn_major && K2 > 0, "gemm_tc: chained pair must share the layouts");
+  TcMaps maps;
+  HCA_TRY(make_tmap(&maps.A, A, P, A.mn_major ? 64 : BM));
+  HCA_TRY(make_tmap(&maps.B, B, P, B.mn_major ? 64 : BN));
+  if (A2) {
+    HCA_TRY(make_tmap(&maps.A2, *A2, P, A2->mn_major ? 64 : BM));
+    HCA_TRY(make_tmap(&maps.B2, *B2, P, B2->mn_major ? 64 : BN));
+  } else {
+    maps.A2 = maps.A;
+    maps.B2 = maps.B;
+  }
+  const bool need_store = e.mode != TC_EPI_ROWDOT;
+  const bool tma_store = need_store && f32_tma_ok(e.D, e.ldd, e.d_batch_stride);
+  if (need_store) HCA_CHECK_ARG(e.D != nullptr, "gemm_tc: null output");
+  if (tma_store) HCA_TRY(make_tmap_f32(&maps.D, e.D, e.ldd, e.d_batch_stride, batch, M, N));
+  else maps.D = maps.A;                                                // unused placeholder
+  if (e.aux_mode != TC_AUX_NONE) {
+    HCA_CHECK_ARG(e.aux && f32_tma_ok(e.aux, e.aux_ld, e.aux_batch_stride), "gemm_tc: aux tile must have 16-byte aligned rows");
+    HCA_TRY(make_tmap_f32(&maps.AUX, e.aux, e.aux_ld, e.aux_batch_stride, e.aux_nbatch, M, N));
+  } else {
+    maps.AUX = maps.A;
+  }
   TcParams p;
-  p.M = M; p.N = N; p.K = K; p.P = P;
-  p.a_mn = A.mn_major ? 1 : 0;
-  p.b_mn = B.mn_major ? 1 : 0;
+  p.M = M; p.N = N; p.K = K;
   const int stage_bytes = P * (A_TILE_BYTES + BN * BK * 2);
   p.stages = SMEM_BUDGET / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  { const char* e = getenv("HCA_TC_STAGES"); if (e && atoi(e) >= 1 && atoi(e) < p.stages) p.stages = atoi(e); }
+  { const char* ev = getenv("HCA_TC_STAGES"); if (ev && atoi(ev) >= 1 && atoi(ev) < p.stages) p.stages = atoi(ev); }
   HCA_CHECK_ARG(p.stages >= 2, "gemm_tc: tile does not fit two pipeline stages");
-  p.kb_total = (K + BK - 1) / BK;
+  HCA_CHECK_ARG((size_t)p.stages * stage_bytes >= (size_t)(2 + BN / 32) * BM * 128, "gemm_tc: staging tiles do not fit");
+  p.kb1 = (K + BK - 1) / BK;
+  p.kb_total = p.kb1 + (A2 ? (K2 + BK - 1) / BK : 0);
   if (splitk > p.kb_total) splitk = p.kb_total;
   p.kb_per_split = (p.kb_total + splitk - 1) / splitk;
   splitk = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;      // no empty split
-  p.D = e.D; p.ldd = e.ldd; p.bias = e.bias; p.act_tanh = e.act_tanh; p.mulx = e.mulx; p.mulx_ld = e.mulx_ld;
+  p.splitk = splitk;
+  p.D = e.D; p.ldd = e.ldd; p.d_sb = e.d_batch_stride;
+  p.bias = e.bias; p.bias_sb = e.bias_batch_stride;
+  p.act_tanh = e.act_tanh; p.mulx = e.mulx; p.mulx_ld = e.mulx_ld;
   p.accumulate = e.accumulate;
   p.atomic = splitk > 1 ? 1 : 0;
   p.tma_store = tma_store ? 1 : 0;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("HCA_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+  p.mode = e.mode; p.aux_mode = e.aux_mode; p.aux_nbatch = e.aux_nbatch > 0 ? e.aux_nbatch : 1;
+  p.rowv = e.rowv; p.rowv_sb = e.rowv_batch_stride;
+  p.colv = e.colv;
+  p.r1col = e.r1col; p.r1col_sb = e.r1col_batch_stride;
+  p.red_row = e.red_row; p.red_row_sb = e.red_row_batch_stride;
+  p.red_col = e.red_col;
+  p.a_nb = A.nbatch > 0 ? A.nbatch : 1; p.b_nb = B.nbatch > 0 ? B.nbatch : 1;
+  p.a2_nb = A2 ? (A2->nbatch > 0 ? A2->nbatch : 1) : 1; p.b2_nb = B2 ? (B2->nbatch > 0 ? B2->nbatch : 1) : 1;
+  HCA_CHECK_ARG(!(p.atomic && (e.bias || e.act_tanh || e.mulx || e.aux_mode || e.mode != TC_EPI_STORE || e.r1col)),
+                "gemm_tc: split-K needs a linear epilogue");
+  HCA_CHECK_ARG(e.mode != TC_EPI_ROWDOT || (e.colv && e.red_row), "gemm_tc: ROWDOT needs colv and red_row");
+  HCA_CHECK_ARG(e.mode != TC_EPI_DZ || (e.colv && e.rowv && e.red_col), "gemm_tc: DZ needs rowv, colv and red_col");
+  HCA_CHECK_ARG(!e.r1col || (e.rowv && e.mode == TC_EPI_STORE), "gemm_tc: the rank-1 term needs rowv and the STORE mode");
+  { static int dbg = -1; if (dbg < 0) { const char* ev = getenv("HCA_TC_DBG"); dbg = ev ? atoi(ev) : 0; } p.dbg = dbg; }
   p.timeline = g_timeline;
   p.timeline_ctas = g_timeline_ctas;
-  HCA_CHECK_ARG(!(p.atomic && (e.bias || e.act_tanh || e.mulx)), "gemm_tc: split-K needs a linear epilogue");
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splitk);
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch * splitk);
   HCA_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "gemm_tc: grid too large");
-  HCA_CHECK_ARG(!(A.mn_major && !B.mn_major), "gemm_tc: (MN-major A, K-major B) is not instantiated");
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+  typedef void (*KernelFn)(const TcMaps, const TcParams);
   KernelFn fn = nullptr;
   const int combo = (A.mn_major ? 2 : (B.mn_major ? 1 : 0));    // 0 = NT, 1 = NN, 2 = TN
 #define HCA_TC_CASE(PP, CC, AMN, BMN) if (P == PP && combo == CC) fn = gemm_tc_kernel<BN, PP, AMN, BMN>;
@@ -609,7 +696,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
     HCA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048));
     attr_set[P - 1][combo] = true;
   }
-  fn<<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, tmD, p);
+  fn<<<grid, NUM_THREADS, smem, s>>>(maps, p);
   HCA_LAUNCHED();
   return 0;
 }
