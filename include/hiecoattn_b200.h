@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HCA_ABI_VERSION 1
+#define HCA_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define HCA_API __attribute__((visibility("default")))
@@ -80,25 +80,24 @@ HCA_API int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const floa
 /* ---- ParallelCoAttention, all three levels (replaces model.py:356-397) -------------------------- */
 /* V [B,N,d] with ELEMENT strides (v_sb, v_sn, v_sd) -- the reference hands a permuted VGG view
  * (model.py:217); q0,q1,q2 = word / phrase / sentence features, each dense [B,T,d];
- * Wv,Wq [d,d] (nn.Linear layout [out,in]), bv,bq [d], wv,wq [d], cv,cq device scalars [1].
+ * Wv,Wq [d,d] (nn.Linear layout [out,in]), bv,bq [d], wv,wq [d], cv,cq device scalars [1].  d % 8 == 0.
  * W_b is declared by the reference (model.py:347) but never used (model.py:377): it is not an input.
  * outputs: vhat [3,B,d], qhat [3,B,d];
- * saved for backward: PV [B,N,d], PQ [3,B,T,d], C [3,B,T,N], av [3,B,N], aq [3,B,T]. */
+ * saved for backward: one opaque, 256-byte aligned buffer of hca_coattn_saved_bytes(B,N,T,d) bytes (bf16 hi/lo
+ * operand planes of V, the stacked question levels, PV, PQ, C and the attention weights a_v, a_q). */
+HCA_API size_t hca_coattn_saved_bytes(int B, int N, int T, int d);
 HCA_API size_t hca_coattn_workspace(int B, int N, int T, int d, int need_dv);
 HCA_API int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_t v_sd,
                    const float* q0, const float* q1, const float* q2,
                    const float* Wv, const float* bv, const float* Wq, const float* bq,
                    const float* wv, const float* cv, const float* wq, const float* cq,
-                   float* vhat, float* qhat, float* PV, float* PQ, float* C, float* av, float* aq,
+                   float* vhat, float* qhat, void* saved, size_t saved_bytes,
                    int B, int N, int T, int d, void* ws, size_t ws_bytes, void* stream);
-/* gvhat,gqhat [3,B,d] = dL/dvhat, dL/dqhat.  Outputs: dQ [3,B,T,d]; dWv,dWq [d,d]; dbv,dbq,dwv,dwq [d];
- * dcv,dcq [1]; dV [B,N,d] dense or null when the image features need no gradient (frozen VGG,
- * main.py:67).  Weight gradients are summed over batch and levels. */
-HCA_API int hca_coattn_bwd(const float* V, int64_t v_sb, int64_t v_sn, int64_t v_sd,
-                   const float* q0, const float* q1, const float* q2,
-                   const float* Wv, const float* Wq, const float* wv, const float* wq,
-                   const float* PV, const float* PQ, const float* C, const float* av, const float* aq,
-                   const float* gvhat, const float* gqhat,
+/* gvhat,gqhat [3,B,d] = dL/dvhat, dL/dqhat.  Outputs: dQ [3,B,T,d] (dQ[l] = gradient of q_l); dWv,dWq [d,d];
+ * dbv,dbq,dwv,dwq [d]; dcv,dcq [1]; dV [B,N,d] dense or null when the image features need no gradient (frozen
+ * VGG, main.py:67).  Weight gradients are summed over batch and levels. */
+HCA_API int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv, const float* wq,
+                   const void* saved, size_t saved_bytes, const float* gvhat, const float* gqhat,
                    float* dV, float* dQ, float* dWv, float* dbv, float* dWq, float* dbq,
                    float* dwv, float* dcv, float* dwq, float* dcq,
                    int B, int N, int T, int d, void* ws, size_t ws_bytes, void* stream);

@@ -25,7 +25,7 @@ def load_golden(name):
 
 def test_library_loaded_and_cuda_only():
     h = _h()
-    assert h.PKG._lib.lib().hca_abi_version() == 1
+    assert h.PKG._lib.lib().hca_abi_version() == h.PKG._lib.ABI_VERSION
     with pytest.raises((NotImplementedError, RuntimeError)):
         h.PKG.ops.embedding(torch.zeros(2, 3, dtype=torch.long), torch.zeros(4, 8))     # CPU tensors: no fallback
 

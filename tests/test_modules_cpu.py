@@ -53,7 +53,7 @@ def test_library_exports_every_declared_symbol(pkg):
     lib = pkg._lib.lib()                                   # loads the .so; no CUDA call is made
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.hca_abi_version() == 1
+    assert lib.hca_abi_version() == pkg._lib.ABI_VERSION
     assert lib.hca_phrase_conv_pool_workspace(160, 26, 512) > 0     # pure host arithmetic
     assert pkg._lib.get_option("gemm") in ("tc", "ffma")
 

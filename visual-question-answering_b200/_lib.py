@@ -30,8 +30,9 @@ SIGNATURES = {
     "hca_phrase_conv_pool_fwd": (_i, [_p] * 10 + [_i, _i, _i, _p, _sz, _p]),
     "hca_phrase_conv_pool_bwd": (_i, [_p] * 15 + [_i, _i, _i, _p, _sz, _p]),
     "hca_coattn_workspace": (_sz, [_i, _i, _i, _i, _i]),
-    "hca_coattn_fwd": (_i, [_p, _i64, _i64, _i64] + [_p] * 18 + [_i, _i, _i, _i, _p, _sz, _p]),
-    "hca_coattn_bwd": (_i, [_p, _i64, _i64, _i64] + [_p] * 24 + [_i, _i, _i, _i, _p, _sz, _p]),
+    "hca_coattn_saved_bytes": (_sz, [_i, _i, _i, _i]),
+    "hca_coattn_fwd": (_i, [_p, _i64, _i64, _i64] + [_p] * 14 + [_sz] + [_i, _i, _i, _i, _p, _sz, _p]),
+    "hca_coattn_bwd": (_i, [_p] * 5 + [_sz] + [_p] * 12 + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_mlp_workspace": (_sz, [_i, _i, _i, _i]),
     "hca_mlp_fwd": (_i, [_p] * 15 + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_mlp_bwd": (_i, [_p] * 18 + [_i, _i, _i, _i, _p, _sz, _p]),
@@ -40,6 +41,7 @@ SIGNATURES = {
     "hca_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
 }
 
+ABI_VERSION = 2
 _lib = None
 
 
@@ -56,7 +58,7 @@ def lib():
             fn = getattr(handle, name)      # AttributeError here = header / library mismatch
             fn.restype = res
             fn.argtypes = args
-        if handle.hca_abi_version() != 1:
+        if handle.hca_abi_version() != ABI_VERSION:
             raise RuntimeError("libhiecoattn_b200.so: ABI version mismatch, rebuild it")
         _lib = handle
     return _lib

@@ -1,50 +1,30 @@
 // ParallelCoAttention, three levels with shared weights (replaces reference model.py:356-397).
 //
-// Per sample b and level l (V = image features [N,d], Q = question level [T,d]):
-//   C  = tanh(Q V^T)                 PV = V Wv^T + bv  (level independent: once per step)
-//   Hv = tanh(PV + C^T PQ)           PQ = Q Wq^T + bq  (once per level)
-//   Hq = tanh(PQ + C PV)
-//   av = softmax_N(Hv wv + cv)       aq = softmax_T(Hq wq + cq)   (all T positions, pads included)
-//   vhat = av^T V                    qhat = aq^T Q
+// Per sample b and level l (V = image features [N,d], Q_l = question level [T,d]):
+//   C_l  = tanh(Q_l V^T)               PV = V Wv^T + bv  (level independent: once per step)
+//   Hv_l = tanh(PV + C_l^T PQ_l)       PQ_l = Q_l Wq^T + bq
+//   Hq_l = tanh(PQ_l + C_l PV)
+//   av_l = softmax_N(Hv_l wv + cv)     aq_l = softmax_T(Hq_l wq + cq)   (all T positions, pads included)
+//   vhat_l = av_l^T V                  qhat_l = aq_l^T Q_l
 // W_b of the reference is dead code (model.py:347 vs :377) and does not appear.
 //
-// Backward follows SURVEY.md section 3.3; Hv / Hq are recomputed from the saved PV, PQ, C instead of being
-// stored (3 x B x N x d floats otherwise).
+// Every contraction runs on tcgen05 (gemm_tc.cuh, bf16x2 operand planes).  The three levels are STACKED along the
+// row axis of every question-side matrix -- Q_all[b] = [Q_0; Q_1; Q_2] is [3T, d] -- so that the products whose
+// image-side operand is level independent are one M = 3T (or K = 3T) product per sample instead of three M = T ones,
+// and the products that contract over T per level put the long image axis (N or d) on the 128-row M side of the
+// tensor core and T on a 32-wide N tile (transposed epilogue).  Intermediates are never written as fp32: each GEMM
+// epilogue emits the bf16 hi/lo planes its consumers take as operands.  Hv / Hq are recomputed in backward.
 //
-// This file is the orchestration + the warp-level glue kernels; the contractions go through dense.cuh
-// (large, tensor-core capable) and gemm_ffma.cuh (per-sample strided products with fused epilogues).
+// Saved for backward (one opaque buffer, hca_coattn_saved_bytes): planes of V, Q_all, PV, PQ_all, C_all; av, aq.
 #include <algorithm>
 #include "common.cuh"
-#include "dense.cuh"
-#include "gemm_ffma.cuh"
 #include "gemm_tc.cuh"
 #include "util_kernels.cuh"
 
 namespace hca {
 namespace {
 
-__device__ __forceinline__ float block_sum(float v, float* red) {   // red: >= 33 floats of smem
-  v = warp_sum(v);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) red[w] = v;
-  __syncthreads();
-  const int nw = blockDim.x >> 5;
-  float s = (l < nw) ? red[l] : 0.f;
-  s = warp_sum(s);
-  return s;
-}
-__device__ __forceinline__ float block_max(float v, float* red) {
-  v = warp_max(v);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) red[w] = v;
-  __syncthreads();
-  const int nw = blockDim.x >> 5;
-  float s = (l < nw) ? red[l] : -INFINITY;
-  s = warp_max(s);
-  return s;
-}
+inline int64_t round8(int64_t x) { return (x + 7) / 8 * 8; }
 
 // dense copy of a strided [B,N,d] tensor
 __global__ void __launch_bounds__(256) gather_strided_kernel(const float* __restrict__ V, int64_t sb, int64_t sn, int64_t sd,
@@ -58,40 +38,34 @@ __global__ void __launch_bounds__(256) gather_strided_kernel(const float* __rest
   }
 }
 
-// softmax over L scores, then the attention-weighted sum of the L rows of X [L,d].
-//   a[l] = softmax(s[l] + c) ; out[c] = sum_l a[l] X[l][c]
-__device__ void softmax_wsum(const float* __restrict__ s, float cbias, const float* __restrict__ X, int L, int d,
-                             float* __restrict__ a_out, float* __restrict__ out, float* a_sm, float* red) {
+// one warp: a = softmax(s + c) over L entries; a -> smem and global
+__device__ __forceinline__ void softmax_warp(const float* __restrict__ s, float cbias, int L, float* a_sm, float* __restrict__ a_out) {
+  const int lane = threadIdx.x & 31;
   float m = -INFINITY;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+  for (int i = lane; i < L; i += 32) {
     const float v = s[i] + cbias;
     a_sm[i] = v;
     m = fmaxf(m, v);
   }
-  m = block_max(m, red);
+  m = warp_max(m);
   float sum = 0.f;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+  for (int i = lane; i < L; i += 32) {
     const float e = expf(a_sm[i] - m);
     a_sm[i] = e;
     sum += e;
   }
-  sum = block_sum(sum, red);
+  sum = warp_sum(sum);
   const float inv = 1.f / sum;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+  for (int i = lane; i < L; i += 32) {
     const float a = a_sm[i] * inv;
     a_sm[i] = a;
     a_out[i] = a;
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float acc = 0.f;
-    for (int l = 0; l < L; ++l) acc = fmaf(a_sm[l], X[(int64_t)l * d + c], acc);
-    out[c] = acc;
-  }
-  __syncthreads();
 }
 
-// one block per (level, sample)
+// One block per sample: the six softmaxes (3 levels x {regions, tokens}) and the attention-weighted sums.  V[b] is read
+// once for all three levels; thread c owns a float2 column pair so no cross-thread reduction is needed.
+//   sv [B][3][N], sq [B][3][T] scores ; av, aq same layout ; vhat, qhat [3][B][d]
 __global__ void __launch_bounds__(256) attn_finish_kernel(const float* __restrict__ sv, const float* __restrict__ sq,
                                                           const float* __restrict__ cv, const float* __restrict__ cq,
                                                           const float* __restrict__ V, const float* __restrict__ q0,
@@ -100,105 +74,203 @@ __global__ void __launch_bounds__(256) attn_finish_kernel(const float* __restric
                                                           float* __restrict__ vhat, float* __restrict__ qhat,
                                                           int B, int N, int T, int d) {
   extern __shared__ float sm[];
-  float* red = sm;          // 64
-  float* a_sm = sm + 64;    // max(N,T)
-  const int z = blockIdx.x, l = z / B, b = z % B;
-  const float* Q = (l == 0 ? q0 : (l == 1 ? q1 : q2)) + (int64_t)b * T * d;
-  softmax_wsum(sv + (int64_t)z * N, cv[0], V + (int64_t)b * N * d, N, d, av + (int64_t)z * N, vhat + (int64_t)z * d, a_sm, red);
-  softmax_wsum(sq + (int64_t)z * T, cq[0], Q, T, d, aq + (int64_t)z * T, qhat + (int64_t)z * d, a_sm, red);
+  float* a_sm = sm;              // [3][N]
+  float* q_sm = sm + 3 * N;      // [3][T]
+  const int b = blockIdx.x, w = threadIdx.x >> 5;
+  if (w < 3) softmax_warp(sv + ((int64_t)b * 3 + w) * N, cv[0], N, a_sm + w * N, av + ((int64_t)b * 3 + w) * N);
+  else if (w < 6) softmax_warp(sq + ((int64_t)b * 3 + (w - 3)) * T, cq[0], T, q_sm + (w - 3) * T, aq + ((int64_t)b * 3 + (w - 3)) * T);
+  __syncthreads();
+  const int d2 = d >> 1;
+  const float2* V2 = reinterpret_cast<const float2*>(V + (int64_t)b * N * d);
+  for (int c = threadIdx.x; c < d2; c += blockDim.x) {
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
+    int n = 0;
+    for (; n + 4 <= N; n += 4) {
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(V2 + (int64_t)(n + u) * d2 + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float w0 = a_sm[n + u], w1 = a_sm[N + n + u], w2 = a_sm[2 * N + n + u];
+        a0.x = fmaf(w0, v[u].x, a0.x); a0.y = fmaf(w0, v[u].y, a0.y);
+        a1.x = fmaf(w1, v[u].x, a1.x); a1.y = fmaf(w1, v[u].y, a1.y);
+        a2.x = fmaf(w2, v[u].x, a2.x); a2.y = fmaf(w2, v[u].y, a2.y);
+      }
+    }
+    for (; n < N; ++n) {
+      const float2 v = __ldg(V2 + (int64_t)n * d2 + c);
+      const float w0 = a_sm[n], w1 = a_sm[N + n], w2 = a_sm[2 * N + n];
+      a0.x = fmaf(w0, v.x, a0.x); a0.y = fmaf(w0, v.y, a0.y);
+      a1.x = fmaf(w1, v.x, a1.x); a1.y = fmaf(w1, v.y, a1.y);
+      a2.x = fmaf(w2, v.x, a2.x); a2.y = fmaf(w2, v.y, a2.y);
+    }
+    float2* o = reinterpret_cast<float2*>(vhat + (int64_t)b * d) + c;
+    o[0] = a0;
+    o[(int64_t)B * d2] = a1;
+    o[(int64_t)2 * B * d2] = a2;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      const float2* Q2 = reinterpret_cast<const float2*>((l == 0 ? q0 : (l == 1 ? q1 : q2)) + (int64_t)b * T * d);
+      float2 acc = make_float2(0.f, 0.f);
+      for (int t = 0; t < T; ++t) {
+        const float2 v = __ldg(Q2 + (int64_t)t * d2 + c);
+        const float wq = q_sm[l * T + t];
+        acc.x = fmaf(wq, v.x, acc.x); acc.y = fmaf(wq, v.y, acc.y);
+      }
+      reinterpret_cast<float2*>(qhat + ((int64_t)l * B + b) * d)[c] = acc;
+    }
+  }
 }
 
-// da[l] = X[l,:] . g ; ds = a * (da - <a,da>) ; dc += sum ds
-__device__ void softmax_bwd(const float* __restrict__ a, const float* __restrict__ X, const float* __restrict__ g, int L, int d,
-                            float* __restrict__ ds_out, float* __restrict__ dc, float* da_sm, float* red) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int l = w; l < L; l += nw) {
-    const float* x = X + (int64_t)l * d;
-    float acc = 0.f;
-    for (int c = lane; c < d; c += 32) acc = fmaf(x[c], g[c], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) da_sm[l] = acc;
+__device__ __forceinline__ float bf2f_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf2f_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// dots of one row (hi + lo bf16 planes, d columns) with up to 3 vectors held in smem; warp-cooperative
+template <int NG>
+__device__ __forceinline__ void row_dots(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int d,
+                                         const float* g_sm, int g_stride, float (&out)[NG]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) out[g] = 0.f;
+  for (int c = lane * 8; c < d; c += 256) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + c));
+    const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + c));
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      x[2 * k] = bf2f_lo(hw[k]) + bf2f_lo(lw[k]);
+      x[2 * k + 1] = bf2f_hi(hw[k]) + bf2f_hi(lw[k]);
+    }
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const float* gg = g_sm + g * g_stride + c;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out[g] = fmaf(x[k], gg[k], out[g]);
+    }
   }
-  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < NG; ++g) out[g] = warp_sum(out[g]);
+}
+
+// one warp: ds = a * (da - <a, da>) ; *dc += sum ds
+__device__ __forceinline__ void softmax_bwd_warp(const float* __restrict__ a, const float* da_sm, int L, float* __restrict__ ds_out,
+                                                 float* __restrict__ dc) {
+  const int lane = threadIdx.x & 31;
   float dot = 0.f;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) dot = fmaf(a[i], da_sm[i], dot);
-  dot = block_sum(dot, red);
+  for (int i = lane; i < L; i += 32) dot = fmaf(a[i], da_sm[i], dot);
+  dot = warp_sum(dot);
   float tot = 0.f;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+  for (int i = lane; i < L; i += 32) {
     const float v = a[i] * (da_sm[i] - dot);
     ds_out[i] = v;
     tot += v;
   }
-  tot = block_sum(tot, red);
-  if (threadIdx.x == 0) atomicAdd(dc, tot);
-  __syncthreads();
+  tot = warp_sum(tot);
+  if (lane == 0) atomicAdd(dc, tot);
 }
 
+// One block per sample: da_v[l][n] = V[n,:] . g_v[l] for the three levels in one pass over V[b] (bf16 hi + lo planes),
+// da_q[l][t] = Q_l[t,:] . g_q[l], then the softmax backward of all six attention vectors.
+//   Vp planes [2][B*N][d], Qp planes [2][B][3T][d] ; gv, gq [3][B][d] ; av, aq, dsv, dsq [B][3][N|T]
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const float* __restrict__ av, const float* __restrict__ aq,
-                                                            const float* __restrict__ V, const float* __restrict__ q0,
-                                                            const float* __restrict__ q1, const float* __restrict__ q2,
+                                                            const __nv_bfloat16* __restrict__ Vp, int64_t v_ps,
+                                                            const __nv_bfloat16* __restrict__ Qp, int64_t q_ps,
                                                             const float* __restrict__ gv, const float* __restrict__ gq,
                                                             float* __restrict__ dsv, float* __restrict__ dsq,
                                                             float* __restrict__ dcv, float* __restrict__ dcq,
                                                             int B, int N, int T, int d) {
   extern __shared__ float sm[];
-  float* red = sm;
-  float* da_sm = sm + 64;
-  const int z = blockIdx.x, l = z / B, b = z % B;
-  const float* Q = (l == 0 ? q0 : (l == 1 ? q1 : q2)) + (int64_t)b * T * d;
-  softmax_bwd(av + (int64_t)z * N, V + (int64_t)b * N * d, gv + (int64_t)z * d, N, d, dsv + (int64_t)z * N, dcv, da_sm, red);
-  softmax_bwd(aq + (int64_t)z * T, Q, gq + (int64_t)z * d, T, d, dsq + (int64_t)z * T, dcq, da_sm, red);
+  float* gv_sm = sm;                  // [3][d]
+  float* gq_sm = sm + 3 * d;          // [3][d]
+  float* dav_sm = sm + 6 * d;         // [3][N]
+  float* daq_sm = dav_sm + 3 * N;     // [3][T]
+  const int b = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) {
+    const int l = i / d, c = i - l * d;
+    gv_sm[i] = gv[((int64_t)l * B + b) * d + c];
+    gq_sm[i] = gq[((int64_t)l * B + b) * d + c];
+  }
+  __syncthreads();
+  for (int n = w; n < N; n += nw) {
+    const __nv_bfloat16* hi = Vp + ((int64_t)b * N + n) * d;
+    float o[3];
+    row_dots<3>(hi, hi + v_ps, d, gv_sm, d, o);
+    if (lane == 0) { dav_sm[n] = o[0]; dav_sm[N + n] = o[1]; dav_sm[2 * N + n] = o[2]; }
+  }
+  for (int r = w; r < 3 * T; r += nw) {
+    const int l = r / T;
+    const __nv_bfloat16* hi = Qp + ((int64_t)b * 3 * T + r) * d;
+    float o[1];
+    row_dots<1>(hi, hi + q_ps, d, gq_sm + l * d, d, o);
+    if (lane == 0) daq_sm[r] = o[0];
+  }
+  __syncthreads();
+  if (w < 3) softmax_bwd_warp(av + ((int64_t)b * 3 + w) * N, dav_sm + w * N, N, dsv + ((int64_t)b * 3 + w) * N, dcv);
+  else if (w < 6) softmax_bwd_warp(aq + ((int64_t)b * 3 + (w - 3)) * T, daq_sm + (w - 3) * T, T, dsq + ((int64_t)b * 3 + (w - 3)) * T, dcq);
 }
 
-
+// dV[b][n][:] += sum_l av[b][l][n] * gv[l][b][:]      (only when the image features need a gradient)
+__global__ void __launch_bounds__(256) dv_rank3_kernel(float* __restrict__ dV, const float* __restrict__ av, const float* __restrict__ gv,
+                                                       int B, int N, int d) {
+  const int d4 = d >> 2;
+  const int64_t total = (int64_t)B * N * d4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d4);
+    const int64_t bn = i / d4;
+    const int b = (int)(bn / N), n = (int)(bn - (int64_t)b * N);
+    float4 acc = reinterpret_cast<float4*>(dV)[i];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      const float a = av[((int64_t)b * 3 + l) * N + n];
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gv + ((int64_t)l * B + b) * d) + c);
+      acc.x = fmaf(a, g.x, acc.x); acc.y = fmaf(a, g.y, acc.y); acc.z = fmaf(a, g.z, acc.z); acc.w = fmaf(a, g.w, acc.w);
+    }
+    reinterpret_cast<float4*>(dV)[i] = acc;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------------
-// tensor-core path: every contraction of the module on tcgen05 with bf16x2 operand planes (gemm_tc.cuh).  Per-sample
-// products are batched launches (grid.z = level * B + sample); image-side operands are shared across levels through
-// the batch modulo of the TMA batch coordinate.
-constexpr int TCP = 2;    // planes
-
-struct Planes {
+struct Pl {                 // bf16 hi/lo planes of a [rows][cols] matrix, leading dimension ld
   __nv_bfloat16* p = nullptr;
-  int64_t ld = 0, plane_stride = 0;
+  int64_t ld = 0, ps = 0;   // plane stride (elements)
   int64_t rows = 0;
   int cols = 0;
 };
-
-inline int64_t round8(int64_t x) { return (x + 7) / 8 * 8; }
-
-// allocate planes for an fp32 matrix [rows, cols] (rows may be filled by several split launches)
-int alloc_planes(Planes& pl, int64_t rows, int cols, Workspace& w) {
-  pl.ld = round8(cols);
-  pl.rows = rows;
-  pl.cols = cols;
-  pl.plane_stride = rows * pl.ld;
-  pl.p = w.take<__nv_bfloat16>((size_t)TCP * pl.plane_stride);
-  if (!pl.p) return set_err(HCA_ERR_WORKSPACE, "coattn: workspace too small for bf16 operand planes (%lld x %d)", (long long)rows, cols);
-  return 0;
+size_t pl_bytes(int64_t rows, int cols) { return align_up((size_t)2 * rows * round8(cols) * 2); }
+Pl pl_at(void* base, int64_t rows, int cols) {
+  Pl r;
+  r.p = (__nv_bfloat16*)base;
+  r.ld = round8(cols);
+  r.ps = rows * r.ld;
+  r.rows = rows;
+  r.cols = cols;
+  return r;
 }
-int fill_planes(const Planes& pl, const float* src, int64_t ld, int64_t row0, int64_t rows, cudaStream_t s) {
-  return launch_split_planes(src, ld, rows, pl.cols, pl.p + row0 * pl.ld, pl.ld, pl.plane_stride, TCP, s);
-}
-int make_planes(Planes& pl, const float* src, int64_t ld, int64_t rows, int cols, Workspace& w, cudaStream_t s) {
-  HCA_TRY(alloc_planes(pl, rows, cols, w));
-  return fill_planes(pl, src, ld, 0, rows, s);
-}
-// batched view: entry z = rows [row0 + z * rows_per_batch, +rows_per_batch) of the plane matrix
-TcOperand view(const Planes& pl, int64_t row0, int rows_per_batch, int nbatch, bool mn_major) {
+// operand view: batch entry z = rows [row0 + z * rows_per_entry, + rows_used) of the plane matrix
+TcOperand opv(const Pl& pl, int64_t row0, int rows_used, int64_t rows_per_entry, int nbatch, bool mn_major, int zdiv = 1) {
   TcOperand o;
   o.planes = pl.p + row0 * pl.ld;
   o.ld = pl.ld;
-  o.plane_stride = pl.plane_stride;
-  o.batch_stride = (int64_t)rows_per_batch * pl.ld;
+  o.plane_stride = pl.ps;
+  o.batch_stride = rows_per_entry * pl.ld;
   o.nbatch = nbatch;
-  o.rows = rows_per_batch;
+  o.zdiv = zdiv;
+  o.rows = rows_used;
   o.cols = pl.cols;
   o.mn_major = mn_major;
   return o;
 }
-
-bool tc_path_ok(int N, int d) { return use_tc() && tc_available() && (d % 8 == 0) && (N % 4 == 0); }
+TcPlanes plv(const Pl& pl, int64_t row0, int64_t rows_per_entry, int nbatch, int zdiv = 1) {
+  TcPlanes t;
+  t.p = pl.p + row0 * pl.ld;
+  t.ld = pl.ld;
+  t.plane_stride = pl.ps;
+  t.batch_stride = rows_per_entry * pl.ld;
+  t.nbatch = nbatch;
+  t.zdiv = zdiv;
+  return t;
+}
 
 int tc_splitk(int M, int N, int K) {
   const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
@@ -209,138 +281,33 @@ int tc_splitk(int M, int N, int K) {
   return sk < 1 ? 1 : sk;
 }
 
-struct CoattnPlanes {
-  Planes V, Q, C, PV, PQ, Wv, Wq;
+struct Saved {
+  Pl V, Q, PV, PQ, C;
+  float *av, *aq;
 };
-
-// planes every direction needs: V, the three question levels stacked [3*B*T, d], and the two projection weights
-int common_planes(CoattnPlanes& cp, const float* Vd, const float* const q[3], const float* Wv, const float* Wq, int B, int N, int T,
-                  int d, Workspace& w, cudaStream_t s) {
-  const int64_t BT = (int64_t)B * T;
-  HCA_TRY(make_planes(cp.V, Vd, d, (int64_t)B * N, d, w, s));
-  HCA_TRY(alloc_planes(cp.Q, 3 * BT, d, w));
-  for (int l = 0; l < 3; ++l) HCA_TRY(fill_planes(cp.Q, q[l], d, l * BT, BT, s));
-  HCA_TRY(make_planes(cp.Wv, Wv, d, d, d, w, s));
-  HCA_TRY(make_planes(cp.Wq, Wq, d, d, d, w, s));
-  return 0;
+size_t saved_bytes(int B, int N, int T, int d) {
+  return 2 * pl_bytes((int64_t)B * N, d) + 2 * pl_bytes((int64_t)B * 3 * T, d) + pl_bytes((int64_t)B * 3 * T, N) +
+         align_up((size_t)B * 3 * N * 4) + align_up((size_t)B * 3 * T * 4) + 256;
 }
-
-int coattn_fwd_tc(const float* Vd, const float* const q[3], const float* Wv, const float* bv, const float* Wq, const float* bq,
-                  const float* wv, const float* wq, float* PV, float* PQ, float* C, float* sv, float* sq, int B, int N, int T, int d,
-                  Workspace& w, cudaStream_t s) {
-  const int64_t BT = (int64_t)B * T, BN = (int64_t)B * N;
-  CoattnPlanes cp;
-  HCA_TRY(common_planes(cp, Vd, q, Wv, Wq, B, N, T, d, w, s));
-  {  // PV = V Wv^T + bv   (once per step: level independent)
-    TcEpilogue e; e.D = PV; e.ldd = d; e.bias = bv;
-    HCA_TRY(launch_gemm_tc(view(cp.V, 0, (int)BN, 1, false), view(cp.Wv, 0, d, 1, false), TCP, (int)BN, d, d, e, 1, s));
-  }
-  {  // PQ = Q Wq^T + bq   (the three levels in one launch)
-    TcEpilogue e; e.D = PQ; e.ldd = d; e.bias = bq;
-    HCA_TRY(launch_gemm_tc(view(cp.Q, 0, (int)(3 * BT), 1, false), view(cp.Wq, 0, d, 1, false), TCP, (int)(3 * BT), d, d, e, 1, s));
-  }
-  {  // C[z] = tanh(Q[z] V[b]^T)
-    TcEpilogue e; e.D = C; e.ldd = N; e.d_batch_stride = (int64_t)T * N; e.act_tanh = 1;
-    HCA_TRY(launch_gemm_tc(view(cp.Q, 0, T, 3 * B, false), view(cp.V, 0, N, B, false), TCP, T, N, d, e, 1, s, 3 * B));
-  }
-  HCA_TRY(make_planes(cp.C, C, N, 3 * BT, N, w, s));
-  HCA_TRY(make_planes(cp.PV, PV, d, BN, d, w, s));
-  HCA_TRY(make_planes(cp.PQ, PQ, d, 3 * BT, d, w, s));
-  {  // sq[z][t] = sum_j tanh(PQ + C PV)[t][j] wq[j]
-    TcEpilogue e; e.mode = TC_EPI_ROWDOT; e.act_tanh = 1; e.colv = wq; e.red_row = sq; e.red_row_batch_stride = T;
-    e.aux = PQ; e.aux_ld = d; e.aux_batch_stride = (int64_t)T * d; e.aux_nbatch = 3 * B; e.aux_mode = TC_AUX_ADD;
-    HCA_TRY(launch_gemm_tc(view(cp.C, 0, T, 3 * B, false), view(cp.PV, 0, N, B, true), TCP, T, d, N, e, 1, s, 3 * B));
-  }
-  {  // sv[z][n] = sum_j tanh(PV + C^T PQ)[n][j] wv[j]
-    TcEpilogue e; e.mode = TC_EPI_ROWDOT; e.act_tanh = 1; e.colv = wv; e.red_row = sv; e.red_row_batch_stride = N;
-    e.aux = PV; e.aux_ld = d; e.aux_batch_stride = (int64_t)N * d; e.aux_nbatch = B; e.aux_mode = TC_AUX_ADD;
-    HCA_TRY(launch_gemm_tc(view(cp.C, 0, T, 3 * B, true), view(cp.PQ, 0, T, 3 * B, true), TCP, N, d, T, e, 1, s, 3 * B));
-  }
-  return 0;
+bool carve_saved(Saved& s, void* buf, size_t bytes, int B, int N, int T, int d) {
+  if (bytes < saved_bytes(B, N, T, d) || (reinterpret_cast<uintptr_t>(buf) & 255) != 0) return false;
+  char* p = (char*)buf;
+  const int64_t BN = (int64_t)B * N, BT3 = (int64_t)B * 3 * T;
+  s.V = pl_at(p, BN, d); p += pl_bytes(BN, d);
+  s.PV = pl_at(p, BN, d); p += pl_bytes(BN, d);
+  s.Q = pl_at(p, BT3, d); p += pl_bytes(BT3, d);
+  s.PQ = pl_at(p, BT3, d); p += pl_bytes(BT3, d);
+  s.C = pl_at(p, BT3, N); p += pl_bytes(BT3, N);
+  s.av = (float*)p; p += align_up((size_t)B * 3 * N * 4);
+  s.aq = (float*)p;
+  return true;
 }
-
-int coattn_bwd_tc(const float* Vd, const float* const q[3], const float* Wv, const float* Wq, const float* wv, const float* wq,
-                  const float* PV, const float* PQ, const float* C, const float* av, const float* aq, const float* gvhat,
-                  const float* gqhat, const float* dsv, const float* dsq, float* dZv, float* dZq, float* dPQ, float* dPV, float* dS,
-                  float* dV, float* dQ, float* dWv, float* dbv, float* dWq, float* dbq, float* dwv, float* dwq, int B, int N, int T,
-                  int d, Workspace& w, cudaStream_t s) {
-  const int64_t BT = (int64_t)B * T, BN = (int64_t)B * N;
-  CoattnPlanes cp;
-  HCA_TRY(common_planes(cp, Vd, q, Wv, Wq, B, N, T, d, w, s));
-  HCA_TRY(make_planes(cp.C, C, N, 3 * BT, N, w, s));
-  HCA_TRY(make_planes(cp.PV, PV, d, BN, d, w, s));
-  HCA_TRY(make_planes(cp.PQ, PQ, d, 3 * BT, d, w, s));
-  {  // dZv = (dsv x wv) * (1 - Hv^2), Hv = tanh(PV + C^T PQ) recomputed ; dwv += Hv^T dsv
-    TcEpilogue e; e.mode = TC_EPI_DZ; e.act_tanh = 1; e.colv = wv; e.rowv = dsv; e.rowv_batch_stride = N; e.red_col = dwv;
-    e.aux = PV; e.aux_ld = d; e.aux_batch_stride = (int64_t)N * d; e.aux_nbatch = B; e.aux_mode = TC_AUX_ADD;
-    e.D = dZv; e.ldd = d; e.d_batch_stride = (int64_t)N * d;
-    HCA_TRY(launch_gemm_tc(view(cp.C, 0, T, 3 * B, true), view(cp.PQ, 0, T, 3 * B, true), TCP, N, d, T, e, 1, s, 3 * B));
-  }
-  {  // dZq likewise from Hq = tanh(PQ + C PV)
-    TcEpilogue e; e.mode = TC_EPI_DZ; e.act_tanh = 1; e.colv = wq; e.rowv = dsq; e.rowv_batch_stride = T; e.red_col = dwq;
-    e.aux = PQ; e.aux_ld = d; e.aux_batch_stride = (int64_t)T * d; e.aux_nbatch = 3 * B; e.aux_mode = TC_AUX_ADD;
-    e.D = dZq; e.ldd = d; e.d_batch_stride = (int64_t)T * d;
-    HCA_TRY(launch_gemm_tc(view(cp.C, 0, T, 3 * B, false), view(cp.PV, 0, N, B, true), TCP, T, d, N, e, 1, s, 3 * B));
-  }
-  Planes pZv, pZq, pS, pPQg, pPVg;
-  HCA_TRY(make_planes(pZv, dZv, d, 3 * BN, d, w, s));
-  HCA_TRY(make_planes(pZq, dZq, d, 3 * BT, d, w, s));
-  {  // dPQ = dZq + C dZv
-    TcEpilogue e; e.D = dPQ; e.ldd = d; e.d_batch_stride = (int64_t)T * d;
-    e.aux = dZq; e.aux_ld = d; e.aux_batch_stride = (int64_t)T * d; e.aux_nbatch = 3 * B; e.aux_mode = TC_AUX_ADD;
-    HCA_TRY(launch_gemm_tc(view(cp.C, 0, T, 3 * B, false), view(pZv, 0, N, 3 * B, true), TCP, T, d, N, e, 1, s, 3 * B));
-  }
-  for (int l = 0; l < 3; ++l) {  // dPV = sum_l dZv_l + C_l^T dZq_l
-    TcEpilogue e; e.D = dPV; e.ldd = d; e.d_batch_stride = (int64_t)N * d; e.accumulate = (l > 0);
-    e.aux = dZv + l * BN * d; e.aux_ld = d; e.aux_batch_stride = (int64_t)N * d; e.aux_nbatch = B; e.aux_mode = TC_AUX_ADD;
-    HCA_TRY(launch_gemm_tc(view(cp.C, l * BT, T, B, true), view(pZq, l * BT, T, B, true), TCP, N, d, T, e, 1, s, B));
-  }
-  {  // dS = (PQ dZv^T + dZq PV^T) * (1 - C^2): two operand pairs chained along K in one accumulator
-    TcEpilogue e; e.D = dS; e.ldd = N; e.d_batch_stride = (int64_t)T * N;
-    e.aux = C; e.aux_ld = N; e.aux_batch_stride = (int64_t)T * N; e.aux_nbatch = 3 * B; e.aux_mode = TC_AUX_MUL_1MX2;
-    const TcOperand a2 = view(pZq, 0, T, 3 * B, false), b2 = view(cp.PV, 0, N, B, false);
-    HCA_TRY(launch_gemm_tc(view(cp.PQ, 0, T, 3 * B, false), view(pZv, 0, N, 3 * B, false), TCP, T, N, d, e, 1, s, 3 * B, &a2, &b2, d));
-  }
-  HCA_TRY(make_planes(pS, dS, N, 3 * BT, N, w, s));
-  {  // dQ = dS V + aq x gq
-    TcEpilogue e; e.D = dQ; e.ldd = d; e.d_batch_stride = (int64_t)T * d;
-    e.rowv = aq; e.rowv_batch_stride = T; e.r1col = gqhat; e.r1col_batch_stride = d;
-    HCA_TRY(launch_gemm_tc(view(pS, 0, T, 3 * B, false), view(cp.V, 0, N, B, true), TCP, T, d, N, e, 1, s, 3 * B));
-  }
-  HCA_TRY(make_planes(pPQg, dPQ, d, 3 * BT, d, w, s));
-  {  // dQ += dPQ Wq
-    TcEpilogue e; e.D = dQ; e.ldd = d; e.accumulate = 1;
-    HCA_TRY(launch_gemm_tc(view(pPQg, 0, (int)(3 * BT), 1, false), view(cp.Wq, 0, d, 1, true), TCP, (int)(3 * BT), d, d, e, 1, s));
-  }
-  {  // dWq = dPQ^T Q over batch, time and the three levels at once (K = 3*B*T, split-K)
-    const int sk = tc_splitk(d, d, (int)(3 * BT));
-    if (sk > 1) HCA_TRY(zero_async(dWq, (size_t)d * d * 4, s));
-    TcEpilogue e; e.D = dWq; e.ldd = d;
-    HCA_TRY(launch_gemm_tc(view(pPQg, 0, (int)(3 * BT), 1, true), view(cp.Q, 0, (int)(3 * BT), 1, true), TCP, d, d, (int)(3 * BT), e, sk, s));
-  }
-  HCA_TRY(zero_async(dbq, (size_t)d * 4, s));
-  HCA_TRY(launch_colsum(dPQ, d, 3 * BT, d, dbq, s));
-  HCA_TRY(make_planes(pPVg, dPV, d, BN, d, w, s));
-  {  // dWv = dPV^T V   (K = B*N, split-K)
-    const int sk = tc_splitk(d, d, (int)BN);
-    if (sk > 1) HCA_TRY(zero_async(dWv, (size_t)d * d * 4, s));
-    TcEpilogue e; e.D = dWv; e.ldd = d;
-    HCA_TRY(launch_gemm_tc(view(pPVg, 0, (int)BN, 1, true), view(cp.V, 0, (int)BN, 1, true), TCP, d, d, (int)BN, e, sk, s));
-  }
-  HCA_TRY(zero_async(dbv, (size_t)d * 4, s));
-  HCA_TRY(launch_colsum(dPV, d, BN, d, dbv, s));
-  if (dV) {  // only when the image features require grad (--vgg_train true)
-    {
-      TcEpilogue e; e.D = dV; e.ldd = d;
-      HCA_TRY(launch_gemm_tc(view(pPVg, 0, (int)BN, 1, false), view(cp.Wv, 0, d, 1, true), TCP, (int)BN, d, d, e, 1, s));
-    }
-    for (int l = 0; l < 3; ++l) {  // dV += dS_l^T Q_l + av_l x gv_l
-      TcEpilogue e; e.D = dV; e.ldd = d; e.d_batch_stride = (int64_t)N * d; e.accumulate = 1;
-      e.rowv = av + l * BN; e.rowv_batch_stride = N; e.r1col = gvhat + (int64_t)l * B * d; e.r1col_batch_stride = d;
-      HCA_TRY(launch_gemm_tc(view(pS, l * BT, T, B, true), view(cp.Q, l * BT, T, B, true), TCP, N, d, T, e, 1, s, B));
-    }
-  }
-  return 0;
+Pl take_pl(Workspace& w, int64_t rows, int cols) {
+  void* p = w.take<char>(pl_bytes(rows, cols));
+  return p ? pl_at(p, rows, cols) : Pl();
+}
+int split_to(const Pl& pl, const float* src, int64_t ld, cudaStream_t s) {
+  return launch_split_planes(src, ld, pl.rows, pl.cols, pl.p, pl.ld, pl.ps, 2, s);
 }
 
 bool v_is_dense(int64_t sb, int64_t sn, int64_t sd, int N, int d) { return sd == 1 && sn == d && sb == (int64_t)N * d; }
@@ -348,237 +315,192 @@ bool v_is_dense(int64_t sb, int64_t sn, int64_t sd, int N, int d) { return sd ==
 }  // namespace
 }  // namespace hca
 
+extern "C" size_t hca_coattn_saved_bytes(int B, int N, int T, int d) { return hca::saved_bytes(B, N, T, d); }
+
 extern "C" size_t hca_coattn_workspace(int B, int N, int T, int d, int need_dv) {
-  using hca::align_up;
+  using namespace hca;
   (void)need_dv;
-  const size_t b = (size_t)B;
-  size_t s = 0;
-  s += align_up(b * N * d * 4);                                // dense copy of V
-  s += align_up(3 * b * N * 4) + align_up(3 * b * T * 4);      // sv/dsv, sq/dsq
-  s += align_up(3 * b * N * d * 4);                            // dZv
-  s += 2 * align_up(3 * b * T * d * 4);                        // dZq, dPQ
-  s += align_up(b * N * d * 4);                                // dPV
-  s += align_up(3 * b * T * N * 4);                            // dS
-  size_t sc = hca::dense_scratch_bytes((int)(b * N), d, d);                    // PV, dV
-  sc = std::max(sc, hca::dense_scratch_bytes(d, d, (int)(b * N)));            // dWv (K = B*N)
-  sc = std::max(sc, hca::dense_scratch_bytes((int)(3 * b * T), d, d));        // dQ += dPQ Wq
-  sc = std::max(sc, hca::dense_scratch_bytes(d, d, (int)(b * T)));            // dWq
-  s += sc;
-  // tensor-core path: bf16x2 planes of V, Q, C, PV, PQ, dZv, dZq, dS, dPQ, dPV and the two weights
-  const size_t pl = 2 * 2 * (6 * b * N * d + 12 * b * T * d + 6 * b * T * (N + 8) + 2 * (size_t)d * d) + 64 * 256;
-  return s + pl + 1024;
+  const int64_t BN = (int64_t)B * N, BT3 = (int64_t)B * 3 * T;
+  size_t fwd = align_up((size_t)BN * d * 4) + 2 * pl_bytes(d, d) + align_up((size_t)3 * B * (N + T) * 4);
+  size_t bwd = 2 * pl_bytes(d, d) + align_up((size_t)3 * B * (N + T) * 4) + pl_bytes(3 * BN, d) + 2 * pl_bytes(BT3, d) + pl_bytes(BT3, N) +
+               align_up((size_t)BN * d * 4) + pl_bytes(BN, d);
+  return std::max(fwd, bwd) + 4096;
 }
 
 extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_t v_sd, const float* q0, const float* q1,
                               const float* q2, const float* Wv, const float* bv, const float* Wq, const float* bq,
                               const float* wv, const float* cv, const float* wq, const float* cq, float* vhat, float* qhat,
-                              float* PV, float* PQ, float* C, float* av, float* aq, int B, int N, int T, int d, void* ws,
-                              size_t ws_bytes, void* stream) {
+                              void* saved, size_t saved_sz, int B, int N, int T, int d, void* ws, size_t ws_bytes, void* stream) {
   using namespace hca;
   cudaStream_t s = (cudaStream_t)stream;
   HCA_CHECK_ARG(V && q0 && q1 && q2 && Wv && bv && Wq && bq && wv && cv && wq && cq, "coattn_fwd: null input");
-  HCA_CHECK_ARG(vhat && qhat && PV && PQ && C && av && aq, "coattn_fwd: null output");
-  HCA_CHECK_ARG(B > 0 && N > 0 && T > 0 && d > 0 && d % 4 == 0, "coattn_fwd: bad sizes B=%d N=%d T=%d d=%d", B, N, T, d);
-  HCA_CHECK_ARG(3 * B <= 65535, "coattn_fwd: batch too large for one call (B=%d)", B);
+  HCA_CHECK_ARG(vhat && qhat && saved, "coattn_fwd: null output");
+  HCA_CHECK_ARG(B > 0 && N > 0 && T > 0 && d > 0 && d % 8 == 0, "coattn_fwd: bad sizes B=%d N=%d T=%d d=%d (d %% 8 == 0 required)", B, N, T, d);
+  HCA_CHECK_ARG(tc_available(), "coattn_fwd: cuTensorMapEncodeTiled is not available from the driver");
+  Saved sv_;
+  HCA_CHECK_ARG(carve_saved(sv_, saved, saved_sz, B, N, T, d), "coattn_fwd: `saved` must be 256-byte aligned and hca_coattn_saved_bytes large");
   Workspace w(ws, ws_bytes);
+  const int64_t BN = (int64_t)B * N, BT3 = (int64_t)B * 3 * T;
+  const int T3 = 3 * T;
   const float* Vd = V;
   if (!v_is_dense(v_sb, v_sn, v_sd, N, d)) {
-    float* vc = w.take<float>((size_t)B * N * d);
+    float* vc = w.take<float>((size_t)BN * d);
     if (!vc) return set_err(HCA_ERR_WORKSPACE, "coattn_fwd: workspace too small");
-    gather_strided_kernel<<<ew_grid((int64_t)B * N * d), 256, 0, s>>>(V, v_sb, v_sn, v_sd, vc, B, N, d);
+    gather_strided_kernel<<<ew_grid(BN * d), 256, 0, s>>>(V, v_sb, v_sn, v_sd, vc, B, N, d);
     HCA_LAUNCHED();
     Vd = vc;
   }
-  float* sv = w.take<float>((size_t)3 * B * N);
-  float* sq = w.take<float>((size_t)3 * B * T);
-  if (!sv || !sq) return set_err(HCA_ERR_WORKSPACE, "coattn_fwd: workspace too small");
-  const float* q[3] = {q0, q1, q2};
-  const int64_t BT = (int64_t)B * T, BN = (int64_t)B * N;
-  if (tc_path_ok(N, d)) {
-    HCA_TRY(zero_async(sv, (size_t)3 * B * N * 4, s));
-    HCA_TRY(zero_async(sq, (size_t)3 * B * T * 4, s));
-    HCA_TRY(coattn_fwd_tc(Vd, q, Wv, bv, Wq, bq, wv, wq, PV, PQ, C, sv, sq, B, N, T, d, w, s));
-    const size_t smem_tc = (64 + (size_t)max(N, T)) * sizeof(float);
-    attn_finish_kernel<<<3 * B, 256, smem_tc, s>>>(sv, sq, cv, cq, Vd, q0, q1, q2, av, aq, vhat, qhat, B, N, T, d);
-    HCA_LAUNCHED();
-    return 0;
+  Pl Wvp = take_pl(w, d, d), Wqp = take_pl(w, d, d);
+  float* sc = w.take<float>((size_t)3 * B * (N + T));
+  if (!Wqp.p || !sc) return set_err(HCA_ERR_WORKSPACE, "coattn_fwd: workspace too small (%zu bytes)", ws_bytes);
+  float* svs = sc;                          // [B][3][N]
+  float* sqs = sc + (size_t)3 * B * N;      // [B][3][T]
+  const Pl &Vp = sv_.V, &Qp = sv_.Q, &PVp = sv_.PV, &PQp = sv_.PQ, &Cp = sv_.C;
+  HCA_TRY(split_to(Vp, Vd, d, s));
+  HCA_TRY(launch_split_planes_stack3(q0, q1, q2, B, T, d, Qp.p, Qp.ld, Qp.ps, s));
+  HCA_TRY(split_to(Wvp, Wv, d, s));
+  HCA_TRY(split_to(Wqp, Wq, d, s));
+  HCA_TRY(zero_async(sc, (size_t)3 * B * (N + T) * 4, s));
+  {  // PV = V Wv^T + bv   (once per step: level independent)
+    TcEpilogue e; e.bias = bv; e.P = plv(PVp, 0, BN, 1);
+    HCA_TRY(launch_gemm_tc(opv(Vp, 0, (int)BN, BN, 1, false), opv(Wvp, 0, d, d, 1, false), 2, (int)BN, d, d, e, 1, s));
   }
-
-  // projections
-  {
-    DenseEpi e; e.bias = bv;
-    HCA_TRY(dense_nt(Vd, d, Wv, d, PV, d, (int)BN, d, d, e, w, s));
+  {  // PQ_all = Q_all Wq^T + bq   (the three levels in one product)
+    TcEpilogue e; e.bias = bq; e.P = plv(PQp, 0, BT3, 1);
+    HCA_TRY(launch_gemm_tc(opv(Qp, 0, (int)BT3, BT3, 1, false), opv(Wqp, 0, d, d, 1, false), 2, (int)BT3, d, d, e, 1, s));
   }
-  for (int l = 0; l < 3; ++l) {
-    DenseEpi e; e.bias = bq;
-    HCA_TRY(dense_nt(q[l], d, Wq, d, PQ + l * BT * d, d, (int)BT, d, d, e, w, s));
+  {  // C_all[b] = tanh(Q_all[b] V[b]^T)
+    TcEpilogue e; e.act_tanh = 1; e.P = plv(Cp, 0, T3, B);
+    HCA_TRY(launch_gemm_tc(opv(Qp, 0, T3, T3, B, false), opv(Vp, 0, N, N, B, false), 2, T3, N, d, e, 1, s, B));
   }
-  // affinity C_l = tanh(Q_l V^T), batched over samples
-  for (int l = 0; l < 3; ++l) {
-    GemmParams g;
-    g.A = {q[l], (int64_t)T * d, d, 1, 0};
-    g.B = {Vd, (int64_t)N * d, d, 1, 0};
-    g.M = T; g.N = N; g.K = d; g.batch = B;
-    g.D = C + l * BT * N; g.d_sb = (int64_t)T * N; g.d_sm = N; g.d_sn = 1;
-    g.act_tanh = 1;
-    HCA_TRY(launch_gemm_ffma(g, false, s));
+  {  // sq[b][(l,t)] = sum_j tanh(PQ_all + C_all PV)[(l,t)][j] wq[j]
+    TcEpilogue e; e.mode = TC_EPI_ROWDOT; e.act_tanh = 1; e.colv = wq; e.red_row = sqs; e.red_row_batch_stride = T3;
+    e.auxp = plv(PQp, 0, T3, B); e.aux_mode = TC_AUX_ADD;
+    HCA_TRY(launch_gemm_tc(opv(Cp, 0, T3, T3, B, false), opv(PVp, 0, N, N, B, true), 2, T3, d, N, e, 1, s, B));
   }
-  HCA_TRY(zero_async(sv, (size_t)3 * B * N * 4, s));
-  HCA_TRY(zero_async(sq, (size_t)3 * B * T * 4, s));
-  {  // sq[z][t] = sum_j tanh(PQ + C PV)[t][j] * wq[j]
-    GemmParams g;
-    g.A = {C, (int64_t)T * N, N, 1, 0};
-    g.B = {PV, (int64_t)N * d, 1, d, B};
-    g.M = T; g.N = d; g.K = N; g.batch = 3 * B;
-    g.add = {PQ, (int64_t)T * d, d, 1, 0};
-    g.act_tanh = 1;
-    g.epi = EPI_ROWDOT; g.colv = wq; g.red_row = sq; g.red_row_sb = T;
-    HCA_TRY(launch_gemm_ffma(g, false, s));
+  {  // sv[b][l][n] = sum_j tanh(PV + C_l^T PQ_l)[n][j] wv[j]      (z = 3 b + l)
+    TcEpilogue e; e.mode = TC_EPI_ROWDOT; e.act_tanh = 1; e.colv = wv; e.red_row = svs; e.red_row_batch_stride = N;
+    e.auxp = plv(PVp, 0, N, B, 3); e.aux_mode = TC_AUX_ADD;
+    HCA_TRY(launch_gemm_tc(opv(Cp, 0, T, T, 3 * B, true), opv(PQp, 0, T, T, 3 * B, true), 2, N, d, T, e, 1, s, 3 * B));
   }
-  {  // sv[z][n] = sum_j tanh(PV + C^T PQ)[n][j] * wv[j]
-    GemmParams g;
-    g.A = {C, (int64_t)T * N, 1, N, 0};
-    g.B = {PQ, (int64_t)T * d, 1, d, 0};
-    g.M = N; g.N = d; g.K = T; g.batch = 3 * B;
-    g.add = {PV, (int64_t)N * d, d, 1, B};
-    g.act_tanh = 1;
-    g.epi = EPI_ROWDOT; g.colv = wv; g.red_row = sv; g.red_row_sb = N;
-    HCA_TRY(launch_gemm_ffma(g, false, s));
-  }
-  const size_t smem = (64 + (size_t)max(N, T)) * sizeof(float);
-  attn_finish_kernel<<<3 * B, 256, smem, s>>>(sv, sq, cv, cq, Vd, q0, q1, q2, av, aq, vhat, qhat, B, N, T, d);
+  const size_t smem = (size_t)3 * (N + T) * sizeof(float);
+  HCA_CHECK_ARG(smem <= 48 * 1024, "coattn_fwd: N + T too large for the softmax kernel");
+  attn_finish_kernel<<<B, 256, smem, s>>>(svs, sqs, cv, cq, Vd, q0, q1, q2, sv_.av, sv_.aq, vhat, qhat, B, N, T, d);
   HCA_LAUNCHED();
   return 0;
 }
 
-extern "C" int hca_coattn_bwd(const float* V, int64_t v_sb, int64_t v_sn, int64_t v_sd, const float* q0, const float* q1,
-                              const float* q2, const float* Wv, const float* Wq, const float* wv, const float* wq,
-                              const float* PV, const float* PQ, const float* C, const float* av, const float* aq,
+extern "C" int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv, const float* wq, const void* saved, size_t saved_sz,
                               const float* gvhat, const float* gqhat, float* dV, float* dQ, float* dWv, float* dbv, float* dWq,
                               float* dbq, float* dwv, float* dcv, float* dwq, float* dcq, int B, int N, int T, int d, void* ws,
                               size_t ws_bytes, void* stream) {
   using namespace hca;
   cudaStream_t s = (cudaStream_t)stream;
-  HCA_CHECK_ARG(V && q0 && q1 && q2 && Wv && Wq && wv && wq && PV && PQ && C && av && aq && gvhat && gqhat, "coattn_bwd: null input");
+  HCA_CHECK_ARG(Wv && Wq && wv && wq && saved && gvhat && gqhat, "coattn_bwd: null input");
   HCA_CHECK_ARG(dQ && dWv && dbv && dWq && dbq && dwv && dcv && dwq && dcq, "coattn_bwd: null output");
-  HCA_CHECK_ARG(B > 0 && N > 0 && T > 0 && d > 0 && d % 4 == 0, "coattn_bwd: bad sizes");
-  HCA_CHECK_ARG(3 * B <= 65535, "coattn_bwd: batch too large for one call (B=%d)", B);
+  HCA_CHECK_ARG(B > 0 && N > 0 && T > 0 && d > 0 && d % 8 == 0, "coattn_bwd: bad sizes");
+  HCA_CHECK_ARG(tc_available(), "coattn_bwd: cuTensorMapEncodeTiled is not available from the driver");
+  Saved sv_;
+  HCA_CHECK_ARG(carve_saved(sv_, const_cast<void*>(saved), saved_sz, B, N, T, d), "coattn_bwd: bad `saved` buffer");
   Workspace w(ws, ws_bytes);
-  const float* Vd = V;
-  if (!v_is_dense(v_sb, v_sn, v_sd, N, d)) {
-    float* vc = w.take<float>((size_t)B * N * d);
-    if (!vc) return set_err(HCA_ERR_WORKSPACE, "coattn_bwd: workspace too small");
-    gather_strided_kernel<<<ew_grid((int64_t)B * N * d), 256, 0, s>>>(V, v_sb, v_sn, v_sd, vc, B, N, d);
-    HCA_LAUNCHED();
-    Vd = vc;
-  }
-  const int64_t BT = (int64_t)B * T, BN = (int64_t)B * N;
-  float* dsv = w.take<float>((size_t)3 * BN);
-  float* dsq = w.take<float>((size_t)3 * BT);
-  float* dZv = w.take<float>((size_t)3 * BN * d);
-  float* dZq = w.take<float>((size_t)3 * BT * d);
-  float* dPQ = w.take<float>((size_t)3 * BT * d);
-  float* dPV = w.take<float>((size_t)BN * d);
-  float* dS = w.take<float>((size_t)3 * BT * N);
-  if (!dS) return set_err(HCA_ERR_WORKSPACE, "coattn_bwd: workspace too small (%zu bytes)", ws_bytes);
-  const float* q[3] = {q0, q1, q2};
+  const int64_t BN = (int64_t)B * N, BT3 = (int64_t)B * 3 * T;
+  const int T3 = 3 * T;
+  const Pl &Vp = sv_.V, &Qp = sv_.Q, &PVp = sv_.PV, &PQp = sv_.PQ, &Cp = sv_.C;
+  Pl Wvp = take_pl(w, d, d), Wqp = take_pl(w, d, d);
+  float* dsc = w.take<float>((size_t)3 * B * (N + T));
+  Pl dZv = take_pl(w, 3 * BN, d);          // [B][3][N][d]
+  Pl dZq = take_pl(w, BT3, d);             // [B][3T][d]
+  Pl dPQ = take_pl(w, BT3, d);
+  Pl dS = take_pl(w, BT3, N);              // [B][3T][N]
+  float* dPVacc = w.take<float>((size_t)BN * d);
+  Pl dPV = take_pl(w, BN, d);
+  if (!dPV.p || !dPVacc || !dsc) return set_err(HCA_ERR_WORKSPACE, "coattn_bwd: workspace too small (%zu bytes)", ws_bytes);
+  float* dsv = dsc;                        // [B][3][N]
+  float* dsq = dsc + (size_t)3 * B * N;    // [B][3][T]
 
+  HCA_TRY(split_to(Wqp, Wq, d, s));
+  if (dV) HCA_TRY(split_to(Wvp, Wv, d, s));
   HCA_TRY(zero_async(dcv, 4, s));
   HCA_TRY(zero_async(dcq, 4, s));
   HCA_TRY(zero_async(dwv, (size_t)d * 4, s));
   HCA_TRY(zero_async(dwq, (size_t)d * 4, s));
-  const size_t smem = (64 + (size_t)max(N, T)) * sizeof(float);
-  attn_bwd_prep_kernel<<<3 * B, 256, smem, s>>>(av, aq, Vd, q0, q1, q2, gvhat, gqhat, dsv, dsq, dcv, dcq, B, N, T, d);
-  HCA_LAUNCHED();
-  if (tc_path_ok(N, d))
-    return coattn_bwd_tc(Vd, q, Wv, Wq, wv, wq, PV, PQ, C, av, aq, gvhat, gqhat, dsv, dsq, dZv, dZq, dPQ, dPV, dS, dV, dQ, dWv, dbv,
-                         dWq, dbq, dwv, dwq, B, N, T, d, w, s);
-  {  // dZv = (dsv x wv) * (1 - Hv^2), Hv recomputed; dwv += Hv^T dsv
-    GemmParams g;
-    g.A = {C, (int64_t)T * N, 1, N, 0};
-    g.B = {PQ, (int64_t)T * d, 1, d, 0};
-    g.M = N; g.N = d; g.K = T; g.batch = 3 * B;
-    g.add = {PV, (int64_t)N * d, d, 1, B};
-    g.act_tanh = 1;
-    g.epi = EPI_DZ; g.rowv = dsv; g.rowv_sb = N; g.colv = wv; g.red_col = dwv;
-    g.D = dZv; g.d_sb = (int64_t)N * d; g.d_sm = d; g.d_sn = 1;
-    HCA_TRY(launch_gemm_ffma(g, false, s));
-  }
-  {  // dZq likewise
-    GemmParams g;
-    g.A = {C, (int64_t)T * N, N, 1, 0};
-    g.B = {PV, (int64_t)N * d, 1, d, B};
-    g.M = T; g.N = d; g.K = N; g.batch = 3 * B;
-    g.add = {PQ, (int64_t)T * d, d, 1, 0};
-    g.act_tanh = 1;
-    g.epi = EPI_DZ; g.rowv = dsq; g.rowv_sb = T; g.colv = wq; g.red_col = dwq;
-    g.D = dZq; g.d_sb = (int64_t)T * d; g.d_sm = d; g.d_sn = 1;
-    HCA_TRY(launch_gemm_ffma(g, false, s));
-  }
-  {  // dPQ = dZq + C dZv
-    GemmParams g;
-    g.A = {C, (int64_t)T * N, N, 1, 0};
-    g.B = {dZv, (int64_t)N * d, 1, d, 0};
-    g.M = T; g.N = d; g.K = N; g.batch = 3 * B;
-    g.add = {dZq, (int64_t)T * d, d, 1, 0};
-    g.D = dPQ; g.d_sb = (int64_t)T * d; g.d_sm = d; g.d_sn = 1;
-    HCA_TRY(launch_gemm_ffma(g, false, s));
-  }
-  for (int l = 0; l < 3; ++l) {  // dPV = sum_l dZv_l + C_l^T dZq_l
-    GemmParams g;
-    g.A = {C + l * BT * N, (int64_t)T * N, 1, N, 0};
-    g.B = {dZq + l * BT * d, (int64_t)T * d, 1, d, 0};
-    g.M = N; g.N = d; g.K = T; g.batch = B;
-    g.add = {dZv + l * BN * d, (int64_t)N * d, d, 1, 0};
-    g.D = dPV; g.d_sb = (int64_t)N * d; g.d_sm = d; g.d_sn = 1;
-    g.accumulate = (l > 0);
-    HCA_TRY(launch_gemm_ffma(g, false, s));
-  }
-  {  // dS = (PQ dZv^T + dZq PV^T) * (1 - C^2)
-    GemmParams g;
-    g.A = {PQ, (int64_t)T * d, d, 1, 0};
-    g.B = {dZv, (int64_t)N * d, d, 1, 0};
-    g.A2 = {dZq, (int64_t)T * d, d, 1, 0};
-    g.B2 = {PV, (int64_t)N * d, d, 1, B};
-    g.M = T; g.N = N; g.K = d; g.K2 = d; g.batch = 3 * B;
-    g.mulx = {C, (int64_t)T * N, N, 1, 0};
-    g.D = dS; g.d_sb = (int64_t)T * N; g.d_sm = N; g.d_sn = 1;
-    HCA_TRY(launch_gemm_ffma(g, false, s));
-  }
-  {  // dQ = dS V + aq x gq
-    GemmParams g;
-    g.A = {dS, (int64_t)T * N, N, 1, 0};
-    g.B = {Vd, (int64_t)N * d, 1, d, B};
-    g.M = T; g.N = d; g.K = N; g.batch = 3 * B;
-    g.r1_row = aq; g.r1r_sb = T; g.r1_col = gqhat; g.r1c_sb = d;
-    g.D = dQ; g.d_sb = (int64_t)T * d; g.d_sm = d; g.d_sn = 1;
-    HCA_TRY(launch_gemm_ffma(g, false, s));
-  }
-  {  // dQ += dPQ Wq
-    DenseEpi e; e.accumulate = 1;
-    HCA_TRY(dense_nn(dPQ, d, Wq, d, dQ, d, (int)(3 * BT), d, d, e, w, s));
-  }
-  // weight gradients (summed over batch and levels)
-  for (int l = 0; l < 3; ++l)
-    HCA_TRY(dense_tn(dPQ + l * BT * d, d, q[l], d, dWq, d, d, d, (int)BT, l == 0, w, s));
-  HCA_TRY(zero_async(dbq, (size_t)d * 4, s));
-  HCA_TRY(launch_colsum(dPQ, d, 3 * BT, d, dbq, s));
-  HCA_TRY(dense_tn(dPV, d, Vd, d, dWv, d, d, d, (int)BN, true, w, s));
   HCA_TRY(zero_async(dbv, (size_t)d * 4, s));
-  HCA_TRY(launch_colsum(dPV, d, BN, d, dbv, s));
-  if (dV) {  // only when the image features require grad (--vgg_train true)
-    DenseEpi e;
-    HCA_TRY(dense_nn(dPV, d, Wv, d, dV, d, (int)BN, d, d, e, w, s));
-    for (int l = 0; l < 3; ++l) {  // dV += dS_l^T Q_l + av_l x gv_l
-      GemmParams g;
-      g.A = {dS + l * BT * N, (int64_t)T * N, 1, N, 0};
-      g.B = {q[l], (int64_t)T * d, 1, d, 0};
-      g.M = N; g.N = d; g.K = T; g.batch = B;
-      g.r1_row = av + l * BN; g.r1r_sb = N; g.r1_col = gvhat + (int64_t)l * B * d; g.r1c_sb = d;
-      g.D = dV; g.d_sb = (int64_t)N * d; g.d_sm = d; g.d_sn = 1;
-      g.accumulate = 1;
-      HCA_TRY(launch_gemm_ffma(g, false, s));
+  HCA_TRY(zero_async(dbq, (size_t)d * 4, s));
+  {
+    const size_t smem = ((size_t)6 * d + 3 * (N + T)) * sizeof(float);
+    HCA_CHECK_ARG(smem <= 48 * 1024, "coattn_bwd: d / N / T too large for the softmax-backward kernel");
+    attn_bwd_prep_kernel<<<B, 256, smem, s>>>(sv_.av, sv_.aq, Vp.p, Vp.ps, Qp.p, Qp.ps, gvhat, gqhat, dsv, dsq, dcv, dcq, B, N, T, d);
+    HCA_LAUNCHED();
+  }
+  for (int l = 0; l < 3; ++l) {
+    // dZv_l = (dsv_l x wv) * (1 - Hv_l^2), Hv_l = tanh(PV + C_l^T PQ_l) recomputed ; dwv += Hv_l^T dsv_l ;
+    // dPVacc (+)= dZv_l  (level 0 stores, levels 1, 2 reduce-add: no memset of the 64 MB accumulator)
+    TcEpilogue e; e.mode = TC_EPI_DZ; e.act_tanh = 1; e.colv = wv; e.rowv = dsv + (int64_t)l * N; e.rowv_batch_stride = 3 * N; e.red_col = dwv;
+    e.auxp = plv(PVp, 0, N, B); e.aux_mode = TC_AUX_ADD;
+    e.P = plv(dZv, (int64_t)l * N, 3 * N, B);
+    e.D = dPVacc; e.ldd = d; e.d_batch_stride = (int64_t)N * d; e.accumulate = (l > 0);
+    HCA_TRY(launch_gemm_tc(opv(Cp, (int64_t)l * T, T, T3, B, true), opv(PQp, (int64_t)l * T, T, T3, B, true), 2, N, d, T, e, 1, s, B));
+  }
+  {  // dZq_all = (dsq x wq) * (1 - Hq^2), Hq = tanh(PQ_all + C_all PV) recomputed ; dwq += Hq^T dsq
+    TcEpilogue e; e.mode = TC_EPI_DZ; e.act_tanh = 1; e.colv = wq; e.rowv = dsq; e.rowv_batch_stride = T3; e.red_col = dwq;
+    e.auxp = plv(PQp, 0, T3, B); e.aux_mode = TC_AUX_ADD;
+    e.P = plv(dZq, 0, T3, B);
+    HCA_TRY(launch_gemm_tc(opv(Cp, 0, T3, T3, B, false), opv(PVp, 0, N, N, B, true), 2, T3, d, N, e, 1, s, B));
+  }
+  {  // dPQ_l^T [d x T] = dZv_l^T C_l^T + dZq_l^T   (z = 3 b + l; long axis d on M, transposed epilogue) ; dbq += sum_t dPQ
+    TcEpilogue e; e.transposed = 1; e.auxp = plv(dZq, 0, T, 3 * B); e.aux_mode = TC_AUX_ADD;
+    e.P = plv(dPQ, 0, T, 3 * B); e.red_row = dbq;
+    HCA_TRY(launch_gemm_tc(opv(dZv, 0, N, N, 3 * B, true), opv(Cp, 0, T, T, 3 * B, false), 2, d, T, N, e, 1, s, 3 * B));
+  }
+  {  // dPV[b] = sum_l dZv_l + C_all[b]^T dZq_all[b]   (K = 3T stacked) ; dbv += sum_n dPV
+    TcEpilogue e; e.aux = dPVacc; e.aux_ld = d; e.aux_batch_stride = (int64_t)N * d; e.aux_nbatch = B; e.aux_mode = TC_AUX_ADD;
+    e.P = plv(dPV, 0, N, B); e.red_col = dbv;
+    HCA_TRY(launch_gemm_tc(opv(Cp, 0, T3, T3, B, true), opv(dZq, 0, T3, T3, B, true), 2, N, d, T3, e, 1, s, B));
+  }
+  {  // dS_l^T [N x T] = (dZv_l PQ_l^T + PV dZq_l^T) * (1 - C_l^T ^2): two operand pairs chained along K, transposed epilogue
+    TcEpilogue e; e.transposed = 1; e.auxp = plv(Cp, 0, T, 3 * B); e.aux_mode = TC_AUX_MUL_1MX2;
+    e.P = plv(dS, 0, T, 3 * B);
+    const TcOperand a2 = opv(PVp, 0, N, N, B, false, 3), b2 = opv(dZq, 0, T, T, 3 * B, false);
+    HCA_TRY(launch_gemm_tc(opv(dZv, 0, N, N, 3 * B, false), opv(PQp, 0, T, T, 3 * B, false), 2, N, T, d, e, 1, s, 3 * B, &a2, &b2, d));
+  }
+  if (T3 <= 128) {
+    // dQ_all[b] = dS_all[b] V[b] + dPQ_all[b] Wq + aq x gq   -> written straight into the [3][B][T][d] layout
+    TcEpilogue e; e.D = dQ; e.ldd = d; e.d_batch_stride = (int64_t)T * d; e.d_groups = 3; e.d_group_stride = (int64_t)B * T * d;
+    e.rowv = sv_.aq; e.rowv_batch_stride = T3; e.r1col = gqhat; e.r1col_batch_stride = d; e.r1_rows_per_group = T;
+    e.r1_group_stride = (int64_t)B * d;
+    const TcOperand a2 = opv(dPQ, 0, T3, T3, B, false), b2 = opv(Wqp, 0, d, d, 1, true);
+    HCA_TRY(launch_gemm_tc(opv(dS, 0, T3, T3, B, false), opv(Vp, 0, N, N, B, true), 2, T3, d, N, e, 1, s, B, &a2, &b2, d));
+  } else {
+    for (int l = 0; l < 3; ++l) {          // long questions: one product per level
+      TcEpilogue e; e.D = dQ + (int64_t)l * B * T * d; e.ldd = d; e.d_batch_stride = (int64_t)T * d;
+      e.rowv = sv_.aq + (int64_t)l * T; e.rowv_batch_stride = T3; e.r1col = gqhat + (int64_t)l * B * d; e.r1col_batch_stride = d;
+      const TcOperand a2 = opv(dPQ, (int64_t)l * T, T, T3, B, false), b2 = opv(Wqp, 0, d, d, 1, true);
+      HCA_TRY(launch_gemm_tc(opv(dS, (int64_t)l * T, T, T3, B, false), opv(Vp, 0, N, N, B, true), 2, T, d, N, e, 1, s, B, &a2, &b2, d));
     }
+  }
+  {  // dWq = dPQ_all^T Q_all over batch, time and the three levels at once (K = 3*B*T, split-K)
+    const int sk = tc_splitk(d, d, (int)BT3);
+    if (sk > 1) HCA_TRY(zero_async(dWq, (size_t)d * d * 4, s));
+    TcEpilogue e; e.D = dWq; e.ldd = d;
+    HCA_TRY(launch_gemm_tc(opv(dPQ, 0, (int)BT3, BT3, 1, true), opv(Qp, 0, (int)BT3, BT3, 1, true), 2, d, d, (int)BT3, e, sk, s));
+  }
+  {  // dWv = dPV^T V   (K = B*N, split-K)
+    const int sk = tc_splitk(d, d, (int)BN);
+    if (sk > 1) HCA_TRY(zero_async(dWv, (size_t)d * d * 4, s));
+    TcEpilogue e; e.D = dWv; e.ldd = d;
+    HCA_TRY(launch_gemm_tc(opv(dPV, 0, (int)BN, BN, 1, true), opv(Vp, 0, (int)BN, BN, 1, true), 2, d, d, (int)BN, e, sk, s));
+  }
+  if (dV) {  // only when the image features require grad (--vgg_train true)
+    {  // dV = dPV Wv
+      TcEpilogue e; e.D = dV; e.ldd = d;
+      HCA_TRY(launch_gemm_tc(opv(dPV, 0, (int)BN, BN, 1, false), opv(Wvp, 0, d, d, 1, true), 2, (int)BN, d, d, e, 1, s));
+    }
+    {  // dV[b] += dS_all[b]^T Q_all[b]   (K = 3T stacked)
+      TcEpilogue e; e.D = dV; e.ldd = d; e.d_batch_stride = (int64_t)N * d; e.accumulate = 1;
+      HCA_TRY(launch_gemm_tc(opv(dS, 0, T3, T3, B, true), opv(Qp, 0, T3, T3, B, true), 2, N, d, T3, e, 1, s, B));
+    }
+    dv_rank3_kernel<<<ew_grid(BN * (d / 4)), 256, 0, s>>>(dV, sv_.av, gvhat, B, N, d);
+    HCA_LAUNCHED();
   }
   return 0;
 }

@@ -1,19 +1,23 @@
-// tcgen05 / TMEM / TMA GEMM on split-bf16 operand planes (sm_100a), optionally batched, with fused epilogues.
+// tcgen05 / TMEM / TMA GEMM on split-bf16 operand planes (sm_100a): persistent, batched, with fused epilogues.
 //
 // fp32 operands are decomposed into P bf16 "planes"  x = x0 + x1 (+ x2),  x_{i+1} = bf16(x - x0 - .. - x_i),
 // and the product is accumulated in fp32 TMEM from the plane pairs (i,j) with i + j < P:
-//     P = 1 : 1 MMA   (plain bf16,            ~2^-8  operand precision)
-//     P = 2 : 3 MMAs  (bf16x2 split,          ~2^-16)   <- default: meets the 1e-3 budget with margin
+//     P = 2 : 3 MMAs  (bf16x2 split, ~2^-16 operand precision)   <- default: meets the 1e-3 budget with margin
 //     P = 3 : 6 MMAs  (bf16x3 split, ~fp32; the TMEM accumulation itself truncates at ~K * 2^-24)
-// The smem tiles of one k-block are loaded once by TMA and reused by all plane pairs, so a P=2 k-block does
-// 3 MMAs on 4 tiles (better smem/L2 reuse than a plain bf16 GEMM of the same tile shape).
+// The smem tiles of one k-block are loaded once by TMA and reused by all plane pairs.
 //
-// One CTA = one 128 x 128 output tile of one batch entry (x one split-K slice): warp 0 = TMA producer, warp 1 =
-// TMEM allocator + tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> fused math -> swizzled smem -> TMA
-// tile store / reduce-add).  Operands may be K-major ([rows, K]) or MN-major ([K, rows]) -- both through
-// 128-byte-swizzled TMA boxes and the matching UMMA shared-memory descriptors -- so NT (forward), NN (dgrad) and
-// TN (wgrad) products need no transposes in HBM.  A second operand pair may be chained along K
-// (D = A.B^T + A2.B2^T in one accumulator).
+// One persistent CTA per SM walks a static round-robin schedule of 128 x BN output tiles (batch entry z, M tile, N tile,
+// split-K slice): warp 0 = TMA producer, warp 1 = TMEM allocator + tcgen05.mma issuer, warps 2..5 = epilogue.  The fp32
+// accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the mainloop of tile i+1.
+// Operands may be K-major ([rows, K]) or MN-major ([K, rows]) -- both through 128-byte-swizzled TMA boxes and the matching
+// UMMA shared-memory descriptors -- so NT (forward), NN (dgrad) and TN (wgrad) products and per-sample batches need no
+// transposes in HBM.  A second operand pair may be chained along K (D = A.B^T + A2.B2^T in one accumulator).
+//
+// Epilogue (tcgen05.ld -> registers -> fused math -> swizzled smem -> TMA): the result can be written as fp32 (store or
+// reduce-add), as bf16 hi/lo planes ready to be the operand of the next product (no fp32 round trip through HBM, no
+// separate split pass), or both; or reduced on the fly (row dots, column sums).  BN = 32 instantiations run the
+// "transposed" epilogue: the tile is written / its addend read as [n][m] with plain coalesced global accesses, which is
+// how the products whose long dimension sits on M hand their result to consumers that want it K-major.
 #pragma once
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -25,34 +29,53 @@ struct TcOperand {
   int64_t ld = 0;                         // elements, multiple of 8
   int64_t plane_stride = 0;               // elements between planes, multiple of 8
   int64_t batch_stride = 0;               // elements between batch entries, multiple of 8 (0 when nbatch == 1)
-  int nbatch = 1;                         // batch entries present in memory; entry used = z % nbatch
+  int nbatch = 1;                         // batch entries present in memory; entry used = (z / zdiv) % nbatch
+  int zdiv = 1;
   int rows = 0, cols = 0;                 // K-major: rows = M|N, cols = K.  MN-major: rows = K, cols = M|N
   bool mn_major = false;
 };
 
+// bf16 hi/lo planes of a [batch][rows][ld] matrix (always 2 planes)
+struct TcPlanes {
+  __nv_bfloat16* p = nullptr;
+  int64_t ld = 0, plane_stride = 0, batch_stride = 0;   // elements, multiples of 8
+  int nbatch = 1, zdiv = 1;                              // entry = (z / zdiv) % nbatch  (inputs) ; z (outputs)
+};
+
 enum TcEpiMode : int {
-  TC_EPI_STORE = 0,   // D[z] (+)= f
+  TC_EPI_STORE = 0,   // D[z] (+)= f  and / or  planes(f)
   TC_EPI_ROWDOT = 1,  // red_row[z][m] += sum_n f[m][n] * colv[n]                     (nothing stored)
-  TC_EPI_DZ = 2,      // D[z] = rowv[z][m] * colv[n] * (1 - f^2) ; red_col[n] += sum_m f[m][n] * rowv[z][m]
+  TC_EPI_DZ = 2,      // g = rowv[z][m] * colv[n] * (1 - f^2) ; red_col[n] += sum_m f[m][n] * rowv[z][m] ; store g like STORE
 };
 enum TcAuxMode : int { TC_AUX_NONE = 0, TC_AUX_ADD = 1 /* f = act(acc + aux) */, TC_AUX_MUL_1MX2 = 2 /* f *= 1 - aux^2 */ };
 
-// f = act( acc + bias[z][n] + (aux if ADD) ) ; then (+ rowv[z][m] * r1col[z][n]) ; then (* (1 - aux^2) if MUL) ; then mode
+// f = act( acc + bias[z][n] + (aux if ADD) ) ; then (+ rowv[z][m] * r1col[z][group(m)][n]) ; then (* (1 - aux^2) if MUL) ; then mode
 struct TcEpilogue {
+  // fp32 output (optional).  Rows may be grouped: row m of the tile = group g = m / (M / d_groups), i = m % (M / d_groups),
+  // stored at D + z * d_batch_stride + g * d_group_stride + i * ldd   (d_groups > 1 needs M <= 128).
   float* D = nullptr;
   int64_t ldd = 0, d_batch_stride = 0;
+  int d_zdiv = 1;                                         // entry = z / d_zdiv (several z reduce-add into one entry)
+  int d_groups = 1;  int64_t d_group_stride = 0;
+  int accumulate = 0;                                     // D += result
+  TcPlanes P;                                             // bf16 hi/lo planes output (optional)
   const float* bias = nullptr;  int64_t bias_batch_stride = 0;
   int act_tanh = 0;
-  const float* mulx = nullptr;  int64_t mulx_ld = 0;     // legacy per-row (1 - x^2) factor, un-batched, read directly
-  int accumulate = 0;                                     // D += result
+  const float* mulx = nullptr;  int64_t mulx_ld = 0;     // per-element (1 - x^2) factor, un-batched, read directly
   int mode = TC_EPI_STORE;
-  // aux tile [M, N] fp32 per batch entry (entry = z % aux_nbatch), fetched by TMA: needs 16-byte aligned rows
-  const float* aux = nullptr;  int64_t aux_ld = 0, aux_batch_stride = 0;  int aux_nbatch = 1;  int aux_mode = TC_AUX_NONE;
+  // addend / factor tile [M, N] per batch entry, fetched by TMA: either fp32 (aux) or bf16 hi/lo planes (auxp)
+  const float* aux = nullptr;  int64_t aux_ld = 0, aux_batch_stride = 0;  int aux_nbatch = 1, aux_zdiv = 1;
+  TcPlanes auxp;
+  int aux_mode = TC_AUX_NONE;
   const float* rowv = nullptr;  int64_t rowv_batch_stride = 0;      // [z][m]
   const float* colv = nullptr;                                      // [n]
-  const float* r1col = nullptr; int64_t r1col_batch_stride = 0;     // rank-1 term rowv[z][m] * r1col[z][n]
+  const float* r1col = nullptr; int64_t r1col_batch_stride = 0;     // rank-1 term rowv[z][m] * r1col[z][g][n]
+  int r1_rows_per_group = 0;    int64_t r1_group_stride = 0;        // g = m / r1_rows_per_group (0: one group)
   float* red_row = nullptr;     int64_t red_row_batch_stride = 0;
-  float* red_col = nullptr;
+  float* red_col = nullptr;                                         // DZ: see above.  STORE: red_col[n] += sum_m f[m][n]
+  // BN = 32 "transposed" epilogue: outputs and auxp are addressed [z][n][m] (ld = their leading dimension over m); fp32 D,
+  // planes P, auxp (ADD / MUL_1MX2) and red_row (un-batched: red_row[m] += sum_n f[m][n]) are supported, nothing else.
+  int transposed = 0;
 };
 
 // D[z][M,N] (+)= A[z] . B[z]^T (+ A2[z] . B2[z]^T with inner size K2) for z < batch.  splitk >= 1 (un-batched only).
@@ -62,6 +85,9 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
 // fp32 [rows, cols] (leading dim ld) -> P bf16 planes [P][rows][ldp]
 int launch_split_planes(const float* src, int64_t ld, int64_t rows, int cols, __nv_bfloat16* planes, int64_t ldp,
                         int64_t plane_stride, int P, cudaStream_t s);
+// three fp32 sources [B][T][cols] -> stacked bf16 hi/lo planes [2][B][3*T][ldp]  (rows of sample b: level-major, then t)
+int launch_split_planes_stack3(const float* s0, const float* s1, const float* s2, int B, int T, int cols, __nv_bfloat16* planes,
+                               int64_t ldp, int64_t plane_stride, cudaStream_t s);
 
 bool tc_available();   // TMA descriptor encoder resolved from the driver
 // debug: record per-CTA clock64 stamps of the next gemm_tc launches into buf [nctas][64] (nullptr disables)

@@ -168,10 +168,11 @@ phrase_conv_pool.register_autograd(_pcp_backward, setup_context=_pcp_setup)
 # ------------------------------------------------------------------------------------------------ co-attention
 @torch.library.custom_op(f"{NS}::coattn", mutates_args=(), device_types="cuda")
 def coattn(V: Tensor, q0: Tensor, q1: Tensor, q2: Tensor, Wv: Tensor, bv: Tensor, Wq: Tensor, bq: Tensor, wv: Tensor,
-           cv: Tensor, wq: Tensor, cq: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+           cv: Tensor, wq: Tensor, cq: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     """ParallelCoAttention over the three question levels (reference model.py:356-397).
 
-    Returns (vhat [3,B,d], qhat [3,B,d]) and the tensors saved for backward (PV, PQ, C, av, aq).
+    Returns (vhat [3,B,d], qhat [3,B,d], saved) where ``saved`` is the opaque buffer the backward kernel reads
+    (bf16 operand planes of V / Q / PV / PQ / C and the attention weights; layout private to the library).
     V may be any strided [B,N,d] view (the reference passes a permuted VGG feature map)."""
     _cuda_f32(V, q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq)
     q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq = map(_c, (q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq))
@@ -180,33 +181,34 @@ def coattn(V: Tensor, q0: Tensor, q1: Tensor, q2: Tensor, Wv: Tensor, bv: Tensor
     dev = V.device
     f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     vhat, qhat = f(3, B, d), f(3, B, d)
-    PV, PQ, Cm, av, aq = f(B, N, d), f(3, B, T, d), f(3, B, T, N), f(3, B, N), f(3, B, T)
     L = _lib.lib()
     with torch.cuda.device(dev):
+        saved = _ws(L.hca_coattn_saved_bytes(B, N, T, d), dev)
         ws = _ws(L.hca_coattn_workspace(B, N, T, d, 0), dev)
         _lib.check(L.hca_coattn_fwd(_ptr(V), V.stride(0), V.stride(1), V.stride(2), _ptr(q0), _ptr(q1), _ptr(q2), _ptr(Wv), _ptr(bv),
-                                    _ptr(Wq), _ptr(bq), _ptr(wv), _ptr(cv), _ptr(wq), _ptr(cq), _ptr(vhat), _ptr(qhat), _ptr(PV),
-                                    _ptr(PQ), _ptr(Cm), _ptr(av), _ptr(aq), B, N, T, d, _ptr(ws), ws.numel(), _stream()), "coattn_fwd")
-    return vhat, qhat, PV, PQ, Cm, av, aq
+                                    _ptr(Wq), _ptr(bq), _ptr(wv), _ptr(cv), _ptr(wq), _ptr(cq), _ptr(vhat), _ptr(qhat), _ptr(saved),
+                                    saved.numel(), B, N, T, d, _ptr(ws), ws.numel(), _stream()), "coattn_fwd")
+    return vhat, qhat, saved
 
 
 @coattn.register_fake
 def _(V, q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq):
     B, N, d = V.shape
     T = q0.shape[1]
-    f = lambda *s: V.new_empty(*s)
-    return f(3, B, d), f(3, B, d), f(B, N, d), f(3, B, T, d), f(3, B, T, N), f(3, B, N), f(3, B, T)
+    r8 = lambda x: (x + 7) // 8 * 8
+    al = lambda x: (x + 255) // 256 * 256
+    pl = lambda rows, cols: al(2 * rows * r8(cols) * 2)
+    nbytes = 2 * pl(B * N, d) + 2 * pl(B * 3 * T, d) + pl(B * 3 * T, N) + al(B * 3 * N * 4) + al(B * 3 * T * 4) + 256
+    return V.new_empty(3, B, d), V.new_empty(3, B, d), V.new_empty(nbytes, dtype=torch.uint8)
 
 
 @torch.library.custom_op(f"{NS}::coattn_bwd", mutates_args=(), device_types="cuda")
-def coattn_bwd(V: Tensor, q0: Tensor, q1: Tensor, q2: Tensor, Wv: Tensor, Wq: Tensor, wv: Tensor, wq: Tensor, PV: Tensor,
-               PQ: Tensor, Cm: Tensor, av: Tensor, aq: Tensor, gv: Tensor, gq: Tensor, need_dv: bool
+def coattn_bwd(Wv: Tensor, Wq: Tensor, wv: Tensor, wq: Tensor, saved: Tensor, gv: Tensor, gq: Tensor, N: int, T: int, need_dv: bool
                ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    _cuda_f32(V, q0, q1, q2, Wv, Wq, wv, wq, PV, PQ, Cm, av, aq, gv, gq)
-    q0, q1, q2, Wv, Wq, wv, wq, gv, gq = map(_c, (q0, q1, q2, Wv, Wq, wv, wq, gv, gq))
-    B, N, d = V.shape
-    T = q0.shape[1]
-    dev = V.device
+    _cuda_f32(Wv, Wq, wv, wq, gv, gq)
+    Wv, Wq, wv, wq, gv, gq = map(_c, (Wv, Wq, wv, wq, gv, gq))
+    _, B, d = gv.shape
+    dev = gv.device
     f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     dV = f(B, N, d) if need_dv else f(0)
     dQ = f(3, B, T, d)
@@ -215,31 +217,30 @@ def coattn_bwd(V: Tensor, q0: Tensor, q1: Tensor, q2: Tensor, Wv: Tensor, Wq: Te
     L = _lib.lib()
     with torch.cuda.device(dev):
         ws = _ws(L.hca_coattn_workspace(B, N, T, d, int(need_dv)), dev)
-        _lib.check(L.hca_coattn_bwd(_ptr(V), V.stride(0), V.stride(1), V.stride(2), _ptr(q0), _ptr(q1), _ptr(q2), _ptr(Wv), _ptr(Wq),
-                                    _ptr(wv), _ptr(wq), _ptr(PV), _ptr(PQ), _ptr(Cm), _ptr(av), _ptr(aq), _ptr(gv), _ptr(gq),
+        _lib.check(L.hca_coattn_bwd(_ptr(Wv), _ptr(Wq), _ptr(wv), _ptr(wq), _ptr(saved), saved.numel(), _ptr(gv), _ptr(gq),
                                     _ptr(dV) if need_dv else None, _ptr(dQ), _ptr(dWv), _ptr(dbv), _ptr(dWq), _ptr(dbq), _ptr(dwv),
                                     _ptr(dcv), _ptr(dwq), _ptr(dcq), B, N, T, d, _ptr(ws), ws.numel(), _stream()), "coattn_bwd")
     return dV, dQ, dWv, dbv, dWq, dbq, dwv, dcv, dwq, dcq
 
 
 @coattn_bwd.register_fake
-def _(V, q0, q1, q2, Wv, Wq, wv, wq, PV, PQ, Cm, av, aq, gv, gq, need_dv):
-    B, N, d = V.shape
-    T = q0.shape[1]
-    f = lambda *s: V.new_empty(*s)
+def _(Wv, Wq, wv, wq, saved, gv, gq, N, T, need_dv):
+    _, B, d = gv.shape
+    f = lambda *s: gv.new_empty(*s)
     return (f(B, N, d) if need_dv else f(0), f(3, B, T, d), f(d, d), f(d), f(d, d), f(d), f(d), f(1), f(d), f(1))
 
 
 def _coattn_setup(ctx, inputs, output):
     V, q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq = inputs
-    vhat, qhat, PV, PQ, Cm, av, aq = output
-    ctx.save_for_backward(V, q0, q1, q2, Wv, Wq, wv, wq, PV, PQ, Cm, av, aq)
+    vhat, qhat, saved = output
+    ctx.save_for_backward(Wv, Wq, wv, wq, saved)
     ctx.shapes = (wv.shape, cv.shape, wq.shape, cq.shape)
+    ctx.NT = (V.shape[1], q0.shape[1])
     ctx.set_materialize_grads(False)
 
 
 def _coattn_backward(ctx, gv, gq, *_unused):
-    V, q0, q1, q2, Wv, Wq, wv, wq, PV, PQ, Cm, av, aq = ctx.saved_tensors
+    Wv, Wq, wv, wq, saved = ctx.saved_tensors
     if gv is None and gq is None:
         return (None,) * 12
     if gv is None:
@@ -247,7 +248,8 @@ def _coattn_backward(ctx, gv, gq, *_unused):
     if gq is None:
         gq = torch.zeros_like(gv)
     need_dv = ctx.needs_input_grad[0]
-    dV, dQ, dWv, dbv, dWq, dbq, dwv, dcv, dwq, dcq = coattn_bwd(V, q0, q1, q2, Wv, Wq, wv, wq, PV, PQ, Cm, av, aq, gv, gq, need_dv)
+    N, T = ctx.NT
+    dV, dQ, dWv, dbv, dWq, dbq, dwv, dcv, dwq, dcq = coattn_bwd(Wv, Wq, wv, wq, saved, gv, gq, N, T, need_dv)
     s_wv, s_cv, s_wq, s_cq = ctx.shapes
     return ((dV if need_dv else None), dQ[0], dQ[1], dQ[2], dWv, dbv, dWq, dbq, dwv.view(s_wv), dcv.view(s_cv), dwq.view(s_wq),
             dcq.view(s_cq))
