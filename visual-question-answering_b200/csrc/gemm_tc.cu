@@ -1,6 +1,7 @@
 // tcgen05 / TMEM / TMA split-bf16 GEMM, persistent with a double-buffered TMEM accumulator (see gemm_tc.cuh).  sm_100a only.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include "gemm_tc.cuh"
@@ -11,11 +12,10 @@ namespace {
 using namespace ptx;
 
 constexpr int BM = 128;               // UMMA M (cta_group::1): TMEM lane i <-> output row i
-constexpr int BK = 64;                // bf16 elements per k-block = 128 bytes = one SWIZZLE_128B span
 constexpr int UMMA_K = 16;            // bf16
-constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int MAX_STAGES = 6;
-constexpr int NUM_THREADS = 192;      // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int NUM_EG = 2;             // epilogue warp groups (4 warps each: one per TMEM lane quadrant)
+constexpr int NUM_THREADS = 64 + 128 * NUM_EG;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 / 6..9 epilogue groups 0 / 1
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr uint32_t CHUNK_BYTES = BM * 128;    // one [128 rows][32 fp32] staging tile = two [128 rows][32 bf16] plane tiles
 
@@ -25,7 +25,8 @@ struct TcParams {
   int tiles_m, tiles_n, total_tiles;
   int a_nb, a_zd, b_nb, b_zd, a2_nb, a2_zd, b2_nb, b2_zd;   // operand batch entry = (z / zd) % nb
   uint32_t off_store, off_pstore, off_aux;                   // byte offsets of the epilogue staging areas from the smem base
-  int store_nbuf;                                            // staging buffers per output kind (2 = double-buffered, 1 when smem is tight)
+  int store_nbuf;                                            // staging buffers per output kind and epilogue group (2 = double-buffered)
+  int n_eg;                                                  // active epilogue groups: 2 for epilogue-bound products (alternate 32-column chunks)
   // fp32 output
   float* D;
   int64_t ldd, d_sb;
@@ -69,21 +70,41 @@ __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u <<
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
 // ------------------------------------------------------------------------------------------------------ kernel
-template <int BN, int P, bool A_MN, bool B_MN>
+// Column sums over the 32 lanes of a warp of 32 per-lane values: on return lane j holds sum_lanes v[j].  Butterfly
+// "transpose-reduce": 31 shuffles instead of the 160 of 32 independent warp reductions.
+__device__ __forceinline__ float col_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float send = up ? v[j] : v[j + off];
+      const float keep = up ? v[j + off] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN, int P, bool A_MN, bool B_MN, int BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  static_assert(BK == 64 || (BK == 32 && A_MN && B_MN), "BK = 32 k-blocks are for MN-major operand pairs (short contractions)");
+  constexpr int A_TILE_BYTES = BM * BK * 2;
   constexpr int B_TILE_BYTES = BN * BK * 2;
+  constexpr uint32_t MN_CHUNK_BYTES = 64 * BK * 2;       // one TMA box of an MN-major tile: [BK k][64 mn]
   constexpr uint32_t stage_bytes = P * (A_TILE_BYTES + B_TILE_BYTES);
   constexpr int CHUNKS = BN / 32;
   constexpr uint32_t TMEM_COLS = 2 * BN;                 // two accumulator buffers (64 or 256 columns: powers of two >= 32)
   constexpr int BNV = BN < 128 ? 128 : BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
-  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 6];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 4 + NUM_EG];
   __shared__ uint32_t tmem_ptr_smem;
-  __shared__ __align__(16) float bias_sm[BNV];         // this tile's bias slice (per batch entry)
-  __shared__ __align__(16) float colv_sm[BNV];         // colv (ROWDOT / DZ)
-  __shared__ __align__(16) float r1_sm[4][BNV];        // rank-1 column vectors, one per row group
-  __shared__ float colred_sm[BNV];                     // column partial sums of the four epilogue warps
+  // per epilogue group: this tile's per-column vectors
+  __shared__ __align__(16) float bias_sm[NUM_EG][BNV];      // bias slice (per batch entry)
+  __shared__ __align__(16) float colv_sm[NUM_EG][BNV];      // colv (ROWDOT / DZ)
+  __shared__ __align__(16) float r1_sm[NUM_EG][4][BNV];     // rank-1 column vectors, one per row group
+  __shared__ float colred_sm[NUM_EG][BNV];                  // column partial sums of the group's four warps
 
   // warp index through a shuffle: provably warp-uniform for ptxas, so the role branches below are uniform control flow and
   // the MMA descriptors live in uniform registers (otherwise every tcgen05.mma pays an ELECT + VOTEU + 4x R2UR.BROADCAST
@@ -94,7 +115,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   auto empty_bar = [&](int s) { return smem_u32(&bars[MAX_STAGES + s]); };
   auto tmem_full_bar = [&](int a) { return smem_u32(&bars[2 * MAX_STAGES + a]); };
   auto tmem_empty_bar = [&](int a) { return smem_u32(&bars[2 * MAX_STAGES + 2 + a]); };
-  auto aux_bar = [&](int b) { return smem_u32(&bars[2 * MAX_STAGES + 4 + b]); };
+  auto aux_bar = [&](int g) { return smem_u32(&bars[2 * MAX_STAGES + 4 + g]); };
   auto a_tile = [&](int s, int pl) { return smem_base + s * stage_bytes + pl * A_TILE_BYTES; };
   auto b_tile = [&](int s, int pl) { return smem_base + s * stage_bytes + P * A_TILE_BYTES + pl * B_TILE_BYTES; };
   auto decode = [&](int t) {
@@ -126,9 +147,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 4);       // one arrival per epilogue warp
-      mbar_init(aux_bar(a), 1);
+      // one arrival per epilogue warp that drains the buffer: BN = 32 tiles go to ONE group each, wider tiles to all groups
+      mbar_init(tmem_empty_bar(a), BN == 32 ? 4 : 4 * p.n_eg);
     }
+    for (int g = 0; g < NUM_EG; ++g) mbar_init(aux_bar(g), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.A) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.B) : "memory");
@@ -166,13 +188,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               tma_load_4d(a_tile(s, pl), ma, full_bar(s), k0, tc.m0, pl, za);
             } else {
 #pragma unroll
-              for (int c = 0; c < BM / 64; ++c) tma_load_4d(a_tile(s, pl) + c * 8192, ma, full_bar(s), tc.m0 + c * 64, k0, pl, za);
+              for (int c = 0; c < BM / 64; ++c) tma_load_4d(a_tile(s, pl) + c * MN_CHUNK_BYTES, ma, full_bar(s), tc.m0 + c * 64, k0, pl, za);
             }
             if (!B_MN) {
               tma_load_4d(b_tile(s, pl), mb, full_bar(s), k0, tc.n0, pl, zb);
             } else if (BN >= 64) {
 #pragma unroll
-              for (int c = 0; c < BN / 64; ++c) tma_load_4d(b_tile(s, pl) + c * 8192, mb, full_bar(s), tc.n0 + c * 64, k0, pl, zb);
+              for (int c = 0; c < BN / 64; ++c) tma_load_4d(b_tile(s, pl) + c * MN_CHUNK_BYTES, mb, full_bar(s), tc.n0 + c * 64, k0, pl, zb);
             }
           }
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -186,11 +208,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     // smem descriptor halves (cute::UMMA::SmemDescriptor): hi = SBO(1024 B) | version 1 | SWIZZLE_128B, constant;
-    // lo = (addr >> 4) | (LBO >> 4) << 16.  K-major: LBO unused (16 B), K slice = +32 B.  MN-major: LBO = 8192 B
-    // between 64-wide MN chunks, K slice of 16 rows = +2048 B.  Everything below is warp-uniform integer arithmetic,
+    // lo = (addr >> 4) | (LBO >> 4) << 16.  K-major: LBO unused (16 B), K slice = +32 B.  MN-major: LBO = one [BK k][64 mn]
+    // box between 64-wide MN chunks, K slice of 16 rows = +2048 B.  Everything below is warp-uniform integer arithmetic,
     // so ptxas keeps it on the uniform datapath (no per-MMA ELECT / R2UR.BROADCAST sequence).
     constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    constexpr uint32_t a_lbo = (A_MN ? (8192u >> 4) : 1u) << 16, b_lbo = (B_MN ? (8192u >> 4) : 1u) << 16;
+    constexpr uint32_t a_lbo = (A_MN ? (MN_CHUNK_BYTES >> 4) : 1u) << 16, b_lbo = (B_MN ? (MN_CHUNK_BYTES >> 4) : 1u) << 16;
     constexpr uint32_t a_kstep = A_MN ? (2048u >> 4) : (32u >> 4), b_kstep = B_MN ? (2048u >> 4) : (32u >> 4);
     int s = 0;
     uint32_t ph = 0;
@@ -211,14 +233,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         // uniform-register adds of compile-time constants
         const uint32_t au = __shfl_sync(0xffffffffu, a0, 0), bu = __shfl_sync(0xffffffffu, b0, 0);
         const uint32_t first = __shfl_sync(0xffffffffu, it == 0 ? 0u : 1u, 0);
+        // K slices of this block that hold data (the tail of K is zero-filled by TMA: skip those MMAs)
+        const int kb = tc.kb_begin + it;
+        const int kleft = kb >= p.kb1 ? p.K2 - (kb - p.kb1) * BK : p.K - kb * BK;
+        const int nks = __shfl_sync(0xffffffffu, min(BK / UMMA_K, (kleft + UMMA_K - 1) / UMMA_K), 0);
 #pragma unroll
         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          if (ks < nks) {
 #pragma unroll
-          for (int i = 0; i < P; ++i) {
+            for (int i = 0; i < P; ++i) {
 #pragma unroll
-            for (int j = 0; j < P - i; ++j) {
-              umma_bf16_elect32(d_tmem, au + i * (A_TILE_BYTES >> 4) + ks * a_kstep, desc_hi,
-                                bu + j * (B_TILE_BYTES >> 4) + ks * b_kstep, desc_hi, idesc, (ks | i | j) != 0 ? 1u : first);
+              for (int j = 0; j < P - i; ++j) {
+                umma_bf16_elect32(d_tmem, au + i * (A_TILE_BYTES >> 4) + ks * a_kstep, desc_hi,
+                                  bu + j * (B_TILE_BYTES >> 4) + ks * b_kstep, desc_hi, idesc, (ks | i | j) != 0 ? 1u : first);
+              }
             }
           }
         }
@@ -235,23 +263,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       umma_commit_elect(tmem_full_bar(acc));  // accumulator complete -> epilogue
       if (tl && lane == 0 && tile_it == 0) tl[3] = clock64();
     }
-  } else {
+  } else if (((warp - 2) >> 2) < p.n_eg) {
     // ===================================================================== epilogue: TMEM -> registers -> (smem -> TMA) global
+    // Two groups of four warps.  Wide tiles: group g takes the 32-column chunks c = g, g + n_eg, ... of EVERY tile (its own
+    // staging / addend buffers, named barrier and TMA-store queue), so the latency of one group's TMEM loads, MUFU chains,
+    // barriers and stores is covered by the other's arithmetic.  BN = 32 tiles: the groups alternate tiles.
+    const int eg = (warp - 2) >> 2;
+    const int neg = p.n_eg;
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;            // row inside the tile
-    const int et = threadIdx.x - 64;        // 0..127
-    const bool leader = (warp == 2 && lane == 0);
+    const int et = threadIdx.x - 64 - eg * 128;   // 0..127 inside the group
+    const bool leader = (et == 0);
+    const uint32_t bar_id = 1u + (uint32_t)eg;
+    auto epi_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
     int tile_it = 0;
     if constexpr (BN == 32) {
       // ------------------------------------------------------------------ transposed epilogue (direct, coalesced global I/O)
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
+        if ((tile_it & (neg - 1)) != eg) continue;
         const TileCoord tc = decode(t);
         const int acc = tile_it & 1;
         const int row = tc.m0 + r;
         const bool row_ok = row < p.M;
         mbar_wait(tmem_full_bar(acc), (tile_it >> 1) & 1, 3);
         tc_fence_after();
-        if (tl && threadIdx.x == 64 && tile_it == 0) tl[4] = clock64();
+        if (tl && et == 0 && tile_it == 0) tl[4] = clock64();
         uint32_t v[32];
         __syncwarp();
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN), v);
@@ -302,7 +338,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
           if (p.red_row) atomicAdd(p.red_row + row, rsum);
         }
-        if (tl && threadIdx.x == 64 && tile_it == 0) tl[5] = clock64();
+        if (tl && et == 0 && tile_it == 0) tl[5] = clock64();
       }
     } else {
       // ------------------------------------------------------------------ standard epilogue
@@ -310,24 +346,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const bool do_pl = (p.P != nullptr) && p.mode != TC_EPI_ROWDOT;
       const bool stage_tma = (do_f32 && p.tma_store) || do_pl;
       const bool want_colred = (p.red_col != nullptr);
-      uint32_t gc = 0;                        // chunks processed so far (staging / aux double-buffer index and phase)
-      auto issue_aux = [&](const TileCoord& c, int chunk, uint32_t buf) {
-        const uint32_t dst = smem_base + p.off_aux + buf * CHUNK_BYTES;
+      float* const bias_s = bias_sm[eg];
+      float* const colv_s = colv_sm[eg];
+      float* const colred_s = colred_sm[eg];
+      const uint32_t store_base = smem_base + p.off_store + (uint32_t)(eg * p.store_nbuf) * CHUNK_BYTES;
+      const uint32_t pstore_base = smem_base + p.off_pstore + (uint32_t)(eg * p.store_nbuf) * CHUNK_BYTES;
+      const uint32_t aux_base = smem_base + p.off_aux + (uint32_t)eg * CHUNK_BYTES;
+      uint32_t gc = 0;                        // chunks this group has processed (staging double-buffer index)
+      uint32_t aux_n = 0;                     // addend tiles this group has consumed (mbarrier phase)
+      auto nch = [&](int t) { return min(CHUNKS, (p.N - decode(t).n0 + 31) / 32); };
+      // (at, ac): the next (tile, chunk) whose addend tile has not been requested yet; one load in flight per group
+      int at = blockIdx.x, ac = eg;
+      auto settle = [&]() { while (at < p.total_tiles && ac >= nch(at)) { at += gridDim.x; ac = eg; } };
+      auto issue_aux = [&]() {
+        const TileCoord c = decode(at);
         const int za = (c.z / p.aux_zd) % p.aux_nb;
-        mbar_expect_tx(aux_bar(buf), CHUNK_BYTES);
+        mbar_expect_tx(aux_bar(eg), CHUNK_BYTES);
         if (p.aux_kind == 1) {
-          tma_load_3d(dst, &maps.AUX, aux_bar(buf), c.n0 + chunk * 32, c.m0, za);
+          tma_load_3d(aux_base, &maps.AUX, aux_bar(eg), c.n0 + ac * 32, c.m0, za);
         } else {
-          tma_load_4d(dst, &maps.AUX, aux_bar(buf), c.n0 + chunk * 32, c.m0, 0, za);
-          tma_load_4d(dst + CHUNK_BYTES / 2, &maps.AUX, aux_bar(buf), c.n0 + chunk * 32, c.m0, 1, za);
+          tma_load_4d(aux_base, &maps.AUX, aux_bar(eg), c.n0 + ac * 32, c.m0, 0, za);
+          tma_load_4d(aux_base + CHUNK_BYTES / 2, &maps.AUX, aux_bar(eg), c.n0 + ac * 32, c.m0, 1, za);
         }
       };
-      if (p.aux_kind && leader && (int)blockIdx.x < p.total_tiles) issue_aux(decode(blockIdx.x), 0, 0);
+      if (p.aux_kind) {
+        settle();
+        if (leader && at < p.total_tiles) issue_aux();
+      }
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
         const TileCoord tc = decode(t);
-        const int t_next = t + gridDim.x;
-        const bool has_next = t_next < p.total_tiles;
-        const TileCoord tn = decode(has_next ? t_next : t);
         const int acc = tile_it & 1;
         const int row = tc.m0 + r;
         const bool row_ok = row < p.M;
@@ -336,13 +383,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           const float* bias = p.bias ? p.bias + (int64_t)tc.z * p.bias_sb : nullptr;
           for (int j = et; j < BN; j += 128) {
             const bool ok = tc.n0 + j < p.N;
-            bias_sm[j] = (bias && ok) ? __ldg(bias + tc.n0 + j) : 0.f;
-            colv_sm[j] = (p.colv && ok) ? __ldg(p.colv + tc.n0 + j) : 0.f;
-            colred_sm[j] = 0.f;
+            bias_s[j] = (bias && ok) ? __ldg(bias + tc.n0 + j) : 0.f;
+            colv_s[j] = (p.colv && ok) ? __ldg(p.colv + tc.n0 + j) : 0.f;
+            colred_s[j] = 0.f;
             if (p.r1col) {
               const int ng = p.r1_rpg > 0 ? min(4, (p.M + p.r1_rpg - 1) / p.r1_rpg) : 1;
               for (int g = 0; g < ng; ++g)
-                r1_sm[g][j] = ok ? __ldg(p.r1col + (int64_t)tc.z * p.r1col_sb + (int64_t)g * p.r1_gs + tc.n0 + j) : 0.f;
+                r1_sm[eg][g][j] = ok ? __ldg(p.r1col + (int64_t)tc.z * p.r1col_sb + (int64_t)g * p.r1_gs + tc.n0 + j) : 0.f;
             }
           }
           epi_barrier();
@@ -351,8 +398,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int rgroup = (p.r1col && p.r1_rpg > 0) ? min(3, row / p.r1_rpg) : 0;
         mbar_wait(tmem_full_bar(acc), (tile_it >> 1) & 1, 3);
         tc_fence_after();
-        if (tl && threadIdx.x == 64 && tile_it == 0) tl[4] = clock64();
+        if (tl && et == 0 && eg == 0 && tile_it == 0) tl[4] = clock64();
         const int nchunks = min(CHUNKS, (p.N - tc.n0 + 31) / 32);           // uniform across the CTA
+        if (eg >= nchunks) {                                                // no chunk of this tile for this group
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
         float* drow = nullptr;
         if (p.D && !p.tma_store) {
           const int g = row / p.d_rpg;
@@ -361,48 +413,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const float* xrow = p.mulx ? p.mulx + (int64_t)row * p.mulx_ld : nullptr;
         float rowdot = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < nchunks; ++c, ++gc) {
+        for (int c = eg; c < nchunks; c += neg, ++gc) {
           const int col0 = tc.n0 + c * 32;
-          const uint32_t buf = gc & 1u;
-          const uint32_t sbuf = p.store_nbuf == 2 ? buf : 0u;
-          if (stage_tma || p.aux_kind) {
-            if (stage_tma && leader) {                                // the TMA store that last used this staging buffer has read it
+          const uint32_t sbuf = p.store_nbuf == 2 ? (gc & 1u) : 0u;
+          if (stage_tma) {
+            if (leader) {                                             // the TMA store that last used this staging buffer has read it
               if (p.store_nbuf == 2) tma_store_wait_read<1>();
               else tma_store_wait_read<0>();
             }
-            epi_barrier();                                            // ... and everyone is done with the other aux buffer
+            epi_barrier();
           }
-          if (p.aux_kind) {
-            if (leader) {                                             // prefetch the next chunk's addend tile (may belong to the next tile)
-              if (c + 1 < nchunks) issue_aux(tc, c + 1, buf ^ 1u);
-              else if (has_next) issue_aux(tn, 0, buf ^ 1u);
-            }
-            mbar_wait(aux_bar(buf), (gc >> 1) & 1u, 4);
-          }
+          if (p.aux_kind) mbar_wait(aux_bar(eg), aux_n & 1u, 4);
           uint32_t v[32];
           __syncwarp();                                               // tcgen05.ld is warp-collective
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-          if (c == nchunks - 1) {                                     // accumulator fully read: hand the buffer back to the MMA warp
+          if (c + neg >= nchunks) {                                   // this group's last read of the accumulator: hand it back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
           }
-          float f[32];
-          {                                                           // bias slice of this chunk: 8 x LDS.128
-            const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = b4[j];
-              f[4 * j] = b.x; f[4 * j + 1] = b.y; f[4 * j + 2] = b.z; f[4 * j + 3] = b.w;
-            }
-          }
-          if (tc.num_kb != 0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
-          }
           float ax[32];
           if (p.aux_kind == 1) {                                      // this thread's row of the fp32 addend tile (128-byte swizzle)
-            const uint32_t src = smem_base + p.off_aux + buf * CHUNK_BYTES + (uint32_t)r * 128u;
+            const uint32_t src = aux_base + (uint32_t)r * 128u;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -410,7 +442,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                            : "r"(src + (uint32_t)((j ^ (r & 7)) * 16)));
             }
           } else if (p.aux_kind == 2) {                               // hi + lo rows of the bf16 plane tiles (64-byte swizzle)
-            const uint32_t src = smem_base + p.off_aux + buf * CHUNK_BYTES + (uint32_t)r * 64u;
+            const uint32_t src = aux_base + (uint32_t)r * 64u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint32_t h[4], l[4];
@@ -426,17 +458,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               }
             }
           }
+          if (p.aux_kind) {
+            // the addend tile is in registers: request the group's next one now, so that its latency hides behind the
+            // arithmetic and the stores of this chunk (and behind the other group's work)
+            epi_barrier();
+            ++aux_n;
+            ac += neg;
+            settle();
+            if (leader && at < p.total_tiles) issue_aux();
+          }
+          float f[32];
+          {                                                           // bias slice of this chunk: 8 x LDS.128
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = b4[j];
+              f[4 * j] = b.x; f[4 * j + 1] = b.y; f[4 * j + 2] = b.z; f[4 * j + 3] = b.w;
+            }
+          }
+          if (tc.num_kb != 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+          }
           if (p.aux_kind && p.aux_mode == TC_AUX_ADD) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += ax[j];
           }
           if (p.act_tanh) {                                           // uniform branches: no predicated-off code on the common path
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = tanh_acc(f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
           }
           if (p.r1col) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaf(rv, r1_sm[rgroup][c * 32 + j], f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = fmaf(rv, r1_sm[eg][rgroup][c * 32 + j], f[j]);
           }
           if (p.aux_kind && p.aux_mode == TC_AUX_MUL_1MX2) {
 #pragma unroll
@@ -453,29 +507,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
           if (p.mode == TC_EPI_ROWDOT) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) rowdot = fmaf(f[j], colv_sm[c * 32 + j], rowdot);   // colv_sm is 0 beyond N
+            for (int j = 0; j < 32; ++j) rowdot = fmaf(f[j], colv_s[c * 32 + j], rowdot);   // colv_s is 0 beyond N
             continue;
           }
           if (p.mode == TC_EPI_DZ) {
             // column partials of h * rowv over this warp's 32 rows, then dz = rowv * colv * (1 - h^2)
+            float part[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float part = warp_sum(f[j] * rv);
-              if (lane == j) atomicAdd(&colred_sm[c * 32 + j], part);
-              f[j] = rv * colv_sm[c * 32 + j] * (1.f - f[j] * f[j]);
+              part[j] = f[j] * rv;
+              f[j] = rv * colv_s[c * 32 + j] * (1.f - f[j] * f[j]);
             }
+            const float cs = col_reduce32(part, lane);
+            atomicAdd(&colred_s[c * 32 + lane], cs);
           } else if (want_colred) {
+            float part[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float part = warp_sum(row_ok ? f[j] : 0.f);
-              if (lane == j) atomicAdd(&colred_sm[c * 32 + j], part);
-            }
+            for (int j = 0; j < 32; ++j) part[j] = row_ok ? f[j] : 0.f;
+            const float cs = col_reduce32(part, lane);
+            atomicAdd(&colred_s[c * 32 + lane], cs);
           }
           if (stage_tma) {
             if (do_f32 && p.tma_store) {
               // Each thread owns one output row; the 32-column chunk is staged as a [128 rows][128 B] tile in the TMA 128-byte
               // swizzle (16-byte chunk j of row r at chunk j ^ (r & 7): conflict-free float4 stores) and handed to the TMA engine.
-              const uint32_t sb = smem_base + p.off_store + sbuf * CHUNK_BYTES + (uint32_t)r * 128u;
+              const uint32_t sb = store_base + sbuf * CHUNK_BYTES + (uint32_t)r * 128u;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (uint32_t)((j ^ (r & 7)) * 16)), "f"(f[4 * j]),
@@ -485,7 +541,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
             if (do_pl) {
               // hi / lo bf16 planes of the same chunk: two [128 rows][64 B] tiles in the 64-byte swizzle
-              const uint32_t sb = smem_base + p.off_pstore + sbuf * CHUNK_BYTES + (uint32_t)r * 64u;
+              const uint32_t sb = pstore_base + sbuf * CHUNK_BYTES + (uint32_t)r * 64u;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint32_t h[4], l[4];
@@ -508,12 +564,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             epi_barrier();
             if (leader) {
               if (do_f32 && p.tma_store) {
-                const uint32_t sb = smem_base + p.off_store + sbuf * CHUNK_BYTES;
+                const uint32_t sb = store_base + sbuf * CHUNK_BYTES;
                 if (p.atomic || p.accumulate) tma_reduce_add_4d(&maps.D, sb, col0, tc.m0, 0, tc.z / p.d_zd);
                 else tma_store_4d(&maps.D, sb, col0, tc.m0, 0, tc.z / p.d_zd);
               }
               if (do_pl) {
-                const uint32_t sb = smem_base + p.off_pstore + sbuf * CHUNK_BYTES;
+                const uint32_t sb = pstore_base + sbuf * CHUNK_BYTES;
                 tma_store_4d(&maps.DP, sb, col0, tc.m0, 0, tc.z);
                 tma_store_4d(&maps.DP, sb + CHUNK_BYTES / 2, col0, tc.m0, 1, tc.z);
               }
@@ -532,13 +588,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
           }
         }
-        if (p.mode == TC_EPI_ROWDOT && row_ok) atomicAdd(p.red_row + (int64_t)tc.z * p.red_row_sb + row, rowdot);
+        if (p.mode == TC_EPI_ROWDOT && row_ok && eg < nchunks) atomicAdd(p.red_row + (int64_t)tc.z * p.red_row_sb + row, rowdot);
         if (want_colred) {
           epi_barrier();
-          for (int j = et; j < BN; j += 128)
-            if (tc.n0 + j < p.N) atomicAdd(p.red_col + tc.n0 + j, colred_sm[j]);
+          for (int j = et; j < BN; j += 128)                           // only the columns of this group's chunks
+            if (((j >> 5) % neg) == eg && tc.n0 + j < p.N) atomicAdd(p.red_col + tc.n0 + j, colred_s[j]);
         }
-        if (tl && threadIdx.x == 64 && tile_it == 0) tl[5] = clock64();
+        if (tl && et == 0 && eg == 0 && tile_it == 0) tl[5] = clock64();
       }
       if (stage_tma && leader) tma_store_wait_read<0>();   // smem must stay valid until the engine has read it
     }
@@ -759,12 +815,14 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   HCA_CHECK_ARG(!(A.mn_major && !B.mn_major) || e.transposed, "gemm_tc: (MN-major A, K-major B) is only instantiated for the transposed epilogue");
   HCA_CHECK_ARG(!(e.transposed && B.mn_major), "gemm_tc: the transposed (BN = 32) kernel takes a K-major B");
   if (A2) HCA_CHECK_ARG(A2->mn_major == A.mn_major && B2->mn_major == B.mn_major && K2 > 0, "gemm_tc: chained pair must share the layouts");
+  // short contractions over MN-major pairs (K = T tokens per level) use 32-deep k-blocks: half the smem, TMA and MMA work
+  const int BK = (A.mn_major && B.mn_major && P == 2 && BN == 128 && !A2 && K <= 96) ? 32 : 64;
   TcMaps maps;
-  HCA_TRY(make_tmap(&maps.A, A, P, A.mn_major ? 64 : BM));
-  HCA_TRY(make_tmap(&maps.B, B, P, B.mn_major ? 64 : BN));
+  HCA_TRY(make_tmap(&maps.A, A, P, A.mn_major ? BK : BM));
+  HCA_TRY(make_tmap(&maps.B, B, P, B.mn_major ? BK : BN));
   if (A2) {
-    HCA_TRY(make_tmap(&maps.A2, *A2, P, A2->mn_major ? 64 : BM));
-    HCA_TRY(make_tmap(&maps.B2, *B2, P, B2->mn_major ? 64 : BN));
+    HCA_TRY(make_tmap(&maps.A2, *A2, P, A2->mn_major ? BK : BM));
+    HCA_TRY(make_tmap(&maps.B2, *B2, P, B2->mn_major ? BK : BN));
   } else {
     maps.A2 = maps.A;
     maps.B2 = maps.B;
@@ -811,27 +869,37 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   } else {
     maps.AUX = maps.A;
   }
-  // shared memory carve: pipeline stages first, then the epilogue staging areas this launch needs
-  const uint32_t stage_bytes = (uint32_t)P * (A_TILE_BYTES + BN * BK * 2);
-  // (static shared memory + the 1024-byte alignment slack take ~5 KB of the 227 KB)
-  const uint32_t avail = SMEM_LIMIT - 5120;
+  // shared memory carve: pipeline stages first, then the epilogue staging areas this launch needs (per epilogue group)
+  const uint32_t stage_bytes = (uint32_t)P * (uint32_t)(BM * BK * 2 + BN * BK * 2);
+  // (static shared memory + the 1024-byte alignment slack take ~9 KB of the 227 KB)
+  const uint32_t avail = SMEM_LIMIT - 9216;
   const int n_out = (!e.transposed && want_f32 && tma_store ? 1 : 0) + (!e.transposed && want_pl ? 1 : 0);
-  const uint32_t aux_bytes = (!e.transposed && aux_kind) ? 2 * CHUNK_BYTES : 0;
-  auto stages_for = [&](int nbuf) { return (int)((avail - aux_bytes - (uint32_t)(n_out * nbuf) * CHUNK_BYTES) / stage_bytes); };
-  int nbuf = 2;
-  if (stages_for(2) < 4 && stages_for(1) > stages_for(2)) nbuf = 1;   // a deeper operand pipeline beats double-buffered staging
-  int stages = stages_for(nbuf);
+  const bool has_aux_buf = !e.transposed && aux_kind;
+  p.kb1 = (K + BK - 1) / BK;
+  p.kb_total = p.kb1 + (A2 ? (K2 + BK - 1) / BK : 0);
+  auto stages_for = [&](int neg, int nbuf) {
+    const uint32_t epi = (uint32_t)neg * ((uint32_t)(n_out * nbuf) + (has_aux_buf ? 1u : 0u)) * CHUNK_BYTES;
+    return epi >= avail ? 0 : (int)((avail - epi) / stage_bytes);
+  };
+  // Two epilogue groups when the epilogue is the long pole (fused math / plane conversion behind a short mainloop) and the
+  // operand pipeline still gets the stages it needs; one group (deeper pipeline) for plain mainloop-bound products.
+  const bool epi_heavy = e.act_tanh || e.aux_mode != TC_AUX_NONE || e.mode != TC_EPI_STORE || want_pl || e.transposed || e.r1col;
+  int neg = 1, nbuf = 2;
+  if (epi_heavy && stages_for(2, 1) >= 2) neg = 2;
+  { const char* ev = getenv("HCA_TC_EG"); if (ev && (atoi(ev) == 1 || atoi(ev) == 2)) neg = atoi(ev); }
+  if (stages_for(neg, 2) < 4 && stages_for(neg, 1) > stages_for(neg, 2)) nbuf = 1;   // a deeper operand pipeline beats double-buffered staging
+  int stages = stages_for(neg, nbuf);
+  if (stages < 2 && neg == 2) { neg = 1; nbuf = 1; stages = stages_for(1, 1); }
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   { const char* ev = getenv("HCA_TC_STAGES"); if (ev && atoi(ev) >= 1 && atoi(ev) < stages) stages = atoi(ev); }
   HCA_CHECK_ARG(stages >= 2, "gemm_tc: tile does not fit two pipeline stages");
   p.stages = stages;
   p.store_nbuf = nbuf;
+  p.n_eg = neg;
   uint32_t off = (uint32_t)stages * stage_bytes;
-  if (!e.transposed && want_f32 && tma_store) { p.off_store = off; off += nbuf * CHUNK_BYTES; }
-  if (!e.transposed && want_pl) { p.off_pstore = off; off += nbuf * CHUNK_BYTES; }
-  if (aux_bytes) { p.off_aux = off; off += aux_bytes; }
-  p.kb1 = (K + BK - 1) / BK;
-  p.kb_total = p.kb1 + (A2 ? (K2 + BK - 1) / BK : 0);
+  if (!e.transposed && want_f32 && tma_store) { p.off_store = off; off += (uint32_t)(neg * nbuf) * CHUNK_BYTES; }
+  if (!e.transposed && want_pl) { p.off_pstore = off; off += (uint32_t)(neg * nbuf) * CHUNK_BYTES; }
+  if (has_aux_buf) { p.off_aux = off; off += (uint32_t)neg * CHUNK_BYTES; }
   if (splitk > p.kb_total) splitk = p.kb_total;
   p.kb_per_split = (p.kb_total + splitk - 1) / splitk;
   splitk = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;      // no empty split
@@ -879,23 +947,23 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   p.timeline = g_timeline;
   p.timeline_ctas = g_timeline_ctas;
   const size_t smem = (size_t)off + 1024;
-  HCA_CHECK_ARG(smem <= (size_t)SMEM_LIMIT - 4096, "gemm_tc: shared memory carve exceeds the limit");
+  HCA_CHECK_ARG(smem <= (size_t)SMEM_LIMIT - 8192, "gemm_tc: shared memory carve exceeds the limit");
   int ctas = num_sms();
   if (p.total_tiles < ctas) ctas = p.total_tiles;
   typedef void (*KernelFn)(const TcMaps, const TcParams);
   KernelFn fn = nullptr;
   const int combo = (A.mn_major ? 2 : 0) + (B.mn_major ? 1 : 0);    // 0 = NT (K,K), 1 = NN (K,MN), 2 = (MN,K), 3 = TN (MN,MN)
   int slot = -1;
-#define HCA_TC_CASE(SLOT, BNN, PP, CC, AMN, BMN) \
-  if (BN == BNN && P == PP && combo == CC) { fn = gemm_tc_kernel<BNN, PP, AMN, BMN>; slot = SLOT; }
-  HCA_TC_CASE(0, 128, 2, 0, false, false) HCA_TC_CASE(1, 128, 2, 1, false, true) HCA_TC_CASE(2, 128, 2, 3, true, true)
-  HCA_TC_CASE(3, 128, 3, 0, false, false) HCA_TC_CASE(4, 128, 3, 1, false, true) HCA_TC_CASE(5, 128, 3, 3, true, true)
-  HCA_TC_CASE(6, 32, 2, 0, false, false) HCA_TC_CASE(7, 32, 2, 2, true, false)
+#define HCA_TC_CASE(SLOT, BNN, PP, CC, AMN, BMN, BKK) \
+  if (BN == BNN && P == PP && combo == CC && BK == BKK) { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK>; slot = SLOT; }
+  HCA_TC_CASE(0, 128, 2, 0, false, false, 64) HCA_TC_CASE(1, 128, 2, 1, false, true, 64) HCA_TC_CASE(2, 128, 2, 3, true, true, 64)
+  HCA_TC_CASE(3, 128, 3, 0, false, false, 64) HCA_TC_CASE(4, 128, 3, 1, false, true, 64) HCA_TC_CASE(5, 128, 3, 3, true, true, 64)
+  HCA_TC_CASE(6, 32, 2, 0, false, false, 64) HCA_TC_CASE(7, 32, 2, 2, true, false, 64) HCA_TC_CASE(8, 128, 2, 3, true, true, 32)
 #undef HCA_TC_CASE
   HCA_CHECK_ARG(fn != nullptr, "gemm_tc: this (BN, P, layout) combination is not instantiated (BN=%d P=%d combo=%d)", BN, P, combo);
-  static bool attr_set[8] = {};
+  static bool attr_set[9] = {};
   if (!attr_set[slot]) {
-    HCA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 4096));
+    HCA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 8192));
     attr_set[slot] = true;
   }
   fn<<<ctas, NUM_THREADS, smem, s>>>(maps, p);

@@ -167,6 +167,21 @@ __device__ __forceinline__ uint64_t tile_desc(uint32_t tile_addr, int mn_major, 
 
 __device__ __forceinline__ float tanh_acc(float x) { return tanhf(x); }
 
+// Branch-free tanh for the GEMM epilogues: 1 - 2 / (1 + 2^(2 x log2 e)) through MUFU.EX2 / MUFU.RCP (absolute error ~2e-7,
+// saturates to +-1 exactly, NaN propagates), and the odd Taylor polynomial below |x| = 0.3 where the quotient form would
+// lose relative accuracy to cancellation (truncation error < 2e-8 there).  ~12 issue slots against ~40 + a divergent
+// branch for tanhf: the epilogues that recompute Hv / Hq are bound by exactly this.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  const float t = fmaf(-2.f, r, 1.f);
+  const float x2 = x * x;
+  const float pl = x * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 0.021869488536155203f, -0.053968253968253968f), 0.13333333333333333f),
+                                     -0.33333333333333333f), 1.f);
+  return fabsf(x) < 0.3f ? pl : t;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
