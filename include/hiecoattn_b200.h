@@ -131,6 +131,10 @@ HCA_API size_t hca_gemm_workspace(int M, int N, int K);
  * buf [nctas][64] int64 ([0..7]: start, setup done, first tile landed, MMAs issued, epilogue start,
  * epilogue end, CTA end, SM id; [8+i], [24+i], [40+i]: per-k-block producer / landed / issued stamps); pass NULL to switch it off. */
 HCA_API int hca_debug_gemm_timeline(void* buf, int nctas);
+/* same, but only the launch_index-th tensor-core GEMM launch after this call records ([8..63] then hold the epilogue
+ * stamps of one non-leader epilogue thread: per 32-column chunk {buffer free, addend landed, operands in registers,
+ * tile staged, group barrier passed}) */
+HCA_API int hca_debug_gemm_timeline_select(void* buf, int nctas, int launch_index);
 HCA_API int hca_gemm(const float* A, const float* B, const float* bias, float* D, int M, int N, int K,
                      int layout, int path, void* ws, size_t ws_bytes, void* stream);
 

@@ -177,3 +177,7 @@ extern "C" int hca_debug_gemm_timeline(void* buf, int nctas) {
   hca::tc_set_timeline((long long*)buf, buf ? nctas : 0);
   return 0;
 }
+extern "C" int hca_debug_gemm_timeline_select(void* buf, int nctas, int launch_index) {
+  hca::tc_set_timeline((long long*)buf, buf ? nctas : 0, launch_index);
+  return 0;
+}

@@ -54,6 +54,8 @@ struct TcParams {
 
 long long* g_timeline = nullptr;
 int g_timeline_ctas = 0;
+int g_timeline_target = -1;      // record only the launch with this index (counted from the last tc_set_timeline); -1 = every launch
+int g_timeline_seen = 0;
 
 struct TcMaps {            // all TMA descriptors of one launch
   CUtensorMap A, B, A2, B2;   // operands, 4-D bf16: (cols, rows, plane, batch), 128-byte swizzle
@@ -352,6 +354,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const uint32_t store_base = smem_base + p.off_store + (uint32_t)(eg * p.store_nbuf) * CHUNK_BYTES;
       const uint32_t pstore_base = smem_base + p.off_pstore + (uint32_t)(eg * p.store_nbuf) * CHUNK_BYTES;
       const uint32_t aux_base = smem_base + p.off_aux + (uint32_t)eg * CHUNK_BYTES;
+      int tli = 8;                            // debug timeline: stamps of this thread's first chunks (tl[8..63])
+      const bool tlt = tl && eg == 0 && et == 32;
+#define HCA_TL_STAMP() do { if (tlt && tli < 64) tl[tli++] = clock64(); } while (0)
       uint32_t gc = 0;                        // chunks this group has processed (staging double-buffer index)
       uint32_t aux_n = 0;                     // addend tiles this group has consumed (mbarrier phase)
       auto nch = [&](int t) { return min(CHUNKS, (p.N - decode(t).n0 + 31) / 32); };
@@ -423,7 +428,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
             epi_barrier();
           }
+          HCA_TL_STAMP();                                             // 0: staging buffer free
           if (p.aux_kind) mbar_wait(aux_bar(eg), aux_n & 1u, 4);
+          HCA_TL_STAMP();                                             // 1: addend tile landed
           uint32_t v[32];
           __syncwarp();                                               // tcgen05.ld is warp-collective
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
@@ -467,6 +474,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             settle();
             if (leader && at < p.total_tiles) issue_aux();
           }
+          HCA_TL_STAMP();                                             // 2: accumulator + addend in registers, next addend requested
           float f[32];
           {                                                           // bias slice of this chunk: 8 x LDS.128
             const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * 32);
@@ -560,8 +568,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                              : "memory");
               }
             }
+            HCA_TL_STAMP();                                           // 3: math done, tile staged
             fence_proxy_async_smem();                                 // generic-proxy smem writes -> visible to the TMA engine
             epi_barrier();
+            HCA_TL_STAMP();                                           // 4: group barrier passed
             if (leader) {
               if (do_f32 && p.tma_store) {
                 const uint32_t sb = store_base + sbuf * CHUNK_BYTES;
@@ -597,6 +607,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         if (tl && et == 0 && eg == 0 && tile_it == 0) tl[5] = clock64();
       }
       if (stage_tma && leader) tma_store_wait_read<0>();   // smem must stay valid until the engine has read it
+#undef HCA_TL_STAMP
     }
     tc_fence_before();
   }
@@ -769,9 +780,11 @@ bool planes_ok(const TcPlanes& t) {
 
 bool tc_available() { return get_encoder() != nullptr; }
 
-void tc_set_timeline(long long* buf, int nctas) {
+void tc_set_timeline(long long* buf, int nctas, int launch_index) {
   g_timeline = buf;
   g_timeline_ctas = nctas;
+  g_timeline_target = launch_index;
+  g_timeline_seen = 0;
 }
 
 int launch_split_planes(const float* src, int64_t ld, int64_t rows, int cols, __nv_bfloat16* planes, int64_t ldp,
@@ -944,8 +957,9 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
     HCA_CHECK_ARG(!e.bias && !e.act_tanh && !e.mulx && e.mode == TC_EPI_STORE && !e.r1col && !e.red_col && groups == 1 && !e.aux,
                   "gemm_tc: the transposed epilogue supports fp32 / planes output, auxp and red_row only");
   { static int dbg = -1; if (dbg < 0) { const char* ev = getenv("HCA_TC_DBG"); dbg = ev ? atoi(ev) : 0; } p.dbg = dbg; }
-  p.timeline = g_timeline;
+  p.timeline = (g_timeline && (g_timeline_target < 0 || g_timeline_seen == g_timeline_target)) ? g_timeline : nullptr;
   p.timeline_ctas = g_timeline_ctas;
+  if (g_timeline) ++g_timeline_seen;
   const size_t smem = (size_t)off + 1024;
   HCA_CHECK_ARG(smem <= (size_t)SMEM_LIMIT - 8192, "gemm_tc: shared memory carve exceeds the limit");
   int ctas = num_sms();

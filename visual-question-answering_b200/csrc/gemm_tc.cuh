@@ -91,6 +91,7 @@ int launch_split_planes_stack3(const float* s0, const float* s1, const float* s2
 
 bool tc_available();   // TMA descriptor encoder resolved from the driver
 // debug: record per-CTA clock64 stamps of the next gemm_tc launches into buf [nctas][64] (nullptr disables)
-void tc_set_timeline(long long* buf, int nctas);
+// launch_index >= 0: only that gemm_tc launch (counted from this call) records
+void tc_set_timeline(long long* buf, int nctas, int launch_index = -1);
 
 }  // namespace hca

@@ -53,6 +53,16 @@ class _cudnn_fp32:
         return False
 
 
+def _check_lens(lens_cpu: Tensor, max_len: int) -> None:
+    """The misuse pack_padded_sequence rejects in the reference (model.py:287): zero / negative or unsorted lengths."""
+    if lens_cpu.numel() and int(lens_cpu.min()) <= 0:
+        raise RuntimeError("Length of all samples has to be greater than 0, but found an element in 'lengths' that is <= 0")
+    if lens_cpu.numel() > 1 and bool((lens_cpu[1:] > lens_cpu[:-1]).any()):
+        raise RuntimeError("`lengths` array must be sorted in decreasing order when `enforce_sorted` is True.")
+    if lens_cpu.numel() and int(lens_cpu.max()) > max_len:
+        raise RuntimeError(f"a sequence length ({int(lens_cpu.max())}) exceeds the padded length {max_len}")
+
+
 def _f32(t: Tensor) -> Tensor:
     return t if t.dtype == torch.float32 else t.float()
 
@@ -97,10 +107,14 @@ class QuestionCoAttentionEncoder(nn.Module):
         x_word_emb = ops.embedding(x, self.word_embedding.weight)                       # model.py:282
         # phrase level with the pad rows already zeroed (what pack -> pad does at model.py:287,292)
         x_phrase_emb = self.phrase_conv_pool(x_word_emb, lens_dev)                      # model.py:284
-        packed = pack_padded_sequence(x_phrase_emb, lens_cpu, batch_first=True)         # raises on unsorted / zero lens
+        _check_lens(lens_cpu, max_seq_len)                                              # what pack_padded_sequence raises on
+        # pack -> LSTM -> pad (model.py:287-296) without the 26 + 26 per-timestep gather / scatter copies: the LSTM is
+        # causal, so running it over the zero-padded batch and zeroing rows t >= len afterwards gives the same outputs
+        # (and, through the mask, the same gradients) as the packed run
         with _cudnn_fp32():
-            x_sentence_emb, _ = self.sentence_lstm(packed)                              # model.py:289
-        x_sentence_emb = pad_packed_sequence(x_sentence_emb, batch_first=True, total_length=max_seq_len)[0]
+            x_sentence_emb, _ = self.sentence_lstm(x_phrase_emb.transpose(0, 1))         # model.py:289
+        valid = torch.arange(max_seq_len, device=x.device)[:, None] < lens_dev[None, :]
+        x_sentence_emb = (x_sentence_emb * valid[..., None]).transpose(0, 1)
         return x_word_emb, x_phrase_emb, x_sentence_emb
 
 
