@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HCA_ABI_VERSION 2
+#define HCA_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define HCA_API __attribute__((visibility("default")))
@@ -76,6 +76,23 @@ HCA_API int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const floa
                              const float* out, const uint8_t* idx, const float* dout, const int64_t* lens,
                              float* dx, float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3,
                              int B, int T, int E, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- sentence LSTM (replaces pack_padded_sequence -> nn.LSTM(E,H) -> pad_packed_sequence, model.py:269,287-296) ---- */
+/* x [B,T,E]; lens int64 [B] (device), each sequence runs for lens[b] steps from h0 = c0 = 0; w_ih [4H,E], w_hh [4H,H],
+ * b_ih, b_hh [4H] in PyTorch's layout (gates i, f, g, o stacked along rows).  out [B,T,H], rows t >= lens[b] zero.
+ * Supported: E % 8 == 0, H % 16 == 0, H <= 512 (hca_lstm_supported returns 1); `saved` = one opaque 256-byte aligned
+ * buffer of hca_lstm_saved_bytes bytes (gate activations, cell states, bf16 hi/lo planes of x and of the hidden states). */
+HCA_API int hca_lstm_supported(int B, int T, int E, int H);
+HCA_API size_t hca_lstm_saved_bytes(int B, int T, int E, int H);
+HCA_API size_t hca_lstm_workspace(int B, int T, int E, int H);
+HCA_API int hca_lstm_fwd(const float* x, const int64_t* lens, const float* w_ih, const float* w_hh,
+                 const float* b_ih, const float* b_hh, float* out, void* saved, size_t saved_bytes,
+                 int B, int T, int E, int H, void* ws, size_t ws_bytes, void* stream);
+/* dout [B,T,H] -> dx [B,T,E] (may be null), dw_ih [4H,E], dw_hh [4H,H], db_ih, db_hh [4H]; gradients of positions
+ * t >= lens[b] are ignored (their outputs are the constant zero). */
+HCA_API int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float* w_hh, const void* saved, size_t saved_bytes,
+                 const float* dout, float* dx, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
+                 int B, int T, int E, int H, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- ParallelCoAttention, all three levels (replaces model.py:356-397) -------------------------- */
 /* V [B,N,d] with ELEMENT strides (v_sb, v_sn, v_sd) -- the reference hands a permuted VGG view

@@ -1,0 +1,58 @@
+"""-m gpu: the persistent tcgen05 LSTM (csrc/lstm.cu) against the numpy oracle's lstm_fwd / lstm_bwd (reference
+model.py:269,287-296: pack -> nn.LSTM -> pad, zero-filled pads)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(B, T, E, H, seed, sort=True, min_len=1):
+    import gpu_harness as h
+    import hiecoattn_oracle as O
+    ops = h.PKG.ops
+    rng = np.random.RandomState(seed)
+    lens = rng.randint(min_len, T + 1, size=B).astype(np.int64)
+    if sort:
+        lens = np.sort(lens)[::-1].copy()
+    x = rng.standard_normal((B, T, E)).astype(np.float32)
+    for b in range(B):
+        x[b, lens[b]:] = 0
+    k = 1.0 / np.sqrt(H)
+    w_ih = rng.uniform(-k, k, (4 * H, E)).astype(np.float32)
+    w_hh = rng.uniform(-k, k, (4 * H, H)).astype(np.float32)
+    b_ih = rng.uniform(-k, k, (4 * H,)).astype(np.float32)
+    b_hh = rng.uniform(-k, k, (4 * H,)).astype(np.float32)
+    dy = rng.standard_normal((B, T, H)).astype(np.float32)
+    assert ops.lstm_supported(B, T, E, H)
+    tx = torch.from_numpy(x).cuda().requires_grad_(True)
+    tw = [torch.from_numpy(a).cuda().requires_grad_(True) for a in (w_ih, w_hh, b_ih, b_hh)]
+    out, _ = ops.lstm(tx, torch.from_numpy(lens).cuda(), *tw)
+    out.backward(torch.from_numpy(dy).cuda())
+    torch.cuda.synchronize()
+    f64 = lambda a: a.astype(np.float64)
+    y, cache = O.lstm_fwd(f64(x), lens, f64(w_ih), f64(w_hh), f64(b_ih), f64(b_hh))
+    dx, dw_ih, dw_hh, db_ih, db_hh = O.lstm_bwd(f64(x), f64(w_ih), f64(w_hh), cache, f64(dy))
+    got = dict(out=out, dx=tx.grad, dw_ih=tw[0].grad, dw_hh=tw[1].grad, db_ih=tw[2].grad, db_hh=tw[3].grad)
+    ref = dict(out=y, dx=dx, dw_ih=dw_ih, dw_hh=dw_hh, db_ih=db_ih, db_hh=db_hh)
+    errs = {k: h.rel(got[k].detach().cpu().numpy(), ref[k]) for k in ref}
+    # rows past the end are exactly zero, like pad_packed_sequence's fill
+    o = out.detach().cpu().numpy()
+    for b in range(B):
+        assert not o[b, lens[b]:].any()
+    return errs
+
+
+@pytest.mark.parametrize("B,T,E,H", [(3, 7, 32, 32), (5, 4, 64, 64), (2, 1, 32, 32), (7, 9, 48, 80), (160, 26, 512, 512), (200, 26, 512, 512),
+                                      (600, 12, 64, 512)])
+def test_lstm_matches_oracle(B, T, E, H):
+    errs = _run(B, T, E, H, seed=B * 31 + T)
+    assert max(errs.values()) < 1e-3, errs
+    assert errs["out"] < 1e-4, errs
+
+
+def test_lstm_unsorted_lengths_and_len_T():
+    errs = _run(37, 11, 64, 128, seed=5, sort=False)
+    assert max(errs.values()) < 1e-3, errs
+    errs = _run(9, 6, 32, 64, seed=6, min_len=6)          # every sequence has the full length
+    assert max(errs.values()) < 1e-3, errs

@@ -29,6 +29,11 @@ SIGNATURES = {
     "hca_phrase_conv_pool_workspace": (_sz, [_i, _i, _i]),
     "hca_phrase_conv_pool_fwd": (_i, [_p] * 10 + [_i, _i, _i, _p, _sz, _p]),
     "hca_phrase_conv_pool_bwd": (_i, [_p] * 15 + [_i, _i, _i, _p, _sz, _p]),
+    "hca_lstm_supported": (_i, [_i, _i, _i, _i]),
+    "hca_lstm_saved_bytes": (_sz, [_i, _i, _i, _i]),
+    "hca_lstm_workspace": (_sz, [_i, _i, _i, _i]),
+    "hca_lstm_fwd": (_i, [_p] * 8 + [_sz] + [_i, _i, _i, _i, _p, _sz, _p]),
+    "hca_lstm_bwd": (_i, [_p] * 4 + [_sz] + [_p] * 6 + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_coattn_workspace": (_sz, [_i, _i, _i, _i, _i]),
     "hca_coattn_saved_bytes": (_sz, [_i, _i, _i, _i]),
     "hca_coattn_fwd": (_i, [_p, _i64, _i64, _i64] + [_p] * 14 + [_sz] + [_i, _i, _i, _i, _p, _sz, _p]),
@@ -42,7 +47,7 @@ SIGNATURES = {
     "hca_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 

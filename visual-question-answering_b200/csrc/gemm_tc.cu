@@ -780,6 +780,26 @@ bool planes_ok(const TcPlanes& t) {
 
 bool tc_available() { return get_encoder() != nullptr; }
 
+int tc_make_tmap(void* tm, bool bf16, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, int swizzle) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return set_err(HCA_ERR_CUDA, "tc_make_tmap: cuTensorMapEncodeTiled is not available from the driver");
+  HCA_CHECK_ARG(rank >= 2 && rank <= 5 && swizzle >= 0 && swizzle <= 3, "tc_make_tmap: bad rank / swizzle");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  static const CUtensorMapSwizzle swz[4] = {CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_64B,
+                                            CU_TENSOR_MAP_SWIZZLE_128B};
+  CUresult r = enc((CUtensorMap*)tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                   const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz[swizzle],
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_err(HCA_ERR_CUDA, "tc_make_tmap: cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu box=%u,%u", (int)r, rank,
+                   (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+  return 0;
+}
+
 void tc_set_timeline(long long* buf, int nctas, int launch_index) {
   g_timeline = buf;
   g_timeline_ctas = nctas;

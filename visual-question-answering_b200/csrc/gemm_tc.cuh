@@ -90,6 +90,10 @@ int launch_split_planes_stack3(const float* s0, const float* s1, const float* s2
                                int64_t ldp, int64_t plane_stride, cudaStream_t s);
 
 bool tc_available();   // TMA descriptor encoder resolved from the driver
+// generic tiled TMA descriptor (rank 2..5) for the other hand-written kernels: `tm` points at a CUtensorMap; dims / box in
+// elements (dim 0 innermost and contiguous), strides in BYTES for dims 1..rank-1; swizzle 0 none, 1 = 32 B, 2 = 64 B, 3 = 128 B
+int tc_make_tmap(void* tm, bool bf16, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, int swizzle);
 // debug: record per-CTA clock64 stamps of the next gemm_tc launches into buf [nctas][64] (nullptr disables)
 // launch_index >= 0: only that gemm_tc launch (counted from this call) records
 void tc_set_timeline(long long* buf, int nctas, int launch_index = -1);

@@ -1,0 +1,672 @@
+// Sentence-level LSTM over variable-length questions (replaces pack_padded_sequence -> nn.LSTM(E, H) -> pad_packed_sequence,
+// reference model.py:269,287-296).  Gate order i, f, g, o; h0 = c0 = 0; every sequence stops at its own length; rows
+// t >= len of the output are zero.
+//
+//   z_t = x_t W_ih^T + b_ih + b_hh + h_{t-1} W_hh^T        i,f,o = sigmoid(z), g = tanh(z)
+//   c_t = f c_{t-1} + i g                                  h_t = o tanh(c_t)
+//
+// The input projection of all (b, t) is one tcgen05 GEMM (gemm_tc.cuh).  The recurrence -- T dependent steps of a
+// [B, H] x [H, 4H] product -- runs in ONE persistent kernel instead of T library GEMM + cell launches:
+//   * CTA (mi, ni) owns 128 batch rows x 16 hidden units.  Its slice of W_hh (the 64 gate rows of its units, as bf16 hi/lo
+//     planes, 128 KB at H = 512) is loaded into shared memory ONCE and stays there for all steps; the cell state c of its
+//     (row, unit) pairs lives in registers.
+//   * per step the CTAs of one row tile exchange h_{t-1} through global memory (bf16 hi/lo planes, written by the cell
+//     epilogue, streamed back in by TMA as the A operand); a release/acquire counter per (row tile, step) orders the
+//     exchange -- rows of different tiles never wait for each other.
+//   * batch on the UMMA M axis, the 4 gates of a unit on 4 adjacent accumulator columns (W rows are permuted to
+//     [unit][gate] order), so one epilogue thread holds all four gates of its (row, unit) and no cross-thread exchange
+//     is needed; tcgen05.mma kind::f16 on bf16x2 operand planes (3 MMAs per k-step), fp32 accumulation in TMEM.
+// Backward runs the same skeleton in reverse time: the streamed operand is the gate gradient of step t+1 (written as bf16
+// planes by the cell-backward epilogue -- the very array the weight-gradient GEMMs consume afterwards), the resident operand
+// the 16 columns of W_hh belonging to the CTA's units.  dW_ih, dW_hh and dx are three big tcgen05 GEMMs over all (b, t).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <algorithm>
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "tc_ptx.cuh"
+#include "util_kernels.cuh"
+
+namespace hca {
+namespace {
+using namespace ptx;
+
+constexpr int L_BM = 128;                         // batch rows per CTA (UMMA M)
+constexpr int L_BK = 64;                          // bf16 per k-block row = 128 B = one SWIZZLE_128B span
+constexpr int L_UNITS = 16;                       // hidden units per CTA
+constexpr int L_STAGES = 3;
+constexpr int L_THREADS = 64 + 256;               // warp 0 TMA, warp 1 MMA, warps 2..9 cell epilogue (2 groups x 4 TMEM quadrants)
+constexpr uint32_t L_A_PLANE = L_BM * L_BK * 2;   // one plane of one streamed k-block: 16 KB
+constexpr uint32_t L_STAGE_BYTES = 2 * L_A_PLANE; // hi + lo
+constexpr int L_MAX_SMEM = 227 * 1024 - 2048;
+
+struct LstmMaps {
+  CUtensorMap A;   // streamed operand planes, 4-D (cols, t, b, plane), box (64, 1, 128, 1)
+  CUtensorMap W;   // resident operand planes, 4-D (cols, rows, plane, 1), box (64, BN, 1, 1)
+};
+
+struct LstmParams {
+  int B, T, H;
+  int row0;               // first batch row of this launch (multiple of 128)
+  int tiles_n;            // H / 16
+  int kbn;                // k-blocks of the recurrent contraction: fwd ceil(H / 64), bwd ceil(4H / 64)
+  int K;                  // contraction length: fwd H, bwd 4H
+  const int64_t* lens;
+  int* counters;          // [row tiles][T]: CTAs of the row tile that have published step t
+  float* act;             // [B][T][4H], gate columns in [unit][gate] order.  fwd: in = x-projection + biases, out = activations
+  float* c;               // [B][T][H] cell states
+  float* out;             // [B][T][H] (fwd)
+  __nv_bfloat16* hp;      // h planes [2][B][T][H]: slot t holds h_{t-1} (slot 0 = 0)
+  int64_t hp_ps;
+  const float* dout;      // [B][T][H] (bwd)
+  __nv_bfloat16* dgp;     // gate-gradient planes [2][B][T][4H] ([unit][gate] column order) (bwd)
+  int64_t dgp_ps;
+  float* dbias;           // [4H] in [unit][gate] order, accumulated atomically (bwd)
+};
+
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return r;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void cell_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// 8 fp32 -> 8 bf16 hi + 8 bf16 lo (x = hi + lo to ~2^-17), as two 16-byte vectors
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * k] - __low2float(hh), x[2 * k + 1] - __high2float(hh));
+    h[k] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[k] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_constant__ LstmMaps maps, const LstmParams p) {
+  constexpr int BN = BWD ? L_UNITS : 4 * L_UNITS;         // accumulator columns: dh of 16 units / 4 gates of 16 units
+  constexpr uint32_t W_KB_PLANE = BN * L_BK * 2;          // one plane of one resident k-block
+  constexpr uint32_t TMEM_COLS = BWD ? 32 : 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 * L_STAGES + 2];
+  __shared__ uint32_t tmem_ptr_smem;
+  __shared__ int s_maxlen;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[L_STAGES + s]); };
+  const uint32_t w_bar = smem_u32(&bars[2 * L_STAGES]), tmem_full = smem_u32(&bars[2 * L_STAGES + 1]);
+  const int mi = blockIdx.x / p.tiles_n, ni = blockIdx.x - mi * p.tiles_n;
+  const int m0 = p.row0 + mi * L_BM;
+  int* const counters = p.counters + (int64_t)(m0 / L_BM) * p.T;
+  const uint32_t w_base = smem_base;
+  const uint32_t ring_base = smem_base + (uint32_t)p.kbn * 2u * W_KB_PLANE;
+
+  if (threadIdx.x == 0) {
+    s_maxlen = 0;
+    for (int s = 0; s < L_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(w_bar, 1);
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.A) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.W) : "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr_smem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // steps this row tile needs: the longest sequence among its rows (rows are independent, so other tiles may run longer)
+  if (threadIdx.x < L_BM) {
+    const int b = m0 + (int)threadIdx.x;
+    if (b < p.B) {
+      const int64_t l = p.lens[b];
+      atomicMax(&s_maxlen, (int)(l < 0 ? 0 : (l > p.T ? p.T : l)));
+    }
+  }
+  __syncthreads();
+  const int steps = s_maxlen;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_ptr_smem, 0);
+  const int rounds = steps > 0 ? steps - 1 : 0;             // recurrent products: every step but the first one in time order
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, (uint32_t)p.kbn * 2u * W_KB_PLANE);
+      for (int kb = 0; kb < p.kbn; ++kb)
+        for (int pl = 0; pl < 2; ++pl)
+          tma_load_4d(w_base + (uint32_t)(kb * 2 + pl) * W_KB_PLANE, &maps.W, w_bar, kb * L_BK, ni * BN, pl, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int n = 0; n < rounds; ++n) {
+        // forward round n computes step t = n + 1 from h_n (slot n + 1, published at step n);
+        // backward round n computes step t = steps - 2 - n from the gate gradients of step t + 1 (slot t + 1)
+        const int dep = BWD ? steps - 1 - n : n;
+        const int slot = BWD ? dep : n + 1;
+        const int* cnt = counters + dep;
+        if (ld_acquire(cnt) < p.tiles_n) {           // bounded spin: a protocol bug must trap, never hang the device
+          const long long t0 = clock64();
+          while (ld_acquire(cnt) < p.tiles_n) {
+            __nanosleep(20);
+            if (clock64() - t0 > 4000000000LL) {
+              printf("hiecoattn lstm: step counter wait timed out (block %d, round %d)\n", blockIdx.x, n);
+              __trap();
+            }
+          }
+        }
+        fence_proxy_async_global();                  // peers wrote through the generic proxy; TMA reads through the async proxy
+        for (int kb = 0; kb < p.kbn; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1, 11);
+          mbar_expect_tx(full_bar(s), L_STAGE_BYTES);
+          const uint32_t dst = ring_base + (uint32_t)s * L_STAGE_BYTES;
+          tma_load_4d(dst, &maps.A, full_bar(s), kb * L_BK, slot, m0, 0);
+          tma_load_4d(dst + L_A_PLANE, &maps.A, full_bar(s), kb * L_BK, slot, m0, 1);
+          if (++s == L_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(L_BM >> 4) << 24);
+    constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    mbar_wait(w_bar, 0, 12);
+    tc_fence_after();
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a_ring = __shfl_sync(0xffffffffu, ((ring_base & 0x3FFFFu) >> 4) | (1u << 16), 0);
+    const uint32_t w_res = __shfl_sync(0xffffffffu, ((w_base & 0x3FFFFu) >> 4) | (1u << 16), 0);
+    for (int n = 0; n < rounds; ++n) {
+      for (int kb = 0; kb < p.kbn; ++kb) {
+        mbar_wait(full_bar(s), ph, 13);
+        tc_fence_after();
+        const uint32_t au = __shfl_sync(0xffffffffu, a_ring + (uint32_t)s * (L_STAGE_BYTES >> 4), 0);
+        const uint32_t bu = __shfl_sync(0xffffffffu, w_res + (uint32_t)kb * (2u * W_KB_PLANE >> 4), 0);
+        const uint32_t first = __shfl_sync(0xffffffffu, kb == 0 ? 0u : 1u, 0);
+        const int nks = __shfl_sync(0xffffffffu, min(L_BK / 16, (p.K - kb * L_BK + 15) / 16), 0);
+#pragma unroll
+        for (int ks = 0; ks < L_BK / 16; ++ks) {
+          if (ks < nks) {
+            // hi.hi + hi.lo + lo.hi
+            umma_bf16_elect32(d_tmem, au + ks * 2, desc_hi, bu + ks * 2, desc_hi, idesc, ks != 0 ? 1u : first);
+            umma_bf16_elect32(d_tmem, au + ks * 2, desc_hi, bu + (W_KB_PLANE >> 4) + ks * 2, desc_hi, idesc, 1u);
+            umma_bf16_elect32(d_tmem, au + (L_A_PLANE >> 4) + ks * 2, desc_hi, bu + ks * 2, desc_hi, idesc, 1u);
+          }
+        }
+        umma_commit_elect(empty_bar(s));
+        if (++s == L_STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit_elect(tmem_full);
+    }
+  } else {
+    // ============================================================ cell epilogue: thread = (batch row, 8 hidden units)
+    const int eg = (warp - 2) >> 2;                 // which half of the CTA's 16 units
+    const int q = warp & 3;                         // TMEM lane quadrant
+    const int r = q * 32 + lane;
+    const int b = m0 + r;
+    const bool row_ok = b < p.B;
+    int len_b = 0;
+    if (row_ok) {
+      const int64_t l = p.lens[b];
+      len_b = (int)(l < 0 ? 0 : (l > p.T ? p.T : l));
+    }
+    const bool leader = (threadIdx.x == 64);
+    const int H = p.H, H4 = 4 * p.H;
+    const int u0 = ni * L_UNITS + eg * 8;           // first of this thread's 8 units
+    const int g0 = ni * 4 * L_UNITS + eg * 32;      // first of its 32 gate columns ([unit][gate] order)
+    const int64_t bt0 = (int64_t)b * p.T;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if constexpr (!BWD) {
+      float cst[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cst[u] = 0.f;
+      for (int t = 0; t < steps; ++t) {
+        float z[32];
+        if (row_ok) {                                // x-projection + biases of this step (independent of the recurrence)
+          const float4* gx = reinterpret_cast<const float4*>(p.act + (bt0 + t) * H4 + g0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = __ldg(gx + j);
+            z[4 * j] = v.x; z[4 * j + 1] = v.y; z[4 * j + 2] = v.z; z[4 * j + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[j] = 0.f;
+        }
+        if (t > 0) {
+          mbar_wait(tmem_full, (uint32_t)((t - 1) & 1), 14);
+          tc_fence_after();
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(lane_addr + (uint32_t)(eg * 32), v);
+          tc_fence_before();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[j] += __uint_as_float(v[j]);
+        }
+        float h[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float ig = sigmoid_fast(z[4 * u]), fg = sigmoid_fast(z[4 * u + 1]), gg = tanh_fast(z[4 * u + 2]),
+                      og = sigmoid_fast(z[4 * u + 3]);
+          cst[u] = fmaf(fg, cst[u], ig * gg);
+          h[u] = og * tanh_fast(cst[u]);
+          z[4 * u] = ig; z[4 * u + 1] = fg; z[4 * u + 2] = gg; z[4 * u + 3] = og;
+        }
+        // publish h_t (slot t + 1) first: it is on the critical path of every CTA of this row tile
+        if (row_ok && t + 1 < p.T) {
+          uint4 hi, lo;
+          split8(h, hi, lo);
+          __nv_bfloat16* dst = p.hp + (bt0 + t + 1) * H + u0;
+          *reinterpret_cast<uint4*>(dst) = hi;
+          *reinterpret_cast<uint4*>(dst + p.hp_ps) = lo;
+        }
+        fence_proxy_async_global();
+        cell_barrier();
+        if (leader) {
+          __threadfence();
+          red_release_add(counters + t, 1);
+        }
+        if (row_ok) {                                // saved for backward + the module output
+          float4* a4 = reinterpret_cast<float4*>(p.act + (bt0 + t) * H4 + g0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a4[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
+          float4* c4 = reinterpret_cast<float4*>(p.c + (bt0 + t) * H + u0);
+          c4[0] = make_float4(cst[0], cst[1], cst[2], cst[3]);
+          c4[1] = make_float4(cst[4], cst[5], cst[6], cst[7]);
+          float4* o4 = reinterpret_cast<float4*>(p.out + (bt0 + t) * H + u0);
+          const bool valid = t < len_b;
+          o4[0] = valid ? make_float4(h[0], h[1], h[2], h[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          o4[1] = valid ? make_float4(h[4], h[5], h[6], h[7]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (row_ok) {                                  // steps nobody in this row tile reaches: zero output rows
+        for (int t = steps; t < p.T; ++t) {
+          float4* o4 = reinterpret_cast<float4*>(p.out + (bt0 + t) * H + u0);
+          o4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+          o4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    } else {
+      float dcn[8], dbacc[32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dcn[u] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dbacc[j] = 0.f;
+      for (int t = steps - 1; t >= 0; --t) {
+        const bool valid = row_ok && t < len_b;
+        float a[32], ct[8], cp[8], dh[8];
+        if (valid) {
+          const float4* a4 = reinterpret_cast<const float4*>(p.act + (bt0 + t) * H4 + g0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = __ldg(a4 + j);
+            a[4 * j] = v.x; a[4 * j + 1] = v.y; a[4 * j + 2] = v.z; a[4 * j + 3] = v.w;
+          }
+          const float4* c4 = reinterpret_cast<const float4*>(p.c + (bt0 + t) * H + u0);
+          const float4 c0 = __ldg(c4), c1 = __ldg(c4 + 1);
+          ct[0] = c0.x; ct[1] = c0.y; ct[2] = c0.z; ct[3] = c0.w; ct[4] = c1.x; ct[5] = c1.y; ct[6] = c1.z; ct[7] = c1.w;
+          if (t > 0) {
+            const float4 p0 = __ldg(c4 - H / 4), p1 = __ldg(c4 - H / 4 + 1);
+            cp[0] = p0.x; cp[1] = p0.y; cp[2] = p0.z; cp[3] = p0.w; cp[4] = p1.x; cp[5] = p1.y; cp[6] = p1.z; cp[7] = p1.w;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cp[u] = 0.f;
+          }
+          const float4* d4 = reinterpret_cast<const float4*>(p.dout + (bt0 + t) * H + u0);
+          const float4 d0 = __ldg(d4), d1 = __ldg(d4 + 1);
+          dh[0] = d0.x; dh[1] = d0.y; dh[2] = d0.z; dh[3] = d0.w; dh[4] = d1.x; dh[5] = d1.y; dh[6] = d1.z; dh[7] = d1.w;
+        }
+        if (t < steps - 1) {                         // + W_hh^T dz_{t+1}
+          mbar_wait(tmem_full, (uint32_t)((steps - 2 - t) & 1), 15);
+          tc_fence_after();
+          uint32_t v[8];
+          __syncwarp();
+          tmem_ld8(lane_addr + (uint32_t)(eg * 8), v);
+          tc_fence_before();
+          if (valid) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dh[u] += __uint_as_float(v[u]);
+          }
+        }
+        float dz[32];
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float ig = a[4 * u], fg = a[4 * u + 1], gg = a[4 * u + 2], og = a[4 * u + 3];
+            const float tc = tanh_fast(ct[u]);
+            const float dc = fmaf(dh[u] * og, 1.f - tc * tc, dcn[u]);
+            dz[4 * u] = dc * gg * ig * (1.f - ig);
+            dz[4 * u + 1] = dc * cp[u] * fg * (1.f - fg);
+            dz[4 * u + 2] = dc * ig * (1.f - gg * gg);
+            dz[4 * u + 3] = dh[u] * tc * og * (1.f - og);
+            dcn[u] = dc * fg;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dz[j] = 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dcn[u] = 0.f;
+        }
+        if (row_ok) {                                // gate gradients of step t: operand of step t - 1 and of the weight-gradient GEMMs
+          __nv_bfloat16* dst = p.dgp + (bt0 + t) * H4 + g0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = dz[8 * j + k];
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            *reinterpret_cast<uint4*>(dst + 8 * j) = hi;
+            *reinterpret_cast<uint4*>(dst + p.dgp_ps + 8 * j) = lo;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dbacc[j] += dz[j];
+        fence_proxy_async_global();
+        cell_barrier();
+        if (leader) {
+          __threadfence();
+          red_release_add(counters + t, 1);
+        }
+      }
+      // bias gradient: column sums over this warp's 32 rows, then one atomic per column
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+          const float send = up ? dbacc[j] : dbacc[j + off];
+          const float keep = up ? dbacc[j + off] : dbacc[j];
+          dbacc[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      if (steps > 0) atomicAdd(p.dbias + g0 + lane, dbacc[0]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- weight layout helpers.  Gate row j' = 64 * ni + 4 * u + g of the permuted matrices is row g * H + 16 * ni + u of the
+// PyTorch [4H, .] layout (gates i, f, g, o stacked along rows).
+__device__ __forceinline__ int perm_row(int jp, int H) {
+  const int ni = jp >> 6, rem = jp & 63;
+  return (rem & 3) * H + ni * L_UNITS + (rem >> 2);
+}
+// planes [2][4H][cols] <- W[perm][cols]
+__global__ void __launch_bounds__(256) lstm_split_perm_kernel(const float* __restrict__ W, int H, int cols, __nv_bfloat16* __restrict__ planes,
+                                                              int64_t ps) {
+  const int64_t total = (int64_t)4 * H * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int jp = (int)(i / cols), c = (int)(i - (int64_t)jp * cols);
+    const float x = W[(int64_t)perm_row(jp, H) * cols + c];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    planes[i] = h;
+    planes[ps + i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+// planes [2][H][4H] <- W_hh[perm(j')][k] at [k][j']   (the resident operand of the backward recurrence)
+__global__ void __launch_bounds__(256) lstm_split_perm_t_kernel(const float* __restrict__ Whh, int H, __nv_bfloat16* __restrict__ planes,
+                                                                int64_t ps) {
+  const int64_t total = (int64_t)4 * H * H;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / (4 * H)), jp = (int)(i - (int64_t)k * 4 * H);
+    const float x = Whh[(int64_t)perm_row(jp, H) * H + k];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    planes[i] = h;
+    planes[ps + i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+__global__ void __launch_bounds__(256) lstm_bias_perm_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, int H,
+                                                             float* __restrict__ out) {
+  const int jp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (jp < 4 * H) {
+    const int j = perm_row(jp, H);
+    out[jp] = b_ih[j] + b_hh[j];
+  }
+}
+// dst[perm(j')][c] = src[j'][c]   (dst2 optional second destination: b_ih and b_hh receive the same gradient)
+__global__ void __launch_bounds__(256) lstm_unperm_kernel(const float* __restrict__ src, int H, int cols, float* __restrict__ dst,
+                                                          float* __restrict__ dst2) {
+  const int64_t total = (int64_t)4 * H * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int jp = (int)(i / cols), c = (int)(i - (int64_t)jp * cols);
+    const float v = src[i];
+    const int64_t o = (int64_t)perm_row(jp, H) * cols + c;
+    dst[o] = v;
+    if (dst2) dst2[o] = v;
+  }
+}
+
+inline int64_t r8(int64_t x) { return (x + 7) / 8 * 8; }
+
+struct Saved {
+  float* act;              // [B][T][4H]
+  float* c;                // [B][T][H]
+  __nv_bfloat16* hp;       // [2][B][T][H]
+  __nv_bfloat16* xp;       // [2][B][T][E]
+};
+size_t saved_bytes(int B, int T, int E, int H) {
+  const size_t BT = (size_t)B * T;
+  return align_up(BT * 4 * H * 4) + align_up(BT * H * 4) + align_up(2 * BT * H * 2) + align_up(2 * BT * E * 2) + 256;
+}
+bool carve_saved(Saved& s, void* buf, size_t bytes, int B, int T, int E, int H) {
+  if (bytes < saved_bytes(B, T, E, H) || (reinterpret_cast<uintptr_t>(buf) & 255) != 0) return false;
+  const size_t BT = (size_t)B * T;
+  char* p = (char*)buf;
+  s.act = (float*)p; p += align_up(BT * 4 * H * 4);
+  s.c = (float*)p; p += align_up(BT * H * 4);
+  s.hp = (__nv_bfloat16*)p; p += align_up(2 * BT * H * 2);
+  s.xp = (__nv_bfloat16*)p;
+  return true;
+}
+
+bool shape_ok(int B, int T, int E, int H) { return B > 0 && T > 0 && E > 0 && E % 8 == 0 && H >= 16 && H % 16 == 0 && H <= 512; }
+
+TcOperand operand(const __nv_bfloat16* planes, int64_t ld, int64_t ps, int rows, int cols, bool mn_major) {
+  TcOperand o;
+  o.planes = planes; o.ld = ld; o.plane_stride = ps; o.rows = rows; o.cols = cols; o.mn_major = mn_major;
+  return o;
+}
+int tc_splitk(int M, int N, int K) {
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  if (tiles >= 96) return 1;
+  int sk = (148 + tiles - 1) / tiles;
+  const int maxk = (K + 255) / 256;
+  if (sk > maxk) sk = maxk;
+  return sk < 1 ? 1 : sk;
+}
+
+template <bool BWD>
+int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64_t stream_ps, int stream_cols,
+               const __nv_bfloat16* w_planes, int64_t w_ps, int w_rows, int w_cols, cudaStream_t s) {
+  constexpr int BN = BWD ? L_UNITS : 4 * L_UNITS;
+  LstmMaps maps;
+  {  // streamed operand [2][B][T][cols]: dims (cols, T, B, 2)
+    const uint64_t dims[4] = {(uint64_t)stream_cols, (uint64_t)base.T, (uint64_t)base.B, 2};
+    const uint64_t str[3] = {(uint64_t)stream_cols * 2, (uint64_t)base.T * stream_cols * 2, (uint64_t)stream_ps * 2};
+    const uint32_t box[4] = {L_BK, 1, L_BM, 1};
+    HCA_TRY(tc_make_tmap(&maps.A, true, 4, stream_planes, dims, str, box, 3));
+  }
+  {  // resident operand [2][rows][cols]: dims (cols, rows, 2, 1)
+    const uint64_t dims[4] = {(uint64_t)w_cols, (uint64_t)w_rows, 2, 1};
+    const uint64_t str[3] = {(uint64_t)w_cols * 2, (uint64_t)w_ps * 2, (uint64_t)w_ps * 4};
+    const uint32_t box[4] = {L_BK, BN, 1, 1};
+    HCA_TRY(tc_make_tmap(&maps.W, true, 4, w_planes, dims, str, box, 3));
+  }
+  LstmParams p = base;
+  p.tiles_n = base.H / L_UNITS;
+  p.K = BWD ? 4 * base.H : base.H;
+  p.kbn = (p.K + L_BK - 1) / L_BK;
+  const size_t smem = (size_t)p.kbn * 2 * BN * L_BK * 2 + (size_t)L_STAGES * L_STAGE_BYTES + 1024;
+  HCA_CHECK_ARG(smem <= (size_t)L_MAX_SMEM, "lstm: hidden size %d needs %zu bytes of shared memory", base.H, smem);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[BWD ? 1 : 0]) {
+    HCA_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_MAX_SMEM));
+    attr_set[BWD ? 1 : 0] = true;
+  }
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+      cudaGetLastError();
+      sms = 148;
+    }
+  }
+  // every CTA of a launch must be resident at once (the row tiles synchronise through global counters): at most
+  // floor(SMs / tiles_n) row tiles per launch; row tiles are independent, so the launches simply follow each other
+  const int tiles_m = (base.B + L_BM - 1) / L_BM;
+  const int per_launch = std::max(1, sms / p.tiles_n);
+  HCA_CHECK_ARG(p.tiles_n <= sms, "lstm: hidden size %d needs more CTAs per row tile than the device has SMs", base.H);
+  for (int t0 = 0; t0 < tiles_m; t0 += per_launch) {
+    const int nm = std::min(per_launch, tiles_m - t0);
+    p.row0 = t0 * L_BM;
+    lstm_rec_kernel<BWD><<<nm * p.tiles_n, L_THREADS, smem, s>>>(maps, p);
+    HCA_LAUNCHED();
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace hca
+
+extern "C" int hca_lstm_supported(int B, int T, int E, int H) { return hca::shape_ok(B, T, E, H) && hca::tc_available() ? 1 : 0; }
+
+extern "C" size_t hca_lstm_saved_bytes(int B, int T, int E, int H) { return hca::saved_bytes(B, T, E, H); }
+
+extern "C" size_t hca_lstm_workspace(int B, int T, int E, int H) {
+  using hca::align_up;
+  const size_t BT = (size_t)B * T, H4 = (size_t)4 * H;
+  const size_t fwd = align_up(2 * H4 * E * 2) + align_up(2 * H4 * H * 2) + align_up(H4 * 4) + align_up(((size_t)(B + 127) / 128) * T * 4);
+  const size_t bwd = align_up(2 * BT * H4 * 2) + align_up(2 * H4 * E * 2) + align_up(2 * H4 * H * 2) + align_up(H4 * E * 4) + align_up(H4 * H * 4) +
+                     align_up(H4 * 4) + align_up(((size_t)(B + 127) / 128) * T * 4);
+  return std::max(fwd, bwd) + 4096;
+}
+
+extern "C" int hca_lstm_fwd(const float* x, const int64_t* lens, const float* w_ih, const float* w_hh, const float* b_ih,
+                            const float* b_hh, float* out, void* saved, size_t saved_sz, int B, int T, int E, int H, void* ws,
+                            size_t ws_bytes, void* stream) {
+  using namespace hca;
+  cudaStream_t s = (cudaStream_t)stream;
+  HCA_CHECK_ARG(x && lens && w_ih && w_hh && b_ih && b_hh && out && saved, "lstm_fwd: null pointer");
+  HCA_CHECK_ARG(shape_ok(B, T, E, H), "lstm_fwd: unsupported sizes B=%d T=%d E=%d H=%d (E %% 8 == 0, H %% 16 == 0, H <= 512)", B, T, E, H);
+  HCA_CHECK_ARG(tc_available(), "lstm_fwd: cuTensorMapEncodeTiled is not available from the driver");
+  Saved sv;
+  HCA_CHECK_ARG(carve_saved(sv, saved, saved_sz, B, T, E, H), "lstm_fwd: `saved` must be 256-byte aligned and hca_lstm_saved_bytes large");
+  Workspace w(ws, ws_bytes);
+  const int64_t BT = (int64_t)B * T;
+  const int H4 = 4 * H;
+  __nv_bfloat16* wip = w.take<__nv_bfloat16>((size_t)2 * H4 * E);
+  __nv_bfloat16* whp = w.take<__nv_bfloat16>((size_t)2 * H4 * H);
+  float* biasp = w.take<float>((size_t)H4);
+  const int tiles_m = (B + L_BM - 1) / L_BM;
+  int* counters = w.take<int>((size_t)tiles_m * T);
+  if (!counters) return set_err(HCA_ERR_WORKSPACE, "lstm_fwd: workspace too small (%zu bytes)", ws_bytes);
+  HCA_TRY(launch_split_planes(x, E, BT, E, sv.xp, E, BT * E, 2, s));
+  lstm_split_perm_kernel<<<ew_grid((int64_t)H4 * E), 256, 0, s>>>(w_ih, H, E, wip, (int64_t)H4 * E);
+  HCA_LAUNCHED();
+  lstm_split_perm_kernel<<<ew_grid((int64_t)H4 * H), 256, 0, s>>>(w_hh, H, H, whp, (int64_t)H4 * H);
+  HCA_LAUNCHED();
+  lstm_bias_perm_kernel<<<(H4 + 255) / 256, 256, 0, s>>>(b_ih, b_hh, H, biasp);
+  HCA_LAUNCHED();
+  HCA_TRY(zero_async(sv.hp, (size_t)2 * BT * H * 2, s));      // slot 0 (h_{-1} = 0) and the slots no step reaches
+  HCA_TRY(zero_async(counters, (size_t)tiles_m * T * 4, s));
+  {  // x-projection of every (b, t), gate columns in [unit][gate] order, biases folded in
+    TcEpilogue e;
+    e.D = sv.act; e.ldd = H4; e.bias = biasp;
+    HCA_TRY(launch_gemm_tc(operand(sv.xp, E, BT * E, (int)BT, E, false), operand(wip, E, (int64_t)H4 * E, H4, E, false), 2, (int)BT, H4, E,
+                           e, 1, s));
+  }
+  LstmParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.T = T; p.H = H; p.lens = lens; p.counters = counters;
+  p.act = sv.act; p.c = sv.c; p.out = out; p.hp = sv.hp; p.hp_ps = BT * H;
+  return launch_rec<false>(p, sv.hp, BT * H, H, whp, (int64_t)H4 * H, H4, H, s);
+}
+
+extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float* w_hh, const void* saved, size_t saved_sz,
+                            const float* dout, float* dx, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, int B, int T, int E,
+                            int H, void* ws, size_t ws_bytes, void* stream) {
+  using namespace hca;
+  cudaStream_t s = (cudaStream_t)stream;
+  HCA_CHECK_ARG(lens && w_ih && w_hh && saved && dout && dw_ih && dw_hh && db_ih && db_hh, "lstm_bwd: null pointer");
+  HCA_CHECK_ARG(shape_ok(B, T, E, H), "lstm_bwd: unsupported sizes B=%d T=%d E=%d H=%d", B, T, E, H);
+  HCA_CHECK_ARG(tc_available(), "lstm_bwd: cuTensorMapEncodeTiled is not available from the driver");
+  Saved sv;
+  HCA_CHECK_ARG(carve_saved(sv, const_cast<void*>(saved), saved_sz, B, T, E, H), "lstm_bwd: bad `saved` buffer");
+  Workspace w(ws, ws_bytes);
+  const int64_t BT = (int64_t)B * T;
+  const int H4 = 4 * H;
+  __nv_bfloat16* dgp = w.take<__nv_bfloat16>((size_t)2 * BT * H4);
+  __nv_bfloat16* wip = w.take<__nv_bfloat16>((size_t)2 * H4 * E);
+  __nv_bfloat16* wtp = w.take<__nv_bfloat16>((size_t)2 * H4 * H);
+  float* dwi = w.take<float>((size_t)H4 * E);
+  float* dwh = w.take<float>((size_t)H4 * H);
+  float* dbp = w.take<float>((size_t)H4);
+  const int tiles_m = (B + L_BM - 1) / L_BM;
+  int* counters = w.take<int>((size_t)tiles_m * T);
+  if (!counters) return set_err(HCA_ERR_WORKSPACE, "lstm_bwd: workspace too small (%zu bytes)", ws_bytes);
+  HCA_TRY(zero_async(dgp, (size_t)2 * BT * H4 * 2, s));       // rows no step writes must read as zero in the GEMMs below
+  HCA_TRY(zero_async(dbp, (size_t)H4 * 4, s));
+  HCA_TRY(zero_async(counters, (size_t)tiles_m * T * 4, s));
+  lstm_split_perm_t_kernel<<<ew_grid((int64_t)H4 * H), 256, 0, s>>>(w_hh, H, wtp, (int64_t)H4 * H);
+  HCA_LAUNCHED();
+  LstmParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.T = T; p.H = H; p.lens = lens; p.counters = counters;
+  p.act = sv.act; p.c = sv.c; p.dout = dout; p.dgp = dgp; p.dgp_ps = BT * H4; p.dbias = dbp;
+  HCA_TRY(launch_rec<true>(p, dgp, BT * H4, H4, wtp, (int64_t)H4 * H, H, H4, s));
+  const TcOperand dg_mn = operand(dgp, H4, BT * H4, (int)BT, H4, true);
+  {  // dW_ih' = dz^T x   (K = B*T, split-K)
+    const int sk = tc_splitk(H4, E, (int)BT);
+    if (sk > 1) HCA_TRY(zero_async(dwi, (size_t)H4 * E * 4, s));
+    TcEpilogue e; e.D = dwi; e.ldd = E;
+    HCA_TRY(launch_gemm_tc(dg_mn, operand(sv.xp, E, BT * E, (int)BT, E, true), 2, H4, E, (int)BT, e, sk, s));
+    lstm_unperm_kernel<<<ew_grid((int64_t)H4 * E), 256, 0, s>>>(dwi, H, E, dw_ih, nullptr);
+    HCA_LAUNCHED();
+  }
+  {  // dW_hh' = dz^T h_prev
+    const int sk = tc_splitk(H4, H, (int)BT);
+    if (sk > 1) HCA_TRY(zero_async(dwh, (size_t)H4 * H * 4, s));
+    TcEpilogue e; e.D = dwh; e.ldd = H;
+    HCA_TRY(launch_gemm_tc(dg_mn, operand(sv.hp, H, BT * H, (int)BT, H, true), 2, H4, H, (int)BT, e, sk, s));
+    lstm_unperm_kernel<<<ew_grid((int64_t)H4 * H), 256, 0, s>>>(dwh, H, H, dw_hh, nullptr);
+    HCA_LAUNCHED();
+  }
+  lstm_unperm_kernel<<<ew_grid((int64_t)H4), 256, 0, s>>>(dbp, H, 1, db_ih, db_hh);
+  HCA_LAUNCHED();
+  if (dx) {  // dx = dz W_ih
+    lstm_split_perm_kernel<<<ew_grid((int64_t)H4 * E), 256, 0, s>>>(w_ih, H, E, wip, (int64_t)H4 * E);
+    HCA_LAUNCHED();
+    TcEpilogue e; e.D = dx; e.ldd = E;
+    HCA_TRY(launch_gemm_tc(operand(dgp, H4, BT * H4, (int)BT, H4, false), operand(wip, E, (int64_t)H4 * E, H4, E, true), 2, (int)BT, E, H4,
+                           e, 1, s));
+  }
+  return 0;
+}

@@ -108,13 +108,19 @@ class QuestionCoAttentionEncoder(nn.Module):
         # phrase level with the pad rows already zeroed (what pack -> pad does at model.py:287,292)
         x_phrase_emb = self.phrase_conv_pool(x_word_emb, lens_dev)                      # model.py:284
         _check_lens(lens_cpu, max_seq_len)                                              # what pack_padded_sequence raises on
-        # pack -> LSTM -> pad (model.py:287-296) without the 26 + 26 per-timestep gather / scatter copies: the LSTM is
-        # causal, so running it over the zero-padded batch and zeroing rows t >= len afterwards gives the same outputs
-        # (and, through the mask, the same gradients) as the packed run
-        with _cudnn_fp32():
-            x_sentence_emb, _ = self.sentence_lstm(x_phrase_emb.transpose(0, 1))         # model.py:289
-        valid = torch.arange(max_seq_len, device=x.device)[:, None] < lens_dev[None, :]
-        x_sentence_emb = (x_sentence_emb * valid[..., None]).transpose(0, 1)
+        lstm = self.sentence_lstm
+        B, T, E = x_phrase_emb.shape
+        if ops.lstm_supported(B, T, E, lstm.hidden_size) and lstm.num_layers == 1 and not lstm.bidirectional:
+            # pack -> LSTM -> pad (model.py:287-296) as one persistent tcgen05 recurrence over the padded batch (csrc/lstm.cu)
+            x_sentence_emb = ops.lstm(x_phrase_emb, lens_dev, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)[0]
+        else:
+            # widths the kernel does not cover: stock cuDNN over the padded batch.  The LSTM is causal, so running it over the
+            # zero-padded batch and zeroing rows t >= len afterwards gives the packed run's outputs (and, through the mask, its
+            # gradients) without the per-timestep gather / scatter copies of pack / pad
+            with _cudnn_fp32():
+                x_sentence_emb, _ = lstm(x_phrase_emb.transpose(0, 1))                    # model.py:289
+            valid = torch.arange(max_seq_len, device=x.device)[:, None] < lens_dev[None, :]
+            x_sentence_emb = (x_sentence_emb * valid[..., None]).transpose(0, 1)
         return x_word_emb, x_phrase_emb, x_sentence_emb
 
 

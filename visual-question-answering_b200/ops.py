@@ -165,6 +165,88 @@ def _pcp_backward(ctx, dout, _didx):
 phrase_conv_pool.register_autograd(_pcp_backward, setup_context=_pcp_setup)
 
 
+# ------------------------------------------------------------------------------------------------ sentence LSTM
+def lstm_supported(B: int, T: int, E: int, H: int) -> bool:
+    return bool(_lib.lib().hca_lstm_supported(B, T, E, H))
+
+
+@torch.library.custom_op(f"{NS}::lstm", mutates_args=(), device_types="cuda")
+def lstm(x: Tensor, lens: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor) -> Tuple[Tensor, Tensor]:
+    """pack_padded_sequence -> nn.LSTM -> pad_packed_sequence (reference model.py:287-296) on the padded batch.
+
+    x [B,T,E], lens int64 [B] on the GPU.  Returns (out [B,T,H] with rows t >= len zeroed, saved) where ``saved`` is
+    the opaque buffer the backward kernels read (layout private to the library)."""
+    _cuda_f32(x, w_ih, w_hh, b_ih, b_hh)
+    x, lens, w_ih, w_hh, b_ih, b_hh = map(_c, (x, lens, w_ih, w_hh, b_ih, b_hh))
+    assert lens.dtype == torch.int64 and lens.is_cuda
+    B, T, E = x.shape
+    H = w_hh.shape[1]
+    out = torch.empty(B, T, H, dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        saved = _ws(L.hca_lstm_saved_bytes(B, T, E, H), x.device)
+        ws = _ws(L.hca_lstm_workspace(B, T, E, H), x.device)
+        _lib.check(L.hca_lstm_fwd(_ptr(x), _ptr(lens), _ptr(w_ih), _ptr(w_hh), _ptr(b_ih), _ptr(b_hh), _ptr(out), _ptr(saved),
+                                  saved.numel(), B, T, E, H, _ptr(ws), ws.numel(), _stream()), "lstm_fwd")
+    return out, saved
+
+
+@lstm.register_fake
+def _(x, lens, w_ih, w_hh, b_ih, b_hh):
+    B, T, E = x.shape
+    H = w_hh.shape[1]
+    al = lambda n: (n + 255) // 256 * 256
+    BT = B * T
+    nbytes = al(BT * 4 * H * 4) + al(BT * H * 4) + al(2 * BT * H * 2) + al(2 * BT * E * 2) + 256
+    return x.new_empty(B, T, H), x.new_empty(nbytes, dtype=torch.uint8)
+
+
+@torch.library.custom_op(f"{NS}::lstm_bwd", mutates_args=(), device_types="cuda")
+def lstm_bwd(lens: Tensor, w_ih: Tensor, w_hh: Tensor, saved: Tensor, dout: Tensor, E: int, need_dx: bool
+             ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    _cuda_f32(w_ih, w_hh, dout)
+    lens, w_ih, w_hh, dout = map(_c, (lens, w_ih, w_hh, dout))
+    B, T, H = dout.shape
+    dev = dout.device
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    dx = f(B, T, E) if need_dx else f(0)
+    dw_ih, dw_hh, db_ih, db_hh = f(4 * H, E), f(4 * H, H), f(4 * H), f(4 * H)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = _ws(L.hca_lstm_workspace(B, T, E, H), dev)
+        _lib.check(L.hca_lstm_bwd(_ptr(lens), _ptr(w_ih), _ptr(w_hh), _ptr(saved), saved.numel(), _ptr(dout),
+                                  _ptr(dx) if need_dx else None, _ptr(dw_ih), _ptr(dw_hh), _ptr(db_ih), _ptr(db_hh), B, T, E, H,
+                                  _ptr(ws), ws.numel(), _stream()), "lstm_bwd")
+    return dx, dw_ih, dw_hh, db_ih, db_hh
+
+
+@lstm_bwd.register_fake
+def _(lens, w_ih, w_hh, saved, dout, E, need_dx):
+    B, T, H = dout.shape
+    f = lambda *s: dout.new_empty(*s)
+    return (f(B, T, E) if need_dx else f(0)), f(4 * H, E), f(4 * H, H), f(4 * H), f(4 * H)
+
+
+def _lstm_setup(ctx, inputs, output):
+    x, lens, w_ih, w_hh, b_ih, b_hh = inputs
+    out, saved = output
+    ctx.save_for_backward(lens, w_ih, w_hh, saved)
+    ctx.E = x.shape[2]
+    ctx.set_materialize_grads(False)
+
+
+def _lstm_backward(ctx, dout, _dsaved):
+    lens, w_ih, w_hh, saved = ctx.saved_tensors
+    if dout is None:
+        return (None,) * 6
+    need_dx = ctx.needs_input_grad[0]
+    dx, dw_ih, dw_hh, db_ih, db_hh = lstm_bwd(lens, w_ih, w_hh, saved, dout, ctx.E, need_dx)
+    return (dx if need_dx else None), None, dw_ih, dw_hh, db_ih, db_hh
+
+
+lstm.register_autograd(_lstm_backward, setup_context=_lstm_setup)
+
+
 # ------------------------------------------------------------------------------------------------ co-attention
 @torch.library.custom_op(f"{NS}::coattn", mutates_args=(), device_types="cuda")
 def coattn(V: Tensor, q0: Tensor, q1: Tensor, q2: Tensor, Wv: Tensor, bv: Tensor, Wq: Tensor, bq: Tensor, wv: Tensor,
