@@ -158,8 +158,8 @@ class Stepper:
         p = syn.make_params(CFG["d"], CFG["vocab"], CFG["K"], CFG["mlp"], seed=0)
         self.net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()}, strict=False)
         self.net.to(device)
-        self.dp = pkg.dp.FlatGradAllReduce(self.net.named_parameters(), group, overlap=not use_graph)
-        self.opt = torch.optim.Adam(self.dp.params, lr=1e-4, capturable=use_graph, foreach=True)
+        self.dp = pkg.dp.FlatGradAllReduce(self.net.named_parameters(), group, overlap=not use_graph, flat_params=True)
+        self.opt = pkg.optim.FlatAdam(self.dp, lr=1e-4)          # Adam(lr=1e-4), README.md:95-100 / main.py:180
         self.slots = []
         rank = torch.distributed.get_rank() if world > 1 else 0
         for s in range(slots):

@@ -137,6 +137,13 @@ HCA_API int hca_mlp_bwd(const float* dlogits, const float* Ww, const float* Wp, 
                 float* dWh, float* dbh, int B, int d, int mlp, int K,
                 void* ws, size_t ws_bytes, void* stream);
 
+/* ---- optimizer step (replaces torch.optim.Adam(model.parameters(), lr), main.py:180,222) ------------------------ */
+/* One fused pass over flat fp32 buffers p, g, m, v of n elements (n % 4 == 0, 16-byte aligned): Adam with bias correction,
+ * no weight decay, no amsgrad.  `step` (device int64[1]) is advanced by one and `coef` (device float[2], scratch) receives
+ * the bias-correction factors, so the call can be captured in a CUDA graph. */
+HCA_API int hca_adam_step(float* p, const float* g, float* m, float* v, int64_t n, long long* step, float* coef,
+                  float lr, float beta1, float beta2, float eps, void* stream);
+
 /* ---- building block exposed for tests and profiling: one dense contraction ------------------------- */
 /* fp32 row-major in and out.  layout 0 "nt": D[M,N] = A[M,K] . B[N,K]^T (+bias[N])   (nn.Linear forward)
  *                            layout 1 "nn": D[M,N] = A[M,K] . B[K,N]     (+bias[N])   (data gradient)

@@ -56,3 +56,25 @@ def test_lstm_unsorted_lengths_and_len_T():
     assert max(errs.values()) < 1e-3, errs
     errs = _run(9, 6, 32, 64, seed=6, min_len=6)          # every sequence has the full length
     assert max(errs.values()) < 1e-3, errs
+
+
+def test_flat_adam_matches_torch_adam():
+    """optim.FlatAdam (one fused kernel over flat buffers) against torch.optim.Adam, 4 steps (reference main.py:180,222)."""
+    import gpu_harness as h
+    pkg = h.PKG
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.Tanh(), torch.nn.Linear(53, 11)).cuda()
+    ref = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.Tanh(), torch.nn.Linear(53, 11)).cuda()
+    ref.load_state_dict(net.state_dict())
+    red = pkg.dp.FlatGradAllReduce(net.named_parameters(), skip=(), flat_params=True)
+    opt = pkg.optim.FlatAdam(red, lr=1e-3)
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    x = torch.randn(16, 37, device="cuda")
+    for _ in range(4):
+        red.zero_grad(); ropt.zero_grad()
+        net(x).square().mean().backward()
+        ref(x).square().mean().backward()
+        opt.step(); ropt.step()
+    for (n, a), (_, b) in zip(net.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(a, b, rtol=2e-5, atol=1e-7), (n, float((a - b).abs().max()))
+    assert int(opt.step_count) == 4

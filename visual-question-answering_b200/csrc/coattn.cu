@@ -63,9 +63,12 @@ __device__ __forceinline__ void softmax_warp(const float* __restrict__ s, float 
   }
 }
 
-// One block per sample: the six softmaxes (3 levels x {regions, tokens}) and the attention-weighted sums.  V[b] is read
-// once for all three levels; thread c owns a float2 column pair so no cross-thread reduction is needed.
+// ATTN_SPLIT blocks per sample: the six softmaxes (3 levels x {regions, tokens}; recomputed by every block of the sample,
+// they are tiny) and the attention-weighted sums.  Block (b, s) sums the regions n = s (mod ATTN_SPLIT) of V[b] for all three
+// levels and, for s < 3, the tokens of question level s; partial sums are added atomically into the zeroed outputs.  Thread
+// c owns a float2 column pair so no cross-thread reduction is needed.
 //   sv [B][3][N], sq [B][3][T] scores ; av, aq same layout ; vhat, qhat [3][B][d]
+constexpr int ATTN_SPLIT = 4;
 __global__ void __launch_bounds__(256) attn_finish_kernel(const float* __restrict__ sv, const float* __restrict__ sq,
                                                           const float* __restrict__ cv, const float* __restrict__ cq,
                                                           const float* __restrict__ V, const float* __restrict__ q0,
@@ -76,40 +79,44 @@ __global__ void __launch_bounds__(256) attn_finish_kernel(const float* __restric
   extern __shared__ float sm[];
   float* a_sm = sm;              // [3][N]
   float* q_sm = sm + 3 * N;      // [3][T]
-  const int b = blockIdx.x, w = threadIdx.x >> 5;
-  if (w < 3) softmax_warp(sv + ((int64_t)b * 3 + w) * N, cv[0], N, a_sm + w * N, av + ((int64_t)b * 3 + w) * N);
-  else if (w < 6) softmax_warp(sq + ((int64_t)b * 3 + (w - 3)) * T, cq[0], T, q_sm + (w - 3) * T, aq + ((int64_t)b * 3 + (w - 3)) * T);
+  const int b = blockIdx.x, sp = blockIdx.y, w = threadIdx.x >> 5;
+  // every block needs the weights; only split 0 publishes them (the other blocks write to a scratch row of shared memory)
+  float* dump = sm + 3 * (N + T);
+  if (w < 3) softmax_warp(sv + ((int64_t)b * 3 + w) * N, cv[0], N, a_sm + w * N, sp == 0 ? av + ((int64_t)b * 3 + w) * N : dump + w * N);
+  else if (w < 6) softmax_warp(sq + ((int64_t)b * 3 + (w - 3)) * T, cq[0], T, q_sm + (w - 3) * T,
+                               sp == 0 ? aq + ((int64_t)b * 3 + (w - 3)) * T : dump + 3 * N + (w - 3) * T);
   __syncthreads();
   const int d2 = d >> 1;
   const float2* V2 = reinterpret_cast<const float2*>(V + (int64_t)b * N * d);
   for (int c = threadIdx.x; c < d2; c += blockDim.x) {
     float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
-    int n = 0;
-    for (; n + 4 <= N; n += 4) {
+    int n = sp;
+    for (; n + 3 * ATTN_SPLIT < N; n += 4 * ATTN_SPLIT) {
       float2 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(V2 + (int64_t)(n + u) * d2 + c);
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(V2 + (int64_t)(n + u * ATTN_SPLIT) * d2 + c);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float w0 = a_sm[n + u], w1 = a_sm[N + n + u], w2 = a_sm[2 * N + n + u];
+        const int nn = n + u * ATTN_SPLIT;
+        const float w0 = a_sm[nn], w1 = a_sm[N + nn], w2 = a_sm[2 * N + nn];
         a0.x = fmaf(w0, v[u].x, a0.x); a0.y = fmaf(w0, v[u].y, a0.y);
         a1.x = fmaf(w1, v[u].x, a1.x); a1.y = fmaf(w1, v[u].y, a1.y);
         a2.x = fmaf(w2, v[u].x, a2.x); a2.y = fmaf(w2, v[u].y, a2.y);
       }
     }
-    for (; n < N; ++n) {
+    for (; n < N; n += ATTN_SPLIT) {
       const float2 v = __ldg(V2 + (int64_t)n * d2 + c);
       const float w0 = a_sm[n], w1 = a_sm[N + n], w2 = a_sm[2 * N + n];
       a0.x = fmaf(w0, v.x, a0.x); a0.y = fmaf(w0, v.y, a0.y);
       a1.x = fmaf(w1, v.x, a1.x); a1.y = fmaf(w1, v.y, a1.y);
       a2.x = fmaf(w2, v.x, a2.x); a2.y = fmaf(w2, v.y, a2.y);
     }
-    float2* o = reinterpret_cast<float2*>(vhat + (int64_t)b * d) + c;
-    o[0] = a0;
-    o[(int64_t)B * d2] = a1;
-    o[(int64_t)2 * B * d2] = a2;
-#pragma unroll
-    for (int l = 0; l < 3; ++l) {
+    float* o = vhat + (int64_t)b * d + 2 * c;
+    atomicAdd(o, a0.x); atomicAdd(o + 1, a0.y);
+    atomicAdd(o + (int64_t)B * d, a1.x); atomicAdd(o + (int64_t)B * d + 1, a1.y);
+    atomicAdd(o + (int64_t)2 * B * d, a2.x); atomicAdd(o + (int64_t)2 * B * d + 1, a2.y);
+    if (sp < 3) {
+      const int l = sp;
       const float2* Q2 = reinterpret_cast<const float2*>((l == 0 ? q0 : (l == 1 ? q1 : q2)) + (int64_t)b * T * d);
       float2 acc = make_float2(0.f, 0.f);
       for (int t = 0; t < T; ++t) {
@@ -170,44 +177,53 @@ __device__ __forceinline__ void softmax_bwd_warp(const float* __restrict__ a, co
   if (lane == 0) atomicAdd(dc, tot);
 }
 
-// One block per sample: da_v[l][n] = V[n,:] . g_v[l] for the three levels in one pass over V[b] (bf16 hi + lo planes),
-// da_q[l][t] = Q_l[t,:] . g_q[l], then the softmax backward of all six attention vectors.
-//   Vp planes [2][B*N][d], Qp planes [2][B][3T][d] ; gv, gq [3][B][d] ; av, aq, dsv, dsq [B][3][N|T]
-__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const float* __restrict__ av, const float* __restrict__ aq,
-                                                            const __nv_bfloat16* __restrict__ Vp, int64_t v_ps,
+// da_v[b][l][n] = V[b][n,:] . g_v[l][b] for the three levels in one pass over V[b] (bf16 hi + lo planes), and
+// da_q[b][l][t] = Q_l[b][t,:] . g_q[l][b].  ATTN_SPLIT blocks per sample, each taking every ATTN_SPLIT-th row (one warp per row).
+//   Vp planes [2][B*N][d], Qp planes [2][B][3T][d] ; gv, gq [3][B][d] ; dav [B][3][N], daq [B][3][T]
+__global__ void __launch_bounds__(256) attn_bwd_dots_kernel(const __nv_bfloat16* __restrict__ Vp, int64_t v_ps,
                                                             const __nv_bfloat16* __restrict__ Qp, int64_t q_ps,
                                                             const float* __restrict__ gv, const float* __restrict__ gq,
-                                                            float* __restrict__ dsv, float* __restrict__ dsq,
-                                                            float* __restrict__ dcv, float* __restrict__ dcq,
-                                                            int B, int N, int T, int d) {
+                                                            float* __restrict__ dav, float* __restrict__ daq, int B, int N, int T, int d) {
   extern __shared__ float sm[];
   float* gv_sm = sm;                  // [3][d]
   float* gq_sm = sm + 3 * d;          // [3][d]
-  float* dav_sm = sm + 6 * d;         // [3][N]
-  float* daq_sm = dav_sm + 3 * N;     // [3][T]
-  const int b = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int b = blockIdx.x, sp = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) {
     const int l = i / d, c = i - l * d;
     gv_sm[i] = gv[((int64_t)l * B + b) * d + c];
     gq_sm[i] = gq[((int64_t)l * B + b) * d + c];
   }
   __syncthreads();
-  for (int n = w; n < N; n += nw) {
+  for (int n = sp * nw + w; n < N; n += nw * ATTN_SPLIT) {
     const __nv_bfloat16* hi = Vp + ((int64_t)b * N + n) * d;
     float o[3];
     row_dots<3>(hi, hi + v_ps, d, gv_sm, d, o);
-    if (lane == 0) { dav_sm[n] = o[0]; dav_sm[N + n] = o[1]; dav_sm[2 * N + n] = o[2]; }
+    if (lane == 0) {
+      float* dst = dav + (int64_t)b * 3 * N + n;
+      dst[0] = o[0]; dst[N] = o[1]; dst[2 * N] = o[2];
+    }
   }
-  for (int r = w; r < 3 * T; r += nw) {
+  for (int r = sp * nw + w; r < 3 * T; r += nw * ATTN_SPLIT) {
     const int l = r / T;
     const __nv_bfloat16* hi = Qp + ((int64_t)b * 3 * T + r) * d;
     float o[1];
     row_dots<1>(hi, hi + q_ps, d, gq_sm + l * d, d, o);
-    if (lane == 0) daq_sm[r] = o[0];
+    if (lane == 0) daq[(int64_t)b * 3 * T + r] = o[0];
   }
-  __syncthreads();
-  if (w < 3) softmax_bwd_warp(av + ((int64_t)b * 3 + w) * N, dav_sm + w * N, N, dsv + ((int64_t)b * 3 + w) * N, dcv);
-  else if (w < 6) softmax_bwd_warp(aq + ((int64_t)b * 3 + (w - 3)) * T, daq_sm + (w - 3) * T, T, dsq + ((int64_t)b * 3 + (w - 3)) * T, dcq);
+}
+// softmax backward of all six attention vectors of a sample: ds = a * (da - <a, da>) ; dc += sum ds.  One block (6 warps) per sample.
+__global__ void __launch_bounds__(192) attn_bwd_softmax_kernel(const float* __restrict__ av, const float* __restrict__ aq,
+                                                               const float* __restrict__ dav, const float* __restrict__ daq,
+                                                               float* __restrict__ dsv, float* __restrict__ dsq,
+                                                               float* __restrict__ dcv, float* __restrict__ dcq, int N, int T) {
+  const int b = blockIdx.x, w = threadIdx.x >> 5;
+  if (w < 3) {
+    const int64_t o = ((int64_t)b * 3 + w) * N;
+    softmax_bwd_warp(av + o, dav + o, N, dsv + o, dcv);
+  } else {
+    const int64_t o = ((int64_t)b * 3 + (w - 3)) * T;
+    softmax_bwd_warp(aq + o, daq + o, T, dsq + o, dcq);
+  }
 }
 
 // dV[b][n][:] += sum_l av[b][l][n] * gv[l][b][:]      (only when the image features need a gradient)
@@ -322,7 +338,7 @@ extern "C" size_t hca_coattn_workspace(int B, int N, int T, int d, int need_dv) 
   (void)need_dv;
   const int64_t BN = (int64_t)B * N, BT3 = (int64_t)B * 3 * T;
   size_t fwd = align_up((size_t)BN * d * 4) + 2 * pl_bytes(d, d) + align_up((size_t)3 * B * (N + T) * 4);
-  size_t bwd = 2 * pl_bytes(d, d) + align_up((size_t)3 * B * (N + T) * 4) + pl_bytes(3 * BN, d) + 2 * pl_bytes(BT3, d) + pl_bytes(BT3, N) +
+  size_t bwd = 2 * pl_bytes(d, d) + 2 * align_up((size_t)3 * B * (N + T) * 4) + pl_bytes(3 * BN, d) + 2 * pl_bytes(BT3, d) + pl_bytes(BT3, N) +
                align_up((size_t)BN * d * 4) + pl_bytes(BN, d);
   return std::max(fwd, bwd) + 4096;
 }
@@ -383,9 +399,10 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
     e.auxp = plv(PVp, 0, N, B, 3); e.aux_mode = TC_AUX_ADD;
     HCA_TRY(launch_gemm_tc(opv(Cp, 0, T, T, 3 * B, true), opv(PQp, 0, T, T, 3 * B, true), 2, N, d, T, e, 1, s, 3 * B));
   }
-  const size_t smem = (size_t)3 * (N + T) * sizeof(float);
+  const size_t smem = (size_t)6 * (N + T) * sizeof(float);
   HCA_CHECK_ARG(smem <= 48 * 1024, "coattn_fwd: N + T too large for the softmax kernel");
-  attn_finish_kernel<<<B, 256, smem, s>>>(svs, sqs, cv, cq, Vd, q0, q1, q2, sv_.av, sv_.aq, vhat, qhat, B, N, T, d);
+  HCA_TRY(zero_async(vhat, (size_t)3 * B * d * 4, s));
+  attn_finish_kernel<<<dim3(B, ATTN_SPLIT), 256, smem, s>>>(svs, sqs, cv, cq, Vd, q0, q1, q2, sv_.av, sv_.aq, vhat, qhat, B, N, T, d);
   HCA_LAUNCHED();
   return 0;
 }
@@ -408,13 +425,14 @@ extern "C" int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv,
   const Pl &Vp = sv_.V, &Qp = sv_.Q, &PVp = sv_.PV, &PQp = sv_.PQ, &Cp = sv_.C;
   Pl Wvp = take_pl(w, d, d), Wqp = take_pl(w, d, d);
   float* dsc = w.take<float>((size_t)3 * B * (N + T));
+  float* dscr = w.take<float>((size_t)3 * B * (N + T));
   Pl dZv = take_pl(w, 3 * BN, d);          // [B][3][N][d]
   Pl dZq = take_pl(w, BT3, d);             // [B][3T][d]
   Pl dPQ = take_pl(w, BT3, d);
   Pl dS = take_pl(w, BT3, N);              // [B][3T][N]
   float* dPVacc = w.take<float>((size_t)BN * d);
   Pl dPV = take_pl(w, BN, d);
-  if (!dPV.p || !dPVacc || !dsc) return set_err(HCA_ERR_WORKSPACE, "coattn_bwd: workspace too small (%zu bytes)", ws_bytes);
+  if (!dPV.p || !dPVacc || !dsc || !dscr) return set_err(HCA_ERR_WORKSPACE, "coattn_bwd: workspace too small (%zu bytes)", ws_bytes);
   float* dsv = dsc;                        // [B][3][N]
   float* dsq = dsc + (size_t)3 * B * N;    // [B][3][T]
 
@@ -427,9 +445,13 @@ extern "C" int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv,
   HCA_TRY(zero_async(dbv, (size_t)d * 4, s));
   HCA_TRY(zero_async(dbq, (size_t)d * 4, s));
   {
-    const size_t smem = ((size_t)6 * d + 3 * (N + T)) * sizeof(float);
-    HCA_CHECK_ARG(smem <= 48 * 1024, "coattn_bwd: d / N / T too large for the softmax-backward kernel");
-    attn_bwd_prep_kernel<<<B, 256, smem, s>>>(sv_.av, sv_.aq, Vp.p, Vp.ps, Qp.p, Qp.ps, gvhat, gqhat, dsv, dsq, dcv, dcq, B, N, T, d);
+    const size_t smem = (size_t)6 * d * sizeof(float);
+    HCA_CHECK_ARG(smem <= 48 * 1024, "coattn_bwd: d too large for the attention-backward kernel");
+    float* dav = dscr;                       // [B][3][N]
+    float* daq = dscr + (size_t)3 * B * N;   // [B][3][T]
+    attn_bwd_dots_kernel<<<dim3(B, ATTN_SPLIT), 256, smem, s>>>(Vp.p, Vp.ps, Qp.p, Qp.ps, gvhat, gqhat, dav, daq, B, N, T, d);
+    HCA_LAUNCHED();
+    attn_bwd_softmax_kernel<<<B, 192, 0, s>>>(sv_.av, sv_.aq, dav, daq, dsv, dsq, dcv, dcq, N, T);
     HCA_LAUNCHED();
   }
   for (int l = 0; l < 3; ++l) {

@@ -40,14 +40,17 @@ constexpr uint32_t L_A_PLANE = L_BM * L_BK * 2;   // one plane of one streamed k
 constexpr uint32_t L_STAGE_BYTES = 2 * L_A_PLANE; // hi + lo
 constexpr int L_MAX_SMEM = 227 * 1024 - 2048;
 
+constexpr int L_TMAX = 128;                       // longest sequence for which the per-step row trimming is tabulated
 struct LstmMaps {
-  CUtensorMap A;   // streamed operand planes, 4-D (cols, t, b, plane), box (64, 1, 128, 1)
-  CUtensorMap W;   // resident operand planes, 4-D (cols, rows, plane, 1), box (64, BN, 1, 1)
+  CUtensorMap A[3];   // streamed operand planes, 4-D (cols, t, b, plane), boxes (64, 1, box_rows[i], 1): full, half and quarter row tile
+  CUtensorMap W;      // resident operand planes, 4-D (cols, rows, plane, 1), box (64, BN, 1, 1)
 };
 
 struct LstmParams {
   int B, T, H;
-  int row0;               // first batch row of this launch (multiple of 128)
+  int tile0;              // first row tile of this launch
+  int rpt;                // batch rows per row tile (<= 128, multiple of 8): tile i owns rows [i * rpt, (i + 1) * rpt)
+  int box_rows[3];        // rows of the three TMA boxes of the streamed operand
   int tiles_n;            // H / 16
   int kbn;                // k-blocks of the recurrent contraction: fwd ceil(H / 64), bwd ceil(4H / 64)
   int K;                  // contraction length: fwd H, bwd 4H
@@ -112,13 +115,14 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
   __shared__ __align__(8) uint64_t bars[2 * L_STAGES + 2];
   __shared__ uint32_t tmem_ptr_smem;
   __shared__ int s_maxlen;
+  __shared__ int s_nact[L_TMAX];     // rows of this tile still running at step t (1 + the last row with len > t)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[L_STAGES + s]); };
   const uint32_t w_bar = smem_u32(&bars[2 * L_STAGES]), tmem_full = smem_u32(&bars[2 * L_STAGES + 1]);
   const int mi = blockIdx.x / p.tiles_n, ni = blockIdx.x - mi * p.tiles_n;
-  const int m0 = p.row0 + mi * L_BM;
-  int* const counters = p.counters + (int64_t)(m0 / L_BM) * p.T;
+  const int m0 = (p.tile0 + mi) * p.rpt;
+  int* const counters = p.counters + (int64_t)(p.tile0 + mi) * p.T;
   const uint32_t w_base = smem_base;
   const uint32_t ring_base = smem_base + (uint32_t)p.kbn * 2u * W_KB_PLANE;
 
@@ -131,19 +135,22 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
     mbar_init(w_bar, 1);
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.A) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.A[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.W) : "memory");
   }
+  for (int i = threadIdx.x; i < L_TMAX; i += blockDim.x) s_nact[i] = 0;
   if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr_smem), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   // steps this row tile needs: the longest sequence among its rows (rows are independent, so other tiles may run longer)
-  if (threadIdx.x < L_BM) {
+  if ((int)threadIdx.x < p.rpt) {
     const int b = m0 + (int)threadIdx.x;
     if (b < p.B) {
-      const int64_t l = p.lens[b];
-      atomicMax(&s_maxlen, (int)(l < 0 ? 0 : (l > p.T ? p.T : l)));
+      const int64_t l64 = p.lens[b];
+      const int l = (int)(l64 < 0 ? 0 : (l64 > p.T ? p.T : l64));
+      atomicMax(&s_maxlen, l);
+      for (int t = 0; t < l && t < L_TMAX; ++t) atomicMax(&s_nact[t], (int)threadIdx.x + 1);
     }
   }
   __syncthreads();
@@ -165,6 +172,12 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         // backward round n computes step t = steps - 2 - n from the gate gradients of step t + 1 (slot t + 1)
         const int dep = BWD ? steps - 1 - n : n;
         const int slot = BWD ? dep : n + 1;
+        const int t_cur = BWD ? steps - 2 - n : n + 1;            // the step this round computes
+        // rows of the tile that are still inside their sequence at that step: the others need no operand rows (their
+        // accumulator rows are never used), so the smallest of the three boxes that covers the running rows is loaded
+        const int nrun = (p.T <= L_TMAX) ? s_nact[t_cur] : p.rpt;
+        const int bi = nrun <= p.box_rows[2] ? 2 : (nrun <= p.box_rows[1] ? 1 : 0);
+        const uint32_t plane_bytes = (uint32_t)p.box_rows[bi] * L_BK * 2;
         const int* cnt = counters + dep;
         if (ld_acquire(cnt) < p.tiles_n) {           // bounded spin: a protocol bug must trap, never hang the device
           const long long t0 = clock64();
@@ -179,10 +192,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         fence_proxy_async_global();                  // peers wrote through the generic proxy; TMA reads through the async proxy
         for (int kb = 0; kb < p.kbn; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1, 11);
-          mbar_expect_tx(full_bar(s), L_STAGE_BYTES);
+          mbar_expect_tx(full_bar(s), 2u * plane_bytes);
           const uint32_t dst = ring_base + (uint32_t)s * L_STAGE_BYTES;
-          tma_load_4d(dst, &maps.A, full_bar(s), kb * L_BK, slot, m0, 0);
-          tma_load_4d(dst + L_A_PLANE, &maps.A, full_bar(s), kb * L_BK, slot, m0, 1);
+          tma_load_4d(dst, &maps.A[bi], full_bar(s), kb * L_BK, slot, m0, 0);
+          tma_load_4d(dst + L_A_PLANE, &maps.A[bi], full_bar(s), kb * L_BK, slot, m0, 1);
           if (++s == L_STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
     const int q = warp & 3;                         // TMEM lane quadrant
     const int r = q * 32 + lane;
     const int b = m0 + r;
-    const bool row_ok = b < p.B;
+    const bool row_ok = r < p.rpt && b < p.B;
     int len_b = 0;
     if (row_ok) {
       const int64_t l = p.lens[b];
@@ -275,7 +288,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
           z[4 * u] = ig; z[4 * u + 1] = fg; z[4 * u + 2] = gg; z[4 * u + 3] = og;
         }
         // publish h_t (slot t + 1) first: it is on the critical path of every CTA of this row tile
-        if (row_ok && t + 1 < p.T) {
+        if (t < len_b && t + 1 < p.T) {                 // (rows past their end keep the zero slot: their h is never read)
           uint4 hi, lo;
           split8(h, hi, lo);
           __nv_bfloat16* dst = p.hp + (bt0 + t + 1) * H + u0;
@@ -464,8 +477,6 @@ __global__ void __launch_bounds__(256) lstm_unperm_kernel(const float* __restric
   }
 }
 
-inline int64_t r8(int64_t x) { return (x + 7) / 8 * 8; }
-
 struct Saved {
   float* act;              // [B][T][4H]
   float* c;                // [B][T][H]
@@ -503,16 +514,48 @@ int tc_splitk(int M, int N, int K) {
   return sk < 1 ? 1 : sk;
 }
 
+// Row tiling: as many row tiles as fit on the device next to each other (tiles * H/16 CTAs <= SMs), so that every tile is as
+// short as possible -- the per-step cost of a CTA is dominated by streaming its tile's rows of the exchanged operand.
+struct RowTiling {
+  int rpt, tiles, per_launch;
+};
+RowTiling row_tiling(int B, int H) {
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+    cudaGetLastError();
+    sms = 148;
+  }
+  RowTiling r;
+  r.per_launch = std::max(1, sms / (H / L_UNITS));
+  const int launches = ((B + L_BM - 1) / L_BM + r.per_launch - 1) / r.per_launch;
+  const int slots = launches * r.per_launch;
+  r.rpt = std::min(L_BM, (int)(((B + slots - 1) / slots + 7) / 8 * 8));
+  r.tiles = (B + r.rpt - 1) / r.rpt;
+  return r;
+}
+size_t counter_count(int B, int T) { return (size_t)((B + 7) / 8 + 1) * T; }
+
 template <bool BWD>
 int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64_t stream_ps, int stream_cols,
                const __nv_bfloat16* w_planes, int64_t w_ps, int w_rows, int w_cols, cudaStream_t s) {
   constexpr int BN = BWD ? L_UNITS : 4 * L_UNITS;
+  LstmParams p = base;
+  p.tiles_n = base.H / L_UNITS;
+  p.K = BWD ? 4 * base.H : base.H;
+  p.kbn = (p.K + L_BK - 1) / L_BK;
+  const RowTiling rt = row_tiling(base.B, base.H);
+  HCA_CHECK_ARG(p.tiles_n <= rt.per_launch * p.tiles_n, "lstm: hidden size %d needs more CTAs per row tile than the device has SMs", base.H);
+  p.rpt = rt.rpt;
+  p.box_rows[0] = rt.rpt;
+  p.box_rows[1] = std::min(rt.rpt, (rt.rpt / 2 + 7) / 8 * 8);
+  p.box_rows[2] = std::min(rt.rpt, (rt.rpt / 4 + 7) / 8 * 8);
   LstmMaps maps;
-  {  // streamed operand [2][B][T][cols]: dims (cols, T, B, 2)
+  for (int i = 0; i < 3; ++i) {  // streamed operand [2][B][T][cols]: dims (cols, T, B, 2)
     const uint64_t dims[4] = {(uint64_t)stream_cols, (uint64_t)base.T, (uint64_t)base.B, 2};
     const uint64_t str[3] = {(uint64_t)stream_cols * 2, (uint64_t)base.T * stream_cols * 2, (uint64_t)stream_ps * 2};
-    const uint32_t box[4] = {L_BK, 1, L_BM, 1};
-    HCA_TRY(tc_make_tmap(&maps.A, true, 4, stream_planes, dims, str, box, 3));
+    const uint32_t box[4] = {L_BK, 1, (uint32_t)p.box_rows[i], 1};
+    HCA_TRY(tc_make_tmap(&maps.A[i], true, 4, stream_planes, dims, str, box, 3));
   }
   {  // resident operand [2][rows][cols]: dims (cols, rows, 2, 1)
     const uint64_t dims[4] = {(uint64_t)w_cols, (uint64_t)w_rows, 2, 1};
@@ -520,10 +563,6 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
     const uint32_t box[4] = {L_BK, BN, 1, 1};
     HCA_TRY(tc_make_tmap(&maps.W, true, 4, w_planes, dims, str, box, 3));
   }
-  LstmParams p = base;
-  p.tiles_n = base.H / L_UNITS;
-  p.K = BWD ? 4 * base.H : base.H;
-  p.kbn = (p.K + L_BK - 1) / L_BK;
   const size_t smem = (size_t)p.kbn * 2 * BN * L_BK * 2 + (size_t)L_STAGES * L_STAGE_BYTES + 1024;
   HCA_CHECK_ARG(smem <= (size_t)L_MAX_SMEM, "lstm: hidden size %d needs %zu bytes of shared memory", base.H, smem);
   static bool attr_set[2] = {false, false};
@@ -531,22 +570,11 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
     HCA_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_MAX_SMEM));
     attr_set[BWD ? 1 : 0] = true;
   }
-  int sms = 148;
-  {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
-      cudaGetLastError();
-      sms = 148;
-    }
-  }
-  // every CTA of a launch must be resident at once (the row tiles synchronise through global counters): at most
-  // floor(SMs / tiles_n) row tiles per launch; row tiles are independent, so the launches simply follow each other
-  const int tiles_m = (base.B + L_BM - 1) / L_BM;
-  const int per_launch = std::max(1, sms / p.tiles_n);
-  HCA_CHECK_ARG(p.tiles_n <= sms, "lstm: hidden size %d needs more CTAs per row tile than the device has SMs", base.H);
-  for (int t0 = 0; t0 < tiles_m; t0 += per_launch) {
-    const int nm = std::min(per_launch, tiles_m - t0);
-    p.row0 = t0 * L_BM;
+  // every CTA of a launch must be resident at once (the CTAs of a row tile synchronise through global counters); row tiles
+  // are independent, so when the batch needs more tiles than fit the launches simply follow each other
+  for (int t0 = 0; t0 < rt.tiles; t0 += rt.per_launch) {
+    const int nm = std::min(rt.per_launch, rt.tiles - t0);
+    p.tile0 = t0;
     lstm_rec_kernel<BWD><<<nm * p.tiles_n, L_THREADS, smem, s>>>(maps, p);
     HCA_LAUNCHED();
   }
@@ -563,9 +591,9 @@ extern "C" size_t hca_lstm_saved_bytes(int B, int T, int E, int H) { return hca:
 extern "C" size_t hca_lstm_workspace(int B, int T, int E, int H) {
   using hca::align_up;
   const size_t BT = (size_t)B * T, H4 = (size_t)4 * H;
-  const size_t fwd = align_up(2 * H4 * E * 2) + align_up(2 * H4 * H * 2) + align_up(H4 * 4) + align_up(((size_t)(B + 127) / 128) * T * 4);
+  const size_t fwd = align_up(2 * H4 * E * 2) + align_up(2 * H4 * H * 2) + align_up(H4 * 4) + align_up(hca::counter_count(B, T) * 4);
   const size_t bwd = align_up(2 * BT * H4 * 2) + align_up(2 * H4 * E * 2) + align_up(2 * H4 * H * 2) + align_up(H4 * E * 4) + align_up(H4 * H * 4) +
-                     align_up(H4 * 4) + align_up(((size_t)(B + 127) / 128) * T * 4);
+                     align_up(H4 * 4) + align_up(hca::counter_count(B, T) * 4);
   return std::max(fwd, bwd) + 4096;
 }
 
@@ -585,8 +613,7 @@ extern "C" int hca_lstm_fwd(const float* x, const int64_t* lens, const float* w_
   __nv_bfloat16* wip = w.take<__nv_bfloat16>((size_t)2 * H4 * E);
   __nv_bfloat16* whp = w.take<__nv_bfloat16>((size_t)2 * H4 * H);
   float* biasp = w.take<float>((size_t)H4);
-  const int tiles_m = (B + L_BM - 1) / L_BM;
-  int* counters = w.take<int>((size_t)tiles_m * T);
+  int* counters = w.take<int>(counter_count(B, T));
   if (!counters) return set_err(HCA_ERR_WORKSPACE, "lstm_fwd: workspace too small (%zu bytes)", ws_bytes);
   HCA_TRY(launch_split_planes(x, E, BT, E, sv.xp, E, BT * E, 2, s));
   lstm_split_perm_kernel<<<ew_grid((int64_t)H4 * E), 256, 0, s>>>(w_ih, H, E, wip, (int64_t)H4 * E);
@@ -596,7 +623,7 @@ extern "C" int hca_lstm_fwd(const float* x, const int64_t* lens, const float* w_
   lstm_bias_perm_kernel<<<(H4 + 255) / 256, 256, 0, s>>>(b_ih, b_hh, H, biasp);
   HCA_LAUNCHED();
   HCA_TRY(zero_async(sv.hp, (size_t)2 * BT * H * 2, s));      // slot 0 (h_{-1} = 0) and the slots no step reaches
-  HCA_TRY(zero_async(counters, (size_t)tiles_m * T * 4, s));
+  HCA_TRY(zero_async(counters, counter_count(B, T) * 4, s));
   {  // x-projection of every (b, t), gate columns in [unit][gate] order, biases folded in
     TcEpilogue e;
     e.D = sv.act; e.ldd = H4; e.bias = biasp;
@@ -629,12 +656,11 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
   float* dwi = w.take<float>((size_t)H4 * E);
   float* dwh = w.take<float>((size_t)H4 * H);
   float* dbp = w.take<float>((size_t)H4);
-  const int tiles_m = (B + L_BM - 1) / L_BM;
-  int* counters = w.take<int>((size_t)tiles_m * T);
+  int* counters = w.take<int>(counter_count(B, T));
   if (!counters) return set_err(HCA_ERR_WORKSPACE, "lstm_bwd: workspace too small (%zu bytes)", ws_bytes);
   HCA_TRY(zero_async(dgp, (size_t)2 * BT * H4 * 2, s));       // rows no step writes must read as zero in the GEMMs below
   HCA_TRY(zero_async(dbp, (size_t)H4 * 4, s));
-  HCA_TRY(zero_async(counters, (size_t)tiles_m * T * 4, s));
+  HCA_TRY(zero_async(counters, counter_count(B, T) * 4, s));
   lstm_split_perm_t_kernel<<<ew_grid((int64_t)H4 * H), 256, 0, s>>>(w_hh, H, wtp, (int64_t)H4 * H);
   HCA_LAUNCHED();
   LstmParams p;

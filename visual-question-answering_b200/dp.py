@@ -40,7 +40,8 @@ def shard_batch(n_items: int, rank: int, world: int) -> slice:
 
 class FlatGradAllReduce:
     def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], process_group=None,
-                 skip: Sequence[str] = ("co_attention.W_b.",), bucket_bytes: int = 16 << 20, overlap: bool = True):
+                 skip: Sequence[str] = ("co_attention.W_b.",), bucket_bytes: int = 16 << 20, overlap: bool = True,
+                 flat_params: bool = False, align: int = 64):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.loss_scale = 1.0 / self.world
@@ -59,16 +60,26 @@ class FlatGradAllReduce:
         if not self.params:
             raise ValueError("no parameters to reduce")
         dev, dt = self.params[0].device, self.params[0].dtype
-        total = sum(p.numel() for p in self.params)
+        # every tensor starts on an `align`-element boundary (256 bytes for fp32): vector loads, TMA and the fused optimizer
+        # all want 16-byte aligned bases; the padding elements stay zero
+        pad = lambda n: (n + align - 1) // align * align
+        total = sum(pad(p.numel()) for p in self.params)
         self.flat = torch.zeros(total, dtype=dt, device=dev)
+        # optional: the parameters themselves become views of one flat buffer too (same offsets), which is what lets the
+        # optimizer step be ONE fused kernel over (flat_p, flat, m, v) -- see optim.FlatAdam
+        self.flat_p = torch.zeros(total, dtype=dt, device=dev) if flat_params else None
         # carve views and buckets
         self.buckets: List[Tuple[int, int]] = []            # [start, end) element ranges of the flat buffer
         self._bucket_of: List[int] = []
         off, b_start, limit = 0, 0, max(1, bucket_bytes // self.flat.element_size())
         for p in self.params:
             n = p.numel()
+            if self.flat_p is not None:
+                view = self.flat_p[off:off + n].view_as(p)
+                view.copy_(p.data)
+                p.data = view
             p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+            off += pad(n)
             self._bucket_of.append(len(self.buckets))
             if off - b_start >= limit:
                 self.buckets.append((b_start, off))

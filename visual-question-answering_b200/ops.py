@@ -416,6 +416,18 @@ def _mlp_backward(ctx, dlogits, *_unused):
 mlp.register_autograd(_mlp_backward, setup_context=_mlp_setup)
 
 
+# ------------------------------------------------------------------------------------------------ optimizer
+@torch.library.custom_op(f"{NS}::adam_step", mutates_args=("p", "m", "v", "step", "coef"), device_types="cuda")
+def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: Tensor, coef: Tensor, lr: float, beta1: float, beta2: float,
+              eps: float) -> None:
+    """Fused Adam update of the flat fp32 parameter buffer (reference main.py:180,222); step is a device int64[1]."""
+    _cuda_f32(p, g, m, v, coef)
+    assert step.dtype == torch.int64 and step.is_cuda and all(t.is_contiguous() for t in (p, g, m, v))
+    with torch.cuda.device(p.device):
+        _lib.check(_lib.lib().hca_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(step), _ptr(coef), lr, beta1, beta2, eps,
+                                            _stream()), "adam_step")
+
+
 # ---------------------------------------------------------------------------------- raw GEMM (tests / profiling)
 _LAYOUTS = {"nt": 0, "nn": 1, "tn": 2}
 

@@ -1,0 +1,38 @@
+"""Optimizer step of the training loop (reference main.py:180,222: ``torch.optim.Adam(model.parameters(), lr)``) as one
+fused CUDA kernel over flat buffers.
+
+``FlatAdam`` takes the ``dp.FlatGradAllReduce`` that owns the flat gradient buffer (built with ``flat_params=True`` so
+that the parameters are views of a second flat buffer with the same offsets).  The update then reads / writes four flat
+fp32 arrays in a single pass (csrc/adam.cu) instead of torch's eight multi-tensor passes, keeps its step counter on the
+device (CUDA-graph capturable) and touches exactly the tensors the all-reduce covers: ``co_attention.W_b`` (never used by
+the reference's forward, model.py:347 vs :377, so its gradient is None and torch's Adam skips it too) and frozen VGG
+weights are left alone.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class FlatAdam:
+    def __init__(self, reducer, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        if reducer.flat_p is None:
+            raise ValueError("FlatAdam needs FlatGradAllReduce(..., flat_params=True)")
+        if not reducer.flat.is_cuda:
+            raise RuntimeError("FlatAdam runs on CUDA only (no CPU fallback)")
+        self.reducer = reducer
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.exp_avg = torch.zeros_like(reducer.flat)
+        self.exp_avg_sq = torch.zeros_like(reducer.flat)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=reducer.flat.device)
+        self._coef = torch.zeros(2, dtype=torch.float32, device=reducer.flat.device)
+
+    @torch.no_grad()
+    def step(self):
+        r = self.reducer
+        ops.adam_step(r.flat_p, r.flat, self.exp_avg, self.exp_avg_sq, self.step_count, self._coef, self.lr, self.betas[0],
+                      self.betas[1], self.eps)
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.reducer.zero_grad()
