@@ -125,7 +125,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     B = 32                                        # bounded sample of the workload: 32 of the 160 samples per step
-    val, ms, threads = cpu_reference(B, args.steps, max(args.warmup, 1))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm is meant to use every host core it can
+    val, ms, threads = cpu_reference(B, args.steps, max(args.warmup, 1), threads=os.cpu_count())
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
@@ -158,7 +159,7 @@ class Stepper:
         p = syn.make_params(CFG["d"], CFG["vocab"], CFG["K"], CFG["mlp"], seed=0)
         self.net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()}, strict=False)
         self.net.to(device)
-        self.dp = pkg.dp.FlatGradAllReduce(self.net.named_parameters(), group, overlap=not use_graph, flat_params=True)
+        self.dp = pkg.dp.FlatGradAllReduce(self.net.named_parameters(), group, overlap=True, flat_params=True)
         self.opt = pkg.optim.FlatAdam(self.dp, lr=1e-4)          # Adam(lr=1e-4), README.md:95-100 / main.py:180
         self.slots = []
         rank = torch.distributed.get_rank() if world > 1 else 0
@@ -261,7 +262,17 @@ def run_ours(args):
             with torch.cuda.stream(s):
                 st.warm(3)                      # warm up on the side stream torch.cuda.graph captures from
             torch.cuda.current_stream().wait_stream(s)
-            st.capture()
+            try:
+                st.capture()                    # bucketed all-reduce launched from the gradient hooks, inside the graph
+            except Exception:
+                if world == 1:
+                    raise
+                torch.cuda.synchronize()
+                st.dp.set_overlap(False)        # NCCL launched from hooks did not capture: one all-reduce pass after backward
+                graph_note = "cuda-graph replay (all-reduce after backward: hook-launched NCCL did not capture)"
+                for slot in st.slots:
+                    slot["graph"] = None
+                st.capture()
         except Exception as e:                  # capture is an optimisation, never a requirement
             graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
             for slot in st.slots:
@@ -340,7 +351,7 @@ def run_ours(args):
         step_tflops = FLOPS_PER_SAMPLE * args.batch / (ms_step * 1e-3) / 1e12
         cpu = None
         if world == 1 and not args.skip_cpu_baseline:
-            v, ms, threads = cpu_reference(32, 5, 2)
+            v, ms, threads = cpu_reference(32, 5, 2, threads=os.cpu_count())
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "5 steps of batch 32 (of the 160-sample batch), torch CPU fp32, oracle/torch_port.py", "ms_per_step": ms}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -241,14 +241,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int nks = __shfl_sync(0xffffffffu, min(BK / UMMA_K, (kleft + UMMA_K - 1) / UMMA_K), 0);
 #pragma unroll
         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-          if (ks < nks) {
+          const uint32_t active = ks < nks ? 1u : 0u;          // predicate, not a branch (see umma_bf16_elect32)
 #pragma unroll
-            for (int i = 0; i < P; ++i) {
+          for (int i = 0; i < P; ++i) {
 #pragma unroll
-              for (int j = 0; j < P - i; ++j) {
-                umma_bf16_elect32(d_tmem, au + i * (A_TILE_BYTES >> 4) + ks * a_kstep, desc_hi,
-                                  bu + j * (B_TILE_BYTES >> 4) + ks * b_kstep, desc_hi, idesc, (ks | i | j) != 0 ? 1u : first);
-              }
+            for (int j = 0; j < P - i; ++j) {
+              umma_bf16_elect32(d_tmem, au + i * (A_TILE_BYTES >> 4) + ks * a_kstep, desc_hi,
+                                bu + j * (B_TILE_BYTES >> 4) + ks * b_kstep, desc_hi, idesc, (ks | i | j) != 0 ? 1u : first, active);
             }
           }
         }

@@ -34,10 +34,9 @@ using namespace ptx;
 constexpr int L_BM = 128;                         // batch rows per CTA (UMMA M)
 constexpr int L_BK = 64;                          // bf16 per k-block row = 128 B = one SWIZZLE_128B span
 constexpr int L_UNITS = 16;                       // hidden units per CTA
-constexpr int L_STAGES = 3;
+constexpr int L_MAX_STAGES = 16;                  // ring slots of the streamed operand (as many as fit: short row tiles -> many small slots)
+constexpr uint32_t L_RING_BYTES = 96 * 1024;
 constexpr int L_THREADS = 64 + 256;               // warp 0 TMA, warp 1 MMA, warps 2..9 cell epilogue (2 groups x 4 TMEM quadrants)
-constexpr uint32_t L_A_PLANE = L_BM * L_BK * 2;   // one plane of one streamed k-block: 16 KB
-constexpr uint32_t L_STAGE_BYTES = 2 * L_A_PLANE; // hi + lo
 constexpr int L_MAX_SMEM = 227 * 1024 - 2048;
 
 constexpr int L_TMAX = 128;                       // longest sequence for which the per-step row trimming is tabulated
@@ -51,6 +50,8 @@ struct LstmParams {
   int tile0;              // first row tile of this launch
   int rpt;                // batch rows per row tile (<= 128, multiple of 8): tile i owns rows [i * rpt, (i + 1) * rpt)
   int box_rows[3];        // rows of the three TMA boxes of the streamed operand
+  int stages;             // ring slots in use
+  uint32_t plane_bytes;   // bytes of one plane of one ring slot (rpt rows x 128 B); a slot = hi plane + lo plane
   int tiles_n;            // H / 16
   int kbn;                // k-blocks of the recurrent contraction: fwd ceil(H / 64), bwd ceil(4H / 64)
   int K;                  // contraction length: fwd H, bwd 4H
@@ -112,14 +113,15 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
   constexpr uint32_t TMEM_COLS = BWD ? 32 : 64;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  __shared__ __align__(8) uint64_t bars[2 * L_STAGES + 2];
+  __shared__ __align__(8) uint64_t bars[2 * L_MAX_STAGES + 2];
   __shared__ uint32_t tmem_ptr_smem;
   __shared__ int s_maxlen;
   __shared__ int s_nact[L_TMAX];     // rows of this tile still running at step t (1 + the last row with len > t)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
-  auto empty_bar = [&](int s) { return smem_u32(&bars[L_STAGES + s]); };
-  const uint32_t w_bar = smem_u32(&bars[2 * L_STAGES]), tmem_full = smem_u32(&bars[2 * L_STAGES + 1]);
+  auto empty_bar = [&](int s) { return smem_u32(&bars[L_MAX_STAGES + s]); };
+  const uint32_t w_bar = smem_u32(&bars[2 * L_MAX_STAGES]), tmem_full = smem_u32(&bars[2 * L_MAX_STAGES + 1]);
+  const uint32_t stage_bytes = 2u * p.plane_bytes;
   const int mi = blockIdx.x / p.tiles_n, ni = blockIdx.x - mi * p.tiles_n;
   const int m0 = (p.tile0 + mi) * p.rpt;
   int* const counters = p.counters + (int64_t)(p.tile0 + mi) * p.T;
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     s_maxlen = 0;
-    for (int s = 0; s < L_STAGES; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -193,16 +195,17 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         for (int kb = 0; kb < p.kbn; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1, 11);
           mbar_expect_tx(full_bar(s), 2u * plane_bytes);
-          const uint32_t dst = ring_base + (uint32_t)s * L_STAGE_BYTES;
+          const uint32_t dst = ring_base + (uint32_t)s * stage_bytes;
           tma_load_4d(dst, &maps.A[bi], full_bar(s), kb * L_BK, slot, m0, 0);
-          tma_load_4d(dst + L_A_PLANE, &maps.A[bi], full_bar(s), kb * L_BK, slot, m0, 1);
-          if (++s == L_STAGES) { s = 0; ph ^= 1; }
+          tma_load_4d(dst + p.plane_bytes, &maps.A[bi], full_bar(s), kb * L_BK, slot, m0, 1);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(L_BM >> 4) << 24);
+    constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(L_BM >> 4) << 24);
     constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     mbar_wait(w_bar, 0, 12);
     tc_fence_after();
@@ -211,25 +214,33 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
     const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t a_ring = __shfl_sync(0xffffffffu, ((ring_base & 0x3FFFFu) >> 4) | (1u << 16), 0);
     const uint32_t w_res = __shfl_sync(0xffffffffu, ((w_base & 0x3FFFFu) >> 4) | (1u << 16), 0);
+    const uint32_t a_lo = __shfl_sync(0xffffffffu, p.plane_bytes >> 4, 0);
     for (int n = 0; n < rounds; ++n) {
       for (int kb = 0; kb < p.kbn; ++kb) {
         mbar_wait(full_bar(s), ph, 13);
         tc_fence_after();
-        const uint32_t au = __shfl_sync(0xffffffffu, a_ring + (uint32_t)s * (L_STAGE_BYTES >> 4), 0);
+        const uint32_t au = __shfl_sync(0xffffffffu, a_ring + (uint32_t)s * (stage_bytes >> 4), 0);
         const uint32_t bu = __shfl_sync(0xffffffffu, w_res + (uint32_t)kb * (2u * W_KB_PLANE >> 4), 0);
         const uint32_t first = __shfl_sync(0xffffffffu, kb == 0 ? 0u : 1u, 0);
         const int nks = __shfl_sync(0xffffffffu, min(L_BK / 16, (p.K - kb * L_BK + 15) / 16), 0);
 #pragma unroll
         for (int ks = 0; ks < L_BK / 16; ++ks) {
-          if (ks < nks) {
+          const uint32_t active = ks < nks ? 1u : 0u;          // predicate, not a branch (keeps the descriptors in uniform registers)
+          const uint32_t acc0 = ks != 0 ? 1u : first;
+          if constexpr (BWD) {
+            // the hi and lo planes of the resident slice lie back to back (16 + 16 rows): one N = 32 MMA gives hi.hi (columns
+            // 0..15) and hi.lo (columns 16..31), a second N = 16 MMA adds lo.hi -- 2 instructions per k-step instead of 3
+            umma_bf16_imm<desc_hi, idesc2>(d_tmem, au + ks * 2, bu + ks * 2, acc0, active);
+            umma_bf16_imm<desc_hi, idesc>(d_tmem, au + a_lo + ks * 2, bu + ks * 2, 1u, active);
+          } else {
             // hi.hi + hi.lo + lo.hi
-            umma_bf16_elect32(d_tmem, au + ks * 2, desc_hi, bu + ks * 2, desc_hi, idesc, ks != 0 ? 1u : first);
-            umma_bf16_elect32(d_tmem, au + ks * 2, desc_hi, bu + (W_KB_PLANE >> 4) + ks * 2, desc_hi, idesc, 1u);
-            umma_bf16_elect32(d_tmem, au + (L_A_PLANE >> 4) + ks * 2, desc_hi, bu + ks * 2, desc_hi, idesc, 1u);
+            umma_bf16_imm<desc_hi, idesc>(d_tmem, au + ks * 2, bu + ks * 2, acc0, active);
+            umma_bf16_imm<desc_hi, idesc>(d_tmem, au + ks * 2, bu + (W_KB_PLANE >> 4) + ks * 2, 1u, active);
+            umma_bf16_imm<desc_hi, idesc>(d_tmem, au + a_lo + ks * 2, bu + ks * 2, 1u, active);
           }
         }
         umma_commit_elect(empty_bar(s));
-        if (++s == L_STAGES) { s = 0; ph ^= 1; }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
       umma_commit_elect(tmem_full);
     }
@@ -354,13 +365,14 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         if (t < steps - 1) {                         // + W_hh^T dz_{t+1}
           mbar_wait(tmem_full, (uint32_t)((steps - 2 - t) & 1), 15);
           tc_fence_after();
-          uint32_t v[8];
+          uint32_t v[8], v2[8];                    // columns 0..15: hi.hi + lo.hi ; columns 16..31: hi.lo
           __syncwarp();
           tmem_ld8(lane_addr + (uint32_t)(eg * 8), v);
+          tmem_ld8(lane_addr + (uint32_t)(L_UNITS + eg * 8), v2);
           tc_fence_before();
           if (valid) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) dh[u] += __uint_as_float(v[u]);
+            for (int u = 0; u < 8; ++u) dh[u] += __uint_as_float(v[u]) + __uint_as_float(v2[u]);
           }
         }
         float dz[32];
@@ -563,7 +575,13 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
     const uint32_t box[4] = {L_BK, BN, 1, 1};
     HCA_TRY(tc_make_tmap(&maps.W, true, 4, w_planes, dims, str, box, 3));
   }
-  const size_t smem = (size_t)p.kbn * 2 * BN * L_BK * 2 + (size_t)L_STAGES * L_STAGE_BYTES + 1024;
+  // ring slots of the streamed operand: hi + lo plane of rpt rows x 64 k each (whole 8-row swizzle atoms: rpt % 8 == 0)
+  p.plane_bytes = (uint32_t)rt.rpt * L_BK * 2;
+  // (the MMA always reads 128 rows = 16 KB from a plane's base: rows beyond rpt are other slots' data and only feed unused
+  // accumulator rows, but the last slot's read must stay inside the allocation, hence the tail padding)
+  const uint32_t tail_pad = 16 * 1024 - p.plane_bytes;
+  p.stages = std::max(2, std::min(L_MAX_STAGES, (int)((L_RING_BYTES - tail_pad) / (2 * p.plane_bytes))));
+  const size_t smem = (size_t)p.kbn * 2 * BN * L_BK * 2 + (size_t)p.stages * 2 * p.plane_bytes + tail_pad + 1024;
   HCA_CHECK_ARG(smem <= (size_t)L_MAX_SMEM, "lstm: hidden size %d needs %zu bytes of shared memory", base.H, smem);
   static bool attr_set[2] = {false, false};
   if (!attr_set[BWD ? 1 : 0]) {

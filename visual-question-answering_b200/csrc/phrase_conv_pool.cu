@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(256) pool3_fwd_kernel(const float* __restrict_
 
 // one warp per listed element: the three pre-activations of its channel triple in plain fp32, then tanh and the max again
 __global__ void __launch_bounds__(256) fixup_ties_kernel(const int* __restrict__ tie_list, const int* __restrict__ tie_count, int tie_cap,
-                                                         const float* __restrict__ acat, const float* __restrict__ w1,
-                                                         const float* __restrict__ wr2, const float* __restrict__ wr3,
+                                                         const float* __restrict__ x, int T, const float* __restrict__ w1,
+                                                         const float* __restrict__ w2, const float* __restrict__ w3,
                                                          const float* __restrict__ b1, const float* __restrict__ b2,
                                                          const float* __restrict__ b3, float* __restrict__ out,
                                                          uint8_t* __restrict__ idx, int E) {
@@ -126,10 +126,16 @@ __global__ void __launch_bounds__(256) fixup_ties_kernel(const int* __restrict__
     for (int j = 0; j < 3; ++j) {
       const int c = 3 * e + j;                    // channel of the concatenated [uni|bi|tri] axis
       const int k = c / E + 1, o = c % E;         // which conv, which output channel
-      const float* wrow = (k == 1 ? w1 : (k == 2 ? wr2 : wr3)) + (int64_t)o * k * E;
-      const float* arow = acat + r * 3 * (int64_t)E + (k == 1 ? E : 0);
+      const float* wrow = (k == 1 ? w1 : (k == 2 ? w2 : w3)) + (int64_t)o * E * k;   // conv layout [C_in][k]
+      const int t = (int)(r % T);
       float acc = 0.f;
-      for (int kk = lane; kk < k * E; kk += 32) acc = fmaf(arow[kk], wrow[kk], acc);
+      // taps of conv k cover x[t-1], x[t] (k = 2), x[t-1..t+1] (k = 3), x[t] (k = 1); zeros outside [0, T)
+      for (int tap = 0; tap < k; ++tap) {
+        const int tt = t + tap - (k == 1 ? 0 : 1);
+        if (tt < 0 || tt >= T) continue;
+        const float* xrow = x + (r + tt - t) * (int64_t)E;
+        for (int cc = lane; cc < E; cc += 32) acc = fmaf(xrow[cc], wrow[(int64_t)cc * k + tap], acc);
+      }
       acc = warp_sum(acc);
       v[j] = tanhf(acc + (k == 1 ? b1 : (k == 2 ? b2 : b3))[o]);
     }
@@ -168,6 +174,108 @@ __global__ void __launch_bounds__(256) pool3_bwd_kernel(const float* __restrict_
 }
 
 
+// ---- tensor-core path helpers: operands are produced directly as bf16 planes (no fp32 im2col / repack round trips) ----
+// x = x0 + x1 (+ x2), planes of 4 consecutive elements packed as uint2
+template <int P>
+__device__ __forceinline__ void split4(float (&x)[4], uint2 (&out)[P]) {
+#pragma unroll
+  for (int pl = 0; pl < P; ++pl) {
+    __nv_bfloat16 h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __float2bfloat16_rn(x[j]);
+      x[j] -= __bfloat162float(h[j]);
+    }
+    out[pl] = *reinterpret_cast<const uint2*>(h);
+  }
+}
+// planes [P][R][3E] of Acat[r][j*E + c] = x[b][t+j-1][c]
+template <int P>
+__global__ void __launch_bounds__(256) im2col3_planes_kernel(const float4* __restrict__ x, __nv_bfloat16* __restrict__ planes, int64_t ps,
+                                                             int B, int T, int E4) {
+  const int64_t total = (int64_t)B * T * 3 * E4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % E4);
+    const int j = (int)((i / E4) % 3);
+    const int64_t r = i / (3 * E4);
+    const int t = (int)(r % T) + j - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < T) v = __ldg(x + (r + j - 1) * E4 + c);
+    float xv[4] = {v.x, v.y, v.z, v.w};
+    uint2 o[P];
+    split4<P>(xv, o);
+#pragma unroll
+    for (int pl = 0; pl < P; ++pl) *reinterpret_cast<uint2*>(planes + pl * ps + i * 4) = o[pl];
+  }
+}
+// planes [P][E][k*E] of the tap-major weight Wr[o][j*E + c] = w[o][c][j]  (conv layout [C_out][C_in][k])
+template <int P>
+__global__ void __launch_bounds__(256) conv_w_planes_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ planes, int64_t ps, int E,
+                                                            int k) {
+  const int64_t total = (int64_t)E * E * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % E);
+    const int j = (int)((i / E) % k);
+    const int64_t o = i / ((int64_t)E * k);
+    float x = w[(o * E + c) * k + j];
+#pragma unroll
+    for (int pl = 0; pl < P; ++pl) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      planes[pl * ps + i] = h;
+      x -= __bfloat162float(h);
+    }
+  }
+}
+// Pool backward straight into operand planes: dcat[r][3e+j] = (j == idx) ? dout * (1 - out^2) : 0 as bf16 hi/lo planes
+// [2][R][3E], plus the three bias gradients (column sums of dcat over r).  Thread <-> one channel triple e, block <-> a slab
+// of rows, so the column sums stay in registers until one atomic per column and block.
+constexpr int POOL_BWD_ROWS = 32;
+__global__ void __launch_bounds__(256) pool3_bwd_planes_kernel(const float* __restrict__ out, const uint8_t* __restrict__ idx,
+                                                               const float* __restrict__ dout, const int64_t* __restrict__ lens,
+                                                               __nv_bfloat16* __restrict__ planes, int64_t ps, float* __restrict__ db1,
+                                                               float* __restrict__ db2, float* __restrict__ db3, int B, int T, int E) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t R = (int64_t)B * T;
+  const int64_t r0 = (int64_t)blockIdx.y * POOL_BWD_ROWS, r1 = min(R, r0 + POOL_BWD_ROWS);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    const int b = (int)(r / T), t = (int)(r - (int64_t)b * T);
+    float g = 0.f;
+    int j = 0;
+    if (!lens || t < lens[b]) {
+      const float o = out[r * E + e];
+      g = dout[r * E + e] * (1.f - o * o);
+      j = idx[r * E + e];
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(g);
+    const __nv_bfloat16 l = __float2bfloat16_rn(g - __bfloat162float(h));
+    const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+    __nv_bfloat16* ph = planes + r * 3 * (int64_t)E + 3 * e;
+    ph[0] = j == 0 ? h : z; ph[1] = j == 1 ? h : z; ph[2] = j == 2 ? h : z;
+    ph[ps] = j == 0 ? l : z; ph[ps + 1] = j == 1 ? l : z; ph[ps + 2] = j == 2 ? l : z;
+    s0 += j == 0 ? g : 0.f; s1 += j == 1 ? g : 0.f; s2 += j == 2 ? g : 0.f;
+  }
+  const float sv[3] = {s0, s1, s2};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int c = 3 * e + j;                    // channel of the concatenated [uni|bi|tri] axis
+    float* db = c < E ? db1 : (c < 2 * E ? db2 : db3);
+    atomicAdd(db + (c % E), sv[j]);
+  }
+}
+// tap-major fp32 weight gradient -> conv layout: w[o][c][j] = wr[o][j*E + c]
+__global__ void __launch_bounds__(256) unpack_conv_w_kernel(const float* __restrict__ wr, float* __restrict__ w, int E, int k) {
+  const int64_t total = (int64_t)E * E * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % k);
+    const int c = (int)((i / k) % E);
+    const int64_t o = i / ((int64_t)E * k);
+    w[i] = wr[(o * k + j) * E + c];
+  }
+}
+
+
 struct ConvWs {
   Workspace w;
   float *acat, *cat, *dA, *wr2, *wr3, *dwr2, *dwr3;
@@ -202,7 +310,7 @@ extern "C" size_t hca_phrase_conv_pool_workspace(int B, int T, int E) {
   const size_t R = (size_t)B * T;
   return 3 * align_up(R * 3 * E * 4) + 2 * (align_up((size_t)E * 2 * E * 4) + align_up((size_t)E * 3 * E * 4)) + 1024 +
          align_up((R * E / 8 + 1024) * 4) +                                             // near-tie list
-         3 * 2 * (align_up(R * 3 * E) + 3 * align_up((size_t)E * 3 * E)) +               // bf16x3 planes of Acat and the weights
+         4 * 2 * align_up(R * 3 * E) + 3 * 3 * 2 * align_up((size_t)E * 3 * E) + 8192 +   // bf16 planes: Acat (x3 fwd) / Acat + dcat (x2 bwd), weights
 
          std::max(hca::dense_scratch_bytes(E, 3 * E, (int)R), hca::dense_scratch_bytes((int)R, 3 * E, E));
 }
@@ -217,28 +325,25 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
   ConvWs c = carve(ws, ws_bytes, B, T, E);
   if (!c.ok) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small (%zu bytes)", ws_bytes);
   const int R = B * T;
-  im2col3_kernel<<<ew_grid((int64_t)R * 3 * E / 4), 256, 0, s>>>((const float4*)x, (float4*)c.acat, B, T, E / 4);
-  HCA_LAUNCHED();
-  repack_conv_w_kernel<<<ew_grid((int64_t)E * E * 2), 256, 0, s>>>(w2, c.wr2, E, 2, false);
-  HCA_LAUNCHED();
-  repack_conv_w_kernel<<<ew_grid((int64_t)E * E * 3), 256, 0, s>>>(w3, c.wr3, E, 3, false);
-  HCA_LAUNCHED();
-  const float* wr[3] = {w1, c.wr2, c.wr3};
   const float* bs[3] = {b1, b2, b3};
   const bool tc = use_tc() && tc_available() && (E % 8 == 0);      // TMA needs 16-byte aligned plane windows
   if (tc) {
-    // tensor cores, bf16x3 operand split (6 MMAs per product, fp32-grade): Acat is split once and the three convs read
-    // column windows of its planes; bias + tanh fused in the epilogue; near-ties are repaired exactly below
+    // tensor cores, bf16x3 operand split (6 MMAs per product, fp32-grade): the row-shifted operand Acat and the tap-major
+    // weights are written directly as bf16 planes (no fp32 im2col / repack round trip); the three convs read column windows
+    // of the Acat planes; bias + tanh fused in the epilogue; near-ties are repaired exactly below
     const int P = 3;
     const int64_t lda = 3 * (int64_t)E, a_stride = (int64_t)R * lda;
     __nv_bfloat16* ap = c.w.take<__nv_bfloat16>((size_t)P * a_stride);
     if (!ap) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for operand planes");
-    HCA_TRY(launch_split_planes(c.acat, lda, R, 3 * E, ap, lda, a_stride, P, s));
+    im2col3_planes_kernel<3><<<ew_grid((int64_t)R * 3 * E / 4), 256, 0, s>>>((const float4*)x, ap, a_stride, B, T, E / 4);
+    HCA_LAUNCHED();
+    const float* ws_[3] = {w1, w2, w3};
     for (int k = 1; k <= 3; ++k) {
       const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
       __nv_bfloat16* wp = c.w.take<__nv_bfloat16>((size_t)P * w_stride);
       if (!wp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for weight planes");
-      HCA_TRY(launch_split_planes(wr[k - 1], ldw, E, k * E, wp, ldw, w_stride, P, s));
+      conv_w_planes_kernel<3><<<ew_grid((int64_t)E * E * k), 256, 0, s>>>(ws_[k - 1], wp, w_stride, E, k);
+      HCA_LAUNCHED();
       TcOperand A, Bw;
       A.planes = ap + (k == 1 ? E : 0); A.ld = lda; A.plane_stride = a_stride; A.rows = R; A.cols = k * E;
       Bw.planes = wp; Bw.ld = ldw; Bw.plane_stride = w_stride; Bw.rows = E; Bw.cols = k * E;
@@ -249,10 +354,17 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
     HCA_TRY(zero_async(c.tie_count, sizeof(int), s));
     pool3_fwd_kernel<<<ew_grid((int64_t)R * E), 256, 0, s>>>(c.cat, lens, out, idx, B, T, E, c.tie_list, c.tie_count, c.tie_cap);
     HCA_LAUNCHED();
-    fixup_ties_kernel<<<148 * 2, 256, 0, s>>>(c.tie_list, c.tie_count, c.tie_cap, c.acat, w1, c.wr2, c.wr3, b1, b2, b3, out, idx, E);
+    fixup_ties_kernel<<<148 * 2, 256, 0, s>>>(c.tie_list, c.tie_count, c.tie_cap, x, T, w1, w2, w3, b1, b2, b3, out, idx, E);
     HCA_LAUNCHED();
     return 0;
   }
+  im2col3_kernel<<<ew_grid((int64_t)R * 3 * E / 4), 256, 0, s>>>((const float4*)x, (float4*)c.acat, B, T, E / 4);
+  HCA_LAUNCHED();
+  repack_conv_w_kernel<<<ew_grid((int64_t)E * E * 2), 256, 0, s>>>(w2, c.wr2, E, 2, false);
+  HCA_LAUNCHED();
+  repack_conv_w_kernel<<<ew_grid((int64_t)E * E * 3), 256, 0, s>>>(w3, c.wr3, E, 3, false);
+  HCA_LAUNCHED();
+  const float* wr[3] = {w1, c.wr2, c.wr3};
   // exact-fp32 CUDA-core path: three GEMMs, bias + tanh fused, writing the column blocks of cat [R, 3E]
   for (int k = 1; k <= 3; ++k) {
     GemmParams g;
@@ -281,6 +393,57 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
   ConvWs c = carve(ws, ws_bytes, B, T, E);
   if (!c.ok) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small (%zu bytes)", ws_bytes);
   const int R = B * T;
+  if (use_tc() && tc_available() && (E % 8 == 0)) {
+    // tensor-core path: every operand is produced once, directly as bf16 hi/lo planes, and the six products read windows of them
+    const int64_t ld3 = 3 * (int64_t)E, pstride = (int64_t)R * ld3;
+    __nv_bfloat16* ap = c.w.take<__nv_bfloat16>((size_t)2 * pstride);       // Acat planes
+    __nv_bfloat16* dp = c.w.take<__nv_bfloat16>((size_t)2 * pstride);       // dcat planes
+    if (!dp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for operand planes");
+    im2col3_planes_kernel<2><<<ew_grid((int64_t)R * 3 * E / 4), 256, 0, s>>>((const float4*)x, ap, pstride, B, T, E / 4);
+    HCA_LAUNCHED();
+    float* dbs[3] = {db1, db2, db3};
+    for (int k = 0; k < 3; ++k) HCA_TRY(zero_async(dbs[k], (size_t)E * 4, s));
+    pool3_bwd_planes_kernel<<<dim3((E + 255) / 256, (R + POOL_BWD_ROWS - 1) / POOL_BWD_ROWS), 256, 0, s>>>(out, idx, dout, lens, dp, pstride, db1,
+                                                                                                       db2, db3, B, T, E);
+    HCA_LAUNCHED();
+    // weight gradients, tap-major: dWr_k[o][kk] = sum_r dcat[r][(k-1)E + o] * Acat[r][a_off + kk]   (K = R, split-K)
+    float* dwr[3] = {dw1, c.dwr2, c.dwr3};
+    for (int k = 1; k <= 3; ++k) {
+      TcOperand A, Bm;
+      A.planes = dp + (k - 1) * E; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = E; A.mn_major = true;
+      Bm.planes = ap + (k == 1 ? E : 0); Bm.ld = ld3; Bm.plane_stride = pstride; Bm.rows = R; Bm.cols = k * E; Bm.mn_major = true;
+      const int tiles = ((E + 127) / 128) * ((k * E + 127) / 128);
+      int sk = tiles >= 96 ? 1 : std::max(1, std::min((148 + tiles - 1) / tiles, (R + 255) / 256));
+      if (sk > 1) HCA_TRY(zero_async(dwr[k - 1], (size_t)E * k * E * 4, s));
+      TcEpilogue ep;
+      ep.D = dwr[k - 1]; ep.ldd = (int64_t)k * E;
+      HCA_TRY(launch_gemm_tc(A, Bm, 2, E, k * E, R, ep, sk, s));
+    }
+    unpack_conv_w_kernel<<<ew_grid((int64_t)E * E * 2), 256, 0, s>>>(c.dwr2, dw2, E, 2);
+    HCA_LAUNCHED();
+    unpack_conv_w_kernel<<<ew_grid((int64_t)E * E * 3), 256, 0, s>>>(c.dwr3, dw3, E, 3);
+    HCA_LAUNCHED();
+    if (dx) {
+      // dA[r][a_off + kk] (+)= sum_o dcat[r][(k-1)E + o] * Wr_k[o][kk]: tri first (covers all 3E columns), bi and uni accumulate
+      const float* ws_[3] = {w1, w2, w3};
+      for (int k = 3; k >= 1; --k) {
+        const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
+        __nv_bfloat16* wp = c.w.take<__nv_bfloat16>((size_t)2 * w_stride);
+        if (!wp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for weight planes");
+        conv_w_planes_kernel<2><<<ew_grid((int64_t)E * E * k), 256, 0, s>>>(ws_[k - 1], wp, w_stride, E, k);
+        HCA_LAUNCHED();
+        TcOperand A, Bm;
+        A.planes = dp + (k - 1) * E; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = E;
+        Bm.planes = wp; Bm.ld = ldw; Bm.plane_stride = w_stride; Bm.rows = E; Bm.cols = k * E; Bm.mn_major = true;
+        TcEpilogue ep;
+        ep.D = c.dA + (k == 1 ? E : 0); ep.ldd = ld3; ep.accumulate = (k != 3);
+        HCA_TRY(launch_gemm_tc(A, Bm, 2, R, k * E, E, ep, 1, s));
+      }
+      col2im3_kernel<<<ew_grid((int64_t)R * E / 4), 256, 0, s>>>((const float4*)c.dA, (float4*)dx, B, T, E / 4);
+      HCA_LAUNCHED();
+    }
+    return 0;
+  }
   float* dcat = c.cat;
   im2col3_kernel<<<ew_grid((int64_t)R * 3 * E / 4), 256, 0, s>>>((const float4*)x, (float4*)c.acat, B, T, E / 4);
   HCA_LAUNCHED();

@@ -111,17 +111,38 @@ __device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc,
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// descriptors passed as 32-bit halves so that ptxas can build them on the uniform datapath
+// descriptors passed as 32-bit halves so that ptxas can build them on the uniform datapath.  `active` (warp-uniform 0 / 1)
+// predicates the instruction off without a branch: a branch on a run-time value around the MMA makes ptxas treat the
+// descriptors as divergent again (ELECT + VOTEU + R2UR per MMA), which is what the uniform-register form exists to avoid.
 __device__ __forceinline__ void umma_bf16_elect32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                                  uint32_t idesc, uint32_t accumulate) {
+                                                  uint32_t idesc, uint32_t accumulate, uint32_t active = 1u) {
   asm volatile(
-      "{\n\t.reg .pred p, pe;\n\t.reg .b64 da, db;\n\t"
+      "{\n\t.reg .pred p, pe, pa;\n\t.reg .b64 da, db;\n\t"
       "mov.b64 da, {%1, %2};\n\t"
       "mov.b64 db, {%3, %4};\n\t"
       "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %7, 0;\n\t"
+      "and.pred pe, pe, pa;\n\t"
       "setp.ne.b32 p, %6, 0;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(active)
+      : "memory");
+}
+// Same, with the constant descriptor halves and the instruction descriptor as PTX immediates: only the two address words have
+// to travel from vector to uniform registers per MMA (2 R2UR instead of 5), which matters when the MMAs are small (N = 16 / 32:
+// 8-16 tensor cycles each) and the issue rate, not the tensor pipe, is the limit.
+template <uint32_t DESC_HI, uint32_t IDESC>
+__device__ __forceinline__ void umma_bf16_imm(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate, uint32_t active = 1u) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe, pa;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "and.pred pe, pe, pa;\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(accumulate), "r"(active), "n"(DESC_HI), "n"(IDESC)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {

@@ -106,6 +106,16 @@ class FlatGradAllReduce:
                 self._launch(b)
         return hook
 
+    def set_overlap(self, overlap: bool):
+        """Switch between all-reduce launched from the gradient hooks (overlapped with backward) and one pass in finish()."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        self.overlap = overlap
+        if self.world > 1 and overlap:
+            for i, p in enumerate(self.params):
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+
     def _launch(self, b):
         s, e = self.buckets[b]
         self._work.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
