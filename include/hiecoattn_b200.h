@@ -159,6 +159,8 @@ HCA_API int hca_debug_gemm_timeline(void* buf, int nctas);
  * stamps of one non-leader epilogue thread: per 32-column chunk {buffer free, addend landed, operands in registers,
  * tile staged, group barrier passed}) */
 HCA_API int hca_debug_gemm_timeline_select(void* buf, int nctas, int launch_index);
+/* debug: CTA 0 of the following LSTM recurrence launches records clock64() stamps into buf (int64 [7 rounds][8]); NULL = off */
+HCA_API int hca_debug_lstm_timeline(void* buf);
 HCA_API int hca_gemm(const float* A, const float* B, const float* bias, float* D, int M, int N, int K,
                      int layout, int path, void* ws, size_t ws_bytes, void* stream);
 

@@ -45,6 +45,7 @@ SIGNATURES = {
     "hca_gemm_workspace": (_sz, [_i, _i, _i]),
     "hca_debug_gemm_timeline": (_i, [_p, _i]),
     "hca_debug_gemm_timeline_select": (_i, [_p, _i, _i]),
+    "hca_debug_lstm_timeline": (_i, [_p]),
     "hca_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
 }
 

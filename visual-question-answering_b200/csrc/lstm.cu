@@ -35,9 +35,9 @@ constexpr int L_BM = 128;                         // batch rows per CTA (UMMA M)
 constexpr int L_BK = 64;                          // bf16 per k-block row = 128 B = one SWIZZLE_128B span
 constexpr int L_UNITS = 16;                       // hidden units per CTA
 constexpr int L_MAX_STAGES = 16;                  // ring slots of the streamed operand (as many as fit: short row tiles -> many small slots)
-constexpr uint32_t L_RING_BYTES = 96 * 1024;
+constexpr uint32_t L_RING_BYTES = 80 * 1024;
 constexpr int L_THREADS = 64 + 256;               // warp 0 TMA, warp 1 MMA, warps 2..9 cell epilogue (2 groups x 4 TMEM quadrants)
-constexpr int L_MAX_SMEM = 227 * 1024 - 2048;
+constexpr int L_MAX_SMEM = 227 * 1024 - 18 * 1024;    // dynamic part: the kernel also holds 16 KB (fwd) of static exchange buffers
 
 constexpr int L_TMAX = 128;                       // longest sequence for which the per-step row trimming is tabulated
 struct LstmMaps {
@@ -52,6 +52,9 @@ struct LstmParams {
   int box_rows[3];        // rows of the three TMA boxes of the streamed operand
   int stages;             // ring slots in use
   uint32_t plane_bytes;   // bytes of one plane of one ring slot (rpt rows x 128 B); a slot = hi plane + lo plane
+  uint32_t lo_off;        // offset of the lo plane inside a slot
+  uint32_t stage_bytes;   // bytes of one ring slot
+  int mstack;             // rpt <= 64: the lo plane sits at tile rows 64.. of the SAME 128-row MMA tile (see the MMA warp)
   int tiles_n;            // H / 16
   int kbn;                // k-blocks of the recurrent contraction: fwd ceil(H / 64), bwd ceil(4H / 64)
   int K;                  // contraction length: fwd H, bwd 4H
@@ -66,7 +69,10 @@ struct LstmParams {
   __nv_bfloat16* dgp;     // gate-gradient planes [2][B][T][4H] ([unit][gate] column order) (bwd)
   int64_t dgp_ps;
   float* dbias;           // [4H] in [unit][gate] order, accumulated atomically (bwd)
+  long long* timeline;    // debug: clock64 stamps of CTA 0 ([round][8]: counter seen, loads issued, first operand landed, MMAs issued,
+                          // accumulator seen by the cell threads, cell math done, barrier passed, step published), else nullptr
 };
+long long* g_lstm_timeline = nullptr;
 
 __device__ __forceinline__ float sigmoid_fast(float x) {
   float e, r;
@@ -110,7 +116,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_constant__ LstmMaps maps, const LstmParams p) {
   constexpr int BN = BWD ? L_UNITS : 4 * L_UNITS;         // accumulator columns: dh of 16 units / 4 gates of 16 units
   constexpr uint32_t W_KB_PLANE = BN * L_BK * 2;          // one plane of one resident k-block
-  constexpr uint32_t TMEM_COLS = BWD ? 32 : 64;
+  constexpr uint32_t TMEM_COLS = BWD ? 32 : 128;             // [x.W_hi | x.W_lo] column blocks
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t bars[2 * L_MAX_STAGES + 2];
@@ -121,10 +127,13 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[L_MAX_STAGES + s]); };
   const uint32_t w_bar = smem_u32(&bars[2 * L_MAX_STAGES]), tmem_full = smem_u32(&bars[2 * L_MAX_STAGES + 1]);
-  const uint32_t stage_bytes = 2u * p.plane_bytes;
+  const uint32_t stage_bytes = p.stage_bytes;
+  // exchange buffer of the M-stacked mode: the partial sums of tile rows 64..127 (lo-plane rows) travel to the threads of rows 0..63
+  __shared__ __align__(16) float xch[2][64][BWD ? 8 : 32];
   const int mi = blockIdx.x / p.tiles_n, ni = blockIdx.x - mi * p.tiles_n;
   const int m0 = (p.tile0 + mi) * p.rpt;
   int* const counters = p.counters + (int64_t)(p.tile0 + mi) * p.T;
+  long long* const tl = blockIdx.x == 0 ? p.timeline : nullptr;
   const uint32_t w_base = smem_base;
   const uint32_t ring_base = smem_base + (uint32_t)p.kbn * 2u * W_KB_PLANE;
 
@@ -192,14 +201,16 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
           }
         }
         fence_proxy_async_global();                  // peers wrote through the generic proxy; TMA reads through the async proxy
+        if (tl && n < 7) tl[n * 8 + 0] = clock64();
         for (int kb = 0; kb < p.kbn; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1, 11);
           mbar_expect_tx(full_bar(s), 2u * plane_bytes);
           const uint32_t dst = ring_base + (uint32_t)s * stage_bytes;
           tma_load_4d(dst, &maps.A[bi], full_bar(s), kb * L_BK, slot, m0, 0);
-          tma_load_4d(dst + p.plane_bytes, &maps.A[bi], full_bar(s), kb * L_BK, slot, m0, 1);
+          tma_load_4d(dst + p.lo_off, &maps.A[bi], full_bar(s), kb * L_BK, slot, m0, 1);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
+        if (tl && n < 7) tl[n * 8 + 1] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -214,11 +225,13 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
     const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t a_ring = __shfl_sync(0xffffffffu, ((ring_base & 0x3FFFFu) >> 4) | (1u << 16), 0);
     const uint32_t w_res = __shfl_sync(0xffffffffu, ((w_base & 0x3FFFFu) >> 4) | (1u << 16), 0);
-    const uint32_t a_lo = __shfl_sync(0xffffffffu, p.plane_bytes >> 4, 0);
+    const uint32_t a_lo = __shfl_sync(0xffffffffu, p.lo_off >> 4, 0);
+    const uint32_t mstack = __shfl_sync(0xffffffffu, (uint32_t)p.mstack, 0);
     for (int n = 0; n < rounds; ++n) {
       for (int kb = 0; kb < p.kbn; ++kb) {
         mbar_wait(full_bar(s), ph, 13);
         tc_fence_after();
+        if (tl && lane == 0 && n < 7 && kb == 0) tl[n * 8 + 2] = clock64();
         const uint32_t au = __shfl_sync(0xffffffffu, a_ring + (uint32_t)s * (stage_bytes >> 4), 0);
         const uint32_t bu = __shfl_sync(0xffffffffu, w_res + (uint32_t)kb * (2u * W_KB_PLANE >> 4), 0);
         const uint32_t first = __shfl_sync(0xffffffffu, kb == 0 ? 0u : 1u, 0);
@@ -227,21 +240,18 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         for (int ks = 0; ks < L_BK / 16; ++ks) {
           const uint32_t active = ks < nks ? 1u : 0u;          // predicate, not a branch (keeps the descriptors in uniform registers)
           const uint32_t acc0 = ks != 0 ? 1u : first;
-          if constexpr (BWD) {
-            // the hi and lo planes of the resident slice lie back to back (16 + 16 rows): one N = 32 MMA gives hi.hi (columns
-            // 0..15) and hi.lo (columns 16..31), a second N = 16 MMA adds lo.hi -- 2 instructions per k-step instead of 3
-            umma_bf16_imm<desc_hi, idesc2>(d_tmem, au + ks * 2, bu + ks * 2, acc0, active);
-            umma_bf16_imm<desc_hi, idesc>(d_tmem, au + a_lo + ks * 2, bu + ks * 2, 1u, active);
-          } else {
-            // hi.hi + hi.lo + lo.hi
-            umma_bf16_imm<desc_hi, idesc>(d_tmem, au + ks * 2, bu + ks * 2, acc0, active);
-            umma_bf16_imm<desc_hi, idesc>(d_tmem, au + ks * 2, bu + (W_KB_PLANE >> 4) + ks * 2, 1u, active);
-            umma_bf16_imm<desc_hi, idesc>(d_tmem, au + a_lo + ks * 2, bu + ks * 2, 1u, active);
-          }
+          // The hi and lo planes of the resident slice lie back to back (BN + BN rows), so ONE MMA of width 2 BN gives x.W_hi
+          // (columns 0..BN-1) and x.W_lo (columns BN..2BN-1).  M-stacked mode (row tiles of <= 64 rows): the streamed lo plane
+          // occupies tile rows 64..127 of the same A tile, so that single MMA also covers the lo rows -- all four hi/lo cross
+          // terms in one instruction per k-step; the epilogue adds accumulator rows r and r + 64.  Otherwise a second MMA of
+          // width BN adds lo.hi from the separate lo tile.  (These MMAs are small; the issue rate is the limit, not the pipe.)
+          umma_bf16_imm<desc_hi, idesc2>(d_tmem, au + ks * 2, bu + ks * 2, acc0, active);
+          umma_bf16_imm<desc_hi, idesc>(d_tmem, au + a_lo + ks * 2, bu + ks * 2, 1u, active & (mstack ^ 1u));
         }
         umma_commit_elect(empty_bar(s));
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
+      if (tl && lane == 0 && n < 7) tl[n * 8 + 3] = clock64();
       umma_commit_elect(tmem_full);
     }
   } else {
@@ -262,6 +272,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
     const int g0 = ni * 4 * L_UNITS + eg * 32;      // first of its 32 gate columns ([unit][gate] order)
     const int64_t bt0 = (int64_t)b * p.T;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t xch_bar = 2u + (uint32_t)eg;
+    auto xch_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(xch_bar) : "memory"); };
     if constexpr (!BWD) {
       float cst[8];
 #pragma unroll
@@ -282,12 +294,33 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         if (t > 0) {
           mbar_wait(tmem_full, (uint32_t)((t - 1) & 1), 14);
           tc_fence_after();
-          uint32_t v[32];
+          if (tl && leader && t - 1 < 7) tl[(t - 1) * 8 + 4] = clock64();
+          uint32_t v[32], v2[32];                   // x.W_hi block and x.W_lo block of this thread's 32 gate columns
           __syncwarp();
           tmem_ld32(lane_addr + (uint32_t)(eg * 32), v);
+          tmem_ld32(lane_addr + (uint32_t)(4 * L_UNITS + eg * 32), v2);
           tc_fence_before();
+          float acc[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) z[j] += __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+          if (p.mstack) {                           // rows 64..127 of the tile are the lo-plane rows of rows 0..63: fold them in
+            if (q >= 2) {
+              float4* dst = reinterpret_cast<float4*>(&xch[eg][r - 64][0]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j ^ (r & 7)] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            }
+            xch_barrier();
+            if (q < 2) {
+              const float4* src = reinterpret_cast<const float4*>(&xch[eg][r][0]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 x4 = src[j ^ (r & 7)];
+                acc[4 * j] += x4.x; acc[4 * j + 1] += x4.y; acc[4 * j + 2] += x4.z; acc[4 * j + 3] += x4.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[j] += acc[j];
         }
         float h[8];
 #pragma unroll
@@ -306,11 +339,14 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
           *reinterpret_cast<uint4*>(dst) = hi;
           *reinterpret_cast<uint4*>(dst + p.hp_ps) = lo;
         }
+        if (tl && leader && t >= 1 && t - 1 < 7) tl[(t - 1) * 8 + 5] = clock64();
         fence_proxy_async_global();
         cell_barrier();
+        if (tl && leader && t >= 1 && t - 1 < 7) tl[(t - 1) * 8 + 6] = clock64();
         if (leader) {
           __threadfence();
           red_release_add(counters + t, 1);
+          if (tl && t >= 1 && t - 1 < 7) tl[(t - 1) * 8 + 7] = clock64();
         }
         if (row_ok) {                                // saved for backward + the module output
           float4* a4 = reinterpret_cast<float4*>(p.act + (bt0 + t) * H4 + g0);
@@ -365,14 +401,32 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         if (t < steps - 1) {                         // + W_hh^T dz_{t+1}
           mbar_wait(tmem_full, (uint32_t)((steps - 2 - t) & 1), 15);
           tc_fence_after();
-          uint32_t v[8], v2[8];                    // columns 0..15: hi.hi + lo.hi ; columns 16..31: hi.lo
+          if (tl && leader && steps - 2 - t < 7) tl[(steps - 2 - t) * 8 + 4] = clock64();
+          uint32_t v[8], v2[8];                    // columns 0..15: x.W_hi ; columns 16..31: x.W_lo
           __syncwarp();
           tmem_ld8(lane_addr + (uint32_t)(eg * 8), v);
           tmem_ld8(lane_addr + (uint32_t)(L_UNITS + eg * 8), v2);
           tc_fence_before();
+          float acc[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] = __uint_as_float(v[u]) + __uint_as_float(v2[u]);
+          if (p.mstack) {                           // fold the lo-plane rows (tile rows 64..127) into rows 0..63
+            if (q >= 2) {
+              float4* dst = reinterpret_cast<float4*>(&xch[eg][r - 64][0]);
+              dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+              dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+            xch_barrier();
+            if (q < 2) {
+              const float4* src = reinterpret_cast<const float4*>(&xch[eg][r][0]);
+              const float4 x0 = src[0], x1 = src[1];
+              acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
+              acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+            }
+          }
           if (valid) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) dh[u] += __uint_as_float(v[u]) + __uint_as_float(v2[u]);
+            for (int u = 0; u < 8; ++u) dh[u] += acc[u];
           }
         }
         float dz[32];
@@ -409,11 +463,15 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) dbacc[j] += dz[j];
+        const int rn = steps - 2 - t;
+        if (tl && leader && rn >= 0 && rn < 7) tl[rn * 8 + 5] = clock64();
         fence_proxy_async_global();
         cell_barrier();
+        if (tl && leader && rn >= 0 && rn < 7) tl[rn * 8 + 6] = clock64();
         if (leader) {
           __threadfence();
           red_release_add(counters + t, 1);
+          if (tl && rn >= 0 && rn < 7) tl[rn * 8 + 7] = clock64();
         }
       }
       // bias gradient: column sums over this warp's 32 rows, then one atomic per column
@@ -553,6 +611,7 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
                const __nv_bfloat16* w_planes, int64_t w_ps, int w_rows, int w_cols, cudaStream_t s) {
   constexpr int BN = BWD ? L_UNITS : 4 * L_UNITS;
   LstmParams p = base;
+  p.timeline = g_lstm_timeline;
   p.tiles_n = base.H / L_UNITS;
   p.K = BWD ? 4 * base.H : base.H;
   p.kbn = (p.K + L_BK - 1) / L_BK;
@@ -577,11 +636,15 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
   }
   // ring slots of the streamed operand: hi + lo plane of rpt rows x 64 k each (whole 8-row swizzle atoms: rpt % 8 == 0)
   p.plane_bytes = (uint32_t)rt.rpt * L_BK * 2;
-  // (the MMA always reads 128 rows = 16 KB from a plane's base: rows beyond rpt are other slots' data and only feed unused
-  // accumulator rows, but the last slot's read must stay inside the allocation, hence the tail padding)
-  const uint32_t tail_pad = 16 * 1024 - p.plane_bytes;
-  p.stages = std::max(2, std::min(L_MAX_STAGES, (int)((L_RING_BYTES - tail_pad) / (2 * p.plane_bytes))));
-  const size_t smem = (size_t)p.kbn * 2 * BN * L_BK * 2 + (size_t)p.stages * 2 * p.plane_bytes + tail_pad + 1024;
+  p.mstack = rt.rpt <= 64 ? 1 : 0;
+  p.lo_off = p.mstack ? 64u * L_BK * 2 : p.plane_bytes;      // M-stacked: the lo plane starts at tile row 64
+  p.stage_bytes = p.lo_off + p.plane_bytes;
+  // (the MMA always reads 128 rows = 16 KB from a tile base: rows beyond the loaded ones are other slots' data and only feed
+  // unused accumulator rows, but the last slot's reads must stay inside the allocation, hence the tail padding)
+  const uint32_t last_read_end = (p.mstack ? 0u : p.lo_off) + 16u * 1024u;
+  const uint32_t tail_pad = last_read_end > p.stage_bytes ? last_read_end - p.stage_bytes : 0u;
+  p.stages = std::max(2, std::min(L_MAX_STAGES, (int)((L_RING_BYTES - tail_pad) / p.stage_bytes)));
+  const size_t smem = (size_t)p.kbn * 2 * BN * L_BK * 2 + (size_t)p.stages * p.stage_bytes + tail_pad + 1024;
   HCA_CHECK_ARG(smem <= (size_t)L_MAX_SMEM, "lstm: hidden size %d needs %zu bytes of shared memory", base.H, smem);
   static bool attr_set[2] = {false, false};
   if (!attr_set[BWD ? 1 : 0]) {
@@ -601,6 +664,11 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
 
 }  // namespace
 }  // namespace hca
+
+extern "C" int hca_debug_lstm_timeline(void* buf) {
+  hca::g_lstm_timeline = (long long*)buf;
+  return 0;
+}
 
 extern "C" int hca_lstm_supported(int B, int T, int E, int H) { return hca::shape_ok(B, T, E, H) && hca::tc_available() ? 1 : 0; }
 
