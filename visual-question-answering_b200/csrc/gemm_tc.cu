@@ -168,14 +168,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   if (tl && threadIdx.x == 0) tl[1] = clock64();
 
   if (warp == 0) {
-    // ===================================================================== TMA producer (one lane)
-    if (lane == 0 && !(p.dbg & 1)) {
+    // ===================================================================== TMA producer (one elected lane, uniform datapath)
+    if (elect_one_sync() && !(p.dbg & 1)) {
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = decode(t);
         for (int it = 0; it < tc.num_kb; ++it) {
-          mbar_wait(empty_bar(s), ph ^ 1, 1);
+          mbar_spin(empty_bar(s), ph ^ 1);
           mbar_expect_tx(full_bar(s), stage_bytes);
           const int kb = tc.kb_begin + it;
           const bool second = kb >= p.kb1;                    // chained second operand pair
@@ -204,65 +204,61 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (whole warp converged, one lane issues)
+    // ===================================================================== MMA issuer (one elected lane, uniform datapath)
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6), a=bf16 [7,10), b=bf16 [10,13),
     // a_major bit 15, b_major bit 16, N>>3 [17,23), M>>4 [24,29)
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     // smem descriptor halves (cute::UMMA::SmemDescriptor): hi = SBO(1024 B) | version 1 | SWIZZLE_128B, constant;
     // lo = (addr >> 4) | (LBO >> 4) << 16.  K-major: LBO unused (16 B), K slice = +32 B.  MN-major: LBO = one [BK k][64 mn]
-    // box between 64-wide MN chunks, K slice of 16 rows = +2048 B.  Everything below is warp-uniform integer arithmetic,
-    // so ptxas keeps it on the uniform datapath (no per-MMA ELECT / R2UR.BROADCAST sequence).
+    // box between 64-wide MN chunks, K slice of 16 rows = +2048 B.
     constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     constexpr uint32_t a_lbo = (A_MN ? (MN_CHUNK_BYTES >> 4) : 1u) << 16, b_lbo = (B_MN ? (MN_CHUNK_BYTES >> 4) : 1u) << 16;
     constexpr uint32_t a_kstep = A_MN ? (2048u >> 4) : (32u >> 4), b_kstep = B_MN ? (2048u >> 4) : (32u >> 4);
-    int s = 0;
-    uint32_t ph = 0;
-    uint32_t a0 = ((smem_base & 0x3FFFFu) >> 4) | a_lbo;
-    uint32_t b0 = (((smem_base + P * A_TILE_BYTES) & 0x3FFFFu) >> 4) | b_lbo;
-    int tile_it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
-      const TileCoord tc = decode(t);
-      const int acc = tile_it & 1;
-      mbar_wait(tmem_empty_bar(acc), ((tile_it >> 1) & 1) ^ 1, 5);      // the epilogue has drained this accumulator buffer
-      tc_fence_after();
-      const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(acc * BN), 0);   // warp-uniform for ptxas
-      for (int it = 0; it < tc.num_kb; ++it) {
-        if (!(p.dbg & 1)) mbar_wait(full_bar(s), ph, 2);
+    // The whole loop runs in ONE elected thread with inline waits: inside such a region every value is trivially warp-uniform,
+    // so ptxas builds the descriptors with uniform-datapath adds and issues the UTCHMMAs back to back.  (Per-instruction
+    // elect / predicate forms cost ELECT + VOTEU + 4-5 R2UR per MMA, ~75 cycles each: that, not L2 bandwidth, bound the mainloop.)
+    if (elect_one_sync()) {
+      const uint32_t tm = *reinterpret_cast<volatile uint32_t*>(&tmem_ptr_smem);
+      const uint32_t a_base = ((smem_base & 0x3FFFFu) >> 4) | a_lbo;
+      const uint32_t b_base = (((smem_base + P * A_TILE_BYTES) & 0x3FFFFu) >> 4) | b_lbo;
+      int s = 0;
+      uint32_t ph = 0;
+      int tile_it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
+        const TileCoord tc = decode(t);
+        const int acc = tile_it & 1;
+        mbar_spin(tmem_empty_bar(acc), ((tile_it >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator buffer
         tc_fence_after();
-        if (tl && lane == 0 && tile_it == 0 && it == 0) tl[2] = clock64();
-        // shuffle-broadcast: tells ptxas these are warp-uniform, so the descriptor variants below are
-        // uniform-register adds of compile-time constants
-        const uint32_t au = __shfl_sync(0xffffffffu, a0, 0), bu = __shfl_sync(0xffffffffu, b0, 0);
-        const uint32_t first = __shfl_sync(0xffffffffu, it == 0 ? 0u : 1u, 0);
-        // K slices of this block that hold data (the tail of K is zero-filled by TMA: skip those MMAs)
-        const int kb = tc.kb_begin + it;
-        const int kleft = kb >= p.kb1 ? p.K2 - (kb - p.kb1) * BK : p.K - kb * BK;
-        const int nks = __shfl_sync(0xffffffffu, min(BK / UMMA_K, (kleft + UMMA_K - 1) / UMMA_K), 0);
+        const uint32_t d_tmem = tm + (uint32_t)(acc * BN);
+        for (int it = 0; it < tc.num_kb; ++it) {
+          if (!(p.dbg & 1)) mbar_spin(full_bar(s), ph);
+          tc_fence_after();
+          if (tl && tile_it == 0 && it == 0) tl[2] = clock64();
+          const uint32_t au = a_base + (uint32_t)s * (stage_bytes >> 4), bu = b_base + (uint32_t)s * (stage_bytes >> 4);
+          // K slices of this block that hold data (the tail of K is zero-filled by TMA: skip those MMAs)
+          const int kb = tc.kb_begin + it;
+          const int kleft = kb >= p.kb1 ? p.K2 - (kb - p.kb1) * BK : p.K - kb * BK;
+          const int nks = min(BK / UMMA_K, (kleft + UMMA_K - 1) / UMMA_K);
 #pragma unroll
-        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-          const uint32_t active = ks < nks ? 1u : 0u;          // predicate, not a branch (see umma_bf16_elect32)
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            if (ks < nks) {
 #pragma unroll
-          for (int i = 0; i < P; ++i) {
+              for (int i = 0; i < P; ++i) {
 #pragma unroll
-            for (int j = 0; j < P - i; ++j) {
-              umma_bf16_elect32(d_tmem, au + i * (A_TILE_BYTES >> 4) + ks * a_kstep, desc_hi,
-                                bu + j * (B_TILE_BYTES >> 4) + ks * b_kstep, desc_hi, idesc, (ks | i | j) != 0 ? 1u : first, active);
+                for (int j = 0; j < P - i; ++j) {
+                  umma_bf16_one<desc_hi, idesc>(d_tmem, au + i * (A_TILE_BYTES >> 4) + ks * a_kstep, bu + j * (B_TILE_BYTES >> 4) + ks * b_kstep,
+                                                (ks | i | j) != 0 ? 1u : (it == 0 ? 0u : 1u));
+                }
+              }
             }
           }
+          umma_commit(empty_bar(s));            // frees the smem stage once the MMAs above have read it
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit_elect(empty_bar(s));      // frees the smem stage once the MMAs above have read it
-        a0 += stage_bytes >> 4;
-        b0 += stage_bytes >> 4;
-        if (++s == p.stages) {
-          s = 0;
-          ph ^= 1;
-          a0 -= p.stages * (stage_bytes >> 4);
-          b0 -= p.stages * (stage_bytes >> 4);
-        }
+        umma_commit(tmem_full_bar(acc));        // accumulator complete -> epilogue
+        if (tl && tile_it == 0) tl[3] = clock64();
       }
-      umma_commit_elect(tmem_full_bar(acc));  // accumulator complete -> epilogue
-      if (tl && lane == 0 && tile_it == 0) tl[3] = clock64();
     }
   } else if (((warp - 2) >> 2) < p.n_eg) {
     // ===================================================================== epilogue: TMEM -> registers -> (smem -> TMA) global

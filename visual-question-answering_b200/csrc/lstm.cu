@@ -35,13 +35,13 @@ constexpr int L_BM = 128;                         // batch rows per CTA (UMMA M)
 constexpr int L_BK = 64;                          // bf16 per k-block row = 128 B = one SWIZZLE_128B span
 constexpr int L_UNITS = 16;                       // hidden units per CTA
 constexpr int L_MAX_STAGES = 16;                  // ring slots of the streamed operand (as many as fit: short row tiles -> many small slots)
-constexpr uint32_t L_RING_BYTES = 80 * 1024;
+constexpr uint32_t L_RING_BYTES = 96 * 1024;
 constexpr int L_THREADS = 64 + 256;               // warp 0 TMA, warp 1 MMA, warps 2..9 cell epilogue (2 groups x 4 TMEM quadrants)
-constexpr int L_MAX_SMEM = 227 * 1024 - 18 * 1024;    // dynamic part: the kernel also holds 16 KB (fwd) of static exchange buffers
+constexpr int L_MAX_SMEM = 227 * 1024 - 2048;
 
 constexpr int L_TMAX = 128;                       // longest sequence for which the per-step row trimming is tabulated
 struct LstmMaps {
-  CUtensorMap A[3];   // streamed operand planes, 4-D (cols, t, b, plane), boxes (64, 1, box_rows[i], 1): full, half and quarter row tile
+  CUtensorMap A[3];   // streamed operand planes, 5-D (64 cols, b, k-block, t, plane), boxes (64, box_rows[i], nkb, 1, 1): full, half, quarter tile
   CUtensorMap W;      // resident operand planes, 4-D (cols, rows, plane, 1), box (64, BN, 1, 1)
 };
 
@@ -52,9 +52,11 @@ struct LstmParams {
   int box_rows[3];        // rows of the three TMA boxes of the streamed operand
   int stages;             // ring slots in use
   uint32_t plane_bytes;   // bytes of one plane of one ring slot (rpt rows x 128 B); a slot = hi plane + lo plane
-  uint32_t lo_off;        // offset of the lo plane inside a slot
-  uint32_t stage_bytes;   // bytes of one ring slot
-  int mstack;             // rpt <= 64: the lo plane sits at tile rows 64.. of the SAME 128-row MMA tile (see the MMA warp)
+  uint32_t lo_off;        // offset of the lo-plane tiles inside a slot (= nkb * plane_bytes)
+  uint32_t stage_bytes;   // bytes of one ring slot: nkb k-blocks x (hi tile + lo tile)
+  int nkb;                // k-blocks per ring slot: ONE TMA box per plane brings nkb k-blocks (the issue rate of small boxes,
+                          // ~450 cycles per slot iteration, bounded the recurrence when every k-block was its own slot)
+  int nslots;             // slots per round = ceil(kbn / nkb)
   int tiles_n;            // H / 16
   int kbn;                // k-blocks of the recurrent contraction: fwd ceil(H / 64), bwd ceil(4H / 64)
   int K;                  // contraction length: fwd H, bwd 4H
@@ -86,6 +88,30 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "r"(taddr)
                : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(e));
+  return e;
+}
+// tcgen05.mma predicated by an integer flag (elected lane && k-slice holds data), constant descriptor halves as immediates
+template <uint32_t DESC_HI, uint32_t IDESC>
+__device__ __forceinline__ void umma_bf16_imm_pred(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 pe, %4, 0;\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(accumulate), "r"(issue), "n"(DESC_HI), "n"(IDESC)
+      : "memory");
 }
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -128,8 +154,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
   auto empty_bar = [&](int s) { return smem_u32(&bars[L_MAX_STAGES + s]); };
   const uint32_t w_bar = smem_u32(&bars[2 * L_MAX_STAGES]), tmem_full = smem_u32(&bars[2 * L_MAX_STAGES + 1]);
   const uint32_t stage_bytes = p.stage_bytes;
-  // exchange buffer of the M-stacked mode: the partial sums of tile rows 64..127 (lo-plane rows) travel to the threads of rows 0..63
-  __shared__ __align__(16) float xch[2][64][BWD ? 8 : 32];
+
   const int mi = blockIdx.x / p.tiles_n, ni = blockIdx.x - mi * p.tiles_n;
   const int m0 = (p.tile0 + mi) * p.rpt;
   int* const counters = p.counters + (int64_t)(p.tile0 + mi) * p.T;
@@ -170,8 +195,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
   const int rounds = steps > 0 ? steps - 1 : 0;             // recurrent products: every step but the first one in time order
 
   if (warp == 0) {
-    // ============================================================ TMA producer
-    if (lane == 0) {
+    // ============================================================ TMA producer (one elected lane, inline waits: uniform datapath)
+    if (elect_one_sync()) {
       mbar_expect_tx(w_bar, (uint32_t)p.kbn * 2u * W_KB_PLANE);
       for (int kb = 0; kb < p.kbn; ++kb)
         for (int pl = 0; pl < 2; ++pl)
@@ -188,7 +213,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         // accumulator rows are never used), so the smallest of the three boxes that covers the running rows is loaded
         const int nrun = (p.T <= L_TMAX) ? s_nact[t_cur] : p.rpt;
         const int bi = nrun <= p.box_rows[2] ? 2 : (nrun <= p.box_rows[1] ? 1 : 0);
-        const uint32_t plane_bytes = (uint32_t)p.box_rows[bi] * L_BK * 2;
+        const uint32_t plane_bytes = (uint32_t)p.box_rows[bi] * L_BK * 2;      // one k-block of one plane in the chosen box
         const int* cnt = counters + dep;
         if (ld_acquire(cnt) < p.tiles_n) {           // bounded spin: a protocol bug must trap, never hang the device
           const long long t0 = clock64();
@@ -202,12 +227,12 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         }
         fence_proxy_async_global();                  // peers wrote through the generic proxy; TMA reads through the async proxy
         if (tl && n < 7) tl[n * 8 + 0] = clock64();
-        for (int kb = 0; kb < p.kbn; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1, 11);
-          mbar_expect_tx(full_bar(s), 2u * plane_bytes);
+        for (int sl = 0; sl < p.nslots; ++sl) {
+          mbar_spin(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), 2u * (uint32_t)p.nkb * plane_bytes);      // (k-blocks beyond K arrive as fill: full box bytes)
           const uint32_t dst = ring_base + (uint32_t)s * stage_bytes;
-          tma_load_4d(dst, &maps.A[bi], full_bar(s), kb * L_BK, slot, m0, 0);
-          tma_load_4d(dst + p.lo_off, &maps.A[bi], full_bar(s), kb * L_BK, slot, m0, 1);
+          tma_load_5d(dst, &maps.A[bi], full_bar(s), 0, m0, sl * p.nkb, slot, 0);
+          tma_load_5d(dst + p.lo_off, &maps.A[bi], full_bar(s), 0, m0, sl * p.nkb, slot, 1);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (tl && n < 7) tl[n * 8 + 1] = clock64();
@@ -218,41 +243,50 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(L_BM >> 4) << 24);
     constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(L_BM >> 4) << 24);
     constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    mbar_wait(w_bar, 0, 12);
-    tc_fence_after();
-    int s = 0;
-    uint32_t ph = 0;
-    const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t a_ring = __shfl_sync(0xffffffffu, ((ring_base & 0x3FFFFu) >> 4) | (1u << 16), 0);
-    const uint32_t w_res = __shfl_sync(0xffffffffu, ((w_base & 0x3FFFFu) >> 4) | (1u << 16), 0);
-    const uint32_t a_lo = __shfl_sync(0xffffffffu, p.lo_off >> 4, 0);
-    const uint32_t mstack = __shfl_sync(0xffffffffu, (uint32_t)p.mstack, 0);
-    for (int n = 0; n < rounds; ++n) {
-      for (int kb = 0; kb < p.kbn; ++kb) {
-        mbar_wait(full_bar(s), ph, 13);
-        tc_fence_after();
-        if (tl && lane == 0 && n < 7 && kb == 0) tl[n * 8 + 2] = clock64();
-        const uint32_t au = __shfl_sync(0xffffffffu, a_ring + (uint32_t)s * (stage_bytes >> 4), 0);
-        const uint32_t bu = __shfl_sync(0xffffffffu, w_res + (uint32_t)kb * (2u * W_KB_PLANE >> 4), 0);
-        const uint32_t first = __shfl_sync(0xffffffffu, kb == 0 ? 0u : 1u, 0);
-        const int nks = __shfl_sync(0xffffffffu, min(L_BK / 16, (p.K - kb * L_BK + 15) / 16), 0);
+    // The whole loop runs in ONE elected thread with inline waits: inside such a region every value is trivially warp-uniform, so
+    // ptxas builds the descriptors with uniform-datapath adds and the UTCHMMAs issue back to back (the per-instruction elect /
+    // predicate forms cost ~75 cycles per MMA, which bounded the recurrence: its MMAs are small and many).
+    if (elect_one_sync()) {
+      mbar_spin(w_bar, 0);
+      tc_fence_after();
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t d_tmem = *reinterpret_cast<volatile uint32_t*>(&tmem_ptr_smem);
+      const uint32_t a_ring = ((ring_base & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t w_res = ((w_base & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t a_lo = p.lo_off >> 4;
+      for (int n = 0; n < rounds; ++n) {
+        // the tiles of a slot are packed with the pitch of the box that was loaded (the producer picks the same box: both read s_nact)
+        const int t_cur = BWD ? steps - 2 - n : n + 1;
+        const int nrun = (p.T <= L_TMAX) ? s_nact[t_cur] : p.rpt;
+        const int bi = nrun <= p.box_rows[2] ? 2 : (nrun <= p.box_rows[1] ? 1 : 0);
+        const uint32_t tile16 = ((uint32_t)p.box_rows[bi] * L_BK * 2) >> 4;
+        for (int sl = 0; sl < p.nslots; ++sl) {
+          mbar_spin(full_bar(s), ph);
+          tc_fence_after();
+          if (tl && n < 7 && sl == 0) tl[n * 8 + 2] = clock64();
+          const uint32_t a_slot = a_ring + (uint32_t)s * (stage_bytes >> 4);
+          for (int j = 0; j < p.nkb; ++j) {
+            const int kb = sl * p.nkb + j;
+            const uint32_t au = a_slot + (uint32_t)j * tile16;
+            const uint32_t bu = w_res + (uint32_t)kb * (2u * W_KB_PLANE >> 4);
+            const int nks = max(0, min(L_BK / 16, (p.K - kb * L_BK + 15) / 16));
 #pragma unroll
-        for (int ks = 0; ks < L_BK / 16; ++ks) {
-          const uint32_t active = ks < nks ? 1u : 0u;          // predicate, not a branch (keeps the descriptors in uniform registers)
-          const uint32_t acc0 = ks != 0 ? 1u : first;
-          // The hi and lo planes of the resident slice lie back to back (BN + BN rows), so ONE MMA of width 2 BN gives x.W_hi
-          // (columns 0..BN-1) and x.W_lo (columns BN..2BN-1).  M-stacked mode (row tiles of <= 64 rows): the streamed lo plane
-          // occupies tile rows 64..127 of the same A tile, so that single MMA also covers the lo rows -- all four hi/lo cross
-          // terms in one instruction per k-step; the epilogue adds accumulator rows r and r + 64.  Otherwise a second MMA of
-          // width BN adds lo.hi from the separate lo tile.  (These MMAs are small; the issue rate is the limit, not the pipe.)
-          umma_bf16_imm<desc_hi, idesc2>(d_tmem, au + ks * 2, bu + ks * 2, acc0, active);
-          umma_bf16_imm<desc_hi, idesc>(d_tmem, au + a_lo + ks * 2, bu + ks * 2, 1u, active & (mstack ^ 1u));
+            for (int ks = 0; ks < L_BK / 16; ++ks) {
+              if (ks < nks) {
+                // The hi and lo planes of the resident slice lie back to back (BN + BN rows), so ONE MMA of width 2 BN gives
+                // x_hi.W_hi (columns 0..BN-1) and x_hi.W_lo (columns BN..2BN-1); a second MMA of width BN adds x_lo.W_hi.
+                umma_bf16_one<desc_hi, idesc2>(d_tmem, au + ks * 2, bu + ks * 2, (kb | ks) != 0 ? 1u : 0u);
+                umma_bf16_one<desc_hi, idesc>(d_tmem, au + a_lo + ks * 2, bu + ks * 2, 1u);
+              }
+            }
+          }
+          umma_commit(empty_bar(s));
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit_elect(empty_bar(s));
-        if (++s == p.stages) { s = 0; ph ^= 1; }
+        if (tl && n < 7) tl[n * 8 + 3] = clock64();
+        umma_commit(tmem_full);
       }
-      if (tl && lane == 0 && n < 7) tl[n * 8 + 3] = clock64();
-      umma_commit_elect(tmem_full);
     }
   } else {
     // ============================================================ cell epilogue: thread = (batch row, 8 hidden units)
@@ -272,8 +306,6 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
     const int g0 = ni * 4 * L_UNITS + eg * 32;      // first of its 32 gate columns ([unit][gate] order)
     const int64_t bt0 = (int64_t)b * p.T;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t xch_bar = 2u + (uint32_t)eg;
-    auto xch_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(xch_bar) : "memory"); };
     if constexpr (!BWD) {
       float cst[8];
 #pragma unroll
@@ -303,22 +335,6 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
           float acc[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
-          if (p.mstack) {                           // rows 64..127 of the tile are the lo-plane rows of rows 0..63: fold them in
-            if (q >= 2) {
-              float4* dst = reinterpret_cast<float4*>(&xch[eg][r - 64][0]);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j ^ (r & 7)] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-            }
-            xch_barrier();
-            if (q < 2) {
-              const float4* src = reinterpret_cast<const float4*>(&xch[eg][r][0]);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 x4 = src[j ^ (r & 7)];
-                acc[4 * j] += x4.x; acc[4 * j + 1] += x4.y; acc[4 * j + 2] += x4.z; acc[4 * j + 3] += x4.w;
-              }
-            }
-          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) z[j] += acc[j];
         }
@@ -344,8 +360,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         cell_barrier();
         if (tl && leader && t >= 1 && t - 1 < 7) tl[(t - 1) * 8 + 6] = clock64();
         if (leader) {
-          __threadfence();
-          red_release_add(counters + t, 1);
+          red_release_add(counters + t, 1);      // release at gpu scope: covers the CTA's writes ordered before it by the barrier
           if (tl && t >= 1 && t - 1 < 7) tl[(t - 1) * 8 + 7] = clock64();
         }
         if (row_ok) {                                // saved for backward + the module output
@@ -410,20 +425,6 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
           float acc[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) acc[u] = __uint_as_float(v[u]) + __uint_as_float(v2[u]);
-          if (p.mstack) {                           // fold the lo-plane rows (tile rows 64..127) into rows 0..63
-            if (q >= 2) {
-              float4* dst = reinterpret_cast<float4*>(&xch[eg][r - 64][0]);
-              dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-              dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            }
-            xch_barrier();
-            if (q < 2) {
-              const float4* src = reinterpret_cast<const float4*>(&xch[eg][r][0]);
-              const float4 x0 = src[0], x1 = src[1];
-              acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
-              acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
-            }
-          }
           if (valid) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) dh[u] += acc[u];
@@ -469,8 +470,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         cell_barrier();
         if (tl && leader && rn >= 0 && rn < 7) tl[rn * 8 + 6] = clock64();
         if (leader) {
-          __threadfence();
-          red_release_add(counters + t, 1);
+          red_release_add(counters + t, 1);      // release at gpu scope: covers the CTA's writes ordered before it by the barrier
           if (tl && rn >= 0 && rn < 7) tl[rn * 8 + 7] = clock64();
         }
       }
@@ -621,12 +621,27 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
   p.box_rows[0] = rt.rpt;
   p.box_rows[1] = std::min(rt.rpt, (rt.rpt / 2 + 7) / 8 * 8);
   p.box_rows[2] = std::min(rt.rpt, (rt.rpt / 4 + 7) / 8 * 8);
+  // ring slots of the streamed operand: nkb k-blocks x (hi tile + lo tile) of rpt rows x 64 k (whole 8-row swizzle atoms: rpt % 8 == 0);
+  // as many k-blocks per slot as still leave two slots (one TMA box per plane and slot: few large boxes, not many small ones)
+  p.plane_bytes = (uint32_t)rt.rpt * L_BK * 2;
+  // (the MMA always reads 128 rows = 16 KB from a tile base: rows beyond the loaded ones are other tiles' data and only feed
+  // unused accumulator rows, but the last tile's read must stay inside the allocation, hence the tail padding)
+  const uint32_t tail_pad = 16u * 1024u - p.plane_bytes;
+  p.nkb = std::max(1, std::min(p.kbn, (int)((L_RING_BYTES - tail_pad) / (4 * p.plane_bytes))));
+  p.nslots = (p.kbn + p.nkb - 1) / p.nkb;
+  p.lo_off = (uint32_t)p.nkb * p.plane_bytes;
+  p.stage_bytes = 2u * p.lo_off;
+  p.stages = std::max(2, std::min(L_MAX_STAGES, (int)((L_RING_BYTES - tail_pad) / p.stage_bytes)));
+  const size_t smem = (size_t)p.kbn * 2 * BN * L_BK * 2 + (size_t)p.stages * p.stage_bytes + tail_pad + 1024;
   LstmMaps maps;
-  for (int i = 0; i < 3; ++i) {  // streamed operand [2][B][T][cols]: dims (cols, T, B, 2)
-    const uint64_t dims[4] = {(uint64_t)stream_cols, (uint64_t)base.T, (uint64_t)base.B, 2};
-    const uint64_t str[3] = {(uint64_t)stream_cols * 2, (uint64_t)base.T * stream_cols * 2, (uint64_t)stream_ps * 2};
-    const uint32_t box[4] = {L_BK, 1, (uint32_t)p.box_rows[i], 1};
-    HCA_TRY(tc_make_tmap(&maps.A[i], true, 4, stream_planes, dims, str, box, 3));
+  for (int i = 0; i < 3; ++i) {
+    // streamed operand [2][B][T][cols] seen as (64 cols of a k-block, b, k-block, t, plane).  Dimension 0 is always a full 64:
+    // when cols is not a multiple of 64 the last k-block of a row runs into the following row -- finite data that only feeds
+    // k-slices the MMA warp predicates off (K is a multiple of 16); the buffers carry slack behind their last row.
+    const uint64_t dims[5] = {(uint64_t)L_BK, (uint64_t)base.B, (uint64_t)((stream_cols + L_BK - 1) / L_BK), (uint64_t)base.T, 2};
+    const uint64_t str[4] = {(uint64_t)base.T * stream_cols * 2, (uint64_t)L_BK * 2, (uint64_t)stream_cols * 2, (uint64_t)stream_ps * 2};
+    const uint32_t box[5] = {L_BK, (uint32_t)p.box_rows[i], (uint32_t)p.nkb, 1, 1};
+    HCA_TRY(tc_make_tmap(&maps.A[i], true, 5, stream_planes, dims, str, box, 3));
   }
   {  // resident operand [2][rows][cols]: dims (cols, rows, 2, 1)
     const uint64_t dims[4] = {(uint64_t)w_cols, (uint64_t)w_rows, 2, 1};
@@ -634,17 +649,6 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
     const uint32_t box[4] = {L_BK, BN, 1, 1};
     HCA_TRY(tc_make_tmap(&maps.W, true, 4, w_planes, dims, str, box, 3));
   }
-  // ring slots of the streamed operand: hi + lo plane of rpt rows x 64 k each (whole 8-row swizzle atoms: rpt % 8 == 0)
-  p.plane_bytes = (uint32_t)rt.rpt * L_BK * 2;
-  p.mstack = rt.rpt <= 64 ? 1 : 0;
-  p.lo_off = p.mstack ? 64u * L_BK * 2 : p.plane_bytes;      // M-stacked: the lo plane starts at tile row 64
-  p.stage_bytes = p.lo_off + p.plane_bytes;
-  // (the MMA always reads 128 rows = 16 KB from a tile base: rows beyond the loaded ones are other slots' data and only feed
-  // unused accumulator rows, but the last slot's reads must stay inside the allocation, hence the tail padding)
-  const uint32_t last_read_end = (p.mstack ? 0u : p.lo_off) + 16u * 1024u;
-  const uint32_t tail_pad = last_read_end > p.stage_bytes ? last_read_end - p.stage_bytes : 0u;
-  p.stages = std::max(2, std::min(L_MAX_STAGES, (int)((L_RING_BYTES - tail_pad) / p.stage_bytes)));
-  const size_t smem = (size_t)p.kbn * 2 * BN * L_BK * 2 + (size_t)p.stages * p.stage_bytes + tail_pad + 1024;
   HCA_CHECK_ARG(smem <= (size_t)L_MAX_SMEM, "lstm: hidden size %d needs %zu bytes of shared memory", base.H, smem);
   static bool attr_set[2] = {false, false};
   if (!attr_set[BWD ? 1 : 0]) {

@@ -41,6 +41,21 @@ static __device__ __noinline__ void mbar_wait(uint32_t bar, uint32_t parity, int
     }
   }
 }
+// Inline bounded wait for the single-thread (elected) producer / MMA loops: no call, no printf, so that ptxas keeps the whole
+// loop on the uniform datapath (descriptors and TMA coordinates in uniform registers, UTCHMMA / UTMALDG issued back to back).
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+// true in exactly one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\t@P1 mov.s32 %0, 1;\n\t}" : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
@@ -143,6 +158,20 @@ __device__ __forceinline__ void umma_bf16_imm(uint32_t tmem_d, uint32_t a_lo, ui
       "setp.ne.b32 p, %3, 0;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, p;\n\t}" ::"r"(tmem_d),
       "r"(a_lo), "r"(b_lo), "r"(accumulate), "r"(active), "n"(DESC_HI), "n"(IDESC)
+      : "memory");
+}
+// Unpredicated MMA for code that already runs in ONE elected thread (if (elect_one_sync()) { ... }): inside such a region every
+// value is trivially warp-uniform, ptxas builds the descriptors with UIADD3 in uniform registers and the UTCHMMAs issue back to
+// back -- measured ~75 cycles per MMA with the per-instruction elect / R2UR forms above, which bound every mainloop.
+template <uint32_t DESC_HI, uint32_t IDESC>
+__device__ __forceinline__ void umma_bf16_one(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %4};\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(accumulate), "n"(DESC_HI), "n"(IDESC)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
