@@ -352,14 +352,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       int tli = 8;                            // debug timeline: stamps of this thread's first chunks (tl[8..63])
       const bool tlt = tl && eg == 0 && et == 32;
 #define HCA_TL_STAMP() do { if (tlt && tli < 64) tl[tli++] = clock64(); } while (0)
+      int staged_n0 = -1;                     // n0 of the per-column vectors currently in shared memory
+      // this group's column sums -> global, one atomic per column (only the columns of its own chunks), then cleared
+      auto flush_colred = [&](int n0) {
+        for (int j = et; j < BN; j += 128) {
+          if (((j >> 5) % neg) == eg && n0 + j < p.N) atomicAdd(p.red_col + n0 + j, colred_s[j]);
+        }
+      };
       uint32_t gc = 0;                        // chunks this group has processed (staging double-buffer index)
       uint32_t aux_n = 0;                     // addend tiles this group has consumed (mbarrier phase)
-      auto nch = [&](int t) { return min(CHUNKS, (p.N - decode(t).n0 + 31) / 32); };
-      // (at, ac): the next (tile, chunk) whose addend tile has not been requested yet; one load in flight per group
+      // (at, ac): the next (tile, chunk) whose addend tile has not been requested yet; one load in flight per group.
+      // atc caches the decoded coordinates of tile `at` (the decode costs several integer divisions)
       int at = blockIdx.x, ac = eg;
-      auto settle = [&]() { while (at < p.total_tiles && ac >= nch(at)) { at += gridDim.x; ac = eg; } };
+      TileCoord atc = decode(at < p.total_tiles ? at : 0);
+      auto settle = [&]() {
+        while (at < p.total_tiles && ac >= min(CHUNKS, (p.N - atc.n0 + 31) / 32)) {
+          at += gridDim.x;
+          ac = eg;
+          if (at < p.total_tiles) atc = decode(at);
+        }
+      };
       auto issue_aux = [&]() {
-        const TileCoord c = decode(at);
+        const TileCoord& c = atc;
         const int za = (c.z / p.aux_zd) % p.aux_nb;
         mbar_expect_tx(aux_bar(eg), CHUNK_BYTES);
         if (p.aux_kind == 1) {
@@ -378,20 +392,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int acc = tile_it & 1;
         const int row = tc.m0 + r;
         const bool row_ok = row < p.M;
-        epi_barrier();                        // the previous tile's readers of the per-column vectors are done
-        {                                     // stage the per-column vectors while the mainloop runs
+        // per-column vectors of this tile: restaged only when they change (a persistent CTA usually keeps its n0: the round-robin
+        // stride is a multiple of tiles_n), which also lets the column sums accumulate in shared memory across its tiles
+        const bool restage = tc.n0 != staged_n0 || (p.bias && p.bias_sb != 0) || p.r1col;
+        if (restage) {
+          epi_barrier();                      // the previous tile's readers of the per-column vectors are done
+          if (want_colred && staged_n0 >= 0 && tc.n0 != staged_n0) flush_colred(staged_n0);
           const float* bias = p.bias ? p.bias + (int64_t)tc.z * p.bias_sb : nullptr;
           for (int j = et; j < BN; j += 128) {
             const bool ok = tc.n0 + j < p.N;
             bias_s[j] = (bias && ok) ? __ldg(bias + tc.n0 + j) : 0.f;
             colv_s[j] = (p.colv && ok) ? __ldg(p.colv + tc.n0 + j) : 0.f;
-            colred_s[j] = 0.f;
+            if (tc.n0 != staged_n0) colred_s[j] = 0.f;
             if (p.r1col) {
               const int ng = p.r1_rpg > 0 ? min(4, (p.M + p.r1_rpg - 1) / p.r1_rpg) : 1;
               for (int g = 0; g < ng; ++g)
                 r1_sm[eg][g][j] = ok ? __ldg(p.r1col + (int64_t)tc.z * p.r1col_sb + (int64_t)g * p.r1_gs + tc.n0 + j) : 0.f;
             }
           }
+          staged_n0 = tc.n0;
           epi_barrier();
         }
         const float rv = (p.rowv && row_ok) ? __ldg(p.rowv + (int64_t)tc.z * p.rowv_sb + row) : 0.f;
@@ -594,12 +613,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
         }
         if (p.mode == TC_EPI_ROWDOT && row_ok && eg < nchunks) atomicAdd(p.red_row + (int64_t)tc.z * p.red_row_sb + row, rowdot);
-        if (want_colred) {
-          epi_barrier();
-          for (int j = et; j < BN; j += 128)                           // only the columns of this group's chunks
-            if (((j >> 5) % neg) == eg && tc.n0 + j < p.N) atomicAdd(p.red_col + tc.n0 + j, colred_s[j]);
-        }
         if (tl && et == 0 && eg == 0 && tile_it == 0) tl[5] = clock64();
+      }
+      if (want_colred && staged_n0 >= 0) {
+        epi_barrier();
+        flush_colred(staged_n0);
       }
       if (stage_tma && leader) tma_store_wait_read<0>();   // smem must stay valid until the engine has read it
 #undef HCA_TL_STAMP
@@ -913,14 +931,21 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   // operand pipeline still gets the stages it needs; one group (deeper pipeline) for plain mainloop-bound products.
   const bool epi_heavy = e.act_tanh || e.aux_mode != TC_AUX_NONE || e.mode != TC_EPI_STORE || want_pl || e.transposed || e.r1col;
   int neg = 1, nbuf = 2;
-  if (epi_heavy && stages_for(2, 1) >= 2) neg = 2;
+  if (epi_heavy && stages_for(2, 1) >= (p.kb_total == 1 ? 1 : 2)) neg = 2;
   { const char* ev = getenv("HCA_TC_EG"); if (ev && (atoi(ev) == 1 || atoi(ev) == 2)) neg = atoi(ev); }
-  if (stages_for(neg, 2) < 4 && stages_for(neg, 1) > stages_for(neg, 2)) nbuf = 1;   // a deeper operand pipeline beats double-buffered staging
+  // single-k-block tiles (the K = T products) need no operand pipelining beyond the TMEM double buffer: one stage is enough
+  // there, which leaves room to double-buffer the epilogue staging -- their long pole
+  const int min_stages = p.kb_total == 1 ? 1 : 2;
+  if (p.kb_total == 1) {
+    if (stages_for(neg, 2) < 1) nbuf = 1;
+  } else if (stages_for(neg, 2) < 4 && stages_for(neg, 1) > stages_for(neg, 2)) {
+    nbuf = 1;                                     // a deeper operand pipeline beats double-buffered staging
+  }
   int stages = stages_for(neg, nbuf);
-  if (stages < 2 && neg == 2) { neg = 1; nbuf = 1; stages = stages_for(1, 1); }
+  if (stages < min_stages && neg == 2) { neg = 1; nbuf = 1; stages = stages_for(1, 1); }
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   { const char* ev = getenv("HCA_TC_STAGES"); if (ev && atoi(ev) >= 1 && atoi(ev) < stages) stages = atoi(ev); }
-  HCA_CHECK_ARG(stages >= 2, "gemm_tc: tile does not fit two pipeline stages");
+  HCA_CHECK_ARG(stages >= min_stages, "gemm_tc: tile does not fit its pipeline stages");
   p.stages = stages;
   p.store_nbuf = nbuf;
   p.n_eg = neg;
