@@ -159,7 +159,9 @@ class Stepper:
         p = syn.make_params(CFG["d"], CFG["vocab"], CFG["K"], CFG["mlp"], seed=0)
         self.net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()}, strict=False)
         self.net.to(device)
-        self.dp = pkg.dp.FlatGradAllReduce(self.net.named_parameters(), group, overlap=True, flat_params=True)
+        # graph mode: the bucketed all-reduce follows backward inside the captured step (hook-launched NCCL did not replay
+        # reliably from a captured graph: observed a hang); eager mode launches each bucket from the gradient hooks instead
+        self.dp = pkg.dp.FlatGradAllReduce(self.net.named_parameters(), group, overlap=not use_graph, flat_params=True)
         self.opt = pkg.optim.FlatAdam(self.dp, lr=1e-4)          # Adam(lr=1e-4), README.md:95-100 / main.py:180
         self.slots = []
         rank = torch.distributed.get_rank() if world > 1 else 0
@@ -210,30 +212,64 @@ class Stepper:
         return slot
 
 
+# ncu --set full capture of this kernel (profiles/): DRAM bytes per launch, read + write.  None until a capture is committed.
+ROOFLINE_TRAFFIC_BYTES = None
+ROOFLINE_TRAFFIC_SOURCE = None
+
+
 def time_roofline_kernel(pkg, device, steps, pk):
-    """Dominant kernel timed alone: PV = V . W_v^T + b_v, M = 160*196, N = K = 512."""
+    """The largest dense contraction of the path timed alone with CUDA events: PV = V . W_v^T + b_v, M = 160*196, N = K = 512
+    (SURVEY section 8a row a6), ONE launch of gemm_tc_kernel on operands already in bf16 hi/lo planes, planes out."""
     M, N, K = 160 * CFG["N"], CFG["d"], CFG["d"]
     g = torch.Generator(device="cpu").manual_seed(0)
-    As = [torch.randn(M, K, generator=g).to(device) for _ in range(3)]        # 3 x 64 MB inputs + 64 MB outputs > L2
-    W = torch.randn(N, K, generator=g).to(device) * 0.04
+    Ap = [pkg.ops.split_planes(torch.randn(M, K, generator=g).to(device)) for _ in range(3)]     # 3 x 64 MB in + 3 x 64 MB out > L2
+    Wp = pkg.ops.split_planes((torch.randn(N, K, generator=g) * 0.04).to(device))
     b = torch.randn(N, generator=g).to(device)
-    path = 1 if pkg._lib.get_option("gemm") == "tc" else 0
+    outs = [torch.empty(2, M, N, dtype=torch.bfloat16, device=device) for _ in range(3)]
     for i in range(3):
-        pkg.ops.gemm_nt(As[i % 3], W, b, path=path)
+        pkg.ops.proj_planes(Ap[i % 3], Wp, b, outs[i % 3])
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
     for i in range(steps):
-        pkg.ops.gemm_nt(As[i % 3], W, b, path=path)
+        pkg.ops.proj_planes(Ap[i % 3], Wp, b, outs[i % 3])
     ev[1].record()
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1]) / steps
     flops = 2.0 * M * N * K
     achieved = flops / (ms * 1e-3) / 1e12
-    # the split-precision path issues 3 bf16 MMAs per algorithmic product; report algorithmic TFLOP/s against the bf16 peak
+    # the split-precision path issues 3 bf16 MMAs per algorithmic product; `achieved` is ALGORITHMIC TFLOP/s against the bf16 peak
     return {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-            "traffic": None, "kernel": "proj_v gemm_nt M=31360 N=512 K=512 (" + ("tcgen05 bf16x2" if path else "fp32 CUDA cores") + ")",
-            "ms_per_launch": ms, "algorithmic_flops_per_launch": flops, "peak_source": pk["source"] + " bf16 burst"}
+            "traffic": ROOFLINE_TRAFFIC_BYTES, "traffic_source": ROOFLINE_TRAFFIC_SOURCE,
+            "kernel": "gemm_tc_kernel<128,2,K-major,K-major,64>: PV = V.Wv^T + bv, M=31360 N=512 K=512, bf16 hi/lo planes in and out",
+            "ms_per_launch": ms, "algorithmic_flops_per_launch": flops, "issued_mma_flops_per_launch": 3.0 * flops,
+            "frac_issued": 3.0 * achieved / pk["bf16_tflops"],
+            "algorithmic_bytes_per_launch": 2.0 * (2 * M * K * 2) + 2 * N * K * 2,
+            "hbm_gbs_if_algorithmic": (2.0 * (2 * M * K * 2) + 2 * N * K * 2) / (ms * 1e-3) / 1e9,
+            "peak_source": pk["source"] + " bf16 burst (kernel timed alone)"}
+
+
+def kernel_shares(st, steps=4, top=8):
+    """Per-kernel device time of the timed step under CUPTI activity tracing (torch.profiler): which kernels the step is made of."""
+    try:
+        import collections
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            for i in range(steps):
+                st.step(i)
+            torch.cuda.synchronize()
+        agg = collections.OrderedDict()
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                a = agg.setdefault(ev.name, [0, 0.0])
+                a[0] += 1
+                a[1] += ev.device_time
+        tot = sum(v[1] for v in agg.values())
+        rows = sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]
+        short = lambda n: n.replace("hca::(anonymous namespace)::", "").replace("void ", "")[:60]
+        return {"kernel_us_per_step": tot / steps,
+                "top": [{"kernel": short(k), "us_per_step": us / steps, "launches_per_step": n / steps, "share": us / tot} for k, (n, us) in rows]}
+    except Exception as e:                      # evidence only: never fail the bench over it
+        return {"error": f"{type(e).__name__}: {str(e)[:100]}"}
 
 
 def run_ours(args):
@@ -244,8 +280,18 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    if world > 1:
+        # a rank that dies or a collective that never completes must not hold the GPUs until the launcher's own timeout
+        def _watchdog():
+            sys.stderr.write(f"bench.py rank {rank}: no result after 300 s, giving up\n")
+            sys.stderr.flush()
+            os._exit(3)
+        wd = threading.Timer(300.0, _watchdog)
+        wd.daemon = True
+        wd.start()
     group = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line only
         torch.distributed.init_process_group("nccl", device_id=device)
     pkg = importlib.import_module("visual-question-answering_b200")
     importlib.import_module("visual-question-answering_b200.dp")
@@ -262,17 +308,7 @@ def run_ours(args):
             with torch.cuda.stream(s):
                 st.warm(3)                      # warm up on the side stream torch.cuda.graph captures from
             torch.cuda.current_stream().wait_stream(s)
-            try:
-                st.capture()                    # bucketed all-reduce launched from the gradient hooks, inside the graph
-            except Exception:
-                if world == 1:
-                    raise
-                torch.cuda.synchronize()
-                st.dp.set_overlap(False)        # NCCL launched from hooks did not capture: one all-reduce pass after backward
-                graph_note = "cuda-graph replay (all-reduce after backward: hook-launched NCCL did not capture)"
-                for slot in st.slots:
-                    slot["graph"] = None
-                st.capture()
+            st.capture()
         except Exception as e:                  # capture is an optimisation, never a requirement
             graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
             for slot in st.slots:
@@ -348,6 +384,7 @@ def run_ours(args):
 
     if rank == 0:
         roof = time_roofline_kernel(pkg, device, max(args.steps, 10), pk)
+        shares = kernel_shares(st) if world == 1 else None      # (the step holds collectives when world > 1: not a rank-0-only job)
         step_tflops = FLOPS_PER_SAMPLE * args.batch / (ms_step * 1e-3) / 1e12
         cpu = None
         if world == 1 and not args.skip_cpu_baseline:
@@ -356,13 +393,13 @@ def run_ours(args):
                    "sample": "5 steps of batch 32 (of the 160-sample batch), torch CPU fp32, oracle/torch_port.py", "ms_per_step": ms}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (fp32 CUDA cores)" if pkg._lib.get_option("gemm") == "ffma" else "bf16x2-split operands, fp32 accumulate",
+                "dtype": "f32 (fp32 CUDA cores)" if pkg._lib.get_option("gemm") == "ffma" else "bf16x2 (fp32 operands as bf16 hi+lo planes, 3 tcgen05 MMAs per product, fp32 accumulate)",
                 "data": "synthetic", "config": workload_config(args.batch, world, {"mode": graph_note}),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st.h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_ms},
                 "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
-                "roofline": roof, "cpu_baseline": cpu,
+                "roofline": roof, "cpu_baseline": cpu, "kernel_shares": shares,
                 "step_algorithmic_tflops": step_tflops, "step_frac_of_bf16_peak": step_tflops / pk["bf16_tflops_sustained"],
                 "final_loss": final_loss, "grad_allreduce_bytes": st.dp.grad_bytes() if world > 1 else 0}
         print(json.dumps(line), flush=True)

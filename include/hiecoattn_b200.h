@@ -151,6 +151,12 @@ HCA_API int hca_adam_step(float* p, const float* g, float* m, float* v, int64_t 
  * path 0 = fp32 CUDA cores; 1 = tcgen05 with bf16x2 operand splitting (3 MMAs, ~2^-16 operand
  * precision); 2 = tcgen05 bf16x3 (6 MMAs, fp32-grade). */
 HCA_API size_t hca_gemm_workspace(int M, int N, int K);
+/* The projection kernel of the co-attention (PV = V.Wv^T + bv, model.py:380-384) on its own, operands already in the library's
+ * operand format: bf16 hi/lo planes [2][rows][cols] (x = hi + lo).  hca_split_planes produces that format from fp32 [rows, cols];
+ * hca_proj_planes computes out planes [2][M][N] = A[M,K] . W[N,K]^T + bias[N] with one tcgen05 GEMM launch (3 MMAs per product). */
+HCA_API int hca_split_planes(const float* src, int64_t rows, int cols, void* planes, void* stream);
+HCA_API int hca_proj_planes(const void* a_planes, int64_t M, int K, const void* w_planes, int N, const float* bias,
+                    void* out_planes, void* stream);
 /* debug / profiling aid: subsequent tensor-core GEMM launches record per-CTA clock64() stamps into
  * buf [nctas][64] int64 ([0..7]: start, setup done, first tile landed, MMAs issued, epilogue start,
  * epilogue end, CTA end, SM id; [8+i], [24+i], [40+i]: per-k-block producer / landed / issued stamps); pass NULL to switch it off. */

@@ -173,6 +173,27 @@ extern "C" int hca_gemm(const float* A, const float* B, const float* bias, float
   return tc_gemm(A, M, K, M, true, B, N, K, N, true, D, N, M, N, K, &e, sk, w, s, P);
 }
 
+// ---- the projection kernel on its own (bench.py's roofline leg): operands already split into bf16 hi/lo planes ------
+extern "C" int hca_split_planes(const float* src, int64_t rows, int cols, void* planes, void* stream) {
+  using namespace hca;
+  HCA_CHECK_ARG(src && planes && rows > 0 && cols > 0 && cols % 8 == 0, "split_planes: bad arguments (cols %% 8 == 0 required)");
+  return launch_split_planes(src, cols, rows, cols, (__nv_bfloat16*)planes, cols, rows * cols, 2, (cudaStream_t)stream);
+}
+extern "C" int hca_proj_planes(const void* a_planes, int64_t M, int K, const void* w_planes, int N, const float* bias, void* out_planes,
+                               void* stream) {
+  using namespace hca;
+  HCA_CHECK_ARG(a_planes && w_planes && out_planes && M > 0 && M < (1LL << 31) && K > 0 && N > 0 && K % 8 == 0 && N % 8 == 0,
+                "proj_planes: bad arguments (K, N %% 8 == 0 required)");
+  HCA_CHECK_ARG(tc_available(), "proj_planes: cuTensorMapEncodeTiled is not available from the driver");
+  TcOperand A, B;
+  A.planes = (const __nv_bfloat16*)a_planes; A.ld = K; A.plane_stride = M * K; A.rows = (int)M; A.cols = K;
+  B.planes = (const __nv_bfloat16*)w_planes; B.ld = K; B.plane_stride = (int64_t)N * K; B.rows = N; B.cols = K;
+  TcEpilogue e;
+  e.bias = bias;
+  e.P.p = (__nv_bfloat16*)out_planes; e.P.ld = N; e.P.plane_stride = M * N; e.P.batch_stride = 0; e.P.nbatch = 1;
+  return launch_gemm_tc(A, B, 2, (int)M, N, K, e, 1, (cudaStream_t)stream);
+}
+
 extern "C" int hca_debug_gemm_timeline(void* buf, int nctas) {
   hca::tc_set_timeline((long long*)buf, buf ? nctas : 0);
   return 0;

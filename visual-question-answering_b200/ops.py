@@ -454,5 +454,25 @@ def gemm(A: Tensor, B: Tensor, bias: Optional[Tensor] = None, layout: str = "nt"
     return D
 
 
+def split_planes(x: Tensor) -> Tensor:
+    """fp32 [rows, cols] -> the library's operand format: bf16 hi/lo planes [2, rows, cols] (x = hi + lo to ~2^-17)."""
+    _cuda_f32(x)
+    x = _c(x)
+    out = torch.empty(2, x.shape[0], x.shape[1], dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().hca_split_planes(_ptr(x), x.shape[0], x.shape[1], _ptr(out), _stream()), "split_planes")
+    return out
+
+
+def proj_planes(a_planes: Tensor, w_planes: Tensor, bias: Tensor, out_planes: Tensor) -> Tensor:
+    """out planes [2, M, N] = A[M, K] . W[N, K]^T + bias: ONE launch of the projection kernel (no operand conversion)."""
+    _, M, K = a_planes.shape
+    N = w_planes.shape[1]
+    with torch.cuda.device(a_planes.device):
+        _lib.check(_lib.lib().hca_proj_planes(_ptr(a_planes), M, K, _ptr(w_planes), N, _ptr(bias), _ptr(out_planes), _stream()),
+                   "proj_planes")
+    return out_planes
+
+
 def gemm_nt(A: Tensor, B: Tensor, bias: Optional[Tensor] = None, path: int = 1) -> Tensor:
     return gemm(A, B, bias, "nt", path)
