@@ -19,6 +19,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "hv_fused.cuh"
 #include "util_kernels.cuh"
 
 namespace hca {
@@ -326,6 +327,12 @@ int split_to(const Pl& pl, const float* src, int64_t ld, cudaStream_t s) {
   return launch_split_planes(src, ld, pl.rows, pl.cols, pl.p, pl.ld, pl.ps, 2, s);
 }
 
+HvPlanes hvp(const Pl& pl) {
+  HvPlanes h;
+  h.p = pl.p; h.ld = pl.ld; h.ps = pl.ps;
+  return h;
+}
+
 bool v_is_dense(int64_t sb, int64_t sn, int64_t sd, int N, int d) { return sd == 1 && sn == d && sb == (int64_t)N * d; }
 
 }  // namespace
@@ -394,11 +401,8 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
     e.auxp = plv(PQp, 0, T3, B); e.aux_mode = TC_AUX_ADD;
     HCA_TRY(launch_gemm_tc(opv(Cp, 0, T3, T3, B, false), opv(PVp, 0, N, N, B, true), 2, T3, d, N, e, 1, s, B));
   }
-  {  // sv[b][l][n] = sum_j tanh(PV + C_l^T PQ_l)[n][j] wv[j]      (z = 3 b + l)
-    TcEpilogue e; e.mode = TC_EPI_ROWDOT; e.act_tanh = 1; e.colv = wv; e.red_row = svs; e.red_row_batch_stride = N;
-    e.auxp = plv(PVp, 0, N, B, 3); e.aux_mode = TC_AUX_ADD;
-    HCA_TRY(launch_gemm_tc(opv(Cp, 0, T, T, 3 * B, true), opv(PQp, 0, T, T, 3 * B, true), 2, N, d, T, e, 1, s, 3 * B));
-  }
+  // sv[b][l][n] = sum_j tanh(PV + C_l^T PQ_l)[n][j] wv[j]: the three levels of a tile in one pass over its PV tile (hv_fused.cu)
+  HCA_TRY(launch_hv_scores(hvp(Cp), hvp(PQp), hvp(PVp), wv, svs, B, N, T, d, s));
   const size_t smem = (size_t)6 * (N + T) * sizeof(float);
   HCA_CHECK_ARG(smem <= 48 * 1024, "coattn_fwd: N + T too large for the softmax kernel");
   HCA_TRY(zero_async(vhat, (size_t)3 * B * d * 4, s));
@@ -430,9 +434,8 @@ extern "C" int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv,
   Pl dZq = take_pl(w, BT3, d);             // [B][3T][d]
   Pl dPQ = take_pl(w, BT3, d);
   Pl dS = take_pl(w, BT3, N);              // [B][3T][N]
-  float* dPVacc = w.take<float>((size_t)BN * d);
   Pl dPV = take_pl(w, BN, d);
-  if (!dPV.p || !dPVacc || !dsc || !dscr) return set_err(HCA_ERR_WORKSPACE, "coattn_bwd: workspace too small (%zu bytes)", ws_bytes);
+  if (!dPV.p || !dsc || !dscr) return set_err(HCA_ERR_WORKSPACE, "coattn_bwd: workspace too small (%zu bytes)", ws_bytes);
   float* dsv = dsc;                        // [B][3][N]
   float* dsq = dsc + (size_t)3 * B * N;    // [B][3][T]
 
@@ -454,30 +457,19 @@ extern "C" int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv,
     attn_bwd_softmax_kernel<<<B, 192, 0, s>>>(sv_.av, sv_.aq, dav, daq, dsv, dsq, dcv, dcq, N, T);
     HCA_LAUNCHED();
   }
-  for (int l = 0; l < 3; ++l) {
-    // dZv_l = (dsv_l x wv) * (1 - Hv_l^2), Hv_l = tanh(PV + C_l^T PQ_l) recomputed ; dwv += Hv_l^T dsv_l ;
-    // dPVacc (+)= dZv_l  (level 0 stores, levels 1, 2 reduce-add: no memset of the 64 MB accumulator)
-    TcEpilogue e; e.mode = TC_EPI_DZ; e.act_tanh = 1; e.colv = wv; e.rowv = dsv + (int64_t)l * N; e.rowv_batch_stride = 3 * N; e.red_col = dwv;
-    e.auxp = plv(PVp, 0, N, B); e.aux_mode = TC_AUX_ADD;
-    e.P = plv(dZv, (int64_t)l * N, 3 * N, B);
-    e.D = dPVacc; e.ldd = d; e.d_batch_stride = (int64_t)N * d; e.accumulate = (l > 0);
-    HCA_TRY(launch_gemm_tc(opv(Cp, (int64_t)l * T, T, T3, B, true), opv(PQp, (int64_t)l * T, T, T3, B, true), 2, N, d, T, e, 1, s, B));
-  }
   {  // dZq_all = (dsq x wq) * (1 - Hq^2), Hq = tanh(PQ_all + C_all PV) recomputed ; dwq += Hq^T dsq
     TcEpilogue e; e.mode = TC_EPI_DZ; e.act_tanh = 1; e.colv = wq; e.rowv = dsq; e.rowv_batch_stride = T3; e.red_col = dwq;
     e.auxp = plv(PQp, 0, T3, B); e.aux_mode = TC_AUX_ADD;
     e.P = plv(dZq, 0, T3, B);
     HCA_TRY(launch_gemm_tc(opv(Cp, 0, T3, T3, B, false), opv(PVp, 0, N, N, B, true), 2, T3, d, N, e, 1, s, B));
   }
+  // dZv_l = (dsv_l x wv) * (1 - Hv_l^2) with Hv_l = tanh(PV + C_l^T PQ_l) recomputed, dwv += Hv_l^T dsv_l, and
+  // dPV = sum_l dZv_l + C_all^T dZq_all, dbv += sum_n dPV: one kernel, four TMEM accumulators per tile (hv_fused.cu)
+  HCA_TRY(launch_hv_grads(hvp(Cp), hvp(PQp), hvp(PVp), hvp(dZq), wv, dsv, hvp(dZv), hvp(dPV), dwv, dbv, B, N, T, d, s));
   {  // dPQ_l^T [d x T] = dZv_l^T C_l^T + dZq_l^T   (z = 3 b + l; long axis d on M, transposed epilogue) ; dbq += sum_t dPQ
     TcEpilogue e; e.transposed = 1; e.auxp = plv(dZq, 0, T, 3 * B); e.aux_mode = TC_AUX_ADD;
     e.P = plv(dPQ, 0, T, 3 * B); e.red_row = dbq;
     HCA_TRY(launch_gemm_tc(opv(dZv, 0, N, N, 3 * B, true), opv(Cp, 0, T, T, 3 * B, false), 2, d, T, N, e, 1, s, 3 * B));
-  }
-  {  // dPV[b] = sum_l dZv_l + C_all[b]^T dZq_all[b]   (K = 3T stacked) ; dbv += sum_n dPV
-    TcEpilogue e; e.aux = dPVacc; e.aux_ld = d; e.aux_batch_stride = (int64_t)N * d; e.aux_nbatch = B; e.aux_mode = TC_AUX_ADD;
-    e.P = plv(dPV, 0, N, B); e.red_col = dbv;
-    HCA_TRY(launch_gemm_tc(opv(Cp, 0, T3, T3, B, true), opv(dZq, 0, T3, T3, B, true), 2, N, d, T3, e, 1, s, B));
   }
   {  // dS_l^T [N x T] = (dZv_l PQ_l^T + PV dZq_l^T) * (1 - C_l^T ^2): two operand pairs chained along K, transposed epilogue
     TcEpilogue e; e.transposed = 1; e.auxp = plv(Cp, 0, T, 3 * B); e.aux_mode = TC_AUX_MUL_1MX2;
