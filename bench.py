@@ -213,8 +213,8 @@ class Stepper:
 
 
 # ncu --set full capture of this kernel (profiles/): DRAM bytes per launch, read + write.  None until a capture is committed.
-ROOFLINE_TRAFFIC_BYTES = None
-ROOFLINE_TRAFFIC_SOURCE = None
+ROOFLINE_TRAFFIC_BYTES = 86.4e6
+ROOFLINE_TRAFFIC_SOURCE = "profiles/r1c_pv_gemm_ncu_full.md: dram__bytes_read.sum 65.4 MB + dram__bytes_write.sum 21.0 MB, one launch"
 
 
 def time_roofline_kernel(pkg, device, steps, pk):
