@@ -163,6 +163,7 @@ class Stepper:
         # reliably from a captured graph: observed a hang); eager mode launches each bucket from the gradient hooks instead
         self.dp = pkg.dp.FlatGradAllReduce(self.net.named_parameters(), group, overlap=not use_graph, flat_params=True)
         self.opt = pkg.optim.FlatAdam(self.dp, lr=1e-4)          # Adam(lr=1e-4), README.md:95-100 / main.py:180
+        self.criterion = pkg.CrossEntropyLoss(scale=self.dp.loss_scale)   # nn.CrossEntropyLoss(), main.py:179
         self.slots = []
         rank = torch.distributed.get_rank() if world > 1 else 0
         for s in range(slots):
@@ -178,8 +179,8 @@ class Stepper:
         d = slot["dev"]
         self.dp.zero_grad()
         logits = self.net(d["feats"], d["tokens"], slot["lens"])
-        loss = torch.nn.functional.cross_entropy(logits, d["labels"])
-        (loss * self.dp.loss_scale).backward()
+        loss = self.criterion(logits, d["labels"])           # mean CE x 1/world, loss + gradient in one launch
+        loss.backward()
         self.dp.finish()
         self.opt.step()
         slot["loss"].copy_(loss.detach())
@@ -380,7 +381,7 @@ def run_ours(args):
         torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
     e2e_ms = float(t2.item()) / args.steps
     e2e_value = args.batch * world / (e2e_ms * 1e-3)
-    final_loss = float(loss_host)
+    final_loss = float(loss_host) / st.dp.loss_scale
 
     if rank == 0:
         roof = time_roofline_kernel(pkg, device, max(args.steps, 10), pk)

@@ -144,6 +144,13 @@ HCA_API int hca_mlp_bwd(const float* dlogits, const float* Ww, const float* Wp, 
 HCA_API int hca_adam_step(float* p, const float* g, float* m, float* v, int64_t n, long long* step, float* coef,
                   float lr, float beta1, float beta2, float eps, void* stream);
 
+/* ---- loss (replaces nn.CrossEntropyLoss()(logits, labels) and its backward, main.py:179,214) ---------------------- */
+/* loss[0] = scale * mean_b CE(logits[b,:K], labels[b]); dlogits (optional, leading dim ldd) = d loss / d logits.  One launch.
+ * `ws` >= hca_ce_loss_workspace(B) bytes of scratch.  labels int64 in [0,K): others give NaN. */
+HCA_API size_t hca_ce_loss_workspace(int B);
+HCA_API int hca_ce_loss(const float* logits, int64_t ld, const int64_t* labels, int B, int K, float scale, float* loss,
+                float* dlogits, int64_t ldd, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- building block exposed for tests and profiling: one dense contraction ------------------------- */
 /* fp32 row-major in and out.  layout 0 "nt": D[M,N] = A[M,K] . B[N,K]^T (+bias[N])   (nn.Linear forward)
  *                            layout 1 "nn": D[M,N] = A[M,K] . B[K,N]     (+bias[N])   (data gradient)

@@ -270,3 +270,59 @@ def test_opcheck_schemas():
     torch.library.opcheck(ops.coattn, tuple(ca), test_utils=kinds)
     ml = [r(3, B, d).requires_grad_(), r(3, B, d), r(d, d), r(d), r(d, 2 * d), r(d), r(m, 2 * d), r(m), r(K, m).requires_grad_(), r(K)]
     torch.library.opcheck(ops.mlp, tuple(ml), test_utils=kinds)
+
+
+def test_fused_cross_entropy_matches_torch():
+    """hiecoattn::cross_entropy (loss + gradient in one launch) against F.cross_entropy and its autograd, K = 1001 and odd sizes."""
+    h = _h()
+    ops = h.PKG.ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for B, K, scale in ((160, 1001, 1.0), (7, 13, 0.5), (1, 3001, 1.0)):
+        logits = (torch.randn(B, K, generator=g) * 3).cuda().requires_grad_()
+        labels = torch.randint(0, K, (B,), generator=g).cuda()
+        ref_in = logits.detach().double().requires_grad_()
+        ref = torch.nn.functional.cross_entropy(ref_in, labels) * scale
+        ref.backward()
+        for _ in range(2):                      # twice: the completion counter re-arms itself
+            logits.grad = None
+            loss = ops.cross_entropy(logits, labels, scale)
+            (loss * 2.0).backward()
+            assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+            assert h.rel(logits.grad.cpu().numpy(), 2.0 * ref_in.grad.cpu().numpy()) < 1e-5
+    crit = h.PKG.CrossEntropyLoss()
+    assert abs(float(crit(logits.detach(), labels)) - float(torch.nn.functional.cross_entropy(logits.detach(), labels))) < 1e-5
+
+
+def test_flat_gradient_sink_direct_write(syn):
+    """dp.FlatGradAllReduce as a gradient sink: the backward kernels write into the flat buffer, param.grad stays a view of
+    it, values equal the plain autograd path, and a second step does not see the first step's gradients."""
+    h = _h()
+    d, N, T, vocab, K, mlp = 64, 12, 6, 50, 9, 32
+    p = syn.make_params(d, vocab, K, mlp, seed=6)
+    xa = syn.make_inputs(4, N, T, d, vocab, K, seed=4, min_len=1)
+    xb = syn.make_inputs(4, N, T, d, vocab, K, seed=5, min_len=1)
+    plain = h.build_net(p, d, vocab, K, mlp)
+    ref_b = h.run_ours(plain, xb)["grads"]
+    net = h.build_net(p, d, vocab, K, mlp)
+    red = h.PKG.dp.FlatGradAllReduce(net.named_parameters(), None, flat_params=True)
+    try:
+        for x in (xa, xb, xb):
+            red.zero_grad()
+            dev = "cuda"
+            logits = net(torch.from_numpy(x["feats"]).to(dev), torch.from_numpy(x["tokens"]).to(dev), torch.from_numpy(x["lens"]))
+            before = h.PKG._lib.launch_count()
+            h.PKG.ops.cross_entropy(logits, torch.from_numpy(x["labels"]).to(dev)).backward()
+            red.finish()
+        assert len(red._direct_prev) == len(red.params)          # every trained tensor was written in place
+        for n, q in net.named_parameters():
+            if n.startswith("co_attention.W_b"):
+                assert q.grad is None
+                continue
+            assert red.flat.data_ptr() <= q.grad.data_ptr() < red.flat.data_ptr() + red.flat.numel() * 4
+            g = q.grad.cpu().numpy()
+            if n in h.ZERO_BIASES:
+                assert np.abs(g).max() < 1e-6
+            else:
+                assert h.rel(g, ref_b[n]) < 1e-4, n
+    finally:
+        h.PKG.ops.remove_grad_sink(red)

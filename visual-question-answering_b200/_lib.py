@@ -42,6 +42,8 @@ SIGNATURES = {
     "hca_mlp_fwd": (_i, [_p] * 15 + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_mlp_bwd": (_i, [_p] * 18 + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_adam_step": (_i, [_p, _p, _p, _p, _i64, _p, _p, C.c_float, C.c_float, C.c_float, C.c_float, _p]),
+    "hca_ce_loss_workspace": (_sz, [_i]),
+    "hca_ce_loss": (_i, [_p, _i64, _p, _i, _i, C.c_float, _p, _p, _i64, _p, _sz, _p]),
     "hca_gemm_workspace": (_sz, [_i, _i, _i]),
     "hca_split_planes": (_i, [_p, _i64, _i, _p, _p]),
     "hca_proj_planes": (_i, [_p, _i64, _i, _p, _i, _p, _p, _p]),

@@ -929,7 +929,10 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   };
   // Two epilogue groups when the epilogue is the long pole (fused math / plane conversion behind a short mainloop) and the
   // operand pipeline still gets the stages it needs; one group (deeper pipeline) for plain mainloop-bound products.
-  const bool epi_heavy = e.act_tanh || e.aux_mode != TC_AUX_NONE || e.mode != TC_EPI_STORE || want_pl || e.transposed || e.r1col;
+  // (measured on the PV projection, K = 512, planes out: one group + a third operand stage 56.7 us, two groups + two stages 67.2 us --
+  // a plane-conversion epilogue hides behind 8 k-blocks of MMAs; only fused math or a short mainloop needs the second group)
+  const bool epi_math = e.act_tanh || e.aux_mode != TC_AUX_NONE || e.mode != TC_EPI_STORE || e.transposed || e.r1col;
+  const bool epi_heavy = epi_math || (want_pl && p.kb_total < 8);
   int neg = 1, nbuf = 2;
   if (epi_heavy && stages_for(2, 1) >= (p.kb_total == 1 ? 1 : 2)) neg = 2;
   { const char* ev = getenv("HCA_TC_EG"); if (ev && (atoi(ev) == 1 || atoi(ev) == 2)) neg = atoi(ev); }

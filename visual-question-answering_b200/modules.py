@@ -217,6 +217,18 @@ class HierarchicalCoAttentionNet(nn.Module):
         return self.mlp_classify.forward_stacked(vhat, qhat)
 
 
+class CrossEntropyLoss(nn.Module):
+    """``nn.CrossEntropyLoss()`` as the reference's loop builds it (main.py:179: default mean reduction, no weights) with the
+    loss and its gradient computed in one launch; ``scale`` folds a constant factor (1 / world size in data-parallel runs) in."""
+
+    def __init__(self, scale: float = 1.0):
+        super().__init__()
+        self.scale = float(scale)
+
+    def forward(self, logits: Tensor, labels: Tensor) -> Tensor:
+        return ops.cross_entropy(logits, labels, self.scale)
+
+
 class HieCoAttnHotPath(nn.Module):
     """question encoder -> co-attention x3 -> MLP on precomputed image features.
 

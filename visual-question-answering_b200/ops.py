@@ -43,6 +43,42 @@ def _ws(nbytes: int, device) -> Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+# ------------------------------------------------------------------------------------------------ gradient sinks
+# A training loop that keeps every parameter gradient in one flat buffer (dp.FlatGradAllReduce) registers itself here.  The
+# autograd formulas below then let the backward kernels write each weight gradient straight into its slot of that buffer
+# (the ``*_bwd`` ops take their weight-gradient destinations as mutable arguments) and return None for those inputs: the
+# gradient is already where ``param.grad`` points, so autograd has nothing to add (it used to cost one elementwise kernel
+# per parameter and step, ~30 launches) and the buffer needs no clearing pass.
+_SINKS: list = []
+
+
+def add_grad_sink(sink) -> None:
+    if sink not in _SINKS:
+        _SINKS.append(sink)
+
+
+def remove_grad_sink(sink) -> None:
+    if sink in _SINKS:
+        _SINKS.remove(sink)
+
+
+def _gbuf(w: Tensor) -> Tensor:
+    """Destination of the gradient of parameter tensor ``w``: its slot in a registered sink, else a fresh tensor."""
+    for sink in _SINKS:
+        t = sink.take(w)
+        if t is not None:
+            return t
+    return torch.empty_like(w)
+
+
+def _gret(g: Tensor):
+    """What an autograd formula hands back for a weight gradient the kernel has written into ``g``."""
+    for sink in _SINKS:
+        if sink.delivered(g):
+            return None
+    return g
+
+
 # ------------------------------------------------------------------------------------------------ embedding
 @torch.library.custom_op(f"{NS}::embedding", mutates_args=(), device_types="cuda")
 def embedding(tokens: Tensor, table: Tensor) -> Tensor:
@@ -62,32 +98,28 @@ def _(tokens, table):
     return table.new_empty(*tokens.shape, table.shape[1])
 
 
-@torch.library.custom_op(f"{NS}::embedding_bwd", mutates_args=(), device_types="cuda")
-def embedding_bwd(tokens: Tensor, dout: Tensor, vocab: int) -> Tensor:
-    _cuda_f32(dout)
+@torch.library.custom_op(f"{NS}::embedding_bwd", mutates_args=("dtable",), device_types="cuda")
+def embedding_bwd(tokens: Tensor, dout: Tensor, dtable: Tensor) -> None:
+    """dtable [vocab, E] (overwritten) = scatter-add of dout rows by token."""
+    _cuda_f32(dout, dtable)
     tokens, dout = _c(tokens), _c(dout)
-    E = dout.shape[-1]
-    dtable = torch.empty(vocab, E, dtype=torch.float32, device=dout.device)
+    vocab, E = dtable.shape
+    assert dtable.is_contiguous()
     with torch.cuda.device(dout.device):
         _lib.check(_lib.lib().hca_embedding_bwd(_ptr(tokens), _ptr(dout), _ptr(dtable), tokens.numel(), E, vocab, _stream()),
                    "embedding_bwd")
-    return dtable
-
-
-@embedding_bwd.register_fake
-def _(tokens, dout, vocab):
-    return dout.new_empty(vocab, dout.shape[-1])
 
 
 def _embedding_setup(ctx, inputs, output):
     tokens, table = inputs
-    ctx.save_for_backward(tokens)
-    ctx.vocab = table.shape[0]
+    ctx.save_for_backward(tokens, table)
 
 
 def _embedding_backward(ctx, dout):
-    (tokens,) = ctx.saved_tensors
-    return None, embedding_bwd(tokens, dout, ctx.vocab)
+    tokens, table = ctx.saved_tensors
+    dtable = _gbuf(table)
+    embedding_bwd(tokens, dout, dtable)
+    return None, _gret(dtable)
 
 
 embedding.register_autograd(_embedding_backward, setup_context=_embedding_setup)
@@ -120,15 +152,16 @@ def _(x, w1, b1, w2, b2, w3, b3, lens):
     return torch.empty_like(x), x.new_empty(x.shape, dtype=torch.uint8)
 
 
-@torch.library.custom_op(f"{NS}::phrase_conv_pool_bwd", mutates_args=(), device_types="cuda")
+@torch.library.custom_op(f"{NS}::phrase_conv_pool_bwd", mutates_args=("dw1", "db1", "dw2", "db2", "dw3", "db3"), device_types="cuda")
 def phrase_conv_pool_bwd(x: Tensor, w1: Tensor, w2: Tensor, w3: Tensor, out: Tensor, idx: Tensor, dout: Tensor,
-                         lens: Optional[Tensor], need_dx: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    _cuda_f32(x, w1, w2, w3, out, dout)
+                         lens: Optional[Tensor], need_dx: bool, dw1: Tensor, db1: Tensor, dw2: Tensor, db2: Tensor, dw3: Tensor,
+                         db3: Tensor) -> Tensor:
+    """Returns dx; the weight / bias gradients are WRITTEN into dw* / db* (contiguous, 16-byte aligned)."""
+    _cuda_f32(x, w1, w2, w3, out, dout, dw1, db1, dw2, db2, dw3, db3)
     x, w1, w2, w3, out, idx, dout = map(_c, (x, w1, w2, w3, out, idx, dout))
+    assert all(t.is_contiguous() for t in (dw1, db1, dw2, db2, dw3, db3))
     B, T, E = x.shape
     dx = torch.empty_like(x) if need_dx else x.new_empty(0)
-    dw1, dw2, dw3 = torch.empty_like(w1), torch.empty_like(w2), torch.empty_like(w3)
-    db1, db2, db3 = (x.new_empty(E) for _ in range(3))
     L = _lib.lib()
     with torch.cuda.device(x.device):
         ws = _ws(L.hca_phrase_conv_pool_workspace(B, T, E), x.device)
@@ -136,30 +169,29 @@ def phrase_conv_pool_bwd(x: Tensor, w1: Tensor, w2: Tensor, w3: Tensor, out: Ten
                                               _ptr(None if lens is None else _c(lens)), _ptr(dx) if need_dx else None,
                                               _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _ptr(dw3), _ptr(db3), B, T, E,
                                               _ptr(ws), ws.numel(), _stream()), "phrase_conv_pool_bwd")
-    return dx, dw1, db1, dw2, db2, dw3, db3
+    return dx
 
 
 @phrase_conv_pool_bwd.register_fake
-def _(x, w1, w2, w3, out, idx, dout, lens, need_dx):
-    E = x.shape[-1]
-    return (torch.empty_like(x) if need_dx else x.new_empty(0), torch.empty_like(w1), x.new_empty(E), torch.empty_like(w2),
-            x.new_empty(E), torch.empty_like(w3), x.new_empty(E))
+def _(x, w1, w2, w3, out, idx, dout, lens, need_dx, dw1, db1, dw2, db2, dw3, db3):
+    return torch.empty_like(x) if need_dx else x.new_empty(0)
 
 
 def _pcp_setup(ctx, inputs, output):
     x, w1, b1, w2, b2, w3, b3, lens = inputs
     out, idx = output
-    ctx.save_for_backward(x, w1, w2, w3, out, idx, lens)
+    ctx.save_for_backward(x, w1, b1, w2, b2, w3, b3, out, idx, lens)
     ctx.set_materialize_grads(False)
 
 
 def _pcp_backward(ctx, dout, _didx):
-    x, w1, w2, w3, out, idx, lens = ctx.saved_tensors
+    x, w1, b1, w2, b2, w3, b3, out, idx, lens = ctx.saved_tensors
     if dout is None:
         return (None,) * 8
     need_dx = ctx.needs_input_grad[0]
-    dx, dw1, db1, dw2, db2, dw3, db3 = phrase_conv_pool_bwd(x, w1, w2, w3, out, idx, dout, lens, need_dx)
-    return (dx if need_dx else None), dw1, db1, dw2, db2, dw3, db3, None
+    gs = [_gbuf(t) for t in (w1, b1, w2, b2, w3, b3)]
+    dx = phrase_conv_pool_bwd(x, w1, w2, w3, out, idx, dout, lens, need_dx, *gs)
+    return ((dx if need_dx else None), *(_gret(g) for g in gs), None)
 
 
 phrase_conv_pool.register_autograd(_pcp_backward, setup_context=_pcp_setup)
@@ -201,47 +233,48 @@ def _(x, lens, w_ih, w_hh, b_ih, b_hh):
     return x.new_empty(B, T, H), x.new_empty(nbytes, dtype=torch.uint8)
 
 
-@torch.library.custom_op(f"{NS}::lstm_bwd", mutates_args=(), device_types="cuda")
-def lstm_bwd(lens: Tensor, w_ih: Tensor, w_hh: Tensor, saved: Tensor, dout: Tensor, E: int, need_dx: bool
-             ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
-    _cuda_f32(w_ih, w_hh, dout)
+@torch.library.custom_op(f"{NS}::lstm_bwd", mutates_args=("dw_ih", "dw_hh", "db_ih", "db_hh"), device_types="cuda")
+def lstm_bwd(lens: Tensor, w_ih: Tensor, w_hh: Tensor, saved: Tensor, dout: Tensor, E: int, need_dx: bool, dw_ih: Tensor,
+             dw_hh: Tensor, db_ih: Tensor, db_hh: Tensor) -> Tensor:
+    """Returns dx; the weight / bias gradients are WRITTEN into dw_* / db_*."""
+    _cuda_f32(w_ih, w_hh, dout, dw_ih, dw_hh, db_ih, db_hh)
     lens, w_ih, w_hh, dout = map(_c, (lens, w_ih, w_hh, dout))
+    assert all(t.is_contiguous() for t in (dw_ih, dw_hh, db_ih, db_hh))
     B, T, H = dout.shape
     dev = dout.device
     f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     dx = f(B, T, E) if need_dx else f(0)
-    dw_ih, dw_hh, db_ih, db_hh = f(4 * H, E), f(4 * H, H), f(4 * H), f(4 * H)
     L = _lib.lib()
     with torch.cuda.device(dev):
         ws = _ws(L.hca_lstm_workspace(B, T, E, H), dev)
         _lib.check(L.hca_lstm_bwd(_ptr(lens), _ptr(w_ih), _ptr(w_hh), _ptr(saved), saved.numel(), _ptr(dout),
                                   _ptr(dx) if need_dx else None, _ptr(dw_ih), _ptr(dw_hh), _ptr(db_ih), _ptr(db_hh), B, T, E, H,
                                   _ptr(ws), ws.numel(), _stream()), "lstm_bwd")
-    return dx, dw_ih, dw_hh, db_ih, db_hh
+    return dx
 
 
 @lstm_bwd.register_fake
-def _(lens, w_ih, w_hh, saved, dout, E, need_dx):
+def _(lens, w_ih, w_hh, saved, dout, E, need_dx, dw_ih, dw_hh, db_ih, db_hh):
     B, T, H = dout.shape
-    f = lambda *s: dout.new_empty(*s)
-    return (f(B, T, E) if need_dx else f(0)), f(4 * H, E), f(4 * H, H), f(4 * H), f(4 * H)
+    return dout.new_empty(B, T, E) if need_dx else dout.new_empty(0)
 
 
 def _lstm_setup(ctx, inputs, output):
     x, lens, w_ih, w_hh, b_ih, b_hh = inputs
     out, saved = output
-    ctx.save_for_backward(lens, w_ih, w_hh, saved)
+    ctx.save_for_backward(lens, w_ih, w_hh, b_ih, b_hh, saved)
     ctx.E = x.shape[2]
     ctx.set_materialize_grads(False)
 
 
 def _lstm_backward(ctx, dout, _dsaved):
-    lens, w_ih, w_hh, saved = ctx.saved_tensors
+    lens, w_ih, w_hh, b_ih, b_hh, saved = ctx.saved_tensors
     if dout is None:
         return (None,) * 6
     need_dx = ctx.needs_input_grad[0]
-    dx, dw_ih, dw_hh, db_ih, db_hh = lstm_bwd(lens, w_ih, w_hh, saved, dout, ctx.E, need_dx)
-    return (dx if need_dx else None), None, dw_ih, dw_hh, db_ih, db_hh
+    gs = [_gbuf(t) for t in (w_ih, w_hh, b_ih, b_hh)]
+    dx = lstm_bwd(lens, w_ih, w_hh, saved, dout, ctx.E, need_dx, *gs)
+    return ((dx if need_dx else None), None, *(_gret(g) for g in gs))
 
 
 lstm.register_autograd(_lstm_backward, setup_context=_lstm_setup)
@@ -284,45 +317,46 @@ def _(V, q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq):
     return V.new_empty(3, B, d), V.new_empty(3, B, d), V.new_empty(nbytes, dtype=torch.uint8)
 
 
-@torch.library.custom_op(f"{NS}::coattn_bwd", mutates_args=(), device_types="cuda")
-def coattn_bwd(Wv: Tensor, Wq: Tensor, wv: Tensor, wq: Tensor, saved: Tensor, gv: Tensor, gq: Tensor, N: int, T: int, need_dv: bool
-               ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    _cuda_f32(Wv, Wq, wv, wq, gv, gq)
+@torch.library.custom_op(f"{NS}::coattn_bwd", mutates_args=("dWv", "dbv", "dWq", "dbq", "dwv", "dcv", "dwq", "dcq"),
+                         device_types="cuda")
+def coattn_bwd(Wv: Tensor, Wq: Tensor, wv: Tensor, wq: Tensor, saved: Tensor, gv: Tensor, gq: Tensor, N: int, T: int, need_dv: bool,
+               dWv: Tensor, dbv: Tensor, dWq: Tensor, dbq: Tensor, dwv: Tensor, dcv: Tensor, dwq: Tensor, dcq: Tensor
+               ) -> Tuple[Tensor, Tensor]:
+    """Returns (dV, dQ [3,B,T,d]); the parameter gradients are WRITTEN into dWv .. dcq."""
+    _cuda_f32(Wv, Wq, wv, wq, gv, gq, dWv, dbv, dWq, dbq, dwv, dcv, dwq, dcq)
     Wv, Wq, wv, wq, gv, gq = map(_c, (Wv, Wq, wv, wq, gv, gq))
+    assert all(t.is_contiguous() for t in (dWv, dbv, dWq, dbq, dwv, dcv, dwq, dcq))
     _, B, d = gv.shape
     dev = gv.device
     f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     dV = f(B, N, d) if need_dv else f(0)
     dQ = f(3, B, T, d)
-    dWv, dbv, dWq, dbq = f(d, d), f(d), f(d, d), f(d)
-    dwv, dcv, dwq, dcq = f(d), f(1), f(d), f(1)
     L = _lib.lib()
     with torch.cuda.device(dev):
         ws = _ws(L.hca_coattn_workspace(B, N, T, d, int(need_dv)), dev)
         _lib.check(L.hca_coattn_bwd(_ptr(Wv), _ptr(Wq), _ptr(wv), _ptr(wq), _ptr(saved), saved.numel(), _ptr(gv), _ptr(gq),
                                     _ptr(dV) if need_dv else None, _ptr(dQ), _ptr(dWv), _ptr(dbv), _ptr(dWq), _ptr(dbq), _ptr(dwv),
                                     _ptr(dcv), _ptr(dwq), _ptr(dcq), B, N, T, d, _ptr(ws), ws.numel(), _stream()), "coattn_bwd")
-    return dV, dQ, dWv, dbv, dWq, dbq, dwv, dcv, dwq, dcq
+    return dV, dQ
 
 
 @coattn_bwd.register_fake
-def _(Wv, Wq, wv, wq, saved, gv, gq, N, T, need_dv):
+def _(Wv, Wq, wv, wq, saved, gv, gq, N, T, need_dv, dWv, dbv, dWq, dbq, dwv, dcv, dwq, dcq):
     _, B, d = gv.shape
     f = lambda *s: gv.new_empty(*s)
-    return (f(B, N, d) if need_dv else f(0), f(3, B, T, d), f(d, d), f(d), f(d, d), f(d), f(d), f(1), f(d), f(1))
+    return (f(B, N, d) if need_dv else f(0)), f(3, B, T, d)
 
 
 def _coattn_setup(ctx, inputs, output):
     V, q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq = inputs
     vhat, qhat, saved = output
-    ctx.save_for_backward(Wv, Wq, wv, wq, saved)
-    ctx.shapes = (wv.shape, cv.shape, wq.shape, cq.shape)
+    ctx.save_for_backward(Wv, bv, Wq, bq, wv, cv, wq, cq, saved)
     ctx.NT = (V.shape[1], q0.shape[1])
     ctx.set_materialize_grads(False)
 
 
 def _coattn_backward(ctx, gv, gq, *_unused):
-    Wv, Wq, wv, wq, saved = ctx.saved_tensors
+    Wv, bv, Wq, bq, wv, cv, wq, cq, saved = ctx.saved_tensors
     if gv is None and gq is None:
         return (None,) * 12
     if gv is None:
@@ -331,10 +365,9 @@ def _coattn_backward(ctx, gv, gq, *_unused):
         gq = torch.zeros_like(gv)
     need_dv = ctx.needs_input_grad[0]
     N, T = ctx.NT
-    dV, dQ, dWv, dbv, dWq, dbq, dwv, dcv, dwq, dcq = coattn_bwd(Wv, Wq, wv, wq, saved, gv, gq, N, T, need_dv)
-    s_wv, s_cv, s_wq, s_cq = ctx.shapes
-    return ((dV if need_dv else None), dQ[0], dQ[1], dQ[2], dWv, dbv, dWq, dbq, dwv.view(s_wv), dcv.view(s_cv), dwq.view(s_wq),
-            dcq.view(s_cq))
+    gs = [_gbuf(t) for t in (Wv, bv, Wq, bq, wv, cv, wq, cq)]
+    dV, dQ = coattn_bwd(Wv, Wq, wv, wq, saved, gv, gq, N, T, need_dv, *gs)
+    return ((dV if need_dv else None), dQ[0], dQ[1], dQ[2], *(_gret(g) for g in gs))
 
 
 coattn.register_autograd(_coattn_backward, setup_context=_coattn_setup)
@@ -370,50 +403,95 @@ def _(vhat, qhat, Ww, bw, Wp, bp, Ws, bs, Wh, bh):
     return f(B, Wh.shape[0]), f(B, d), f(B, 2 * d), f(B, 2 * d), f(B, Ws.shape[0])
 
 
-@torch.library.custom_op(f"{NS}::mlp_bwd", mutates_args=(), device_types="cuda")
-def mlp_bwd(dlogits: Tensor, Ww: Tensor, Wp: Tensor, Ws: Tensor, Wh: Tensor, xw: Tensor, xp: Tensor, xs: Tensor, hs: Tensor
-            ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    _cuda_f32(dlogits, Ww, Wp, Ws, Wh, xw, xp, xs, hs)
+@torch.library.custom_op(f"{NS}::mlp_bwd", mutates_args=("dWw", "dbw", "dWp", "dbp", "dWs", "dbs", "dWh", "dbh"), device_types="cuda")
+def mlp_bwd(dlogits: Tensor, Ww: Tensor, Wp: Tensor, Ws: Tensor, Wh: Tensor, xw: Tensor, xp: Tensor, xs: Tensor, hs: Tensor,
+            dWw: Tensor, dbw: Tensor, dWp: Tensor, dbp: Tensor, dWs: Tensor, dbs: Tensor, dWh: Tensor, dbh: Tensor) -> Tensor:
+    """Returns g [3,B,d] (gradient of q_l + v_l per level); the parameter gradients are WRITTEN into dWw .. dbh."""
+    _cuda_f32(dlogits, Ww, Wp, Ws, Wh, xw, xp, xs, hs, dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh)
     dlogits, Ww, Wp, Ws, Wh = map(_c, (dlogits, Ww, Wp, Ws, Wh))
+    assert all(t.is_contiguous() for t in (dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh))
     B, d = xw.shape
     m, K = Ws.shape[0], Wh.shape[0]
     dev = dlogits.device
-    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-    g = f(3, B, d)
-    dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh = f(d, d), f(d), f(d, 2 * d), f(d), f(m, 2 * d), f(m), f(K, m), f(K)
+    g = torch.empty(3, B, d, dtype=torch.float32, device=dev)
     L = _lib.lib()
     with torch.cuda.device(dev):
         ws = _ws(L.hca_mlp_workspace(B, d, m, K), dev)
         _lib.check(L.hca_mlp_bwd(_ptr(dlogits), _ptr(Ww), _ptr(Wp), _ptr(Ws), _ptr(Wh), _ptr(xw), _ptr(xp), _ptr(xs), _ptr(hs), _ptr(g),
                                  _ptr(dWw), _ptr(dbw), _ptr(dWp), _ptr(dbp), _ptr(dWs), _ptr(dbs), _ptr(dWh), _ptr(dbh), B, d, m, K,
                                  _ptr(ws), ws.numel(), _stream()), "mlp_bwd")
-    return g, dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh
+    return g
 
 
 @mlp_bwd.register_fake
-def _(dlogits, Ww, Wp, Ws, Wh, xw, xp, xs, hs):
+def _(dlogits, Ww, Wp, Ws, Wh, xw, xp, xs, hs, dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh):
     B, d = xw.shape
-    m, K = Ws.shape[0], Wh.shape[0]
-    f = lambda *s: dlogits.new_empty(*s)
-    return f(3, B, d), f(d, d), f(d), f(d, 2 * d), f(d), f(m, 2 * d), f(m), f(K, m), f(K)
+    return dlogits.new_empty(3, B, d)
 
 
 def _mlp_setup(ctx, inputs, output):
     vhat, qhat, Ww, bw, Wp, bp, Ws, bs, Wh, bh = inputs
     logits, xw, xp, xs, hs = output
-    ctx.save_for_backward(Ww, Wp, Ws, Wh, xw, xp, xs, hs)
+    ctx.save_for_backward(Ww, bw, Wp, bp, Ws, bs, Wh, bh, xw, xp, xs, hs)
     ctx.set_materialize_grads(False)
 
 
 def _mlp_backward(ctx, dlogits, *_unused):
-    Ww, Wp, Ws, Wh, xw, xp, xs, hs = ctx.saved_tensors
+    Ww, bw, Wp, bp, Ws, bs, Wh, bh, xw, xp, xs, hs = ctx.saved_tensors
     if dlogits is None:
         return (None,) * 10
-    g, dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh = mlp_bwd(dlogits, Ww, Wp, Ws, Wh, xw, xp, xs, hs)
-    return g, g, dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh      # q_l + v_l: both receive the same gradient
+    gs = [_gbuf(t) for t in (Ww, bw, Wp, bp, Ws, bs, Wh, bh)]
+    g = mlp_bwd(dlogits, Ww, Wp, Ws, Wh, xw, xp, xs, hs, *gs)
+    return (g, g, *(_gret(t) for t in gs))                    # q_l + v_l: both receive the same gradient
 
 
 mlp.register_autograd(_mlp_backward, setup_context=_mlp_setup)
+
+
+# ------------------------------------------------------------------------------------------------------- loss
+@torch.library.custom_op(f"{NS}::cross_entropy_fwd", mutates_args=(), device_types="cuda")
+def cross_entropy_fwd(logits: Tensor, labels: Tensor, scale: float) -> Tuple[Tensor, Tensor]:
+    """(scale * mean CE, d/dlogits of it) in one launch (reference main.py:179,214: nn.CrossEntropyLoss, mean reduction)."""
+    _cuda_f32(logits)
+    logits, labels = _c(logits), _c(labels)
+    assert logits.dim() == 2 and labels.dtype == torch.int64 and labels.shape == (logits.shape[0],)
+    B, K = logits.shape
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty_like(logits)
+    with torch.cuda.device(logits.device):
+        ws = _ws(_lib.lib().hca_ce_loss_workspace(B), logits.device)
+        _lib.check(_lib.lib().hca_ce_loss(_ptr(logits), K, _ptr(labels), B, K, scale, _ptr(loss), _ptr(dlogits), K, _ptr(ws),
+                                          ws.numel(), _stream()), "ce_loss")
+    return loss, dlogits
+
+
+@cross_entropy_fwd.register_fake
+def _(logits, labels, scale):
+    return logits.new_empty(()), torch.empty_like(logits)
+
+
+def _ce_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+    ctx.set_materialize_grads(False)
+
+
+def _ce_backward(ctx, dloss, _unused):
+    (dlogits,) = ctx.saved_tensors
+    return (None if dloss is None else dlogits * dloss), None, None
+
+
+cross_entropy_fwd.register_autograd(_ce_backward, setup_context=_ce_setup)
+
+
+def cross_entropy(logits: Tensor, labels: Tensor, scale: float = 1.0) -> Tensor:
+    """scale * F.cross_entropy(logits, labels) (mean over the batch) with the gradient computed in the same launch."""
+    if not logits.is_cuda:
+        raise RuntimeError("hiecoattn_b200 ops run on CUDA only (no CPU fallback); got a CPU tensor")
+    return cross_entropy_fwd(_f32c(logits), labels, float(scale))[0]
+
+
+def _f32c(t: Tensor) -> Tensor:
+    return t if t.dtype == torch.float32 else t.float()
 
 
 # ------------------------------------------------------------------------------------------------ optimizer
