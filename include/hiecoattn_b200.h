@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HCA_ABI_VERSION 3
+#define HCA_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define HCA_API __attribute__((visibility("default")))
@@ -120,19 +120,19 @@ HCA_API int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv, co
                    int B, int N, int T, int d, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- MLPClassifier (replaces model.py:414-434) -------------------------------------------------- */
-/* vhat,qhat [3,B,d] (levels word, phrase, sentence); Ww [d,d], Wp [d,2d], Ws [mlp,2d], Wh [K,mlp].
- * outputs: logits [B,K]; saved: xw [B,d], xp [B,2d] (= [q_p+v_p | h_w]), xs [B,2d] (= [q_s+v_s | h_p]),
- * hs [B,mlp]. */
+/* vhat,qhat [3,B,d] (levels word, phrase, sentence); Ww [d,d], Wp [d,2d], Ws [mlp,2d], Wh [K,mlp]; d % 8 == 0.
+ * outputs: logits [B,K]; `saved` (hca_mlp_saved_bytes, 256-byte aligned, opaque): bf16 hi/lo operand planes of the four
+ * weights, of xw [B,d], xp [B,2d] (= [q_p+v_p | h_w]), xs [B,2d] (= [q_s+v_s | h_p]) and of hs [B,mlp]. */
 HCA_API size_t hca_mlp_workspace(int B, int d, int mlp, int K);
+HCA_API size_t hca_mlp_saved_bytes(int B, int d, int mlp, int K);
 HCA_API int hca_mlp_fwd(const float* vhat, const float* qhat,
                 const float* Ww, const float* bw, const float* Wp, const float* bp,
                 const float* Ws, const float* bs, const float* Wh, const float* bh,
-                float* logits, float* xw, float* xp, float* xs, float* hs,
+                float* logits, void* saved, size_t saved_bytes,
                 int B, int d, int mlp, int K, void* ws, size_t ws_bytes, void* stream);
 /* dlogits [B,K] -> g [3,B,d] (gradient of BOTH vhat and qhat of each level: they enter as q+v),
- * and all weight / bias gradients. */
-HCA_API int hca_mlp_bwd(const float* dlogits, const float* Ww, const float* Wp, const float* Ws, const float* Wh,
-                const float* xw, const float* xp, const float* xs, const float* hs,
+ * and all weight / bias gradients (written, not accumulated). */
+HCA_API int hca_mlp_bwd(const float* dlogits, const void* saved, size_t saved_bytes,
                 float* g, float* dWw, float* dbw, float* dWp, float* dbp, float* dWs, float* dbs,
                 float* dWh, float* dbh, int B, int d, int mlp, int K,
                 void* ws, size_t ws_bytes, void* stream);

@@ -39,8 +39,9 @@ SIGNATURES = {
     "hca_coattn_fwd": (_i, [_p, _i64, _i64, _i64] + [_p] * 14 + [_sz] + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_coattn_bwd": (_i, [_p] * 5 + [_sz] + [_p] * 12 + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_mlp_workspace": (_sz, [_i, _i, _i, _i]),
-    "hca_mlp_fwd": (_i, [_p] * 15 + [_i, _i, _i, _i, _p, _sz, _p]),
-    "hca_mlp_bwd": (_i, [_p] * 18 + [_i, _i, _i, _i, _p, _sz, _p]),
+    "hca_mlp_saved_bytes": (_sz, [_i, _i, _i, _i]),
+    "hca_mlp_fwd": (_i, [_p] * 12 + [_sz] + [_i, _i, _i, _i, _p, _sz, _p]),
+    "hca_mlp_bwd": (_i, [_p] * 2 + [_sz] + [_p] * 9 + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_adam_step": (_i, [_p, _p, _p, _p, _i64, _p, _p, C.c_float, C.c_float, C.c_float, C.c_float, _p]),
     "hca_ce_loss_workspace": (_sz, [_i]),
     "hca_ce_loss": (_i, [_p, _i64, _p, _i, _i, C.c_float, _p, _p, _i64, _p, _sz, _p]),
@@ -53,7 +54,7 @@ SIGNATURES = {
     "hca_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 

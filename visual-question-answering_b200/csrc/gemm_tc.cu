@@ -297,6 +297,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         float* drow = p.D ? p.D + (int64_t)(tc.z / p.d_zd) * p.d_sb + (int64_t)tc.n0 * p.ldd + row : nullptr;
         __nv_bfloat16* prow = p.P ? p.P + (int64_t)tc.z * p.p_sb + (int64_t)tc.n0 * p.p_ld + row : nullptr;
         float rsum = 0.f;
+        // transposed tiles: the bias is indexed by the tile ROW m (the output feature: these products put the weight on M)
+        const float bm = (p.bias && row_ok) ? __ldg(p.bias + (int64_t)tc.z * p.bias_sb + row) : 0.f;
         if (row_ok) {
 #pragma unroll
           for (int j0 = 0; j0 < 32; j0 += 8) {
@@ -314,9 +316,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (j0 + j < ncols) {
-                float f = (tc.num_kb != 0) ? __uint_as_float(v[j0 + j]) : 0.f;
+                float f = ((tc.num_kb != 0) ? __uint_as_float(v[j0 + j]) : 0.f) + bm;
                 if (p.aux_mode == TC_AUX_ADD) f += ax[j];
-                else if (p.aux_mode == TC_AUX_MUL_1MX2) f *= (1.f - ax[j] * ax[j]);
+                if (p.act_tanh) f = tanh_fast(f);
+                if (p.aux_mode == TC_AUX_MUL_1MX2) f *= (1.f - ax[j] * ax[j]);
                 rsum += f;
                 if (drow) {
                   float* d = drow + (int64_t)(j0 + j) * p.ldd;
@@ -997,8 +1000,8 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   HCA_CHECK_ARG(!e.r1col || e.r1_rows_per_group <= 0 || (M + e.r1_rows_per_group - 1) / e.r1_rows_per_group <= 4,
                 "gemm_tc: at most 4 rank-1 row groups");
   if (e.transposed)
-    HCA_CHECK_ARG(!e.bias && !e.act_tanh && !e.mulx && e.mode == TC_EPI_STORE && !e.r1col && !e.red_col && groups == 1 && !e.aux,
-                  "gemm_tc: the transposed epilogue supports fp32 / planes output, auxp and red_row only");
+    HCA_CHECK_ARG(!e.mulx && e.mode == TC_EPI_STORE && !e.r1col && !e.red_col && groups == 1 && !e.aux,
+                  "gemm_tc: the transposed epilogue supports fp32 / planes output, a per-row bias, tanh, auxp and red_row only");
   { static int dbg = -1; if (dbg < 0) { const char* ev = getenv("HCA_TC_DBG"); dbg = ev ? atoi(ev) : 0; } p.dbg = dbg; }
   p.timeline = (g_timeline && (g_timeline_target < 0 || g_timeline_seen == g_timeline_target)) ? g_timeline : nullptr;
   p.timeline_ctas = g_timeline_ctas;

@@ -74,7 +74,8 @@ struct TcEpilogue {
   float* red_row = nullptr;     int64_t red_row_batch_stride = 0;
   float* red_col = nullptr;                                         // DZ: see above.  STORE: red_col[n] += sum_m f[m][n]
   // BN = 32 "transposed" epilogue: outputs and auxp are addressed [z][n][m] (ld = their leading dimension over m); fp32 D,
-  // planes P, auxp (ADD / MUL_1MX2) and red_row (un-batched: red_row[m] += sum_n f[m][n]) are supported, nothing else.
+  // planes P, auxp (ADD / MUL_1MX2), act_tanh, red_row (un-batched: red_row[m] += sum_n f[m][n]) and a bias indexed by the
+  // tile ROW (bias[z][m]: these products put the weight matrix on M) are supported, nothing else.
   int transposed = 0;
 };
 

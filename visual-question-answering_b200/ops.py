@@ -376,72 +376,75 @@ coattn.register_autograd(_coattn_backward, setup_context=_coattn_setup)
 # -------------------------------------------------------------------------------------------------------- MLP
 @torch.library.custom_op(f"{NS}::mlp", mutates_args=(), device_types="cuda")
 def mlp(vhat: Tensor, qhat: Tensor, Ww: Tensor, bw: Tensor, Wp: Tensor, bp: Tensor, Ws: Tensor, bs: Tensor, Wh: Tensor,
-        bh: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+        bh: Tensor) -> Tuple[Tensor, Tensor]:
     """MLPClassifier forward (reference model.py:414-434) on stacked [3,B,d] attended features.
 
-    Returns logits [B,K] and the tensors saved for backward (xw, xp, xs, hs)."""
+    Returns logits [B,K] and ``saved``, the opaque buffer the backward kernels read (bf16 operand planes of the weights
+    and of the layer inputs; layout private to the library)."""
     _cuda_f32(vhat, qhat, Ww, bw, Wp, bp, Ws, bs, Wh, bh)
     vhat, qhat, Ww, bw, Wp, bp, Ws, bs, Wh, bh = map(_c, (vhat, qhat, Ww, bw, Wp, bp, Ws, bs, Wh, bh))
     _, B, d = vhat.shape
     m, K = Ws.shape[0], Wh.shape[0]
     dev = vhat.device
-    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-    logits, xw, xp, xs, hs = f(B, K), f(B, d), f(B, 2 * d), f(B, 2 * d), f(B, m)
+    logits = torch.empty(B, K, dtype=torch.float32, device=dev)
     L = _lib.lib()
     with torch.cuda.device(dev):
-        ws = _ws(L.hca_mlp_workspace(B, d, m, K), dev)
+        saved = _ws(L.hca_mlp_saved_bytes(B, d, m, K), dev)
         _lib.check(L.hca_mlp_fwd(_ptr(vhat), _ptr(qhat), _ptr(Ww), _ptr(bw), _ptr(Wp), _ptr(bp), _ptr(Ws), _ptr(bs), _ptr(Wh), _ptr(bh),
-                                 _ptr(logits), _ptr(xw), _ptr(xp), _ptr(xs), _ptr(hs), B, d, m, K, _ptr(ws), ws.numel(), _stream()),
-                   "mlp_fwd")
-    return logits, xw, xp, xs, hs
+                                 _ptr(logits), _ptr(saved), saved.numel(), B, d, m, K, None, 0, _stream()), "mlp_fwd")
+    return logits, saved
+
+
+def _mlp_saved_bytes(B: int, d: int, m: int, K: int) -> int:
+    r8 = lambda x: (x + 7) // 8 * 8
+    pl = lambda rows, ld: (2 * rows * ld * 2 + 255) // 256 * 256
+    return pl(d, d) + pl(d, 2 * d) + pl(m, 2 * d) + pl(K, r8(m)) + pl(B, d) + 2 * pl(B, 2 * d) + pl(B, r8(m)) + 256
 
 
 @mlp.register_fake
 def _(vhat, qhat, Ww, bw, Wp, bp, Ws, bs, Wh, bh):
     _, B, d = vhat.shape
-    f = lambda *s: vhat.new_empty(*s)
-    return f(B, Wh.shape[0]), f(B, d), f(B, 2 * d), f(B, 2 * d), f(B, Ws.shape[0])
+    return vhat.new_empty(B, Wh.shape[0]), vhat.new_empty(_mlp_saved_bytes(B, d, Ws.shape[0], Wh.shape[0]), dtype=torch.uint8)
 
 
 @torch.library.custom_op(f"{NS}::mlp_bwd", mutates_args=("dWw", "dbw", "dWp", "dbp", "dWs", "dbs", "dWh", "dbh"), device_types="cuda")
-def mlp_bwd(dlogits: Tensor, Ww: Tensor, Wp: Tensor, Ws: Tensor, Wh: Tensor, xw: Tensor, xp: Tensor, xs: Tensor, hs: Tensor,
-            dWw: Tensor, dbw: Tensor, dWp: Tensor, dbp: Tensor, dWs: Tensor, dbs: Tensor, dWh: Tensor, dbh: Tensor) -> Tensor:
+def mlp_bwd(dlogits: Tensor, saved: Tensor, d: int, dWw: Tensor, dbw: Tensor, dWp: Tensor, dbp: Tensor, dWs: Tensor, dbs: Tensor,
+            dWh: Tensor, dbh: Tensor) -> Tensor:
     """Returns g [3,B,d] (gradient of q_l + v_l per level); the parameter gradients are WRITTEN into dWw .. dbh."""
-    _cuda_f32(dlogits, Ww, Wp, Ws, Wh, xw, xp, xs, hs, dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh)
-    dlogits, Ww, Wp, Ws, Wh = map(_c, (dlogits, Ww, Wp, Ws, Wh))
+    _cuda_f32(dlogits, dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh)
+    dlogits = _c(dlogits)
     assert all(t.is_contiguous() for t in (dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh))
-    B, d = xw.shape
-    m, K = Ws.shape[0], Wh.shape[0]
+    B, K = dlogits.shape
+    m = dWs.shape[0]
     dev = dlogits.device
     g = torch.empty(3, B, d, dtype=torch.float32, device=dev)
     L = _lib.lib()
     with torch.cuda.device(dev):
         ws = _ws(L.hca_mlp_workspace(B, d, m, K), dev)
-        _lib.check(L.hca_mlp_bwd(_ptr(dlogits), _ptr(Ww), _ptr(Wp), _ptr(Ws), _ptr(Wh), _ptr(xw), _ptr(xp), _ptr(xs), _ptr(hs), _ptr(g),
-                                 _ptr(dWw), _ptr(dbw), _ptr(dWp), _ptr(dbp), _ptr(dWs), _ptr(dbs), _ptr(dWh), _ptr(dbh), B, d, m, K,
-                                 _ptr(ws), ws.numel(), _stream()), "mlp_bwd")
+        _lib.check(L.hca_mlp_bwd(_ptr(dlogits), _ptr(saved), saved.numel(), _ptr(g), _ptr(dWw), _ptr(dbw), _ptr(dWp), _ptr(dbp),
+                                 _ptr(dWs), _ptr(dbs), _ptr(dWh), _ptr(dbh), B, d, m, K, _ptr(ws), ws.numel(), _stream()), "mlp_bwd")
     return g
 
 
 @mlp_bwd.register_fake
-def _(dlogits, Ww, Wp, Ws, Wh, xw, xp, xs, hs, dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh):
-    B, d = xw.shape
-    return dlogits.new_empty(3, B, d)
+def _(dlogits, saved, d, dWw, dbw, dWp, dbp, dWs, dbs, dWh, dbh):
+    return dlogits.new_empty(3, dlogits.shape[0], d)
 
 
 def _mlp_setup(ctx, inputs, output):
     vhat, qhat, Ww, bw, Wp, bp, Ws, bs, Wh, bh = inputs
-    logits, xw, xp, xs, hs = output
-    ctx.save_for_backward(Ww, bw, Wp, bp, Ws, bs, Wh, bh, xw, xp, xs, hs)
+    logits, saved = output
+    ctx.save_for_backward(Ww, bw, Wp, bp, Ws, bs, Wh, bh, saved)
+    ctx.d = vhat.shape[2]
     ctx.set_materialize_grads(False)
 
 
 def _mlp_backward(ctx, dlogits, *_unused):
-    Ww, bw, Wp, bp, Ws, bs, Wh, bh, xw, xp, xs, hs = ctx.saved_tensors
+    *params, saved = ctx.saved_tensors
     if dlogits is None:
         return (None,) * 10
-    gs = [_gbuf(t) for t in (Ww, bw, Wp, bp, Ws, bs, Wh, bh)]
-    g = mlp_bwd(dlogits, Ww, Wp, Ws, Wh, xw, xp, xs, hs, *gs)
+    gs = [_gbuf(t) for t in params]
+    g = mlp_bwd(dlogits, saved, ctx.d, *gs)
     return (g, g, *(_gret(t) for t in gs))                    # q_l + v_l: both receive the same gradient
 
 
