@@ -11,7 +11,7 @@ outs = [torch.empty(2, M, N, dtype=torch.bfloat16, device="cuda") for _ in range
 
 
 def run(label, env):
-    for k in ("HCA_TC_EG", "HCA_TC_STAGES"):
+    for k in ("HCA_TC_EG", "HCA_TC_STAGES", "HCA_TC_PAIR", "HCA_TC_PLDIRECT"):
         os.environ.pop(k, None)
     os.environ.update(env)
     for i in range(5):
@@ -27,6 +27,9 @@ def run(label, env):
     print(f"{label:28s} {us:7.1f} us  {2.0 * M * N * K * 3 / us / 1e6:7.1f} issued TFLOP/s")
 
 
-run("default (2 groups)", {})
-run("1 epilogue group, 3 stages", {"HCA_TC_EG": "1"})
-run("1 group, 2 stages", {"HCA_TC_EG": "1", "HCA_TC_STAGES": "2"})
+run("default (pair 256x256, direct plane stores)", {})
+run("pair, 2 epilogue groups", {"HCA_TC_EG": "2"})
+run("pair, TMA plane stores", {"HCA_TC_PLDIRECT": "0"})
+run("single CTA 128x128", {"HCA_TC_PAIR": "0"})
+run("single CTA, 2 groups", {"HCA_TC_PAIR": "0", "HCA_TC_EG": "2"})
+run("single CTA, TMA plane stores", {"HCA_TC_PAIR": "0", "HCA_TC_PLDIRECT": "0"})

@@ -58,3 +58,33 @@ def test_gemm_tc_large_k_splitk_wgrad_shape():
     D = ops.gemm(A.cuda(), B.cuda(), None, layout="tn", path=1)
     ref = A.double().T @ B.double()
     assert float((D.double().cpu() - ref).norm() / ref.norm()) < 3e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(8192 + 100, 512, 512), (700, 256, 192), (31360, 512, 512)])
+def test_gemm_cta_pair_mode_matches_single_cta(M, N, K):
+    """CTA-pair (cta_group::2, 256x256 tiles) projection kernel: fp32 output through ops.gemm and bf16 hi/lo planes through
+    ops.proj_planes, against fp64 and against the single-CTA kernel (HCA_TC_PAIR=0).  M tails that leave the second CTA of a
+    pair partly / completely out of range are included."""
+    import os
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N + K)
+    A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05, torch.randn(N, generator=g)
+    ref = A.double() @ W.double().T + b.double()
+    prev = os.environ.get("HCA_TC_PAIR")
+    try:
+        res = {}
+        for mode in ("1", "0"):
+            os.environ["HCA_TC_PAIR"] = mode
+            D = ops.gemm(A.cuda(), W.cuda(), b.cuda(), layout="nt", path=1)
+            out = torch.full((2, M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+            ops.proj_planes(ops.split_planes(A.cuda()), ops.split_planes(W.cuda()), b.cuda(), out)
+            torch.cuda.synchronize()
+            res[mode] = (D.double().cpu(), (out[0].double() + out[1].double()).cpu())
+            for r in res[mode]:
+                assert float((r - ref).norm() / ref.norm()) < 3e-5, (mode, M, N, K)
+        assert torch.equal(res["1"][0], res["0"][0]) and torch.equal(res["1"][1], res["0"][1])     # same k order, same accumulator
+    finally:
+        if prev is None:
+            os.environ.pop("HCA_TC_PAIR", None)
+        else:
+            os.environ["HCA_TC_PAIR"] = prev

@@ -152,14 +152,59 @@ __device__ __forceinline__ void row_dots(const __nv_bfloat16* __restrict__ hi, c
     }
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      const float* gg = g_sm + g * g_stride + c;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) out[g] = fmaf(x[k], gg[k], out[g]);
+      // two 16-byte shared loads per vector (lane stride 32 B: conflict-free per quarter warp) instead of eight scalar loads
+      // whose lane stride of 8 words put the whole warp on four banks
+      const float4 g0 = *reinterpret_cast<const float4*>(g_sm + g * g_stride + c);
+      const float4 g1 = *reinterpret_cast<const float4*>(g_sm + g * g_stride + c + 4);
+      out[g] = fmaf(x[0], g0.x, out[g]); out[g] = fmaf(x[1], g0.y, out[g]); out[g] = fmaf(x[2], g0.z, out[g]); out[g] = fmaf(x[3], g0.w, out[g]);
+      out[g] = fmaf(x[4], g1.x, out[g]); out[g] = fmaf(x[5], g1.y, out[g]); out[g] = fmaf(x[6], g1.z, out[g]); out[g] = fmaf(x[7], g1.w, out[g]);
     }
   }
 #pragma unroll
   for (int g = 0; g < NG; ++g) out[g] = warp_sum(out[g]);
 }
+
+// Same dots with the vectors held in REGISTERS: lane l always multiplies the columns 8 l + 256 j, so for d <= 512 the 2 x 8 values of
+// each vector it needs are loaded once per block and reused for every row (no shared-memory traffic in the row loop at all).
+template <int NG>
+struct RowDotRegs {
+  float g[NG][2][8];
+  __device__ __forceinline__ void load(const float* g_sm, int g_stride, int d) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int v = 0; v < NG; ++v)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = lane * 8 + 256 * j + k;
+          g[v][j][k] = c < d ? g_sm[v * g_stride + c] : 0.f;
+        }
+  }
+  // rows are processed TWO at a time so that four 16-byte loads per lane are in flight before the first reduction
+  __device__ __forceinline__ void dots(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int d, float (&out)[NG]) const {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int v = 0; v < NG; ++v) out[v] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = lane * 8 + 256 * j;
+      if (c < d) {
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + c));
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + c));
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float x0 = bf2f_lo(hw[k]) + bf2f_lo(lw[k]), x1 = bf2f_hi(hw[k]) + bf2f_hi(lw[k]);
+#pragma unroll
+          for (int v = 0; v < NG; ++v) out[v] = fmaf(x1, g[v][j][2 * k + 1], fmaf(x0, g[v][j][2 * k], out[v]));
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NG; ++v) out[v] = warp_sum(out[v]);
+  }
+};
 
 // one warp: ds = a * (da - <a, da>) ; *dc += sum ds
 __device__ __forceinline__ void softmax_bwd_warp(const float* __restrict__ a, const float* da_sm, int L, float* __restrict__ ds_out,
@@ -185,9 +230,9 @@ __global__ void __launch_bounds__(256) attn_bwd_dots_kernel(const __nv_bfloat16*
                                                             const __nv_bfloat16* __restrict__ Qp, int64_t q_ps,
                                                             const float* __restrict__ gv, const float* __restrict__ gq,
                                                             float* __restrict__ dav, float* __restrict__ daq, int B, int N, int T, int d) {
-  extern __shared__ float sm[];
-  float* gv_sm = sm;                  // [3][d]
-  float* gq_sm = sm + 3 * d;          // [3][d]
+  extern __shared__ __align__(16) float sm16[];
+  float* gv_sm = sm16;                // [3][d]
+  float* gq_sm = sm16 + 3 * d;        // [3][d]
   const int b = blockIdx.x, sp = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) {
     const int l = i / d, c = i - l * d;
@@ -195,13 +240,27 @@ __global__ void __launch_bounds__(256) attn_bwd_dots_kernel(const __nv_bfloat16*
     gq_sm[i] = gq[((int64_t)l * B + b) * d + c];
   }
   __syncthreads();
-  for (int n = sp * nw + w; n < N; n += nw * ATTN_SPLIT) {
-    const __nv_bfloat16* hi = Vp + ((int64_t)b * N + n) * d;
-    float o[3];
-    row_dots<3>(hi, hi + v_ps, d, gv_sm, d, o);
-    if (lane == 0) {
-      float* dst = dav + (int64_t)b * 3 * N + n;
-      dst[0] = o[0]; dst[N] = o[1]; dst[2 * N] = o[2];
+  if (d <= 512) {
+    RowDotRegs<3> rd;
+    rd.load(gv_sm, d, d);
+    for (int n = sp * nw + w; n < N; n += nw * ATTN_SPLIT) {
+      const __nv_bfloat16* hi = Vp + ((int64_t)b * N + n) * d;
+      float o[3];
+      rd.dots(hi, hi + v_ps, d, o);
+      if (lane == 0) {
+        float* dst = dav + (int64_t)b * 3 * N + n;
+        dst[0] = o[0]; dst[N] = o[1]; dst[2 * N] = o[2];
+      }
+    }
+  } else {
+    for (int n = sp * nw + w; n < N; n += nw * ATTN_SPLIT) {
+      const __nv_bfloat16* hi = Vp + ((int64_t)b * N + n) * d;
+      float o[3];
+      row_dots<3>(hi, hi + v_ps, d, gv_sm, d, o);
+      if (lane == 0) {
+        float* dst = dav + (int64_t)b * 3 * N + n;
+        dst[0] = o[0]; dst[N] = o[1]; dst[2 * N] = o[2];
+      }
     }
   }
   for (int r = sp * nw + w; r < 3 * T; r += nw * ATTN_SPLIT) {

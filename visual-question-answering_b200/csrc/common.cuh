@@ -83,4 +83,20 @@ __device__ __forceinline__ float warp_max(float v) {
 // options
 bool use_tc();
 
+// ---- side stream -------------------------------------------------------------------------------------
+// Independent branches of one entry point (e.g. the weight-gradient products of the classifier, which nothing later in the
+// call consumes) run on a per-device helper stream: fork() makes the helper wait for the work enqueued on `main` so far,
+// join() makes `main` wait for the helper.  Both are event record / wait pairs, so under CUDA-graph capture they become
+// parallel branches of the graph.  The helper is created on the first call made OUTSIDE a capture; until then (or with
+// HCA_SIDE_STREAM=0) `stream()` is `main` itself and everything stays serial.
+struct SideStream {
+  explicit SideStream(cudaStream_t main);
+  cudaStream_t stream() const { return side_ ? side_ : main_; }
+  int fork();                 // helper waits for main (call again after each producer the helper depends on)
+  int join();                 // main waits for the helper
+ private:
+  cudaStream_t main_, side_ = nullptr;
+  cudaEvent_t ev_[2] = {nullptr, nullptr};
+};
+
 }  // namespace hca

@@ -34,6 +34,7 @@ struct TcParams {
   int64_t d_gs;
   int accumulate, atomic;
   int tma_store;            // fp32 output goes through smem + TMA tile store / reduce-add
+  int pl_direct;            // bf16 planes are stored straight from registers (64 B per row and plane), not staged for a TMA store
   // bf16 hi/lo planes output
   __nv_bfloat16* P;
   int64_t p_ld, p_ps, p_sb;
@@ -88,11 +89,17 @@ __device__ __forceinline__ float col_reduce32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int BN, int P, bool A_MN, bool B_MN, int BK>
+// CG = 2: CTA-pair mode (cluster of 2, tcgen05 cta_group::2).  The pair computes a 256 x BN tile: each CTA loads its own 128 rows
+// of A and HALF of the B tile, the leader issues M = 256 MMAs that read both halves, and each CTA drains its own 128 accumulator
+// lanes.  Per output element only half the operand bytes cross the L2 -> SM fabric -- the measured limit of the big K-major
+// products (profiles/r1c_pv_gemm_ncu_full.md: 83 B/clk/SM of operand fill against a ~43 B/clk/SM chip-wide L2 cap).
+template <int BN, int P, bool A_MN, bool B_MN, int BK, int CG = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   static_assert(BK == 64 || (BK == 32 && A_MN && B_MN), "BK = 32 k-blocks are for MN-major operand pairs (short contractions)");
+  static_assert(CG == 1 || (CG == 2 && BN == 256 && !A_MN && !B_MN && BK == 64), "CTA-pair mode: K-major operands, 256-wide tiles");
   constexpr int A_TILE_BYTES = BM * BK * 2;
-  constexpr int B_TILE_BYTES = BN * BK * 2;
+  constexpr int B_ROWS = BN / CG;                         // rows of the B tile this CTA loads
+  constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
   constexpr uint32_t MN_CHUNK_BYTES = 64 * BK * 2;       // one TMA box of an MN-major tile: [BK k][64 mn]
   constexpr uint32_t stage_bytes = P * (A_TILE_BYTES + B_TILE_BYTES);
   constexpr int CHUNKS = BN / 32;
@@ -105,13 +112,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   // per epilogue group: this tile's per-column vectors
   __shared__ __align__(16) float bias_sm[NUM_EG][BNV];      // bias slice (per batch entry)
   __shared__ __align__(16) float colv_sm[NUM_EG][BNV];      // colv (ROWDOT / DZ)
-  __shared__ __align__(16) float r1_sm[NUM_EG][4][BNV];     // rank-1 column vectors, one per row group
+  __shared__ __align__(16) float r1_sm[NUM_EG][CG == 2 ? 1 : 4][BNV];   // rank-1 column vectors, one per row group (not in pair mode)
   __shared__ float colred_sm[NUM_EG][BNV];                  // column partial sums of the group's four warps
 
   // warp index through a shuffle: provably warp-uniform for ptxas, so the role branches below are uniform control flow and
   // the MMA descriptors live in uniform registers (otherwise every tcgen05.mma pays an ELECT + VOTEU + 4x R2UR.BROADCAST
   // sequence, ~250 cycles per instruction, measured)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  // pair mode: rank inside the pair, and the persistent schedule walks pair tiles with the pair index / pair count
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int sched0 = CG == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int sched_step = CG == 2 ? (int)cluster_nclusters_x() : (int)gridDim.x;
 
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[MAX_STAGES + s]); };
@@ -128,7 +139,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     t /= p.tiles_m;
     const int ks = t % p.splitk;
     c.z = t / p.splitk;
-    c.m0 = mt * BM;
+    c.m0 = mt * (BM * CG) + rank * BM;
     c.n0 = nt * BN;
     c.kb_begin = ks * p.kb_per_split;
     c.num_kb = min(p.kb_total, c.kb_begin + p.kb_per_split) - c.kb_begin;
@@ -150,7 +161,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
       // one arrival per epilogue warp that drains the buffer: BN = 32 tiles go to ONE group each, wider tiles to all groups
-      mbar_init(tmem_empty_bar(a), BN == 32 ? 4 : 4 * p.n_eg);
+      // (pair mode: the leader's barrier collects the epilogue warps of both CTAs)
+      mbar_init(tmem_empty_bar(a), BN == 32 ? 4 : 4 * p.n_eg * CG);
     }
     for (int g = 0; g < NUM_EG; ++g) mbar_init(aux_bar(g), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -160,9 +172,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     if (p.P && BN != 32) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.DP) : "memory");
     if (p.aux_kind && BN != 32) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.AUX) : "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr_smem), TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_2sm(smem_u32(&tmem_ptr_smem), TMEM_COLS);
+    else tmem_alloc(smem_u32(&tmem_ptr_smem), TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_ptr_smem, 0);
   if (tl && threadIdx.x == 0) tl[1] = clock64();
@@ -172,10 +188,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     if (elect_one_sync() && !(p.dbg & 1)) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = sched0; t < p.total_tiles; t += sched_step) {
         const TileCoord tc = decode(t);
         for (int it = 0; it < tc.num_kb; ++it) {
           mbar_spin(empty_bar(s), ph ^ 1);
+          if constexpr (CG == 2) {
+            // both CTAs' loads report to the leader's barrier (the MMA issuer waits there): it expects the bytes of both
+            if (rank == 0) mbar_expect_tx(full_bar(s), 2 * stage_bytes);
+            const int k0 = (tc.kb_begin + it) * BK;
+#pragma unroll
+            for (int pl = 0; pl < P; ++pl) {
+              tma_load_4d_2sm(a_tile(s, pl), &maps.A, full_bar(s), k0, tc.m0, pl, 0);
+              tma_load_4d_2sm(b_tile(s, pl), &maps.B, full_bar(s), k0, tc.n0 + rank * B_ROWS, pl, 0);
+            }
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+            continue;
+          }
           mbar_expect_tx(full_bar(s), stage_bytes);
           const int kb = tc.kb_begin + it;
           const bool second = kb >= p.kb1;                    // chained second operand pair
@@ -202,13 +230,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
+      if constexpr (CG == 2) {
+        // drain: every MMA-completion signal multicast to this CTA's barriers has landed before the CTA may exit
+        for (int i = 0; i < p.stages; ++i) {
+          mbar_spin(empty_bar(s), ph ^ 1);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (one elected lane, uniform datapath)
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6), a=bf16 [7,10), b=bf16 [10,13),
     // a_major bit 15, b_major bit 16, N>>3 [17,23), M>>4 [24,29)
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     // smem descriptor halves (cute::UMMA::SmemDescriptor): hi = SBO(1024 B) | version 1 | SWIZZLE_128B, constant;
     // lo = (addr >> 4) | (LBO >> 4) << 16.  K-major: LBO unused (16 B), K slice = +32 B.  MN-major: LBO = one [BK k][64 mn]
     // box between 64-wide MN chunks, K slice of 16 rows = +2048 B.
@@ -218,14 +253,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     // The whole loop runs in ONE elected thread with inline waits: inside such a region every value is trivially warp-uniform,
     // so ptxas builds the descriptors with uniform-datapath adds and issues the UTCHMMAs back to back.  (Per-instruction
     // elect / predicate forms cost ELECT + VOTEU + 4-5 R2UR per MMA, ~75 cycles each: that, not L2 bandwidth, bound the mainloop.)
-    if (elect_one_sync()) {
+    if (rank == 0 && elect_one_sync()) {
       const uint32_t tm = *reinterpret_cast<volatile uint32_t*>(&tmem_ptr_smem);
       const uint32_t a_base = ((smem_base & 0x3FFFFu) >> 4) | a_lbo;
       const uint32_t b_base = (((smem_base + P * A_TILE_BYTES) & 0x3FFFFu) >> 4) | b_lbo;
       int s = 0;
       uint32_t ph = 0;
       int tile_it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
+      for (int t = sched0; t < p.total_tiles; t += sched_step, ++tile_it) {
         const TileCoord tc = decode(t);
         const int acc = tile_it & 1;
         mbar_spin(tmem_empty_bar(acc), ((tile_it >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator buffer
@@ -247,16 +282,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               for (int i = 0; i < P; ++i) {
 #pragma unroll
                 for (int j = 0; j < P - i; ++j) {
+                  if constexpr (CG == 2)
+                    umma_bf16_one_2sm<desc_hi, idesc>(d_tmem, au + i * (A_TILE_BYTES >> 4) + ks * a_kstep,
+                                                      bu + j * (B_TILE_BYTES >> 4) + ks * b_kstep, (ks | i | j) != 0 ? 1u : (it == 0 ? 0u : 1u));
+                  else
                   umma_bf16_one<desc_hi, idesc>(d_tmem, au + i * (A_TILE_BYTES >> 4) + ks * a_kstep, bu + j * (B_TILE_BYTES >> 4) + ks * b_kstep,
                                                 (ks | i | j) != 0 ? 1u : (it == 0 ? 0u : 1u));
                 }
               }
             }
           }
-          umma_commit(empty_bar(s));            // frees the smem stage once the MMAs above have read it
+          if constexpr (CG == 2) umma_commit_2sm(empty_bar(s));   // frees the stage in both CTAs
+          else umma_commit(empty_bar(s));       // frees the smem stage once the MMAs above have read it
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(tmem_full_bar(acc));        // accumulator complete -> epilogue
+        if constexpr (CG == 2) umma_commit_2sm(tmem_full_bar(acc));   // accumulator halves complete -> both epilogues
+        else umma_commit(tmem_full_bar(acc));   // accumulator complete -> epilogue
         if (tl && tile_it == 0) tl[3] = clock64();
       }
     }
@@ -344,7 +385,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       // ------------------------------------------------------------------ standard epilogue
       const bool do_f32 = (p.D != nullptr) && p.mode != TC_EPI_ROWDOT;
       const bool do_pl = (p.P != nullptr) && p.mode != TC_EPI_ROWDOT;
-      const bool stage_tma = (do_f32 && p.tma_store) || do_pl;
+      const bool pl_direct = p.pl_direct != 0;
+      const bool stage_tma = (do_f32 && p.tma_store) || (do_pl && !pl_direct);
       const bool want_colred = (p.red_col != nullptr);
       float* const bias_s = bias_sm[eg];
       float* const colv_s = colv_sm[eg];
@@ -366,11 +408,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       uint32_t aux_n = 0;                     // addend tiles this group has consumed (mbarrier phase)
       // (at, ac): the next (tile, chunk) whose addend tile has not been requested yet; one load in flight per group.
       // atc caches the decoded coordinates of tile `at` (the decode costs several integer divisions)
-      int at = blockIdx.x, ac = eg;
+      int at = sched0, ac = eg;
       TileCoord atc = decode(at < p.total_tiles ? at : 0);
       auto settle = [&]() {
         while (at < p.total_tiles && ac >= min(CHUNKS, (p.N - atc.n0 + 31) / 32)) {
-          at += gridDim.x;
+          at += sched_step;
           ac = eg;
           if (at < p.total_tiles) atc = decode(at);
         }
@@ -390,7 +432,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         settle();
         if (leader && at < p.total_tiles) issue_aux();
       }
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
+      for (int t = sched0; t < p.total_tiles; t += sched_step, ++tile_it) {
         const TileCoord tc = decode(t);
         const int acc = tile_it & 1;
         const int row = tc.m0 + r;
@@ -407,10 +449,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             bias_s[j] = (bias && ok) ? __ldg(bias + tc.n0 + j) : 0.f;
             colv_s[j] = (p.colv && ok) ? __ldg(p.colv + tc.n0 + j) : 0.f;
             if (tc.n0 != staged_n0) colred_s[j] = 0.f;
-            if (p.r1col) {
-              const int ng = p.r1_rpg > 0 ? min(4, (p.M + p.r1_rpg - 1) / p.r1_rpg) : 1;
-              for (int g = 0; g < ng; ++g)
-                r1_sm[eg][g][j] = ok ? __ldg(p.r1col + (int64_t)tc.z * p.r1col_sb + (int64_t)g * p.r1_gs + tc.n0 + j) : 0.f;
+            if constexpr (CG == 1) {
+              if (p.r1col) {
+                const int ng = p.r1_rpg > 0 ? min(4, (p.M + p.r1_rpg - 1) / p.r1_rpg) : 1;
+                for (int g = 0; g < ng; ++g)
+                  r1_sm[eg][g][j] = ok ? __ldg(p.r1col + (int64_t)tc.z * p.r1col_sb + (int64_t)g * p.r1_gs + tc.n0 + j) : 0.f;
+              }
             }
           }
           staged_n0 = tc.n0;
@@ -425,7 +469,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         if (eg >= nchunks) {                                                // no chunk of this tile for this group
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_leader(tmem_empty_bar(acc));
+            else mbar_arrive(tmem_empty_bar(acc));
+          }
         }
         float* drow = nullptr;
         if (p.D && !p.tma_store) {
@@ -454,7 +501,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           if (c + neg >= nchunks) {                                   // this group's last read of the accumulator: hand it back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_leader(tmem_empty_bar(acc));
+              else mbar_arrive(tmem_empty_bar(acc));
+            }
           }
           float ax[32];
           if (p.aux_kind == 1) {                                      // this thread's row of the fp32 addend tile (128-byte swizzle)
@@ -513,9 +563,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
           }
-          if (p.r1col) {
+          if constexpr (CG == 1) {
+            if (p.r1col) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaf(rv, r1_sm[eg][rgroup][c * 32 + j], f[j]);
+              for (int j = 0; j < 32; ++j) f[j] = fmaf(rv, r1_sm[eg][rgroup][c * 32 + j], f[j]);
+            }
           }
           if (p.aux_kind && p.aux_mode == TC_AUX_MUL_1MX2) {
 #pragma unroll
@@ -564,7 +616,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                              : "memory");
               }
             }
-            if (do_pl) {
+            if (do_pl && !pl_direct) {
               // hi / lo bf16 planes of the same chunk: two [128 rows][64 B] tiles in the 64-byte swizzle
               const uint32_t sb = pstore_base + sbuf * CHUNK_BYTES + (uint32_t)r * 64u;
 #pragma unroll
@@ -595,13 +647,66 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 if (p.atomic || p.accumulate) tma_reduce_add_4d(&maps.D, sb, col0, tc.m0, 0, tc.z / p.d_zd);
                 else tma_store_4d(&maps.D, sb, col0, tc.m0, 0, tc.z / p.d_zd);
               }
-              if (do_pl) {
+              if (do_pl && !pl_direct) {
                 const uint32_t sb = pstore_base + sbuf * CHUNK_BYTES;
                 tma_store_4d(&maps.DP, sb, col0, tc.m0, 0, tc.z);
                 tma_store_4d(&maps.DP, sb + CHUNK_BYTES / 2, col0, tc.m0, 1, tc.z);
               }
               tma_store_commit();
             }
+          }
+          if (do_pl && pl_direct) {
+            // hi / lo planes through a WARP-PRIVATE staging tile (32 rows x 64 B, 64-byte swizzle) and coalesced 16-byte global
+            // stores: lane l writes segment l & 3 of row 8 i + (l >> 2), so one instruction covers 8 rows x 64 contiguous bytes (whole
+            // sectors).  Only __syncwarp orders it: no group barrier, no proxy fence, and no wait for a TMA store that sits in the
+            // engine's queue behind the mainloop's operand loads (the timeline showed 0.5-1.8k cycles per chunk there).
+            const uint32_t wst = smem_base + p.off_pstore + (uint32_t)((eg * 4 + q) * 2048);
+            uint32_t hl[2][16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float x0 = f[2 * k], x1 = f[2 * k + 1];
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+              const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __low2float(hh), x1 - __high2float(hh));
+              hl[0][k] = *reinterpret_cast<const uint32_t*>(&hh);
+              hl[1][k] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            const int rr = lane >> 2, cc = lane & 3;
+            __nv_bfloat16* pbase = p.P + (int64_t)tc.z * p.p_sb + (int64_t)(tc.m0 + q * 32) * p.p_ld + col0 + cc * 8;
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+              __syncwarp();                                           // the previous readers of the staging tile are done
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) * 16)),
+                             "r"(hl[pl][4 * j]), "r"(hl[pl][4 * j + 1]), "r"(hl[pl][4 * j + 2]), "r"(hl[pl][4 * j + 3])
+                             : "memory");
+              }
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int R = 8 * i + rr;
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                             : "r"(wst + (uint32_t)R * 64u + (uint32_t)((cc ^ ((R >> 1) & 3)) * 16)));
+                if (tc.m0 + q * 32 + R < p.M) {
+                  __nv_bfloat16* dst = pbase + (int64_t)pl * p.p_ps + (int64_t)R * p.p_ld;
+                  const int colg = col0 + cc * 8;
+                  if (colg + 8 <= p.N) {
+                    *reinterpret_cast<uint4*>(dst) = v;
+                  } else {
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e2 = 0; e2 < 8; ++e2)
+                      if (colg + e2 < p.N) reinterpret_cast<unsigned short*>(dst)[e2] = (unsigned short)(w[e2 >> 1] >> ((e2 & 1) * 16));
+                  }
+                }
+              }
+            }
+          }
+          if (!stage_tma) {
+            HCA_TL_STAMP();                                           // 3 / 4: math done, planes stored (no TMA staging on this path)
+            HCA_TL_STAMP();
           }
           if (drow && row_ok) {                                       // unaligned fp32 output (e.g. K = 1001 logits): direct stores
 #pragma unroll
@@ -629,9 +734,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   }
   __syncthreads();
   if (tl && threadIdx.x == 0) tl[6] = clock64();
+  if constexpr (CG == 2) cluster_sync_all();   // remote arrivals and the leader's reads of the peer's shared memory are over
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -851,8 +958,30 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   HCA_CHECK_ARG(P >= 2 && P <= 3 && M > 0 && N > 0 && K > 0 && splitk >= 1 && batch >= 1, "gemm_tc: bad sizes");
   HCA_CHECK_ARG(batch == 1 || splitk == 1, "gemm_tc: split-K is for un-batched products");
   HCA_CHECK_ARG((A2 == nullptr) == (B2 == nullptr), "gemm_tc: the chained operand pair needs both A2 and B2");
-  const int BN = e.transposed ? 32 : 128;
   HCA_CHECK_ARG(!e.transposed || P == 2, "gemm_tc: the transposed epilogue is instantiated for P = 2");
+  // CTA-pair mode (cta_group::2, 256 x 256 tiles per pair): the large K-major products with a plain epilogue, where the L2 -> SM
+  // operand fill is the limit.  HCA_TC_PAIR=0 disables it, =1 also takes smaller M (tests).
+  bool pair = !e.transposed && P == 2 && !A.mn_major && !B.mn_major && !A2 && splitk == 1 && batch == 1 && (N % 256) == 0 &&
+              M >= 8192 && K >= 256 && e.mode == TC_EPI_STORE && e.aux_mode == TC_AUX_NONE && !e.r1col && !e.mulx && e.d_groups <= 1 &&
+              A.nbatch <= 1 && B.nbatch <= 1 && num_sms() >= 2;
+  if (pair) {
+    // wave quantisation: a pair tile is four single tiles of MMA time on two SMs.  Take the pair schedule only when its last,
+    // partly filled wave does not cost more than the fabric traffic it saves (PV, M = 31360: 4 pair waves vs 7 single waves;
+    // PQ, M = 12480: 2 pair waves vs 3 single ones -- measured slower as a pair)
+    const int64_t t2 = (int64_t)((M + 255) / 256) * (N / 256), t1 = (int64_t)((M + 127) / 128) * ((N + 127) / 128);
+    const int64_t nc = num_sms() / 2, w2 = (t2 + nc - 1) / nc, w1 = (t1 + num_sms() - 1) / num_sms();
+    if ((double)(2 * w2) > 1.15 * (double)w1) pair = false;
+  }
+  {
+    const char* ev = getenv("HCA_TC_PAIR");
+    const int pair_env = ev ? atoi(ev) : -1;
+    if (pair_env == 0) pair = false;
+    if (pair_env == 1 && !e.transposed && P == 2 && !A.mn_major && !B.mn_major && !A2 && splitk == 1 && batch == 1 && (N % 256) == 0 &&
+        e.mode == TC_EPI_STORE && e.aux_mode == TC_AUX_NONE && !e.r1col && !e.mulx && e.d_groups <= 1 && A.nbatch <= 1 && B.nbatch <= 1)
+      pair = true;
+  }
+  const int BN = e.transposed ? 32 : (pair ? 256 : 128);
+  const int CGn = pair ? 2 : 1;
   const TcOperand* ops[4] = {&A, &B, A2, B2};
   for (const TcOperand* o : ops) {
     if (!o) continue;
@@ -868,7 +997,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   const int BK = (A.mn_major && B.mn_major && P == 2 && BN == 128 && !A2 && K <= 96) ? 32 : 64;
   TcMaps maps;
   HCA_TRY(make_tmap(&maps.A, A, P, A.mn_major ? BK : BM));
-  HCA_TRY(make_tmap(&maps.B, B, P, B.mn_major ? BK : BN));
+  HCA_TRY(make_tmap(&maps.B, B, P, B.mn_major ? BK : BN / CGn));
   if (A2) {
     HCA_TRY(make_tmap(&maps.A2, *A2, P, A2->mn_major ? BK : BM));
     HCA_TRY(make_tmap(&maps.B2, *B2, P, B2->mn_major ? BK : BN));
@@ -919,15 +1048,19 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
     maps.AUX = maps.A;
   }
   // shared memory carve: pipeline stages first, then the epilogue staging areas this launch needs (per epilogue group)
-  const uint32_t stage_bytes = (uint32_t)P * (uint32_t)(BM * BK * 2 + BN * BK * 2);
-  // (static shared memory + the 1024-byte alignment slack take ~9 KB of the 227 KB)
-  const uint32_t avail = SMEM_LIMIT - 9216;
-  const int n_out = (!e.transposed && want_f32 && tma_store ? 1 : 0) + (!e.transposed && want_pl ? 1 : 0);
+  const uint32_t stage_bytes = (uint32_t)P * (uint32_t)(BM * BK * 2 + (BN / CGn) * BK * 2);
+  // (static shared memory + the 1024-byte alignment slack take ~9 KB of the 227 KB; ~10.5 KB with the 256-wide per-column vectors)
+  const uint32_t avail = SMEM_LIMIT - (pair ? 11264 : 9216);
+  // (only behind a long mainloop: there a TMA store queues behind the operand loads; the single-k-block products keep the
+  // double-buffered asynchronous TMA stores their epilogue-bound tiles were tuned with)
+  bool pl_direct = want_pl && !e.transposed && p.kb_total >= 4;
+  { const char* ev = getenv("HCA_TC_PLDIRECT"); if (ev && atoi(ev) == 0) pl_direct = false; }
+  const int n_out = (!e.transposed && want_f32 && tma_store ? 1 : 0) + (!e.transposed && want_pl && !pl_direct ? 1 : 0);
   const bool has_aux_buf = !e.transposed && aux_kind;
   p.kb1 = (K + BK - 1) / BK;
   p.kb_total = p.kb1 + (A2 ? (K2 + BK - 1) / BK : 0);
   auto stages_for = [&](int neg, int nbuf) {
-    const uint32_t epi = (uint32_t)neg * ((uint32_t)(n_out * nbuf) + (has_aux_buf ? 1u : 0u)) * CHUNK_BYTES;
+    const uint32_t epi = (uint32_t)neg * ((uint32_t)(n_out * nbuf) + (has_aux_buf ? 1u : 0u)) * CHUNK_BYTES + (pl_direct ? (uint32_t)neg * 8192u : 0u);
     return epi >= avail ? 0 : (int)((avail - epi) / stage_bytes);
   };
   // Two epilogue groups when the epilogue is the long pole (fused math / plane conversion behind a short mainloop) and the
@@ -938,6 +1071,8 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   const bool epi_heavy = epi_math || (want_pl && p.kb_total < 8);
   int neg = 1, nbuf = 2;
   if (epi_heavy && stages_for(2, 1) >= (p.kb_total == 1 ? 1 : 2)) neg = 2;
+  // planes-only output through the warp-private staging costs 8 KB per group: take the second group whenever it is free
+  if (neg == 1 && pl_direct && n_out == 0 && std::min(stages_for(2, 1), MAX_STAGES) >= std::min(stages_for(1, 1), MAX_STAGES)) neg = 2;
   { const char* ev = getenv("HCA_TC_EG"); if (ev && (atoi(ev) == 1 || atoi(ev) == 2)) neg = atoi(ev); }
   // single-k-block tiles (the K = T products) need no operand pipelining beyond the TMEM double buffer: one stage is enough
   // there, which leaves room to double-buffer the epilogue staging -- their long pole
@@ -957,13 +1092,14 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   p.n_eg = neg;
   uint32_t off = (uint32_t)stages * stage_bytes;
   if (!e.transposed && want_f32 && tma_store) { p.off_store = off; off += (uint32_t)(neg * nbuf) * CHUNK_BYTES; }
-  if (!e.transposed && want_pl) { p.off_pstore = off; off += (uint32_t)(neg * nbuf) * CHUNK_BYTES; }
+  if (!e.transposed && want_pl && !pl_direct) { p.off_pstore = off; off += (uint32_t)(neg * nbuf) * CHUNK_BYTES; }
+  if (pl_direct) { p.off_pstore = off; off += (uint32_t)neg * 8192u; }      // 2 KB of warp-private staging per epilogue warp
   if (has_aux_buf) { p.off_aux = off; off += (uint32_t)neg * CHUNK_BYTES; }
   if (splitk > p.kb_total) splitk = p.kb_total;
   p.kb_per_split = (p.kb_total + splitk - 1) / splitk;
   splitk = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;      // no empty split
   p.splitk = splitk;
-  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_m = (M + BM * CGn - 1) / (BM * CGn);
   p.tiles_n = (N + BN - 1) / BN;
   const int64_t total = (int64_t)p.tiles_m * p.tiles_n * splitk * batch;
   HCA_CHECK_ARG(total < (1LL << 30), "gemm_tc: too many tiles");
@@ -976,6 +1112,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   p.accumulate = e.accumulate;
   p.atomic = (splitk > 1 || (p.d_zd > 1 && want_f32)) ? 1 : 0;
   p.tma_store = tma_store ? 1 : 0;
+  p.pl_direct = pl_direct ? 1 : 0;
   p.P = want_pl ? e.P.p : nullptr; p.p_ld = e.P.ld; p.p_ps = e.P.plane_stride; p.p_sb = e.P.batch_stride;
   p.bias = e.bias; p.bias_sb = e.bias_batch_stride;
   p.act_tanh = e.act_tanh; p.mulx = e.mulx; p.mulx_ld = e.mulx_ld;
@@ -1007,9 +1144,11 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   p.timeline_ctas = g_timeline_ctas;
   if (g_timeline) ++g_timeline_seen;
   const size_t smem = (size_t)off + 1024;
-  HCA_CHECK_ARG(smem <= (size_t)SMEM_LIMIT - 8192, "gemm_tc: shared memory carve exceeds the limit");
+  const size_t smem_cap = (size_t)SMEM_LIMIT - (pair ? 10240 : 8192);
+  HCA_CHECK_ARG(smem <= smem_cap, "gemm_tc: shared memory carve exceeds the limit");
   int ctas = num_sms();
-  if (p.total_tiles < ctas) ctas = p.total_tiles;
+  if (pair) ctas = 2 * std::min(num_sms() / 2, p.total_tiles);
+  else if (p.total_tiles < ctas) ctas = p.total_tiles;
   typedef void (*KernelFn)(const TcMaps, const TcParams);
   KernelFn fn = nullptr;
   const int combo = (A.mn_major ? 2 : 0) + (B.mn_major ? 1 : 0);    // 0 = NT (K,K), 1 = NN (K,MN), 2 = (MN,K), 3 = TN (MN,MN)
@@ -1020,13 +1159,28 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   HCA_TC_CASE(3, 128, 3, 0, false, false, 64) HCA_TC_CASE(4, 128, 3, 1, false, true, 64) HCA_TC_CASE(5, 128, 3, 3, true, true, 64)
   HCA_TC_CASE(6, 32, 2, 0, false, false, 64) HCA_TC_CASE(7, 32, 2, 2, true, false, 64) HCA_TC_CASE(8, 128, 2, 3, true, true, 32)
 #undef HCA_TC_CASE
+  if (pair) { fn = gemm_tc_kernel<256, 2, false, false, 64, 2>; slot = 9; }
   HCA_CHECK_ARG(fn != nullptr, "gemm_tc: this (BN, P, layout) combination is not instantiated (BN=%d P=%d combo=%d)", BN, P, combo);
-  static bool attr_set[9] = {};
+  static bool attr_set[10] = {};
   if (!attr_set[slot]) {
-    HCA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 8192));
+    HCA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
     attr_set[slot] = true;
   }
-  fn<<<ctas, NUM_THREADS, smem, s>>>(maps, p);
+  if (pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HCA_CUDA(cudaLaunchKernelEx(&cfg, fn, maps, p));
+  } else {
+    fn<<<ctas, NUM_THREADS, smem, s>>>(maps, p);
+  }
   HCA_LAUNCHED();
   return 0;
 }

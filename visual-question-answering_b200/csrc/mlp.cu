@@ -219,24 +219,33 @@ extern "C" int hca_mlp_bwd(const float* dlogits, const void* saved, size_t saved
   float* g_p = g + (size_t)B * d;
   float* g_s = g + (size_t)2 * B * d;
 
+  // The four weight-gradient products feed nothing later in this call: they run on the helper stream, next to the chain of
+  // data-gradient products (each 20-64 CTAs: together they still do not fill the 148 SMs).
+  SideStream side(s);
+  cudaStream_t sw = side.stream();
   // W_h: planes of dlogits + db_h in one pass; dW_h; dz_s = (dlogits W_h) * (1 - h_s^2) with db_s
   split_colsum_kernel<<<(K + 31) / 32, 256, 0, s>>>(dlogits, K, B, K, dl.p, dl.ld, dl.ps, dbh);
   HCA_LAUNCHED();
   HCA_TRY(zero_async(dbs, (size_t)mlp * 4, s));
   HCA_TRY(zero_async(dbp, (size_t)d * 4, s));
   HCA_TRY(zero_async(dbw, (size_t)d * 4, s));
-  HCA_TRY(bwd_weight(dl, K, sv.hs, mlp, B, dWh, s));
+  HCA_TRY(side.fork());
+  HCA_TRY(bwd_weight(dl, K, sv.hs, mlp, B, dWh, sw));
   HCA_TRY(bwd_data(sv.Wh, K, 0, mlp, dl, B, &sv.hs, 0, &dzs, nullptr, dbs, s));
   // W_s: dx_s = dz_s W_s : left half -> g_s, right half * (1 - h_p^2) -> dz_p
-  HCA_TRY(bwd_weight(dzs, mlp, sv.xs, 2 * d, B, dWs, s));
-  HCA_TRY(bwd_data(sv.Ws, mlp, 0, d, dzs, B, nullptr, 0, nullptr, g_s, nullptr, s));
+  HCA_TRY(side.fork());
+  HCA_TRY(bwd_weight(dzs, mlp, sv.xs, 2 * d, B, dWs, sw));
   HCA_TRY(bwd_data(sv.Ws, mlp, d, d, dzs, B, &sv.xs, d, &dzp, nullptr, dbp, s));
   // W_p
-  HCA_TRY(bwd_weight(dzp, d, sv.xp, 2 * d, B, dWp, s));
-  HCA_TRY(bwd_data(sv.Wp, d, 0, d, dzp, B, nullptr, 0, nullptr, g_p, nullptr, s));
+  HCA_TRY(side.fork());
+  HCA_TRY(bwd_weight(dzp, d, sv.xp, 2 * d, B, dWp, sw));
+  HCA_TRY(bwd_data(sv.Ws, mlp, 0, d, dzs, B, nullptr, 0, nullptr, g_s, nullptr, sw));    // off the critical path too
   HCA_TRY(bwd_data(sv.Wp, d, d, d, dzp, B, &sv.xp, d, &dzw, nullptr, dbw, s));
   // W_w
-  HCA_TRY(bwd_weight(dzw, d, sv.xw, d, B, dWw, s));
+  HCA_TRY(side.fork());
+  HCA_TRY(bwd_weight(dzw, d, sv.xw, d, B, dWw, sw));
+  HCA_TRY(bwd_data(sv.Wp, d, 0, d, dzp, B, nullptr, 0, nullptr, g_p, nullptr, sw));
   HCA_TRY(bwd_data(sv.Ww, d, 0, d, dzw, B, nullptr, 0, nullptr, g_w, nullptr, s));
+  HCA_TRY(side.join());
   return 0;
 }

@@ -32,6 +32,49 @@ bool use_tc() {
   return m == 1;
 }
 
+namespace {
+struct SideRes {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool ok = false, tried = false;
+};
+SideRes g_side[64];
+}  // namespace
+
+SideStream::SideStream(cudaStream_t main) : main_(main) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("HCA_SIDE_STREAM"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+  if (!enabled) return;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return; }
+  SideRes& r = g_side[dev];
+  if (!r.tried) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(main, &st) != cudaSuccess) { cudaGetLastError(); return; }
+    if (st != cudaStreamCaptureStatusNone) return;        // never create resources inside a capture: stay serial this time
+    r.tried = true;
+    r.ok = cudaStreamCreateWithFlags(&r.s, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&r.ev[0], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&r.ev[1], cudaEventDisableTiming) == cudaSuccess;
+    if (!r.ok) cudaGetLastError();
+  }
+  if (r.ok) { side_ = r.s; ev_[0] = r.ev[0]; ev_[1] = r.ev[1]; }
+}
+
+int SideStream::fork() {
+  if (!side_) return 0;
+  HCA_CUDA(cudaEventRecord(ev_[0], main_));
+  HCA_CUDA(cudaStreamWaitEvent(side_, ev_[0], 0));
+  return 0;
+}
+
+int SideStream::join() {
+  if (!side_) return 0;
+  HCA_CUDA(cudaEventRecord(ev_[1], side_));
+  HCA_CUDA(cudaStreamWaitEvent(main_, ev_[1], 0));
+  return 0;
+}
+
 }  // namespace hca
 
 extern "C" {
