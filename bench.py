@@ -34,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG = dict(N=196, d=512, T=26, vocab=10000, K=1001, mlp=1024)
+_REAL_STDOUT = sys.stdout
 METRIC = "hiecoattn_train_samples_per_sec"
 UNIT = "samples/s"
 FLOPS_PER_SAMPLE = 720e6          # algorithmic fwd+bwd, SURVEY.md section 8(a) ledger (no LSTM, no VGG, no Adam)
@@ -58,7 +59,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -135,7 +136,7 @@ def run_reference_arm(args):
                              "sample": f"{args.steps} steps of batch {B} (of the 160-sample batch), torch CPU fp32, oracle/torch_port.py"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 def workload_config(batch, world, extra=None):
@@ -403,7 +404,7 @@ def run_ours(args):
                 "roofline": roof, "cpu_baseline": cpu, "kernel_shares": shares,
                 "step_algorithmic_tflops": step_tflops, "step_frac_of_bf16_peak": step_tflops / pk["bf16_tflops_sustained"],
                 "final_loss": final_loss, "grad_allreduce_bytes": st.dp.grad_bytes() if world > 1 else 0}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         # NCCL communicators that were captured into CUDA graphs do not always tear down cleanly (observed: the job
         # printed its line and then sat in destroy_process_group until the launcher's timeout).  Everything this process
@@ -416,10 +417,21 @@ def run_ours(args):
         os._exit(0)
 
 
+def _claim_stdout():
+    """Route this process's fd 1 to stderr and return a file object on the ORIGINAL stdout: libraries that print banners to
+    stdout (NCCL's version line) must not end up next to the one JSON line the caller parses."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=160, help="samples per GPU")
