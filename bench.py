@@ -252,13 +252,19 @@ def time_roofline_kernel(pkg, device, steps, pk):
 
 
 def kernel_shares(st, steps=4, top=8):
-    """Per-kernel device time of the timed step under CUPTI activity tracing (torch.profiler): which kernels the step is made of."""
+    """Per-kernel device time of the step under CUPTI activity tracing (torch.profiler): which kernels the step is made of.
+    Runs the step EAGERLY with programmatic dependent launch off (HCA_PDL=0): in the timed graph every kernel starts while its
+    predecessor drains and waits in griddepcontrol.wait, so its CUPTI duration would include that wait."""
     try:
         import collections
+        os.environ["HCA_PDL"] = "0"
+        st._step_body(st.slots[0])
+        torch.cuda.synchronize()
         with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
             for i in range(steps):
-                st.step(i)
+                st._step_body(st.slots[i % len(st.slots)])
             torch.cuda.synchronize()
+        os.environ.pop("HCA_PDL", None)
         agg = collections.OrderedDict()
         for ev in prof.events():
             if ev.device_type == torch.autograd.DeviceType.CUDA:
@@ -271,6 +277,7 @@ def kernel_shares(st, steps=4, top=8):
         return {"kernel_us_per_step": tot / steps,
                 "top": [{"kernel": short(k), "us_per_step": us / steps, "launches_per_step": n / steps, "share": us / tot} for k, (n, us) in rows]}
     except Exception as e:                      # evidence only: never fail the bench over it
+        os.environ.pop("HCA_PDL", None)
         return {"error": f"{type(e).__name__}: {str(e)[:100]}"}
 
 

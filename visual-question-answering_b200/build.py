@@ -23,6 +23,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", INCLUDE]
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]   # accurate math is the default; keep it explicit in docs
+if os.environ.get("HCA_BUILD_TIMELINE") == "1":                # clock64 stamps in gemm_tc_kernel for profiles/timeline_*.py
+    FLAGS.append("-DHCA_TC_TIMELINE=1")
 
 
 def sources():

@@ -12,6 +12,7 @@ namespace hca {
 namespace {
 
 __global__ void adam_prep_kernel(long long* __restrict__ step, float* __restrict__ coef, float lr, float b1, float b2) {
+  pdl_enter();
   const long long t = step[0] + 1;
   step[0] = t;
   coef[0] = (float)((double)lr / (1.0 - pow((double)b1, (double)t)));   // step size
@@ -21,6 +22,7 @@ __global__ void adam_prep_kernel(long long* __restrict__ step, float* __restrict
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                                                    float4* __restrict__ v, int64_t n4, const float* __restrict__ coef, float b1, float b2,
                                                    float eps) {
+  pdl_enter();
   const float step_size = coef[0], inv_bc2 = coef[1];
   const float c1 = 1.f - b1, c2 = 1.f - b2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -47,9 +49,9 @@ extern "C" int hca_adam_step(float* p, const float* g, float* m, float* v, int64
   HCA_CHECK_ARG(n > 0 && n % 4 == 0, "adam_step: the flat buffers must hold a multiple of 4 elements (got %lld)", (long long)n);
   HCA_CHECK_ARG(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                   reinterpret_cast<uintptr_t>(v)) & 15) == 0, "adam_step: buffers must be 16-byte aligned");
-  adam_prep_kernel<<<1, 1, 0, s>>>(step, coef, lr, beta1, beta2);
+  HCA_LAUNCH_K((adam_prep_kernel), 1, 1, 0, s, step, coef, lr, beta1, beta2);
   HCA_LAUNCHED();
-  adam_kernel<<<ew_grid(n / 4), 256, 0, s>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, n / 4, coef, beta1, beta2, eps);
+  HCA_LAUNCH_K((adam_kernel), ew_grid(n / 4), 256, 0, s, (float4*)p, (const float4*)g, (float4*)m, (float4*)v, n / 4, coef, beta1, beta2, eps);
   HCA_LAUNCHED();
   return 0;
 }

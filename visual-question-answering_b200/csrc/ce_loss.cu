@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(CE_THREADS) ce_loss_kernel(const float* __rest
                                                              int B, int K, float scale, float* __restrict__ row_loss,
                                                              float* __restrict__ loss, float* __restrict__ dlogits, int64_t ldd,
                                                              unsigned int* __restrict__ counter) {
+  pdl_enter();
   __shared__ float red[CE_THREADS / 32];
   __shared__ bool last;
   const int b = blockIdx.x;
@@ -82,7 +83,7 @@ extern "C" int hca_ce_loss(const float* logits, int64_t ld, const int64_t* label
   unsigned int* counter = (unsigned int*)ws;
   HCA_TRY(zero_async(counter, 4, (cudaStream_t)stream));
   float* row_loss = (float*)((char*)ws + 256);
-  ce_loss_kernel<<<B, CE_THREADS, 0, (cudaStream_t)stream>>>(logits, ld, labels, B, K, scale, row_loss, loss, dlogits, ldd, counter);
+  HCA_LAUNCH_K((ce_loss_kernel), B, CE_THREADS, 0, (cudaStream_t)stream, logits, ld, labels, B, K, scale, row_loss, loss, dlogits, ldd, counter);
   HCA_LAUNCHED();
   return 0;
 }

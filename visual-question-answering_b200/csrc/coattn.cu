@@ -30,6 +30,7 @@ inline int64_t round8(int64_t x) { return (x + 7) / 8 * 8; }
 // dense copy of a strided [B,N,d] tensor
 __global__ void __launch_bounds__(256) gather_strided_kernel(const float* __restrict__ V, int64_t sb, int64_t sn, int64_t sd,
                                                              float* __restrict__ out, int B, int N, int d) {
+  pdl_enter();
   const int64_t total = (int64_t)B * N * d;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % d);
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) attn_finish_kernel(const float* __restric
                                                           float* __restrict__ av, float* __restrict__ aq,
                                                           float* __restrict__ vhat, float* __restrict__ qhat,
                                                           int B, int N, int T, int d) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* a_sm = sm;              // [3][N]
   float* q_sm = sm + 3 * N;      // [3][T]
@@ -230,6 +232,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dots_kernel(const __nv_bfloat16*
                                                             const __nv_bfloat16* __restrict__ Qp, int64_t q_ps,
                                                             const float* __restrict__ gv, const float* __restrict__ gq,
                                                             float* __restrict__ dav, float* __restrict__ daq, int B, int N, int T, int d) {
+  pdl_enter();
   extern __shared__ __align__(16) float sm16[];
   float* gv_sm = sm16;                // [3][d]
   float* gq_sm = sm16 + 3 * d;        // [3][d]
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(192) attn_bwd_softmax_kernel(const float* __re
                                                                const float* __restrict__ dav, const float* __restrict__ daq,
                                                                float* __restrict__ dsv, float* __restrict__ dsq,
                                                                float* __restrict__ dcv, float* __restrict__ dcq, int N, int T) {
+  pdl_enter();
   const int b = blockIdx.x, w = threadIdx.x >> 5;
   if (w < 3) {
     const int64_t o = ((int64_t)b * 3 + w) * N;
@@ -289,6 +293,7 @@ __global__ void __launch_bounds__(192) attn_bwd_softmax_kernel(const float* __re
 // dV[b][n][:] += sum_l av[b][l][n] * gv[l][b][:]      (only when the image features need a gradient)
 __global__ void __launch_bounds__(256) dv_rank3_kernel(float* __restrict__ dV, const float* __restrict__ av, const float* __restrict__ gv,
                                                        int B, int N, int d) {
+  pdl_enter();
   const int d4 = d >> 2;
   const int64_t total = (int64_t)B * N * d4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -428,7 +433,7 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
   if (!v_is_dense(v_sb, v_sn, v_sd, N, d)) {
     float* vc = w.take<float>((size_t)BN * d);
     if (!vc) return set_err(HCA_ERR_WORKSPACE, "coattn_fwd: workspace too small");
-    gather_strided_kernel<<<ew_grid(BN * d), 256, 0, s>>>(V, v_sb, v_sn, v_sd, vc, B, N, d);
+    HCA_LAUNCH_K((gather_strided_kernel), ew_grid(BN * d), 256, 0, s, V, v_sb, v_sn, v_sd, vc, B, N, d);
     HCA_LAUNCHED();
     Vd = vc;
   }
@@ -465,7 +470,7 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
   const size_t smem = (size_t)6 * (N + T) * sizeof(float);
   HCA_CHECK_ARG(smem <= 48 * 1024, "coattn_fwd: N + T too large for the softmax kernel");
   HCA_TRY(zero_async(vhat, (size_t)3 * B * d * 4, s));
-  attn_finish_kernel<<<dim3(B, ATTN_SPLIT), 256, smem, s>>>(svs, sqs, cv, cq, Vd, q0, q1, q2, sv_.av, sv_.aq, vhat, qhat, B, N, T, d);
+  HCA_LAUNCH_K((attn_finish_kernel), dim3(B, ATTN_SPLIT), 256, smem, s, svs, sqs, cv, cq, Vd, q0, q1, q2, sv_.av, sv_.aq, vhat, qhat, B, N, T, d);
   HCA_LAUNCHED();
   return 0;
 }
@@ -511,9 +516,9 @@ extern "C" int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv,
     HCA_CHECK_ARG(smem <= 48 * 1024, "coattn_bwd: d too large for the attention-backward kernel");
     float* dav = dscr;                       // [B][3][N]
     float* daq = dscr + (size_t)3 * B * N;   // [B][3][T]
-    attn_bwd_dots_kernel<<<dim3(B, ATTN_SPLIT), 256, smem, s>>>(Vp.p, Vp.ps, Qp.p, Qp.ps, gvhat, gqhat, dav, daq, B, N, T, d);
+    HCA_LAUNCH_K((attn_bwd_dots_kernel), dim3(B, ATTN_SPLIT), 256, smem, s, Vp.p, Vp.ps, Qp.p, Qp.ps, gvhat, gqhat, dav, daq, B, N, T, d);
     HCA_LAUNCHED();
-    attn_bwd_softmax_kernel<<<B, 192, 0, s>>>(sv_.av, sv_.aq, dav, daq, dsv, dsq, dcv, dcq, N, T);
+    HCA_LAUNCH_K((attn_bwd_softmax_kernel), B, 192, 0, s, sv_.av, sv_.aq, dav, daq, dsv, dsq, dcv, dcq, N, T);
     HCA_LAUNCHED();
   }
   {  // dZq_all = (dsq x wq) * (1 - Hq^2), Hq = tanh(PQ_all + C_all PV) recomputed ; dwq += Hq^T dsq
@@ -572,7 +577,7 @@ extern "C" int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv,
       TcEpilogue e; e.D = dV; e.ldd = d; e.d_batch_stride = (int64_t)N * d; e.accumulate = 1;
       HCA_TRY(launch_gemm_tc(opv(dS, 0, T3, T3, B, true), opv(Qp, 0, T3, T3, B, true), 2, N, d, T3, e, 1, s, B));
     }
-    dv_rank3_kernel<<<ew_grid(BN * (d / 4)), 256, 0, s>>>(dV, sv_.av, gvhat, B, N, d);
+    HCA_LAUNCH_K((dv_rank3_kernel), ew_grid(BN * (d / 4)), 256, 0, s, dV, sv_.av, gvhat, B, N, d);
     HCA_LAUNCHED();
   }
   return 0;

@@ -82,6 +82,40 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // options
 bool use_tc();
+bool pdl_enabled();      // HCA_PDL=0 turns programmatic dependent launch off (plain stream-ordered launches)
+
+// ---- programmatic dependent launch -------------------------------------------------------------------
+// The step is a chain of ~90 kernels, many of them a few microseconds long: the gap between a kernel's last CTA retiring and
+// the first CTA of its successor running (launch latency, block scheduling, parameter fetch) is a visible share of it.  Every
+// kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_enter():
+// `launch_dependents` lets the NEXT kernel's CTAs be scheduled as soon as all of this kernel's CTAs have started (they then
+// sit in their own pdl_enter), and `wait` blocks until every prerequisite grid has completed and its writes are visible --
+// i.e. exactly stream order for all memory effects, minus the launch gap.  Under CUDA-graph capture the edges become
+// programmatic edges of the graph.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// kernel in parentheses (template commas): HCA_LAUNCH_K((k<1, 2>), grid, block, smem, stream, args...); follow with HCA_LAUNCHED()
+#define HCA_LAUNCH_K(kernel, grid, block, smem, stream, ...) \
+  (void)::hca::launch_k(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
 
 // ---- side stream -------------------------------------------------------------------------------------
 // Independent branches of one entry point (e.g. the weight-gradient products of the classifier, which nothing later in the

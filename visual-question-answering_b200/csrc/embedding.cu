@@ -7,6 +7,7 @@ namespace {
 
 __global__ void __launch_bounds__(256) embedding_fwd_kernel(const int64_t* __restrict__ tokens, const float4* __restrict__ table,
                                                             float4* __restrict__ out, int64_t rows, int E4, int64_t vocab) {
+  pdl_enter();
   const int64_t total = rows * E4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / E4;
@@ -19,6 +20,7 @@ __global__ void __launch_bounds__(256) embedding_fwd_kernel(const int64_t* __res
 
 __global__ void __launch_bounds__(256) embedding_bwd_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ dout,
                                                             float* __restrict__ dtable, int64_t rows, int E, int64_t vocab) {
+  pdl_enter();
   const int64_t total = rows * E;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / E;
@@ -40,7 +42,7 @@ extern "C" int hca_embedding_fwd(const int64_t* tokens, const float* table, floa
   if (rows == 0) return 0;
   const int64_t total = rows * (E / 4);
   const int grid = ew_grid(total);
-  embedding_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tokens, (const float4*)table, (float4*)out, rows, E / 4, vocab);
+  HCA_LAUNCH_K((embedding_fwd_kernel), grid, 256, 0, (cudaStream_t)stream, tokens, (const float4*)table, (float4*)out, rows, E / 4, vocab);
   HCA_LAUNCHED();
   return 0;
 }
@@ -54,7 +56,7 @@ extern "C" int hca_embedding_bwd(const int64_t* tokens, const float* dout, float
   if (rows == 0) return 0;
   const int64_t total = rows * E;
   const int grid = ew_grid(total);
-  embedding_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tokens, dout, dtable, rows, E, vocab);
+  HCA_LAUNCH_K((embedding_bwd_kernel), grid, 256, 0, (cudaStream_t)stream, tokens, dout, dtable, rows, E, vocab);
   HCA_LAUNCHED();
   return 0;
 }

@@ -14,6 +14,7 @@ __device__ __forceinline__ float mat_at(const MatRef& r, int z, int m, int n) {
 
 template <int TM, int TN>
 __global__ void __launch_bounds__(256) gemm_ffma_kernel(const GemmParams p) {
+  pdl_enter();
   constexpr int BM = 16 * TM, BN = 16 * TN, BK = 16;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -146,8 +147,8 @@ int launch_gemm_ffma(const GemmParams& p, bool big, cudaStream_t stream) {
   const int BM = big ? 128 : 64, BN = big ? 128 : 64;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.batch * p.splitk);
   HCA_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "gemm_ffma: grid too large");
-  if (big) gemm_ffma_kernel<8, 8><<<grid, 256, 0, stream>>>(p);
-  else gemm_ffma_kernel<4, 4><<<grid, 256, 0, stream>>>(p);
+  if (big) HCA_LAUNCH_K((gemm_ffma_kernel<8, 8>), grid, 256, 0, stream, p);
+  else HCA_LAUNCH_K((gemm_ffma_kernel<4, 4>), grid, 256, 0, stream, p);
   HCA_LAUNCHED();
   return 0;
 }

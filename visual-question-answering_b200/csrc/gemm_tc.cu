@@ -11,6 +11,9 @@ namespace hca {
 namespace {
 using namespace ptx;
 
+#ifndef HCA_TC_TIMELINE
+#define HCA_TC_TIMELINE 0
+#endif
 constexpr int BM = 128;               // UMMA M (cta_group::1): TMEM lane i <-> output row i
 constexpr int UMMA_K = 16;            // bf16
 constexpr int MAX_STAGES = 6;
@@ -93,8 +96,12 @@ __device__ __forceinline__ float col_reduce32(float (&v)[32], int lane) {
 // of A and HALF of the B tile, the leader issues M = 256 MMAs that read both halves, and each CTA drains its own 128 accumulator
 // lanes.  Per output element only half the operand bytes cross the L2 -> SM fabric -- the measured limit of the big K-major
 // products (profiles/r1c_pv_gemm_ncu_full.md: 83 B/clk/SM of operand fill against a ~43 B/clk/SM chip-wide L2 cap).
-template <int BN, int P, bool A_MN, bool B_MN, int BK, int CG = 1>
+// EPI = 0: "lean" epilogue (bias, fp32 / planes output, split-K reduce-add): the feature blocks of the full epilogue (addend tiles, tanh,
+// row dots, dZ, rank-1 terms, column sums) are compiled out.  The profile of the full variant on a plain product showed the chunk loop
+// executing ~340 of ~3200 instructions, with 22 % of its stall samples waiting for instruction fetch and 7 % resolving branches.
+template <int BN, int P, bool A_MN, bool B_MN, int BK, int CG = 1, int EPI = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  pdl_trigger();      // (the wait follows the set-up below: barrier init, descriptor prefetch and TMEM allocation touch no dependent data)
   static_assert(BK == 64 || (BK == 32 && A_MN && B_MN), "BK = 32 k-blocks are for MN-major operand pairs (short contractions)");
   static_assert(CG == 1 || (CG == 2 && BN == 256 && !A_MN && !B_MN && BK == 64), "CTA-pair mode: K-major operands, 256-wide tiles");
   constexpr int A_TILE_BYTES = BM * BK * 2;
@@ -146,7 +153,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     return c;
   };
 
-  long long* tl = (p.timeline && (int)blockIdx.x < p.timeline_ctas) ? p.timeline + (size_t)blockIdx.x * 64 : nullptr;
+  // (clock64 stamps for profiles/timeline_*.py: compiled in only with -DHCA_TC_TIMELINE=1, see build.py)
+  long long* tl = (HCA_TC_TIMELINE && p.timeline && (int)blockIdx.x < p.timeline_ctas) ? p.timeline + (size_t)blockIdx.x * 64 : nullptr;
   if (tl && threadIdx.x == 0) {
     tl[0] = clock64();
     unsigned smid;
@@ -180,6 +188,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   __syncthreads();
   if constexpr (CG == 2) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tc_fence_after();
+  pdl_wait();                                    // every producer kernel has completed: operands, addends and outputs may be touched
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_ptr_smem, 0);
   if (tl && threadIdx.x == 0) tl[1] = clock64();
 
@@ -383,11 +392,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       }
     } else {
       // ------------------------------------------------------------------ standard epilogue
-      const bool do_f32 = (p.D != nullptr) && p.mode != TC_EPI_ROWDOT;
-      const bool do_pl = (p.P != nullptr) && p.mode != TC_EPI_ROWDOT;
+      constexpr bool FULL = (EPI == 1);
+      const int aux_kind = FULL ? p.aux_kind : 0;
+      const int aux_mode = FULL ? p.aux_mode : (int)TC_AUX_NONE;
+      const int mode = FULL ? p.mode : (int)TC_EPI_STORE;
+      const bool act_tanh = FULL && p.act_tanh != 0;
+      const bool has_r1 = FULL && CG == 1 && p.r1col != nullptr;
+      const float* const mulx = FULL ? p.mulx : nullptr;
+      const float* const rowv = FULL ? p.rowv : nullptr;
+      const float* const colv = FULL ? p.colv : nullptr;
+      const bool do_f32 = (p.D != nullptr) && mode != TC_EPI_ROWDOT;
+      const bool do_pl = (p.P != nullptr) && mode != TC_EPI_ROWDOT;
       const bool pl_direct = p.pl_direct != 0;
       const bool stage_tma = (do_f32 && p.tma_store) || (do_pl && !pl_direct);
-      const bool want_colred = (p.red_col != nullptr);
+      const bool want_colred = FULL && (p.red_col != nullptr);
       float* const bias_s = bias_sm[eg];
       float* const colv_s = colv_sm[eg];
       float* const colred_s = colred_sm[eg];
@@ -421,14 +439,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const TileCoord& c = atc;
         const int za = (c.z / p.aux_zd) % p.aux_nb;
         mbar_expect_tx(aux_bar(eg), CHUNK_BYTES);
-        if (p.aux_kind == 1) {
+        if (aux_kind == 1) {
           tma_load_3d(aux_base, &maps.AUX, aux_bar(eg), c.n0 + ac * 32, c.m0, za);
         } else {
           tma_load_4d(aux_base, &maps.AUX, aux_bar(eg), c.n0 + ac * 32, c.m0, 0, za);
           tma_load_4d(aux_base + CHUNK_BYTES / 2, &maps.AUX, aux_bar(eg), c.n0 + ac * 32, c.m0, 1, za);
         }
       };
-      if (p.aux_kind) {
+      if (aux_kind) {
         settle();
         if (leader && at < p.total_tiles) issue_aux();
       }
@@ -439,7 +457,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const bool row_ok = row < p.M;
         // per-column vectors of this tile: restaged only when they change (a persistent CTA usually keeps its n0: the round-robin
         // stride is a multiple of tiles_n), which also lets the column sums accumulate in shared memory across its tiles
-        const bool restage = tc.n0 != staged_n0 || (p.bias && p.bias_sb != 0) || p.r1col;
+        const bool restage = tc.n0 != staged_n0 || (p.bias && p.bias_sb != 0) || has_r1;
         if (restage) {
           epi_barrier();                      // the previous tile's readers of the per-column vectors are done
           if (want_colred && staged_n0 >= 0 && tc.n0 != staged_n0) flush_colred(staged_n0);
@@ -447,9 +465,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           for (int j = et; j < BN; j += 128) {
             const bool ok = tc.n0 + j < p.N;
             bias_s[j] = (bias && ok) ? __ldg(bias + tc.n0 + j) : 0.f;
-            colv_s[j] = (p.colv && ok) ? __ldg(p.colv + tc.n0 + j) : 0.f;
+            colv_s[j] = (colv && ok) ? __ldg(colv + tc.n0 + j) : 0.f;
             if (tc.n0 != staged_n0) colred_s[j] = 0.f;
-            if constexpr (CG == 1) {
+            if constexpr (CG == 1 && FULL) {
               if (p.r1col) {
                 const int ng = p.r1_rpg > 0 ? min(4, (p.M + p.r1_rpg - 1) / p.r1_rpg) : 1;
                 for (int g = 0; g < ng; ++g)
@@ -460,8 +478,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           staged_n0 = tc.n0;
           epi_barrier();
         }
-        const float rv = (p.rowv && row_ok) ? __ldg(p.rowv + (int64_t)tc.z * p.rowv_sb + row) : 0.f;
-        const int rgroup = (p.r1col && p.r1_rpg > 0) ? min(3, row / p.r1_rpg) : 0;
+        const float rv = (rowv && row_ok) ? __ldg(rowv + (int64_t)tc.z * p.rowv_sb + row) : 0.f;
+        const int rgroup = (has_r1 && p.r1_rpg > 0) ? min(3, row / p.r1_rpg) : 0;
         mbar_wait(tmem_full_bar(acc), (tile_it >> 1) & 1, 3);
         tc_fence_after();
         if (tl && et == 0 && eg == 0 && tile_it == 0) tl[4] = clock64();
@@ -479,7 +497,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           const int g = row / p.d_rpg;
           drow = p.D + (int64_t)(tc.z / p.d_zd) * p.d_sb + (int64_t)g * p.d_gs + (int64_t)(row - g * p.d_rpg) * p.ldd;
         }
-        const float* xrow = p.mulx ? p.mulx + (int64_t)row * p.mulx_ld : nullptr;
+        const float* xrow = mulx ? mulx + (int64_t)row * p.mulx_ld : nullptr;
         float rowdot = 0.f;
 #pragma unroll 1
         for (int c = eg; c < nchunks; c += neg, ++gc) {
@@ -493,7 +511,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             epi_barrier();
           }
           HCA_TL_STAMP();                                             // 0: staging buffer free
-          if (p.aux_kind) mbar_wait(aux_bar(eg), aux_n & 1u, 4);
+          if (aux_kind) mbar_wait(aux_bar(eg), aux_n & 1u, 4);
           HCA_TL_STAMP();                                             // 1: addend tile landed
           uint32_t v[32];
           __syncwarp();                                               // tcgen05.ld is warp-collective
@@ -507,7 +525,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
           }
           float ax[32];
-          if (p.aux_kind == 1) {                                      // this thread's row of the fp32 addend tile (128-byte swizzle)
+          if (aux_kind == 1) {                                      // this thread's row of the fp32 addend tile (128-byte swizzle)
             const uint32_t src = aux_base + (uint32_t)r * 128u;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -515,7 +533,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                            : "=f"(ax[4 * j]), "=f"(ax[4 * j + 1]), "=f"(ax[4 * j + 2]), "=f"(ax[4 * j + 3])
                            : "r"(src + (uint32_t)((j ^ (r & 7)) * 16)));
             }
-          } else if (p.aux_kind == 2) {                               // hi + lo rows of the bf16 plane tiles (64-byte swizzle)
+          } else if (aux_kind == 2) {                               // hi + lo rows of the bf16 plane tiles (64-byte swizzle)
             const uint32_t src = aux_base + (uint32_t)r * 64u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -532,7 +550,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               }
             }
           }
-          if (p.aux_kind) {
+          if (aux_kind) {
             // the addend tile is in registers: request the group's next one now, so that its latency hides behind the
             // arithmetic and the stores of this chunk (and behind the other group's work)
             epi_barrier();
@@ -555,21 +573,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
           }
-          if (p.aux_kind && p.aux_mode == TC_AUX_ADD) {
+          if (aux_kind && aux_mode == TC_AUX_ADD) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += ax[j];
           }
-          if (p.act_tanh) {                                           // uniform branches: no predicated-off code on the common path
+          if (act_tanh) {                                           // uniform branches: no predicated-off code on the common path
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
           }
-          if constexpr (CG == 1) {
+          if constexpr (CG == 1 && FULL) {
             if (p.r1col) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaf(rv, r1_sm[eg][rgroup][c * 32 + j], f[j]);
             }
           }
-          if (p.aux_kind && p.aux_mode == TC_AUX_MUL_1MX2) {
+          if (aux_kind && aux_mode == TC_AUX_MUL_1MX2) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= (1.f - ax[j] * ax[j]);
           }
@@ -582,12 +600,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               }
             }
           }
-          if (p.mode == TC_EPI_ROWDOT) {
+          if (mode == TC_EPI_ROWDOT) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) rowdot = fmaf(f[j], colv_s[c * 32 + j], rowdot);   // colv_s is 0 beyond N
             continue;
           }
-          if (p.mode == TC_EPI_DZ) {
+          if (mode == TC_EPI_DZ) {
             // column partials of h * rowv over this warp's 32 rows, then dz = rowv * colv * (1 - h^2)
             float part[32];
 #pragma unroll
@@ -720,7 +738,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
           }
         }
-        if (p.mode == TC_EPI_ROWDOT && row_ok && eg < nchunks) atomicAdd(p.red_row + (int64_t)tc.z * p.red_row_sb + row, rowdot);
+        if (mode == TC_EPI_ROWDOT && row_ok && eg < nchunks) atomicAdd(p.red_row + (int64_t)tc.z * p.red_row_sb + row, rowdot);
         if (tl && et == 0 && eg == 0 && tile_it == 0) tl[5] = clock64();
       }
       if (want_colred && staged_n0 >= 0) {
@@ -746,6 +764,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols,
                                                            __nv_bfloat16* __restrict__ planes, int64_t ldp, int64_t plane_stride,
                                                            int P) {
+  pdl_enter();
   const int c4n = (cols + 3) / 4;
   const int64_t total = rows * c4n;
   const bool aligned = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -777,6 +796,7 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 __global__ void __launch_bounds__(256) split_planes_stack3_kernel(const float4* __restrict__ s0, const float4* __restrict__ s1,
                                                                   const float4* __restrict__ s2, int B, int T, int c4n,
                                                                   __nv_bfloat16* __restrict__ planes, int64_t ldp, int64_t plane_stride) {
+  pdl_enter();
   const int64_t per = (int64_t)B * T * c4n, total = 3 * per;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int l = (int)(i / per);
@@ -935,7 +955,7 @@ int launch_split_planes(const float* src, int64_t ld, int64_t rows, int cols, __
   HCA_CHECK_ARG(src && planes && rows > 0 && cols > 0 && P >= 1 && P <= 3 && (ldp % 8) == 0 && (plane_stride % 8) == 0,
                 "split_planes: bad arguments");
   const int64_t total = rows * ((cols + 3) / 4);
-  split_planes_kernel<<<ew_grid(total), 256, 0, s>>>(src, ld, rows, cols, planes, ldp, plane_stride, P);
+  HCA_LAUNCH_K((split_planes_kernel), ew_grid(total), 256, 0, s, src, ld, rows, cols, planes, ldp, plane_stride, P);
   HCA_LAUNCHED();
   return 0;
 }
@@ -947,7 +967,7 @@ int launch_split_planes_stack3(const float* s0, const float* s1, const float* s2
   HCA_CHECK_ARG(((reinterpret_cast<uintptr_t>(s0) | reinterpret_cast<uintptr_t>(s1) | reinterpret_cast<uintptr_t>(s2)) & 15) == 0,
                 "split_planes_stack3: sources must be 16-byte aligned");
   const int64_t total = 3LL * B * T * (cols / 4);
-  split_planes_stack3_kernel<<<ew_grid(total), 256, 0, s>>>((const float4*)s0, (const float4*)s1, (const float4*)s2, B, T, cols / 4, planes,
+  HCA_LAUNCH_K((split_planes_stack3_kernel), ew_grid(total), 256, 0, s, (const float4*)s0, (const float4*)s1, (const float4*)s2, B, T, cols / 4, planes,
                                                            ldp, plane_stride);
   HCA_LAUNCHED();
   return 0;
@@ -1153,15 +1173,25 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   KernelFn fn = nullptr;
   const int combo = (A.mn_major ? 2 : 0) + (B.mn_major ? 1 : 0);    // 0 = NT (K,K), 1 = NN (K,MN), 2 = (MN,K), 3 = TN (MN,MN)
   int slot = -1;
-#define HCA_TC_CASE(SLOT, BNN, PP, CC, AMN, BMN, BKK) \
-  if (BN == BNN && P == PP && combo == CC && BK == BKK) { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK>; slot = SLOT; }
+  // lean epilogue instantiation (EPI = 0) for products without fused epilogue math; HCA_TC_LEAN=0 forces the full one
+  bool lean = !e.transposed && !e.act_tanh && e.aux_mode == TC_AUX_NONE && e.mode == TC_EPI_STORE && !e.r1col && !e.mulx && !e.red_col &&
+              !e.rowv && !e.colv;
+  { const char* ev = getenv("HCA_TC_LEAN"); if (ev && atoi(ev) == 0) lean = false; }
+#define HCA_TC_CASE(SLOT, BNN, PP, CC, AMN, BMN, BKK)                                                   \
+  if (BN == BNN && P == PP && combo == CC && BK == BKK) {                                                \
+    if (lean && BNN != 32) { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK, 1, 0>; slot = SLOT + 10; }      \
+    else { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK, 1, 1>; slot = SLOT; }                             \
+  }
   HCA_TC_CASE(0, 128, 2, 0, false, false, 64) HCA_TC_CASE(1, 128, 2, 1, false, true, 64) HCA_TC_CASE(2, 128, 2, 3, true, true, 64)
   HCA_TC_CASE(3, 128, 3, 0, false, false, 64) HCA_TC_CASE(4, 128, 3, 1, false, true, 64) HCA_TC_CASE(5, 128, 3, 3, true, true, 64)
   HCA_TC_CASE(6, 32, 2, 0, false, false, 64) HCA_TC_CASE(7, 32, 2, 2, true, false, 64) HCA_TC_CASE(8, 128, 2, 3, true, true, 32)
 #undef HCA_TC_CASE
-  if (pair) { fn = gemm_tc_kernel<256, 2, false, false, 64, 2>; slot = 9; }
+  if (pair) {
+    if (lean) { fn = gemm_tc_kernel<256, 2, false, false, 64, 2, 0>; slot = 19; }
+    else { fn = gemm_tc_kernel<256, 2, false, false, 64, 2, 1>; slot = 9; }
+  }
   HCA_CHECK_ARG(fn != nullptr, "gemm_tc: this (BN, P, layout) combination is not instantiated (BN=%d P=%d combo=%d)", BN, P, combo);
-  static bool attr_set[10] = {};
+  static bool attr_set[20] = {};
   if (!attr_set[slot]) {
     HCA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
     attr_set[slot] = true;
@@ -1172,14 +1202,16 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     HCA_CUDA(cudaLaunchKernelEx(&cfg, fn, maps, p));
   } else {
-    fn<<<ctas, NUM_THREADS, smem, s>>>(maps, p);
+    HCA_LAUNCH_K((fn), ctas, NUM_THREADS, smem, s, maps, p);
   }
   HCA_LAUNCHED();
   return 0;

@@ -69,6 +69,7 @@ __device__ __forceinline__ float col_reduce32(float (&v)[32], int lane) {
 
 template <bool BWD>
 __global__ void __launch_bounds__(V_THREADS, 1) hv_kernel(const __grid_constant__ HvMaps maps, const HvParams p) {
+  pdl_enter();
   constexpr int NACC = BWD ? 4 : 3;
   constexpr uint32_t TMEM_COLS = 512;
   extern __shared__ uint8_t smem_raw[];
@@ -447,7 +448,7 @@ int launch(const HvPlanes& C, const HvPlanes& PQ, const HvPlanes& PV, const HvPl
     sms = 148;
   }
   const int ctas = (int)std::min<int64_t>(sms, total);
-  hv_kernel<BWD><<<ctas, V_THREADS, smem, s>>>(maps, p);
+  HCA_LAUNCH_K((hv_kernel<BWD>), ctas, V_THREADS, smem, s, maps, p);
   HCA_LAUNCHED();
   return 0;
 }

@@ -27,6 +27,10 @@
 #include "tc_ptx.cuh"
 #include "util_kernels.cuh"
 
+#ifndef HCA_TC_TIMELINE
+#define HCA_TC_TIMELINE 0
+#endif
+
 namespace hca {
 namespace {
 using namespace ptx;
@@ -140,6 +144,7 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 
 template <bool BWD>
 __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_constant__ LstmMaps maps, const LstmParams p) {
+  pdl_enter();
   constexpr int BN = BWD ? L_UNITS : 4 * L_UNITS;         // accumulator columns: dh of 16 units / 4 gates of 16 units
   constexpr uint32_t W_KB_PLANE = BN * L_BK * 2;          // one plane of one resident k-block
   constexpr uint32_t TMEM_COLS = BWD ? 32 : 128;             // [x.W_hi | x.W_lo] column blocks
@@ -158,7 +163,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
   const int mi = blockIdx.x / p.tiles_n, ni = blockIdx.x - mi * p.tiles_n;
   const int m0 = (p.tile0 + mi) * p.rpt;
   int* const counters = p.counters + (int64_t)(p.tile0 + mi) * p.T;
-  long long* const tl = blockIdx.x == 0 ? p.timeline : nullptr;
+  // (clock64 stamps for profiles/timeline_lstm.py: compiled in only with -DHCA_TC_TIMELINE=1, see build.py)
+  long long* const tl = (HCA_TC_TIMELINE && blockIdx.x == 0) ? p.timeline : nullptr;
   const uint32_t w_base = smem_base;
   const uint32_t ring_base = smem_base + (uint32_t)p.kbn * 2u * W_KB_PLANE;
 
@@ -505,6 +511,7 @@ __device__ __forceinline__ int perm_row(int jp, int H) {
 // planes [2][4H][cols] <- W[perm][cols]
 __global__ void __launch_bounds__(256) lstm_split_perm_kernel(const float* __restrict__ W, int H, int cols, __nv_bfloat16* __restrict__ planes,
                                                               int64_t ps) {
+  pdl_enter();
   const int64_t total = (int64_t)4 * H * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int jp = (int)(i / cols), c = (int)(i - (int64_t)jp * cols);
@@ -517,6 +524,7 @@ __global__ void __launch_bounds__(256) lstm_split_perm_kernel(const float* __res
 // planes [2][H][4H] <- W_hh[perm(j')][k] at [k][j']   (the resident operand of the backward recurrence)
 __global__ void __launch_bounds__(256) lstm_split_perm_t_kernel(const float* __restrict__ Whh, int H, __nv_bfloat16* __restrict__ planes,
                                                                 int64_t ps) {
+  pdl_enter();
   const int64_t total = (int64_t)4 * H * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i / (4 * H)), jp = (int)(i - (int64_t)k * 4 * H);
@@ -528,6 +536,7 @@ __global__ void __launch_bounds__(256) lstm_split_perm_t_kernel(const float* __r
 }
 __global__ void __launch_bounds__(256) lstm_bias_perm_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, int H,
                                                              float* __restrict__ out) {
+  pdl_enter();
   const int jp = blockIdx.x * blockDim.x + threadIdx.x;
   if (jp < 4 * H) {
     const int j = perm_row(jp, H);
@@ -537,6 +546,7 @@ __global__ void __launch_bounds__(256) lstm_bias_perm_kernel(const float* __rest
 // dst[perm(j')][c] = src[j'][c]   (dst2 optional second destination: b_ih and b_hh receive the same gradient)
 __global__ void __launch_bounds__(256) lstm_unperm_kernel(const float* __restrict__ src, int H, int cols, float* __restrict__ dst,
                                                           float* __restrict__ dst2) {
+  pdl_enter();
   const int64_t total = (int64_t)4 * H * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int jp = (int)(i / cols), c = (int)(i - (int64_t)jp * cols);
@@ -660,7 +670,7 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
   for (int t0 = 0; t0 < rt.tiles; t0 += rt.per_launch) {
     const int nm = std::min(rt.per_launch, rt.tiles - t0);
     p.tile0 = t0;
-    lstm_rec_kernel<BWD><<<nm * p.tiles_n, L_THREADS, smem, s>>>(maps, p);
+    HCA_LAUNCH_K((lstm_rec_kernel<BWD>), nm * p.tiles_n, L_THREADS, smem, s, maps, p);
     HCA_LAUNCHED();
   }
   return 0;
@@ -706,11 +716,11 @@ extern "C" int hca_lstm_fwd(const float* x, const int64_t* lens, const float* w_
   int* counters = w.take<int>(counter_count(B, T));
   if (!counters) return set_err(HCA_ERR_WORKSPACE, "lstm_fwd: workspace too small (%zu bytes)", ws_bytes);
   HCA_TRY(launch_split_planes(x, E, BT, E, sv.xp, E, BT * E, 2, s));
-  lstm_split_perm_kernel<<<ew_grid((int64_t)H4 * E), 256, 0, s>>>(w_ih, H, E, wip, (int64_t)H4 * E);
+  HCA_LAUNCH_K((lstm_split_perm_kernel), ew_grid((int64_t)H4 * E), 256, 0, s, w_ih, H, E, wip, (int64_t)H4 * E);
   HCA_LAUNCHED();
-  lstm_split_perm_kernel<<<ew_grid((int64_t)H4 * H), 256, 0, s>>>(w_hh, H, H, whp, (int64_t)H4 * H);
+  HCA_LAUNCH_K((lstm_split_perm_kernel), ew_grid((int64_t)H4 * H), 256, 0, s, w_hh, H, H, whp, (int64_t)H4 * H);
   HCA_LAUNCHED();
-  lstm_bias_perm_kernel<<<(H4 + 255) / 256, 256, 0, s>>>(b_ih, b_hh, H, biasp);
+  HCA_LAUNCH_K((lstm_bias_perm_kernel), (H4 + 255) / 256, 256, 0, s, b_ih, b_hh, H, biasp);
   HCA_LAUNCHED();
   HCA_TRY(zero_async(sv.hp, (size_t)2 * BT * H * 2, s));      // slot 0 (h_{-1} = 0) and the slots no step reaches
   HCA_TRY(zero_async(counters, counter_count(B, T) * 4, s));
@@ -751,7 +761,7 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
   HCA_TRY(zero_async(dgp, (size_t)2 * BT * H4 * 2, s));       // rows no step writes must read as zero in the GEMMs below
   HCA_TRY(zero_async(dbp, (size_t)H4 * 4, s));
   HCA_TRY(zero_async(counters, counter_count(B, T) * 4, s));
-  lstm_split_perm_t_kernel<<<ew_grid((int64_t)H4 * H), 256, 0, s>>>(w_hh, H, wtp, (int64_t)H4 * H);
+  HCA_LAUNCH_K((lstm_split_perm_t_kernel), ew_grid((int64_t)H4 * H), 256, 0, s, w_hh, H, wtp, (int64_t)H4 * H);
   HCA_LAUNCHED();
   LstmParams p;
   memset(&p, 0, sizeof(p));
@@ -764,7 +774,7 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
     if (sk > 1) HCA_TRY(zero_async(dwi, (size_t)H4 * E * 4, s));
     TcEpilogue e; e.D = dwi; e.ldd = E;
     HCA_TRY(launch_gemm_tc(dg_mn, operand(sv.xp, E, BT * E, (int)BT, E, true), 2, H4, E, (int)BT, e, sk, s));
-    lstm_unperm_kernel<<<ew_grid((int64_t)H4 * E), 256, 0, s>>>(dwi, H, E, dw_ih, nullptr);
+    HCA_LAUNCH_K((lstm_unperm_kernel), ew_grid((int64_t)H4 * E), 256, 0, s, dwi, H, E, dw_ih, nullptr);
     HCA_LAUNCHED();
   }
   {  // dW_hh' = dz^T h_prev
@@ -772,13 +782,13 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
     if (sk > 1) HCA_TRY(zero_async(dwh, (size_t)H4 * H * 4, s));
     TcEpilogue e; e.D = dwh; e.ldd = H;
     HCA_TRY(launch_gemm_tc(dg_mn, operand(sv.hp, H, BT * H, (int)BT, H, true), 2, H4, H, (int)BT, e, sk, s));
-    lstm_unperm_kernel<<<ew_grid((int64_t)H4 * H), 256, 0, s>>>(dwh, H, H, dw_hh, nullptr);
+    HCA_LAUNCH_K((lstm_unperm_kernel), ew_grid((int64_t)H4 * H), 256, 0, s, dwh, H, H, dw_hh, nullptr);
     HCA_LAUNCHED();
   }
-  lstm_unperm_kernel<<<ew_grid((int64_t)H4), 256, 0, s>>>(dbp, H, 1, db_ih, db_hh);
+  HCA_LAUNCH_K((lstm_unperm_kernel), ew_grid((int64_t)H4), 256, 0, s, dbp, H, 1, db_ih, db_hh);
   HCA_LAUNCHED();
   if (dx) {  // dx = dz W_ih
-    lstm_split_perm_kernel<<<ew_grid((int64_t)H4 * E), 256, 0, s>>>(w_ih, H, E, wip, (int64_t)H4 * E);
+    HCA_LAUNCH_K((lstm_split_perm_kernel), ew_grid((int64_t)H4 * E), 256, 0, s, w_ih, H, E, wip, (int64_t)H4 * E);
     HCA_LAUNCHED();
     TcEpilogue e; e.D = dx; e.ldd = E;
     HCA_TRY(launch_gemm_tc(operand(dgp, H4, BT * H4, (int)BT, H4, false), operand(wip, E, (int64_t)H4 * E, H4, E, true), 2, (int)BT, E, H4,

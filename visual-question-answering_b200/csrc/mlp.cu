@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256) mlp_inputs_planes_kernel(const float4* __
                                                                 __nv_bfloat16* __restrict__ xw, int64_t xw_ld, int64_t xw_ps,
                                                                 __nv_bfloat16* __restrict__ xp, int64_t xp_ld, int64_t xp_ps,
                                                                 __nv_bfloat16* __restrict__ xs, int64_t xs_ld, int64_t xs_ps, int B, int d4) {
+  pdl_enter();
   const int64_t per = (int64_t)B * d4, total = 3 * per;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int l = (int)(i / per);
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) mlp_inputs_planes_kernel(const float4* __
 __global__ void __launch_bounds__(256) split_colsum_kernel(const float* __restrict__ X, int64_t ld, int rows, int cols,
                                                            __nv_bfloat16* __restrict__ planes, int64_t ldp, int64_t ps,
                                                            float* __restrict__ colsum) {
+  pdl_enter();
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -182,7 +184,7 @@ extern "C" int hca_mlp_fwd(const float* vhat, const float* qhat, const float* Ww
   HCA_CHECK_ARG(tc_available(), "mlp_fwd: cuTensorMapEncodeTiled is not available from the driver");
   Saved sv;
   HCA_CHECK_ARG(carve(sv, saved, saved_sz, B, d, mlp, K), "mlp_fwd: `saved` must be 256-byte aligned and hca_mlp_saved_bytes large");
-  mlp_inputs_planes_kernel<<<ew_grid(3LL * B * d / 4), 256, 0, s>>>((const float4*)vhat, (const float4*)qhat, sv.xw.p, sv.xw.ld, sv.xw.ps,
+  HCA_LAUNCH_K((mlp_inputs_planes_kernel), ew_grid(3LL * B * d / 4), 256, 0, s, (const float4*)vhat, (const float4*)qhat, sv.xw.p, sv.xw.ld, sv.xw.ps,
                                                                   sv.xp.p, sv.xp.ld, sv.xp.ps, sv.xs.p, sv.xs.ld, sv.xs.ps, B, d / 4);
   HCA_LAUNCHED();
   HCA_TRY(split_w(Ww, d, d, sv.Ww, s));
@@ -224,7 +226,7 @@ extern "C" int hca_mlp_bwd(const float* dlogits, const void* saved, size_t saved
   SideStream side(s);
   cudaStream_t sw = side.stream();
   // W_h: planes of dlogits + db_h in one pass; dW_h; dz_s = (dlogits W_h) * (1 - h_s^2) with db_s
-  split_colsum_kernel<<<(K + 31) / 32, 256, 0, s>>>(dlogits, K, B, K, dl.p, dl.ld, dl.ps, dbh);
+  HCA_LAUNCH_K((split_colsum_kernel), (K + 31) / 32, 256, 0, s, dlogits, K, B, K, dl.p, dl.ld, dl.ps, dbh);
   HCA_LAUNCHED();
   HCA_TRY(zero_async(dbs, (size_t)mlp * 4, s));
   HCA_TRY(zero_async(dbp, (size_t)d * 4, s));

@@ -24,6 +24,7 @@ namespace {
 
 // Acat[r][j*E + c] = x[b][t+j-1][c]   (float4 granularity)
 __global__ void __launch_bounds__(256) im2col3_kernel(const float4* __restrict__ x, float4* __restrict__ acat, int B, int T, int E4) {
+  pdl_enter();
   const int64_t total = (int64_t)B * T * 3 * E4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % E4);
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const float4* __restrict__
 
 // dx[b][t] = dA[r][E:2E] + dA[r+1][0:E] (t+1<T) + dA[r-1][2E:3E] (t>0)
 __global__ void __launch_bounds__(256) col2im3_kernel(const float4* __restrict__ dA, float4* __restrict__ dx, int B, int T, int E4) {
+  pdl_enter();
   const int64_t total = (int64_t)B * T * E4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % E4);
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(256) col2im3_kernel(const float4* __restrict__
 
 // wr[o][j*E + c] = w[o][c][j]   (to_conv == false)      or      w[o][c][j] = wr[o][j*E + c]  (to_conv == true)
 __global__ void __launch_bounds__(256) repack_conv_w_kernel(const float* __restrict__ src, float* __restrict__ dst, int E, int k, bool to_conv) {
+  pdl_enter();
   const int64_t total = (int64_t)E * E * k;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     // i indexes the tap-major layout [o][j][c]
@@ -79,6 +82,7 @@ constexpr float TIE_TOL = 2e-4f;
 __global__ void __launch_bounds__(256) pool3_fwd_kernel(const float* __restrict__ cat, const int64_t* __restrict__ lens,
                                                         float* __restrict__ out, uint8_t* __restrict__ idx, int B, int T, int E,
                                                         int* __restrict__ tie_list, int* __restrict__ tie_count, int tie_cap) {
+  pdl_enter();
   const int64_t total = (int64_t)B * T * E;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / E;
@@ -114,6 +118,7 @@ __global__ void __launch_bounds__(256) fixup_ties_kernel(const int* __restrict__
                                                          const float* __restrict__ b1, const float* __restrict__ b2,
                                                          const float* __restrict__ b3, float* __restrict__ out,
                                                          uint8_t* __restrict__ idx, int E) {
+  pdl_enter();
   const int n = min(*tie_count, tie_cap);
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -154,6 +159,7 @@ __global__ void __launch_bounds__(256) fixup_ties_kernel(const int* __restrict__
 __global__ void __launch_bounds__(256) pool3_bwd_kernel(const float* __restrict__ out, const uint8_t* __restrict__ idx,
                                                         const float* __restrict__ dout, const int64_t* __restrict__ lens,
                                                         float* __restrict__ dcat, int B, int T, int E) {
+  pdl_enter();
   const int64_t total = (int64_t)B * T * E;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / E;
@@ -193,6 +199,7 @@ __device__ __forceinline__ void split4(float (&x)[4], uint2 (&out)[P]) {
 template <int P>
 __global__ void __launch_bounds__(256) im2col3_planes_kernel(const float4* __restrict__ x, __nv_bfloat16* __restrict__ planes, int64_t ps,
                                                              int B, int T, int E4) {
+  pdl_enter();
   const int64_t total = (int64_t)B * T * 3 * E4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % E4);
@@ -212,6 +219,7 @@ __global__ void __launch_bounds__(256) im2col3_planes_kernel(const float4* __res
 template <int P>
 __global__ void __launch_bounds__(256) conv_w_planes_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ planes, int64_t ps, int E,
                                                             int k) {
+  pdl_enter();
   const int64_t total = (int64_t)E * E * k;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % E);
@@ -234,6 +242,7 @@ __global__ void __launch_bounds__(256) pool3_bwd_planes_kernel(const float* __re
                                                                const float* __restrict__ dout, const int64_t* __restrict__ lens,
                                                                __nv_bfloat16* __restrict__ planes, int64_t ps, float* __restrict__ db1,
                                                                float* __restrict__ db2, float* __restrict__ db3, int B, int T, int E) {
+  pdl_enter();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   const int64_t R = (int64_t)B * T;
@@ -266,6 +275,7 @@ __global__ void __launch_bounds__(256) pool3_bwd_planes_kernel(const float* __re
 }
 // tap-major fp32 weight gradient -> conv layout: w[o][c][j] = wr[o][j*E + c]
 __global__ void __launch_bounds__(256) unpack_conv_w_kernel(const float* __restrict__ wr, float* __restrict__ w, int E, int k) {
+  pdl_enter();
   const int64_t total = (int64_t)E * E * k;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(i % k);
@@ -335,14 +345,14 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
     const int64_t lda = 3 * (int64_t)E, a_stride = (int64_t)R * lda;
     __nv_bfloat16* ap = c.w.take<__nv_bfloat16>((size_t)P * a_stride);
     if (!ap) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for operand planes");
-    im2col3_planes_kernel<3><<<ew_grid((int64_t)R * 3 * E / 4), 256, 0, s>>>((const float4*)x, ap, a_stride, B, T, E / 4);
+    HCA_LAUNCH_K((im2col3_planes_kernel<3>), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, ap, a_stride, B, T, E / 4);
     HCA_LAUNCHED();
     const float* ws_[3] = {w1, w2, w3};
     for (int k = 1; k <= 3; ++k) {
       const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
       __nv_bfloat16* wp = c.w.take<__nv_bfloat16>((size_t)P * w_stride);
       if (!wp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for weight planes");
-      conv_w_planes_kernel<3><<<ew_grid((int64_t)E * E * k), 256, 0, s>>>(ws_[k - 1], wp, w_stride, E, k);
+      HCA_LAUNCH_K((conv_w_planes_kernel<3>), ew_grid((int64_t)E * E * k), 256, 0, s, ws_[k - 1], wp, w_stride, E, k);
       HCA_LAUNCHED();
       TcOperand A, Bw;
       A.planes = ap + (k == 1 ? E : 0); A.ld = lda; A.plane_stride = a_stride; A.rows = R; A.cols = k * E;
@@ -352,17 +362,17 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
       HCA_TRY(launch_gemm_tc(A, Bw, P, R, E, k * E, ep, 1, s));
     }
     HCA_TRY(zero_async(c.tie_count, sizeof(int), s));
-    pool3_fwd_kernel<<<ew_grid((int64_t)R * E), 256, 0, s>>>(c.cat, lens, out, idx, B, T, E, c.tie_list, c.tie_count, c.tie_cap);
+    HCA_LAUNCH_K((pool3_fwd_kernel), ew_grid((int64_t)R * E), 256, 0, s, c.cat, lens, out, idx, B, T, E, c.tie_list, c.tie_count, c.tie_cap);
     HCA_LAUNCHED();
-    fixup_ties_kernel<<<148 * 2, 256, 0, s>>>(c.tie_list, c.tie_count, c.tie_cap, x, T, w1, w2, w3, b1, b2, b3, out, idx, E);
+    HCA_LAUNCH_K((fixup_ties_kernel), 148 * 2, 256, 0, s, c.tie_list, c.tie_count, c.tie_cap, x, T, w1, w2, w3, b1, b2, b3, out, idx, E);
     HCA_LAUNCHED();
     return 0;
   }
-  im2col3_kernel<<<ew_grid((int64_t)R * 3 * E / 4), 256, 0, s>>>((const float4*)x, (float4*)c.acat, B, T, E / 4);
+  HCA_LAUNCH_K((im2col3_kernel), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, (float4*)c.acat, B, T, E / 4);
   HCA_LAUNCHED();
-  repack_conv_w_kernel<<<ew_grid((int64_t)E * E * 2), 256, 0, s>>>(w2, c.wr2, E, 2, false);
+  HCA_LAUNCH_K((repack_conv_w_kernel), ew_grid((int64_t)E * E * 2), 256, 0, s, w2, c.wr2, E, 2, false);
   HCA_LAUNCHED();
-  repack_conv_w_kernel<<<ew_grid((int64_t)E * E * 3), 256, 0, s>>>(w3, c.wr3, E, 3, false);
+  HCA_LAUNCH_K((repack_conv_w_kernel), ew_grid((int64_t)E * E * 3), 256, 0, s, w3, c.wr3, E, 3, false);
   HCA_LAUNCHED();
   const float* wr[3] = {w1, c.wr2, c.wr3};
   // exact-fp32 CUDA-core path: three GEMMs, bias + tanh fused, writing the column blocks of cat [R, 3E]
@@ -377,7 +387,7 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
     g.act_tanh = 1;
     HCA_TRY(launch_gemm_ffma(g, true, s));
   }
-  pool3_fwd_kernel<<<ew_grid((int64_t)R * E), 256, 0, s>>>(c.cat, lens, out, idx, B, T, E, nullptr, nullptr, 0);
+  HCA_LAUNCH_K((pool3_fwd_kernel), ew_grid((int64_t)R * E), 256, 0, s, c.cat, lens, out, idx, B, T, E, nullptr, nullptr, 0);
   HCA_LAUNCHED();
   return 0;
 }
@@ -399,11 +409,11 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
     __nv_bfloat16* ap = c.w.take<__nv_bfloat16>((size_t)2 * pstride);       // Acat planes
     __nv_bfloat16* dp = c.w.take<__nv_bfloat16>((size_t)2 * pstride);       // dcat planes
     if (!dp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for operand planes");
-    im2col3_planes_kernel<2><<<ew_grid((int64_t)R * 3 * E / 4), 256, 0, s>>>((const float4*)x, ap, pstride, B, T, E / 4);
+    HCA_LAUNCH_K((im2col3_planes_kernel<2>), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, ap, pstride, B, T, E / 4);
     HCA_LAUNCHED();
     float* dbs[3] = {db1, db2, db3};
     for (int k = 0; k < 3; ++k) HCA_TRY(zero_async(dbs[k], (size_t)E * 4, s));
-    pool3_bwd_planes_kernel<<<dim3((E + 255) / 256, (R + POOL_BWD_ROWS - 1) / POOL_BWD_ROWS), 256, 0, s>>>(out, idx, dout, lens, dp, pstride, db1,
+    HCA_LAUNCH_K((pool3_bwd_planes_kernel), dim3((E + 255) / 256, (R + POOL_BWD_ROWS - 1) / POOL_BWD_ROWS), 256, 0, s, out, idx, dout, lens, dp, pstride, db1,
                                                                                                        db2, db3, B, T, E);
     HCA_LAUNCHED();
     // weight gradients, tap-major: dWr_k[o][kk] = sum_r dcat[r][(k-1)E + o] * Acat[r][a_off + kk]   (K = R, split-K)
@@ -419,9 +429,9 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
       ep.D = dwr[k - 1]; ep.ldd = (int64_t)k * E;
       HCA_TRY(launch_gemm_tc(A, Bm, 2, E, k * E, R, ep, sk, s));
     }
-    unpack_conv_w_kernel<<<ew_grid((int64_t)E * E * 2), 256, 0, s>>>(c.dwr2, dw2, E, 2);
+    HCA_LAUNCH_K((unpack_conv_w_kernel), ew_grid((int64_t)E * E * 2), 256, 0, s, c.dwr2, dw2, E, 2);
     HCA_LAUNCHED();
-    unpack_conv_w_kernel<<<ew_grid((int64_t)E * E * 3), 256, 0, s>>>(c.dwr3, dw3, E, 3);
+    HCA_LAUNCH_K((unpack_conv_w_kernel), ew_grid((int64_t)E * E * 3), 256, 0, s, c.dwr3, dw3, E, 3);
     HCA_LAUNCHED();
     if (dx) {
       // dA[r][a_off + kk] (+)= sum_o dcat[r][(k-1)E + o] * Wr_k[o][kk]: tri first (covers all 3E columns), bi and uni accumulate
@@ -430,7 +440,7 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
         const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
         __nv_bfloat16* wp = c.w.take<__nv_bfloat16>((size_t)2 * w_stride);
         if (!wp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for weight planes");
-        conv_w_planes_kernel<2><<<ew_grid((int64_t)E * E * k), 256, 0, s>>>(ws_[k - 1], wp, w_stride, E, k);
+        HCA_LAUNCH_K((conv_w_planes_kernel<2>), ew_grid((int64_t)E * E * k), 256, 0, s, ws_[k - 1], wp, w_stride, E, k);
         HCA_LAUNCHED();
         TcOperand A, Bm;
         A.planes = dp + (k - 1) * E; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = E;
@@ -439,15 +449,15 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
         ep.D = c.dA + (k == 1 ? E : 0); ep.ldd = ld3; ep.accumulate = (k != 3);
         HCA_TRY(launch_gemm_tc(A, Bm, 2, R, k * E, E, ep, 1, s));
       }
-      col2im3_kernel<<<ew_grid((int64_t)R * E / 4), 256, 0, s>>>((const float4*)c.dA, (float4*)dx, B, T, E / 4);
+      HCA_LAUNCH_K((col2im3_kernel), ew_grid((int64_t)R * E / 4), 256, 0, s, (const float4*)c.dA, (float4*)dx, B, T, E / 4);
       HCA_LAUNCHED();
     }
     return 0;
   }
   float* dcat = c.cat;
-  im2col3_kernel<<<ew_grid((int64_t)R * 3 * E / 4), 256, 0, s>>>((const float4*)x, (float4*)c.acat, B, T, E / 4);
+  HCA_LAUNCH_K((im2col3_kernel), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, (float4*)c.acat, B, T, E / 4);
   HCA_LAUNCHED();
-  pool3_bwd_kernel<<<ew_grid((int64_t)R * E), 256, 0, s>>>(out, idx, dout, lens, dcat, B, T, E);
+  HCA_LAUNCH_K((pool3_bwd_kernel), ew_grid((int64_t)R * E), 256, 0, s, out, idx, dout, lens, dcat, B, T, E);
   HCA_LAUNCHED();
   // bias gradients: column sums of the three blocks of dcat
   float* dbs[3] = {db1, db2, db3};
@@ -462,15 +472,15 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
     HCA_TRY(dense_tn(dcat + (k - 1) * E, 3 * (int64_t)E, c.acat + a_off, 3 * (int64_t)E, dwr[k - 1], (int64_t)k * E,
                      /*M=*/E, /*N=*/k * E, /*K=*/R, /*zero_first=*/true, c.w, s));
   }
-  repack_conv_w_kernel<<<ew_grid((int64_t)E * E * 2), 256, 0, s>>>(c.dwr2, dw2, E, 2, true);
+  HCA_LAUNCH_K((repack_conv_w_kernel), ew_grid((int64_t)E * E * 2), 256, 0, s, c.dwr2, dw2, E, 2, true);
   HCA_LAUNCHED();
-  repack_conv_w_kernel<<<ew_grid((int64_t)E * E * 3), 256, 0, s>>>(c.dwr3, dw3, E, 3, true);
+  HCA_LAUNCH_K((repack_conv_w_kernel), ew_grid((int64_t)E * E * 3), 256, 0, s, c.dwr3, dw3, E, 3, true);
   HCA_LAUNCHED();
   if (dx) {
     // dA[r][kk] = sum_o dcat[r][blk + o] * Wr_k[o][kk], accumulated over the three convs
-    repack_conv_w_kernel<<<ew_grid((int64_t)E * E * 2), 256, 0, s>>>(w2, c.wr2, E, 2, false);
+    HCA_LAUNCH_K((repack_conv_w_kernel), ew_grid((int64_t)E * E * 2), 256, 0, s, w2, c.wr2, E, 2, false);
     HCA_LAUNCHED();
-    repack_conv_w_kernel<<<ew_grid((int64_t)E * E * 3), 256, 0, s>>>(w3, c.wr3, E, 3, false);
+    HCA_LAUNCH_K((repack_conv_w_kernel), ew_grid((int64_t)E * E * 3), 256, 0, s, w3, c.wr3, E, 3, false);
     HCA_LAUNCHED();
     const float* wr[3] = {w1, c.wr2, c.wr3};
     for (int k = 3; k >= 1; --k) {   // tri first (covers all 3E columns, plain store), then bi, uni accumulate
@@ -479,7 +489,7 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
       HCA_TRY(dense_nn(dcat + (k - 1) * E, 3 * (int64_t)E, wr[k - 1], (int64_t)k * E, c.dA + ((k == 1) ? E : 0), 3 * (int64_t)E,
                        /*M=*/R, /*N=*/k * E, /*K=*/E, e, c.w, s));
     }
-    col2im3_kernel<<<ew_grid((int64_t)R * E / 4), 256, 0, s>>>((const float4*)c.dA, (float4*)dx, B, T, E / 4);
+    HCA_LAUNCH_K((col2im3_kernel), ew_grid((int64_t)R * E / 4), 256, 0, s, (const float4*)c.dA, (float4*)dx, B, T, E / 4);
     HCA_LAUNCHED();
   }
   return 0;

@@ -32,6 +32,11 @@ bool use_tc() {
   return m == 1;
 }
 
+bool pdl_enabled() {
+  const char* e = getenv("HCA_PDL");          // read per launch: a profiler leg may switch it off to get exclusive kernel durations
+  return !(e && atoi(e) == 0);
+}
+
 namespace {
 struct SideRes {
   cudaStream_t s = nullptr;

@@ -5,6 +5,7 @@ namespace {
 // 256 threads = 32 columns x 8 row lanes; one block reduces 32 columns over a 512-row slab.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ld, int64_t rows, int cols,
                                                      float* __restrict__ out) {
+  pdl_enter();
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -24,7 +25,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
 
 int launch_colsum(const float* X, int64_t ld, int64_t rows, int cols, float* out, cudaStream_t s) {
   dim3 grid((cols + 31) / 32, (unsigned)((rows + 511) / 512));
-  colsum_kernel<<<grid, 256, 0, s>>>(X, ld, rows, cols, out);
+  HCA_LAUNCH_K((colsum_kernel), grid, 256, 0, s, X, ld, rows, cols, out);
   HCA_LAUNCHED();
   return 0;
 }
