@@ -96,7 +96,7 @@ __device__ __forceinline__ float col_reduce32(float (&v)[32], int lane) {
 // of A and HALF of the B tile, the leader issues M = 256 MMAs that read both halves, and each CTA drains its own 128 accumulator
 // lanes.  Per output element only half the operand bytes cross the L2 -> SM fabric -- the measured limit of the big K-major
 // products (profiles/r1c_pv_gemm_ncu_full.md: 83 B/clk/SM of operand fill against a ~43 B/clk/SM chip-wide L2 cap).
-// EPI = 0: "lean" epilogue (bias, fp32 / planes output, split-K reduce-add): the feature blocks of the full epilogue (addend tiles, tanh,
+// EPI = 0: "lean" epilogue (bias, fp32 / planes output, split-K reduce-add; EPI = 2 adds tanh): the feature blocks of the full epilogue (addend tiles,
 // row dots, dZ, rank-1 terms, column sums) are compiled out.  The profile of the full variant on a plain product showed the chunk loop
 // executing ~340 of ~3200 instructions, with 22 % of its stall samples waiting for instruction fetch and 7 % resolving branches.
 template <int BN, int P, bool A_MN, bool B_MN, int BK, int CG = 1, int EPI = 1>
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const int aux_kind = FULL ? p.aux_kind : 0;
       const int aux_mode = FULL ? p.aux_mode : (int)TC_AUX_NONE;
       const int mode = FULL ? p.mode : (int)TC_EPI_STORE;
-      const bool act_tanh = FULL && p.act_tanh != 0;
+      const bool act_tanh = (EPI != 0) && p.act_tanh != 0;       // EPI = 2: the lean epilogue + tanh
       const bool has_r1 = FULL && CG == 1 && p.r1col != nullptr;
       const float* const mulx = FULL ? p.mulx : nullptr;
       const float* const rowv = FULL ? p.rowv : nullptr;
@@ -1174,24 +1174,26 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   const int combo = (A.mn_major ? 2 : 0) + (B.mn_major ? 1 : 0);    // 0 = NT (K,K), 1 = NN (K,MN), 2 = (MN,K), 3 = TN (MN,MN)
   int slot = -1;
   // lean epilogue instantiation (EPI = 0) for products without fused epilogue math; HCA_TC_LEAN=0 forces the full one
-  bool lean = !e.transposed && !e.act_tanh && e.aux_mode == TC_AUX_NONE && e.mode == TC_EPI_STORE && !e.r1col && !e.mulx && !e.red_col &&
-              !e.rowv && !e.colv;
+  bool lean = !e.transposed && e.aux_mode == TC_AUX_NONE && e.mode == TC_EPI_STORE && !e.r1col && !e.mulx && !e.red_col && !e.rowv && !e.colv;
   { const char* ev = getenv("HCA_TC_LEAN"); if (ev && atoi(ev) == 0) lean = false; }
-#define HCA_TC_CASE(SLOT, BNN, PP, CC, AMN, BMN, BKK)                                                   \
-  if (BN == BNN && P == PP && combo == CC && BK == BKK) {                                                \
-    if (lean && BNN != 32) { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK, 1, 0>; slot = SLOT + 10; }      \
-    else { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK, 1, 1>; slot = SLOT; }                             \
+  const bool lean_tanh = lean && e.act_tanh;
+#define HCA_TC_CASE(SLOT, BNN, PP, CC, AMN, BMN, BKK)                                                            \
+  if (BN == BNN && P == PP && combo == CC && BK == BKK) {                                                         \
+    else if (lean_tanh && BNN != 32) { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK, 1, 2>; slot = SLOT + 20; }     \
+    else if (lean && BNN != 32) { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK, 1, 0>; slot = SLOT + 10; }          \
+    else { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK, 1, 1>; slot = SLOT; }                                      \
   }
   HCA_TC_CASE(0, 128, 2, 0, false, false, 64) HCA_TC_CASE(1, 128, 2, 1, false, true, 64) HCA_TC_CASE(2, 128, 2, 3, true, true, 64)
   HCA_TC_CASE(3, 128, 3, 0, false, false, 64) HCA_TC_CASE(4, 128, 3, 1, false, true, 64) HCA_TC_CASE(5, 128, 3, 3, true, true, 64)
   HCA_TC_CASE(6, 32, 2, 0, false, false, 64) HCA_TC_CASE(7, 32, 2, 2, true, false, 64) HCA_TC_CASE(8, 128, 2, 3, true, true, 32)
 #undef HCA_TC_CASE
   if (pair) {
-    if (lean) { fn = gemm_tc_kernel<256, 2, false, false, 64, 2, 0>; slot = 19; }
+    if (lean_tanh) { fn = gemm_tc_kernel<256, 2, false, false, 64, 2, 2>; slot = 29; }
+    else if (lean) { fn = gemm_tc_kernel<256, 2, false, false, 64, 2, 0>; slot = 19; }
     else { fn = gemm_tc_kernel<256, 2, false, false, 64, 2, 1>; slot = 9; }
   }
   HCA_CHECK_ARG(fn != nullptr, "gemm_tc: this (BN, P, layout) combination is not instantiated (BN=%d P=%d combo=%d)", BN, P, combo);
-  static bool attr_set[20] = {};
+  static bool attr_set[30] = {};
   if (!attr_set[slot]) {
     HCA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
     attr_set[slot] = true;
