@@ -1179,7 +1179,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   const bool lean_tanh = lean && e.act_tanh;
 #define HCA_TC_CASE(SLOT, BNN, PP, CC, AMN, BMN, BKK)                                                            \
   if (BN == BNN && P == PP && combo == CC && BK == BKK) {                                                         \
-    else if (lean_tanh && BNN != 32) { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK, 1, 2>; slot = SLOT + 20; }     \
+    if (lean_tanh && BNN != 32) { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK, 1, 2>; slot = SLOT + 20; }          \
     else if (lean && BNN != 32) { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK, 1, 0>; slot = SLOT + 10; }          \
     else { fn = gemm_tc_kernel<BNN, PP, AMN, BMN, BKK, 1, 1>; slot = SLOT; }                                      \
   }
