@@ -162,7 +162,10 @@ class Stepper:
         self.net.to(device)
         # graph mode: the bucketed all-reduce follows backward inside the captured step (hook-launched NCCL did not replay
         # reliably from a captured graph: observed a hang); eager mode launches each bucket from the gradient hooks instead
-        self.dp = pkg.dp.FlatGradAllReduce(self.net.named_parameters(), group, overlap=not use_graph, flat_params=True)
+        # (graph mode reduces after backward, so ONE collective over the whole 48.7 MB buffer beats four 16 MB buckets: fewer launches,
+        # better NVLink / NVSwitch efficiency per message)
+        self.dp = pkg.dp.FlatGradAllReduce(self.net.named_parameters(), group, overlap=not use_graph, flat_params=True,
+                                           bucket_bytes=(1 << 30) if use_graph else (16 << 20))
         self.opt = pkg.optim.FlatAdam(self.dp, lr=1e-4)          # Adam(lr=1e-4), README.md:95-100 / main.py:180
         self.criterion = pkg.CrossEntropyLoss(scale=self.dp.loss_scale)   # nn.CrossEntropyLoss(), main.py:179
         self.slots = []
