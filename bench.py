@@ -218,8 +218,8 @@ class Stepper:
 
 
 # ncu --set full capture of this kernel (profiles/): DRAM bytes per launch, read + write.  None until a capture is committed.
-ROOFLINE_TRAFFIC_BYTES = 86.4e6
-ROOFLINE_TRAFFIC_SOURCE = "profiles/r1c_pv_gemm_ncu_full.md: dram__bytes_read.sum 65.4 MB + dram__bytes_write.sum 21.0 MB, one launch"
+ROOFLINE_TRAFFIC_BYTES = 81.6e6
+ROOFLINE_TRAFFIC_SOURCE = "profiles/r1d_pv_gemm_ncu_full.md: dram__bytes_read.sum 65.4 MB + dram__bytes_write.sum 16.2 MB, one launch"
 
 
 def time_roofline_kernel(pkg, device, steps, pk):
@@ -246,7 +246,8 @@ def time_roofline_kernel(pkg, device, steps, pk):
     # the split-precision path issues 3 bf16 MMAs per algorithmic product; `achieved` is ALGORITHMIC TFLOP/s against the bf16 peak
     return {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
             "traffic": ROOFLINE_TRAFFIC_BYTES, "traffic_source": ROOFLINE_TRAFFIC_SOURCE,
-            "kernel": "gemm_tc_kernel<128,2,K-major,K-major,64>: PV = V.Wv^T + bv, M=31360 N=512 K=512, bf16 hi/lo planes in and out",
+            "kernel": "gemm_tc_kernel<256,2,K-major,K-major,64,CG=2,EPI=0> (CTA pair, cta_group::2): PV = V.Wv^T + bv, M=31360 N=512 K=512, "
+                      "bf16 hi/lo planes in and out",
             "ms_per_launch": ms, "algorithmic_flops_per_launch": flops, "issued_mma_flops_per_launch": 3.0 * flops,
             "frac_issued": 3.0 * achieved / pk["bf16_tflops"],
             "algorithmic_bytes_per_launch": 2.0 * (2 * M * K * 2) + 2 * N * K * 2,
