@@ -88,3 +88,25 @@ def test_gemm_cta_pair_mode_matches_single_cta(M, N, K):
             os.environ.pop("HCA_TC_PAIR", None)
         else:
             os.environ["HCA_TC_PAIR"] = prev
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 512, 4160), (2048, 512, 4160), (512, 1536, 4160)])
+def test_gemm_cta_pair_weight_gradient_shapes(M, N, K):
+    """Split-K weight-gradient products (both operands MN-major) through the CTA-pair kernel and through the single-CTA one."""
+    import os
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B = torch.randn(K, M, generator=g), torch.randn(K, N, generator=g)
+    ref = A.double().T @ B.double()
+    prev = os.environ.get("HCA_TC_PAIR_WGRAD")
+    try:
+        for mode in ("1", "0"):
+            os.environ["HCA_TC_PAIR_WGRAD"] = mode
+            D = ops.gemm(A.cuda(), B.cuda(), None, layout="tn", path=1)
+            torch.cuda.synchronize()
+            assert float((D.double().cpu() - ref).norm() / ref.norm()) < 3e-5, (mode, M, N, K)
+    finally:
+        if prev is None:
+            os.environ.pop("HCA_TC_PAIR_WGRAD", None)
+        else:
+            os.environ["HCA_TC_PAIR_WGRAD"] = prev

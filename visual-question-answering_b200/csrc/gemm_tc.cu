@@ -103,7 +103,7 @@ template <int BN, int P, bool A_MN, bool B_MN, int BK, int CG = 1, int EPI = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   pdl_trigger();      // (the wait follows the set-up below: barrier init, descriptor prefetch and TMEM allocation touch no dependent data)
   static_assert(BK == 64 || (BK == 32 && A_MN && B_MN), "BK = 32 k-blocks are for MN-major operand pairs (short contractions)");
-  static_assert(CG == 1 || (CG == 2 && BN == 256 && !A_MN && !B_MN && BK == 64), "CTA-pair mode: K-major operands, 256-wide tiles");
+  static_assert(CG == 1 || (CG == 2 && BN == 256 && A_MN == B_MN && BK == 64), "CTA-pair mode: (K,K) or (MN,MN) operands, 256-wide tiles");
   constexpr int A_TILE_BYTES = BM * BK * 2;
   constexpr int B_ROWS = BN / CG;                         // rows of the B tile this CTA loads
   constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
@@ -207,8 +207,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             const int k0 = (tc.kb_begin + it) * BK;
 #pragma unroll
             for (int pl = 0; pl < P; ++pl) {
-              tma_load_4d_2sm(a_tile(s, pl), &maps.A, full_bar(s), k0, tc.m0, pl, 0);
-              tma_load_4d_2sm(b_tile(s, pl), &maps.B, full_bar(s), k0, tc.n0 + rank * B_ROWS, pl, 0);
+              if constexpr (!A_MN) {
+                tma_load_4d_2sm(a_tile(s, pl), &maps.A, full_bar(s), k0, tc.m0, pl, 0);
+                tma_load_4d_2sm(b_tile(s, pl), &maps.B, full_bar(s), k0, tc.n0 + rank * B_ROWS, pl, 0);
+              } else {                                        // MN-major pair (weight gradients): [BK k][64 mn] boxes
+#pragma unroll
+                for (int c = 0; c < BM / 64; ++c)
+                  tma_load_4d_2sm(a_tile(s, pl) + c * MN_CHUNK_BYTES, &maps.A, full_bar(s), tc.m0 + c * 64, k0, pl, 0);
+#pragma unroll
+                for (int c = 0; c < B_ROWS / 64; ++c)
+                  tma_load_4d_2sm(b_tile(s, pl) + c * MN_CHUNK_BYTES, &maps.B, full_bar(s), tc.n0 + rank * B_ROWS + c * 64, k0, pl, 0);
+              }
             }
             if (++s == p.stages) { s = 0; ph ^= 1; }
             continue;
@@ -981,9 +990,14 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   HCA_CHECK_ARG(!e.transposed || P == 2, "gemm_tc: the transposed epilogue is instantiated for P = 2");
   // CTA-pair mode (cta_group::2, 256 x 256 tiles per pair): the large K-major products with a plain epilogue, where the L2 -> SM
   // operand fill is the limit.  HCA_TC_PAIR=0 disables it, =1 also takes smaller M (tests).
-  bool pair = !e.transposed && P == 2 && !A.mn_major && !B.mn_major && !A2 && splitk == 1 && batch == 1 && (N % 256) == 0 &&
-              M >= 8192 && K >= 256 && e.mode == TC_EPI_STORE && e.aux_mode == TC_AUX_NONE && !e.r1col && !e.mulx && e.d_groups <= 1 &&
-              A.nbatch <= 1 && B.nbatch <= 1 && num_sms() >= 2;
+  const bool pair_epi = !e.transposed && P == 2 && !A2 && batch == 1 && e.mode == TC_EPI_STORE && e.aux_mode == TC_AUX_NONE && !e.r1col &&
+                        !e.mulx && e.d_groups <= 1 && A.nbatch <= 1 && B.nbatch <= 1 && num_sms() >= 2;
+  // (a) large K-major projections, (b) split-K weight gradients (both operands MN-major, plain fp32 reduce-add epilogue, K long
+  // enough to leave every pair several k-blocks): there the mainloop's operand fill is the limit and the pair halves it
+  bool pair_wgrad = pair_epi && splitk > 1 /* the caller has cleared D */ && A.mn_major && B.mn_major && (M % 256) == 0 && (N % 256) == 0 && K >= 2048 && !e.bias && !e.act_tanh &&
+                    !e.red_col && !e.P.p && e.D != nullptr && f32_tma_ok(e.D, e.ldd, e.d_batch_stride, 0);
+  { const char* ev = getenv("HCA_TC_PAIR_WGRAD"); if (ev && atoi(ev) == 0) pair_wgrad = false; }
+  bool pair = pair_epi && !A.mn_major && !B.mn_major && splitk == 1 && (N % 256) == 0 && M >= 8192 && K >= 256;
   if (pair) {
     // wave quantisation: a pair tile is four single tiles of MMA time on two SMs.  Take the pair schedule only when its last,
     // partly filled wave does not cost more than the fabric traffic it saves (PV, M = 31360: 4 pair waves vs 7 single waves;
@@ -999,6 +1013,18 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
     if (pair_env == 1 && !e.transposed && P == 2 && !A.mn_major && !B.mn_major && !A2 && splitk == 1 && batch == 1 && (N % 256) == 0 &&
         e.mode == TC_EPI_STORE && e.aux_mode == TC_AUX_NONE && !e.r1col && !e.mulx && e.d_groups <= 1 && A.nbatch <= 1 && B.nbatch <= 1)
       pair = true;
+  }
+  if (pair_wgrad) {
+    const char* ev = getenv("HCA_TC_PAIR");
+    if (ev && atoi(ev) == 0) pair_wgrad = false;
+  }
+  if (pair_wgrad) {
+    pair = true;
+    // the split is chosen for the pair grid: one 256 x 256 tile per pair and wave, at least 4 k-blocks per split
+    const int t2 = (M / 256) * (N / 256), nc = num_sms() / 2, kbt = (K + 63) / 64;
+    int sk = (nc + t2 - 1) / t2;
+    if (sk > kbt / 4) sk = kbt / 4;
+    splitk = sk < 1 ? 1 : sk;
   }
   const int BN = e.transposed ? 32 : (pair ? 256 : 128);
   const int CGn = pair ? 2 : 1;
@@ -1188,7 +1214,8 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   HCA_TC_CASE(6, 32, 2, 0, false, false, 64) HCA_TC_CASE(7, 32, 2, 2, true, false, 64) HCA_TC_CASE(8, 128, 2, 3, true, true, 32)
 #undef HCA_TC_CASE
   if (pair) {
-    if (lean_tanh) { fn = gemm_tc_kernel<256, 2, false, false, 64, 2, 2>; slot = 29; }
+    if (A.mn_major) { fn = gemm_tc_kernel<256, 2, true, true, 64, 2, 0>; slot = 28; }
+    else if (lean_tanh) { fn = gemm_tc_kernel<256, 2, false, false, 64, 2, 2>; slot = 29; }
     else if (lean) { fn = gemm_tc_kernel<256, 2, false, false, 64, 2, 0>; slot = 19; }
     else { fn = gemm_tc_kernel<256, 2, false, false, 64, 2, 1>; slot = 9; }
   }
