@@ -110,6 +110,10 @@ HCA_API int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_t v
                    const float* wv, const float* cv, const float* wq, const float* cq,
                    float* vhat, float* qhat, void* saved, size_t saved_bytes,
                    int B, int N, int T, int d, void* ws, size_t ws_bytes, void* stream);
+/* Byte offsets, inside the `saved` buffer hca_coattn_fwd has filled, of the attention weights (fp32): a_v [B][3][N] and
+ * a_q [B][3][T] (level order word, phrase, sentence; softmax over regions / over all T token positions, model.py:387-388).
+ * For attention-map export at inference time (README "Inference", TO-DO in the reference). */
+HCA_API int hca_coattn_saved_attention(int B, int N, int T, int d, size_t* av_offset, size_t* aq_offset);
 /* gvhat,gqhat [3,B,d] = dL/dvhat, dL/dqhat.  Outputs: dQ [3,B,T,d] (dQ[l] = gradient of q_l); dWv,dWq [d,d];
  * dbv,dbq,dwv,dwq [d]; dcv,dcq [1]; dV [B,N,d] dense or null when the image features need no gradient (frozen
  * VGG, main.py:67).  Weight gradients are summed over batch and levels. */

@@ -326,3 +326,23 @@ def test_flat_gradient_sink_direct_write(syn):
                 assert h.rel(g, ref_b[n]) < 1e-4, n
     finally:
         h.PKG.ops.remove_grad_sink(red)
+
+
+def test_inference_predict_and_attention_maps(syn):
+    """Attention-map export / top-k prediction: a_v, a_q against the oracle's softmaxes, top-1 against its logits."""
+    h = _h()
+    d, N, T, vocab, K, mlp = 64, 12, 6, 50, 9, 32
+    p = syn.make_params(d, vocab, K, mlp, seed=6)
+    x = syn.make_inputs(5, N, T, d, vocab, K, seed=8, min_len=1)
+    net = h.build_net(p, d, vocab, K, mlp).eval()
+    feats = torch.from_numpy(x["feats"]).cuda()
+    prob, idx, a_v, a_q = net.predict(feats, torch.from_numpy(x["tokens"]).cuda(), torch.from_numpy(x["lens"]), topk=3, return_attention=True)
+    assert prob.shape == (5, 3) and idx.shape == (5, 3) and a_v.shape == (5, 3, N) and a_q.shape == (5, 3, T)
+    assert torch.allclose(a_v.sum(-1), torch.ones_like(a_v.sum(-1)), atol=1e-5) and torch.allclose(a_q.sum(-1), torch.ones_like(a_q.sum(-1)), atol=1e-5)
+    pp = {k: v.astype(np.float64) for k, v in p.items()}
+    ref_logits = h.O.hiecoattn_forward(pp, x["feats"].astype(np.float64), x["tokens"], x["lens"])
+    assert (idx[:, 0].cpu().numpy() == ref_logits.argmax(1)).all()
+    orc = h.run_oracle(p, x, np.float64)
+    for l, c in enumerate(orc["cache"]["ca_caches"]):          # per-level caches of the oracle: av [B,N], aq [B,T]
+        assert h.rel(a_v[:, l].cpu().numpy(), np.asarray(c["av"]).reshape(5, N)) < 1e-4
+        assert h.rel(a_q[:, l].cpu().numpy(), np.asarray(c["aq"]).reshape(5, T)) < 1e-4

@@ -36,6 +36,7 @@ SIGNATURES = {
     "hca_lstm_bwd": (_i, [_p] * 4 + [_sz] + [_p] * 6 + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_coattn_workspace": (_sz, [_i, _i, _i, _i, _i]),
     "hca_coattn_saved_bytes": (_sz, [_i, _i, _i, _i]),
+    "hca_coattn_saved_attention": (_i, [_i, _i, _i, _i, C.POINTER(_sz), C.POINTER(_sz)]),
     "hca_coattn_fwd": (_i, [_p, _i64, _i64, _i64] + [_p] * 14 + [_sz] + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_coattn_bwd": (_i, [_p] * 5 + [_sz] + [_p] * 12 + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_mlp_workspace": (_sz, [_i, _i, _i, _i]),

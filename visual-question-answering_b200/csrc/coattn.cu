@@ -40,6 +40,28 @@ __global__ void __launch_bounds__(256) gather_strided_kernel(const float* __rest
   }
 }
 
+// Same for the layout the reference's image encoder hands over (model.py:217: a [B, d, N] feature map viewed as [B, N, d], i.e.
+// region stride 1 and channel stride N): a 32 x 32 shared-memory tile transpose, coalesced on both sides (the element-wise gather
+// above reads that layout with a stride of N floats per thread).
+__global__ void __launch_bounds__(256) gather_transposed_kernel(const float* __restrict__ V, int64_t sb, int64_t sd,
+                                                                float* __restrict__ out, int N, int d) {
+  pdl_enter();
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* src = V + (int64_t)b * sb;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, n = n0 + tx;
+    if (c < d && n < N) tile[i][tx] = src[(int64_t)c * sd + n];
+  }
+  __syncthreads();
+  float* dst = out + (int64_t)b * N * d;
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, c = c0 + tx;
+    if (n < N && c < d) dst[(int64_t)n * d + c] = tile[tx][i];
+  }
+}
+
 // one warp: a = softmax(s + c) over L entries; a -> smem and global
 __device__ __forceinline__ void softmax_warp(const float* __restrict__ s, float cbias, int L, float* a_sm, float* __restrict__ a_out) {
   const int lane = threadIdx.x & 31;
@@ -183,26 +205,39 @@ struct RowDotRegs {
           g[v][j][k] = c < d ? g_sm[v * g_stride + c] : 0.f;
         }
   }
-  // rows are processed TWO at a time so that four 16-byte loads per lane are in flight before the first reduction
-  __device__ __forceinline__ void dots(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int d, float (&out)[NG]) const {
+  // all four 16-byte loads of a row (hi / lo x two column groups) are issued before the first multiply
+  __device__ __forceinline__ void load_row(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int d, uint4 (&h)[2],
+                                           uint4 (&l)[2]) const {
     const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = lane * 8 + 256 * j;
+      h[j] = make_uint4(0u, 0u, 0u, 0u);
+      l[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (c < d) {
+        h[j] = __ldg(reinterpret_cast<const uint4*>(hi + c));
+        l[j] = __ldg(reinterpret_cast<const uint4*>(lo + c));
+      }
+    }
+  }
+  __device__ __forceinline__ void fma_row(const uint4 (&h)[2], const uint4 (&l)[2], float (&out)[NG]) const {
 #pragma unroll
     for (int v = 0; v < NG; ++v) out[v] = 0.f;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const int c = lane * 8 + 256 * j;
-      if (c < d) {
-        const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + c));
-        const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + c));
-        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+      const uint32_t hw[4] = {h[j].x, h[j].y, h[j].z, h[j].w}, lw[4] = {l[j].x, l[j].y, l[j].z, l[j].w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float x0 = bf2f_lo(hw[k]) + bf2f_lo(lw[k]), x1 = bf2f_hi(hw[k]) + bf2f_hi(lw[k]);
+      for (int k = 0; k < 4; ++k) {
+        const float x0 = bf2f_lo(hw[k]) + bf2f_lo(lw[k]), x1 = bf2f_hi(hw[k]) + bf2f_hi(lw[k]);
 #pragma unroll
-          for (int v = 0; v < NG; ++v) out[v] = fmaf(x1, g[v][j][2 * k + 1], fmaf(x0, g[v][j][2 * k], out[v]));
-        }
+        for (int v = 0; v < NG; ++v) out[v] = fmaf(x1, g[v][j][2 * k + 1], fmaf(x0, g[v][j][2 * k], out[v]));
       }
     }
+  }
+  __device__ __forceinline__ void dots(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int d, float (&out)[NG]) const {
+    uint4 h[2], l[2];
+    load_row(hi, lo, d, h, l);
+    fma_row(h, l, out);
 #pragma unroll
     for (int v = 0; v < NG; ++v) out[v] = warp_sum(out[v]);
   }
@@ -246,7 +281,27 @@ __global__ void __launch_bounds__(256) attn_bwd_dots_kernel(const __nv_bfloat16*
   if (d <= 512) {
     RowDotRegs<3> rd;
     rd.load(gv_sm, d, d);
-    for (int n = sp * nw + w; n < N; n += nw * ATTN_SPLIT) {
+    // two rows per iteration: eight 16-byte loads per lane in flight before the first reduction (the loop is latency-bound otherwise)
+    const int stride = nw * ATTN_SPLIT;
+    int n = sp * nw + w;
+    for (; n + stride < N; n += 2 * stride) {
+      const __nv_bfloat16* hi0 = Vp + ((int64_t)b * N + n) * d;
+      const __nv_bfloat16* hi1 = hi0 + (int64_t)stride * d;
+      uint4 h0[2], l0[2], h1[2], l1[2];
+      rd.load_row(hi0, hi0 + v_ps, d, h0, l0);
+      rd.load_row(hi1, hi1 + v_ps, d, h1, l1);
+      float o0[3], o1[3];
+      rd.fma_row(h0, l0, o0);
+      rd.fma_row(h1, l1, o1);
+#pragma unroll
+      for (int v = 0; v < 3; ++v) { o0[v] = warp_sum(o0[v]); o1[v] = warp_sum(o1[v]); }
+      if (lane == 0) {
+        float* dst = dav + (int64_t)b * 3 * N + n;
+        dst[0] = o0[0]; dst[N] = o0[1]; dst[2 * N] = o0[2];
+        dst[stride] = o1[0]; dst[N + stride] = o1[1]; dst[2 * N + stride] = o1[2];
+      }
+    }
+    for (; n < N; n += stride) {
       const __nv_bfloat16* hi = Vp + ((int64_t)b * N + n) * d;
       float o[3];
       rd.dots(hi, hi + v_ps, d, o);
@@ -414,6 +469,19 @@ extern "C" size_t hca_coattn_workspace(int B, int N, int T, int d, int need_dv) 
   return std::max(fwd, bwd) + 4096;
 }
 
+// Byte offsets of the attention weights inside `saved` (fp32, written by hca_coattn_fwd): a_v [B][3][N] (softmax over the N regions,
+// per level) and a_q [B][3][T] (softmax over all T token positions, pads included: reference model.py:387-388).  The rest of the
+// buffer stays private to the library; this is the hook for attention-map export (README "Inference", left TO-DO by the reference).
+extern "C" int hca_coattn_saved_attention(int B, int N, int T, int d, size_t* av_offset, size_t* aq_offset) {
+  using namespace hca;
+  HCA_CHECK_ARG(B > 0 && N > 0 && T > 0 && d > 0 && av_offset && aq_offset, "coattn_saved_attention: bad arguments");
+  const int64_t BN = (int64_t)B * N, BT3 = (int64_t)B * 3 * T;
+  const size_t av = 2 * pl_bytes(BN, d) + 2 * pl_bytes(BT3, d) + pl_bytes(BT3, N);
+  *av_offset = av;
+  *aq_offset = av + align_up((size_t)B * 3 * N * 4);
+  return 0;
+}
+
 extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_t v_sd, const float* q0, const float* q1,
                               const float* q2, const float* Wv, const float* bv, const float* Wq, const float* bq,
                               const float* wv, const float* cv, const float* wq, const float* cq, float* vhat, float* qhat,
@@ -433,7 +501,11 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
   if (!v_is_dense(v_sb, v_sn, v_sd, N, d)) {
     float* vc = w.take<float>((size_t)BN * d);
     if (!vc) return set_err(HCA_ERR_WORKSPACE, "coattn_fwd: workspace too small");
-    HCA_LAUNCH_K((gather_strided_kernel), ew_grid(BN * d), 256, 0, s, V, v_sb, v_sn, v_sd, vc, B, N, d);
+    if (v_sn == 1 && B <= 65535) {            // channel-major feature map (the VGG encoder's view): tiled transpose
+      HCA_LAUNCH_K((gather_transposed_kernel), dim3((N + 31) / 32, (d + 31) / 32, B), 256, 0, s, V, v_sb, v_sd, vc, N, d);
+    } else {
+      HCA_LAUNCH_K((gather_strided_kernel), ew_grid(BN * d), 256, 0, s, V, v_sb, v_sn, v_sd, vc, B, N, d);
+    }
     HCA_LAUNCHED();
     Vd = vc;
   }

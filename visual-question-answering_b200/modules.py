@@ -143,6 +143,18 @@ class ParallelCoAttention(nn.Module):
                          self.w_v.weight, self.w_v.bias, self.w_q.weight, self.w_q.bias)
         return out[0], out[1]
 
+    @torch.no_grad()
+    def attention_maps(self, x_img: Tensor, x_ques_hierarchy: Sequence[Tensor]) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        """Inference-time export of the co-attention: (vhat [3,B,d], qhat [3,B,d], a_v [B,3,N], a_q [B,3,T]) -- the weights over
+        the N image regions and over the T token positions at the word / phrase / sentence level (model.py:387-388).  The
+        reference computes them and throws them away; its README leaves visualisation as a TO-DO."""
+        q0, q1, q2 = (_f32(q) for q in x_ques_hierarchy)
+        vhat, qhat, saved = ops.coattn(_f32(x_img), q0, q1, q2, self.W_v.weight, self.W_v.bias, self.W_q.weight, self.W_q.bias,
+                                       self.w_v.weight, self.w_v.bias, self.w_q.weight, self.w_q.bias)
+        B, N, d = x_img.shape
+        a_v, a_q = ops.coattn_attention_maps(saved, B, N, q0.shape[1], d)
+        return vhat, qhat, a_v.clone(), a_q.clone()
+
     def forward(self, x_img: Tensor, x_ques_hierarchy: Sequence[Tensor]) -> Tuple[List[Tensor], List[Tensor]]:
         if len(x_ques_hierarchy) != 3:
             raise ValueError("ParallelCoAttention expects the (word, phrase, sentence) hierarchy: 3 tensors")
@@ -245,6 +257,16 @@ class HieCoAttnHotPath(nn.Module):
         hier = self.question_encoder(x_ques, x_ques_lens)
         vhat, qhat = self.co_attention.forward_stacked(x_img_features, hier)
         return self.mlp_classify.forward_stacked(vhat, qhat)
+
+    @torch.no_grad()
+    def predict(self, x_img_features, x_ques, x_ques_lens, topk: int = 5, return_attention: bool = False):
+        """Inference (the reference's unimplemented ``--mode test``, main.py:286-287): top-k answer classes with their softmax
+        probabilities, optionally with the attention maps (a_v [B,3,N] over regions, a_q [B,3,T] over tokens)."""
+        hier = self.question_encoder(x_ques, x_ques_lens)
+        vhat, qhat, a_v, a_q = self.co_attention.attention_maps(x_img_features, hier)
+        logits = self.mlp_classify.forward_stacked(vhat, qhat)
+        prob, idx = torch.softmax(logits, dim=1).topk(min(topk, logits.shape[1]), dim=1)
+        return (prob, idx, a_v, a_q) if return_attention else (prob, idx)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -373,6 +373,16 @@ def _coattn_backward(ctx, gv, gq, *_unused):
 coattn.register_autograd(_coattn_backward, setup_context=_coattn_setup)
 
 
+def coattn_attention_maps(saved: Tensor, B: int, N: int, T: int, d: int) -> Tuple[Tensor, Tensor]:
+    """The attention weights a forward call of ``coattn`` left in its ``saved`` buffer: (a_v [B,3,N], a_q [B,3,T]) as views."""
+    import ctypes as C
+    av, aq = C.c_size_t(0), C.c_size_t(0)
+    _lib.check(_lib.lib().hca_coattn_saved_attention(B, N, T, d, C.byref(av), C.byref(aq)), "coattn_saved_attention")
+    a_v = saved[av.value:av.value + B * 3 * N * 4].view(torch.float32).view(B, 3, N)
+    a_q = saved[aq.value:aq.value + B * 3 * T * 4].view(torch.float32).view(B, 3, T)
+    return a_v, a_q
+
+
 # -------------------------------------------------------------------------------------------------------- MLP
 @torch.library.custom_op(f"{NS}::mlp", mutates_args=(), device_types="cuda")
 def mlp(vhat: Tensor, qhat: Tensor, Ww: Tensor, bw: Tensor, Wp: Tensor, bp: Tensor, Ws: Tensor, bs: Tensor, Wh: Tensor,
