@@ -346,3 +346,21 @@ def test_inference_predict_and_attention_maps(syn):
     for l, c in enumerate(orc["cache"]["ca_caches"]):          # per-level caches of the oracle: av [B,N], aq [B,T]
         assert h.rel(a_v[:, l].cpu().numpy(), np.asarray(c["av"]).reshape(5, N)) < 1e-4
         assert h.rel(a_q[:, l].cpu().numpy(), np.asarray(c["aq"]).reshape(5, T)) < 1e-4
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_random_ragged_shapes_full_step(seed, syn):
+    """Randomly drawn small shapes (ragged tiles everywhere: N, T, K, B not multiples of anything; d, mlp multiples of 8 as the
+    operand planes require): logits + every gradient + dfeats against the fp64 oracle."""
+    h = _h()
+    rng = np.random.RandomState(1000 + seed)
+    d = int(rng.choice([8, 16, 40, 64, 96, 136]))
+    mlp = int(rng.choice([8, 24, 40, 72, 136]))
+    N, T, B, K, vocab = int(rng.randint(1, 71)), int(rng.randint(1, 13)), int(rng.randint(1, 10)), int(rng.randint(2, 41)), int(rng.randint(5, 60))
+    p = syn.make_params(d, vocab, K, mlp, seed=seed)
+    x = syn.make_inputs(B, N, T, d, vocab, K, seed=seed + 50, dist="D1" if seed % 2 else "D2", min_len=1)
+    net = h.build_net(p, d, vocab, K, mlp)
+    ours = h.run_ours(net, x, feats_grad=True, lens_on="both" if seed % 3 else "cuda")
+    orc = h.run_oracle(p, x, np.float64, need_dfeats=True)
+    errs = h.compare(ours, orc, tol=1e-3, check_dfeats=True)
+    print(dict(d=d, mlp=mlp, N=N, T=T, B=B, K=K), f"worst {max(v for k, v in errs.items() if k not in h.ZERO_BIASES):.1e}")
