@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HCA_ABI_VERSION 4
+#define HCA_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define HCA_API __attribute__((visibility("default")))
@@ -67,13 +67,18 @@ HCA_API int hca_embedding_bwd(const int64_t* tokens, const float* dout, float* d
  * out [B,T,E]; idx [B,T,E] uint8 = position (0..2) inside the consecutive channel triple of
  * [uni|bi|tri] that attained the max, first index on ties (MaxPool2d((1,3)), model.py:311,329-332). */
 HCA_API size_t hca_phrase_conv_pool_workspace(int B, int T, int E);
+/* `fsaved` (optional, hca_phrase_conv_pool_saved_bytes, 256-byte aligned, opaque): when non-null the forward leaves the bf16 operand
+ * planes of the row-shifted input and of the three weights there, and a backward call that is handed the same buffer reuses them instead
+ * of converting the operands again (the weights do not change between the forward and the backward of a step). */
+HCA_API size_t hca_phrase_conv_pool_saved_bytes(int B, int T, int E);
 HCA_API int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const float* b1, const float* w2,
                              const float* b2, const float* w3, const float* b3, const int64_t* lens,
-                             float* out, uint8_t* idx, int B, int T, int E,
+                             float* out, uint8_t* idx, void* fsaved, size_t fsaved_bytes, int B, int T, int E,
                              void* ws, size_t ws_bytes, void* stream);
-/* gradients of the above given dout [B,T,E]; dx may be null (input does not need grad). */
+/* gradients of the above given dout [B,T,E]; dx may be null (input does not need grad); fsaved may be null. */
 HCA_API int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const float* w2, const float* w3,
                              const float* out, const uint8_t* idx, const float* dout, const int64_t* lens,
+                             const void* fsaved, size_t fsaved_bytes,
                              float* dx, float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3,
                              int B, int T, int E, void* ws, size_t ws_bytes, void* stream);
 

@@ -27,8 +27,9 @@ SIGNATURES = {
     "hca_embedding_fwd": (_i, [_p, _p, _p, _i64, _i, _i64, _p]),
     "hca_embedding_bwd": (_i, [_p, _p, _p, _i64, _i, _i64, _p]),
     "hca_phrase_conv_pool_workspace": (_sz, [_i, _i, _i]),
-    "hca_phrase_conv_pool_fwd": (_i, [_p] * 10 + [_i, _i, _i, _p, _sz, _p]),
-    "hca_phrase_conv_pool_bwd": (_i, [_p] * 15 + [_i, _i, _i, _p, _sz, _p]),
+    "hca_phrase_conv_pool_saved_bytes": (_sz, [_i, _i, _i]),
+    "hca_phrase_conv_pool_fwd": (_i, [_p] * 11 + [_sz] + [_i, _i, _i, _p, _sz, _p]),
+    "hca_phrase_conv_pool_bwd": (_i, [_p] * 9 + [_sz] + [_p] * 7 + [_i, _i, _i, _p, _sz, _p]),
     "hca_lstm_supported": (_i, [_i, _i, _i, _i]),
     "hca_lstm_saved_bytes": (_sz, [_i, _i, _i, _i]),
     "hca_lstm_workspace": (_sz, [_i, _i, _i, _i]),
@@ -55,7 +56,7 @@ SIGNATURES = {
     "hca_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
 }
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 _lib = None
 
 

@@ -327,9 +327,36 @@ extern "C" size_t hca_phrase_conv_pool_workspace(int B, int T, int E) {
          std::max(hca::dense_scratch_bytes(E, 3 * E, (int)R), hca::dense_scratch_bytes((int)R, 3 * E, E));
 }
 
+namespace hca {
+namespace {
+// operand planes kept from forward to backward: Acat [2][R][3E], W1 [2][E][E], W2 [2][E][2E], W3 [2][E][3E]  (bf16)
+struct ConvSaved {
+  __nv_bfloat16* ap = nullptr;
+  __nv_bfloat16* wp[3] = {nullptr, nullptr, nullptr};
+};
+size_t conv_saved_bytes(int B, int T, int E) {
+  const size_t R = (size_t)B * T;
+  size_t n = align_up(2 * R * 3 * E * 2);
+  for (int k = 1; k <= 3; ++k) n += align_up((size_t)2 * E * k * E * 2);
+  return n + 256;
+}
+bool carve_saved(ConvSaved& v, void* buf, size_t bytes, int B, int T, int E) {
+  if (!buf || (reinterpret_cast<uintptr_t>(buf) & 255) || bytes < conv_saved_bytes(B, T, E)) return false;
+  char* p = (char*)buf;
+  const size_t R = (size_t)B * T;
+  v.ap = (__nv_bfloat16*)p; p += align_up(2 * R * 3 * E * 2);
+  for (int k = 1; k <= 3; ++k) { v.wp[k - 1] = (__nv_bfloat16*)p; p += align_up((size_t)2 * E * k * E * 2); }
+  return true;
+}
+}  // namespace
+}  // namespace hca
+
+extern "C" size_t hca_phrase_conv_pool_saved_bytes(int B, int T, int E) { return hca::conv_saved_bytes(B, T, E); }
+
 extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                         const float* w3, const float* b3, const int64_t* lens, float* out, uint8_t* idx,
-                                        int B, int T, int E, void* ws, size_t ws_bytes, void* stream) {
+                                        void* fsaved, size_t fsaved_bytes, int B, int T, int E, void* ws, size_t ws_bytes,
+                                        void* stream) {
   using namespace hca;
   cudaStream_t s = (cudaStream_t)stream;
   HCA_CHECK_ARG(x && w1 && b1 && w2 && b2 && w3 && b3 && out && idx, "phrase_conv_pool_fwd: null pointer");
@@ -345,14 +372,16 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
     // of the Acat planes; bias + tanh fused in the epilogue; near-ties are repaired exactly below
     const int P = 2;
     const int64_t lda = 3 * (int64_t)E, a_stride = (int64_t)R * lda;
-    __nv_bfloat16* ap = c.w.take<__nv_bfloat16>((size_t)P * a_stride);
+    ConvSaved sv;
+    if (fsaved) HCA_CHECK_ARG(carve_saved(sv, fsaved, fsaved_bytes, B, T, E), "phrase_conv_pool_fwd: `fsaved` must be 256-byte aligned and hca_phrase_conv_pool_saved_bytes large");
+    __nv_bfloat16* ap = fsaved ? sv.ap : c.w.take<__nv_bfloat16>((size_t)P * a_stride);
     if (!ap) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for operand planes");
     HCA_LAUNCH_K((im2col3_planes_kernel<2>), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, ap, a_stride, B, T, E / 4);
     HCA_LAUNCHED();
     const float* ws_[3] = {w1, w2, w3};
     for (int k = 1; k <= 3; ++k) {
       const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
-      __nv_bfloat16* wp = c.w.take<__nv_bfloat16>((size_t)P * w_stride);
+      __nv_bfloat16* wp = fsaved ? sv.wp[k - 1] : c.w.take<__nv_bfloat16>((size_t)P * w_stride);
       if (!wp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for weight planes");
       HCA_LAUNCH_K((conv_w_planes_kernel<2>), ew_grid((int64_t)E * E * k), 256, 0, s, ws_[k - 1], wp, w_stride, E, k);
       HCA_LAUNCHED();
@@ -395,9 +424,9 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
 }
 
 extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const float* w2, const float* w3, const float* out,
-                                        const uint8_t* idx, const float* dout, const int64_t* lens, float* dx, float* dw1,
-                                        float* db1, float* dw2, float* db2, float* dw3, float* db3, int B, int T, int E,
-                                        void* ws, size_t ws_bytes, void* stream) {
+                                        const uint8_t* idx, const float* dout, const int64_t* lens, const void* fsaved,
+                                        size_t fsaved_bytes, float* dx, float* dw1, float* db1, float* dw2, float* db2, float* dw3,
+                                        float* db3, int B, int T, int E, void* ws, size_t ws_bytes, void* stream) {
   using namespace hca;
   cudaStream_t s = (cudaStream_t)stream;
   HCA_CHECK_ARG(x && w1 && w2 && w3 && out && idx && dout && dw1 && db1 && dw2 && db2 && dw3 && db3, "phrase_conv_pool_bwd: null pointer");
@@ -408,11 +437,16 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
   if (use_tc() && tc_available() && (E % 8 == 0)) {
     // tensor-core path: every operand is produced once, directly as bf16 hi/lo planes, and the six products read windows of them
     const int64_t ld3 = 3 * (int64_t)E, pstride = (int64_t)R * ld3;
-    __nv_bfloat16* ap = c.w.take<__nv_bfloat16>((size_t)2 * pstride);       // Acat planes
+    // (the planes of Acat and of the weights are the forward's when it left them in `fsaved`: same conversion, same inputs)
+    ConvSaved sv;
+    if (fsaved) HCA_CHECK_ARG(carve_saved(sv, const_cast<void*>(fsaved), fsaved_bytes, B, T, E), "phrase_conv_pool_bwd: bad `fsaved` buffer");
+    __nv_bfloat16* ap = fsaved ? sv.ap : c.w.take<__nv_bfloat16>((size_t)2 * pstride);       // Acat planes
     __nv_bfloat16* dp = c.w.take<__nv_bfloat16>((size_t)2 * pstride);       // dcat planes
-    if (!dp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for operand planes");
-    HCA_LAUNCH_K((im2col3_planes_kernel<2>), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, ap, pstride, B, T, E / 4);
-    HCA_LAUNCHED();
+    if (!dp || !ap) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for operand planes");
+    if (!fsaved) {
+      HCA_LAUNCH_K((im2col3_planes_kernel<2>), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, ap, pstride, B, T, E / 4);
+      HCA_LAUNCHED();
+    }
     float* dbs[3] = {db1, db2, db3};
     for (int k = 0; k < 3; ++k) HCA_TRY(zero_async(dbs[k], (size_t)E * 4, s));
     HCA_LAUNCH_K((pool3_bwd_planes_kernel), dim3((E + 255) / 256, (R + POOL_BWD_ROWS - 1) / POOL_BWD_ROWS), 256, 0, s, out, idx, dout, lens, dp, pstride, db1,
@@ -440,10 +474,12 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
       const float* ws_[3] = {w1, w2, w3};
       for (int k = 3; k >= 1; --k) {
         const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
-        __nv_bfloat16* wp = c.w.take<__nv_bfloat16>((size_t)2 * w_stride);
+        __nv_bfloat16* wp = fsaved ? sv.wp[k - 1] : c.w.take<__nv_bfloat16>((size_t)2 * w_stride);
         if (!wp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for weight planes");
-        HCA_LAUNCH_K((conv_w_planes_kernel<2>), ew_grid((int64_t)E * E * k), 256, 0, s, ws_[k - 1], wp, w_stride, E, k);
-        HCA_LAUNCHED();
+        if (!fsaved) {
+          HCA_LAUNCH_K((conv_w_planes_kernel<2>), ew_grid((int64_t)E * E * k), 256, 0, s, ws_[k - 1], wp, w_stride, E, k);
+          HCA_LAUNCHED();
+        }
         TcOperand A, Bm;
         A.planes = dp + (k - 1) * E; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = E;
         Bm.planes = wp; Bm.ld = ldw; Bm.plane_stride = w_stride; Bm.rows = E; Bm.cols = k * E; Bm.mn_major = true;

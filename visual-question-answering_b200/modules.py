@@ -81,7 +81,7 @@ class PhraseConvPool(nn.Module):
     def forward(self, x_question: Tensor, lens_dev: Optional[Tensor] = None, return_indices: bool = False):
         """x_question [B,T,E] -> [B,T,E].  ``lens_dev`` (optional, int64 on the GPU) zeroes rows t >= len."""
         u, b, t = self.conv_unigram[1], self.conv_bigram[1], self.conv_trigram[1]
-        out, idx = ops.phrase_conv_pool(_f32(x_question), u.weight, u.bias, b.weight, b.bias, t.weight, t.bias, lens_dev)
+        out, idx, _ = ops.phrase_conv_pool(_f32(x_question), u.weight, u.bias, b.weight, b.bias, t.weight, t.bias, lens_dev)
         return (out, idx) if return_indices else out
 
 

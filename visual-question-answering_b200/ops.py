@@ -126,12 +126,18 @@ embedding.register_autograd(_embedding_backward, setup_context=_embedding_setup)
 
 
 # ------------------------------------------------------------------------------------------ phrase conv + pool
+def _pcp_saved_bytes(B: int, T: int, E: int) -> int:
+    al = lambda n: (n + 255) // 256 * 256
+    return al(2 * B * T * 3 * E * 2) + sum(al(2 * E * k * E * 2) for k in (1, 2, 3)) + 256
+
+
 @torch.library.custom_op(f"{NS}::phrase_conv_pool", mutates_args=(), device_types="cuda")
 def phrase_conv_pool(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, w3: Tensor, b3: Tensor,
-                     lens: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
-    """PhraseConvPool forward (reference model.py:313-334) -> (out [B,T,E], idx uint8 [B,T,E]).
+                     lens: Optional[Tensor]) -> Tuple[Tensor, Tensor, Tensor]:
+    """PhraseConvPool forward (reference model.py:313-334) -> (out [B,T,E], idx uint8 [B,T,E], saved).
 
-    ``lens`` (int64, CUDA, optional) additionally zeroes rows t >= len (model.py:287-292)."""
+    ``lens`` (int64, CUDA, optional) additionally zeroes rows t >= len (model.py:287-292).  ``saved`` is an opaque buffer
+    (operand planes of the shifted input and of the weights) that the backward op reuses."""
     _cuda_f32(x, w1, b1, w2, b2, w3, b3)
     x, w1, b1, w2, b2, w3, b3 = map(_c, (x, w1, b1, w2, b2, w3, b3))
     B, T, E = x.shape
@@ -141,21 +147,28 @@ def phrase_conv_pool(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, 
     with torch.cuda.device(x.device):
         nb = L.hca_phrase_conv_pool_workspace(B, T, E)
         ws = _ws(nb, x.device)
+        # the operand planes are produced by the forward anyway: leaving them in a returned buffer instead of the workspace costs
+        # nothing and saves the backward three weight conversions and the im2col pass
+        keep = E % 8 == 0
+        saved = _ws(_pcp_saved_bytes(B, T, E) if keep else 0, x.device)
         _lib.check(L.hca_phrase_conv_pool_fwd(_ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(w3), _ptr(b3),
-                                              _ptr(None if lens is None else _c(lens)), _ptr(out), _ptr(idx), B, T, E,
+                                              _ptr(None if lens is None else _c(lens)), _ptr(out), _ptr(idx),
+                                              _ptr(saved) if keep else None, saved.numel() if keep else 0, B, T, E,
                                               _ptr(ws), ws.numel(), _stream()), "phrase_conv_pool_fwd")
-    return out, idx
+    return out, idx, saved
 
 
 @phrase_conv_pool.register_fake
 def _(x, w1, b1, w2, b2, w3, b3, lens):
-    return torch.empty_like(x), x.new_empty(x.shape, dtype=torch.uint8)
+    B, T, E = x.shape
+    return (torch.empty_like(x), x.new_empty(x.shape, dtype=torch.uint8),
+            x.new_empty(_pcp_saved_bytes(B, T, E) if E % 8 == 0 else 256, dtype=torch.uint8))
 
 
 @torch.library.custom_op(f"{NS}::phrase_conv_pool_bwd", mutates_args=("dw1", "db1", "dw2", "db2", "dw3", "db3"), device_types="cuda")
 def phrase_conv_pool_bwd(x: Tensor, w1: Tensor, w2: Tensor, w3: Tensor, out: Tensor, idx: Tensor, dout: Tensor,
-                         lens: Optional[Tensor], need_dx: bool, dw1: Tensor, db1: Tensor, dw2: Tensor, db2: Tensor, dw3: Tensor,
-                         db3: Tensor) -> Tensor:
+                         lens: Optional[Tensor], saved: Tensor, need_dx: bool, dw1: Tensor, db1: Tensor, dw2: Tensor, db2: Tensor,
+                         dw3: Tensor, db3: Tensor) -> Tensor:
     """Returns dx; the weight / bias gradients are WRITTEN into dw* / db* (contiguous, 16-byte aligned)."""
     _cuda_f32(x, w1, w2, w3, out, dout, dw1, db1, dw2, db2, dw3, db3)
     x, w1, w2, w3, out, idx, dout = map(_c, (x, w1, w2, w3, out, idx, dout))
@@ -165,32 +178,34 @@ def phrase_conv_pool_bwd(x: Tensor, w1: Tensor, w2: Tensor, w3: Tensor, out: Ten
     L = _lib.lib()
     with torch.cuda.device(x.device):
         ws = _ws(L.hca_phrase_conv_pool_workspace(B, T, E), x.device)
+        have = saved.numel() >= L.hca_phrase_conv_pool_saved_bytes(B, T, E)
         _lib.check(L.hca_phrase_conv_pool_bwd(_ptr(x), _ptr(w1), _ptr(w2), _ptr(w3), _ptr(out), _ptr(idx), _ptr(dout),
-                                              _ptr(None if lens is None else _c(lens)), _ptr(dx) if need_dx else None,
+                                              _ptr(None if lens is None else _c(lens)), _ptr(saved) if have else None,
+                                              saved.numel() if have else 0, _ptr(dx) if need_dx else None,
                                               _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _ptr(dw3), _ptr(db3), B, T, E,
                                               _ptr(ws), ws.numel(), _stream()), "phrase_conv_pool_bwd")
     return dx
 
 
 @phrase_conv_pool_bwd.register_fake
-def _(x, w1, w2, w3, out, idx, dout, lens, need_dx, dw1, db1, dw2, db2, dw3, db3):
+def _(x, w1, w2, w3, out, idx, dout, lens, saved, need_dx, dw1, db1, dw2, db2, dw3, db3):
     return torch.empty_like(x) if need_dx else x.new_empty(0)
 
 
 def _pcp_setup(ctx, inputs, output):
     x, w1, b1, w2, b2, w3, b3, lens = inputs
-    out, idx = output
-    ctx.save_for_backward(x, w1, b1, w2, b2, w3, b3, out, idx, lens)
+    out, idx, saved = output
+    ctx.save_for_backward(x, w1, b1, w2, b2, w3, b3, out, idx, lens, saved)
     ctx.set_materialize_grads(False)
 
 
-def _pcp_backward(ctx, dout, _didx):
-    x, w1, b1, w2, b2, w3, b3, out, idx, lens = ctx.saved_tensors
+def _pcp_backward(ctx, dout, _didx, _dsaved):
+    x, w1, b1, w2, b2, w3, b3, out, idx, lens, saved = ctx.saved_tensors
     if dout is None:
         return (None,) * 8
     need_dx = ctx.needs_input_grad[0]
     gs = [_gbuf(t) for t in (w1, b1, w2, b2, w3, b3)]
-    dx = phrase_conv_pool_bwd(x, w1, w2, w3, out, idx, dout, lens, need_dx, *gs)
+    dx = phrase_conv_pool_bwd(x, w1, w2, w3, out, idx, dout, lens, saved, need_dx, *gs)
     return ((dx if need_dx else None), *(_gret(g) for g in gs), None)
 
 
