@@ -562,10 +562,12 @@ struct Saved {
   float* c;                // [B][T][H]
   __nv_bfloat16* hp;       // [2][B][T][H]
   __nv_bfloat16* xp;       // [2][B][T][E]
+  __nv_bfloat16* wip;      // [2][4H][E]: gate-permuted planes of w_ih (the input-gradient product of backward reads them again)
 };
 size_t saved_bytes(int B, int T, int E, int H) {
   const size_t BT = (size_t)B * T;
-  return align_up(BT * 4 * H * 4) + align_up(BT * H * 4) + align_up(2 * BT * H * 2) + align_up(2 * BT * E * 2) + 256;
+  return align_up(BT * 4 * H * 4) + align_up(BT * H * 4) + align_up(2 * BT * H * 2) + align_up(2 * BT * E * 2) +
+         align_up((size_t)2 * 4 * H * E * 2) + 256;
 }
 bool carve_saved(Saved& s, void* buf, size_t bytes, int B, int T, int E, int H) {
   if (bytes < saved_bytes(B, T, E, H) || (reinterpret_cast<uintptr_t>(buf) & 255) != 0) return false;
@@ -574,7 +576,8 @@ bool carve_saved(Saved& s, void* buf, size_t bytes, int B, int T, int E, int H) 
   s.act = (float*)p; p += align_up(BT * 4 * H * 4);
   s.c = (float*)p; p += align_up(BT * H * 4);
   s.hp = (__nv_bfloat16*)p; p += align_up(2 * BT * H * 2);
-  s.xp = (__nv_bfloat16*)p;
+  s.xp = (__nv_bfloat16*)p; p += align_up(2 * BT * E * 2);
+  s.wip = (__nv_bfloat16*)p;
   return true;
 }
 
@@ -710,7 +713,7 @@ extern "C" int hca_lstm_fwd(const float* x, const int64_t* lens, const float* w_
   Workspace w(ws, ws_bytes);
   const int64_t BT = (int64_t)B * T;
   const int H4 = 4 * H;
-  __nv_bfloat16* wip = w.take<__nv_bfloat16>((size_t)2 * H4 * E);
+  __nv_bfloat16* wip = sv.wip;                                   // kept in `saved`: backward's dx product reads them again
   __nv_bfloat16* whp = w.take<__nv_bfloat16>((size_t)2 * H4 * H);
   float* biasp = w.take<float>((size_t)H4);
   int* counters = w.take<int>(counter_count(B, T));
@@ -751,7 +754,7 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
   const int64_t BT = (int64_t)B * T;
   const int H4 = 4 * H;
   __nv_bfloat16* dgp = w.take<__nv_bfloat16>((size_t)2 * BT * H4);
-  __nv_bfloat16* wip = w.take<__nv_bfloat16>((size_t)2 * H4 * E);
+  const __nv_bfloat16* wip = sv.wip;                             // written by the forward call
   __nv_bfloat16* wtp = w.take<__nv_bfloat16>((size_t)2 * H4 * H);
   float* dwi = w.take<float>((size_t)H4 * E);
   float* dwh = w.take<float>((size_t)H4 * H);
@@ -788,8 +791,6 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
   HCA_LAUNCH_K((lstm_unperm_kernel), ew_grid((int64_t)H4), 256, 0, s, dbp, H, 1, db_ih, db_hh);
   HCA_LAUNCHED();
   if (dx) {  // dx = dz W_ih
-    HCA_LAUNCH_K((lstm_split_perm_kernel), ew_grid((int64_t)H4 * E), 256, 0, s, w_ih, H, E, wip, (int64_t)H4 * E);
-    HCA_LAUNCHED();
     TcEpilogue e; e.D = dx; e.ldd = E;
     HCA_TRY(launch_gemm_tc(operand(dgp, H4, BT * H4, (int)BT, H4, false), operand(wip, E, (int64_t)H4 * E, H4, E, true), 2, (int)BT, E, H4,
                            e, 1, s));
