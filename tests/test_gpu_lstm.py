@@ -51,6 +51,23 @@ def test_lstm_matches_oracle(B, T, E, H):
     assert errs["out"] < 1e-4, errs
 
 
+@pytest.mark.parametrize("env", ["HCA_LSTM_STK", "HCA_LSTM_MC"])
+@pytest.mark.parametrize("B,T,E,H", [(160, 26, 512, 512), (37, 9, 64, 128)])
+def test_lstm_backward_variants_match_oracle(env, B, T, E, H):
+    """The opt-in backward variants (M-stacked hi/lo operand tile; cluster multicast of the streamed operand) give the same results."""
+    import os
+    prev = os.environ.get(env)
+    os.environ[env] = "1"
+    try:
+        errs = _run(B, T, E, H, seed=B + T)
+    finally:
+        if prev is None:
+            os.environ.pop(env, None)
+        else:
+            os.environ[env] = prev
+    assert max(errs.values()) < 1e-3, errs
+
+
 def test_lstm_unsorted_lengths_and_len_T():
     errs = _run(37, 11, 64, 128, seed=5, sort=False)
     assert max(errs.values()) < 1e-3, errs

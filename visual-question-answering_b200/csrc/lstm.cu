@@ -43,10 +43,15 @@ constexpr uint32_t L_RING_BYTES = 96 * 1024;
 constexpr int L_THREADS = 64 + 256;               // warp 0 TMA, warp 1 MMA, warps 2..9 cell epilogue (2 groups x 4 TMEM quadrants)
 constexpr int L_MAX_SMEM = 227 * 1024 - 2048;
 
+constexpr int L_CL = 8;                           // cluster size of the multicast variant: 8 CTAs of one row tile share the streamed operand
 constexpr int L_TMAX = 128;                       // longest sequence for which the per-step row trimming is tabulated
 struct LstmMaps {
   CUtensorMap A[3];   // streamed operand planes, 5-D (64 cols, b, k-block, t, plane), boxes (64, box_rows[i], nkb, 1, 1): full, half, quarter tile
   CUtensorMap W;      // resident operand planes, 4-D (cols, rows, plane, 1), box (64, BN, 1, 1)
+  CUtensorMap AS;     // "stacked" view of the streamed operand, dims (64 cols, b, plane, k-block, t), box (64, 64, 2, 1, 1): one k-block
+                      // lands as a 128-row tile whose rows 0..63 are the hi plane and 64..127 the lo plane of the same 64 batch rows
+  CUtensorMap A1[3];  // the streamed operand again with ONE k-block per box (64, box_rows[i], 1, 1, 1): the pieces of a ring slot that the
+                      // CTAs of a cluster load for each other in multicast mode
 };
 
 struct LstmParams {
@@ -99,6 +104,20 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
       "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// multicast variant: the box lands at the same shared-memory offset of every CTA in `mask`, and each of them gets the bytes
+// signalled on ITS barrier at the same offset
+__device__ __forceinline__ void tma_load_5d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(mask)
+      : "memory");
+}
+// MMA completion -> the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t e;
   asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(e));
@@ -142,8 +161,20 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-template <bool BWD>
+// MC = true (launched as clusters of L_CL CTAs = L_CL unit blocks of ONE row tile): the streamed operand of a step is the same for
+// all CTAs of a row tile, so every CTA loads 1 / L_CL of each ring slot and multicasts it to the whole cluster.  A slot is free once
+// ALL CTAs of the cluster have read it (their MMA completions are multicast to everybody's empty barrier, count L_CL); every CTA still
+// arms its own full barrier with the bytes of the whole slot.  Per SM this divides the TMA requests by L_CL and the L2 -> SM traffic of
+// the recurrence by the cluster's deduplication (the per-step stream of the [rows x 4H] gate gradients bounded the backward kernel).
+//
+// STK = true (backward, row tiles of at most 64 rows): the hi and lo planes of the streamed operand are stacked along M -- one 128-row
+// tile per k-block (AS map) -- so ONE MMA of width 2 BN per k-step yields x_hi.[W_hi | W_lo] in lanes 0..63 and x_lo.[W_hi | W_lo] in lanes
+// 64..127, instead of two MMAs.  The backward recurrence issues 4H / 16 k-steps per step of tiny MMAs (N = 32 / 16) and is bound by their
+// issue rate (~47 clock ticks per instruction from the single issuing thread, measured), so halving the instruction count is what counts;
+// the x_lo.W_hi block is handed from the warps of lanes 64..127 to the owners of the rows through shared memory.
+template <bool BWD, bool MC, bool STK = false>
 __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_constant__ LstmMaps maps, const LstmParams p) {
+  static_assert(!STK || (BWD && !MC), "the stacked variant is the backward kernel without multicast");
   pdl_enter();
   constexpr int BN = BWD ? L_UNITS : 4 * L_UNITS;         // accumulator columns: dh of 16 units / 4 gates of 16 units
   constexpr uint32_t W_KB_PLANE = BN * L_BK * 2;          // one plane of one resident k-block
@@ -154,6 +185,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
   __shared__ uint32_t tmem_ptr_smem;
   __shared__ int s_maxlen;
   __shared__ int s_nact[L_TMAX];     // rows of this tile still running at step t (1 + the last row with len > t)
+  __shared__ __align__(16) float s_xch[STK ? 2 * 64 * 8 : 4];   // stacked variant: x_lo.W_hi blocks, [unit half][row][8 units]
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[L_MAX_STAGES + s]); };
@@ -172,7 +204,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
     s_maxlen = 0;
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), MC ? L_CL : 1);
     }
     mbar_init(w_bar, 1);
     mbar_init(tmem_full, 1);
@@ -184,6 +216,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
   if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr_smem), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();      // every CTA's barriers exist before a peer's multicast or commit can reach them
   tc_fence_after();
   // steps this row tile needs: the longest sequence among its rows (rows are independent, so other tiles may run longer)
   if ((int)threadIdx.x < p.rpt) {
@@ -235,10 +268,23 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         if (tl && n < 7) tl[n * 8 + 0] = clock64();
         for (int sl = 0; sl < p.nslots; ++sl) {
           mbar_spin(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), 2u * (uint32_t)p.nkb * plane_bytes);      // (k-blocks beyond K arrive as fill: full box bytes)
+          mbar_expect_tx(full_bar(s), STK ? (uint32_t)p.nkb * 16384u : 2u * (uint32_t)p.nkb * plane_bytes);   // (k-blocks beyond K arrive as fill: full box bytes)
           const uint32_t dst = ring_base + (uint32_t)s * stage_bytes;
-          tma_load_5d(dst, &maps.A[bi], full_bar(s), 0, m0, sl * p.nkb, slot, 0);
-          tma_load_5d(dst + p.lo_off, &maps.A[bi], full_bar(s), 0, m0, sl * p.nkb, slot, 1);
+          if constexpr (STK) {
+            // (the expect_tx above counted 2 nkb plane tiles of the chosen row box; the stacked box is nkb tiles of 128 rows)
+            tma_load_5d(dst, &maps.AS, full_bar(s), 0, m0, 0, sl * p.nkb, slot);
+          } else if constexpr (MC) {
+            // this CTA's share of the slot: pieces (plane, k-block) cr, cr + L_CL, ... -- one box each, multicast to the cluster
+            const int cr = (int)cluster_ctarank();
+            for (int piece = cr; piece < 2 * p.nkb; piece += L_CL) {
+              const int pl = piece / p.nkb, j = piece - pl * p.nkb;
+              tma_load_5d_mc(dst + (uint32_t)pl * p.lo_off + (uint32_t)j * plane_bytes, &maps.A1[bi], full_bar(s), 0, m0, sl * p.nkb + j, slot, pl,
+                             (uint16_t)((1u << L_CL) - 1u));
+            }
+          } else {
+            tma_load_5d(dst, &maps.A[bi], full_bar(s), 0, m0, sl * p.nkb, slot, 0);
+            tma_load_5d(dst + p.lo_off, &maps.A[bi], full_bar(s), 0, m0, sl * p.nkb, slot, 1);
+          }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (tl && n < 7) tl[n * 8 + 1] = clock64();
@@ -266,7 +312,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         const int t_cur = BWD ? steps - 2 - n : n + 1;
         const int nrun = (p.T <= L_TMAX) ? s_nact[t_cur] : p.rpt;
         const int bi = nrun <= p.box_rows[2] ? 2 : (nrun <= p.box_rows[1] ? 1 : 0);
-        const uint32_t tile16 = ((uint32_t)p.box_rows[bi] * L_BK * 2) >> 4;
+        const uint32_t tile16 = STK ? (16384u >> 4) : (((uint32_t)p.box_rows[bi] * L_BK * 2) >> 4);
         for (int sl = 0; sl < p.nslots; ++sl) {
           mbar_spin(full_bar(s), ph);
           tc_fence_after();
@@ -283,11 +329,12 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
                 // The hi and lo planes of the resident slice lie back to back (BN + BN rows), so ONE MMA of width 2 BN gives
                 // x_hi.W_hi (columns 0..BN-1) and x_hi.W_lo (columns BN..2BN-1); a second MMA of width BN adds x_lo.W_hi.
                 umma_bf16_one<desc_hi, idesc2>(d_tmem, au + ks * 2, bu + ks * 2, (kb | ks) != 0 ? 1u : 0u);
-                umma_bf16_one<desc_hi, idesc>(d_tmem, au + a_lo + ks * 2, bu + ks * 2, 1u);
+                if constexpr (!STK) umma_bf16_one<desc_hi, idesc>(d_tmem, au + a_lo + ks * 2, bu + ks * 2, 1u);
               }
             }
           }
-          umma_commit(empty_bar(s));
+          if constexpr (MC) umma_commit_mc(empty_bar(s), (uint16_t)((1u << L_CL) - 1u));   // the slot is free when the whole cluster has read it
+          else umma_commit(empty_bar(s));
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (tl && n < 7) tl[n * 8 + 3] = clock64();
@@ -426,11 +473,34 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
           uint32_t v[8], v2[8];                    // columns 0..15: x.W_hi ; columns 16..31: x.W_lo
           __syncwarp();
           tmem_ld8(lane_addr + (uint32_t)(eg * 8), v);
-          tmem_ld8(lane_addr + (uint32_t)(L_UNITS + eg * 8), v2);
-          tc_fence_before();
           float acc[8];
+          if constexpr (STK) {
+            // lanes 0..63: x_hi.[W_hi | W_lo] of row r ; lanes 64..127: x_lo.[W_hi | W_lo] of row r - 64 (only its W_hi block is used)
+            if (q >= 2) {
+              float4* x4 = reinterpret_cast<float4*>(s_xch + ((eg * 64 + (r - 64)) * 8));
+              x4[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+              x4[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+            } else {
+              tmem_ld8(lane_addr + (uint32_t)(L_UNITS + eg * 8), v2);
+            }
+            tc_fence_before();
+            cell_barrier();
+            if (q < 2) {
+              const float4* x4 = reinterpret_cast<const float4*>(s_xch + ((eg * 64 + r) * 8));
+              const float4 a0 = x4[0], a1 = x4[1];
+              const float lo[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-          for (int u = 0; u < 8; ++u) acc[u] = __uint_as_float(v[u]) + __uint_as_float(v2[u]);
+              for (int u = 0; u < 8; ++u) acc[u] = __uint_as_float(v[u]) + __uint_as_float(v2[u]) + lo[u];
+            } else {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+            }
+          } else {
+            tmem_ld8(lane_addr + (uint32_t)(L_UNITS + eg * 8), v2);
+            tc_fence_before();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] = __uint_as_float(v[u]) + __uint_as_float(v2[u]);
+          }
           if (valid) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) dh[u] += acc[u];
@@ -496,6 +566,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
     tc_fence_before();
   }
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();      // no peer multicasts into, or signals, a CTA that has left
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -602,7 +673,7 @@ int tc_splitk(int M, int N, int K) {
 struct RowTiling {
   int rpt, tiles, per_launch;
 };
-RowTiling row_tiling(int B, int H) {
+RowTiling row_tiling(int B, int H, int max_tiles_per_launch = 1 << 30) {
   int sms = 148;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
@@ -610,7 +681,7 @@ RowTiling row_tiling(int B, int H) {
     sms = 148;
   }
   RowTiling r;
-  r.per_launch = std::max(1, sms / (H / L_UNITS));
+  r.per_launch = std::max(1, std::min(sms / (H / L_UNITS), max_tiles_per_launch));
   const int launches = ((B + L_BM - 1) / L_BM + r.per_launch - 1) / r.per_launch;
   const int slots = launches * r.per_launch;
   r.rpt = std::min(L_BM, (int)(((B + slots - 1) / slots + 7) / 8 * 8));
@@ -628,7 +699,40 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
   p.tiles_n = base.H / L_UNITS;
   p.K = BWD ? 4 * base.H : base.H;
   p.kbn = (p.K + L_BK - 1) / L_BK;
-  const RowTiling rt = row_tiling(base.B, base.H);
+  // Backward, multicast variant (clusters of L_CL unit blocks of one row tile): taken when the unit blocks divide into clusters; the
+  // residency requirement (every CTA of a launch resident at once) then applies to whole clusters, so the row tiling is chosen for the
+  // number of clusters the device can hold (B200: 15 clusters of 8 at this shared-memory size -> 3 row tiles of 56 rows instead of 4
+  // of 40 for H = 512; the MMAs cost the same either way, M is 128 rows per tile).  opt-in: HCA_LSTM_MC=1.
+  bool mc = false;
+  int mc_tiles = 0;
+  if constexpr (BWD) {
+    mc = (p.tiles_n % L_CL) == 0;
+    // (measured at B = 160, H = 512: 287 us against 263 us without -- the stream is not what bounds the kernel, the MMA issue rate is:
+    // the variant stays as an opt-in, HCA_LSTM_MC=1)
+    { const char* ev = getenv("HCA_LSTM_MC"); if (!(ev && atoi(ev) == 1)) mc = false; }
+    if (mc) {
+      static bool mc_attr = false;
+      if (!mc_attr) {
+        HCA_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_MAX_SMEM));
+        mc_attr = true;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(L_CL * 64));
+      cfg.blockDim = dim3(L_THREADS);
+      cfg.dynamicSmemBytes = L_MAX_SMEM;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = L_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int max_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, lstm_rec_kernel<true, true>, &cfg) != cudaSuccess) { cudaGetLastError(); max_clusters = 0; }
+      mc_tiles = max_clusters / (p.tiles_n / L_CL);
+      { const char* ev = getenv("HCA_LSTM_DEBUG"); if (ev && atoi(ev) != 0) fprintf(stderr, "lstm bwd: %d clusters of %d can be resident -> %d row tiles per launch\n", max_clusters, L_CL, mc_tiles); }
+      if (mc_tiles < 1) mc = false;
+    }
+  }
+  const RowTiling rt = mc ? row_tiling(base.B, base.H, mc_tiles) : row_tiling(base.B, base.H);
   HCA_CHECK_ARG(p.tiles_n <= rt.per_launch * p.tiles_n, "lstm: hidden size %d needs more CTAs per row tile than the device has SMs", base.H);
   p.rpt = rt.rpt;
   p.box_rows[0] = rt.rpt;
@@ -641,11 +745,27 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
   // unused accumulator rows, but the last tile's read must stay inside the allocation, hence the tail padding)
   const uint32_t tail_pad = 16u * 1024u - p.plane_bytes;
   p.nkb = std::max(1, std::min(p.kbn, (int)((L_RING_BYTES - tail_pad) / (4 * p.plane_bytes))));
+  { const char* ev = getenv(BWD ? "HCA_LSTM_NKB_BWD" : "HCA_LSTM_NKB_FWD"); if (ev && atoi(ev) >= 1 && atoi(ev) < p.nkb) p.nkb = atoi(ev); }
   p.nslots = (p.kbn + p.nkb - 1) / p.nkb;
   p.lo_off = (uint32_t)p.nkb * p.plane_bytes;
   p.stage_bytes = 2u * p.lo_off;
   p.stages = std::max(2, std::min(L_MAX_STAGES, (int)((L_RING_BYTES - tail_pad) / p.stage_bytes)));
-  const size_t smem = (size_t)p.kbn * 2 * BN * L_BK * 2 + (size_t)p.stages * p.stage_bytes + tail_pad + 1024;
+  // stacked variant (backward, row tiles of <= 64 rows, see the kernel): one 128-row tile (16 KB) per k-block and ring slot
+  bool stk = BWD && !mc && rt.rpt <= 64 &&
+             (size_t)p.kbn * 2 * BN * L_BK * 2 + 2 * 16384u + 1024 <= (size_t)L_MAX_SMEM - 6144;
+  // (measured at B = 160, H = 512: 270 us against 262 us for the two-MMA form, and finer ring slots are slower still (282 / 334 us at 2 / 1
+  // k-blocks per slot): the backward step is a latency chain -- producer waits for the slot, TMA lands, issuer waits, MMAs complete, commit
+  // -- over a ring that the 128 KB resident W_hh slice leaves only 96 KB for, not an issue-rate or bandwidth limit.  Opt-in: HCA_LSTM_STK=1)
+  { const char* ev = getenv("HCA_LSTM_STK"); if (!(ev && atoi(ev) == 1)) stk = false; }
+  if (stk) {
+    p.nkb = 1;
+    p.nslots = p.kbn;
+    p.stage_bytes = 16384u;
+    p.lo_off = 8192u;
+    const size_t room = (size_t)L_MAX_SMEM - 6144 - 1024 - (size_t)p.kbn * 2 * BN * L_BK * 2;
+    p.stages = std::max(2, std::min(std::min(L_MAX_STAGES, 6), (int)(room / p.stage_bytes)));
+  }
+  const size_t smem = (size_t)p.kbn * 2 * BN * L_BK * 2 + (size_t)p.stages * p.stage_bytes + (stk ? 0 : tail_pad) + 1024;
   LstmMaps maps;
   for (int i = 0; i < 3; ++i) {
     // streamed operand [2][B][T][cols] seen as (64 cols of a k-block, b, k-block, t, plane).  Dimension 0 is always a full 64:
@@ -655,6 +775,17 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
     const uint64_t str[4] = {(uint64_t)base.T * stream_cols * 2, (uint64_t)L_BK * 2, (uint64_t)stream_cols * 2, (uint64_t)stream_ps * 2};
     const uint32_t box[5] = {L_BK, (uint32_t)p.box_rows[i], (uint32_t)p.nkb, 1, 1};
     HCA_TRY(tc_make_tmap(&maps.A[i], true, 5, stream_planes, dims, str, box, 3));
+    const uint32_t box1[5] = {L_BK, (uint32_t)p.box_rows[i], 1, 1, 1};
+    HCA_TRY(tc_make_tmap(&maps.A1[i], true, 5, stream_planes, dims, str, box1, 3));
+  }
+  if (stk) {
+    // (64 cols of a k-block, b, plane, k-block, t): the box (64, 64, 2, 1, 1) lands as [plane][row][64] = hi rows 0..63, lo rows 64..127
+    const uint64_t dims[5] = {(uint64_t)L_BK, (uint64_t)base.B, 2, (uint64_t)((stream_cols + L_BK - 1) / L_BK), (uint64_t)base.T};
+    const uint64_t str[4] = {(uint64_t)base.T * stream_cols * 2, (uint64_t)stream_ps * 2, (uint64_t)L_BK * 2, (uint64_t)stream_cols * 2};
+    const uint32_t box[5] = {L_BK, 64, 2, 1, 1};
+    HCA_TRY(tc_make_tmap(&maps.AS, true, 5, stream_planes, dims, str, box, 3));
+  } else {
+    maps.AS = maps.A[0];
   }
   {  // resident operand [2][rows][cols]: dims (cols, rows, 2, 1)
     const uint64_t dims[4] = {(uint64_t)w_cols, (uint64_t)w_rows, 2, 1};
@@ -665,7 +796,7 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
   HCA_CHECK_ARG(smem <= (size_t)L_MAX_SMEM, "lstm: hidden size %d needs %zu bytes of shared memory", base.H, smem);
   static bool attr_set[2] = {false, false};
   if (!attr_set[BWD ? 1 : 0]) {
-    HCA_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_MAX_SMEM));
+    HCA_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<BWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_MAX_SMEM));
     attr_set[BWD ? 1 : 0] = true;
   }
   // every CTA of a launch must be resident at once (the CTAs of a row tile synchronise through global counters); row tiles
@@ -673,7 +804,39 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
   for (int t0 = 0; t0 < rt.tiles; t0 += rt.per_launch) {
     const int nm = std::min(rt.per_launch, rt.tiles - t0);
     p.tile0 = t0;
-    HCA_LAUNCH_K((lstm_rec_kernel<BWD>), nm * p.tiles_n, L_THREADS, smem, s, maps, p);
+    if constexpr (BWD) {
+      if (mc) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(nm * p.tiles_n));
+        cfg.blockDim = dim3(L_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = L_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        HCA_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_kernel<true, true>, maps, p));
+        HCA_LAUNCHED();
+        continue;
+      }
+    }
+    if constexpr (BWD) {
+      if (stk) {
+        static bool stk_attr = false;
+        if (!stk_attr) {
+          // (the exchange buffer adds 4 KB of static shared memory: the dynamic limit shrinks by as much)
+          HCA_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_MAX_SMEM - 6144));
+          stk_attr = true;
+        }
+        HCA_LAUNCH_K((lstm_rec_kernel<true, false, true>), nm * p.tiles_n, L_THREADS, smem, s, maps, p);
+        HCA_LAUNCHED();
+        continue;
+      }
+    }
+    HCA_LAUNCH_K((lstm_rec_kernel<BWD, false>), nm * p.tiles_n, L_THREADS, smem, s, maps, p);
     HCA_LAUNCHED();
   }
   return 0;
