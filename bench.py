@@ -255,7 +255,7 @@ def time_roofline_kernel(pkg, device, steps, pk):
             "peak_source": pk["source"] + " bf16 burst (kernel timed alone)"}
 
 
-def kernel_shares(st, steps=4, top=8):
+def kernel_shares(st, steps=4, top=48):
     """Per-kernel device time of the step under CUPTI activity tracing (torch.profiler): which kernels the step is made of.
     Runs the step EAGERLY with programmatic dependent launch off (HCA_PDL=0): in the timed graph every kernel starts while its
     predecessor drains and waits in griddepcontrol.wait, so its CUPTI duration would include that wait."""

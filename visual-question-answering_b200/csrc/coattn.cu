@@ -519,7 +519,12 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
   HCA_TRY(launch_split_planes_stack3(q0, q1, q2, B, T, d, Qp.p, Qp.ld, Qp.ps, s));
   HCA_TRY(split_to(Wvp, Wv, d, s));
   HCA_TRY(split_to(Wqp, Wq, d, s));
-  HCA_TRY(zero_async(sc, (size_t)3 * B * (N + T) * 4, s));
+  {  // the two accumulated outputs (scores, attended image features) cleared by one launch
+    ZeroBatch zb(s);
+    HCA_TRY(zb.add(sc, (size_t)3 * B * (N + T) * 4));
+    HCA_TRY(zb.add(vhat, (size_t)3 * B * d * 4));
+    HCA_TRY(zb.flush());
+  }
   {  // PV = V Wv^T + bv   (once per step: level independent)
     TcEpilogue e; e.bias = bv; e.P = plv(PVp, 0, BN, 1);
     HCA_TRY(launch_gemm_tc(opv(Vp, 0, (int)BN, BN, 1, false), opv(Wvp, 0, d, d, 1, false), 2, (int)BN, d, d, e, 1, s));
@@ -541,7 +546,6 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
   HCA_TRY(launch_hv_scores(hvp(Cp), hvp(PQp), hvp(PVp), wv, svs, B, N, T, d, s));
   const size_t smem = (size_t)6 * (N + T) * sizeof(float);
   HCA_CHECK_ARG(smem <= 48 * 1024, "coattn_fwd: N + T too large for the softmax kernel");
-  HCA_TRY(zero_async(vhat, (size_t)3 * B * d * 4, s));
   HCA_LAUNCH_K((attn_finish_kernel), dim3(B, ATTN_SPLIT), 256, smem, s, svs, sqs, cv, cq, Vd, q0, q1, q2, sv_.av, sv_.aq, vhat, qhat, B, N, T, d);
   HCA_LAUNCHED();
   return 0;
@@ -577,12 +581,16 @@ extern "C" int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv,
 
   HCA_TRY(split_to(Wqp, Wq, d, s));
   if (dV) HCA_TRY(split_to(Wvp, Wv, d, s));
-  HCA_TRY(zero_async(dcv, 4, s));
-  HCA_TRY(zero_async(dcq, 4, s));
-  HCA_TRY(zero_async(dwv, (size_t)d * 4, s));
-  HCA_TRY(zero_async(dwq, (size_t)d * 4, s));
-  HCA_TRY(zero_async(dbv, (size_t)d * 4, s));
-  HCA_TRY(zero_async(dbq, (size_t)d * 4, s));
+  const int sk_wq = tc_splitk(d, d, (int)BT3), sk_wv = tc_splitk(d, d, (int)BN);
+  {  // every accumulated output of this call (bias / score-vector gradients, split-K weight gradients) cleared by one launch
+    ZeroBatch zb(s);
+    HCA_TRY(zb.add(dcv, 4)); HCA_TRY(zb.add(dcq, 4));
+    HCA_TRY(zb.add(dwv, (size_t)d * 4)); HCA_TRY(zb.add(dwq, (size_t)d * 4));
+    HCA_TRY(zb.add(dbv, (size_t)d * 4)); HCA_TRY(zb.add(dbq, (size_t)d * 4));
+    if (sk_wq > 1) HCA_TRY(zb.add(dWq, (size_t)d * d * 4));
+    if (sk_wv > 1) HCA_TRY(zb.add(dWv, (size_t)d * d * 4));
+    HCA_TRY(zb.flush());
+  }
   {
     const size_t smem = (size_t)6 * d * sizeof(float);
     HCA_CHECK_ARG(smem <= 48 * 1024, "coattn_bwd: d too large for the attention-backward kernel");
@@ -629,14 +637,12 @@ extern "C" int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv,
     }
   }
   {  // dWq = dPQ_all^T Q_all over batch, time and the three levels at once (K = 3*B*T, split-K)
-    const int sk = tc_splitk(d, d, (int)BT3);
-    if (sk > 1) HCA_TRY(zero_async(dWq, (size_t)d * d * 4, s));
+    const int sk = sk_wq;
     TcEpilogue e; e.D = dWq; e.ldd = d;
     HCA_TRY(launch_gemm_tc(opv(dPQ, 0, (int)BT3, BT3, 1, true), opv(Qp, 0, (int)BT3, BT3, 1, true), 2, d, d, (int)BT3, e, sk, s));
   }
   {  // dWv = dPV^T V   (K = B*N, split-K)
-    const int sk = tc_splitk(d, d, (int)BN);
-    if (sk > 1) HCA_TRY(zero_async(dWv, (size_t)d * d * 4, s));
+    const int sk = sk_wv;
     TcEpilogue e; e.D = dWv; e.ldd = d;
     HCA_TRY(launch_gemm_tc(opv(dPV, 0, (int)BN, BN, 1, true), opv(Vp, 0, (int)BN, BN, 1, true), 2, d, d, (int)BN, e, sk, s));
   }

@@ -888,8 +888,12 @@ extern "C" int hca_lstm_fwd(const float* x, const int64_t* lens, const float* w_
   HCA_LAUNCHED();
   HCA_LAUNCH_K((lstm_bias_perm_kernel), (H4 + 255) / 256, 256, 0, s, b_ih, b_hh, H, biasp);
   HCA_LAUNCHED();
-  HCA_TRY(zero_async(sv.hp, (size_t)2 * BT * H * 2, s));      // slot 0 (h_{-1} = 0) and the slots no step reaches
-  HCA_TRY(zero_async(counters, counter_count(B, T) * 4, s));
+  {
+    ZeroBatch zb(s);
+    HCA_TRY(zb.add(sv.hp, (size_t)2 * BT * H * 2));            // slot 0 (h_{-1} = 0) and the slots no step reaches
+    HCA_TRY(zb.add(counters, counter_count(B, T) * 4));
+    HCA_TRY(zb.flush());
+  }
   {  // x-projection of every (b, t), gate columns in [unit][gate] order, biases folded in
     TcEpilogue e;
     e.D = sv.act; e.ldd = H4; e.bias = biasp;
@@ -924,9 +928,16 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
   float* dbp = w.take<float>((size_t)H4);
   int* counters = w.take<int>(counter_count(B, T));
   if (!counters) return set_err(HCA_ERR_WORKSPACE, "lstm_bwd: workspace too small (%zu bytes)", ws_bytes);
-  HCA_TRY(zero_async(dgp, (size_t)2 * BT * H4 * 2, s));       // rows no step writes must read as zero in the GEMMs below
-  HCA_TRY(zero_async(dbp, (size_t)H4 * 4, s));
-  HCA_TRY(zero_async(counters, counter_count(B, T) * 4, s));
+  const int sk_wi = tc_splitk(H4, E, (int)BT), sk_wh = tc_splitk(H4, H, (int)BT);
+  {
+    ZeroBatch zb(s);
+    HCA_TRY(zb.add(dgp, (size_t)2 * BT * H4 * 2));             // rows no step writes must read as zero in the GEMMs below
+    HCA_TRY(zb.add(dbp, (size_t)H4 * 4));
+    HCA_TRY(zb.add(counters, counter_count(B, T) * 4));
+    if (sk_wi > 1) HCA_TRY(zb.add(dwi, (size_t)H4 * E * 4));
+    if (sk_wh > 1) HCA_TRY(zb.add(dwh, (size_t)H4 * H * 4));
+    HCA_TRY(zb.flush());
+  }
   HCA_LAUNCH_K((lstm_split_perm_t_kernel), ew_grid((int64_t)H4 * H), 256, 0, s, w_hh, H, wtp, (int64_t)H4 * H);
   HCA_LAUNCHED();
   LstmParams p;
@@ -936,16 +947,14 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
   HCA_TRY(launch_rec<true>(p, dgp, BT * H4, H4, wtp, (int64_t)H4 * H, H, H4, s));
   const TcOperand dg_mn = operand(dgp, H4, BT * H4, (int)BT, H4, true);
   {  // dW_ih' = dz^T x   (K = B*T, split-K)
-    const int sk = tc_splitk(H4, E, (int)BT);
-    if (sk > 1) HCA_TRY(zero_async(dwi, (size_t)H4 * E * 4, s));
+    const int sk = sk_wi;
     TcEpilogue e; e.D = dwi; e.ldd = E;
     HCA_TRY(launch_gemm_tc(dg_mn, operand(sv.xp, E, BT * E, (int)BT, E, true), 2, H4, E, (int)BT, e, sk, s));
     HCA_LAUNCH_K((lstm_unperm_kernel), ew_grid((int64_t)H4 * E), 256, 0, s, dwi, H, E, dw_ih, nullptr);
     HCA_LAUNCHED();
   }
   {  // dW_hh' = dz^T h_prev
-    const int sk = tc_splitk(H4, H, (int)BT);
-    if (sk > 1) HCA_TRY(zero_async(dwh, (size_t)H4 * H * 4, s));
+    const int sk = sk_wh;
     TcEpilogue e; e.D = dwh; e.ldd = H;
     HCA_TRY(launch_gemm_tc(dg_mn, operand(sv.hp, H, BT * H, (int)BT, H, true), 2, H4, H, (int)BT, e, sk, s));
     HCA_LAUNCH_K((lstm_unperm_kernel), ew_grid((int64_t)H4 * H), 256, 0, s, dwh, H, H, dw_hh, nullptr);

@@ -228,9 +228,11 @@ extern "C" int hca_mlp_bwd(const float* dlogits, const void* saved, size_t saved
   // W_h: planes of dlogits + db_h in one pass; dW_h; dz_s = (dlogits W_h) * (1 - h_s^2) with db_s
   HCA_LAUNCH_K((split_colsum_kernel), (K + 31) / 32, 256, 0, s, dlogits, K, B, K, dl.p, dl.ld, dl.ps, dbh);
   HCA_LAUNCHED();
-  HCA_TRY(zero_async(dbs, (size_t)mlp * 4, s));
-  HCA_TRY(zero_async(dbp, (size_t)d * 4, s));
-  HCA_TRY(zero_async(dbw, (size_t)d * 4, s));
+  {
+    ZeroBatch zb(s);
+    HCA_TRY(zb.add(dbs, (size_t)mlp * 4)); HCA_TRY(zb.add(dbp, (size_t)d * 4)); HCA_TRY(zb.add(dbw, (size_t)d * 4));
+    HCA_TRY(zb.flush());
+  }
   HCA_TRY(side.fork());
   HCA_TRY(bwd_weight(dl, K, sv.hs, mlp, B, dWh, sw));
   HCA_TRY(bwd_data(sv.Wh, K, 0, mlp, dl, B, &sv.hs, 0, &dzs, nullptr, dbs, s));

@@ -448,19 +448,27 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
       HCA_LAUNCHED();
     }
     float* dbs[3] = {db1, db2, db3};
-    for (int k = 0; k < 3; ++k) HCA_TRY(zero_async(dbs[k], (size_t)E * 4, s));
+    float* dwr[3] = {dw1, c.dwr2, c.dwr3};
+    int sks[3];
+    {  // bias gradients and the split-K weight-gradient accumulators cleared by one launch
+      ZeroBatch zb(s);
+      for (int k = 1; k <= 3; ++k) {
+        HCA_TRY(zb.add(dbs[k - 1], (size_t)E * 4));
+        const int tiles = ((E + 127) / 128) * ((k * E + 127) / 128);
+        sks[k - 1] = tiles >= 96 ? 1 : std::max(1, std::min((148 + tiles - 1) / tiles, (R + 255) / 256));
+        if (sks[k - 1] > 1) HCA_TRY(zb.add(dwr[k - 1], (size_t)E * k * E * 4));
+      }
+      HCA_TRY(zb.flush());
+    }
     HCA_LAUNCH_K((pool3_bwd_planes_kernel), dim3((E + 255) / 256, (R + POOL_BWD_ROWS - 1) / POOL_BWD_ROWS), 256, 0, s, out, idx, dout, lens, dp, pstride, db1,
                                                                                                        db2, db3, B, T, E);
     HCA_LAUNCHED();
     // weight gradients, tap-major: dWr_k[o][kk] = sum_r dcat[r][(k-1)E + o] * Acat[r][a_off + kk]   (K = R, split-K)
-    float* dwr[3] = {dw1, c.dwr2, c.dwr3};
     for (int k = 1; k <= 3; ++k) {
       TcOperand A, Bm;
       A.planes = dp + (k - 1) * E; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = E; A.mn_major = true;
       Bm.planes = ap + (k == 1 ? E : 0); Bm.ld = ld3; Bm.plane_stride = pstride; Bm.rows = R; Bm.cols = k * E; Bm.mn_major = true;
-      const int tiles = ((E + 127) / 128) * ((k * E + 127) / 128);
-      int sk = tiles >= 96 ? 1 : std::max(1, std::min((148 + tiles - 1) / tiles, (R + 255) / 256));
-      if (sk > 1) HCA_TRY(zero_async(dwr[k - 1], (size_t)E * k * E * 4, s));
+      const int sk = sks[k - 1];
       TcEpilogue ep;
       ep.D = dwr[k - 1]; ep.ldd = (int64_t)k * E;
       HCA_TRY(launch_gemm_tc(A, Bm, 2, E, k * E, R, ep, sk, s));
