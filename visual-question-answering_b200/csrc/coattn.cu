@@ -517,8 +517,12 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
   const Pl &Vp = sv_.V, &Qp = sv_.Q, &PVp = sv_.PV, &PQp = sv_.PQ, &Cp = sv_.C;
   HCA_TRY(split_to(Vp, Vd, d, s));
   HCA_TRY(launch_split_planes_stack3(q0, q1, q2, B, T, d, Qp.p, Qp.ld, Qp.ps, s));
-  HCA_TRY(split_to(Wvp, Wv, d, s));
-  HCA_TRY(split_to(Wqp, Wq, d, s));
+  {  // both projection weights -> operand planes, one launch
+    SplitBatch sb(s);
+    HCA_TRY(sb.add(Wv, d, d, d, Wvp.p, Wvp.ld, Wvp.ps));
+    HCA_TRY(sb.add(Wq, d, d, d, Wqp.p, Wqp.ld, Wqp.ps));
+    HCA_TRY(sb.flush());
+  }
   {  // the two accumulated outputs (scores, attended image features) cleared by one launch
     ZeroBatch zb(s);
     HCA_TRY(zb.add(sc, (size_t)3 * B * (N + T) * 4));

@@ -801,6 +801,37 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
   }
 }
 
+struct SplitJobs {
+  SplitBatch::Job job[SplitBatch::MAX];
+  long long start[SplitBatch::MAX + 1];      // prefix sums of the jobs' float4 counts
+  int count;
+};
+__global__ void __launch_bounds__(256) split_planes_multi_kernel(const SplitJobs jobs) {
+  pdl_enter();
+  const long long total = jobs.start[jobs.count];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int j = 0;
+    while (j + 1 < jobs.count && i >= jobs.start[j + 1]) ++j;
+    const SplitBatch::Job& b = jobs.job[j];
+    const long long k = i - jobs.start[j];
+    const int c4n = b.cols >> 2;
+    const long long r = k / c4n;
+    const int c = (int)(k - r * c4n) * 4;
+    const float4 t = __ldg(reinterpret_cast<const float4*>(b.src + r * b.ld + c));
+    float x[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+      __nv_bfloat16 h[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        h[q] = __float2bfloat16_rn(x[q]);
+        x[q] -= __bfloat162float(h[q]);
+      }
+      *reinterpret_cast<uint2*>(b.dst + pl * b.ps + r * b.ldp + c) = *reinterpret_cast<const uint2*>(h);
+    }
+  }
+}
+
 // three [B][T][cols] sources -> stacked planes [2][B][3T][ldp]   (cols % 4 == 0, sources 16-byte aligned)
 __global__ void __launch_bounds__(256) split_planes_stack3_kernel(const float4* __restrict__ s0, const float4* __restrict__ s1,
                                                                   const float4* __restrict__ s2, int B, int T, int c4n,
@@ -965,6 +996,34 @@ int launch_split_planes(const float* src, int64_t ld, int64_t rows, int cols, __
                 "split_planes: bad arguments");
   const int64_t total = rows * ((cols + 3) / 4);
   HCA_LAUNCH_K((split_planes_kernel), ew_grid(total), 256, 0, s, src, ld, rows, cols, planes, ldp, plane_stride, P);
+  HCA_LAUNCHED();
+  return 0;
+}
+
+int SplitBatch::add(const float* src, int64_t ld, int64_t rows, int cols, __nv_bfloat16* planes, int64_t ldp, int64_t plane_stride) {
+  HCA_CHECK_ARG(src && planes && rows > 0 && cols > 0, "SplitBatch: bad arguments");
+  const bool vec = (cols % 4) == 0 && (ld % 4) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (ldp % 4) == 0 && (plane_stride % 4) == 0 &&
+                   (reinterpret_cast<uintptr_t>(planes) & 7) == 0;
+  if (!vec) return launch_split_planes(src, ld, rows, cols, planes, ldp, plane_stride, 2, stream);      // odd shapes: the general kernel
+  if (count == MAX) HCA_TRY(flush());
+  job[count++] = Job{src, planes, (long long)ld, (long long)rows, (long long)ldp, (long long)plane_stride, cols};
+  return 0;
+}
+
+int SplitBatch::flush() {
+  if (count == 0) return 0;
+  SplitJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  long long total = 0;
+  for (int i = 0; i < count; ++i) {
+    jobs.job[i] = job[i];
+    jobs.start[i] = total;
+    total += job[i].rows * (job[i].cols / 4);
+  }
+  jobs.start[count] = total;
+  jobs.count = count;
+  count = 0;
+  HCA_LAUNCH_K((split_planes_multi_kernel), ew_grid(total), 256, 0, stream, jobs);
   HCA_LAUNCHED();
   return 0;
 }

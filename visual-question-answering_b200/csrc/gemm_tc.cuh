@@ -90,6 +90,18 @@ int launch_split_planes(const float* src, int64_t ld, int64_t rows, int cols, __
 int launch_split_planes_stack3(const float* s0, const float* s1, const float* s2, int B, int T, int cols, __nv_bfloat16* planes,
                                int64_t ldp, int64_t plane_stride, cudaStream_t s);
 
+// Several fp32 matrices -> bf16 hi/lo planes in ONE launch (the weight matrices of an entry point: each conversion alone is a
+// ~3 us launch for ~1 us of work).  Sources 16-byte aligned with ld % 4 == 0 and cols % 4 == 0; always 2 planes.
+struct SplitBatch {
+  static constexpr int MAX = 6;
+  struct Job { const float* src; __nv_bfloat16* dst; long long ld, rows, ldp, ps; int cols; } job[MAX];
+  int count = 0;
+  cudaStream_t stream;
+  explicit SplitBatch(cudaStream_t s) : stream(s) {}
+  int add(const float* src, int64_t ld, int64_t rows, int cols, __nv_bfloat16* planes, int64_t ldp, int64_t plane_stride);
+  int flush();
+};
+
 bool tc_available();   // TMA descriptor encoder resolved from the driver
 // generic tiled TMA descriptor (rank 2..5) for the other hand-written kernels: `tm` points at a CUtensorMap; dims / box in
 // elements (dim 0 innermost and contiguous), strides in BYTES for dims 1..rank-1; swizzle 0 none, 1 = 32 B, 2 = 64 B, 3 = 128 B

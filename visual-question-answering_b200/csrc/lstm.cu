@@ -605,6 +605,33 @@ __global__ void __launch_bounds__(256) lstm_split_perm_t_kernel(const float* __r
     planes[ps + i] = __float2bfloat16_rn(x - __bfloat162float(h));
   }
 }
+// forward prologue in one launch: planes of W_ih and W_hh (gate rows permuted) and the permuted bias sum
+__global__ void __launch_bounds__(256) lstm_prep_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                                        const float* __restrict__ b_ih, const float* __restrict__ b_hh, int H, int E,
+                                                        __nv_bfloat16* __restrict__ wip, __nv_bfloat16* __restrict__ whp,
+                                                        float* __restrict__ biasp) {
+  pdl_enter();
+  const int64_t n1 = (int64_t)4 * H * E, n2 = (int64_t)4 * H * H, total = n1 + n2 + 4 * H;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    if (g < n1 + n2) {
+      const bool first = g < n1;
+      const int64_t i = first ? g : g - n1;
+      const int cols = first ? E : H;
+      const float* W = first ? w_ih : w_hh;
+      __nv_bfloat16* planes = first ? wip : whp;
+      const int64_t ps = first ? n1 : n2;
+      const int jp = (int)(i / cols), c = (int)(i - (int64_t)jp * cols);
+      const float x = W[(int64_t)perm_row(jp, H) * cols + c];
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      planes[i] = h;
+      planes[ps + i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    } else {
+      const int jp = (int)(g - n1 - n2);
+      const int j = perm_row(jp, H);
+      biasp[jp] = b_ih[j] + b_hh[j];
+    }
+  }
+}
 __global__ void __launch_bounds__(256) lstm_bias_perm_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, int H,
                                                              float* __restrict__ out) {
   pdl_enter();
@@ -625,6 +652,30 @@ __global__ void __launch_bounds__(256) lstm_unperm_kernel(const float* __restric
     const int64_t o = (int64_t)perm_row(jp, H) * cols + c;
     dst[o] = v;
     if (dst2) dst2[o] = v;
+  }
+}
+
+// dW_ih, dW_hh and the bias gradient (both b_ih and b_hh receive it) in one launch
+__global__ void __launch_bounds__(256) lstm_unperm3_kernel(const float* __restrict__ dwi, const float* __restrict__ dwh,
+                                                           const float* __restrict__ dbp, int H, int E, float* __restrict__ dw_ih,
+                                                           float* __restrict__ dw_hh, float* __restrict__ db_ih, float* __restrict__ db_hh) {
+  pdl_enter();
+  const int64_t n1 = (int64_t)4 * H * E, n2 = (int64_t)4 * H * H, total = n1 + n2 + 4 * H;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    if (g < n1) {
+      const int jp = (int)(g / E), c = (int)(g - (int64_t)jp * E);
+      dw_ih[(int64_t)perm_row(jp, H) * E + c] = dwi[g];
+    } else if (g < n1 + n2) {
+      const int64_t i = g - n1;
+      const int jp = (int)(i / H), c = (int)(i - (int64_t)jp * H);
+      dw_hh[(int64_t)perm_row(jp, H) * H + c] = dwh[i];
+    } else {
+      const int jp = (int)(g - n1 - n2);
+      const float v = dbp[jp];
+      const int o = perm_row(jp, H);
+      db_ih[o] = v;
+      db_hh[o] = v;
+    }
   }
 }
 
@@ -882,11 +933,7 @@ extern "C" int hca_lstm_fwd(const float* x, const int64_t* lens, const float* w_
   int* counters = w.take<int>(counter_count(B, T));
   if (!counters) return set_err(HCA_ERR_WORKSPACE, "lstm_fwd: workspace too small (%zu bytes)", ws_bytes);
   HCA_TRY(launch_split_planes(x, E, BT, E, sv.xp, E, BT * E, 2, s));
-  HCA_LAUNCH_K((lstm_split_perm_kernel), ew_grid((int64_t)H4 * E), 256, 0, s, w_ih, H, E, wip, (int64_t)H4 * E);
-  HCA_LAUNCHED();
-  HCA_LAUNCH_K((lstm_split_perm_kernel), ew_grid((int64_t)H4 * H), 256, 0, s, w_hh, H, H, whp, (int64_t)H4 * H);
-  HCA_LAUNCHED();
-  HCA_LAUNCH_K((lstm_bias_perm_kernel), (H4 + 255) / 256, 256, 0, s, b_ih, b_hh, H, biasp);
+  HCA_LAUNCH_K((lstm_prep_kernel), ew_grid((int64_t)H4 * (E + H + 1)), 256, 0, s, w_ih, w_hh, b_ih, b_hh, H, E, wip, whp, biasp);
   HCA_LAUNCHED();
   {
     ZeroBatch zb(s);
@@ -950,17 +997,14 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
     const int sk = sk_wi;
     TcEpilogue e; e.D = dwi; e.ldd = E;
     HCA_TRY(launch_gemm_tc(dg_mn, operand(sv.xp, E, BT * E, (int)BT, E, true), 2, H4, E, (int)BT, e, sk, s));
-    HCA_LAUNCH_K((lstm_unperm_kernel), ew_grid((int64_t)H4 * E), 256, 0, s, dwi, H, E, dw_ih, nullptr);
-    HCA_LAUNCHED();
   }
   {  // dW_hh' = dz^T h_prev
     const int sk = sk_wh;
     TcEpilogue e; e.D = dwh; e.ldd = H;
     HCA_TRY(launch_gemm_tc(dg_mn, operand(sv.hp, H, BT * H, (int)BT, H, true), 2, H4, H, (int)BT, e, sk, s));
-    HCA_LAUNCH_K((lstm_unperm_kernel), ew_grid((int64_t)H4 * H), 256, 0, s, dwh, H, H, dw_hh, nullptr);
-    HCA_LAUNCHED();
   }
-  HCA_LAUNCH_K((lstm_unperm_kernel), ew_grid((int64_t)H4), 256, 0, s, dbp, H, 1, db_ih, db_hh);
+  // the three gradients back to PyTorch's gate order, one launch
+  HCA_LAUNCH_K((lstm_unperm3_kernel), ew_grid((int64_t)H4 * (E + H + 1)), 256, 0, s, dwi, dwh, dbp, H, E, dw_ih, dw_hh, db_ih, db_hh);
   HCA_LAUNCHED();
   if (dx) {  // dx = dz W_ih
     TcEpilogue e; e.D = dx; e.ldd = E;

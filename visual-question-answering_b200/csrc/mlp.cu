@@ -124,9 +124,6 @@ __global__ void __launch_bounds__(256) split_colsum_kernel(const float* __restri
   }
 }
 
-int split_w(const float* W, int rows, int cols, const Pl& dst, cudaStream_t s) {
-  return launch_split_planes(W, cols, rows, cols, dst.p, dst.ld, dst.ps, 2, s);
-}
 
 // out[b][j] (planes at `dst` and / or fp32 `D`) = act( sum_k X[b][k] W[j][k] + bias[j] )       W K-major [out, in]
 int fwd_layer(const Pl& W, int out, int in, const Pl& X, int B, const float* bias, int act_tanh, const Pl* dst, int64_t dst_col0,
@@ -187,10 +184,14 @@ extern "C" int hca_mlp_fwd(const float* vhat, const float* qhat, const float* Ww
   HCA_LAUNCH_K((mlp_inputs_planes_kernel), ew_grid(3LL * B * d / 4), 256, 0, s, (const float4*)vhat, (const float4*)qhat, sv.xw.p, sv.xw.ld, sv.xw.ps,
                                                                   sv.xp.p, sv.xp.ld, sv.xp.ps, sv.xs.p, sv.xs.ld, sv.xs.ps, B, d / 4);
   HCA_LAUNCHED();
-  HCA_TRY(split_w(Ww, d, d, sv.Ww, s));
-  HCA_TRY(split_w(Wp, d, 2 * d, sv.Wp, s));
-  HCA_TRY(split_w(Ws, mlp, 2 * d, sv.Ws, s));
-  HCA_TRY(split_w(Wh, K, mlp, sv.Wh, s));
+  {  // the four weight matrices -> operand planes, one launch
+    SplitBatch sb(s);
+    HCA_TRY(sb.add(Ww, d, d, d, sv.Ww.p, sv.Ww.ld, sv.Ww.ps));
+    HCA_TRY(sb.add(Wp, 2 * d, d, 2 * d, sv.Wp.p, sv.Wp.ld, sv.Wp.ps));
+    HCA_TRY(sb.add(Ws, 2 * d, mlp, 2 * d, sv.Ws.p, sv.Ws.ld, sv.Ws.ps));
+    HCA_TRY(sb.add(Wh, mlp, K, mlp, sv.Wh.p, sv.Wh.ld, sv.Wh.ps));
+    HCA_TRY(sb.flush());
+  }
   HCA_TRY(fwd_layer(sv.Ww, d, d, sv.xw, B, bw, 1, &sv.xp, d, nullptr, 0, s));            // h_w -> xp[:, d:]
   HCA_TRY(fwd_layer(sv.Wp, d, 2 * d, sv.xp, B, bp, 1, &sv.xs, d, nullptr, 0, s));        // h_p -> xs[:, d:]
   HCA_TRY(fwd_layer(sv.Ws, mlp, 2 * d, sv.xs, B, bs, 1, &sv.hs, 0, nullptr, 0, s));      // h_s

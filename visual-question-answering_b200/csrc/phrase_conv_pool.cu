@@ -236,6 +236,29 @@ __global__ void __launch_bounds__(256) conv_w_planes_kernel(const float* __restr
     }
   }
 }
+// The three weights in one launch (hi/lo planes), which also clears the near-tie counter of the pool kernel.
+__global__ void __launch_bounds__(256) conv_w_planes3_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
+                                                             const float* __restrict__ w3, __nv_bfloat16* __restrict__ p1,
+                                                             __nv_bfloat16* __restrict__ p2, __nv_bfloat16* __restrict__ p3, int E,
+                                                             int* __restrict__ tie_count) {
+  pdl_enter();
+  if (tie_count && blockIdx.x == 0 && threadIdx.x == 0) *tie_count = 0;
+  const int64_t EE = (int64_t)E * E, total = 6 * EE;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    const int k = g < EE ? 1 : (g < 3 * EE ? 2 : 3);
+    const int64_t i = g - (k == 1 ? 0 : (k == 2 ? EE : 3 * EE));
+    const float* w = k == 1 ? w1 : (k == 2 ? w2 : w3);
+    __nv_bfloat16* planes = k == 1 ? p1 : (k == 2 ? p2 : p3);
+    const int64_t ps = EE * k;
+    const int c = (int)(i % E);
+    const int j = (int)((i / E) % k);
+    const int64_t o = i / ((int64_t)E * k);
+    const float x = w[(o * E + c) * k + j];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    planes[i] = h;
+    planes[ps + i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
 // Pool backward straight into operand planes: dcat[r][3e+j] = (j == idx) ? dout * (1 - out^2) : 0 as bf16 hi/lo planes
 // [2][R][3E], plus the three bias gradients (column sums of dcat over r).  Thread <-> one channel triple e, block <-> a slab
 // of rows, so the column sums stay in registers until one atomic per column and block.
@@ -286,7 +309,20 @@ __global__ void __launch_bounds__(256) unpack_conv_w_kernel(const float* __restr
     w[i] = wr[(o * k + j) * E + c];
   }
 }
-
+// both in one launch (bigram and trigram weight gradients)
+__global__ void __launch_bounds__(256) unpack_conv_w23_kernel(const float* __restrict__ wr2, float* __restrict__ w2,
+                                                              const float* __restrict__ wr3, float* __restrict__ w3, int E) {
+  pdl_enter();
+  const int64_t n2 = (int64_t)E * E * 2, total = n2 + (int64_t)E * E * 3;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    const int k = g < n2 ? 2 : 3;
+    const int64_t i = g < n2 ? g : g - n2;
+    const int j = (int)(i % k);
+    const int c = (int)((i / k) % E);
+    const int64_t o = i / ((int64_t)E * k);
+    (k == 2 ? w2 : w3)[i] = (k == 2 ? wr2 : wr3)[(o * k + j) * E + c];
+  }
+}
 
 struct ConvWs {
   Workspace w;
@@ -378,13 +414,16 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
     if (!ap) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for operand planes");
     HCA_LAUNCH_K((im2col3_planes_kernel<2>), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, ap, a_stride, B, T, E / 4);
     HCA_LAUNCHED();
-    const float* ws_[3] = {w1, w2, w3};
+    __nv_bfloat16* wps[3];
+    for (int k = 1; k <= 3; ++k) {
+      wps[k - 1] = fsaved ? sv.wp[k - 1] : c.w.take<__nv_bfloat16>((size_t)P * E * k * E);
+      if (!wps[k - 1]) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for weight planes");
+    }
+    HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid((int64_t)6 * E * E), 256, 0, s, w1, w2, w3, wps[0], wps[1], wps[2], E, c.tie_count);
+    HCA_LAUNCHED();
     for (int k = 1; k <= 3; ++k) {
       const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
-      __nv_bfloat16* wp = fsaved ? sv.wp[k - 1] : c.w.take<__nv_bfloat16>((size_t)P * w_stride);
-      if (!wp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for weight planes");
-      HCA_LAUNCH_K((conv_w_planes_kernel<2>), ew_grid((int64_t)E * E * k), 256, 0, s, ws_[k - 1], wp, w_stride, E, k);
-      HCA_LAUNCHED();
+      __nv_bfloat16* wp = wps[k - 1];
       TcOperand A, Bw;
       A.planes = ap + (k == 1 ? E : 0); A.ld = lda; A.plane_stride = a_stride; A.rows = R; A.cols = k * E;
       Bw.planes = wp; Bw.ld = ldw; Bw.plane_stride = w_stride; Bw.rows = E; Bw.cols = k * E;
@@ -392,7 +431,6 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
       ep.D = c.cat + (k - 1) * E; ep.ldd = lda; ep.bias = bs[k - 1]; ep.act_tanh = 1;
       HCA_TRY(launch_gemm_tc(A, Bw, P, R, E, k * E, ep, 1, s));
     }
-    HCA_TRY(zero_async(c.tie_count, sizeof(int), s));
     HCA_LAUNCH_K((pool3_fwd_kernel), ew_grid((int64_t)R * E), 256, 0, s, c.cat, lens, out, idx, B, T, E, c.tie_list, c.tie_count, c.tie_cap);
     HCA_LAUNCHED();
     HCA_LAUNCH_K((fixup_ties_kernel), 148 * 2, 256, 0, s, c.tie_list, c.tie_count, c.tie_cap, x, T, w1, w2, w3, b1, b2, b3, out, idx, E);
@@ -473,9 +511,7 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
       ep.D = dwr[k - 1]; ep.ldd = (int64_t)k * E;
       HCA_TRY(launch_gemm_tc(A, Bm, 2, E, k * E, R, ep, sk, s));
     }
-    HCA_LAUNCH_K((unpack_conv_w_kernel), ew_grid((int64_t)E * E * 2), 256, 0, s, c.dwr2, dw2, E, 2);
-    HCA_LAUNCHED();
-    HCA_LAUNCH_K((unpack_conv_w_kernel), ew_grid((int64_t)E * E * 3), 256, 0, s, c.dwr3, dw3, E, 3);
+    HCA_LAUNCH_K((unpack_conv_w23_kernel), ew_grid((int64_t)E * E * 5), 256, 0, s, c.dwr2, dw2, c.dwr3, dw3, E);
     HCA_LAUNCHED();
     if (dx) {
       // dA[r][a_off + kk] (+)= sum_o dcat[r][(k-1)E + o] * Wr_k[o][kk]: tri first (covers all 3E columns), bi and uni accumulate
