@@ -218,8 +218,8 @@ class Stepper:
 
 
 # ncu --set full capture of this kernel (profiles/): DRAM bytes per launch, read + write.  None until a capture is committed.
-ROOFLINE_TRAFFIC_BYTES = 81.6e6
-ROOFLINE_TRAFFIC_SOURCE = "profiles/r1d_pv_gemm_ncu_full.md: dram__bytes_read.sum 65.4 MB + dram__bytes_write.sum 16.2 MB, one launch"
+ROOFLINE_TRAFFIC_BYTES = 81.0e6
+ROOFLINE_TRAFFIC_SOURCE = "profiles/r1e_pv_gemm_ncu_full.md: dram__bytes_read.sum 65.4 MB + dram__bytes_write.sum 15.6 MB, one launch"
 
 
 def time_roofline_kernel(pkg, device, steps, pk):

@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU visit r1d: parity tests, bench line (with CPU baseline), reference arm, ncu launch list of one step, ncu --set full of the PV GEMM.
+# GPU visit r1e: parity tests, bench line (with CPU baseline), reference arm, ncu launch list of one step, ncu --set full of the PV GEMM.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
