@@ -116,12 +116,13 @@ __global__ void __launch_bounds__(256) attn_finish_kernel(const float* __restric
   for (int c = threadIdx.x; c < d2; c += blockDim.x) {
     float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
     int n = sp;
-    for (; n + 3 * ATTN_SPLIT < N; n += 4 * ATTN_SPLIT) {
-      float2 v[4];
+    constexpr int UNR = 8;                       // rows in flight per thread (8-byte loads: the loop is latency-bound with fewer)
+    for (; n + (UNR - 1) * ATTN_SPLIT < N; n += UNR * ATTN_SPLIT) {
+      float2 v[UNR];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(V2 + (int64_t)(n + u * ATTN_SPLIT) * d2 + c);
+      for (int u = 0; u < UNR; ++u) v[u] = __ldg(V2 + (int64_t)(n + u * ATTN_SPLIT) * d2 + c);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UNR; ++u) {
         const int nn = n + u * ATTN_SPLIT;
         const float w0 = a_sm[nn], w1 = a_sm[N + nn], w2 = a_sm[2 * N + nn];
         a0.x = fmaf(w0, v[u].x, a0.x); a0.y = fmaf(w0, v[u].y, a0.y);
