@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(256) pool3_bwd_planes_kernel(const float* __re
   const int64_t R = (int64_t)B * T;
   const int64_t r0 = (int64_t)blockIdx.y * POOL_BWD_ROWS, r1 = min(R, r0 + POOL_BWD_ROWS);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 4                      // four rows' loads in flight per thread (the rows are independent; one at a time is latency-bound)
   for (int64_t r = r0; r < r1; ++r) {
     const int b = (int)(r / T), t = (int)(r - (int64_t)b * T);
     float g = 0.f;
