@@ -88,3 +88,40 @@ def test_shard_batch_keeps_sorted_order():
         assert (sh[:-1] >= sh[1:]).all() and len(sh) == 4
     with pytest.raises(ValueError):
         dp.shard_batch(10, 0, 4)
+
+
+def test_gradient_sink_bookkeeping_on_cpu():
+    """The sink protocol of FlatGradAllReduce (ops._gbuf / ops._gret call take() / delivered()) exercised by hand on CPU tensors:
+    a slot is handed out once per step, a direct write is never followed by a clearing pass, a slot that was neither written nor
+    cleared is zeroed by finish() (stale gradients cannot reach the optimizer), and an accumulate into a stale slot raises."""
+    dp = importlib.import_module("visual-question-answering_b200.dp")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    red = dp.FlatGradAllReduce(net.named_parameters(), None, skip=(), flat_params=True, direct_write=False)
+    w0, b0, w1, b1 = list(net.parameters())
+    # step 1: everything is cleared (no history), two tensors are written directly, two arrive through autograd
+    red.zero_grad()
+    assert float(red.flat.abs().sum()) == 0.0
+    slot = red.take(w0)
+    assert slot is not None and slot.data_ptr() == w0.grad.data_ptr() and red.take(w0) is None      # one direct write per step
+    slot.fill_(1.0)
+    assert red.delivered(slot) and not red.delivered(torch.zeros_like(slot))
+    sb = red.take(b1)
+    sb.fill_(2.0)
+    assert red.delivered(sb)
+    net(torch.randn(4, 5)).sum().backward(inputs=[b0, w1])          # autograd accumulates into the cleared views
+    red.finish()
+    assert torch.all(w0.grad == 1.0) and torch.all(b1.grad == 2.0) and float(w1.grad.abs().sum()) > 0
+    assert red._direct_prev == {red._by_param[w0.data_ptr()], red._by_param[b1.data_ptr()]}
+    # step 2: only the slots NOT written directly last time are cleared; the direct ones keep stale data until they are rewritten
+    red.zero_grad()
+    assert float(w1.grad.abs().sum()) == 0.0 and torch.all(w0.grad == 1.0)
+    s2 = red.take(w0)
+    s2.fill_(3.0)
+    red.delivered(s2)
+    red.finish()                                                     # b1 was neither rewritten nor cleared: finish() zeroes it
+    assert torch.all(w0.grad == 3.0) and float(b1.grad.abs().sum()) == 0.0
+    # step 3: accumulating into a slot that still holds last step's direct write is refused
+    red.zero_grad()
+    with pytest.raises(RuntimeError):
+        net(torch.randn(4, 5)).sum().backward(inputs=[w0])
