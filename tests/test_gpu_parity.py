@@ -325,7 +325,8 @@ def test_flat_gradient_sink_direct_write(syn):
             else:
                 assert h.rel(g, ref_b[n]) < 1e-4, n
     finally:
-        h.PKG.ops.remove_grad_sink(red)
+        red.close()
+        assert red not in h.PKG.ops._SINKS
 
 
 def test_inference_predict_and_attention_maps(syn):

@@ -199,5 +199,14 @@ class FlatGradAllReduce:
         self._work = []
         self._left = list(self._need)
 
+    def close(self):
+        """Detach from autograd and from the backward kernels: removes the hooks and the gradient-sink registration (the flat buffers
+        and the ``.grad`` / ``.data`` views stay valid)."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        from . import ops
+        ops.remove_grad_sink(self)
+
     def grad_bytes(self) -> int:
         return self.flat.numel() * self.flat.element_size()
