@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HCA_ABI_VERSION 5
+#define HCA_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define HCA_API __attribute__((visibility("default")))
@@ -47,8 +47,10 @@ HCA_API const char* hca_last_error(void);
 /* number of CUDA kernels this library has launched from the calling process so far (bench.py's
  * gpu_launches is the difference across the timed region) */
 HCA_API int64_t hca_launch_count(void);
-/* runtime switches: name in {"gemm"}; value "tc" (tcgen05 tensor-core path, default on sm_100) or
- * "ffma" (plain fp32 CUDA-core path, the bring-up / cross-check path).  Returns 0 or HCA_ERR_ARG. */
+/* runtime switches.  "pdl" = "0" / "1": programmatic dependent launch off / on (a profiler leg that wants exclusive kernel
+ * durations turns it off); "pool_tie_cap" = "<n>": test hook, caps the near-tie list of the phrase max-pool repair at n entries
+ * (0 = default) so that its exhaustive mode can be exercised; "gemm" reports "tc" (tcgen05: the only contraction backend).
+ * Returns 0 or HCA_ERR_ARG. */
 HCA_API int hca_set_option(const char* name, const char* value);
 HCA_API const char* hca_get_option(const char* name);
 
@@ -153,6 +155,30 @@ HCA_API int hca_mlp_bwd(const float* dlogits, const void* saved, size_t saved_by
 HCA_API int hca_adam_step(float* p, const float* g, float* m, float* v, int64_t n, long long* step, float* coef,
                   float lr, float beta1, float beta2, float eps, void* stream);
 
+/* advances `step` and fills `coef` only (the first half of hca_adam_step), for callers that apply the update with
+ * hca_dp_reduce_adam below */
+HCA_API int hca_adam_prep(long long* step, float* coef, float lr, float beta1, float beta2, void* stream);
+
+/* ---- data parallel: gradient all-reduce + Adam + parameter broadcast in ONE kernel over NVLink / NVSwitch ----------
+ * (the reference has no multi-GPU path: main.py:102-106 is a commented-out nn.DataParallel TODO; this is the collective
+ * `north_star` adds, fused with the optimizer of main.py:180,222.)
+ * Every rank holds one SYMMETRIC block (same layout on every GPU, mapped into every peer): [flags | ... g ... | ... p ...].
+ *   peer_bases  HOST array [world] of the block's base address on every rank as mapped into THIS process (peer_bases[rank] is
+ *               the local one); mc_base = the block's multicast (NVLS) address, or 0 to use plain peer loads / stores;
+ *   flags_off   byte offset of hca_dp_flags_bytes() bytes of zero-initialised flag words; g_off / p_off: byte offsets of the
+ *               flat fp32 gradient / parameter buffers; [begin, end) the element range to process (multiples of 4);
+ *   channel     0..3: launches that may run concurrently (different streams) must use different channels;
+ *   max_ctas    cap on the grid (0 = no cap): a launch meant to overlap other work leaves SMs to it;
+ *   mode        bit 0: Adam update of the owner's slice + broadcast of the new parameters to every rank (m, v: local fp32 [n]
+ *               moment buffers, of which each rank uses only its slice; coef from hca_adam_prep);
+ *               bit 1: the summed gradient is written back to every rank's g (a plain all-reduce).
+ * Collective: every rank must make the same call (same range, channel, max_ctas, mode).  A rank that never arrives trips a
+ * bounded wait (the kernel traps, the host sees a CUDA error): no hang. */
+HCA_API size_t hca_dp_flags_bytes(void);
+HCA_API int hca_dp_reduce_adam(const uint64_t* peer_bases, uint64_t mc_base, size_t flags_off, size_t g_off, size_t p_off,
+                       int64_t begin, int64_t end, int rank, int world, int channel, int max_ctas, float* m, float* v,
+                       const float* coef, float beta1, float beta2, float eps, int mode, void* stream);
+
 /* ---- loss (replaces nn.CrossEntropyLoss()(logits, labels) and its backward, main.py:179,214) ---------------------- */
 /* loss[0] = scale * mean_b CE(logits[b,:K], labels[b]); dlogits (optional, leading dim ldd) = d loss / d logits.  One launch.
  * `ws` >= hca_ce_loss_workspace(B) bytes of scratch.  labels int64 in [0,K): others give NaN. */
@@ -183,6 +209,7 @@ HCA_API int hca_debug_gemm_timeline(void* buf, int nctas);
 HCA_API int hca_debug_gemm_timeline_select(void* buf, int nctas, int launch_index);
 /* debug: CTA 0 of the following LSTM recurrence launches records clock64() stamps into buf (int64 [7 rounds][8]); NULL = off */
 HCA_API int hca_debug_lstm_timeline(void* buf);
+/* one dense contraction from fp32 operands (tests / profiling): layout 0 nt, 1 nn, 2 tn; path 1 = bf16x2 split (3 MMAs), 2 = bf16x3 */
 HCA_API int hca_gemm(const float* A, const float* B, const float* bias, float* D, int M, int N, int K,
                      int layout, int path, void* ws, size_t ws_bytes, void* stream);
 

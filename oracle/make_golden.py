@@ -177,6 +177,62 @@ def record_state_dict_keys():
     print("wrote state_dict_keys.json", len(out))
 
 
+WRAPPER_CFG = dict(B=2, img=448, T=9, vocab=200, K=21, mlp_dim=1024, d=512, vgg_seed=1234, seed=7)
+
+
+def make_vgg_weights_file(path, seed):
+    """Random-init vgg11_bn state_dict written the way ``--vgg_wts_path`` expects it (main.py:66, model.py:229-234).  torch's CPU
+    generator is deterministic for a given version, so the GPU-side test regenerates the same file from the same seed (and
+    checks the digest stored in the fixture before trusting it)."""
+    import torchvision
+    torch.manual_seed(seed)
+    vgg = torchvision.models.vgg11_bn(weights=None)
+    torch.save(vgg.state_dict(), path)
+    sd = vgg.state_dict()
+    return np.asarray([float(sd["features.0.weight"].double().sum()), float(sd["features.25.weight"].double().norm())])
+
+
+def wrapper_fixture():
+    """The FULL reference wrapper (model.py:157-187): random-init VGG11-bn trunk from a generated weights file -> permuted
+    [B,196,512] view -> question encoder -> co-attention -> MLP, fp32 on CPU, eval mode (BatchNorm on its running statistics).
+    Stores logits, loss, a digest of the image features, the gradient digests of every trainable tensor, and the full list of
+    state_dict keys / shapes (85 keys: 56 of them VGG's)."""
+    import tempfile
+    c = WRAPPER_CFG
+    path = os.path.join(tempfile.mkdtemp(), "vgg11_bn_random.pth")
+    vgg_digest = make_vgg_weights_file(path, c["vgg_seed"])
+    net = ref.HierarchicalCoAttentionNet(dict(vocab_size=c["vocab"], word_emb_dim=c["d"], hidden_dim=c["d"]),
+                                         dict(is_trainable=False, weights_path=path), K=c["K"], mlp_dim=c["mlp_dim"])
+    p = syn.make_params(c["d"], c["vocab"], c["K"], c["mlp_dim"], seed=c["seed"])
+    missing, unexpected = net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()}, strict=False)
+    assert not unexpected and all(k.startswith("image_encoder.") for k in missing)
+    net.eval()
+    x = syn.make_inputs(c["B"], 196, c["T"], c["d"], c["vocab"], c["K"], seed=c["seed"], min_len=1)
+    rng = np.random.RandomState(c["seed"])
+    images = rng.standard_normal((c["B"], 3, c["img"], c["img"])).astype(np.float32)
+    feats = net.image_encoder(torch.from_numpy(images))
+    assert tuple(feats.shape) == (c["B"], 196, 512) and feats.stride() == (196 * 512, 1, 196) and not feats.requires_grad
+    logits = net(torch.from_numpy(images), torch.from_numpy(x["tokens"]), torch.from_numpy(x["lens"]))     # main.py:211
+    loss = torch.nn.CrossEntropyLoss()(logits, torch.from_numpy(x["labels"]))                               # main.py:179,214
+    loss.backward()
+    blob = {f"cfg.{k}": np.asarray(v) for k, v in c.items()}
+    blob["vgg_digest"] = vgg_digest
+    blob["logits"] = logits.detach().numpy()
+    blob["loss"] = loss.detach().numpy()
+    blob["feats.digest"] = digest(feats.detach().numpy())
+    for n, prm in net.named_parameters():
+        if prm.grad is not None:
+            blob[f"grad.{n}.digest"] = digest(prm.grad.numpy())
+        else:
+            assert n.startswith("co_attention.W_b") or n.startswith("image_encoder."), n
+    import json
+    blob["state_dict"] = np.asarray(json.dumps({k: list(v.shape) for k, v in net.state_dict().items()}))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "wrapper_448.npz"), **blob)
+    print("wrote wrapper_448", "loss", float(loss), "keys", len(net.state_dict()))
+
+
 if __name__ == "__main__":
-    main()
-    record_state_dict_keys()
+    if "--wrapper-only" not in sys.argv:
+        main()
+        record_state_dict_keys()
+    wrapper_fixture()

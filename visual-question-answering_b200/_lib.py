@@ -45,6 +45,9 @@ SIGNATURES = {
     "hca_mlp_fwd": (_i, [_p] * 12 + [_sz] + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_mlp_bwd": (_i, [_p] * 2 + [_sz] + [_p] * 9 + [_i, _i, _i, _i, _p, _sz, _p]),
     "hca_adam_step": (_i, [_p, _p, _p, _p, _i64, _p, _p, C.c_float, C.c_float, C.c_float, C.c_float, _p]),
+    "hca_adam_prep": (_i, [_p, _p, C.c_float, C.c_float, C.c_float, _p]),
+    "hca_dp_flags_bytes": (_sz, []),
+    "hca_dp_reduce_adam": (_i, [_p, C.c_uint64, _sz, _sz, _sz, _i64, _i64, _i, _i, _i, _i, _p, _p, _p, C.c_float, C.c_float, C.c_float, _i, _p]),
     "hca_ce_loss_workspace": (_sz, [_i]),
     "hca_ce_loss": (_i, [_p, _i64, _p, _i, _i, C.c_float, _p, _p, _i64, _p, _sz, _p]),
     "hca_gemm_workspace": (_sz, [_i, _i, _i]),
@@ -56,7 +59,7 @@ SIGNATURES = {
     "hca_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
 }
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 _lib = None
 
 

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstdlib>
 #include <atomic>
 
 #include "../../include/hiecoattn_b200.h"
@@ -80,9 +81,20 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Tuning knobs for profiling experiments come from the environment and are read ONCE per process (function-local static), never
+// on the per-launch path: HCA_ENV_INT("NAME", default).
+#define HCA_ENV_INT(name, dflt)                    \
+  ([]() -> int {                                   \
+    static const int v = []() -> int {             \
+      const char* e_ = getenv(name);               \
+      return e_ ? atoi(e_) : (dflt);               \
+    }();                                           \
+    return v;                                      \
+  }())
+int current_device();      // cudaGetDevice, clamped to [0, 64)
+
 // options
-bool use_tc();
-bool pdl_enabled();      // HCA_PDL=0 turns programmatic dependent launch off (plain stream-ordered launches)
+bool pdl_enabled();      // HCA_PDL=0 / hca_set_option("pdl", "0") turns programmatic dependent launch off (plain stream-ordered launches)
 
 // ---- programmatic dependent launch -------------------------------------------------------------------
 // The step is a chain of ~90 kernels, many of them a few microseconds long: the gap between a kernel's last CTA retiring and

@@ -1055,7 +1055,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   // enough to leave every pair several k-blocks): there the mainloop's operand fill is the limit and the pair halves it
   bool pair_wgrad = pair_epi && splitk > 1 /* the caller has cleared D */ && A.mn_major && B.mn_major && (M % 256) == 0 && (N % 256) == 0 && K >= 2048 && !e.bias && !e.act_tanh &&
                     !e.red_col && !e.P.p && e.D != nullptr && f32_tma_ok(e.D, e.ldd, e.d_batch_stride, 0);
-  { const char* ev = getenv("HCA_TC_PAIR_WGRAD"); if (ev && atoi(ev) == 0) pair_wgrad = false; }
+  if (HCA_ENV_INT("HCA_TC_PAIR_WGRAD", 1) == 0) pair_wgrad = false;
   bool pair = pair_epi && !A.mn_major && !B.mn_major && splitk == 1 && (N % 256) == 0 && M >= 8192 && K >= 256;
   if (pair) {
     // wave quantisation: a pair tile is four single tiles of MMA time on two SMs.  Take the pair schedule only when its last,
@@ -1066,17 +1066,13 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
     if ((double)(2 * w2) > 1.15 * (double)w1) pair = false;
   }
   {
-    const char* ev = getenv("HCA_TC_PAIR");
-    const int pair_env = ev ? atoi(ev) : -1;
+    const int pair_env = HCA_ENV_INT("HCA_TC_PAIR", -1);
     if (pair_env == 0) pair = false;
     if (pair_env == 1 && !e.transposed && P == 2 && !A.mn_major && !B.mn_major && !A2 && splitk == 1 && batch == 1 && (N % 256) == 0 &&
         e.mode == TC_EPI_STORE && e.aux_mode == TC_AUX_NONE && !e.r1col && !e.mulx && e.d_groups <= 1 && A.nbatch <= 1 && B.nbatch <= 1)
       pair = true;
   }
-  if (pair_wgrad) {
-    const char* ev = getenv("HCA_TC_PAIR");
-    if (ev && atoi(ev) == 0) pair_wgrad = false;
-  }
+  if (HCA_ENV_INT("HCA_TC_PAIR", -1) == 0) pair_wgrad = false;
   if (pair_wgrad) {
     pair = true;
     // the split is chosen for the pair grid: one 256 x 256 tile per pair and wave, at least 4 k-blocks per split
@@ -1158,12 +1154,12 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   const uint32_t avail = SMEM_LIMIT - (pair ? 11264 : 9216);
   // (only behind a long mainloop: there a TMA store queues behind the operand loads; the single-k-block products keep the
   // double-buffered asynchronous TMA stores their epilogue-bound tiles were tuned with)
-  bool pl_direct = want_pl && !e.transposed && p.kb_total >= 4;
-  { const char* ev = getenv("HCA_TC_PLDIRECT"); if (ev && atoi(ev) == 0) pl_direct = false; }
-  const int n_out = (!e.transposed && want_f32 && tma_store ? 1 : 0) + (!e.transposed && want_pl && !pl_direct ? 1 : 0);
-  const bool has_aux_buf = !e.transposed && aux_kind;
   p.kb1 = (K + BK - 1) / BK;
   p.kb_total = p.kb1 + (A2 ? (K2 + BK - 1) / BK : 0);
+  bool pl_direct = want_pl && !e.transposed && p.kb_total >= 4;
+  if (HCA_ENV_INT("HCA_TC_PLDIRECT", 0) == 0) pl_direct = false;      // opt-in (HCA_TC_PLDIRECT=1) until re-measured
+  const int n_out = (!e.transposed && want_f32 && tma_store ? 1 : 0) + (!e.transposed && want_pl && !pl_direct ? 1 : 0);
+  const bool has_aux_buf = !e.transposed && aux_kind;
   auto stages_for = [&](int neg, int nbuf) {
     const uint32_t epi = (uint32_t)neg * ((uint32_t)(n_out * nbuf) + (has_aux_buf ? 1u : 0u)) * CHUNK_BYTES + (pl_direct ? (uint32_t)neg * 8192u : 0u);
     return epi >= avail ? 0 : (int)((avail - epi) / stage_bytes);
@@ -1178,7 +1174,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   if (epi_heavy && stages_for(2, 1) >= (p.kb_total == 1 ? 1 : 2)) neg = 2;
   // planes-only output through the warp-private staging costs 8 KB per group: take the second group whenever it is free
   if (neg == 1 && pl_direct && n_out == 0 && std::min(stages_for(2, 1), MAX_STAGES) >= std::min(stages_for(1, 1), MAX_STAGES)) neg = 2;
-  { const char* ev = getenv("HCA_TC_EG"); if (ev && (atoi(ev) == 1 || atoi(ev) == 2)) neg = atoi(ev); }
+  { const int ev = HCA_ENV_INT("HCA_TC_EG", 0); if (ev == 1 || ev == 2) neg = ev; }
   // single-k-block tiles (the K = T products) need no operand pipelining beyond the TMEM double buffer: one stage is enough
   // there, which leaves room to double-buffer the epilogue staging -- their long pole
   const int min_stages = p.kb_total == 1 ? 1 : 2;
@@ -1190,7 +1186,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   int stages = stages_for(neg, nbuf);
   if (stages < min_stages && neg == 2) { neg = 1; nbuf = 1; stages = stages_for(1, 1); }
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  { const char* ev = getenv("HCA_TC_STAGES"); if (ev && atoi(ev) >= 1 && atoi(ev) < stages) stages = atoi(ev); }
+  { const int ev = HCA_ENV_INT("HCA_TC_STAGES", 0); if (ev >= 1 && ev < stages) stages = ev; }
   HCA_CHECK_ARG(stages >= min_stages, "gemm_tc: tile does not fit its pipeline stages");
   p.stages = stages;
   p.store_nbuf = nbuf;
@@ -1244,7 +1240,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   if (e.transposed)
     HCA_CHECK_ARG(!e.mulx && e.mode == TC_EPI_STORE && !e.r1col && !e.red_col && groups == 1 && !e.aux,
                   "gemm_tc: the transposed epilogue supports fp32 / planes output, a per-row bias, tanh, auxp and red_row only");
-  { static int dbg = -1; if (dbg < 0) { const char* ev = getenv("HCA_TC_DBG"); dbg = ev ? atoi(ev) : 0; } p.dbg = dbg; }
+  p.dbg = HCA_ENV_INT("HCA_TC_DBG", 0);
   p.timeline = (g_timeline && (g_timeline_target < 0 || g_timeline_seen == g_timeline_target)) ? g_timeline : nullptr;
   p.timeline_ctas = g_timeline_ctas;
   if (g_timeline) ++g_timeline_seen;
@@ -1260,7 +1256,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   int slot = -1;
   // lean epilogue instantiation (EPI = 0) for products without fused epilogue math; HCA_TC_LEAN=0 forces the full one
   bool lean = !e.transposed && e.aux_mode == TC_AUX_NONE && e.mode == TC_EPI_STORE && !e.r1col && !e.mulx && !e.red_col && !e.rowv && !e.colv;
-  { const char* ev = getenv("HCA_TC_LEAN"); if (ev && atoi(ev) == 0) lean = false; }
+  if (HCA_ENV_INT("HCA_TC_LEAN", 1) == 0) lean = false;
   const bool lean_tanh = lean && e.act_tanh;
 #define HCA_TC_CASE(SLOT, BNN, PP, CC, AMN, BMN, BKK)                                                            \
   if (BN == BNN && P == PP && combo == CC && BK == BKK) {                                                         \
@@ -1279,10 +1275,11 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
     else { fn = gemm_tc_kernel<256, 2, false, false, 64, 2, 1>; slot = 9; }
   }
   HCA_CHECK_ARG(fn != nullptr, "gemm_tc: this (BN, P, layout) combination is not instantiated (BN=%d P=%d combo=%d)", BN, P, combo);
-  static bool attr_set[30] = {};
-  if (!attr_set[slot]) {
+  static bool attr_set[64][30] = {};                 // function attributes are per device
+  bool& attr_done = attr_set[current_device()][slot];
+  if (!attr_done) {
     HCA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-    attr_set[slot] = true;
+    attr_done = true;
   }
   if (pair) {
     cudaLaunchConfig_t cfg = {};

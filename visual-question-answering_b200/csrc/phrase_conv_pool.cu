@@ -9,33 +9,16 @@
 // channel triples of [uni|bi|tri] (the reshape at model.py:329), records the uint8 argmax (first index
 // on ties, like MaxPool2d) and zeroes rows t >= len (model.py:287-292).
 //
-// The pre-activations must be fp32-grade: an argmax flip re-routes a gradient element,
-// so the forward products run on the exact-fp32 GEMM path.  The backward products (dgrad, wgrad) only
-// need the 1e-3 budget and may use the tensor-core path.
+// An argmax flip re-routes a gradient element, so the pooled indices must be those of an fp32 evaluation.
+// The convs run on tcgen05 as a bf16x2 split (~2^-16 operand precision); every channel triple whose top-2 gap lies inside
+// the error band of that split (scaled by the norms of the rows involved) is then recomputed in plain fp32 -- see tie_band().
 #include <algorithm>
 #include "common.cuh"
-#include "gemm_ffma.cuh"
-#include "dense.cuh"
 #include "gemm_tc.cuh"
 #include "util_kernels.cuh"
 
 namespace hca {
 namespace {
-
-// Acat[r][j*E + c] = x[b][t+j-1][c]   (float4 granularity)
-__global__ void __launch_bounds__(256) im2col3_kernel(const float4* __restrict__ x, float4* __restrict__ acat, int B, int T, int E4) {
-  pdl_enter();
-  const int64_t total = (int64_t)B * T * 3 * E4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % E4);
-    const int j = (int)((i / E4) % 3);
-    const int64_t r = i / (3 * E4);
-    const int t = (int)(r % T) + j - 1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t >= 0 && t < T) v = __ldg(x + (r + j - 1) * E4 + c);
-    acat[i] = v;
-  }
-}
 
 // dx[b][t] = dA[r][E:2E] + dA[r+1][0:E] (t+1<T) + dA[r-1][2E:3E] (t>0)
 __global__ void __launch_bounds__(256) col2im3_kernel(const float4* __restrict__ dA, float4* __restrict__ dx, int B, int T, int E4) {
@@ -58,31 +41,82 @@ __global__ void __launch_bounds__(256) col2im3_kernel(const float4* __restrict__
   }
 }
 
-// wr[o][j*E + c] = w[o][c][j]   (to_conv == false)      or      w[o][c][j] = wr[o][j*E + c]  (to_conv == true)
-__global__ void __launch_bounds__(256) repack_conv_w_kernel(const float* __restrict__ src, float* __restrict__ dst, int E, int k, bool to_conv) {
+// Max-pool argmax must match the reference bit for bit, but the tensor-core conv (bf16x2 operand split, 3 MMAs) is not exact:
+// each operand carries a residual of at most 2^-18 relative and the lo.lo product is dropped, so one term x_i w_i is off by at
+// most 3 * 2^-18 |x_i w_i| and a pre-activation by at most 3 * 2^-18 * sum |x_i w_i| <= 1.15e-5 * ||x|| ||w|| (Cauchy-Schwarz; x =
+// the taps of the token window, w = the filter row).  tie_band() turns that into a band on the gap of two post-tanh values:
+//     EPS = 2^-16 (the bound above with a third to spare for the fp32 accumulation in TMEM)
+//     err = EPS * ||x_window|| * ||w_row||                       (largest of the three channels of the triple)
+//     band = 2 * err * (slope + err) + 1e-6,  slope = 1 - min(a^2, b^2) >= tanh'(.) at either value
+// The band SCALES with the operands (a model whose embeddings or filters have grown 8x gets an 8x..64x wider band), and a saturated
+// triple (values within ulps of +-1) has slope ~ 0, so only the 1e-6 floor is left -- enough for the 2e-7 of tanh_fast.  The pool
+// kernel lists every triple whose top-2 gap is inside the band; fixup_ties_kernel recomputes the listed triples in plain fp32 from
+// the fp32 inputs.  If the list overflows its capacity (R*E/4 entries) nothing is dropped: the fix-up kernel then re-derives the
+// condition for EVERY element from `cat` and repairs those (slower, still exact) -- the repair is fail-safe, never silent.
+constexpr float TIE_EPS = 1.52587890625e-5f;      // 2^-16
+
+// squared norms the band needs, one warp per row: xn2[r] = ||x[r,:]||^2 for the R token rows, wn[c] = ||W_k[o,:,:]|| for the 3E
+// channels c = (k-1) E + o of [uni|bi|tri]
+__global__ void __launch_bounds__(256) conv_norms_kernel(const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ w2,
+                                                         const float* __restrict__ w3, float* __restrict__ xn2, float* __restrict__ wn, int R, int E) {
   pdl_enter();
-  const int64_t total = (int64_t)E * E * k;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    // i indexes the tap-major layout [o][j][c]
-    const int c = (int)(i % E);
-    const int j = (int)((i / E) % k);
-    const int64_t o = i / ((int64_t)E * k);
-    const int64_t conv_idx = (o * E + c) * k + j;
-    if (to_conv) dst[conv_idx] = src[i];
-    else dst[i] = src[conv_idx];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < R + 3 * E; row += warps) {
+    const float* src;
+    int n;
+    if (row < R) {
+      src = x + (int64_t)row * E;
+      n = E;
+    } else {
+      const int c = row - R, k = c / E + 1, o = c - (k - 1) * E;
+      src = (k == 1 ? w1 : (k == 2 ? w2 : w3)) + (int64_t)o * E * k;
+      n = E * k;
+    }
+    float acc = 0.f;
+    for (int i = lane * 4; i < n; i += 128) {             // E % 4 == 0: rows are 16-byte aligned
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+      acc = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, acc))));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (row < R) xn2[row] = acc;
+      else wn[row - R] = sqrtf(acc);
+    }
   }
 }
 
-// Max-pool argmax must match the reference bit for bit, but the tensor-core conv (bf16x2 operand split: per-term relative error
-// <= ~2^-16.5, i.e. sigma ~1.3e-5 on a pre-activation of 1536 terms, ~1.8e-5 on a gap of two) is not exact.  So the pool kernel
-// records every element whose top-2 gap is below TIE_TOL (> 20 sigma of that error) and fixup_ties_kernel recomputes just those
-// elements in exact fp32 (value and index): ~0.1 % of the elements.  (The first version ran the conv as a bf16x3 split, 6 MMAs per
-// product, to stay two orders of magnitude under the band; with the exact repair in place 3 MMAs and a wider band do the same job.)
-constexpr float TIE_TOL = 4e-4f;
+// band on the top-2 gap of the triple e of row r (see above); a, b = the two largest post-tanh values
+__device__ __forceinline__ float tie_band(const float* __restrict__ xn2, const float* __restrict__ wn, int64_t r, int t, int T, int e, int E,
+                                          float a, float b) {
+  const float x0 = xn2[r], xm = t > 0 ? xn2[r - 1] : 0.f, xp = t + 1 < T ? xn2[r + 1] : 0.f;
+  float err = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int c = 3 * e + j;
+    const int k = c < E ? 1 : (c < 2 * E ? 2 : 3);
+    const float win = k == 1 ? x0 : (k == 2 ? x0 + xm : x0 + xm + xp);
+    err = fmaxf(err, sqrtf(win) * wn[c]);
+  }
+  err *= TIE_EPS;
+  const float slope = 1.f - fminf(a * a, b * b);
+  return 2.f * err * (slope + err) + 1e-6f;
+}
+// the two largest of three and the first index attaining the maximum (MaxPool2d semantics: a later element wins only if strictly
+// greater, or is NaN)
+__device__ __forceinline__ void top2_of3(float v0, float v1, float v2, float& best, float& mid, int& bi) {
+  best = v0;
+  bi = 0;
+  if (v1 > best || v1 != v1) { best = v1; bi = 1; }
+  if (v2 > best || v2 != v2) { best = v2; bi = 2; }
+  const float lo = fminf(fminf(v0, v1), v2);
+  mid = v0 + v1 + v2 - best - lo;                          // middle value (approximate is fine: only a trigger)
+}
 
-// cat [R, 3E] (post tanh) -> out [R, E], idx [R, E]; rows t >= len zeroed.  tie_list/tie_count may be null.
+// cat [R, 3E] (post tanh) -> out [R, E], idx [R, E]; rows t >= len zeroed.  Near-ties go to tie_list (count keeps counting past tie_cap).
 __global__ void __launch_bounds__(256) pool3_fwd_kernel(const float* __restrict__ cat, const int64_t* __restrict__ lens,
                                                         float* __restrict__ out, uint8_t* __restrict__ idx, int B, int T, int E,
+                                                        const float* __restrict__ xn2, const float* __restrict__ wn,
                                                         int* __restrict__ tie_list, int* __restrict__ tie_count, int tie_cap) {
   pdl_enter();
   const int64_t total = (int64_t)B * T * E;
@@ -94,18 +128,11 @@ __global__ void __launch_bounds__(256) pool3_fwd_kernel(const float* __restrict_
     int bi = 0;
     if (!lens || t < lens[b]) {
       const float* p = cat + r * 3 * (int64_t)E + 3 * e;
-      const float v0 = p[0], v1 = p[1], v2 = p[2];
-      best = v0;
-      // MaxPool2d semantics: a later element wins only if strictly greater, or is NaN
-      if (v1 > best || v1 != v1) { best = v1; bi = 1; }
-      if (v2 > best || v2 != v2) { best = v2; bi = 2; }
-      if (tie_list) {
-        const float lo = fminf(fminf(v0, v1), v2);
-        const float mid = v0 + v1 + v2 - best - lo;            // middle value (approximate is fine: only a trigger)
-        if (best - mid < TIE_TOL) {
-          const int slot = atomicAdd(tie_count, 1);
-          if (slot < tie_cap) tie_list[slot] = (int)i;
-        }
+      float mid;
+      top2_of3(p[0], p[1], p[2], best, mid, bi);
+      if (!(best - mid >= tie_band(xn2, wn, r, t, T, e, E, best, mid))) {      // (NaN lands here too)
+        const int slot = atomicAdd(tie_count, 1);
+        if (slot < tie_cap) tie_list[slot] = (int)i;
       }
     }
     out[i] = best;
@@ -113,74 +140,104 @@ __global__ void __launch_bounds__(256) pool3_fwd_kernel(const float* __restrict_
   }
 }
 
-// one warp per listed element: the three pre-activations of its channel triple in plain fp32, then tanh and the max again
+// The three pre-activations of channel triple e of row r in plain fp32 from the fp32 inputs (one warp), then tanh and the max again.
+__device__ __forceinline__ void fixup_one(int64_t r, int e, const float* __restrict__ x, int T, const float* __restrict__ w1,
+                                          const float* __restrict__ w2, const float* __restrict__ w3, const float* __restrict__ b1,
+                                          const float* __restrict__ b2, const float* __restrict__ b3, float* __restrict__ out,
+                                          uint8_t* __restrict__ idx, int E) {
+  const int lane = threadIdx.x & 31;
+  const int t = (int)(r % T);
+  const float* x0 = x + r * (int64_t)E;
+  const bool has_m = t > 0, has_p = t + 1 < T;
+  float v[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int c = 3 * e + j;                      // channel of the concatenated [uni|bi|tri] axis
+    const int k = c / E + 1, o = c % E;           // which conv, which output channel
+    const float* wrow = (k == 1 ? w1 : (k == 2 ? w2 : w3)) + (int64_t)o * E * k;   // conv layout [C_in][k]: lane cc reads its k taps contiguously
+    // taps: k = 1: x[t] ; k = 2: x[t-1], x[t] ; k = 3: x[t-1], x[t], x[t+1] ; zeros outside [0, T)
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (k == 1) {
+#pragma unroll 4
+      for (int cc = lane; cc < E; cc += 32) a0 = fmaf(x0[cc], wrow[cc], a0);
+    } else if (k == 2) {
+#pragma unroll 4
+      for (int cc = lane; cc < E; cc += 32) {
+        const float2 w = *reinterpret_cast<const float2*>(wrow + 2 * cc);
+        if (has_m) a0 = fmaf(x0[cc - E], w.x, a0);
+        a1 = fmaf(x0[cc], w.y, a1);
+      }
+    } else {
+#pragma unroll 4
+      for (int cc = lane; cc < E; cc += 32) {
+        const float wa = wrow[3 * cc], wb = wrow[3 * cc + 1], wc = wrow[3 * cc + 2];
+        if (has_m) a0 = fmaf(x0[cc - E], wa, a0);
+        a1 = fmaf(x0[cc], wb, a1);
+        if (has_p) a2 = fmaf(x0[cc + E], wc, a2);
+      }
+    }
+    const float acc = warp_sum(a0 + a1 + a2);
+    v[j] = tanhf(acc + (k == 1 ? b1 : (k == 2 ? b2 : b3))[o]);
+  }
+  float best, mid;
+  int bi;
+  top2_of3(v[0], v[1], v[2], best, mid, bi);
+  if (lane == 0) {
+    out[r * E + e] = best;
+    idx[r * E + e] = (uint8_t)bi;
+  }
+}
+
+// Repairs the listed near-ties (one warp per entry).  When more were found than the list holds, the list is ignored and every element is
+// re-examined instead: each lane re-derives the band condition of one element from `cat`, the warp then repairs the flagged ones in turn.
 __global__ void __launch_bounds__(256) fixup_ties_kernel(const int* __restrict__ tie_list, const int* __restrict__ tie_count, int tie_cap,
-                                                         const float* __restrict__ x, int T, const float* __restrict__ w1,
+                                                         const float* __restrict__ cat, const int64_t* __restrict__ lens,
+                                                         const float* __restrict__ xn2, const float* __restrict__ wn,
+                                                         const float* __restrict__ x, int B, int T, const float* __restrict__ w1,
                                                          const float* __restrict__ w2, const float* __restrict__ w3,
                                                          const float* __restrict__ b1, const float* __restrict__ b2,
                                                          const float* __restrict__ b3, float* __restrict__ out,
-                                                         uint8_t* __restrict__ idx, int E) {
+                                                         uint8_t* __restrict__ idx, int E, int* __restrict__ stats) {
   pdl_enter();
-  const int n = min(*tie_count, tie_cap);
+  const int found = *tie_count;
+  if (stats && blockIdx.x == 0 && threadIdx.x == 0) { stats[0] = found; stats[1] = tie_cap; }
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += warps) {
-    const int i = tie_list[w];
-    const int64_t r = i / E;
-    const int e = i - (int)r * E;
-    float v[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int c = 3 * e + j;                    // channel of the concatenated [uni|bi|tri] axis
-      const int k = c / E + 1, o = c % E;         // which conv, which output channel
-      const float* wrow = (k == 1 ? w1 : (k == 2 ? w2 : w3)) + (int64_t)o * E * k;   // conv layout [C_in][k]
-      const int t = (int)(r % T);
-      float acc = 0.f;
-      // taps of conv k cover x[t-1], x[t] (k = 2), x[t-1..t+1] (k = 3), x[t] (k = 1); zeros outside [0, T)
-      for (int tap = 0; tap < k; ++tap) {
-        const int tt = t + tap - (k == 1 ? 0 : 1);
-        if (tt < 0 || tt >= T) continue;
-        const float* xrow = x + (r + tt - t) * (int64_t)E;
-        for (int cc = lane; cc < E; cc += 32) acc = fmaf(xrow[cc], wrow[(int64_t)cc * k + tap], acc);
-      }
-      acc = warp_sum(acc);
-      v[j] = tanhf(acc + (k == 1 ? b1 : (k == 2 ? b2 : b3))[o]);
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (found <= tie_cap) {
+    for (int w = warp0; w < found; w += warps) {
+      const int i = tie_list[w];
+      const int64_t r = i / E;
+      fixup_one(r, i - (int)r * E, x, T, w1, w2, w3, b1, b2, b3, out, idx, E);
     }
-    float best = v[0];
-    int bi = 0;
-    if (v[1] > best || v[1] != v[1]) { best = v[1]; bi = 1; }
-    if (v[2] > best || v[2] != v[2]) { best = v[2]; bi = 2; }
-    if (lane == 0) {
-      out[i] = best;
-      idx[i] = (uint8_t)bi;
-    }
+    return;
   }
-}
-
-// dcat[r][3e+j] = (j == idx) ? dout * (1 - out^2) : 0 ; masked rows all zero
-__global__ void __launch_bounds__(256) pool3_bwd_kernel(const float* __restrict__ out, const uint8_t* __restrict__ idx,
-                                                        const float* __restrict__ dout, const int64_t* __restrict__ lens,
-                                                        float* __restrict__ dcat, int B, int T, int E) {
-  pdl_enter();
   const int64_t total = (int64_t)B * T * E;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / E;
-    const int e = (int)(i - r * E);
-    const int b = (int)(r / T), t = (int)(r % T);
-    float g = 0.f;
-    int j = 0;
-    if (!lens || t < lens[b]) {
-      const float o = out[i];
-      g = dout[i] * (1.f - o * o);
-      j = idx[i];
+  for (int64_t base = (int64_t)warp0 * 32; base < total; base += (int64_t)warps * 32) {
+    const int64_t i = base + lane;
+    bool flag = false;
+    if (i < total) {
+      const int64_t r = i / E;
+      const int e = (int)(i - r * E);
+      const int b = (int)(r / T), t = (int)(r % T);
+      if (!lens || t < lens[b]) {
+        const float* p = cat + r * 3 * (int64_t)E + 3 * e;
+        float best, mid;
+        int bi;
+        top2_of3(p[0], p[1], p[2], best, mid, bi);
+        flag = !(best - mid >= tie_band(xn2, wn, r, t, T, e, E, best, mid));
+      }
     }
-    float* p = dcat + r * 3 * (int64_t)E + 3 * e;
-    p[0] = j == 0 ? g : 0.f;
-    p[1] = j == 1 ? g : 0.f;
-    p[2] = j == 2 ? g : 0.f;
+    unsigned m = __ballot_sync(0xffffffffu, flag);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int64_t ii = base + src;
+      const int64_t r = ii / E;
+      fixup_one(r, (int)(ii - r * E), x, T, w1, w2, w3, b1, b2, b3, out, idx, E);
+    }
   }
 }
-
 
 // ---- tensor-core path helpers: operands are produced directly as bf16 planes (no fp32 im2col / repack round trips) ----
 // x = x0 + x1 (+ x2), planes of 4 consecutive elements packed as uint2
@@ -299,17 +356,7 @@ __global__ void __launch_bounds__(256) pool3_bwd_planes_kernel(const float* __re
     atomicAdd(db + (c % E), sv[j]);
   }
 }
-// tap-major fp32 weight gradient -> conv layout: w[o][c][j] = wr[o][j*E + c]
-__global__ void __launch_bounds__(256) unpack_conv_w_kernel(const float* __restrict__ wr, float* __restrict__ w, int E, int k) {
-  pdl_enter();
-  const int64_t total = (int64_t)E * E * k;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(i % k);
-    const int c = (int)((i / k) % E);
-    const int64_t o = i / ((int64_t)E * k);
-    w[i] = wr[(o * k + j) * E + c];
-  }
-}
+// tap-major fp32 weight gradients -> conv layout: w[o][c][j] = wr[o][j*E + c]
 // both in one launch (bigram and trigram weight gradients)
 __global__ void __launch_bounds__(256) unpack_conv_w23_kernel(const float* __restrict__ wr2, float* __restrict__ w2,
                                                               const float* __restrict__ wr3, float* __restrict__ w3, int E) {
@@ -325,51 +372,55 @@ __global__ void __launch_bounds__(256) unpack_conv_w23_kernel(const float* __res
   }
 }
 
+int g_tie_cap_override = 0;      // test hook (hca_set_option("pool_tie_cap", n)): a tiny list forces the overflow path of the tie repair
+
 struct ConvWs {
   Workspace w;
-  float *acat, *cat, *dA, *wr2, *wr3, *dwr2, *dwr3;
+  float *cat, *dA, *dwr2, *dwr3, *xn2, *wn;
   int *tie_count, *tie_list;
   int tie_cap;
   bool ok;
   ConvWs(void* p, size_t bytes) : w(p, bytes) {}
 };
+size_t tie_cap_default(size_t R, int E) { return R * E / 4 + 1024; }
 ConvWs carve(void* ws, size_t bytes, int B, int T, int E) {
   ConvWs c(ws, bytes);
   Workspace& w = c.w;
   const size_t R = (size_t)B * T;
-  c.acat = w.take<float>(R * 3 * E);
-  c.cat = w.take<float>(R * 3 * E);     // fwd: tanh(conv) ; bwd: dcat
+  c.cat = w.take<float>(R * 3 * E);     // fwd: tanh(conv)
   c.dA = w.take<float>(R * 3 * E);
-  c.wr2 = w.take<float>((size_t)E * 2 * E);
-  c.wr3 = w.take<float>((size_t)E * 3 * E);
   c.dwr2 = w.take<float>((size_t)E * 2 * E);
   c.dwr3 = w.take<float>((size_t)E * 3 * E);
-  c.tie_cap = (int)(R * E / 8 + 1024);
+  c.xn2 = w.take<float>(R);
+  c.wn = w.take<float>((size_t)3 * E);
+  c.tie_cap = (int)tie_cap_default(R, E);
   c.tie_count = w.take<int>(64);
   c.tie_list = w.take<int>((size_t)c.tie_cap);
   c.ok = c.tie_list != nullptr;
+  if (g_tie_cap_override > 0 && g_tie_cap_override < c.tie_cap) c.tie_cap = g_tie_cap_override;
   return c;
 }
 
 }  // namespace
+void set_pool_tie_cap(int n) { g_tie_cap_override = n; }
 }  // namespace hca
 
 extern "C" size_t hca_phrase_conv_pool_workspace(int B, int T, int E) {
   using hca::align_up;
   const size_t R = (size_t)B * T;
-  return 3 * align_up(R * 3 * E * 4) + 2 * (align_up((size_t)E * 2 * E * 4) + align_up((size_t)E * 3 * E * 4)) + 1024 +
-         align_up((R * E / 8 + 1024) * 4) +                                             // near-tie list
-         4 * 2 * align_up(R * 3 * E) + 3 * 3 * 2 * align_up((size_t)E * 3 * E) + 8192 +   // bf16 planes: Acat (x3 fwd) / Acat + dcat (x2 bwd), weights
-
-         std::max(hca::dense_scratch_bytes(E, 3 * E, (int)R), hca::dense_scratch_bytes((int)R, 3 * E, E));
+  return 2 * align_up(R * 3 * E * 4) + align_up((size_t)E * 2 * E * 4) + align_up((size_t)E * 3 * E * 4) + align_up(R * 4) +
+         align_up((size_t)3 * E * 4) + 1024 + align_up(hca::tie_cap_default(R, E) * 4) +          // near-tie list
+         2 * 2 * align_up(R * 3 * E * 2) + 2 * align_up((size_t)2 * E * 6 * E * 2) + 8192;          // bf16 planes when no `fsaved` is given
 }
 
 namespace hca {
 namespace {
-// operand planes kept from forward to backward: Acat [2][R][3E], W1 [2][E][E], W2 [2][E][2E], W3 [2][E][3E]  (bf16)
+// operand planes kept from forward to backward: Acat [2][R][3E], W1 [2][E][E], W2 [2][E][2E], W3 [2][E][3E]  (bf16); the last 256
+// bytes hold the tie-repair statistics of the forward call (int32: listed near-ties, list capacity)
 struct ConvSaved {
   __nv_bfloat16* ap = nullptr;
   __nv_bfloat16* wp[3] = {nullptr, nullptr, nullptr};
+  int* stats = nullptr;
 };
 size_t conv_saved_bytes(int B, int T, int E) {
   const size_t R = (size_t)B * T;
@@ -383,6 +434,7 @@ bool carve_saved(ConvSaved& v, void* buf, size_t bytes, int B, int T, int E) {
   const size_t R = (size_t)B * T;
   v.ap = (__nv_bfloat16*)p; p += align_up(2 * R * 3 * E * 2);
   for (int k = 1; k <= 3; ++k) { v.wp[k - 1] = (__nv_bfloat16*)p; p += align_up((size_t)2 * E * k * E * 2); }
+  v.stats = (int*)p;
   return true;
 }
 }  // namespace
@@ -397,67 +449,48 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
   using namespace hca;
   cudaStream_t s = (cudaStream_t)stream;
   HCA_CHECK_ARG(x && w1 && b1 && w2 && b2 && w3 && b3 && out && idx, "phrase_conv_pool_fwd: null pointer");
-  HCA_CHECK_ARG(B > 0 && T > 0 && E > 0 && E % 4 == 0, "phrase_conv_pool_fwd: bad sizes B=%d T=%d E=%d (E %% 4 == 0 required)", B, T, E);
+  HCA_CHECK_ARG(B > 0 && T > 0 && E > 0 && E % 8 == 0, "phrase_conv_pool_fwd: bad sizes B=%d T=%d E=%d (E %% 8 == 0 required: 16-byte aligned operand rows)", B, T, E);
+  HCA_CHECK_ARG((int64_t)B * T * E < (1LL << 31), "phrase_conv_pool_fwd: B*T*E must stay below 2^31");
+  HCA_CHECK_ARG(tc_available(), "phrase_conv_pool_fwd: cuTensorMapEncodeTiled is not available from the driver");
   ConvWs c = carve(ws, ws_bytes, B, T, E);
   if (!c.ok) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small (%zu bytes)", ws_bytes);
   const int R = B * T;
   const float* bs[3] = {b1, b2, b3};
-  const bool tc = use_tc() && tc_available() && (E % 8 == 0);      // TMA needs 16-byte aligned plane windows
-  if (tc) {
-    // tensor cores, bf16x2 operand split (3 MMAs per product): the row-shifted operand Acat and the tap-major
-    // weights are written directly as bf16 planes (no fp32 im2col / repack round trip); the three convs read column windows
-    // of the Acat planes; bias + tanh fused in the epilogue; near-ties are repaired exactly below
-    const int P = 2;
-    const int64_t lda = 3 * (int64_t)E, a_stride = (int64_t)R * lda;
-    ConvSaved sv;
-    if (fsaved) HCA_CHECK_ARG(carve_saved(sv, fsaved, fsaved_bytes, B, T, E), "phrase_conv_pool_fwd: `fsaved` must be 256-byte aligned and hca_phrase_conv_pool_saved_bytes large");
-    __nv_bfloat16* ap = fsaved ? sv.ap : c.w.take<__nv_bfloat16>((size_t)P * a_stride);
-    if (!ap) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for operand planes");
-    HCA_LAUNCH_K((im2col3_planes_kernel<2>), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, ap, a_stride, B, T, E / 4);
-    HCA_LAUNCHED();
-    __nv_bfloat16* wps[3];
-    for (int k = 1; k <= 3; ++k) {
-      wps[k - 1] = fsaved ? sv.wp[k - 1] : c.w.take<__nv_bfloat16>((size_t)P * E * k * E);
-      if (!wps[k - 1]) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for weight planes");
-    }
-    HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid((int64_t)6 * E * E), 256, 0, s, w1, w2, w3, wps[0], wps[1], wps[2], E, c.tie_count);
-    HCA_LAUNCHED();
-    for (int k = 1; k <= 3; ++k) {
-      const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
-      __nv_bfloat16* wp = wps[k - 1];
-      TcOperand A, Bw;
-      A.planes = ap + (k == 1 ? E : 0); A.ld = lda; A.plane_stride = a_stride; A.rows = R; A.cols = k * E;
-      Bw.planes = wp; Bw.ld = ldw; Bw.plane_stride = w_stride; Bw.rows = E; Bw.cols = k * E;
-      TcEpilogue ep;
-      ep.D = c.cat + (k - 1) * E; ep.ldd = lda; ep.bias = bs[k - 1]; ep.act_tanh = 1;
-      HCA_TRY(launch_gemm_tc(A, Bw, P, R, E, k * E, ep, 1, s));
-    }
-    HCA_LAUNCH_K((pool3_fwd_kernel), ew_grid((int64_t)R * E), 256, 0, s, c.cat, lens, out, idx, B, T, E, c.tie_list, c.tie_count, c.tie_cap);
-    HCA_LAUNCHED();
-    HCA_LAUNCH_K((fixup_ties_kernel), 148 * 2, 256, 0, s, c.tie_list, c.tie_count, c.tie_cap, x, T, w1, w2, w3, b1, b2, b3, out, idx, E);
-    HCA_LAUNCHED();
-    return 0;
-  }
-  HCA_LAUNCH_K((im2col3_kernel), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, (float4*)c.acat, B, T, E / 4);
+  // tensor cores, bf16x2 operand split (3 MMAs per product): the row-shifted operand Acat and the tap-major weights are written
+  // directly as bf16 planes (no fp32 im2col / repack round trip); the three convs read column windows of the Acat planes; bias +
+  // tanh fused in the epilogue; near-ties are repaired exactly below
+  const int P = 2;
+  const int64_t lda = 3 * (int64_t)E, a_stride = (int64_t)R * lda;
+  ConvSaved sv;
+  if (fsaved) HCA_CHECK_ARG(carve_saved(sv, fsaved, fsaved_bytes, B, T, E), "phrase_conv_pool_fwd: `fsaved` must be 256-byte aligned and hca_phrase_conv_pool_saved_bytes large");
+  __nv_bfloat16* ap = fsaved ? sv.ap : c.w.take<__nv_bfloat16>((size_t)P * a_stride);
+  if (!ap) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for operand planes");
+  HCA_LAUNCH_K((im2col3_planes_kernel<2>), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, ap, a_stride, B, T, E / 4);
   HCA_LAUNCHED();
-  HCA_LAUNCH_K((repack_conv_w_kernel), ew_grid((int64_t)E * E * 2), 256, 0, s, w2, c.wr2, E, 2, false);
-  HCA_LAUNCHED();
-  HCA_LAUNCH_K((repack_conv_w_kernel), ew_grid((int64_t)E * E * 3), 256, 0, s, w3, c.wr3, E, 3, false);
-  HCA_LAUNCHED();
-  const float* wr[3] = {w1, c.wr2, c.wr3};
-  // exact-fp32 CUDA-core path: three GEMMs, bias + tanh fused, writing the column blocks of cat [R, 3E]
+  __nv_bfloat16* wps[3];
   for (int k = 1; k <= 3; ++k) {
-    GemmParams g;
-    const int a_off = (k == 1) ? E : 0;
-    g.A = {c.acat + a_off, 0, 3 * (int64_t)E, 1, 0};
-    g.B = {wr[k - 1], 0, (int64_t)k * E, 1, 0};
-    g.M = R; g.N = E; g.K = k * E;
-    g.D = c.cat + (k - 1) * E; g.d_sm = 3 * (int64_t)E; g.d_sn = 1;
-    g.bias = bs[k - 1];
-    g.act_tanh = 1;
-    HCA_TRY(launch_gemm_ffma(g, true, s));
+    wps[k - 1] = fsaved ? sv.wp[k - 1] : c.w.take<__nv_bfloat16>((size_t)P * E * k * E);
+    if (!wps[k - 1]) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for weight planes");
   }
-  HCA_LAUNCH_K((pool3_fwd_kernel), ew_grid((int64_t)R * E), 256, 0, s, c.cat, lens, out, idx, B, T, E, nullptr, nullptr, 0);
+  HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid((int64_t)6 * E * E), 256, 0, s, w1, w2, w3, wps[0], wps[1], wps[2], E, c.tie_count);
+  HCA_LAUNCHED();
+  HCA_LAUNCH_K((conv_norms_kernel), std::min(148 * 4, (R + 3 * E + 7) / 8), 256, 0, s, x, w1, w2, w3, c.xn2, c.wn, R, E);
+  HCA_LAUNCHED();
+  for (int k = 1; k <= 3; ++k) {
+    const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
+    __nv_bfloat16* wp = wps[k - 1];
+    TcOperand A, Bw;
+    A.planes = ap + (k == 1 ? E : 0); A.ld = lda; A.plane_stride = a_stride; A.rows = R; A.cols = k * E;
+    Bw.planes = wp; Bw.ld = ldw; Bw.plane_stride = w_stride; Bw.rows = E; Bw.cols = k * E;
+    TcEpilogue ep;
+    ep.D = c.cat + (k - 1) * E; ep.ldd = lda; ep.bias = bs[k - 1]; ep.act_tanh = 1;
+    HCA_TRY(launch_gemm_tc(A, Bw, P, R, E, k * E, ep, 1, s));
+  }
+  HCA_LAUNCH_K((pool3_fwd_kernel), ew_grid((int64_t)R * E), 256, 0, s, c.cat, lens, out, idx, B, T, E, c.xn2, c.wn, c.tie_list, c.tie_count,
+               c.tie_cap);
+  HCA_LAUNCHED();
+  HCA_LAUNCH_K((fixup_ties_kernel), 148 * 2, 256, 0, s, c.tie_list, c.tie_count, c.tie_cap, c.cat, lens, c.xn2, c.wn, x, B, T, w1, w2, w3, b1,
+               b2, b3, out, idx, E, fsaved ? sv.stats : (int*)nullptr);
   HCA_LAUNCHED();
   return 0;
 }
@@ -469,108 +502,68 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
   using namespace hca;
   cudaStream_t s = (cudaStream_t)stream;
   HCA_CHECK_ARG(x && w1 && w2 && w3 && out && idx && dout && dw1 && db1 && dw2 && db2 && dw3 && db3, "phrase_conv_pool_bwd: null pointer");
-  HCA_CHECK_ARG(B > 0 && T > 0 && E > 0 && E % 4 == 0, "phrase_conv_pool_bwd: bad sizes");
+  HCA_CHECK_ARG(B > 0 && T > 0 && E > 0 && E % 8 == 0, "phrase_conv_pool_bwd: bad sizes (E %% 8 == 0 required)");
+  HCA_CHECK_ARG(tc_available(), "phrase_conv_pool_bwd: cuTensorMapEncodeTiled is not available from the driver");
   ConvWs c = carve(ws, ws_bytes, B, T, E);
   if (!c.ok) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small (%zu bytes)", ws_bytes);
   const int R = B * T;
-  if (use_tc() && tc_available() && (E % 8 == 0)) {
-    // tensor-core path: every operand is produced once, directly as bf16 hi/lo planes, and the six products read windows of them
-    const int64_t ld3 = 3 * (int64_t)E, pstride = (int64_t)R * ld3;
-    // (the planes of Acat and of the weights are the forward's when it left them in `fsaved`: same conversion, same inputs)
-    ConvSaved sv;
-    if (fsaved) HCA_CHECK_ARG(carve_saved(sv, const_cast<void*>(fsaved), fsaved_bytes, B, T, E), "phrase_conv_pool_bwd: bad `fsaved` buffer");
-    __nv_bfloat16* ap = fsaved ? sv.ap : c.w.take<__nv_bfloat16>((size_t)2 * pstride);       // Acat planes
-    __nv_bfloat16* dp = c.w.take<__nv_bfloat16>((size_t)2 * pstride);       // dcat planes
-    if (!dp || !ap) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for operand planes");
-    if (!fsaved) {
-      HCA_LAUNCH_K((im2col3_planes_kernel<2>), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, ap, pstride, B, T, E / 4);
-      HCA_LAUNCHED();
-    }
-    float* dbs[3] = {db1, db2, db3};
-    float* dwr[3] = {dw1, c.dwr2, c.dwr3};
-    int sks[3];
-    {  // bias gradients and the split-K weight-gradient accumulators cleared by one launch
-      ZeroBatch zb(s);
-      for (int k = 1; k <= 3; ++k) {
-        HCA_TRY(zb.add(dbs[k - 1], (size_t)E * 4));
-        const int tiles = ((E + 127) / 128) * ((k * E + 127) / 128);
-        sks[k - 1] = tiles >= 96 ? 1 : std::max(1, std::min((148 + tiles - 1) / tiles, (R + 255) / 256));
-        if (sks[k - 1] > 1) HCA_TRY(zb.add(dwr[k - 1], (size_t)E * k * E * 4));
-      }
-      HCA_TRY(zb.flush());
-    }
-    HCA_LAUNCH_K((pool3_bwd_planes_kernel), dim3((E + 255) / 256, (R + POOL_BWD_ROWS - 1) / POOL_BWD_ROWS), 256, 0, s, out, idx, dout, lens, dp, pstride, db1,
-                                                                                                       db2, db3, B, T, E);
+  // every operand is produced once, directly as bf16 hi/lo planes, and the six products read windows of them
+  const int64_t ld3 = 3 * (int64_t)E, pstride = (int64_t)R * ld3;
+  // (the planes of Acat and of the weights are the forward's when it left them in `fsaved`: same conversion, same inputs)
+  ConvSaved sv;
+  if (fsaved) HCA_CHECK_ARG(carve_saved(sv, const_cast<void*>(fsaved), fsaved_bytes, B, T, E), "phrase_conv_pool_bwd: bad `fsaved` buffer");
+  __nv_bfloat16* ap = fsaved ? sv.ap : c.w.take<__nv_bfloat16>((size_t)2 * pstride);       // Acat planes
+  __nv_bfloat16* dp = c.w.take<__nv_bfloat16>((size_t)2 * pstride);       // dcat planes
+  if (!dp || !ap) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for operand planes");
+  if (!fsaved) {
+    HCA_LAUNCH_K((im2col3_planes_kernel<2>), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, ap, pstride, B, T, E / 4);
     HCA_LAUNCHED();
-    // weight gradients, tap-major: dWr_k[o][kk] = sum_r dcat[r][(k-1)E + o] * Acat[r][a_off + kk]   (K = R, split-K)
-    for (int k = 1; k <= 3; ++k) {
-      TcOperand A, Bm;
-      A.planes = dp + (k - 1) * E; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = E; A.mn_major = true;
-      Bm.planes = ap + (k == 1 ? E : 0); Bm.ld = ld3; Bm.plane_stride = pstride; Bm.rows = R; Bm.cols = k * E; Bm.mn_major = true;
-      const int sk = sks[k - 1];
-      TcEpilogue ep;
-      ep.D = dwr[k - 1]; ep.ldd = (int64_t)k * E;
-      HCA_TRY(launch_gemm_tc(A, Bm, 2, E, k * E, R, ep, sk, s));
-    }
-    HCA_LAUNCH_K((unpack_conv_w23_kernel), ew_grid((int64_t)E * E * 5), 256, 0, s, c.dwr2, dw2, c.dwr3, dw3, E);
-    HCA_LAUNCHED();
-    if (dx) {
-      // dA[r][a_off + kk] (+)= sum_o dcat[r][(k-1)E + o] * Wr_k[o][kk]: tri first (covers all 3E columns), bi and uni accumulate
-      const float* ws_[3] = {w1, w2, w3};
-      for (int k = 3; k >= 1; --k) {
-        const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
-        __nv_bfloat16* wp = fsaved ? sv.wp[k - 1] : c.w.take<__nv_bfloat16>((size_t)2 * w_stride);
-        if (!wp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for weight planes");
-        if (!fsaved) {
-          HCA_LAUNCH_K((conv_w_planes_kernel<2>), ew_grid((int64_t)E * E * k), 256, 0, s, ws_[k - 1], wp, w_stride, E, k);
-          HCA_LAUNCHED();
-        }
-        TcOperand A, Bm;
-        A.planes = dp + (k - 1) * E; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = E;
-        Bm.planes = wp; Bm.ld = ldw; Bm.plane_stride = w_stride; Bm.rows = E; Bm.cols = k * E; Bm.mn_major = true;
-        TcEpilogue ep;
-        ep.D = c.dA + (k == 1 ? E : 0); ep.ldd = ld3; ep.accumulate = (k != 3);
-        HCA_TRY(launch_gemm_tc(A, Bm, 2, R, k * E, E, ep, 1, s));
-      }
-      HCA_LAUNCH_K((col2im3_kernel), ew_grid((int64_t)R * E / 4), 256, 0, s, (const float4*)c.dA, (float4*)dx, B, T, E / 4);
-      HCA_LAUNCHED();
-    }
-    return 0;
   }
-  float* dcat = c.cat;
-  HCA_LAUNCH_K((im2col3_kernel), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, (float4*)c.acat, B, T, E / 4);
-  HCA_LAUNCHED();
-  HCA_LAUNCH_K((pool3_bwd_kernel), ew_grid((int64_t)R * E), 256, 0, s, out, idx, dout, lens, dcat, B, T, E);
-  HCA_LAUNCHED();
-  // bias gradients: column sums of the three blocks of dcat
   float* dbs[3] = {db1, db2, db3};
-  for (int k = 0; k < 3; ++k) {
-    HCA_TRY(zero_async(dbs[k], (size_t)E * 4, s));
-    HCA_TRY(launch_colsum(dcat + k * E, 3 * (int64_t)E, R, E, dbs[k], s));
-  }
-  // weight gradients in tap-major layout: dWr_k[o][kk] = sum_r dcat[r][(k-1)E + o] * Acat[r][a_off + kk]
   float* dwr[3] = {dw1, c.dwr2, c.dwr3};
-  for (int k = 1; k <= 3; ++k) {
-    const int a_off = (k == 1) ? E : 0;
-    HCA_TRY(dense_tn(dcat + (k - 1) * E, 3 * (int64_t)E, c.acat + a_off, 3 * (int64_t)E, dwr[k - 1], (int64_t)k * E,
-                     /*M=*/E, /*N=*/k * E, /*K=*/R, /*zero_first=*/true, c.w, s));
+  int sks[3];
+  {  // bias gradients and the split-K weight-gradient accumulators cleared by one launch
+    ZeroBatch zb(s);
+    for (int k = 1; k <= 3; ++k) {
+      HCA_TRY(zb.add(dbs[k - 1], (size_t)E * 4));
+      const int tiles = ((E + 127) / 128) * ((k * E + 127) / 128);
+      sks[k - 1] = tiles >= 96 ? 1 : std::max(1, std::min((148 + tiles - 1) / tiles, (R + 255) / 256));
+      if (sks[k - 1] > 1) HCA_TRY(zb.add(dwr[k - 1], (size_t)E * k * E * 4));
+    }
+    HCA_TRY(zb.flush());
   }
-  HCA_LAUNCH_K((repack_conv_w_kernel), ew_grid((int64_t)E * E * 2), 256, 0, s, c.dwr2, dw2, E, 2, true);
+  HCA_LAUNCH_K((pool3_bwd_planes_kernel), dim3((E + 255) / 256, (R + POOL_BWD_ROWS - 1) / POOL_BWD_ROWS), 256, 0, s, out, idx, dout, lens, dp, pstride, db1,
+                                                                                                     db2, db3, B, T, E);
   HCA_LAUNCHED();
-  HCA_LAUNCH_K((repack_conv_w_kernel), ew_grid((int64_t)E * E * 3), 256, 0, s, c.dwr3, dw3, E, 3, true);
+  // weight gradients, tap-major: dWr_k[o][kk] = sum_r dcat[r][(k-1)E + o] * Acat[r][a_off + kk]   (K = R, split-K)
+  for (int k = 1; k <= 3; ++k) {
+    TcOperand A, Bm;
+    A.planes = dp + (k - 1) * E; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = E; A.mn_major = true;
+    Bm.planes = ap + (k == 1 ? E : 0); Bm.ld = ld3; Bm.plane_stride = pstride; Bm.rows = R; Bm.cols = k * E; Bm.mn_major = true;
+    const int sk = sks[k - 1];
+    TcEpilogue ep;
+    ep.D = dwr[k - 1]; ep.ldd = (int64_t)k * E;
+    HCA_TRY(launch_gemm_tc(A, Bm, 2, E, k * E, R, ep, sk, s));
+  }
+  HCA_LAUNCH_K((unpack_conv_w23_kernel), ew_grid((int64_t)E * E * 5), 256, 0, s, c.dwr2, dw2, c.dwr3, dw3, E);
   HCA_LAUNCHED();
   if (dx) {
-    // dA[r][kk] = sum_o dcat[r][blk + o] * Wr_k[o][kk], accumulated over the three convs
-    HCA_LAUNCH_K((repack_conv_w_kernel), ew_grid((int64_t)E * E * 2), 256, 0, s, w2, c.wr2, E, 2, false);
-    HCA_LAUNCHED();
-    HCA_LAUNCH_K((repack_conv_w_kernel), ew_grid((int64_t)E * E * 3), 256, 0, s, w3, c.wr3, E, 3, false);
-    HCA_LAUNCHED();
-    const float* wr[3] = {w1, c.wr2, c.wr3};
-    for (int k = 3; k >= 1; --k) {   // tri first (covers all 3E columns, plain store), then bi, uni accumulate
-      DenseEpi e;
-      e.accumulate = (k != 3);
-      HCA_TRY(dense_nn(dcat + (k - 1) * E, 3 * (int64_t)E, wr[k - 1], (int64_t)k * E, c.dA + ((k == 1) ? E : 0), 3 * (int64_t)E,
-                       /*M=*/R, /*N=*/k * E, /*K=*/E, e, c.w, s));
+    // dA[r][a_off + kk] (+)= sum_o dcat[r][(k-1)E + o] * Wr_k[o][kk]: tri first (covers all 3E columns), bi and uni accumulate
+    const float* ws_[3] = {w1, w2, w3};
+    for (int k = 3; k >= 1; --k) {
+      const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
+      __nv_bfloat16* wp = fsaved ? sv.wp[k - 1] : c.w.take<__nv_bfloat16>((size_t)2 * w_stride);
+      if (!wp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for weight planes");
+      if (!fsaved) {
+        HCA_LAUNCH_K((conv_w_planes_kernel<2>), ew_grid((int64_t)E * E * k), 256, 0, s, ws_[k - 1], wp, w_stride, E, k);
+        HCA_LAUNCHED();
+      }
+      TcOperand A, Bm;
+      A.planes = dp + (k - 1) * E; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = E;
+      Bm.planes = wp; Bm.ld = ldw; Bm.plane_stride = w_stride; Bm.rows = E; Bm.cols = k * E; Bm.mn_major = true;
+      TcEpilogue ep;
+      ep.D = c.dA + (k == 1 ? E : 0); ep.ldd = ld3; ep.accumulate = (k != 3);
+      HCA_TRY(launch_gemm_tc(A, Bm, 2, R, k * E, E, ep, 1, s));
     }
     HCA_LAUNCH_K((col2im3_kernel), ew_grid((int64_t)R * E / 4), 256, 0, s, (const float4*)c.dA, (float4*)dx, B, T, E / 4);
     HCA_LAUNCHED();

@@ -20,21 +20,24 @@ int set_err(int code, const char* fmt, ...) {
   return code;
 }
 
-static std::atomic<int> g_gemm_mode{-1};  // -1 unset, 0 ffma, 1 tc
-
-bool use_tc() {
-  int m = g_gemm_mode.load(std::memory_order_relaxed);
-  if (m < 0) {
-    const char* e = getenv("HCA_GEMM");
-    m = (e && strcmp(e, "ffma") == 0) ? 0 : 1;
-    g_gemm_mode.store(m);
-  }
-  return m == 1;
-}
-
+// HCA_PDL=0 turns programmatic dependent launch off (plain stream-ordered launches).  The environment is read once; a profiler leg
+// that wants exclusive kernel durations switches at run time through hca_set_option("pdl", "0" / "1").
+static std::atomic<int> g_pdl{-1};
 bool pdl_enabled() {
-  const char* e = getenv("HCA_PDL");          // read per launch: a profiler leg may switch it off to get exclusive kernel durations
-  return !(e && atoi(e) == 0);
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("HCA_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+    g_pdl.store(v);
+  }
+  return v == 1;
+}
+void set_pool_tie_cap(int n);      // phrase_conv_pool.cu
+
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
 }
 
 namespace {
@@ -47,9 +50,7 @@ SideRes g_side[64];
 }  // namespace
 
 SideStream::SideStream(cudaStream_t main) : main_(main) {
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("HCA_SIDE_STREAM"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
-  if (!enabled) return;
+  if (HCA_ENV_INT("HCA_SIDE_STREAM", 1) == 0) return;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return; }
   SideRes& r = g_side[dev];
@@ -90,15 +91,15 @@ int64_t hca_launch_count(void) { return hca::g_launches.load(); }
 
 int hca_set_option(const char* name, const char* value) {
   if (!name || !value) return hca::set_err(HCA_ERR_ARG, "hca_set_option: null argument");
-  if (strcmp(name, "gemm") == 0) {
-    if (strcmp(value, "tc") == 0) { hca::g_gemm_mode.store(1); return 0; }
-    if (strcmp(value, "ffma") == 0) { hca::g_gemm_mode.store(0); return 0; }
-  }
+  if (strcmp(name, "pdl") == 0) { hca::g_pdl.store(atoi(value) != 0 ? 1 : 0); return 0; }
+  if (strcmp(name, "pool_tie_cap") == 0) { hca::set_pool_tie_cap(atoi(value)); return 0; }
+  if (strcmp(name, "gemm") == 0 && strcmp(value, "tc") == 0) return 0;      // the only contraction backend there is
   return hca::set_err(HCA_ERR_ARG, "hca_set_option: unknown option %s=%s", name, value);
 }
 
 const char* hca_get_option(const char* name) {
-  if (name && strcmp(name, "gemm") == 0) return hca::use_tc() ? "tc" : "ffma";
+  if (name && strcmp(name, "gemm") == 0) return "tc";
+  if (name && strcmp(name, "pdl") == 0) return hca::pdl_enabled() ? "1" : "0";
   return "";
 }
 

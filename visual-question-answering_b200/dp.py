@@ -1,6 +1,5 @@
-"""Batch-sharded data parallelism for the co-attention path: one process per GPU, NCCL all-reduce of a
-flat gradient buffer over NVLink 5 / NVSwitch, issued bucket by bucket in reverse-backward order so the
-transfer of the early buckets overlaps the remaining backward.
+"""Batch-sharded data parallelism for the co-attention path: one process per GPU, flat gradient / parameter buffers, and
+the gradient all-reduce over NVLink 5 / NVSwitch.
 
 The reference has no multi-GPU support at all (a commented-out nn.DataParallel TODO, main.py:102-106);
 the path shards over the batch because no op in model.py:246-434 mixes samples -- the only cross-sample
@@ -12,15 +11,29 @@ Design:
     there is no gather copy before the collective and no scatter after it;
   * ``co_attention.W_b`` never receives a gradient (reference model.py:347 vs :377) and frozen VGG weights
     have ``requires_grad=False``: both are left out of the buffer (``skip`` / requires_grad);
-  * post-accumulate-grad hooks count down each bucket and launch its all-reduce (SUM) as soon as it is
-    complete; the mean over ranks is obtained by scaling the loss by 1/world_size before backward
-    (``loss_scale``), so no extra pass over the buffer is needed;
-  * ``finish()`` waits for the outstanding collectives before the optimizer step;
+  * the mean over ranks is obtained by scaling the loss by 1/world_size before backward (``loss_scale``), so no
+    extra pass over the buffer is needed;
   * the reducer is a "gradient sink" of ops.py: the backward kernels WRITE each weight gradient straight into its slot of
     the flat buffer (no per-parameter autograd accumulation kernel, no clearing pass over the buffer).  A slot takes one
     direct write per step; a parameter used twice gets its further contributions through autograd's in-place accumulation
     into the same view.  Slots that were not written directly in the previous step are cleared by ``zero_grad()``.
-Works with any backend torch.distributed offers (NCCL on the GPUs; gloo in the CPU unit tests).
+
+Two transports for the collective:
+  * ``fused`` (CUDA, world > 1, the default when symmetric memory can be set up): gradients AND parameters live in one
+    symmetric-memory block per GPU (torch.distributed._symmetric_memory does the allocation and the handle exchange; it is
+    plumbing only).  ``optim.FlatAdam.step()`` then runs ONE hand-written kernel (csrc/dp_fused.cu) that reduces the
+    gradients across ranks in the NVSwitch (``multimem.ld_reduce``), applies Adam to this rank's slice and multicasts
+    the new parameters to every rank (``multimem.st``) -- all-reduce, optimizer and broadcast in one pass, capturable in
+    a CUDA graph, no NCCL call in the step.  Ranges of the buffer that are complete early (classifier + co-attention
+    gradients) can be processed on a side stream while the rest of backward still runs (``reduce_adam_range``).
+  * NCCL / gloo (``fused=False``; gloo in the CPU unit tests): bucketed ``dist.all_reduce`` in ``finish()``; with
+    ``overlap=True`` each bucket is launched from the gradient hooks as soon as it is complete.  Overlap is OFF by default:
+    the persistent LSTM kernel wants its CTAs co-resident (csrc/lstm.cu checks and refuses otherwise), and a collective
+    kernel holding SMs at that moment only delays both.
+
+The model must be on its device BEFORE the reducer is built: ``flat_params=True`` re-points ``param.data`` into the flat
+buffer, and anything that re-allocates parameter storage afterwards (``model.to()``, ``nn.LSTM.flatten_parameters()``)
+would silently detach them -- ``finish()`` / ``FlatAdam.step()`` check the aliasing and raise.
 """
 from __future__ import annotations
 
@@ -44,12 +57,16 @@ def shard_batch(n_items: int, rank: int, world: int) -> slice:
 
 class FlatGradAllReduce:
     def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], process_group=None,
-                 skip: Sequence[str] = ("co_attention.W_b.",), bucket_bytes: int = 16 << 20, overlap: bool = True,
-                 flat_params: bool = False, align: int = 64, direct_write: bool = True):
+                 skip: Sequence[str] = ("co_attention.W_b.",), bucket_bytes: int = 16 << 20, overlap: bool = False,
+                 flat_params: bool = False, align: int = 64, direct_write: bool = True, fused: Optional[bool] = None):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
         self.loss_scale = 1.0 / self.world
         self.overlap = overlap
+        self.fused = False
+        self._symm = None
+        self._optimizer = None              # a FlatAdam that has taken over the collective (fused mode)
         items = [(n, p) for n, p in named_params if p.requires_grad and not any(n.startswith(s) for s in skip)]
 
         def order(item):
@@ -68,10 +85,25 @@ class FlatGradAllReduce:
         # all want 16-byte aligned bases; the padding elements stay zero
         pad = lambda n: (n + align - 1) // align * align
         total = sum(pad(p.numel()) for p in self.params)
-        self.flat = torch.zeros(total, dtype=dt, device=dev)
-        # optional: the parameters themselves become views of one flat buffer too (same offsets), which is what lets the
-        # optimizer step be ONE fused kernel over (flat_p, flat, m, v) -- see optim.FlatAdam
-        self.flat_p = torch.zeros(total, dtype=dt, device=dev) if flat_params else None
+        want_fused = fused if fused is not None else (self.world > 1 and dev.type == "cuda" and flat_params and dt == torch.float32)
+        if want_fused:
+            if not (self.world > 1 and dev.type == "cuda" and flat_params and dt == torch.float32):
+                raise ValueError("fused=True needs world > 1, CUDA fp32 parameters and flat_params=True")
+            try:
+                self._symm = _SymmetricBlock(total, dev, process_group, self.rank, self.world)
+            except Exception as e:                      # no symmetric memory on this system: NCCL transport
+                if fused:
+                    raise
+                import warnings
+                warnings.warn(f"FlatGradAllReduce: symmetric memory unavailable ({type(e).__name__}: {e}); using dist.all_reduce")
+        if self._symm is not None:
+            self.fused = True
+            self.flat, self.flat_p = self._symm.g, self._symm.p
+        else:
+            self.flat = torch.zeros(total, dtype=dt, device=dev)
+            # optional: the parameters themselves become views of one flat buffer too (same offsets), which is what lets the
+            # optimizer step be ONE fused kernel over (flat_p, flat, m, v) -- see optim.FlatAdam
+            self.flat_p = torch.zeros(total, dtype=dt, device=dev) if flat_params else None
         # carve views and buckets
         self.buckets: List[Tuple[int, int]] = []            # [start, end) element ranges of the flat buffer
         self._bucket_of: List[int] = []
@@ -98,6 +130,7 @@ class FlatGradAllReduce:
         self._work = []
         # gradient sink state (see ops._gbuf / ops._gret)
         self._views = [p.grad for p in self.params]
+        self._offsets = [int((g.data_ptr() - self.flat.data_ptr()) // self.flat.element_size()) for g in self._views]
         self._by_param = {p.data_ptr(): i for i, p in enumerate(self.params)}
         self._by_grad = {g.data_ptr(): i for i, g in enumerate(self._views)}
         self._taken: set = set()            # slots handed to a backward kernel this step
@@ -186,7 +219,11 @@ class FlatGradAllReduce:
                 self._views[i].zero_()
                 self._clean.add(i)
         self._direct_prev = set(self._taken)
-        if self.world > 1:
+        self.check_aliasing()
+        if self.fused:
+            if self._optimizer is None:                 # no fused optimizer attached: a plain all-reduce through the same kernel
+                self.reduce_adam_range(0, self.flat.numel(), mode=2)
+        elif self.world > 1:
             if not self.overlap:
                 for b in range(len(self.buckets)):
                     self._launch(b)
@@ -199,6 +236,33 @@ class FlatGradAllReduce:
         self._work = []
         self._left = list(self._need)
 
+    def check_aliasing(self):
+        """Every parameter (with flat_params) and every ``.grad`` must still be the view of the flat buffers carved at construction:
+        ``model.to()`` / ``_apply`` / ``nn.LSTM.flatten_parameters()`` re-allocate parameter storage, after which the optimizer would
+        update a buffer no module reads.  Host-side pointer compares only (no device work, safe during CUDA-graph capture)."""
+        esz = self.flat.element_size()
+        for i, p in enumerate(self.params):
+            if p.grad is not None and p.grad.data_ptr() != self.flat.data_ptr() + self._offsets[i] * esz:
+                raise RuntimeError(f"FlatGradAllReduce: {self.names[i]}.grad no longer points into the flat gradient buffer")
+            if self.flat_p is not None and p.data_ptr() != self.flat_p.data_ptr() + self._offsets[i] * esz:
+                raise RuntimeError(f"FlatGradAllReduce: parameter {self.names[i]} no longer aliases the flat parameter buffer "
+                                   "(was the model moved / re-flattened after the reducer was built? build the reducer last)")
+
+    def reduce_adam_range(self, begin: int, end: int, mode: int, opt=None, channel: int = 0, max_ctas: int = 0):
+        """Fused transport: one launch of csrc/dp_fused.cu over elements [begin, end) of the flat buffers on the current stream.
+        mode 1 = all-reduce + Adam + parameter broadcast (``opt`` = the FlatAdam holding m / v / coef), 2 = all-reduce only."""
+        if not self.fused:
+            raise RuntimeError("reduce_adam_range needs the fused (symmetric-memory) transport")
+        from . import ops
+        ops.dp_reduce_adam(self._symm, begin, end, mode, opt, channel, max_ctas)
+
+    def offset_of(self, prefix: str) -> int:
+        """First element of the flat buffers that belongs to a parameter whose name starts with ``prefix`` (layout = backward order)."""
+        for n, o in zip(self.names, self._offsets):
+            if n.startswith(prefix):
+                return o
+        raise KeyError(prefix)
+
     def close(self):
         """Detach from autograd and from the backward kernels: removes the hooks and the gradient-sink registration (the flat buffers
         and the ``.grad`` / ``.data`` views stay valid)."""
@@ -210,3 +274,35 @@ class FlatGradAllReduce:
 
     def grad_bytes(self) -> int:
         return self.flat.numel() * self.flat.element_size()
+
+
+class _SymmetricBlock:
+    """One symmetric-memory allocation per rank holding [flag words | flat gradients | flat parameters], rendezvoused over the
+    process group so that every rank has every peer's block mapped (and, on NVSwitch systems, a multicast address for it)."""
+
+    def __init__(self, total: int, device, group, rank: int, world: int):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        if world > 8:
+            raise ValueError("the fused transport covers one NVSwitch domain (<= 8 GPUs)")
+        flag_words = int(_lib.lib().hca_dp_flags_bytes()) // 4
+        pad = lambda n: (n + 63) // 64 * 64
+        self.flags_off = 0
+        self.g_off = pad(flag_words) * 4
+        self.p_off = self.g_off + pad(total) * 4
+        nfloat = pad(flag_words) + 2 * pad(total)
+        self.block = symm_mem.empty(nfloat, dtype=torch.float32, device=device)
+        self.block.zero_()
+        torch.cuda.synchronize(device)
+        pg = group if group is not None else dist.group.WORLD
+        self.handle = symm_mem.rendezvous(self.block, pg)
+        ptrs = list(self.handle.buffer_ptrs)
+        if len(ptrs) != world or int(ptrs[rank]) != self.block.data_ptr():
+            raise RuntimeError("symmetric memory rendezvous returned unexpected buffer pointers")
+        self.peers = (C.c_uint64 * world)(*[int(x) for x in ptrs])
+        self.mc = int(self.handle.multicast_ptr) if getattr(self.handle, "multicast_ptr", 0) else 0
+        self.rank, self.world, self.total = rank, world, total
+        self.g = self.block[self.g_off // 4: self.g_off // 4 + total]
+        self.p = self.block[self.p_off // 4: self.p_off // 4 + total]
+        dist.barrier(group=pg)              # every rank's flag words are zero before anybody signals

@@ -7,8 +7,9 @@ reference's main.py (main.py:15,164) picks these up unchanged and checkpoints in
 behind the ``hiecoattn::*`` custom ops (ops.py); parameters are held by stock ``nn.Linear`` /
 ``nn.Conv1d`` / ``nn.Embedding`` containers only so that names, shapes and default initialisation match.
 
-Out of the hot path and therefore stock PyTorch here: the VGG11-bn trunk (torchvision), the sentence
-``nn.LSTM`` (cuDNN) and the GRU baseline network.
+Out of the hot path and therefore stock PyTorch here: the VGG11-bn trunk (torchvision) and the GRU baseline
+network.  The sentence ``nn.LSTM`` container only holds the weights: the recurrence itself runs in the
+persistent kernel of csrc/lstm.cu (cuDNN is the fallback for hidden sizes that kernel does not cover).
 """
 from __future__ import annotations
 
@@ -103,7 +104,10 @@ class QuestionCoAttentionEncoder(nn.Module):
             lens_cpu, lens_dev = x_lens.cpu, x_lens.dev
         else:
             lens_cpu = x_lens.cpu() if x_lens.is_cuda else x_lens          # the one D2H sync the reference also pays
-            lens_dev = x_lens if x_lens.is_cuda else x_lens.to(x.device)
+            lens_dev = x_lens
+        # the kernels read the lengths as int64 on the tokens' device, whatever the caller's loader produced (int32, CPU, ...)
+        lens_cpu = lens_cpu.to(torch.int64)
+        lens_dev = lens_dev.to(x.device, torch.int64)
         x_word_emb = ops.embedding(x, self.word_embedding.weight)                       # model.py:282
         # phrase level with the pad rows already zeroed (what pack -> pad does at model.py:287,292)
         x_phrase_emb = self.phrase_conv_pool(x_word_emb, lens_dev)                      # model.py:284

@@ -39,6 +39,16 @@ def _c(t: Tensor) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _cuda_i64(name: str, t: Optional[Tensor], like: Tensor) -> None:
+    """Index tensors (tokens, lens, labels) reach raw-pointer kernels that read them as int64 on the device of ``like``."""
+    if t is None:
+        return
+    if not t.is_cuda or t.device != like.device:
+        raise RuntimeError(f"hiecoattn_b200: `{name}` must be a CUDA tensor on {like.device} (got {t.device}); there is no CPU fallback")
+    if t.dtype != torch.int64:
+        raise RuntimeError(f"hiecoattn_b200: `{name}` must be int64 (got {t.dtype})")
+
+
 def _ws(nbytes: int, device) -> Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -82,10 +92,11 @@ def _gret(g: Tensor):
 # ------------------------------------------------------------------------------------------------ embedding
 @torch.library.custom_op(f"{NS}::embedding", mutates_args=(), device_types="cuda")
 def embedding(tokens: Tensor, table: Tensor) -> Tensor:
-    """nn.Embedding(padding_idx=0) forward (reference model.py:263,282)."""
+    """nn.Embedding(padding_idx=0) forward (reference model.py:263,282).  Token ids must lie in [0, vocab): the reference raises
+    on an out-of-range id; this kernel cannot raise without a host synchronisation and clamps the id into the table instead."""
     _cuda_f32(table)
+    _cuda_i64("tokens", tokens, table)
     tokens, table = _c(tokens), _c(table)
-    assert tokens.dtype == torch.int64
     out = torch.empty(*tokens.shape, table.shape[1], dtype=torch.float32, device=table.device)
     with torch.cuda.device(table.device):
         _lib.check(_lib.lib().hca_embedding_fwd(_ptr(tokens), _ptr(table), _ptr(out), tokens.numel(), table.shape[1],
@@ -102,6 +113,7 @@ def _(tokens, table):
 def embedding_bwd(tokens: Tensor, dout: Tensor, dtable: Tensor) -> None:
     """dtable [vocab, E] (overwritten) = scatter-add of dout rows by token."""
     _cuda_f32(dout, dtable)
+    _cuda_i64("tokens", tokens, dout)
     tokens, dout = _c(tokens), _c(dout)
     vocab, E = dtable.shape
     assert dtable.is_contiguous()
@@ -139,6 +151,7 @@ def phrase_conv_pool(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, 
     ``lens`` (int64, CUDA, optional) additionally zeroes rows t >= len (model.py:287-292).  ``saved`` is an opaque buffer
     (operand planes of the shifted input and of the weights) that the backward op reuses."""
     _cuda_f32(x, w1, b1, w2, b2, w3, b3)
+    _cuda_i64("lens", lens, x)
     x, w1, b1, w2, b2, w3, b3 = map(_c, (x, w1, b1, w2, b2, w3, b3))
     B, T, E = x.shape
     out = torch.empty_like(x)
@@ -149,20 +162,24 @@ def phrase_conv_pool(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, 
         ws = _ws(nb, x.device)
         # the operand planes are produced by the forward anyway: leaving them in a returned buffer instead of the workspace costs
         # nothing and saves the backward three weight conversions and the im2col pass
-        keep = E % 8 == 0
-        saved = _ws(_pcp_saved_bytes(B, T, E) if keep else 0, x.device)
+        saved = _ws(_pcp_saved_bytes(B, T, E), x.device)
         _lib.check(L.hca_phrase_conv_pool_fwd(_ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(w3), _ptr(b3),
                                               _ptr(None if lens is None else _c(lens)), _ptr(out), _ptr(idx),
-                                              _ptr(saved) if keep else None, saved.numel() if keep else 0, B, T, E,
-                                              _ptr(ws), ws.numel(), _stream()), "phrase_conv_pool_fwd")
+                                              _ptr(saved), saved.numel(), B, T, E, _ptr(ws), ws.numel(), _stream()), "phrase_conv_pool_fwd")
     return out, idx, saved
+
+
+def phrase_conv_pool_tie_stats(saved: Tensor) -> Tuple[int, int]:
+    """(near-ties found, capacity of the tie list) of the forward call that produced ``saved`` -- the bookkeeping of the exact
+    argmax repair (csrc/phrase_conv_pool.cu).  found > capacity means the repair ran in its exhaustive mode.  Synchronises."""
+    st = saved[-256:-248].view(torch.int32).cpu()
+    return int(st[0]), int(st[1])
 
 
 @phrase_conv_pool.register_fake
 def _(x, w1, b1, w2, b2, w3, b3, lens):
     B, T, E = x.shape
-    return (torch.empty_like(x), x.new_empty(x.shape, dtype=torch.uint8),
-            x.new_empty(_pcp_saved_bytes(B, T, E) if E % 8 == 0 else 256, dtype=torch.uint8))
+    return (torch.empty_like(x), x.new_empty(x.shape, dtype=torch.uint8), x.new_empty(_pcp_saved_bytes(B, T, E), dtype=torch.uint8))
 
 
 @torch.library.custom_op(f"{NS}::phrase_conv_pool_bwd", mutates_args=("dw1", "db1", "dw2", "db2", "dw3", "db3"), device_types="cuda")
@@ -171,6 +188,7 @@ def phrase_conv_pool_bwd(x: Tensor, w1: Tensor, w2: Tensor, w3: Tensor, out: Ten
                          dw3: Tensor, db3: Tensor) -> Tensor:
     """Returns dx; the weight / bias gradients are WRITTEN into dw* / db* (contiguous, 16-byte aligned)."""
     _cuda_f32(x, w1, w2, w3, out, dout, dw1, db1, dw2, db2, dw3, db3)
+    _cuda_i64("lens", lens, x)
     x, w1, w2, w3, out, idx, dout = map(_c, (x, w1, w2, w3, out, idx, dout))
     assert all(t.is_contiguous() for t in (dw1, db1, dw2, db2, dw3, db3))
     B, T, E = x.shape
@@ -224,8 +242,8 @@ def lstm(x: Tensor, lens: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh
     x [B,T,E], lens int64 [B] on the GPU.  Returns (out [B,T,H] with rows t >= len zeroed, saved) where ``saved`` is
     the opaque buffer the backward kernels read (layout private to the library)."""
     _cuda_f32(x, w_ih, w_hh, b_ih, b_hh)
+    _cuda_i64("lens", lens, x)
     x, lens, w_ih, w_hh, b_ih, b_hh = map(_c, (x, lens, w_ih, w_hh, b_ih, b_hh))
-    assert lens.dtype == torch.int64 and lens.is_cuda
     B, T, E = x.shape
     H = w_hh.shape[1]
     out = torch.empty(B, T, H, dtype=torch.float32, device=x.device)
@@ -253,6 +271,7 @@ def lstm_bwd(lens: Tensor, w_ih: Tensor, w_hh: Tensor, saved: Tensor, dout: Tens
              dw_hh: Tensor, db_ih: Tensor, db_hh: Tensor) -> Tensor:
     """Returns dx; the weight / bias gradients are WRITTEN into dw_* / db_*."""
     _cuda_f32(w_ih, w_hh, dout, dw_ih, dw_hh, db_ih, db_hh)
+    _cuda_i64("lens", lens, dout)
     lens, w_ih, w_hh, dout = map(_c, (lens, w_ih, w_hh, dout))
     assert all(t.is_contiguous() for t in (dw_ih, dw_hh, db_ih, db_hh))
     B, T, H = dout.shape
@@ -479,10 +498,14 @@ mlp.register_autograd(_mlp_backward, setup_context=_mlp_setup)
 # ------------------------------------------------------------------------------------------------------- loss
 @torch.library.custom_op(f"{NS}::cross_entropy_fwd", mutates_args=(), device_types="cuda")
 def cross_entropy_fwd(logits: Tensor, labels: Tensor, scale: float) -> Tuple[Tensor, Tensor]:
-    """(scale * mean CE, d/dlogits of it) in one launch (reference main.py:179,214: nn.CrossEntropyLoss, mean reduction)."""
+    """(scale * mean CE, d/dlogits of it) in one launch (reference main.py:179,214: nn.CrossEntropyLoss() with its defaults --
+    mean reduction, no class weights).  Labels must be class ids in [0, K): ``ignore_index`` is not implemented (the reference's
+    loop never produces -100; main.py:208 feeds the answer ids straight from the dataset)."""
     _cuda_f32(logits)
+    _cuda_i64("labels", labels, logits)
     logits, labels = _c(logits), _c(labels)
-    assert logits.dim() == 2 and labels.dtype == torch.int64 and labels.shape == (logits.shape[0],)
+    if logits.dim() != 2 or labels.shape != (logits.shape[0],):
+        raise RuntimeError(f"cross_entropy: logits [B,K] and labels [B] expected, got {tuple(logits.shape)} and {tuple(labels.shape)}")
     B, K = logits.shape
     loss = torch.empty((), dtype=torch.float32, device=logits.device)
     dlogits = torch.empty_like(logits)
@@ -534,6 +557,28 @@ def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: Tensor, coef: Te
                                             _stream()), "adam_step")
 
 
+def adam_prep(step: Tensor, coef: Tensor, lr: float, beta1: float, beta2: float) -> None:
+    """Advance the device step counter and derive the bias-correction factors (first half of ``adam_step``)."""
+    with torch.cuda.device(coef.device):
+        _lib.check(_lib.lib().hca_adam_prep(_ptr(step), _ptr(coef), lr, beta1, beta2, _stream()), "adam_prep")
+
+
+def dp_reduce_adam(symm, begin: int, end: int, mode: int, opt=None, channel: int = 0, max_ctas: int = 0) -> None:
+    """One launch of the fused data-parallel kernel (csrc/dp_fused.cu) on the current stream over elements [begin, end) of the
+    symmetric flat buffers ``symm`` (dp._SymmetricBlock).  mode bit 0: Adam (``opt`` = optim.FlatAdam: moments, coefficients),
+    bit 1: write the summed gradient back.  Collective over the ranks of the block; not differentiable; mutates g / p / m / v."""
+    dev = symm.block.device
+    m = v = coef = None
+    b1 = b2 = eps = 0.0
+    if mode & 1:
+        m, v, coef = opt.exp_avg, opt.exp_avg_sq, opt._coef
+        b1, b2, eps = opt.betas[0], opt.betas[1], opt.eps
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().hca_dp_reduce_adam(symm.peers, symm.mc, symm.flags_off, symm.g_off, symm.p_off, int(begin), int(end),
+                                                 symm.rank, symm.world, int(channel), int(max_ctas), _ptr(m), _ptr(v), _ptr(coef),
+                                                 b1, b2, eps, int(mode), _stream()), "dp_reduce_adam")
+
+
 # ---------------------------------------------------------------------------------- raw GEMM (tests / profiling)
 _LAYOUTS = {"nt": 0, "nn": 1, "tn": 2}
 
@@ -542,7 +587,7 @@ def gemm(A: Tensor, B: Tensor, bias: Optional[Tensor] = None, layout: str = "nt"
     """One dense contraction through the library's kernels (not differentiable; tests, benchmarks, ncu).
 
     layout "nt": A[M,K] . B[N,K]^T (+bias)   "nn": A[M,K] . B[K,N] (+bias)   "tn": A[K,M]^T . B[K,N]
-    path 0 = fp32 CUDA cores, 1 = tcgen05 bf16x2 split (3 MMAs), 2 = tcgen05 bf16x3 split (6 MMAs)."""
+    path 1 = tcgen05 bf16x2 split (3 MMAs), 2 = tcgen05 bf16x3 split (6 MMAs)."""
     _cuda_f32(A, B, bias)
     A, B = _c(A), _c(B)
     if layout == "nt":

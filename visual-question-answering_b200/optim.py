@@ -7,6 +7,10 @@ fp32 arrays in a single pass (csrc/adam.cu) instead of torch's eight multi-tenso
 device (CUDA-graph capturable) and touches exactly the tensors the all-reduce covers: ``co_attention.W_b`` (never used by
 the reference's forward, model.py:347 vs :377, so its gradient is None and torch's Adam skips it too) and frozen VGG
 weights are left alone.
+
+With the reducer's fused transport (world > 1, symmetric memory) the step is ALSO the collective: one kernel reduces the
+gradients across ranks in the NVSwitch, updates this rank's slice and multicasts the new parameters (csrc/dp_fused.cu);
+the moment buffers then hold meaningful values only for this rank's slice (sharded optimizer state).
 """
 from __future__ import annotations
 
@@ -27,12 +31,38 @@ class FlatAdam:
         self.exp_avg_sq = torch.zeros_like(reducer.flat)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=reducer.flat.device)
         self._coef = torch.zeros(2, dtype=torch.float32, device=reducer.flat.device)
+        if reducer.fused:
+            reducer._optimizer = self       # finish() leaves the collective to step()
 
     @torch.no_grad()
     def step(self):
         r = self.reducer
+        r.check_aliasing()
+        if r.fused:
+            done = self._early_end          # elements [0, done) were already reduced + updated by step_early() this step
+            self._early_end = 0
+            if done == 0:
+                ops.adam_prep(self.step_count, self._coef, self.lr, self.betas[0], self.betas[1])
+            if done < r.flat.numel():
+                r.reduce_adam_range(done, r.flat.numel(), 1, self)
+            return
         ops.adam_step(r.flat_p, r.flat, self.exp_avg, self.exp_avg_sq, self.step_count, self._coef, self.lr, self.betas[0],
                       self.betas[1], self.eps)
+
+    _early_end = 0
+
+    @torch.no_grad()
+    def step_early(self, end: int, stream, max_ctas: int = 16):
+        """Fused transport only: reduce + update elements [0, end) of the flat buffers NOW on ``stream`` (a side stream that has
+        waited for the kernels producing those gradients), with a grid capped at ``max_ctas`` so that it shares the GPU with the
+        rest of backward.  ``step()`` then covers [end, n).  The step counter advances here."""
+        r = self.reducer
+        if not r.fused or end <= 0:
+            return
+        with torch.cuda.stream(stream):
+            ops.adam_prep(self.step_count, self._coef, self.lr, self.betas[0], self.betas[1])
+            r.reduce_adam_range(0, end, 1, self, channel=1, max_ctas=max_ctas)
+        self._early_end = end
 
     def zero_grad(self, set_to_none: bool = False):
         self.reducer.zero_grad()
