@@ -10,11 +10,18 @@ UNKNOWN class, reference main.py:155), synthetic 196x512 image-feature grids and
 (the VQA/COCO data is not available offline), random-init weights.  Weak scaling: every rank processes
 its own 160-sample shard and the gradients are all-reduced over NCCL (configs[3] is the same at 8 GPUs).
 
+`--scaling strong` is BASELINE.json configs[3] as written: a FIXED global batch of 1280 sharded over the ranks
+(1x1280, 2x640, 4x320, 8x160).
+
 Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same metric
 through the public module API with host buffers (pinned H2D of every step's inputs and a D2H read of the
-loss inside the timed region); `roofline` = the dominant kernel (the W_v.V projection GEMM) timed alone
-with CUDA events; `cpu_baseline` = the reference's algorithm on this box's host cores (oracle/torch_port.py,
-a bounded sample).  `--impl reference` times that CPU port as the whole job instead.
+loss inside the timed region); `roofline` = the kernel that takes the largest share of the step (by the CUPTI
+breakdown of this very run), timed alone with CUDA events, and `roofline_legs` = the same for the other heavy
+kernels (LSTM recurrences, the largest weight-gradient product, the W_v.V projection); `cpu_baseline` = the
+reference's algorithm on this box's host cores (oracle/torch_port.py, a bounded sample); `gpu_eager_baseline`
+= that same reference algorithm run eagerly on THIS GPU by stock PyTorch (fp32, TF32, autocast bf16; also
+CUDA-graph captured where capture succeeds) -- the kernel-for-kernel comparator.  `--impl reference` times
+the CPU port as the whole job instead.
 """
 from __future__ import annotations
 
@@ -125,15 +132,17 @@ def run_reference_arm(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    B = 32                                        # bounded sample of the workload: 32 of the 160 samples per step
-    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm is meant to use every host core it can
-    val, ms, threads = cpu_reference(B, args.steps, max(args.warmup, 1), threads=os.cpu_count())
-    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    B = args.batch                                # the SAME per-step batch as the GPU arm (160): one step = one sample of the workload
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm is meant to use every host core it can.  A CPU step of 160
+    # samples takes ~0.5-1 s, so the step count is bounded to keep the run within minutes (the line reports what was run)
+    steps = min(args.steps, 40)
+    val, ms, threads = cpu_reference(B, steps, min(max(args.warmup, 1), 3), threads=os.cpu_count())
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(max(args.warmup, 1), 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": workload_config(args.batch, 1, extra={"sample_batch": B}),
+            "config": workload_config(args.batch, 1, extra={"sample_batch": B, "steps_requested": args.steps}),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} steps of batch {B} (of the 160-sample batch), torch CPU fp32, oracle/torch_port.py"},
+                             "sample": f"{steps} steps of batch {B} (the GPU arm's batch), fwd+CE+bwd+Adam, torch CPU fp32, oracle/torch_port.py"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
@@ -153,20 +162,26 @@ def workload_config(batch, world, extra=None):
 class Stepper:
     """One training step of the public modules, optionally captured in a CUDA graph per input slot."""
 
-    def __init__(self, pkg, device, batch, world, group, use_graph, slots=3, seed0=1):
+    def __init__(self, pkg, device, batch, world, group, use_graph, slots=3, seed0=1, early_reduce=True):
         self.pkg, self.device, self.batch, self.world = pkg, device, batch, world
         syn = pkg.synthetic
         self.net = pkg.HieCoAttnHotPath(CFG["vocab"], CFG["d"], CFG["K"], CFG["mlp"])
         p = syn.make_params(CFG["d"], CFG["vocab"], CFG["K"], CFG["mlp"], seed=0)
         self.net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()}, strict=False)
         self.net.to(device)
-        # graph mode: the bucketed all-reduce follows backward inside the captured step (hook-launched NCCL did not replay
-        # reliably from a captured graph: observed a hang); eager mode launches each bucket from the gradient hooks instead
-        # (graph mode reduces after backward, so ONE collective over the whole 48.7 MB buffer beats four 16 MB buckets: fewer launches,
-        # better NVLink / NVSwitch efficiency per message)
-        self.dp = pkg.dp.FlatGradAllReduce(self.net.named_parameters(), group, overlap=not use_graph, flat_params=True,
-                                           bucket_bytes=(1 << 30) if use_graph else (16 << 20))
+        # world > 1: gradients and parameters live in symmetric memory and FlatAdam.step() is the collective -- one hand-written kernel
+        # that reduces in the NVSwitch, updates and multicasts (csrc/dp_fused.cu); the classifier + co-attention slice (13 MB, complete
+        # once coattn_bwd has been enqueued) is processed on a side stream, with a small grid, while the LSTM / conv / embedding backward
+        # runs.  Without symmetric memory the reducer falls back to ONE NCCL all-reduce after backward (HCA_DP_FUSED=0 forces that).
+        fused = None if os.environ.get("HCA_DP_FUSED", "1") != "0" else False
+        self.dp = pkg.dp.FlatGradAllReduce(self.net.named_parameters(), group, overlap=False, flat_params=True, bucket_bytes=1 << 30,
+                                           fused=fused, early_split="question_encoder." if early_reduce else None)
         self.opt = pkg.optim.FlatAdam(self.dp, lr=1e-4)          # Adam(lr=1e-4), README.md:95-100 / main.py:180
+        self.early_end = 0
+        self.side = None
+        if self.dp.fused and early_reduce:
+            self.side = torch.cuda.Stream(device)
+            self.dp.on_early = self._early
         self.criterion = pkg.CrossEntropyLoss(scale=self.dp.loss_scale)   # nn.CrossEntropyLoss(), main.py:179
         self.slots = []
         rank = torch.distributed.get_rank() if world > 1 else 0
@@ -179,6 +194,12 @@ class Stepper:
         self.use_graph = use_graph
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.slots[0]["host"].values())
 
+    def _early(self, end):
+        """Called from inside backward when the gradients of [0, end) are complete (their kernels are enqueued on the main stream)."""
+        self.side.wait_stream(torch.cuda.current_stream())
+        self.opt.step_early(end, self.side, max_ctas=16)
+        self.early_end = end
+
     def _step_body(self, slot):
         d = slot["dev"]
         self.dp.zero_grad()
@@ -186,6 +207,8 @@ class Stepper:
         loss = self.criterion(logits, d["labels"])           # mean CE x 1/world, loss + gradient in one launch
         loss.backward()
         self.dp.finish()
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
         self.opt.step()
         slot["loss"].copy_(loss.detach())
 
@@ -217,15 +240,47 @@ class Stepper:
         return slot
 
 
-# ncu --set full capture of this kernel (profiles/): DRAM bytes per launch, read + write.  None until a capture is committed.
-ROOFLINE_TRAFFIC_BYTES = 81.0e6
-ROOFLINE_TRAFFIC_SOURCE = "profiles/r1e_pv_gemm_ncu_full.md: dram__bytes_read.sum 65.4 MB + dram__bytes_write.sum 15.6 MB, one launch"
+# ---------------------------------------------------------------------------------------------------- roofline legs
+# DRAM traffic per launch comes from a committed `ncu --set full` capture, summarised by profiles/summarize_ncu.py into this file;
+# the bench line cites it by content hash (no literal typed into this script).
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 
 
-def time_roofline_kernel(pkg, device, steps, pk):
-    """The largest dense contraction of the path timed alone with CUDA events: PV = V . W_v^T + b_v, M = 160*196, N = K = 512
-    (SURVEY section 8a row a6), ONE launch of gemm_tc_kernel on operands already in bf16 hi/lo planes, planes out."""
-    M, N, K = 160 * CFG["N"], CFG["d"], CFG["d"]
+def ncu_traffic(key):
+    try:
+        import hashlib
+        raw = open(TRAFFIC_FILE, "rb").read()
+        rec = json.loads(raw)["kernels"].get(key)
+        if not rec:
+            return None, None
+        return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), \
+            f"profiles/ncu_traffic.json sha256:{hashlib.sha256(raw).hexdigest()[:16]} <- {rec.get('source', '?')}"
+    except Exception:
+        return None, None
+
+
+def _events(n):
+    return [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+
+
+def _leg(name, kernel, match, ms, flops, abytes, pk, note=None, issued_factor=3.0):
+    """One roofline leg: `achieved` = ALGORITHMIC TFLOP/s of that kernel timed alone with CUDA events on its stream (the split-precision
+    kernels issue 3 bf16 MMAs per algorithmic product: `frac_issued` counts those)."""
+    achieved = flops / (ms * 1e-3) / 1e12
+    traffic, src = ncu_traffic(name)
+    leg = {"name": name, "kernel": kernel, "match": match, "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+           "frac": achieved / pk["bf16_tflops"], "frac_issued": issued_factor * achieved / pk["bf16_tflops"], "ms_per_launch": ms,
+           "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": abytes,
+           "hbm_gbs_if_algorithmic": abytes / (ms * 1e-3) / 1e9, "hbm_frac_if_algorithmic": abytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+           "traffic": traffic, "traffic_source": src, "peak_source": pk["source"] + " bf16 burst (kernel timed alone)"}
+    if note:
+        leg["note"] = note
+    return leg
+
+
+def time_pv_leg(pkg, device, steps, pk, batch):
+    """PV = V . W_v^T + b_v, M = batch*196, N = K = 512: ONE launch of gemm_tc_kernel, bf16 hi/lo planes in and out."""
+    M, N, K = batch * CFG["N"], CFG["d"], CFG["d"]
     g = torch.Generator(device="cpu").manual_seed(0)
     Ap = [pkg.ops.split_planes(torch.randn(M, K, generator=g).to(device)) for _ in range(3)]     # 3 x 64 MB in + 3 x 64 MB out > L2
     Wp = pkg.ops.split_planes((torch.randn(N, K, generator=g) * 0.04).to(device))
@@ -234,41 +289,131 @@ def time_roofline_kernel(pkg, device, steps, pk):
     for i in range(3):
         pkg.ops.proj_planes(Ap[i % 3], Wp, b, outs[i % 3])
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev = _events(2)
     ev[0].record()
     for i in range(steps):
         pkg.ops.proj_planes(Ap[i % 3], Wp, b, outs[i % 3])
     ev[1].record()
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1]) / steps
-    flops = 2.0 * M * N * K
-    achieved = flops / (ms * 1e-3) / 1e12
-    # the split-precision path issues 3 bf16 MMAs per algorithmic product; `achieved` is ALGORITHMIC TFLOP/s against the bf16 peak
-    return {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-            "traffic": ROOFLINE_TRAFFIC_BYTES, "traffic_source": ROOFLINE_TRAFFIC_SOURCE,
-            "kernel": "gemm_tc_kernel<256,2,K-major,K-major,64,CG=2,EPI=0> (CTA pair, cta_group::2): PV = V.Wv^T + bv, M=31360 N=512 K=512, "
-                      "bf16 hi/lo planes in and out",
-            "ms_per_launch": ms, "algorithmic_flops_per_launch": flops, "issued_mma_flops_per_launch": 3.0 * flops,
-            "frac_issued": 3.0 * achieved / pk["bf16_tflops"],
-            "algorithmic_bytes_per_launch": 2.0 * (2 * M * K * 2) + 2 * N * K * 2,
-            "hbm_gbs_if_algorithmic": (2.0 * (2 * M * K * 2) + 2 * N * K * 2) / (ms * 1e-3) / 1e9,
-            "peak_source": pk["source"] + " bf16 burst (kernel timed alone)"}
+    return _leg("pv_proj", "gemm_tc_kernel<256,2,K-major,K-major,64,CG=2,EPI=0> (CTA pair, cta_group::2): PV = V.Wv^T + bv, "
+                f"M={M} N=512 K=512, bf16 hi/lo planes in and out", "gemm_tc_kernel<256, 2, false, false, 64, 2, 0>", ms, 2.0 * M * N * K,
+                2.0 * (2 * M * K * 2) + 2 * N * K * 2, pk)
+
+
+def time_wgrad_leg(pkg, device, steps, pk, batch):
+    """dW_v = dPV^T . V, M = N = 512, K = batch*196 (split-K, fp32 reduce-add): the largest of the weight-gradient products."""
+    import ctypes as C
+    K, M, N = batch * CFG["N"], CFG["d"], CFG["d"]
+    g = torch.Generator(device="cpu").manual_seed(0)
+    Ap = [pkg.ops.split_planes(torch.randn(K, M, generator=g).to(device)) for _ in range(3)]
+    Bp = [pkg.ops.split_planes(torch.randn(K, N, generator=g).to(device)) for _ in range(3)]
+    D = torch.zeros(M, N, device=device)
+    L = pkg._lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(i):
+        pkg._lib.check(L.hca_wgrad_planes(Ap[i % 3].data_ptr(), Bp[i % 3].data_ptr(), M, N, K, D.data_ptr(), st), "wgrad_planes")
+
+    for i in range(3):
+        run(i)
+    torch.cuda.synchronize()
+    ev = _events(2)
+    ev[0].record()
+    for i in range(steps):
+        run(i)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    return _leg("wgrad_dWv", f"gemm_tc_kernel<256,2,MN-major,MN-major,64,CG=2,EPI=0>: dW_v = dPV^T.V, M=N=512 K={K}, split-K, fp32 reduce-add",
+                "gemm_tc_kernel<256, 2, true, true, 64, 2, 0>", ms, 2.0 * M * N * K, 2.0 * (2 * K * M * 2) + M * N * 4, pk,
+                note="one of the 7 launches of this kernel per step (dW_v, dW_q, conv x3, LSTM x2)")
+
+
+def time_lstm_legs(pkg, device, steps, pk, batch):
+    """The two recurrence kernels of the sentence LSTM (csrc/lstm.cu), each bracketed by CUDA events on its stream inside a standalone
+    forward / backward call of the op at the bench shape (batch x 26 x 512, H = 512, synthetic lengths)."""
+    syn = pkg.synthetic
+    T, H = CFG["T"], CFG["d"]
+    x = syn.make_inputs(batch, CFG["N"], T, H, CFG["vocab"], CFG["K"], seed=3)
+    lens = torch.from_numpy(x["lens"]).to(device)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    u = lambda *s_: ((torch.rand(*s_, generator=g) * 2 - 1) / H ** 0.5).to(device).requires_grad_()
+    w_ih, w_hh, b_ih, b_hh = u(4 * H, H), u(4 * H, H), u(4 * H), u(4 * H)
+    xin = torch.randn(batch, T, H, generator=g).to(device).requires_grad_()
+    dout = torch.randn(batch, T, H, generator=g).to(device)
+    L = pkg._lib.lib()
+    evs = {0: [], 1: []}
+    for i in range(steps + 2):
+        pair = {w: _events(2) for w in (0, 1)}
+        for w in (0, 1):
+            for e in pair[w]:
+                e.record()                      # (a torch event gets its cudaEvent_t on the first record)
+            L.hca_debug_lstm_events(pair[w][0].cuda_event, pair[w][1].cuda_event, w)
+        out, _ = pkg.ops.lstm(xin, lens, w_ih, w_hh, b_ih, b_hh)
+        out.backward(dout)
+        for w in (0, 1):
+            L.hca_debug_lstm_events(None, None, w)
+        torch.cuda.synchronize()
+        if i >= 2:
+            for w in (0, 1):
+                evs[w].append(pair[w][0].elapsed_time(pair[w][1]))
+    tokens = float(x["lens"].sum())
+    rec_tokens = float((x["lens"] - 1).sum())
+    flops = 2.0 * 4 * H * H * rec_tokens
+    legs = []
+    for w, nm in ((0, "lstm_rec_fwd"), (1, "lstm_rec_bwd")):
+        ms = float(np.median(evs[w]))
+        abytes = (batch * T * 4 * H * 4 * (2 if w == 0 else 1) + batch * T * H * 4 * 3 + 2 * 4 * H * H * 2 + (2 * batch * T * 4 * H * 2 if w else 0))
+        legs.append(_leg(nm, f"lstm_rec_kernel<{'bwd' if w else 'fwd'}>: {T} dependent steps of [{batch},{H}] x [{H},{4 * H}] (W_hh resident in shared memory), "
+                         f"{int(tokens)} valid tokens", "lstm_rec_kernel<true" if w else "lstm_rec_kernel<false", ms, flops, float(abytes), pk,
+                         note="a latency chain (per-step cross-CTA exchange + small MMAs), bound by neither pipe: see profiles/ for the per-step timeline"))
+    return legs
+
+
+def roofline_legs(pkg, device, steps, pk, batch):
+    legs = []
+    for fn in (time_lstm_legs, time_wgrad_leg, time_pv_leg):
+        try:
+            r = fn(pkg, device, steps, pk, batch)
+            legs.extend(r if isinstance(r, list) else [r])
+        except Exception as e:                  # evidence only: never fail the bench over one leg
+            legs.append({"name": fn.__name__, "error": f"{type(e).__name__}: {str(e)[:160]}"})
+    return legs
+
+
+def pick_dominant(legs, shares):
+    """The leg whose kernel takes the largest share of the step in the CUPTI breakdown of THIS run (falls back to the longest leg)."""
+    good = [l for l in legs if "error" not in l]
+    if not good:
+        return None
+    if shares and "top" in shares:
+        def share(l):
+            return sum(r["us_per_step"] for r in shares["top"] if l["match"].replace(" ", "") in r["kernel"].replace(" ", ""))
+        for l in good:
+            l["step_share_us"] = share(l)
+            l["step_share"] = l["step_share_us"] / shares["kernel_us_per_step"] if shares.get("kernel_us_per_step") else None
+        # a leg is ONE launch; several legs' kernels run more than once per step, so rank by the time of one launch
+        best = max(good, key=lambda l: l["ms_per_launch"])
+        return best
+    return max(good, key=lambda l: l["ms_per_launch"])
 
 
 def kernel_shares(st, steps=4, top=48):
     """Per-kernel device time of the step under CUPTI activity tracing (torch.profiler): which kernels the step is made of.
-    Runs the step EAGERLY with programmatic dependent launch off (HCA_PDL=0): in the timed graph every kernel starts while its
+    Runs the step EAGERLY with programmatic dependent launch off: in the timed graph every kernel starts while its
     predecessor drains and waits in griddepcontrol.wait, so its CUPTI duration would include that wait."""
+    lib = st.pkg._lib
     try:
         import collections
-        os.environ["HCA_PDL"] = "0"
+        lib.set_option("pdl", "0")
         st._step_body(st.slots[0])
         torch.cuda.synchronize()
         with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
             for i in range(steps):
                 st._step_body(st.slots[i % len(st.slots)])
             torch.cuda.synchronize()
-        os.environ.pop("HCA_PDL", None)
+        lib.set_option("pdl", "1")
         agg = collections.OrderedDict()
         for ev in prof.events():
             if ev.device_type == torch.autograd.DeviceType.CUDA:
@@ -277,12 +422,88 @@ def kernel_shares(st, steps=4, top=48):
                 a[1] += ev.device_time
         tot = sum(v[1] for v in agg.values())
         rows = sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]
-        short = lambda n: n.replace("hca::(anonymous namespace)::", "").replace("void ", "")[:60]
+        short = lambda n: n.replace("hca::(anonymous namespace)::", "").replace("void ", "")[:72]
         return {"kernel_us_per_step": tot / steps,
                 "top": [{"kernel": short(k), "us_per_step": us / steps, "launches_per_step": n / steps, "share": us / tot} for k, (n, us) in rows]}
     except Exception as e:                      # evidence only: never fail the bench over it
-        os.environ.pop("HCA_PDL", None)
+        try:
+            lib.set_option("pdl", "1")
+        except Exception:
+            pass
         return {"error": f"{type(e).__name__}: {str(e)[:100]}"}
+
+
+# ------------------------------------------------------------------------------------------- stock-PyTorch GPU baseline
+def gpu_eager_baseline(device, batch, steps=10, warmup=3):
+    """The kernel to beat on the same box: the reference's algorithm (oracle/torch_port.py, op for op what model.py:246-434 issues,
+    incl. the redundant projections) run by stock PyTorch on THIS GPU -- cuBLAS / cuDNN kernels, fwd + CE + bwd + Adam -- in fp32 (TF32
+    off), with TF32 allowed, and under autocast(bf16); eagerly, and replayed from a CUDA graph where capture succeeds."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port as TP
+    syn = importlib.import_module("visual-question-answering_b200.synthetic")
+    x = syn.make_inputs(batch, CFG["N"], CFG["T"], CFG["d"], CFG["vocab"], CFG["K"], seed=1)
+    feats, tokens = torch.from_numpy(x["feats"]).to(device), torch.from_numpy(x["tokens"]).to(device)
+    lens, labels = torch.from_numpy(x["lens"]), torch.from_numpy(x["labels"]).to(device)          # lens stay on the host: pack_padded_sequence wants them there
+    out = {}
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    for mode in ("fp32", "tf32", "autocast_bf16"):
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = (mode != "fp32")
+            p = {k: v.detach().to(device).requires_grad_(v.requires_grad) for k, v in
+                 TP.make_params(syn.make_params(CFG["d"], CFG["vocab"], CFG["K"], CFG["mlp"], seed=0)).items()}
+            opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-4, capturable=True)
+
+            def step():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "autocast_bf16")):
+                    logits = TP.forward(p, feats, tokens, lens)
+                    loss = torch.nn.functional.cross_entropy(logits.float(), labels)
+                opt.zero_grad(set_to_none=False)
+                loss.backward()
+                opt.step()
+                return loss
+
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            ev = _events(2)
+            ev[0].record()
+            for _ in range(steps):
+                step()
+            ev[1].record()
+            torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1]) / steps
+            rec = {"eager_ms_per_step": ms, "eager_samples_per_s": batch / (ms * 1e-3)}
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        step()
+                torch.cuda.current_stream().wait_stream(side)
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph):
+                    step()
+                for _ in range(warmup):
+                    gph.replay()
+                torch.cuda.synchronize()
+                ev = _events(2)
+                ev[0].record()
+                for _ in range(steps):
+                    gph.replay()
+                ev[1].record()
+                torch.cuda.synchronize()
+                gms = ev[0].elapsed_time(ev[1]) / steps
+                rec.update({"graph_ms_per_step": gms, "graph_samples_per_s": batch / (gms * 1e-3)})
+            except Exception as e:
+                rec["graph"] = f"capture failed: {type(e).__name__}: {str(e)[:100]}"
+                torch.cuda.synchronize()
+            out[mode] = rec
+        except Exception as e:
+            out[mode] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    out["what"] = ("oracle/torch_port.py (the reference's ATen call sequence, model.py:246-434 + main.py:179-180,214-222) on this GPU by stock "
+                   f"PyTorch {torch.__version__}: fwd + mean CE + bwd + Adam, batch {batch}, inputs resident")
+    return out
 
 
 def run_ours(args):
@@ -310,7 +531,11 @@ def run_ours(args):
     importlib.import_module("visual-question-answering_b200.dp")
     pk = peaks()
     use_graph = not args.no_graph
-    st = Stepper(pkg, device, args.batch, world, group, use_graph)
+    if args.scaling == "strong":
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        args.batch = args.global_batch // world
+    st = Stepper(pkg, device, args.batch, world, group, use_graph, early_reduce=not args.no_early_reduce)
     st.warm(2)
     launches_per_step = st.count_launches()
     graph_note = "cuda-graph replay"
@@ -396,23 +621,36 @@ def run_ours(args):
     final_loss = float(loss_host) / st.dp.loss_scale
 
     if rank == 0:
-        roof = time_roofline_kernel(pkg, device, max(args.steps, 10), pk)
-        shares = kernel_shares(st) if world == 1 else None      # (the step holds collectives when world > 1: not a rank-0-only job)
+        # the CUPTI breakdown and the legs run the kernels outside the step's collectives: only at world == 1 is that a rank-0-only job
+        shares = kernel_shares(st) if world == 1 else None
+        legs = roofline_legs(pkg, device, 20, pk, args.batch) if not args.skip_legs else []
+        roof = pick_dominant(legs, shares)
         step_tflops = FLOPS_PER_SAMPLE * args.batch / (ms_step * 1e-3) / 1e12
-        cpu = None
+        cpu = eager = None
         if world == 1 and not args.skip_cpu_baseline:
-            v, ms, threads = cpu_reference(32, 5, 2, threads=os.cpu_count())
+            nb = min(args.batch, 160)
+            v, ms, threads = cpu_reference(nb, 8, 2, threads=os.cpu_count())
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "5 steps of batch 32 (of the 160-sample batch), torch CPU fp32, oracle/torch_port.py", "ms_per_step": ms}
+                   "sample": f"8 steps of batch {nb} (the GPU arm's batch), fwd+CE+bwd+Adam, torch CPU fp32, oracle/torch_port.py", "ms_per_step": ms}
+        if world == 1 and not args.skip_gpu_baseline:
+            try:
+                eager = gpu_eager_baseline(device, args.batch)
+            except Exception as e:
+                eager = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+        comm = "none"
+        if world > 1:
+            comm = ("fused NVLink kernel (csrc/dp_fused.cu: " + ("multimem.ld_reduce / multimem.st through the NVSwitch" if st.dp._symm.mc else "peer loads / stores")
+                    + "), all-reduce + Adam + parameter broadcast in one launch" + (", classifier + co-attention slice overlapped with the rest of backward" if st.early_end else "")) \
+                if st.dp.fused else "NCCL all-reduce after backward + fused Adam"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (fp32 CUDA cores)" if pkg._lib.get_option("gemm") == "ffma" else "bf16x2 (fp32 operands as bf16 hi+lo planes, 3 tcgen05 MMAs per product, fp32 accumulate)",
-                "data": "synthetic", "config": workload_config(args.batch, world, {"mode": graph_note}),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                "dtype": "bf16x2 (fp32 operands as bf16 hi+lo planes, 3 tcgen05 MMAs per product, fp32 accumulate)",
+                "data": "synthetic", "config": workload_config(args.batch, world, {"mode": graph_note, "collective": comm}),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st.h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_ms},
                 "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
-                "roofline": roof, "cpu_baseline": cpu, "kernel_shares": shares,
+                "roofline": roof, "roofline_legs": legs, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "kernel_shares": shares,
                 "step_algorithmic_tflops": step_tflops, "step_frac_of_bf16_peak": step_tflops / pk["bf16_tflops_sustained"],
                 "final_loss": final_loss, "grad_allreduce_bytes": st.dp.grad_bytes() if world > 1 else 0}
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
@@ -448,6 +686,12 @@ def main():
     ap.add_argument("--batch", type=int, default=160, help="samples per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-gpu-baseline", action="store_true", help="skip the stock-PyTorch eager legs on the GPU")
+    ap.add_argument("--skip-legs", action="store_true", help="skip the per-kernel roofline legs")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: --batch samples per GPU (configs[2]); strong: --global-batch samples split over the GPUs (configs[3])")
+    ap.add_argument("--global-batch", type=int, default=1280)
+    ap.add_argument("--no-early-reduce", action="store_true", help="fused DP: do not overlap the classifier / co-attention slice with backward")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -209,6 +209,12 @@ HCA_API int hca_debug_gemm_timeline(void* buf, int nctas);
 HCA_API int hca_debug_gemm_timeline_select(void* buf, int nctas, int launch_index);
 /* debug: CTA 0 of the following LSTM recurrence launches records clock64() stamps into buf (int64 [7 rounds][8]); NULL = off */
 HCA_API int hca_debug_lstm_timeline(void* buf);
+/* profiling aid (bench.py's roofline legs): the recurrence kernel launched by the following hca_lstm_fwd (which = 0) /
+ * hca_lstm_bwd (which = 1) calls is bracketed by the two cudaEvent_t handles on the launching stream; NULLs switch it off */
+HCA_API int hca_debug_lstm_events(void* ev_start, void* ev_stop, int which);
+/* one weight-gradient product on its own: D[M,N] += A[K,M]^T . B[K,N] from bf16 hi/lo planes [2][K][M], [2][K][N] (split-K,
+ * fp32 reduce-add into D) */
+HCA_API int hca_wgrad_planes(const void* a_planes, const void* b_planes, int M, int N, int64_t K, float* D, void* stream);
 /* one dense contraction from fp32 operands (tests / profiling): layout 0 nt, 1 nn, 2 tn; path 1 = bf16x2 split (3 MMAs), 2 = bf16x3 */
 HCA_API int hca_gemm(const float* A, const float* B, const float* bias, float* D, int M, int N, int K,
                      int layout, int path, void* ws, size_t ws_bytes, void* stream);

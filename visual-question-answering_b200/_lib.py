@@ -56,6 +56,8 @@ SIGNATURES = {
     "hca_debug_gemm_timeline": (_i, [_p, _i]),
     "hca_debug_gemm_timeline_select": (_i, [_p, _i, _i]),
     "hca_debug_lstm_timeline": (_i, [_p]),
+    "hca_debug_lstm_events": (_i, [_p, _p, _i]),
+    "hca_wgrad_planes": (_i, [_p, _p, _i, _i, _i64, _p, _p]),
     "hca_gemm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
 }
 

@@ -4,6 +4,7 @@
 //   nt : D[M,N] = A[M,K] . B[N,K]^T      forward of nn.Linear (x . W^T), B is a weight [out,in]
 //   nn : D[M,N] = A[M,K] . B[K,N]        data gradient (dY . W)
 //   tn : D[M,N] = A[K,M]^T . B[K,N]      weight gradient (dY^T . X), long K -> split-K
+#include <algorithm>
 #include "gemm_tc.cuh"
 #include "util_kernels.cuh"
 
@@ -90,6 +91,20 @@ extern "C" int hca_proj_planes(const void* a_planes, int64_t M, int K, const voi
   e.bias = bias;
   e.P.p = (__nv_bfloat16*)out_planes; e.P.ld = N; e.P.plane_stride = M * N; e.P.batch_stride = 0; e.P.nbatch = 1;
   return launch_gemm_tc(A, B, 2, (int)M, N, K, e, 1, (cudaStream_t)stream);
+}
+
+// ---- a weight-gradient product on its own (bench.py's roofline legs): D[M,N] += A[K,M]^T . B[K,N], both operands MN-major planes --
+extern "C" int hca_wgrad_planes(const void* a_planes, const void* b_planes, int M, int N, int64_t K, float* D, void* stream) {
+  using namespace hca;
+  HCA_CHECK_ARG(a_planes && b_planes && D && M > 0 && N > 0 && K > 0 && K < (1LL << 31) && M % 8 == 0 && N % 8 == 0,
+                "wgrad_planes: bad arguments (M, N %% 8 == 0 required)");
+  HCA_CHECK_ARG(tc_available(), "wgrad_planes: cuTensorMapEncodeTiled is not available from the driver");
+  TcOperand A, B;
+  A.planes = (const __nv_bfloat16*)a_planes; A.ld = M; A.plane_stride = K * M; A.rows = (int)K; A.cols = M; A.mn_major = true;
+  B.planes = (const __nv_bfloat16*)b_planes; B.ld = N; B.plane_stride = K * N; B.rows = (int)K; B.cols = N; B.mn_major = true;
+  TcEpilogue e;
+  e.D = D; e.ldd = N; e.accumulate = 1;
+  return launch_gemm_tc(A, B, 2, M, N, (int)K, e, std::max(2, tc_splitk(M, N, (int)K)), (cudaStream_t)stream);
 }
 
 extern "C" int hca_debug_gemm_timeline(void* buf, int nctas) {

@@ -84,6 +84,7 @@ struct LstmParams {
                           // accumulator seen by the cell threads, cell math done, barrier passed, step published), else nullptr
 };
 long long* g_lstm_timeline = nullptr;
+cudaEvent_t g_rec_events[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};     // [fwd / bwd][start / stop]: see hca_debug_lstm_events
 
 __device__ __forceinline__ float sigmoid_fast(float x) {
   float e, r;
@@ -887,8 +888,10 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
         continue;
       }
     }
+    if (g_rec_events[BWD ? 1 : 0][0] && t0 == 0) HCA_CUDA(cudaEventRecord(g_rec_events[BWD ? 1 : 0][0], s));
     HCA_LAUNCH_K((lstm_rec_kernel<BWD, false>), nm * p.tiles_n, L_THREADS, smem, s, maps, p);
     HCA_LAUNCHED();
+    if (g_rec_events[BWD ? 1 : 0][1] && t0 + rt.per_launch >= rt.tiles) HCA_CUDA(cudaEventRecord(g_rec_events[BWD ? 1 : 0][1], s));
   }
   return 0;
 }
@@ -898,6 +901,15 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
 
 extern "C" int hca_debug_lstm_timeline(void* buf) {
   hca::g_lstm_timeline = (long long*)buf;
+  return 0;
+}
+
+// bench.py's roofline legs: the recurrence kernel of the next hca_lstm_fwd (which = 0) / hca_lstm_bwd (which = 1) calls is bracketed by
+// these two CUDA events on the launching stream (cudaEvent_t handles; nullptr switches it off)
+extern "C" int hca_debug_lstm_events(void* ev_start, void* ev_stop, int which) {
+  if (which < 0 || which > 1) return hca::set_err(HCA_ERR_ARG, "debug_lstm_events: which = 0 (forward) or 1 (backward)");
+  hca::g_rec_events[which][0] = (cudaEvent_t)ev_start;
+  hca::g_rec_events[which][1] = (cudaEvent_t)ev_stop;
   return 0;
 }
 

@@ -58,7 +58,8 @@ def shard_batch(n_items: int, rank: int, world: int) -> slice:
 class FlatGradAllReduce:
     def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], process_group=None,
                  skip: Sequence[str] = ("co_attention.W_b.",), bucket_bytes: int = 16 << 20, overlap: bool = False,
-                 flat_params: bool = False, align: int = 64, direct_write: bool = True, fused: Optional[bool] = None):
+                 flat_params: bool = False, align: int = 64, direct_write: bool = True, fused: Optional[bool] = None,
+                 early_split: Optional[str] = None):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
@@ -67,6 +68,10 @@ class FlatGradAllReduce:
         self.fused = False
         self._symm = None
         self._optimizer = None              # a FlatAdam that has taken over the collective (fused mode)
+        # early_split = a parameter-name prefix: a bucket boundary is forced in front of the first parameter carrying it, and
+        # ``on_early(end)`` (if set) is called during backward as soon as every gradient in [0, end) has been written -- the hook
+        # the fused transport uses to reduce the classifier / co-attention slice while the encoder's backward still runs
+        self.on_early = None
         items = [(n, p) for n, p in named_params if p.requires_grad and not any(n.startswith(s) for s in skip)]
 
         def order(item):
@@ -108,8 +113,14 @@ class FlatGradAllReduce:
         self.buckets: List[Tuple[int, int]] = []            # [start, end) element ranges of the flat buffer
         self._bucket_of: List[int] = []
         off, b_start, limit = 0, 0, max(1, bucket_bytes // self.flat.element_size())
-        for p in self.params:
+        split_done = early_split is None
+        for name, p in zip(self.names, self.params):
             n = p.numel()
+            if not split_done and name.startswith(early_split):
+                split_done = True
+                if off > b_start:
+                    self.buckets.append((b_start, off))
+                    b_start = off
             if self.flat_p is not None:
                 view = self.flat_p[off:off + n].view_as(p)
                 view.copy_(p.data)
@@ -152,7 +163,9 @@ class FlatGradAllReduce:
         self._counted.add(i)
         b = self._bucket_of[i]
         self._left[b] -= 1
-        if self._left[b] == 0 and self.world > 1 and self.overlap:
+        if self._left[b] == 0 and b == 0 and self.on_early is not None:
+            self.on_early(self.buckets[0][1])
+        if self._left[b] == 0 and self.world > 1 and self.overlap and not self.fused:
             self._launch(b)
 
     def _make_hook(self, i):
