@@ -1,4 +1,4 @@
-"""-m gpu: the dense contraction kernels (fp32 CUDA-core path and the tcgen05 split-bf16 path) against fp64."""
+"""-m gpu: the dense contraction kernel (tcgen05, split-bf16 operand planes) against fp64."""
 import numpy as np
 import pytest
 import torch
@@ -25,12 +25,12 @@ def _ref(A, B, bias, layout):
 
 
 SHAPES = [(128, 128, 64), (256, 512, 512), (1000, 512, 512), (160, 1001, 1024), (77, 40, 200), (4160, 1536, 512), (130, 136, 1001)]
-# expected normwise relative error per path: fp32 ~1e-6, bf16x2 split ~2^-16, bf16x3 split fp32-grade
-TOL = {0: 2e-6, 1: 3e-5, 2: 8e-6}      # tensor-core fp32 accumulation truncates: ~K*2^-24 floor for bf16x3
+# expected normwise relative error per path: bf16x2 split ~2^-16, bf16x3 split fp32-grade
+TOL = {1: 3e-5, 2: 8e-6}      # tensor-core fp32 accumulation truncates: ~K*2^-24 floor for bf16x3
 
 
 @pytest.mark.parametrize("layout", ["nt", "nn", "tn"])
-@pytest.mark.parametrize("path", [0, 1, 2])
+@pytest.mark.parametrize("path", [1, 2])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm_layouts_and_paths(layout, path, M, N, K):
     ops = _ops()

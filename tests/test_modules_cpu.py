@@ -84,3 +84,34 @@ def test_synthetic_inputs_follow_the_reference_conventions(syn):
     assert x["labels"].min() >= 0 and x["labels"].max() < 11
     p = syn.make_params(32, 100, 11, 16)
     assert (p["question_encoder.word_embedding.weight"][0] == 0).all()                  # padding_idx row, model.py:263
+
+
+def test_no_kernel_touches_global_memory_before_its_pdl_wait(pkg):
+    """Every kernel of the library is launched with programmatic dependent launch and begins with griddepcontrol.wait (SASS: ACQBULK):
+    nothing it reads may be fetched before that wait returns.  A load through a `const __restrict__` pointer is an invariant load to
+    the compiler, which is free to hoist it above the inline-asm wait (it happened to the near-tie counter of the max-pool repair: the
+    fix-up kernel read a partial count).  This scans the SASS of the built library: no global / TMA load, store or atomic may
+    precede the kernel's first ACQBULK."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    pkg._lib.lib()
+    sass = subprocess.run([exe, "-sass", pkg._lib.LIB_PATH], capture_output=True, text=True, timeout=900).stdout
+    offenders, kernels, fn, waited = [], 0, None, False
+    mem = re.compile(r"^\s*/\*[0-9a-f]+\*/\s+(@!?U?P\d+\s+)?(LDG|LD\.E|STG|ST\.E|ATOMG|ATOM\.E|RED\.E|UTMALDG|UTMASTG|UBLKCP|UTMAREDG)\b")
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn, waited = m.group(1), False
+            kernels += 1
+            continue
+        if fn is None or "/*" not in line:
+            continue
+        if "ACQBULK" in line:
+            waited = True
+        elif not waited and mem.search(line):
+            offenders.append((fn[:80], line.strip()[:90]))
+    assert kernels > 40, kernels
+    assert not offenders, offenders[:5]

@@ -190,7 +190,7 @@ __device__ __forceinline__ void fixup_one(int64_t r, int e, const float* __restr
 
 // Repairs the listed near-ties (one warp per entry).  When more were found than the list holds, the list is ignored and every element is
 // re-examined instead: each lane re-derives the band condition of one element from `cat`, the warp then repairs the flagged ones in turn.
-__global__ void __launch_bounds__(256) fixup_ties_kernel(const int* __restrict__ tie_list, const int* __restrict__ tie_count, int tie_cap,
+__global__ void __launch_bounds__(256) fixup_ties_kernel(const int* __restrict__ tie_list, const int* tie_count, int tie_cap,
                                                          const float* __restrict__ cat, const int64_t* __restrict__ lens,
                                                          const float* __restrict__ xn2, const float* __restrict__ wn,
                                                          const float* __restrict__ x, int B, int T, const float* __restrict__ w1,
@@ -199,7 +199,10 @@ __global__ void __launch_bounds__(256) fixup_ties_kernel(const int* __restrict__
                                                          const float* __restrict__ b3, float* __restrict__ out,
                                                          uint8_t* __restrict__ idx, int E, int* __restrict__ stats) {
   pdl_enter();
-  const int found = *tie_count;
+  // volatile: a load through a `const __restrict__` pointer is an INVARIANT load to the compiler, which may (and in one build did)
+  // hoist it above griddepcontrol.wait -- i.e. read the counter while the pool kernel is still counting (tests/test_modules_cpu.py
+  // scans the SASS of every kernel for global loads ahead of the wait)
+  const int found = *reinterpret_cast<const volatile int*>(tie_count);
   if (stats && blockIdx.x == 0 && threadIdx.x == 0) { stats[0] = found; stats[1] = tie_cap; }
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
