@@ -51,21 +51,37 @@ def test_lstm_matches_oracle(B, T, E, H):
     assert errs["out"] < 1e-4, errs
 
 
-@pytest.mark.parametrize("env", ["HCA_LSTM_STK", "HCA_LSTM_MC"])
-@pytest.mark.parametrize("B,T,E,H", [(160, 26, 512, 512), (37, 9, 64, 128)])
-def test_lstm_backward_variants_match_oracle(env, B, T, E, H):
-    """The opt-in backward variants (M-stacked hi/lo operand tile; cluster multicast of the streamed operand) give the same results."""
+def test_lstm_refuses_a_device_that_cannot_hold_a_row_tile(tmp_path):
+    """All CTAs of a recurrence launch wait for each other, so they must be co-resident.  With the device pretended to hold only 8 CTAs
+    (HCA_LSTM_MAX_CTAS, read once per process: hence the subprocess) H = 512 (32 CTAs per row tile) must be reported as unsupported --
+    and the encoder must then take the cuDNN fallback and still match the oracle -- rather than being launched into a spin."""
     import os
-    prev = os.environ.get(env)
-    os.environ[env] = "1"
-    try:
-        errs = _run(B, T, E, H, seed=B + T)
-    finally:
-        if prev is None:
-            os.environ.pop(env, None)
-        else:
-            os.environ[env] = prev
-    assert max(errs.values()) < 1e-3, errs
+    import subprocess
+    import sys
+    import textwrap
+    from conftest import ROOT
+    code = textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r}); sys.path.insert(0, {os.path.join(ROOT, 'oracle')!r})
+        import numpy as np, torch
+        import gpu_harness as h
+        ops = h.PKG.ops
+        assert not ops.lstm_supported(160, 26, 512, 512)
+        assert ops.lstm_supported(16, 5, 64, 64)            # 4 CTAs per row tile forward, 4 backward: fits 8
+        syn = h.PKG.synthetic
+        d, N, T, vocab, K, mlp = 512, 20, 7, 60, 9, 64
+        p = syn.make_params(d, vocab, K, mlp, seed=2)
+        x = syn.make_inputs(5, N, T, d, vocab, K, seed=3, min_len=1)
+        net = h.build_net(p, d, vocab, K, mlp)
+        before = h.PKG._lib.launch_count()
+        ours = h.run_ours(net, x, lens_on="both")
+        orc = h.run_oracle(p, x, np.float64)
+        h.compare(ours, orc, tol=1e-3)
+        print("FALLBACK_OK")
+    """)
+    env = dict(os.environ, HCA_LSTM_MAX_CTAS="8")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "FALLBACK_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
 
 
 def test_lstm_unsorted_lengths_and_len_T():

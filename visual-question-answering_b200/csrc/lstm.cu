@@ -6,22 +6,33 @@
 //   c_t = f c_{t-1} + i g                                  h_t = o tanh(c_t)
 //
 // The input projection of all (b, t) is one tcgen05 GEMM (gemm_tc.cuh).  The recurrence -- T dependent steps of a
-// [B, H] x [H, 4H] product -- runs in ONE persistent kernel instead of T library GEMM + cell launches:
-//   * CTA (mi, ni) owns 128 batch rows x 16 hidden units.  Its slice of W_hh (the 64 gate rows of its units, as bf16 hi/lo
-//     planes, 128 KB at H = 512) is loaded into shared memory ONCE and stays there for all steps; the cell state c of its
-//     (row, unit) pairs lives in registers.
-//   * per step the CTAs of one row tile exchange h_{t-1} through global memory (bf16 hi/lo planes, written by the cell
-//     epilogue, streamed back in by TMA as the A operand); a release/acquire counter per (row tile, step) orders the
-//     exchange -- rows of different tiles never wait for each other.
-//   * batch on the UMMA M axis, the 4 gates of a unit on 4 adjacent accumulator columns (W rows are permuted to
-//     [unit][gate] order), so one epilogue thread holds all four gates of its (row, unit) and no cross-thread exchange
-//     is needed; tcgen05.mma kind::f16 on bf16x2 operand planes (3 MMAs per k-step), fp32 accumulation in TMEM.
-// Backward runs the same skeleton in reverse time: the streamed operand is the gate gradient of step t+1 (written as bf16
-// planes by the cell-backward epilogue -- the very array the weight-gradient GEMMs consume afterwards), the resident operand
-// the 16 columns of W_hh belonging to the CTA's units.  dW_ih, dW_hh and dx are three big tcgen05 GEMMs over all (b, t).
+// [B, H] x [H, 4H] product -- runs in ONE persistent kernel per direction instead of T library GEMM + cell launches.
+//
+// Orientation: the WEIGHT rows sit on the UMMA M axis and the batch on N.  A CTA owns the cell math of 16 hidden units of one
+// row tile (rpt <= 40 batch rows).  Its resident operand is a 64-row slice of the weight matrix as bf16 hi / lo planes stacked
+// along M ([W_hi ; W_lo] = 128 rows x K, 128 KB at K = 512, loaded once and kept for all steps); the streamed operand of a step
+// is the [rpt x K] activation tile of the row tile, hi and lo planes stacked along N ([x_hi ; x_lo] = 2 rpt rows).  ONE
+// tcgen05.mma per 16-wide k-slice (M = 128, N = 2 rpt <= 80, fp32 accumulator in TMEM) therefore yields all four partial
+// products W_hi.x_hi, W_hi.x_lo, W_lo.x_hi, W_lo.x_lo; the epilogue adds them.  (The previous orientation put the batch on M:
+// 128 MMA rows for 40 valid batch rows, 3.2x the tensor cycles, and a cell epilogue in which 80 of 256 threads had work.)
+//   forward : rows = the 64 gate rows of the CTA's 16 units ([unit][gate] order), K = H, stream = h_{t-1}.  The accumulator
+//             comes back as D[gate row][batch]; the four TMEM-reader warps add the partial products and lay them out in shared
+//             memory as [batch][gate row], where 320 cell threads (batch row x unit pair) pick up the 4 gates of their units.
+//   backward: dh = dz_{t+1} . W_hh contracts over 4H gate columns.  With 16 units per CTA every CTA would have to stream all
+//             4H columns of the row tile's gate gradients every step (320 KB per CTA and step: that stream bounded the old
+//             kernel).  Instead a CLUSTER of 4 CTAs shares 64 units and splits the contraction: CTA j holds W_hh^T[64 units,
+//             quarter j of the gate columns] (again 128 KB), streams only its quarter (80 KB, like the forward), and the four
+//             partial [64 units x rpt] results are exchanged through DISTRIBUTED SHARED MEMORY (st.shared::cluster + a cluster-
+//             scope mbarrier): each CTA receives the three foreign partials of the 16 units whose cell math it owns.
+// The CTAs of a row tile exchange h_t (forward) / dz_t (backward) through global bf16 planes -- written by the cell threads,
+// ordered by a release/acquire counter per (row tile, step), streamed back in by TMA -- because a row tile spans 32 CTAs, more
+// than a cluster holds; rows of different tiles never wait for each other.  The gate gradients are written as the very planes
+// the three big weight / input-gradient GEMMs consume afterwards.  All CTAs of a launch must be resident at once (they wait for
+// each other): the launcher sizes every launch from the occupancy API and refuses shapes the device cannot hold.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <algorithm>
+#include <cstring>
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
@@ -35,40 +46,35 @@ namespace hca {
 namespace {
 using namespace ptx;
 
-constexpr int L_BM = 128;                         // batch rows per CTA (UMMA M)
 constexpr int L_BK = 64;                          // bf16 per k-block row = 128 B = one SWIZZLE_128B span
-constexpr int L_UNITS = 16;                       // hidden units per CTA
-constexpr int L_MAX_STAGES = 16;                  // ring slots of the streamed operand (as many as fit: short row tiles -> many small slots)
-constexpr uint32_t L_RING_BYTES = 96 * 1024;
-constexpr int L_THREADS = 64 + 256;               // warp 0 TMA, warp 1 MMA, warps 2..9 cell epilogue (2 groups x 4 TMEM quadrants)
+constexpr int L_UNITS = 16;                       // hidden units whose cell math one CTA owns
+constexpr int L_WROWS = 64;                       // weight rows per plane in the resident tile (fwd: 4 gates x 16 units; bwd: 64 units)
+constexpr int L_RPT_MAX = 40;                     // batch rows per row tile (UMMA N = 2 rpt <= 80; the streamed step operand stays in smem)
+constexpr int L_KB_MAX = 8;                       // k-blocks of a CTA's contraction (K <= 512)
+constexpr int L_KSPLIT = 4;                       // backward: CTAs per cluster = slices of the 4H contraction
+constexpr int L_EPI = 320;                        // cell threads: 8 unit pairs x 40 batch rows
+constexpr int L_THREADS = 64 + L_EPI;             // warp 0 TMA, warp 1 MMA, warps 2..11 epilogue (warps 2..5 also read TMEM)
+constexpr int L_PSTRIDE = 132;                    // forward: floats per batch row of the [batch][gate row] staging tile
+constexpr int L_RSTRIDE = 44;                     // backward: floats per unit row of the staging / receive tiles ([unit][batch])
+constexpr uint32_t L_WKB_BYTES = 2u * L_WROWS * L_BK * 2u;                 // one resident k-block: hi tile + lo tile = 16 KB
+constexpr uint32_t L_RECV_BYTES = L_KSPLIT * L_UNITS * L_RSTRIDE * 4u;     // backward: partial sums received from the cluster
 constexpr int L_MAX_SMEM = 227 * 1024 - 2048;
+constexpr uint32_t L_TMEM_COLS = 128;
 
-constexpr int L_CL = 8;                           // cluster size of the multicast variant: 8 CTAs of one row tile share the streamed operand
-constexpr int L_TMAX = 128;                       // longest sequence for which the per-step row trimming is tabulated
 struct LstmMaps {
-  CUtensorMap A[3];   // streamed operand planes, 5-D (64 cols, b, k-block, t, plane), boxes (64, box_rows[i], nkb, 1, 1): full, half, quarter tile
-  CUtensorMap W;      // resident operand planes, 4-D (cols, rows, plane, 1), box (64, BN, 1, 1)
-  CUtensorMap AS;     // "stacked" view of the streamed operand, dims (64 cols, b, plane, k-block, t), box (64, 64, 2, 1, 1): one k-block
-                      // lands as a 128-row tile whose rows 0..63 are the hi plane and 64..127 the lo plane of the same 64 batch rows
-  CUtensorMap A1[3];  // the streamed operand again with ONE k-block per box (64, box_rows[i], 1, 1, 1): the pieces of a ring slot that the
-                      // CTAs of a cluster load for each other in multicast mode
+  CUtensorMap X;      // streamed operand planes, 4-D (col, b, plane, t), box (64, rpt, 2, 1): lands as [x_hi rows ; x_lo rows] x 64 k
+  CUtensorMap W;      // resident operand planes, 4-D (col, row, plane, 1), box (64, 64, 1, 1)
 };
 
 struct LstmParams {
   int B, T, H;
+  int K;                  // contraction length of one CTA: H (forward: all of h; backward: a quarter of the 4H gate columns)
+  int kbn;                // its k-blocks: ceil(K / 64)
   int tile0;              // first row tile of this launch
-  int rpt;                // batch rows per row tile (<= 128, multiple of 8): tile i owns rows [i * rpt, (i + 1) * rpt)
-  int box_rows[3];        // rows of the three TMA boxes of the streamed operand
-  int stages;             // ring slots in use
-  uint32_t plane_bytes;   // bytes of one plane of one ring slot (rpt rows x 128 B); a slot = hi plane + lo plane
-  uint32_t lo_off;        // offset of the lo-plane tiles inside a slot (= nkb * plane_bytes)
-  uint32_t stage_bytes;   // bytes of one ring slot: nkb k-blocks x (hi tile + lo tile)
-  int nkb;                // k-blocks per ring slot: ONE TMA box per plane brings nkb k-blocks (the issue rate of small boxes,
-                          // ~450 cycles per slot iteration, bounded the recurrence when every k-block was its own slot)
-  int nslots;             // slots per round = ceil(kbn / nkb)
-  int tiles_n;            // H / 16
-  int kbn;                // k-blocks of the recurrent contraction: fwd ceil(H / 64), bwd ceil(4H / 64)
-  int K;                  // contraction length: fwd H, bwd 4H
+  int rpt;                // batch rows per row tile (multiple of 8, <= 40): tile i owns rows [i * rpt, (i + 1) * rpt)
+  int ctas_per_tile;      // forward H / 16 ; backward 4 * ceil(H / 64)
+  uint32_t ring_bytes;    // shared memory of the streamed operand (>= the staging tile that aliases it)
+  uint32_t idesc;         // UMMA instruction descriptor (M = 128, N = 2 rpt, bf16 x bf16 -> f32, both operands K-major)
   const int64_t* lens;
   int* counters;          // [row tiles][T]: CTAs of the row tile that have published step t
   float* act;             // [B][T][4H], gate columns in [unit][gate] order.  fwd: in = x-projection + biases, out = activations
@@ -80,8 +86,8 @@ struct LstmParams {
   __nv_bfloat16* dgp;     // gate-gradient planes [2][B][T][4H] ([unit][gate] column order) (bwd)
   int64_t dgp_ps;
   float* dbias;           // [4H] in [unit][gate] order, accumulated atomically (bwd)
-  long long* timeline;    // debug: clock64 stamps of CTA 0 ([round][8]: counter seen, loads issued, first operand landed, MMAs issued,
-                          // accumulator seen by the cell threads, cell math done, barrier passed, step published), else nullptr
+  long long* timeline;    // debug (HCA_BUILD_TIMELINE=1): clock64 stamps of CTA 0, [round][8]: counter seen, loads issued, first k-block landed,
+                          // MMAs issued, accumulator seen by the cell threads, cell math done, barrier passed, step published
 };
 long long* g_lstm_timeline = nullptr;
 cudaEvent_t g_rec_events[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};     // [fwd / bwd][start / stop]: see hca_debug_lstm_events
@@ -97,44 +103,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr)
                : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.mma from ONE elected thread, instruction descriptor in a register (N depends on the row tiling)
+template <uint32_t DESC_HI>
+__device__ __forceinline__ void umma_bf16_rt(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-// multicast variant: the box lands at the same shared-memory offset of every CTA in `mask`, and each of them gets the bytes
-// signalled on ITS barrier at the same offset
-__device__ __forceinline__ void tma_load_5d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(dst),
-      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(mask)
-      : "memory");
-}
-// MMA completion -> the mbarrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t e;
-  asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(e));
-  return e;
-}
-// tcgen05.mma predicated by an integer flag (elected lane && k-slice holds data), constant descriptor halves as immediates
-template <uint32_t DESC_HI, uint32_t IDESC>
-__device__ __forceinline__ void umma_bf16_imm_pred(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate, uint32_t issue) {
-  asm volatile(
-      "{\n\t.reg .pred p, pe;\n\t.reg .b64 da, db;\n\t"
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
       "mov.b64 da, {%1, %5};\n\t"
       "mov.b64 db, {%2, %5};\n\t"
-      "setp.ne.b32 pe, %4, 0;\n\t"
-      "setp.ne.b32 p, %3, 0;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, p;\n\t}" ::"r"(tmem_d),
-      "r"(a_lo), "r"(b_lo), "r"(accumulate), "r"(issue), "n"(DESC_HI), "n"(IDESC)
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(DESC_HI)
       : "memory");
 }
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -142,91 +122,125 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_add(int* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void red_relaxed_add(int* p, int v) {
+  asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Publication of a step: every storing thread makes ITS stores visible at gpu scope (all of them in parallel, ~one L2 round trip in
+// total), the epilogue barrier orders those fences before the leader's relaxed increment of the step counter.  (One releasing
+// increment by the leader after the barrier had to wait for the stores of all 320 threads on its own: 1.7 k cycles forward, 3.8 k
+// backward in the per-step timeline.)
+__device__ __forceinline__ void publish_fence() {
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-__device__ __forceinline__ void cell_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// 8 fp32 -> 8 bf16 hi + 8 bf16 lo (x = hi + lo to ~2^-17), as two 16-byte vectors
-__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
-    const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * k] - __low2float(hh), x[2 * k + 1] - __high2float(hh));
-    h[k] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[k] = *reinterpret_cast<const uint32_t*>(&ll);
+__device__ __forceinline__ void epi_bar_all() { asm volatile("bar.sync 1, 320;" ::: "memory"); }      // the 10 epilogue warps
+__device__ __forceinline__ void reader_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }       // the 4 TMEM-reader warps
+// ---- distributed shared memory (cluster of L_KSPLIT CTAs, backward) ----
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+static __device__ __noinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("hiecoattn lstm: cluster barrier wait timed out (tag %d, block %d, thread %d)\n", tag, blockIdx.x, threadIdx.x);
+      __trap();
+    }
   }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// MC = true (launched as clusters of L_CL CTAs = L_CL unit blocks of ONE row tile): the streamed operand of a step is the same for
-// all CTAs of a row tile, so every CTA loads 1 / L_CL of each ring slot and multicasts it to the whole cluster.  A slot is free once
-// ALL CTAs of the cluster have read it (their MMA completions are multicast to everybody's empty barrier, count L_CL); every CTA still
-// arms its own full barrier with the bytes of the whole slot.  Per SM this divides the TMA requests by L_CL and the L2 -> SM traffic of
-// the recurrence by the cluster's deduplication (the per-step stream of the [rows x 4H] gate gradients bounded the backward kernel).
-//
-// STK = true (backward, row tiles of at most 64 rows): the hi and lo planes of the streamed operand are stacked along M -- one 128-row
-// tile per k-block (AS map) -- so ONE MMA of width 2 BN per k-step yields x_hi.[W_hi | W_lo] in lanes 0..63 and x_lo.[W_hi | W_lo] in lanes
-// 64..127, instead of two MMAs.  The backward recurrence issues 4H / 16 k-steps per step of tiny MMAs (N = 32 / 16) and is bound by their
-// issue rate (~47 clock ticks per instruction from the single issuing thread, measured), so halving the instruction count is what counts;
-// the x_lo.W_hi block is handed from the warps of lanes 64..127 to the owners of the rows through shared memory.
-template <bool BWD, bool MC, bool STK = false>
+// 2 fp32 -> bf16 hi pair + bf16 lo pair (x = hi + lo to ~2^-17)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+  const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __low2float(hh), x1 - __high2float(hh));
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
+
+template <bool BWD>
 __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_constant__ LstmMaps maps, const LstmParams p) {
-  static_assert(!STK || (BWD && !MC), "the stacked variant is the backward kernel without multicast");
   pdl_enter();
-  constexpr int BN = BWD ? L_UNITS : 4 * L_UNITS;         // accumulator columns: dh of 16 units / 4 gates of 16 units
-  constexpr uint32_t W_KB_PLANE = BN * L_BK * 2;          // one plane of one resident k-block
-  constexpr uint32_t TMEM_COLS = BWD ? 32 : 128;             // [x.W_hi | x.W_lo] column blocks
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  __shared__ __align__(8) uint64_t bars[2 * L_MAX_STAGES + 2];
+  __shared__ __align__(8) uint64_t bars[L_KB_MAX + 3];
   __shared__ uint32_t tmem_ptr_smem;
   __shared__ int s_maxlen;
-  __shared__ int s_nact[L_TMAX];     // rows of this tile still running at step t (1 + the last row with len > t)
-  __shared__ __align__(16) float s_xch[STK ? 2 * 64 * 8 : 4];   // stacked variant: x_lo.W_hi blocks, [unit half][row][8 units]
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
-  auto empty_bar = [&](int s) { return smem_u32(&bars[L_MAX_STAGES + s]); };
-  const uint32_t w_bar = smem_u32(&bars[2 * L_MAX_STAGES]), tmem_full = smem_u32(&bars[2 * L_MAX_STAGES + 1]);
-  const uint32_t stage_bytes = p.stage_bytes;
+  auto full_bar = [&](int kb) { return smem_u32(&bars[kb]); };
+  const uint32_t w_bar = smem_u32(&bars[L_KB_MAX]), tmem_full = smem_u32(&bars[L_KB_MAX + 1]), red_bar = smem_u32(&bars[L_KB_MAX + 2]);
 
-  const int mi = blockIdx.x / p.tiles_n, ni = blockIdx.x - mi * p.tiles_n;
+  // which row tile / unit block / contraction slice this CTA is
+  int mi, ub, jg = 0, w_row0, w_col0;
+  if constexpr (BWD) {
+    const int per = p.ctas_per_tile;                      // 4 * unit groups
+    mi = blockIdx.x / per;
+    const int r = blockIdx.x - mi * per;
+    const int ug = r / L_KSPLIT;
+    jg = r - ug * L_KSPLIT;                               // == %cluster_ctarank (the cluster is 4 consecutive CTAs)
+    ub = ug * L_KSPLIT + jg;                              // unit block whose cell math this CTA owns (may lie beyond H: no cell work then)
+    w_row0 = ug * L_WROWS;                                // resident tile: rows = the 64 units of the group, columns = quarter jg of 4H
+    w_col0 = jg * p.H;
+  } else {
+    mi = blockIdx.x / p.ctas_per_tile;
+    ub = blockIdx.x - mi * p.ctas_per_tile;
+    w_row0 = ub * L_WROWS;                                // resident tile: the 64 gate rows of the unit block, all H columns
+    w_col0 = 0;
+  }
   const int m0 = (p.tile0 + mi) * p.rpt;
   int* const counters = p.counters + (int64_t)(p.tile0 + mi) * p.T;
-  // (clock64 stamps for profiles/timeline_lstm.py: compiled in only with -DHCA_TC_TIMELINE=1, see build.py)
   long long* const tl = (HCA_TC_TIMELINE && blockIdx.x == 0) ? p.timeline : nullptr;
+  const uint32_t slot_bytes = (uint32_t)p.rpt * 2u * L_BK * 2u;            // one k-block of the streamed operand: [x_hi ; x_lo] rows x 128 B
   const uint32_t w_base = smem_base;
-  const uint32_t ring_base = smem_base + (uint32_t)p.kbn * 2u * W_KB_PLANE;
+  const uint32_t ring_base = w_base + (uint32_t)p.kbn * L_WKB_BYTES;
+  const uint32_t recv_base = ring_base + p.ring_bytes;                     // (backward only)
+  // staging tiles alias the ring: they are written after the step's last MMA has completed and read before the step is published,
+  // i.e. strictly between two uses of the ring (the next step's loads are issued only after every CTA of the row tile has published)
+  float* const stage = reinterpret_cast<float*>(smem_raw + (ring_base - smem_u32(smem_raw)));
+  const float* const recv = reinterpret_cast<const float*>(smem_raw + (recv_base - smem_u32(smem_raw)));
 
   if (threadIdx.x == 0) {
     s_maxlen = 0;
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), MC ? L_CL : 1);
-    }
+    for (int kb = 0; kb < p.kbn; ++kb) mbar_init(full_bar(kb), 1);
     mbar_init(w_bar, 1);
     mbar_init(tmem_full, 1);
+    mbar_init(red_bar, 2 * L_KSPLIT);                     // (backward) one arrival per sending warp (2) of every CTA of the cluster
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.A[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.X) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.W) : "memory");
   }
-  for (int i = threadIdx.x; i < L_TMAX; i += blockDim.x) s_nact[i] = 0;
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr_smem), TMEM_COLS);
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr_smem), L_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync_all();      // every CTA's barriers exist before a peer's multicast or commit can reach them
+  if constexpr (BWD) cluster_sync_all();     // every CTA's barriers exist before a peer can signal them
   tc_fence_after();
   // steps this row tile needs: the longest sequence among its rows (rows are independent, so other tiles may run longer)
   if ((int)threadIdx.x < p.rpt) {
     const int b = m0 + (int)threadIdx.x;
     if (b < p.B) {
       const int64_t l64 = p.lens[b];
-      const int l = (int)(l64 < 0 ? 0 : (l64 > p.T ? p.T : l64));
-      atomicMax(&s_maxlen, l);
-      for (int t = 0; t < l && t < L_TMAX; ++t) atomicMax(&s_nact[t], (int)threadIdx.x + 1);
+      atomicMax(&s_maxlen, (int)(l64 < 0 ? 0 : (l64 > p.T ? p.T : l64)));
     }
   }
   __syncthreads();
@@ -237,164 +251,120 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
   if (warp == 0) {
     // ============================================================ TMA producer (one elected lane, inline waits: uniform datapath)
     if (elect_one_sync()) {
-      mbar_expect_tx(w_bar, (uint32_t)p.kbn * 2u * W_KB_PLANE);
+      mbar_expect_tx(w_bar, (uint32_t)p.kbn * L_WKB_BYTES);
       for (int kb = 0; kb < p.kbn; ++kb)
-        for (int pl = 0; pl < 2; ++pl)
-          tma_load_4d(w_base + (uint32_t)(kb * 2 + pl) * W_KB_PLANE, &maps.W, w_bar, kb * L_BK, ni * BN, pl, 0);
-      int s = 0;
-      uint32_t ph = 0;
+        for (int pl = 0; pl < 2; ++pl)        // (rows / columns beyond the matrix arrive as zeros: out-of-bounds fill)
+          tma_load_4d(w_base + (uint32_t)kb * L_WKB_BYTES + (uint32_t)pl * (L_WKB_BYTES / 2), &maps.W, w_bar, w_col0 + kb * L_BK, w_row0, pl, 0);
       for (int n = 0; n < rounds; ++n) {
         // forward round n computes step t = n + 1 from h_n (slot n + 1, published at step n);
         // backward round n computes step t = steps - 2 - n from the gate gradients of step t + 1 (slot t + 1)
         const int dep = BWD ? steps - 1 - n : n;
         const int slot = BWD ? dep : n + 1;
-        const int t_cur = BWD ? steps - 2 - n : n + 1;            // the step this round computes
-        // rows of the tile that are still inside their sequence at that step: the others need no operand rows (their
-        // accumulator rows are never used), so the smallest of the three boxes that covers the running rows is loaded
-        const int nrun = (p.T <= L_TMAX) ? s_nact[t_cur] : p.rpt;
-        const int bi = nrun <= p.box_rows[2] ? 2 : (nrun <= p.box_rows[1] ? 1 : 0);
-        const uint32_t plane_bytes = (uint32_t)p.box_rows[bi] * L_BK * 2;      // one k-block of one plane in the chosen box
         const int* cnt = counters + dep;
-        if (ld_acquire(cnt) < p.tiles_n) {           // bounded spin: a protocol bug must trap, never hang the device
+        if (ld_acquire(cnt) < p.ctas_per_tile) {     // bounded spin: a protocol bug must trap, never hang the device
           const long long t0 = clock64();
-          while (ld_acquire(cnt) < p.tiles_n) {
-            __nanosleep(20);
+          while (ld_acquire(cnt) < p.ctas_per_tile) {
             if (clock64() - t0 > 4000000000LL) {
               printf("hiecoattn lstm: step counter wait timed out (block %d, round %d)\n", blockIdx.x, n);
               __trap();
             }
           }
         }
-        fence_proxy_async_global();                  // peers wrote through the generic proxy; TMA reads through the async proxy
+        fence_proxy_async_all();                     // peers wrote through the generic proxy; TMA reads (and overwrites the staging tiles) through the async proxy
         if (tl && n < 7) tl[n * 8 + 0] = clock64();
-        for (int sl = 0; sl < p.nslots; ++sl) {
-          mbar_spin(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), STK ? (uint32_t)p.nkb * 16384u : 2u * (uint32_t)p.nkb * plane_bytes);   // (k-blocks beyond K arrive as fill: full box bytes)
-          const uint32_t dst = ring_base + (uint32_t)s * stage_bytes;
-          if constexpr (STK) {
-            // (the expect_tx above counted 2 nkb plane tiles of the chosen row box; the stacked box is nkb tiles of 128 rows)
-            tma_load_5d(dst, &maps.AS, full_bar(s), 0, m0, 0, sl * p.nkb, slot);
-          } else if constexpr (MC) {
-            // this CTA's share of the slot: pieces (plane, k-block) cr, cr + L_CL, ... -- one box each, multicast to the cluster
-            const int cr = (int)cluster_ctarank();
-            for (int piece = cr; piece < 2 * p.nkb; piece += L_CL) {
-              const int pl = piece / p.nkb, j = piece - pl * p.nkb;
-              tma_load_5d_mc(dst + (uint32_t)pl * p.lo_off + (uint32_t)j * plane_bytes, &maps.A1[bi], full_bar(s), 0, m0, sl * p.nkb + j, slot, pl,
-                             (uint16_t)((1u << L_CL) - 1u));
-            }
-          } else {
-            tma_load_5d(dst, &maps.A[bi], full_bar(s), 0, m0, sl * p.nkb, slot, 0);
-            tma_load_5d(dst + p.lo_off, &maps.A[bi], full_bar(s), 0, m0, sl * p.nkb, slot, 1);
-          }
-          if (++s == p.stages) { s = 0; ph ^= 1; }
+        for (int kb = 0; kb < p.kbn; ++kb) {
+          mbar_expect_tx(full_bar(kb), slot_bytes);
+          tma_load_4d(ring_base + (uint32_t)kb * slot_bytes, &maps.X, full_bar(kb), w_col0 + kb * L_BK, m0, 0, slot);
         }
         if (tl && n < 7) tl[n * 8 + 1] = clock64();
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(L_BM >> 4) << 24);
-    constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(L_BM >> 4) << 24);
+    // ============================================================ MMA issuer (one elected thread: descriptors stay in uniform registers)
     constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    // The whole loop runs in ONE elected thread with inline waits: inside such a region every value is trivially warp-uniform, so
-    // ptxas builds the descriptors with uniform-datapath adds and the UTCHMMAs issue back to back (the per-instruction elect /
-    // predicate forms cost ~75 cycles per MMA, which bounded the recurrence: its MMAs are small and many).
     if (elect_one_sync()) {
       mbar_spin(w_bar, 0);
       tc_fence_after();
-      int s = 0;
-      uint32_t ph = 0;
       const uint32_t d_tmem = *reinterpret_cast<volatile uint32_t*>(&tmem_ptr_smem);
-      const uint32_t a_ring = ((ring_base & 0x3FFFFu) >> 4) | (1u << 16);
-      const uint32_t w_res = ((w_base & 0x3FFFFu) >> 4) | (1u << 16);
-      const uint32_t a_lo = p.lo_off >> 4;
+      const uint32_t a_res = ((w_base & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_ring = ((ring_base & 0x3FFFFu) >> 4) | (1u << 16);
       for (int n = 0; n < rounds; ++n) {
-        // the tiles of a slot are packed with the pitch of the box that was loaded (the producer picks the same box: both read s_nact)
-        const int t_cur = BWD ? steps - 2 - n : n + 1;
-        const int nrun = (p.T <= L_TMAX) ? s_nact[t_cur] : p.rpt;
-        const int bi = nrun <= p.box_rows[2] ? 2 : (nrun <= p.box_rows[1] ? 1 : 0);
-        const uint32_t tile16 = STK ? (16384u >> 4) : (((uint32_t)p.box_rows[bi] * L_BK * 2) >> 4);
-        for (int sl = 0; sl < p.nslots; ++sl) {
-          mbar_spin(full_bar(s), ph);
+        for (int kb = 0; kb < p.kbn; ++kb) {
+          mbar_spin(full_bar(kb), (uint32_t)(n & 1));
           tc_fence_after();
-          if (tl && n < 7 && sl == 0) tl[n * 8 + 2] = clock64();
-          const uint32_t a_slot = a_ring + (uint32_t)s * (stage_bytes >> 4);
-          for (int j = 0; j < p.nkb; ++j) {
-            const int kb = sl * p.nkb + j;
-            const uint32_t au = a_slot + (uint32_t)j * tile16;
-            const uint32_t bu = w_res + (uint32_t)kb * (2u * W_KB_PLANE >> 4);
-            const int nks = max(0, min(L_BK / 16, (p.K - kb * L_BK + 15) / 16));
+          if (tl && n < 7 && kb == 0) tl[n * 8 + 2] = clock64();
+          const uint32_t au = a_res + (uint32_t)kb * (L_WKB_BYTES >> 4);
+          const uint32_t bu = b_ring + (uint32_t)kb * (slot_bytes >> 4);
+          const int nks = max(0, min(L_BK / 16, (p.K - kb * L_BK + 15) / 16));
 #pragma unroll
-            for (int ks = 0; ks < L_BK / 16; ++ks) {
-              if (ks < nks) {
-                // The hi and lo planes of the resident slice lie back to back (BN + BN rows), so ONE MMA of width 2 BN gives
-                // x_hi.W_hi (columns 0..BN-1) and x_hi.W_lo (columns BN..2BN-1); a second MMA of width BN adds x_lo.W_hi.
-                umma_bf16_one<desc_hi, idesc2>(d_tmem, au + ks * 2, bu + ks * 2, (kb | ks) != 0 ? 1u : 0u);
-                if constexpr (!STK) umma_bf16_one<desc_hi, idesc>(d_tmem, au + a_lo + ks * 2, bu + ks * 2, 1u);
-              }
-            }
-          }
-          if constexpr (MC) umma_commit_mc(empty_bar(s), (uint16_t)((1u << L_CL) - 1u));   // the slot is free when the whole cluster has read it
-          else umma_commit(empty_bar(s));
-          if (++s == p.stages) { s = 0; ph ^= 1; }
+          for (int ks = 0; ks < L_BK / 16; ++ks)
+            if (ks < nks) umma_bf16_rt<desc_hi>(d_tmem, au + ks * 2, bu + ks * 2, p.idesc, (kb | ks) != 0 ? 1u : 0u);
         }
         if (tl && n < 7) tl[n * 8 + 3] = clock64();
         umma_commit(tmem_full);
       }
     }
   } else {
-    // ============================================================ cell epilogue: thread = (batch row, 8 hidden units)
-    const int eg = (warp - 2) >> 2;                 // which half of the CTA's 16 units
-    const int q = warp & 3;                         // TMEM lane quadrant
-    const int r = q * 32 + lane;
-    const int b = m0 + r;
-    const bool row_ok = r < p.rpt && b < p.B;
+    // ============================================================ epilogue: 10 warps; thread e = (batch row b, unit pair up)
+    const int e = (int)threadIdx.x - 64;
+    const int b_loc = e >> 3, up = e & 7;
+    const int b = m0 + b_loc;
+    const bool row_ok = b_loc < p.rpt && b < p.B;
+    const bool unit_ok = ub * L_UNITS < p.H;              // (H % 16 == 0: a unit block is entirely inside or outside)
+    const bool cell_ok = row_ok && unit_ok;
     int len_b = 0;
     if (row_ok) {
       const int64_t l = p.lens[b];
       len_b = (int)(l < 0 ? 0 : (l > p.T ? p.T : l));
     }
-    const bool leader = (threadIdx.x == 64);
+    const bool leader = (e == 0);
+    const bool reader = warp < 6;                         // warps 2..5 own the TMEM lane quadrants 2, 3, 0, 1
+    const int lrow = (warp & 3) * 32 + lane;              // accumulator lane (= weight row of the stacked [hi ; lo] tile) of a reader thread
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int H = p.H, H4 = 4 * p.H;
-    const int u0 = ni * L_UNITS + eg * 8;           // first of this thread's 8 units
-    const int g0 = ni * 4 * L_UNITS + eg * 32;      // first of its 32 gate columns ([unit][gate] order)
+    const int u0 = ub * L_UNITS + 2 * up;                 // first of this thread's 2 units
+    const int g0 = 4 * u0;                                // first of its 8 gate columns ([unit][gate] order)
     const int64_t bt0 = (int64_t)b * p.T;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int nchunk = p.rpt >> 3;
     if constexpr (!BWD) {
-      float cst[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) cst[u] = 0.f;
+      float cst[2] = {0.f, 0.f};
       for (int t = 0; t < steps; ++t) {
-        float z[32];
+        float z[8];
         if (row_ok) {                                // x-projection + biases of this step (independent of the recurrence)
           const float4* gx = reinterpret_cast<const float4*>(p.act + (bt0 + t) * H4 + g0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 v = __ldg(gx + j);
-            z[4 * j] = v.x; z[4 * j + 1] = v.y; z[4 * j + 2] = v.z; z[4 * j + 3] = v.w;
-          }
+          const float4 v0 = __ldg(gx), v1 = __ldg(gx + 1);
+          z[0] = v0.x; z[1] = v0.y; z[2] = v0.z; z[3] = v0.w; z[4] = v1.x; z[5] = v1.y; z[6] = v1.z; z[7] = v1.w;
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) z[j] = 0.f;
+          for (int j = 0; j < 8; ++j) z[j] = 0.f;
         }
         if (t > 0) {
           mbar_wait(tmem_full, (uint32_t)((t - 1) & 1), 14);
           tc_fence_after();
           if (tl && leader && t - 1 < 7) tl[(t - 1) * 8 + 4] = clock64();
-          uint32_t v[32], v2[32];                   // x.W_hi block and x.W_lo block of this thread's 32 gate columns
-          __syncwarp();
-          tmem_ld32(lane_addr + (uint32_t)(eg * 32), v);
-          tmem_ld32(lane_addr + (uint32_t)(4 * L_UNITS + eg * 32), v2);
-          tc_fence_before();
-          float acc[32];
+          if (reader) {
+            // D[weight row][2 rpt columns]: columns [0, rpt) = . x_hi, [rpt, 2 rpt) = . x_lo.  stage[b][row] = their sum.
+            for (int c = 0; c < nchunk; ++c) {
+              uint32_t v[8], w2[8];
+              tmem_ld8(lane_addr + (uint32_t)(8 * c), v);
+              tmem_ld8(lane_addr + (uint32_t)(p.rpt + 8 * c), w2);
+              tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) z[j] += acc[j];
+              for (int j = 0; j < 8; ++j) stage[(8 * c + j) * L_PSTRIDE + lrow] = __uint_as_float(v[j]) + __uint_as_float(w2[j]);
+            }
+            tc_fence_before();
+          }
+          epi_bar_all();
+          if (row_ok) {                              // rows 0..63 = W_hi . x, rows 64..127 = W_lo . x, [unit][gate] order: 8 gates of the unit pair
+            const float4* sp = reinterpret_cast<const float4*>(stage + b_loc * L_PSTRIDE + 8 * up);
+            const float4 h0 = sp[0], h1 = sp[1], l0 = sp[L_WROWS / 4], l1 = sp[L_WROWS / 4 + 1];
+            z[0] += h0.x + l0.x; z[1] += h0.y + l0.y; z[2] += h0.z + l0.z; z[3] += h0.w + l0.w;
+            z[4] += h1.x + l1.x; z[5] += h1.y + l1.y; z[6] += h1.z + l1.z; z[7] += h1.w + l1.w;
+          }
         }
-        float h[8];
+        float h[2];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 2; ++u) {
           const float ig = sigmoid_fast(z[4 * u]), fg = sigmoid_fast(z[4 * u + 1]), gg = tanh_fast(z[4 * u + 2]),
                       og = sigmoid_fast(z[4 * u + 3]);
           cst[u] = fmaf(fg, cst[u], ig * gg);
@@ -402,115 +372,119 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
           z[4 * u] = ig; z[4 * u + 1] = fg; z[4 * u + 2] = gg; z[4 * u + 3] = og;
         }
         // publish h_t (slot t + 1) first: it is on the critical path of every CTA of this row tile
-        if (t < len_b && t + 1 < p.T) {                 // (rows past their end keep the zero slot: their h is never read)
-          uint4 hi, lo;
-          split8(h, hi, lo);
+        if (row_ok && t < len_b && t + 1 < p.T) {         // (rows past their end keep the zero slot: their h is never used)
+          uint32_t hi, lo;
+          split2(h[0], h[1], hi, lo);
           __nv_bfloat16* dst = p.hp + (bt0 + t + 1) * H + u0;
-          *reinterpret_cast<uint4*>(dst) = hi;
-          *reinterpret_cast<uint4*>(dst + p.hp_ps) = lo;
+          *reinterpret_cast<uint32_t*>(dst) = hi;
+          *reinterpret_cast<uint32_t*>(dst + p.hp_ps) = lo;
         }
         if (tl && leader && t >= 1 && t - 1 < 7) tl[(t - 1) * 8 + 5] = clock64();
-        fence_proxy_async_global();
-        cell_barrier();
+        publish_fence();
+        epi_bar_all();
         if (tl && leader && t >= 1 && t - 1 < 7) tl[(t - 1) * 8 + 6] = clock64();
         if (leader) {
-          red_release_add(counters + t, 1);      // release at gpu scope: covers the CTA's writes ordered before it by the barrier
+          red_relaxed_add(counters + t, 1);
           if (tl && t >= 1 && t - 1 < 7) tl[(t - 1) * 8 + 7] = clock64();
         }
-        if (row_ok) {                                // saved for backward + the module output
+        if (row_ok) {                                // saved for backward + the module output (off the critical path)
           float4* a4 = reinterpret_cast<float4*>(p.act + (bt0 + t) * H4 + g0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a4[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
-          float4* c4 = reinterpret_cast<float4*>(p.c + (bt0 + t) * H + u0);
-          c4[0] = make_float4(cst[0], cst[1], cst[2], cst[3]);
-          c4[1] = make_float4(cst[4], cst[5], cst[6], cst[7]);
-          float4* o4 = reinterpret_cast<float4*>(p.out + (bt0 + t) * H + u0);
+          a4[0] = make_float4(z[0], z[1], z[2], z[3]);
+          a4[1] = make_float4(z[4], z[5], z[6], z[7]);
+          *reinterpret_cast<float2*>(p.c + (bt0 + t) * H + u0) = make_float2(cst[0], cst[1]);
           const bool valid = t < len_b;
-          o4[0] = valid ? make_float4(h[0], h[1], h[2], h[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-          o4[1] = valid ? make_float4(h[4], h[5], h[6], h[7]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float2*>(p.out + (bt0 + t) * H + u0) = valid ? make_float2(h[0], h[1]) : make_float2(0.f, 0.f);
         }
       }
       if (row_ok) {                                  // steps nobody in this row tile reaches: zero output rows
-        for (int t = steps; t < p.T; ++t) {
-          float4* o4 = reinterpret_cast<float4*>(p.out + (bt0 + t) * H + u0);
-          o4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-          o4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int t = steps; t < p.T; ++t) *reinterpret_cast<float2*>(p.out + (bt0 + t) * H + u0) = make_float2(0.f, 0.f);
       }
     } else {
-      float dcn[8], dbacc[32];
+      float dcn[2] = {0.f, 0.f}, dbacc[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) dcn[u] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) dbacc[j] = 0.f;
+      for (int j = 0; j < 8; ++j) dbacc[j] = 0.f;
       for (int t = steps - 1; t >= 0; --t) {
-        const bool valid = row_ok && t < len_b;
-        float a[32], ct[8], cp[8], dh[8];
+        const bool valid = cell_ok && t < len_b;
+        float a[8], ct[2] = {0.f, 0.f}, cp[2] = {0.f, 0.f}, dh[2] = {0.f, 0.f};
         if (valid) {
           const float4* a4 = reinterpret_cast<const float4*>(p.act + (bt0 + t) * H4 + g0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 v = __ldg(a4 + j);
-            a[4 * j] = v.x; a[4 * j + 1] = v.y; a[4 * j + 2] = v.z; a[4 * j + 3] = v.w;
-          }
-          const float4* c4 = reinterpret_cast<const float4*>(p.c + (bt0 + t) * H + u0);
-          const float4 c0 = __ldg(c4), c1 = __ldg(c4 + 1);
-          ct[0] = c0.x; ct[1] = c0.y; ct[2] = c0.z; ct[3] = c0.w; ct[4] = c1.x; ct[5] = c1.y; ct[6] = c1.z; ct[7] = c1.w;
+          const float4 v0 = __ldg(a4), v1 = __ldg(a4 + 1);
+          a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
+          const float2* c2 = reinterpret_cast<const float2*>(p.c + (bt0 + t) * H + u0);
+          const float2 c0 = __ldg(c2);
+          ct[0] = c0.x; ct[1] = c0.y;
           if (t > 0) {
-            const float4 p0 = __ldg(c4 - H / 4), p1 = __ldg(c4 - H / 4 + 1);
-            cp[0] = p0.x; cp[1] = p0.y; cp[2] = p0.z; cp[3] = p0.w; cp[4] = p1.x; cp[5] = p1.y; cp[6] = p1.z; cp[7] = p1.w;
-          } else {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) cp[u] = 0.f;
+            const float2 p0 = __ldg(c2 - H / 2);
+            cp[0] = p0.x; cp[1] = p0.y;
           }
-          const float4* d4 = reinterpret_cast<const float4*>(p.dout + (bt0 + t) * H + u0);
-          const float4 d0 = __ldg(d4), d1 = __ldg(d4 + 1);
-          dh[0] = d0.x; dh[1] = d0.y; dh[2] = d0.z; dh[3] = d0.w; dh[4] = d1.x; dh[5] = d1.y; dh[6] = d1.z; dh[7] = d1.w;
+          const float2 d0 = __ldg(reinterpret_cast<const float2*>(p.dout + (bt0 + t) * H + u0));
+          dh[0] = d0.x; dh[1] = d0.y;
         }
-        if (t < steps - 1) {                         // + W_hh^T dz_{t+1}
-          mbar_wait(tmem_full, (uint32_t)((steps - 2 - t) & 1), 15);
+        if (t < steps - 1) {                         // + W_hh^T dz_{t+1}: this CTA's quarter of the contraction, then the cluster's other three
+          const int n = steps - 2 - t;
+          mbar_wait(tmem_full, (uint32_t)(n & 1), 15);
           tc_fence_after();
-          if (tl && leader && steps - 2 - t < 7) tl[(steps - 2 - t) * 8 + 4] = clock64();
-          uint32_t v[8], v2[8];                    // columns 0..15: x.W_hi ; columns 16..31: x.W_lo
-          __syncwarp();
-          tmem_ld8(lane_addr + (uint32_t)(eg * 8), v);
-          float acc[8];
-          if constexpr (STK) {
-            // lanes 0..63: x_hi.[W_hi | W_lo] of row r ; lanes 64..127: x_lo.[W_hi | W_lo] of row r - 64 (only its W_hi block is used)
-            if (q >= 2) {
-              float4* x4 = reinterpret_cast<float4*>(s_xch + ((eg * 64 + (r - 64)) * 8));
-              x4[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-              x4[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-            } else {
-              tmem_ld8(lane_addr + (uint32_t)(L_UNITS + eg * 8), v2);
+          if (tl && leader && n < 7) tl[n * 8 + 4] = clock64();
+          if (reader) {
+            // D[unit row of the stacked [hi ; lo] tile][2 rpt columns].  The lo half (lanes 64..127) goes through the local staging tile to the
+            // thread that holds the same unit's hi half, which adds the four partial products and sends the unit's [rpt] partial sums to the CTA
+            // that owns the unit's cell math (units 16 q .. 16 q + 15 of the group -> CTA q of the cluster), into ITS receive tile.
+            float acc[L_RPT_MAX];                      // this thread's accumulator row, hi + lo column halves added
+#pragma unroll
+            for (int c = 0; c < L_RPT_MAX / 8; ++c) {
+              if (c < nchunk) {
+                uint32_t v[8], w2[8];
+                tmem_ld8(lane_addr + (uint32_t)(8 * c), v);
+                tmem_ld8(lane_addr + (uint32_t)(p.rpt + 8 * c), w2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[8 * c + j] = __uint_as_float(v[j]) + __uint_as_float(w2[j]);
+              }
             }
             tc_fence_before();
-            cell_barrier();
-            if (q < 2) {
-              const float4* x4 = reinterpret_cast<const float4*>(s_xch + ((eg * 64 + r) * 8));
-              const float4 a0 = x4[0], a1 = x4[1];
-              const float lo[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            if (lrow >= L_WROWS) {
 #pragma unroll
-              for (int u = 0; u < 8; ++u) acc[u] = __uint_as_float(v[u]) + __uint_as_float(v2[u]) + lo[u];
-            } else {
-#pragma unroll
-              for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+              for (int c = 0; c < L_RPT_MAX / 8; ++c) {
+                if (c < nchunk) {
+                  float4* sp = reinterpret_cast<float4*>(stage + (lrow - L_WROWS) * L_RSTRIDE + 8 * c);
+                  sp[0] = make_float4(acc[8 * c], acc[8 * c + 1], acc[8 * c + 2], acc[8 * c + 3]);
+                  sp[1] = make_float4(acc[8 * c + 4], acc[8 * c + 5], acc[8 * c + 6], acc[8 * c + 7]);
+                }
+              }
             }
-          } else {
-            tmem_ld8(lane_addr + (uint32_t)(L_UNITS + eg * 8), v2);
-            tc_fence_before();
+            reader_bar();
+            if (lrow < L_WROWS) {
+              const uint32_t dst_cta = (uint32_t)(lrow / L_UNITS);
+              const uint32_t dst = mapa_u32(recv_base + (uint32_t)(((jg * L_UNITS + (lrow % L_UNITS)) * L_RSTRIDE) * 4), dst_cta);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc[u] = __uint_as_float(v[u]) + __uint_as_float(v2[u]);
+              for (int c = 0; c < L_RPT_MAX / 8; ++c) {
+                if (c < nchunk) {
+                  const float4* sp = reinterpret_cast<const float4*>(stage + lrow * L_RSTRIDE + 8 * c);
+                  const float4 s0 = sp[0], s1 = sp[1];
+                  st_cluster_v4(dst + (uint32_t)(32 * c), acc[8 * c] + s0.x, acc[8 * c + 1] + s0.y, acc[8 * c + 2] + s0.z, acc[8 * c + 3] + s0.w);
+                  st_cluster_v4(dst + (uint32_t)(32 * c + 16), acc[8 * c + 4] + s1.x, acc[8 * c + 5] + s1.y, acc[8 * c + 6] + s1.z, acc[8 * c + 7] + s1.w);
+                }
+              }
+              __syncwarp();
+              if (lane == 0) {                       // the warp's stores are ordered before its arrivals (release at cluster scope)
+#pragma unroll
+                for (uint32_t q = 0; q < (uint32_t)L_KSPLIT; ++q) mbar_arrive_cluster(mapa_u32(red_bar, q));
+              }
+            }
           }
+          mbar_wait_cluster(red_bar, (uint32_t)(n & 1), 16);         // all four partials of this CTA's 16 units have landed
           if (valid) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) dh[u] += acc[u];
+            for (int q = 0; q < L_KSPLIT; ++q) {
+              dh[0] += recv[(q * L_UNITS + 2 * up) * L_RSTRIDE + b_loc];
+              dh[1] += recv[(q * L_UNITS + 2 * up + 1) * L_RSTRIDE + b_loc];
+            }
           }
         }
-        float dz[32];
+        float dz[8];
         if (valid) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 2; ++u) {
             const float ig = a[4 * u], fg = a[4 * u + 1], gg = a[4 * u + 2], og = a[4 * u + 3];
             const float tc = tanh_fast(ct[u]);
             const float dc = fmaf(dh[u] * og, 1.f - tc * tc, dcn[u]);
@@ -522,55 +496,48 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dz[j] = 0.f;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) dcn[u] = 0.f;
+          for (int j = 0; j < 8; ++j) dz[j] = 0.f;
+          dcn[0] = dcn[1] = 0.f;
         }
-        if (row_ok) {                                // gate gradients of step t: operand of step t - 1 and of the weight-gradient GEMMs
+        if (cell_ok) {                               // gate gradients of step t: operand of step t - 1 and of the weight-gradient GEMMs
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) split2(dz[2 * k], dz[2 * k + 1], hi[k], lo[k]);
           __nv_bfloat16* dst = p.dgp + (bt0 + t) * H4 + g0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float x[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = dz[8 * j + k];
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            *reinterpret_cast<uint4*>(dst + 8 * j) = hi;
-            *reinterpret_cast<uint4*>(dst + p.dgp_ps + 8 * j) = lo;
-          }
+          *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(dst + p.dgp_ps) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dbacc[j] += dz[j];
+        for (int j = 0; j < 8; ++j) dbacc[j] += dz[j];
         const int rn = steps - 2 - t;
         if (tl && leader && rn >= 0 && rn < 7) tl[rn * 8 + 5] = clock64();
-        fence_proxy_async_global();
-        cell_barrier();
+        publish_fence();
+        epi_bar_all();
         if (tl && leader && rn >= 0 && rn < 7) tl[rn * 8 + 6] = clock64();
         if (leader) {
-          red_release_add(counters + t, 1);      // release at gpu scope: covers the CTA's writes ordered before it by the barrier
+          red_relaxed_add(counters + t, 1);
           if (tl && rn >= 0 && rn < 7) tl[rn * 8 + 7] = clock64();
         }
       }
-      // bias gradient: column sums over this warp's 32 rows, then one atomic per column
+      // bias gradient: the 8 threads of a batch row hold different unit pairs; sum over the rows of this warp (4 rows), then one atomic
+      // per column and warp
+      if (unit_ok && steps > 0) {
 #pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int j = 0; j < off; ++j) {
-          const float send = up ? dbacc[j] : dbacc[j + off];
-          const float keep = up ? dbacc[j + off] : dbacc[j];
-          dbacc[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        for (int j = 0; j < 8; ++j) {
+          float v = dbacc[j];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (lane < 8) atomicAdd(p.dbias + g0 + j, v);
         }
       }
-      if (steps > 0) atomicAdd(p.dbias + g0 + lane, dbacc[0]);
     }
     tc_fence_before();
   }
   __syncthreads();
-  if constexpr (MC) cluster_sync_all();      // no peer multicasts into, or signals, a CTA that has left
+  if constexpr (BWD) cluster_sync_all();     // no peer writes into, or signals, a CTA that has left
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc(tmem_base, L_TMEM_COLS);
   }
 }
 
@@ -720,180 +687,154 @@ int tc_splitk(int M, int N, int K) {
   return sk < 1 ? 1 : sk;
 }
 
-// Row tiling: as many row tiles as fit on the device next to each other (tiles * H/16 CTAs <= SMs), so that every tile is as
-// short as possible -- the per-step cost of a CTA is dominated by streaming its tile's rows of the exchanged operand.
-struct RowTiling {
-  int rpt, tiles, per_launch;
+// ---- launch geometry -------------------------------------------------------------------------------------------------
+// Every CTA of a launch waits for the other CTAs of its row tile (and, backward, of its cluster), so a launch may only hold as many
+// row tiles as the device can keep RESIDENT at once: the occupancy API says how many CTAs (forward) / clusters of 4 (backward) that
+// is for this kernel's shared-memory footprint; a shape that does not even fit one row tile is refused (hca_lstm_supported = 0,
+// the module then falls back to cuDNN) instead of being launched into a spin.  Row tiles are independent: when the batch needs
+// more tiles than fit, the launches simply follow each other.  Within that limit the tiles are made as short as the CTA count
+// allows (the per-step cost of a CTA grows with the rows it streams).
+struct Geometry {
+  int ctas_per_tile = 0, per_launch = 0, rpt = 0, tiles = 0, kbn = 0;
+  size_t smem = 0;
 };
-RowTiling row_tiling(int B, int H, int max_tiles_per_launch = 1 << 30) {
-  int sms = 148;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+// the streamed operand of one step (kbn k-blocks of [x_hi ; x_lo] rows), or the staging tile that aliases it if that is larger
+size_t ring_bytes(bool bwd, int kbn, int rpt) {
+  const size_t ring = (size_t)kbn * rpt * 2 * L_BK * 2;
+  const size_t stage = bwd ? (size_t)L_WROWS * L_RSTRIDE * 4 : (size_t)rpt * L_PSTRIDE * 4;
+  return (std::max(ring, stage) + 1023) / 1024 * 1024;
+}
+size_t rec_smem_bytes(bool bwd, int kbn, int rpt) {
+  return (size_t)kbn * L_WKB_BYTES + ring_bytes(bwd, kbn, rpt) + (bwd ? L_RECV_BYTES : 0) + 1024;
+}
+template <bool BWD>
+int resident_ctas(size_t smem) {
+  // (cached per device and footprint: the answer only depends on those)
+  static int cache[64][2] = {};
+  static size_t cache_smem[64][2] = {};
+  const int dev = current_device();
+  if (cache[dev][BWD ? 1 : 0] > 0 && cache_smem[dev][BWD ? 1 : 0] == smem) return cache[dev][BWD ? 1 : 0];
+  if (cudaFuncSetAttribute(lstm_rec_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_MAX_SMEM) != cudaSuccess) {
     cudaGetLastError();
-    sms = 148;
+    return 0;
   }
-  RowTiling r;
-  r.per_launch = std::max(1, std::min(sms / (H / L_UNITS), max_tiles_per_launch));
-  const int launches = ((B + L_BM - 1) / L_BM + r.per_launch - 1) / r.per_launch;
-  const int slots = launches * r.per_launch;
-  r.rpt = std::min(L_BM, (int)(((B + slots - 1) / slots + 7) / 8 * 8));
-  r.tiles = (B + r.rpt - 1) / r.rpt;
-  return r;
+  int n = 0;
+  if constexpr (BWD) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(L_KSPLIT * 64);
+    cfg.blockDim = dim3(L_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = L_KSPLIT; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, lstm_rec_kernel<true>, &cfg) != cudaSuccess) { cudaGetLastError(); clusters = 0; }
+    n = clusters * L_KSPLIT;
+  } else {
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_rec_kernel<false>, L_THREADS, smem) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    n = per_sm * sms;
+  }
+  { const int cap = HCA_ENV_INT("HCA_LSTM_MAX_CTAS", 0); if (cap > 0 && cap < n) n = cap; }      // tests: pretend the device is smaller
+  cache[dev][BWD ? 1 : 0] = n;
+  cache_smem[dev][BWD ? 1 : 0] = smem;
+  return n;
+}
+template <bool BWD>
+bool geometry(Geometry& g, int B, int H) {
+  g.kbn = (H + L_BK - 1) / L_BK;
+  g.ctas_per_tile = BWD ? L_KSPLIT * ((H + L_KSPLIT * L_UNITS - 1) / (L_KSPLIT * L_UNITS)) : H / L_UNITS;
+  // footprint at the longest row tile decides residency (a shorter tile only makes it smaller)
+  const int resident = resident_ctas<BWD>(rec_smem_bytes(BWD, g.kbn, L_RPT_MAX));
+  g.per_launch = resident / g.ctas_per_tile;
+  if (g.per_launch < 1) return false;
+  const int min_tiles = (B + L_RPT_MAX - 1) / L_RPT_MAX;
+  const int launches = (min_tiles + g.per_launch - 1) / g.per_launch;
+  const int slots = launches * g.per_launch;
+  g.rpt = std::min(L_RPT_MAX, (int)(((B + slots - 1) / slots + 7) / 8 * 8));
+  g.tiles = (B + g.rpt - 1) / g.rpt;
+  g.smem = rec_smem_bytes(BWD, g.kbn, g.rpt);
+  return g.smem <= (size_t)L_MAX_SMEM;
 }
 size_t counter_count(int B, int T) { return (size_t)((B + 7) / 8 + 1) * T; }
 
 template <bool BWD>
 int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64_t stream_ps, int stream_cols,
                const __nv_bfloat16* w_planes, int64_t w_ps, int w_rows, int w_cols, cudaStream_t s) {
-  constexpr int BN = BWD ? L_UNITS : 4 * L_UNITS;
+  Geometry g;
+  if (!geometry<BWD>(g, base.B, base.H))
+    return set_err(HCA_ERR_ARG, "lstm: hidden size %d needs %d co-resident CTAs per row tile, more than this device can hold", base.H, g.ctas_per_tile);
   LstmParams p = base;
   p.timeline = g_lstm_timeline;
-  p.tiles_n = base.H / L_UNITS;
-  p.K = BWD ? 4 * base.H : base.H;
-  p.kbn = (p.K + L_BK - 1) / L_BK;
-  // Backward, multicast variant (clusters of L_CL unit blocks of one row tile): taken when the unit blocks divide into clusters; the
-  // residency requirement (every CTA of a launch resident at once) then applies to whole clusters, so the row tiling is chosen for the
-  // number of clusters the device can hold (B200: 15 clusters of 8 at this shared-memory size -> 3 row tiles of 56 rows instead of 4
-  // of 40 for H = 512; the MMAs cost the same either way, M is 128 rows per tile).  opt-in: HCA_LSTM_MC=1.
-  bool mc = false;
-  int mc_tiles = 0;
-  if constexpr (BWD) {
-    mc = (p.tiles_n % L_CL) == 0;
-    // (measured at B = 160, H = 512: 287 us against 263 us without -- the stream is not what bounds the kernel, the MMA issue rate is:
-    // the variant stays as an opt-in, HCA_LSTM_MC=1)
-    { const char* ev = getenv("HCA_LSTM_MC"); if (!(ev && atoi(ev) == 1)) mc = false; }
-    if (mc) {
-      static bool mc_attr = false;
-      if (!mc_attr) {
-        HCA_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_MAX_SMEM));
-        mc_attr = true;
-      }
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)(L_CL * 64));
-      cfg.blockDim = dim3(L_THREADS);
-      cfg.dynamicSmemBytes = L_MAX_SMEM;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = L_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      int max_clusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&max_clusters, lstm_rec_kernel<true, true>, &cfg) != cudaSuccess) { cudaGetLastError(); max_clusters = 0; }
-      mc_tiles = max_clusters / (p.tiles_n / L_CL);
-      { const char* ev = getenv("HCA_LSTM_DEBUG"); if (ev && atoi(ev) != 0) fprintf(stderr, "lstm bwd: %d clusters of %d can be resident -> %d row tiles per launch\n", max_clusters, L_CL, mc_tiles); }
-      if (mc_tiles < 1) mc = false;
-    }
-  }
-  const RowTiling rt = mc ? row_tiling(base.B, base.H, mc_tiles) : row_tiling(base.B, base.H);
-  HCA_CHECK_ARG(p.tiles_n <= rt.per_launch * p.tiles_n, "lstm: hidden size %d needs more CTAs per row tile than the device has SMs", base.H);
-  p.rpt = rt.rpt;
-  p.box_rows[0] = rt.rpt;
-  p.box_rows[1] = std::min(rt.rpt, (rt.rpt / 2 + 7) / 8 * 8);
-  p.box_rows[2] = std::min(rt.rpt, (rt.rpt / 4 + 7) / 8 * 8);
-  // ring slots of the streamed operand: nkb k-blocks x (hi tile + lo tile) of rpt rows x 64 k (whole 8-row swizzle atoms: rpt % 8 == 0);
-  // as many k-blocks per slot as still leave two slots (one TMA box per plane and slot: few large boxes, not many small ones)
-  p.plane_bytes = (uint32_t)rt.rpt * L_BK * 2;
-  // (the MMA always reads 128 rows = 16 KB from a tile base: rows beyond the loaded ones are other tiles' data and only feed
-  // unused accumulator rows, but the last tile's read must stay inside the allocation, hence the tail padding)
-  const uint32_t tail_pad = 16u * 1024u - p.plane_bytes;
-  p.nkb = std::max(1, std::min(p.kbn, (int)((L_RING_BYTES - tail_pad) / (4 * p.plane_bytes))));
-  { const char* ev = getenv(BWD ? "HCA_LSTM_NKB_BWD" : "HCA_LSTM_NKB_FWD"); if (ev && atoi(ev) >= 1 && atoi(ev) < p.nkb) p.nkb = atoi(ev); }
-  p.nslots = (p.kbn + p.nkb - 1) / p.nkb;
-  p.lo_off = (uint32_t)p.nkb * p.plane_bytes;
-  p.stage_bytes = 2u * p.lo_off;
-  p.stages = std::max(2, std::min(L_MAX_STAGES, (int)((L_RING_BYTES - tail_pad) / p.stage_bytes)));
-  // stacked variant (backward, row tiles of <= 64 rows, see the kernel): one 128-row tile (16 KB) per k-block and ring slot
-  bool stk = BWD && !mc && rt.rpt <= 64 &&
-             (size_t)p.kbn * 2 * BN * L_BK * 2 + 2 * 16384u + 1024 <= (size_t)L_MAX_SMEM - 6144;
-  // (measured at B = 160, H = 512: 270 us against 262 us for the two-MMA form, and finer ring slots are slower still (282 / 334 us at 2 / 1
-  // k-blocks per slot): the backward step is a latency chain -- producer waits for the slot, TMA lands, issuer waits, MMAs complete, commit
-  // -- over a ring that the 128 KB resident W_hh slice leaves only 96 KB for, not an issue-rate or bandwidth limit.  Opt-in: HCA_LSTM_STK=1)
-  { const char* ev = getenv("HCA_LSTM_STK"); if (!(ev && atoi(ev) == 1)) stk = false; }
-  if (stk) {
-    p.nkb = 1;
-    p.nslots = p.kbn;
-    p.stage_bytes = 16384u;
-    p.lo_off = 8192u;
-    const size_t room = (size_t)L_MAX_SMEM - 6144 - 1024 - (size_t)p.kbn * 2 * BN * L_BK * 2;
-    p.stages = std::max(2, std::min(std::min(L_MAX_STAGES, 6), (int)(room / p.stage_bytes)));
-  }
-  const size_t smem = (size_t)p.kbn * 2 * BN * L_BK * 2 + (size_t)p.stages * p.stage_bytes + (stk ? 0 : tail_pad) + 1024;
+  p.K = base.H;
+  p.kbn = g.kbn;
+  p.rpt = g.rpt;
+  p.ctas_per_tile = g.ctas_per_tile;
+  p.ring_bytes = (uint32_t)ring_bytes(BWD, g.kbn, g.rpt);
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * g.rpt) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   LstmMaps maps;
-  for (int i = 0; i < 3; ++i) {
-    // streamed operand [2][B][T][cols] seen as (64 cols of a k-block, b, k-block, t, plane).  Dimension 0 is always a full 64:
-    // when cols is not a multiple of 64 the last k-block of a row runs into the following row -- finite data that only feeds
-    // k-slices the MMA warp predicates off (K is a multiple of 16); the buffers carry slack behind their last row.
-    const uint64_t dims[5] = {(uint64_t)L_BK, (uint64_t)base.B, (uint64_t)((stream_cols + L_BK - 1) / L_BK), (uint64_t)base.T, 2};
-    const uint64_t str[4] = {(uint64_t)base.T * stream_cols * 2, (uint64_t)L_BK * 2, (uint64_t)stream_cols * 2, (uint64_t)stream_ps * 2};
-    const uint32_t box[5] = {L_BK, (uint32_t)p.box_rows[i], (uint32_t)p.nkb, 1, 1};
-    HCA_TRY(tc_make_tmap(&maps.A[i], true, 5, stream_planes, dims, str, box, 3));
-    const uint32_t box1[5] = {L_BK, (uint32_t)p.box_rows[i], 1, 1, 1};
-    HCA_TRY(tc_make_tmap(&maps.A1[i], true, 5, stream_planes, dims, str, box1, 3));
-  }
-  if (stk) {
-    // (64 cols of a k-block, b, plane, k-block, t): the box (64, 64, 2, 1, 1) lands as [plane][row][64] = hi rows 0..63, lo rows 64..127
-    const uint64_t dims[5] = {(uint64_t)L_BK, (uint64_t)base.B, 2, (uint64_t)((stream_cols + L_BK - 1) / L_BK), (uint64_t)base.T};
-    const uint64_t str[4] = {(uint64_t)base.T * stream_cols * 2, (uint64_t)stream_ps * 2, (uint64_t)L_BK * 2, (uint64_t)stream_cols * 2};
-    const uint32_t box[5] = {L_BK, 64, 2, 1, 1};
-    HCA_TRY(tc_make_tmap(&maps.AS, true, 5, stream_planes, dims, str, box, 3));
-  } else {
-    maps.AS = maps.A[0];
+  {  // streamed operand [2][B][T][cols] as (col, b, plane, t); a box brings one k-block of both planes for the rows of a tile.  Rows
+     // beyond B and columns beyond `cols` arrive as zeros (out-of-bounds fill).
+    const uint64_t dims[4] = {(uint64_t)stream_cols, (uint64_t)base.B, 2, (uint64_t)base.T};
+    const uint64_t str[3] = {(uint64_t)base.T * stream_cols * 2, (uint64_t)stream_ps * 2, (uint64_t)stream_cols * 2};
+    const uint32_t box[4] = {L_BK, (uint32_t)g.rpt, 2, 1};
+    HCA_TRY(tc_make_tmap(&maps.X, true, 4, stream_planes, dims, str, box, 3));
   }
   {  // resident operand [2][rows][cols]: dims (cols, rows, 2, 1)
     const uint64_t dims[4] = {(uint64_t)w_cols, (uint64_t)w_rows, 2, 1};
     const uint64_t str[3] = {(uint64_t)w_cols * 2, (uint64_t)w_ps * 2, (uint64_t)w_ps * 4};
-    const uint32_t box[4] = {L_BK, BN, 1, 1};
+    const uint32_t box[4] = {L_BK, L_WROWS, 1, 1};
     HCA_TRY(tc_make_tmap(&maps.W, true, 4, w_planes, dims, str, box, 3));
   }
-  HCA_CHECK_ARG(smem <= (size_t)L_MAX_SMEM, "lstm: hidden size %d needs %zu bytes of shared memory", base.H, smem);
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[BWD ? 1 : 0]) {
-    HCA_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<BWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_MAX_SMEM));
-    attr_set[BWD ? 1 : 0] = true;
+  static bool attr_set[64][2] = {};
+  bool& attr_done = attr_set[current_device()][BWD ? 1 : 0];
+  if (!attr_done) {
+    HCA_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_MAX_SMEM));
+    attr_done = true;
   }
-  // every CTA of a launch must be resident at once (the CTAs of a row tile synchronise through global counters); row tiles
-  // are independent, so when the batch needs more tiles than fit the launches simply follow each other
-  for (int t0 = 0; t0 < rt.tiles; t0 += rt.per_launch) {
-    const int nm = std::min(rt.per_launch, rt.tiles - t0);
+  for (int t0 = 0; t0 < g.tiles; t0 += g.per_launch) {
+    const int nm = std::min(g.per_launch, g.tiles - t0);
     p.tile0 = t0;
-    if constexpr (BWD) {
-      if (mc) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(nm * p.tiles_n));
-        cfg.blockDim = dim3(L_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[2];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = L_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        HCA_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_kernel<true, true>, maps, p));
-        HCA_LAUNCHED();
-        continue;
-      }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nm * g.ctas_per_tile));
+    cfg.blockDim = dim3(L_THREADS);
+    cfg.dynamicSmemBytes = g.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[3];
+    int na = 0;
+    if (BWD) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = L_KSPLIT; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+      ++na;
     }
-    if constexpr (BWD) {
-      if (stk) {
-        static bool stk_attr = false;
-        if (!stk_attr) {
-          // (the exchange buffer adds 4 KB of static shared memory: the dynamic limit shrinks by as much)
-          HCA_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_MAX_SMEM - 6144));
-          stk_attr = true;
-        }
-        HCA_LAUNCH_K((lstm_rec_kernel<true, false, true>), nm * p.tiles_n, L_THREADS, smem, s, maps, p);
-        HCA_LAUNCHED();
-        continue;
-      }
+    if (HCA_ENV_INT("HCA_LSTM_COOP", 0) != 0) {       // experiment: let the driver gang-schedule the grid (cooperative launch)
+      attr[na].id = cudaLaunchAttributeCooperative;
+      attr[na].val.cooperative = 1;
+      ++na;
+    } else if (pdl_enabled()) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
     }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
     if (g_rec_events[BWD ? 1 : 0][0] && t0 == 0) HCA_CUDA(cudaEventRecord(g_rec_events[BWD ? 1 : 0][0], s));
-    HCA_LAUNCH_K((lstm_rec_kernel<BWD, false>), nm * p.tiles_n, L_THREADS, smem, s, maps, p);
+    HCA_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_kernel<BWD>, maps, p));
     HCA_LAUNCHED();
-    if (g_rec_events[BWD ? 1 : 0][1] && t0 + rt.per_launch >= rt.tiles) HCA_CUDA(cudaEventRecord(g_rec_events[BWD ? 1 : 0][1], s));
+    if (g_rec_events[BWD ? 1 : 0][1] && t0 + g.per_launch >= g.tiles) HCA_CUDA(cudaEventRecord(g_rec_events[BWD ? 1 : 0][1], s));
   }
   return 0;
+}
+
+bool device_holds(int B, int H) {
+  Geometry g;
+  return geometry<false>(g, B, H) && geometry<true>(g, B, H);
 }
 
 }  // namespace
@@ -913,7 +854,9 @@ extern "C" int hca_debug_lstm_events(void* ev_start, void* ev_stop, int which) {
   return 0;
 }
 
-extern "C" int hca_lstm_supported(int B, int T, int E, int H) { return hca::shape_ok(B, T, E, H) && hca::tc_available() ? 1 : 0; }
+extern "C" int hca_lstm_supported(int B, int T, int E, int H) {
+  return hca::shape_ok(B, T, E, H) && hca::tc_available() && hca::device_holds(B, H) ? 1 : 0;
+}
 
 extern "C" size_t hca_lstm_saved_bytes(int B, int T, int E, int H) { return hca::saved_bytes(B, T, E, H); }
 
