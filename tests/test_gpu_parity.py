@@ -180,6 +180,27 @@ def test_permuted_feature_view_and_lens_devices(syn):
         h.compare(ours, orc, tol=1e-3, check_dfeats=True)
 
 
+def test_channel_major_features_at_real_widths(syn):
+    """the image encoder's output is a [B, 512, 196] map viewed as [B, 196, 512] (model.py:217, strides (100352, 1, 196)).
+    That view goes straight into the operand planes (no dense fp32 copy): logits, every gradient and the feature gradient against the
+    fp64 oracle, and the same results as the contiguous layout (to the run-to-run noise of the fp32 atomics in the weighted sums)."""
+    h = _h()
+    d, N, T, vocab, K, mlp = 512, 196, 26, 10000, 1001, 1024
+    p = syn.make_params(d, vocab, K, mlp, seed=0)
+    x = syn.make_inputs(8, N, T, d, vocab, K, seed=12, dist="D2", min_len=1)
+    net = h.build_net(p, d, vocab, K, mlp)
+    orc = h.run_oracle(p, x, np.float64, need_dfeats=True)
+    before = h.PKG._lib.launch_count()
+    ours = h.run_ours(net, x, feats_grad=True, lens_on="both", feats_view="permuted")
+    n_perm = h.PKG._lib.launch_count() - before
+    h.compare(ours, orc, tol=1e-3, check_dfeats=True)
+    before = h.PKG._lib.launch_count()
+    dense = h.run_ours(net, x, feats_grad=True, lens_on="both")
+    n_dense = h.PKG._lib.launch_count() - before
+    assert n_perm == n_dense                       # one plane-split launch either way: no extra gather pass for the permuted view
+    assert np.allclose(ours["logits"], dense["logits"], rtol=1e-5, atol=1e-6) and np.allclose(ours["vhat"], dense["vhat"], rtol=1e-5, atol=1e-6)
+
+
 def test_misuse_raises_like_the_reference(syn):
     h = _h()
     d, N, T, vocab, K, mlp = 64, 7, 5, 50, 9, 32

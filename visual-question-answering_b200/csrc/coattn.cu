@@ -40,25 +40,32 @@ __global__ void __launch_bounds__(256) gather_strided_kernel(const float* __rest
   }
 }
 
-// Same for the layout the reference's image encoder hands over (model.py:217: a [B, d, N] feature map viewed as [B, N, d], i.e.
-// region stride 1 and channel stride N): a 32 x 32 shared-memory tile transpose, coalesced on both sides (the element-wise gather
-// above reads that layout with a stride of N floats per thread).
-__global__ void __launch_bounds__(256) gather_transposed_kernel(const float* __restrict__ V, int64_t sb, int64_t sd,
-                                                                float* __restrict__ out, int N, int d) {
+// The layout the reference's image encoder hands over (model.py:217: a [B, d, N] feature map viewed as [B, N, d], i.e. region stride 1
+// and channel stride N) goes STRAIGHT to the operand planes: a 64-channel x 32-region tile is read coalesced along the regions,
+// transposed in shared memory and written as bf16 hi / lo rows of the K-major [B*N, d] plane matrices (4-byte stores, 128 bytes per
+// warp and plane).  No dense fp32 copy of the features is made on this path (it used to cost a 64 MB write and a 64 MB read per step).
+__global__ void __launch_bounds__(256) split_planes_channel_major_kernel(const float* __restrict__ V, int64_t sb, int64_t sd,
+                                                                         __nv_bfloat16* __restrict__ planes, int64_t ld, int64_t ps, int N, int d) {
   pdl_enter();
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  __shared__ float tile[64][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const float* src = V + (int64_t)b * sb;
-  for (int i = ty; i < 32; i += 8) {
+  for (int i = ty; i < 64; i += 8) {
     const int c = c0 + i, n = n0 + tx;
-    if (c < d && n < N) tile[i][tx] = src[(int64_t)c * sd + n];
+    tile[i][tx] = (c < d && n < N) ? src[(int64_t)c * sd + n] : 0.f;
   }
   __syncthreads();
-  float* dst = out + (int64_t)b * N * d;
-  for (int i = ty; i < 32; i += 8) {
-    const int n = n0 + i, c = c0 + tx;
-    if (n < N && c < d) dst[(int64_t)n * d + c] = tile[tx][i];
+  for (int i = ty; i < 32; i += 8) {                 // one region row per warp and pass: lane = channel pair
+    const int n = n0 + i, c = c0 + 2 * tx;
+    if (n < N && c < d) {                            // (d % 8 == 0: a channel pair is inside or outside together)
+      const float x0 = tile[2 * tx][i], x1 = tile[2 * tx + 1][i];
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __low2float(hh), x1 - __high2float(hh));
+      __nv_bfloat16* dst = planes + ((int64_t)b * N + n) * ld + c;
+      *reinterpret_cast<__nv_bfloat162*>(dst) = hh;
+      *reinterpret_cast<__nv_bfloat162*>(dst + ps) = ll;
+    }
   }
 }
 
@@ -95,7 +102,8 @@ __device__ __forceinline__ void softmax_warp(const float* __restrict__ s, float 
 constexpr int ATTN_SPLIT = 4;
 __global__ void __launch_bounds__(256) attn_finish_kernel(const float* __restrict__ sv, const float* __restrict__ sq,
                                                           const float* __restrict__ cv, const float* __restrict__ cq,
-                                                          const float* __restrict__ V, const float* __restrict__ q0,
+                                                          const __nv_bfloat16* __restrict__ Vp, int64_t v_ld, int64_t v_ps,
+                                                          const float* __restrict__ q0,
                                                           const float* __restrict__ q1, const float* __restrict__ q2,
                                                           float* __restrict__ av, float* __restrict__ aq,
                                                           float* __restrict__ vhat, float* __restrict__ qhat,
@@ -112,7 +120,15 @@ __global__ void __launch_bounds__(256) attn_finish_kernel(const float* __restric
                                sp == 0 ? aq + ((int64_t)b * 3 + (w - 3)) * T : dump + 3 * N + (w - 3) * T);
   __syncthreads();
   const int d2 = d >> 1;
-  const float2* V2 = reinterpret_cast<const float2*>(V + (int64_t)b * N * d);
+  // V as its operand planes (hi + lo = the fp32 value to 2^-17): the same bytes as the fp32 rows, and the only copy of the image
+  // features that exists in the layout this loop wants when the caller handed over a channel-major view
+  const int64_t vl2 = v_ld >> 1;
+  const uint32_t* Vh = reinterpret_cast<const uint32_t*>(Vp + (int64_t)b * N * v_ld);
+  const uint32_t* Vl = reinterpret_cast<const uint32_t*>(Vp + v_ps + (int64_t)b * N * v_ld);
+  auto ldv = [&](int n, int c) {
+    const uint32_t h = __ldg(Vh + (int64_t)n * vl2 + c), l = __ldg(Vl + (int64_t)n * vl2 + c);
+    return make_float2(__uint_as_float(h << 16) + __uint_as_float(l << 16), __uint_as_float(h & 0xffff0000u) + __uint_as_float(l & 0xffff0000u));
+  };
   for (int c = threadIdx.x; c < d2; c += blockDim.x) {
     float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
     int n = sp;
@@ -120,7 +136,7 @@ __global__ void __launch_bounds__(256) attn_finish_kernel(const float* __restric
     for (; n + (UNR - 1) * ATTN_SPLIT < N; n += UNR * ATTN_SPLIT) {
       float2 v[UNR];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) v[u] = __ldg(V2 + (int64_t)(n + u * ATTN_SPLIT) * d2 + c);
+      for (int u = 0; u < UNR; ++u) v[u] = ldv(n + u * ATTN_SPLIT, c);
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         const int nn = n + u * ATTN_SPLIT;
@@ -131,7 +147,7 @@ __global__ void __launch_bounds__(256) attn_finish_kernel(const float* __restric
       }
     }
     for (; n < N; n += ATTN_SPLIT) {
-      const float2 v = __ldg(V2 + (int64_t)n * d2 + c);
+      const float2 v = ldv(n, c);
       const float w0 = a_sm[n], w1 = a_sm[N + n], w2 = a_sm[2 * N + n];
       a0.x = fmaf(w0, v.x, a0.x); a0.y = fmaf(w0, v.y, a0.y);
       a1.x = fmaf(w1, v.x, a1.x); a1.y = fmaf(w1, v.y, a1.y);
@@ -479,25 +495,25 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
   Workspace w(ws, ws_bytes);
   const int64_t BN = (int64_t)B * N, BT3 = (int64_t)B * 3 * T;
   const int T3 = 3 * T;
-  const float* Vd = V;
-  if (!v_is_dense(v_sb, v_sn, v_sd, N, d)) {
+  const Pl& Vp = sv_.V;
+  if (v_is_dense(v_sb, v_sn, v_sd, N, d)) {
+    HCA_TRY(split_to(Vp, V, d, s));
+  } else if (v_sn == 1 && B <= 65535) {       // channel-major feature map (the VGG encoder's [B, d, N] output viewed as [B, N, d])
+    HCA_LAUNCH_K((split_planes_channel_major_kernel), dim3((N + 31) / 32, (d + 63) / 64, B), 256, 0, s, V, v_sb, v_sd, Vp.p, Vp.ld, Vp.ps, N, d);
+    HCA_LAUNCHED();
+  } else {                                    // any other strides: dense copy first
     float* vc = w.take<float>((size_t)BN * d);
     if (!vc) return set_err(HCA_ERR_WORKSPACE, "coattn_fwd: workspace too small");
-    if (v_sn == 1 && B <= 65535) {            // channel-major feature map (the VGG encoder's view): tiled transpose
-      HCA_LAUNCH_K((gather_transposed_kernel), dim3((N + 31) / 32, (d + 31) / 32, B), 256, 0, s, V, v_sb, v_sd, vc, N, d);
-    } else {
-      HCA_LAUNCH_K((gather_strided_kernel), ew_grid(BN * d), 256, 0, s, V, v_sb, v_sn, v_sd, vc, B, N, d);
-    }
+    HCA_LAUNCH_K((gather_strided_kernel), ew_grid(BN * d), 256, 0, s, V, v_sb, v_sn, v_sd, vc, B, N, d);
     HCA_LAUNCHED();
-    Vd = vc;
+    HCA_TRY(split_to(Vp, vc, d, s));
   }
   Pl Wvp = take_pl(w, d, d), Wqp = take_pl(w, d, d);
   float* sc = w.take<float>((size_t)3 * B * (N + T));
   if (!Wqp.p || !sc) return set_err(HCA_ERR_WORKSPACE, "coattn_fwd: workspace too small (%zu bytes)", ws_bytes);
   float* svs = sc;                          // [B][3][N]
   float* sqs = sc + (size_t)3 * B * N;      // [B][3][T]
-  const Pl &Vp = sv_.V, &Qp = sv_.Q, &PVp = sv_.PV, &PQp = sv_.PQ, &Cp = sv_.C;
-  HCA_TRY(split_to(Vp, Vd, d, s));
+  const Pl &Qp = sv_.Q, &PVp = sv_.PV, &PQp = sv_.PQ, &Cp = sv_.C;
   HCA_TRY(launch_split_planes_stack3(q0, q1, q2, B, T, d, Qp.p, Qp.ld, Qp.ps, s));
   {  // both projection weights -> operand planes, one launch
     SplitBatch sb(s);
@@ -532,7 +548,7 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
   HCA_TRY(launch_hv_scores(hvp(Cp), hvp(PQp), hvp(PVp), wv, svs, B, N, T, d, s));
   const size_t smem = (size_t)6 * (N + T) * sizeof(float);
   HCA_CHECK_ARG(smem <= 48 * 1024, "coattn_fwd: N + T too large for the softmax kernel");
-  HCA_LAUNCH_K((attn_finish_kernel), dim3(B, ATTN_SPLIT), 256, smem, s, svs, sqs, cv, cq, Vd, q0, q1, q2, sv_.av, sv_.aq, vhat, qhat, B, N, T, d);
+  HCA_LAUNCH_K((attn_finish_kernel), dim3(B, ATTN_SPLIT), 256, smem, s, svs, sqs, cv, cq, Vp.p, Vp.ld, Vp.ps, q0, q1, q2, sv_.av, sv_.aq, vhat, qhat, B, N, T, d);
   HCA_LAUNCHED();
   return 0;
 }
