@@ -1,21 +1,12 @@
 #!/bin/bash
-# Quick GPU visit: parity tests, warm co-attention timing, the bench line, ncu launch list of the co-attention kernels.
+# quick GPU check: GEMM + parity tests, then the bench line (no baselines)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
-timeout 300 python profiles/prof_coattn.py 5 > gpurun_out/coattn_warm.log 2>&1; tail -3 gpurun_out/coattn_warm.log
-timeout 600 python bench.py --steps 20 --warmup 3 --skip-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-cat gpurun_out/bench.json | cut -c1-400; tail -3 gpurun_out/bench.err
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/coattn_launches.csv python profiles/prof_coattn.py 3 > /dev/null 2>&1
+timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_parity.py tests/test_gpu_lstm.py -q -m gpu -x 2>&1 | tail -3
+timeout 600 python bench.py --steps 100 --warmup 5 --skip-cpu-baseline --skip-gpu-baseline > gpurun_out/quick_bench.json 2> gpurun_out/quick_bench.err; echo "bench rc=$?"
 python - <<'PY'
-import csv
-rows=[r for r in csv.DictReader(l for l in open('gpurun_out/coattn_launches.csv') if not l.startswith('=='))]
-rows=[r for r in rows if r.get('Metric Name')=='gpu__time_duration.sum']
-n=len(rows)//3
-tot=0
-for r in rows[2*n:]:
-    v=float(r['Metric Value'].replace(',','')); us=v/1000 if r['Metric Unit'].startswith('n') else v
-    tot+=us
-    print(f"{us:8.1f} {r['Grid Size']:>12} {r['Kernel Name'][:90]}")
-print('total',tot)
+import json
+d=json.load(open('gpurun_out/quick_bench.json'))
+print('ms/step', round(d['ms_per_step'],4), 'samples/s', round(d['value']), 'e2e', round(d['e2e']['value']), 'launches', d['gpu_launches_per_step'])
+for l in d['roofline_legs']: print('  leg', l.get('name'), round(l.get('ms_per_launch',0)*1e3,1),'us frac', round(l.get('frac',0),4), 'issued', round(l.get('frac_issued',0),3))
+for r in d['kernel_shares']['top'][:14]: print(f"  {r['us_per_step']:8.1f} {r['launches_per_step']:4.0f}  {r['kernel'][:80]}")
 PY

@@ -406,14 +406,6 @@ TcPlanes plv(const Pl& pl, int64_t row0, int64_t rows_per_entry, int nbatch, int
   return t;
 }
 
-int tc_splitk(int M, int N, int K) {
-  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
-  if (tiles >= 96) return 1;
-  int sk = (148 + tiles - 1) / tiles;
-  const int maxk = (K + 255) / 256;
-  if (sk > maxk) sk = maxk;
-  return sk < 1 ? 1 : sk;
-}
 
 struct Saved {
   Pl V, Q, PV, PQ, C;

@@ -29,14 +29,6 @@ int make_planes(TcOperand& op, const float* src, int64_t ld, int rows, int cols,
   return 0;
 }
 
-int tc_splitk(int M, int N, int K) {
-  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
-  if (tiles >= 96) return 1;
-  int sk = (148 + tiles - 1) / tiles;
-  const int maxk = (K + 255) / 256;       // keep at least 4 k-blocks per split
-  if (sk > maxk) sk = maxk;
-  return sk < 1 ? 1 : sk;
-}
 }  // namespace
 }  // namespace hca
 

@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const TileCoord tc = decode(t);
         for (int it = 0; it < tc.num_kb; ++it) {
           mbar_spin(empty_bar(s), ph ^ 1);
+          if (tl && (p.dbg & 4) && t == sched0 && it < 16) tl[8 + it] = clock64();        // (HCA_TC_DBG=4: per-k-block stamps of the first tile)
           if constexpr (CG == 2) {
             // both CTAs' loads report to the leader's barrier (the MMA issuer waits there): it expects the bytes of both
             if (rank == 0) mbar_expect_tx(full_bar(s), 2 * stage_bytes);
@@ -288,6 +289,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           if (!(p.dbg & 1)) mbar_spin(full_bar(s), ph);
           tc_fence_after();
           if (tl && tile_it == 0 && it == 0) tl[2] = clock64();
+          if (tl && (p.dbg & 4) && tile_it == 0 && it < 16) tl[24 + it] = clock64();
           const uint32_t au = a_base + (uint32_t)s * (stage_bytes >> 4), bu = b_base + (uint32_t)s * (stage_bytes >> 4);
           // K slices of this block that hold data (the tail of K is zero-filled by TMA: skip those MMAs)
           const int kb = tc.kb_begin + it;
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               }
             }
           }
+          if (tl && (p.dbg & 4) && tile_it == 0 && it < 16) tl[40 + it] = clock64();
           if constexpr (CG == 2) umma_commit_2sm(empty_bar(s));   // frees the stage in both CTAs
           else umma_commit(empty_bar(s));       // frees the smem stage once the MMAs above have read it
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const uint32_t pstore_base = smem_base + p.off_pstore + (uint32_t)(eg * p.store_nbuf) * CHUNK_BYTES;
       const uint32_t aux_base = smem_base + p.off_aux + (uint32_t)eg * CHUNK_BYTES;
       int tli = 8;                            // debug timeline: stamps of this thread's first chunks (tl[8..63])
-      const bool tlt = tl && eg == 0 && et == 32;
+      const bool tlt = tl && eg == 0 && et == 32 && !(p.dbg & 4);
 #define HCA_TL_STAMP() do { if (tlt && tli < 64) tl[tli++] = clock64(); } while (0)
       int staged_n0 = -1;                     // n0 of the per-column vectors currently in shared memory
       // this group's column sums -> global, one atomic per column (only the columns of its own chunks), then cleared
@@ -963,6 +966,16 @@ bool planes_ok(const TcPlanes& t) {
 
 bool tc_available() { return get_encoder() != nullptr; }
 
+int tc_splitk(int M, int N, int K) {
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  const int sms = num_sms();
+  if (tiles * 3 >= sms * 2) return 1;             // the tiles alone fill most of a wave
+  int sk = sms / tiles;                           // floor: one work item per SM at most
+  const int maxk = (K + 255) / 256;               // keep at least 4 k-blocks per slice
+  if (sk > maxk) sk = maxk;
+  return sk < 1 ? 1 : sk;
+}
+
 int tc_make_tmap(void* tm, bool bf16, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
                  const uint32_t* box, int swizzle) {
   EncodeTiledFn enc = get_encoder();
@@ -1077,7 +1090,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
     pair = true;
     // the split is chosen for the pair grid: one 256 x 256 tile per pair and wave, at least 4 k-blocks per split
     const int t2 = (M / 256) * (N / 256), nc = num_sms() / 2, kbt = (K + 63) / 64;
-    int sk = (nc + t2 - 1) / t2;
+    int sk = nc / t2;                    // ONE wave: tiles * slices <= pairs (a ceil here left 2 of 76 items for a second wave: 2x the time)
     if (sk > kbt / 4) sk = kbt / 4;
     splitk = sk < 1 ? 1 : sk;
   }

@@ -102,6 +102,11 @@ struct SplitBatch {
   int flush();
 };
 
+// Split-K factor for an un-batched product whose output has few tiles: as many K slices as give every SM ONE work item -- never more
+// (tiles * slices > SMs means a second, nearly empty wave: measured as a 2x longer kernel on the weight gradients) -- with at least
+// 4 k-blocks (256 of K) per slice.
+int tc_splitk(int M, int N, int K);
+
 bool tc_available();   // TMA descriptor encoder resolved from the driver
 // generic tiled TMA descriptor (rank 2..5) for the other hand-written kernels: `tm` points at a CUtensorMap; dims / box in
 // elements (dim 0 innermost and contiguous), strides in BYTES for dims 1..rank-1; swizzle 0 none, 1 = 32 B, 2 = 64 B, 3 = 128 B

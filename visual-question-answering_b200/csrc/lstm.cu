@@ -678,14 +678,6 @@ TcOperand operand(const __nv_bfloat16* planes, int64_t ld, int64_t ps, int rows,
   o.planes = planes; o.ld = ld; o.plane_stride = ps; o.rows = rows; o.cols = cols; o.mn_major = mn_major;
   return o;
 }
-int tc_splitk(int M, int N, int K) {
-  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
-  if (tiles >= 96) return 1;
-  int sk = (148 + tiles - 1) / tiles;
-  const int maxk = (K + 255) / 256;
-  if (sk > maxk) sk = maxk;
-  return sk < 1 ? 1 : sk;
-}
 
 // ---- launch geometry -------------------------------------------------------------------------------------------------
 // Every CTA of a launch waits for the other CTAs of its row tile (and, backward, of its cluster), so a launch may only hold as many

@@ -529,8 +529,7 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
     ZeroBatch zb(s);
     for (int k = 1; k <= 3; ++k) {
       HCA_TRY(zb.add(dbs[k - 1], (size_t)E * 4));
-      const int tiles = ((E + 127) / 128) * ((k * E + 127) / 128);
-      sks[k - 1] = tiles >= 96 ? 1 : std::max(1, std::min((148 + tiles - 1) / tiles, (R + 255) / 256));
+      sks[k - 1] = tc_splitk(E, k * E, R);
       if (sks[k - 1] > 1) HCA_TRY(zb.add(dwr[k - 1], (size_t)E * k * E * 4));
     }
     HCA_TRY(zb.flush());
