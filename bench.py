@@ -187,9 +187,13 @@ class Stepper:
         rank = torch.distributed.get_rank() if world > 1 else 0
         for s in range(slots):
             x = syn.make_inputs(batch, CFG["N"], CFG["T"], CFG["d"], CFG["vocab"], CFG["K"], seed=seed0 + 17 * s + 1000 * rank)
-            host = {k: torch.from_numpy(v).pin_memory() for k, v in x.items()}
+            # loader-side staging buffers: page-locked, write-combined (HCA_STAGING=pinned: plain pin_memory())
+            if os.environ.get("HCA_STAGING", "wc") == "pinned":
+                host = {k: torch.from_numpy(v).pin_memory() for k, v in x.items()}
+            else:
+                host = {k: pkg.staging.staged(v, write_combined=True) for k, v in x.items()}
             dev = {k: v.to(device) for k, v in host.items()}
-            self.slots.append(dict(host=host, dev=dev, lens=pkg.QuestionLens(host["lens"], device, dev["lens"]), graph=None,
+            self.slots.append(dict(host=host, dev=dev, lens=pkg.QuestionLens(torch.from_numpy(x["lens"]), device, dev["lens"]), graph=None,
                                    loss=torch.zeros((), device=device)))
         self.use_graph = use_graph
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.slots[0]["host"].values())

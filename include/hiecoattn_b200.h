@@ -54,6 +54,11 @@ HCA_API int64_t hca_launch_count(void);
 HCA_API int hca_set_option(const char* name, const char* value);
 HCA_API const char* hca_get_option(const char* name);
 
+/* page-locked host staging buffers for the loader -> GPU hand-over of a step's inputs (replaces the pageable .to(device) copies of
+ * main.py:205-208); write_combined != 0: write-combined pages (CPU-write-only staging, cheaper for the device to read) */
+HCA_API int hca_pinned_alloc(size_t bytes, int write_combined, void** out);
+HCA_API int hca_pinned_free(void* p);
+
 /* ---- question encoder: embedding gather (replaces nn.Embedding, model.py:263,282) -------------- */
 /* out[r,:] = table[tokens[r],:] for r < rows; tokens int64 in [0,vocab).  E % 4 == 0. */
 HCA_API int hca_embedding_fwd(const int64_t* tokens, const float* table, float* out,

@@ -324,3 +324,22 @@ def test_two_rank_data_parallel_matches_single_rank(fused):
         assert res[r]["grad_err"] < 1e-4, res[r]
         assert res[r]["replicas_identical"]
         assert res[r]["step_err"] < 3e-2, res[r]
+
+
+def test_staging_buffers_are_pinned_and_copy_asynchronously():
+    """staging.staged(): library-allocated page-locked (write-combined) host tensors; the bytes survive the H2D copy, int64 included.
+    (torch's own ``is_pinned()`` only knows its caching host allocator; the driver recognises the pages as locked, which is what makes
+    ``copy_(non_blocking=True)`` a true asynchronous DMA.)"""
+    h = _h()
+    rng = np.random.RandomState(0)
+    a = rng.standard_normal((33, 196, 8)).astype(np.float32)
+    i = rng.randint(0, 1000, size=(33, 26)).astype(np.int64)
+    for wc in (True, False):
+        ta, ti = h.PKG.staging.staged(a, write_combined=wc), h.PKG.staging.staged(i, write_combined=wc)
+        assert ta.shape == a.shape and ti.dtype == torch.int64 and torch.equal(ta, torch.from_numpy(a))
+        da = torch.empty(a.shape, device="cuda")
+        di = torch.empty(i.shape, dtype=torch.int64, device="cuda")
+        da.copy_(ta, non_blocking=True)
+        di.copy_(ti, non_blocking=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(da.cpu().numpy(), a) and np.array_equal(di.cpu().numpy(), i)

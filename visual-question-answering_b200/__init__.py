@@ -5,11 +5,11 @@ op call and a missing build raises (there is no CPU fallback).  The directory na
 import it with ``importlib.import_module("visual-question-answering_b200")`` or through the root-level
 ``model.py`` shim, which is what the reference's ``main.py`` does (``from model import ...``).
 """
-from . import _lib, dp, modules, ops, optim, synthetic            # noqa: F401
+from . import _lib, dp, modules, ops, optim, staging, synthetic   # noqa: F401
 from .modules import (CrossEntropyLoss, HieCoAttnHotPath, HierarchicalCoAttentionNet, ImageBaselineEncoder, ImageCoAttentionEncoder,  # noqa: F401
                       MLPClassifier, ParallelCoAttention, PhraseConvPool, QuestionBaselineEncoder,
                       QuestionCoAttentionEncoder, QuestionLens, VQABaselineNet)
 
 __all__ = ["HierarchicalCoAttentionNet", "VQABaselineNet", "QuestionCoAttentionEncoder", "PhraseConvPool",
            "ParallelCoAttention", "MLPClassifier", "ImageCoAttentionEncoder", "ImageBaselineEncoder",
-           "QuestionBaselineEncoder", "HieCoAttnHotPath", "CrossEntropyLoss", "QuestionLens", "ops", "synthetic", "dp", "optim"]
+           "QuestionBaselineEncoder", "HieCoAttnHotPath", "CrossEntropyLoss", "QuestionLens", "ops", "synthetic", "dp", "optim", "staging"]

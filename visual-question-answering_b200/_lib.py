@@ -24,6 +24,8 @@ SIGNATURES = {
     "hca_launch_count": (_i64, []),
     "hca_set_option": (_i, [C.c_char_p, C.c_char_p]),
     "hca_get_option": (C.c_char_p, [C.c_char_p]),
+    "hca_pinned_alloc": (_i, [_sz, _i, C.POINTER(_p)]),
+    "hca_pinned_free": (_i, [_p]),
     "hca_embedding_fwd": (_i, [_p, _p, _p, _i64, _i, _i64, _p]),
     "hca_embedding_bwd": (_i, [_p, _p, _p, _i64, _i, _i64, _p]),
     "hca_phrase_conv_pool_workspace": (_sz, [_i, _i, _i]),

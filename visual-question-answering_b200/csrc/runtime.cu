@@ -97,6 +97,33 @@ int hca_set_option(const char* name, const char* value) {
   return hca::set_err(HCA_ERR_ARG, "hca_set_option: unknown option %s=%s", name, value);
 }
 
+// ---- host staging buffers ---------------------------------------------------------------------------------------
+// Page-locked host memory for the loader -> GPU hand-over of a step's inputs (reference main.py:205-208 copies pageable tensors with
+// .to(device)).  write_combined != 0 asks for write-combined pages: the CPU only ever WRITES a staging buffer (the loader fills it
+// once), and uncached write-combined pages are not snooped on the device's reads, which is what limits eight GPUs pulling 64 MB each
+// per step from one host.
+int hca_pinned_alloc(size_t bytes, int write_combined, void** out) {
+  if (!out || bytes == 0) return hca::set_err(HCA_ERR_ARG, "pinned_alloc: bad arguments");
+  void* p = nullptr;
+  const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+  cudaError_t e = cudaHostAlloc(&p, bytes, flags);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return hca::set_err(HCA_ERR_CUDA, "cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  *out = p;
+  return 0;
+}
+int hca_pinned_free(void* p) {
+  if (!p) return 0;
+  cudaError_t e = cudaFreeHost(p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return hca::set_err(HCA_ERR_CUDA, "cudaFreeHost failed: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
 const char* hca_get_option(const char* name) {
   if (name && strcmp(name, "gemm") == 0) return "tc";
   if (name && strcmp(name, "pdl") == 0) return hca::pdl_enabled() ? "1" : "0";
