@@ -6,10 +6,10 @@ import it with ``importlib.import_module("visual-question-answering_b200")`` or 
 ``model.py`` shim, which is what the reference's ``main.py`` does (``from model import ...``).
 """
 from . import _lib, dp, modules, ops, optim, staging, synthetic   # noqa: F401
-from .modules import (CrossEntropyLoss, HieCoAttnHotPath, HierarchicalCoAttentionNet, ImageBaselineEncoder, ImageCoAttentionEncoder,  # noqa: F401
+from .modules import (CrossEntropyLoss, HieCoAttnHotPath, InferenceSession, HierarchicalCoAttentionNet, ImageBaselineEncoder, ImageCoAttentionEncoder,  # noqa: F401
                       MLPClassifier, ParallelCoAttention, PhraseConvPool, QuestionBaselineEncoder,
                       QuestionCoAttentionEncoder, QuestionLens, VQABaselineNet)
 
 __all__ = ["HierarchicalCoAttentionNet", "VQABaselineNet", "QuestionCoAttentionEncoder", "PhraseConvPool",
            "ParallelCoAttention", "MLPClassifier", "ImageCoAttentionEncoder", "ImageBaselineEncoder",
-           "QuestionBaselineEncoder", "HieCoAttnHotPath", "CrossEntropyLoss", "QuestionLens", "ops", "synthetic", "dp", "optim", "staging"]
+           "QuestionBaselineEncoder", "HieCoAttnHotPath", "InferenceSession", "CrossEntropyLoss", "QuestionLens", "ops", "synthetic", "dp", "optim", "staging"]

@@ -273,6 +273,46 @@ class HieCoAttnHotPath(nn.Module):
         return (prob, idx, a_v, a_q) if return_attention else (prob, idx)
 
 
+class InferenceSession:
+    """The validation / serving call of the reference (main.py:301-335: ``eval()``, ``no_grad()``, ``model(image, question, ques_len)``
+    per batch) for ONE fixed shape, replayed from a CUDA graph: the ~40 kernel launches of a forward cost more host time than device
+    time at small batches (0.56 ms eager at batch 1), a replay costs one launch.
+
+    ``session = InferenceSession(net, batch, regions, tokens)`` captures ``net(feats, tokens, lens)`` on static buffers;
+    ``session(feats, tokens, lens)`` copies the inputs in (device or host tensors), replays, and returns the static ``[batch, K]`` logits
+    (clone them to keep them across calls).  Works for ``HieCoAttnHotPath`` (feature grids) -- the VGG trunk of the full wrapper is
+    stock cuDNN and can be captured the same way by passing images of the capture-time size."""
+
+    def __init__(self, net: nn.Module, batch: int, regions: int, tokens: int, device=None, feature_dim: Optional[int] = None):
+        self.net = net.eval()
+        dev = torch.device(device) if device is not None else next(net.parameters()).device
+        d = feature_dim or net.co_attention.hidden_dim
+        self.feats = torch.zeros(batch, regions, d, device=dev)
+        self.tokens = torch.ones(batch, tokens, dtype=torch.int64, device=dev)
+        self.lens_dev = torch.full((batch,), tokens, dtype=torch.int64, device=dev)
+        self._lens = QuestionLens(torch.full((batch,), tokens, dtype=torch.int64), dev, self.lens_dev)
+        self.max_len = tokens
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                                  # warm-up outside the capture (lazy initialisation, allocator)
+                self.net(self.feats, self.tokens, self._lens)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.logits = self.net(self.feats, self.tokens, self._lens)
+
+    @torch.no_grad()
+    def __call__(self, feats: Tensor, tokens: Tensor, lens) -> Tensor:
+        lens_cpu = lens.cpu if isinstance(lens, QuestionLens) else (lens.cpu() if lens.is_cuda else lens)
+        _check_lens(lens_cpu.to(torch.int64), self.max_len)       # what pack_padded_sequence raises on (model.py:287), checked on the host copy
+        self.feats.copy_(feats, non_blocking=True)
+        self.tokens.copy_(tokens, non_blocking=True)
+        self.lens_dev.copy_(lens.dev if isinstance(lens, QuestionLens) else lens, non_blocking=True)
+        self.graph.replay()
+        return self.logits
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Baseline network (reference model.py:10-151).  Not on the accelerated path (BASELINE.json config 2 only
 # times it for context); stock PyTorch layers with the reference's names so `from model import VQABaselineNet`
