@@ -370,6 +370,30 @@ def test_inference_predict_and_attention_maps(syn):
         assert h.rel(a_q[:, l].cpu().numpy(), np.asarray(c["aq"]).reshape(5, T)) < 1e-4
 
 
+def test_inference_session_replays_the_validation_forward(syn):
+    """InferenceSession (CUDA-graph replay of the eval() + no_grad() forward, main.py:301-335): same logits as the eager call and as the
+    fp64 oracle, for fresh inputs on every replay, with lengths given on the host, on the device, or as QuestionLens."""
+    h = _h()
+    d, N, T, vocab, K, mlp, B = 512, 196, 26, 1000, 1001, 1024, 24
+    p = syn.make_params(d, vocab, K, mlp, seed=0)
+    net = h.build_net(p, d, vocab, K, mlp).eval()
+    sess = h.PKG.InferenceSession(net, B, N, T)
+    p64 = {k: v.astype(np.float64) for k, v in p.items()}
+    for i, how in enumerate(("cpu", "cuda", "both")):
+        x = syn.make_inputs(B, N, T, d, vocab, K, seed=40 + i, dist="D2", min_len=1)
+        feats, tokens = torch.from_numpy(x["feats"]).cuda(), torch.from_numpy(x["tokens"]).cuda()
+        lens = torch.from_numpy(x["lens"])
+        lens = lens.cuda() if how == "cuda" else (h.PKG.QuestionLens(lens, "cuda") if how == "both" else lens)
+        got = sess(feats, tokens, lens).clone()
+        with torch.no_grad():
+            eager = net(feats, tokens, lens)
+        ref = h.O.hiecoattn_forward(p64, x["feats"].astype(np.float64), x["tokens"], x["lens"])
+        assert h.rel(got.cpu().numpy(), eager.cpu().numpy()) < 1e-5
+        assert h.rel(got.cpu().numpy(), ref) < 1e-3 and (got.argmax(1).cpu().numpy() == ref.argmax(1)).all()
+    with pytest.raises(RuntimeError):
+        sess(feats, tokens, torch.tensor([3] + [5] * (B - 1)))            # unsorted lengths are still refused (model.py:287)
+
+
 @pytest.mark.parametrize("seed", list(range(8)))
 def test_random_ragged_shapes_full_step(seed, syn):
     """Randomly drawn small shapes (ragged tiles everywhere: N, T, K, B not multiples of anything; d, mlp multiples of 8 as the

@@ -140,104 +140,109 @@ __global__ void __launch_bounds__(256) pool3_fwd_kernel(const float* __restrict_
   }
 }
 
-// The three pre-activations of channel triple e of row r in plain fp32 from the fp32 inputs (one warp), then tanh and the max again.
-__device__ __forceinline__ void fixup_one(int64_t r, int e, const float* __restrict__ x, int T, const float* __restrict__ w1,
-                                          const float* __restrict__ w2, const float* __restrict__ w3, const float* __restrict__ b1,
-                                          const float* __restrict__ b2, const float* __restrict__ b3, float* __restrict__ out,
-                                          uint8_t* __restrict__ idx, int E) {
+// One pre-activation of the concatenated [uni|bi|tri] axis (channel c of token row r) in plain fp32 from the fp32 inputs, by one warp;
+// every lane returns tanh(sum + bias).
+__device__ __forceinline__ float exact_channel(int64_t r, int c, const float* __restrict__ x, int T, const float* __restrict__ w1,
+                                               const float* __restrict__ w2, const float* __restrict__ w3, const float* __restrict__ b1,
+                                               const float* __restrict__ b2, const float* __restrict__ b3, int E) {
   const int lane = threadIdx.x & 31;
   const int t = (int)(r % T);
   const float* x0 = x + r * (int64_t)E;
   const bool has_m = t > 0, has_p = t + 1 < T;
-  float v[3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const int c = 3 * e + j;                      // channel of the concatenated [uni|bi|tri] axis
-    const int k = c / E + 1, o = c % E;           // which conv, which output channel
-    const float* wrow = (k == 1 ? w1 : (k == 2 ? w2 : w3)) + (int64_t)o * E * k;   // conv layout [C_in][k]: lane cc reads its k taps contiguously
-    // taps: k = 1: x[t] ; k = 2: x[t-1], x[t] ; k = 3: x[t-1], x[t], x[t+1] ; zeros outside [0, T)
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (k == 1) {
+  const int k = c / E + 1, o = c % E;             // which conv, which output channel
+  const float* wrow = (k == 1 ? w1 : (k == 2 ? w2 : w3)) + (int64_t)o * E * k;   // conv layout [C_in][k]: lane cc reads its k taps contiguously
+  // taps: k = 1: x[t] ; k = 2: x[t-1], x[t] ; k = 3: x[t-1], x[t], x[t+1] ; zeros outside [0, T)
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  if (k == 1) {
 #pragma unroll 4
-      for (int cc = lane; cc < E; cc += 32) a0 = fmaf(x0[cc], wrow[cc], a0);
-    } else if (k == 2) {
+    for (int cc = lane; cc < E; cc += 32) a0 = fmaf(x0[cc], wrow[cc], a0);
+  } else if (k == 2) {
 #pragma unroll 4
-      for (int cc = lane; cc < E; cc += 32) {
-        const float2 w = *reinterpret_cast<const float2*>(wrow + 2 * cc);
-        if (has_m) a0 = fmaf(x0[cc - E], w.x, a0);
-        a1 = fmaf(x0[cc], w.y, a1);
-      }
-    } else {
-#pragma unroll 4
-      for (int cc = lane; cc < E; cc += 32) {
-        const float wa = wrow[3 * cc], wb = wrow[3 * cc + 1], wc = wrow[3 * cc + 2];
-        if (has_m) a0 = fmaf(x0[cc - E], wa, a0);
-        a1 = fmaf(x0[cc], wb, a1);
-        if (has_p) a2 = fmaf(x0[cc + E], wc, a2);
-      }
+    for (int cc = lane; cc < E; cc += 32) {
+      const float2 w = *reinterpret_cast<const float2*>(wrow + 2 * cc);
+      if (has_m) a0 = fmaf(x0[cc - E], w.x, a0);
+      a1 = fmaf(x0[cc], w.y, a1);
     }
-    const float acc = warp_sum(a0 + a1 + a2);
-    v[j] = tanhf(acc + (k == 1 ? b1 : (k == 2 ? b2 : b3))[o]);
+  } else {
+#pragma unroll 4
+    for (int cc = lane; cc < E; cc += 32) {
+      const float wa = wrow[3 * cc], wb = wrow[3 * cc + 1], wc = wrow[3 * cc + 2];
+      if (has_m) a0 = fmaf(x0[cc - E], wa, a0);
+      a1 = fmaf(x0[cc], wb, a1);
+      if (has_p) a2 = fmaf(x0[cc + E], wc, a2);
+    }
   }
-  float best, mid;
-  int bi;
-  top2_of3(v[0], v[1], v[2], best, mid, bi);
-  if (lane == 0) {
-    out[r * E + e] = best;
-    idx[r * E + e] = (uint8_t)bi;
-  }
+  const float acc = warp_sum(a0 + a1 + a2);
+  return tanhf(acc + (k == 1 ? b1 : (k == 2 ? b2 : b3))[o]);
 }
 
-// Repairs the listed near-ties (one warp per entry).  When more were found than the list holds, the list is ignored and every element is
-// re-examined instead: each lane re-derives the band condition of one element from `cat`, the warp then repairs the flagged ones in turn.
-__global__ void __launch_bounds__(256) fixup_ties_kernel(const int* __restrict__ tie_list, const int* tie_count, int tie_cap,
-                                                         const float* __restrict__ cat, const int64_t* __restrict__ lens,
-                                                         const float* __restrict__ xn2, const float* __restrict__ wn,
-                                                         const float* __restrict__ x, int B, int T, const float* __restrict__ w1,
-                                                         const float* __restrict__ w2, const float* __restrict__ w3,
-                                                         const float* __restrict__ b1, const float* __restrict__ b2,
-                                                         const float* __restrict__ b3, float* __restrict__ out,
-                                                         uint8_t* __restrict__ idx, int E, int* __restrict__ stats) {
+// Repairs the listed near-ties: one block of 3 warps per entry, one warp per channel of the triple (the three dot products of up to 3E
+// terms run side by side instead of one after the other: the kernel is a latency chain, ~1000 entries for 148 SMs).  When more
+// near-ties were found than the list holds, the list is ignored and every element is re-examined instead: each thread of the first
+// warp re-derives the band condition of one element from `cat`, the block then repairs the flagged ones in turn.
+__global__ void __launch_bounds__(96) fixup_ties_kernel(const int* __restrict__ tie_list, const int* tie_count, int tie_cap,
+                                                        const float* __restrict__ cat, const int64_t* __restrict__ lens,
+                                                        const float* __restrict__ xn2, const float* __restrict__ wn,
+                                                        const float* __restrict__ x, int B, int T, const float* __restrict__ w1,
+                                                        const float* __restrict__ w2, const float* __restrict__ w3,
+                                                        const float* __restrict__ b1, const float* __restrict__ b2,
+                                                        const float* __restrict__ b3, float* __restrict__ out,
+                                                        uint8_t* __restrict__ idx, int E, int* __restrict__ stats) {
   pdl_enter();
   // volatile: a load through a `const __restrict__` pointer is an INVARIANT load to the compiler, which may (and in one build did)
   // hoist it above griddepcontrol.wait -- i.e. read the counter while the pool kernel is still counting (tests/test_modules_cpu.py
   // scans the SASS of every kernel for global loads ahead of the wait)
   const int found = *reinterpret_cast<const volatile int*>(tie_count);
   if (stats && blockIdx.x == 0 && threadIdx.x == 0) { stats[0] = found; stats[1] = tie_cap; }
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (found <= tie_cap) {
-    for (int w = warp0; w < found; w += warps) {
-      const int i = tie_list[w];
-      const int64_t r = i / E;
-      fixup_one(r, i - (int)r * E, x, T, w1, w2, w3, b1, b2, b3, out, idx, E);
+  __shared__ float s_v[3];
+  __shared__ unsigned s_mask;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  auto repair = [&](int64_t i) {                 // all 96 threads; i = element index r * E + e
+    const int64_t r = i / E;
+    const int e = (int)(i - r * E);
+    const float v = exact_channel(r, 3 * e + w, x, T, w1, w2, w3, b1, b2, b3, E);
+    if (lane == 0) s_v[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float best, mid;
+      int bi;
+      top2_of3(s_v[0], s_v[1], s_v[2], best, mid, bi);
+      out[i] = best;
+      idx[i] = (uint8_t)bi;
     }
+    __syncthreads();
+  };
+  if (found <= tie_cap) {
+    for (int j = blockIdx.x; j < found; j += gridDim.x) repair(tie_list[j]);
     return;
   }
   const int64_t total = (int64_t)B * T * E;
-  for (int64_t base = (int64_t)warp0 * 32; base < total; base += (int64_t)warps * 32) {
-    const int64_t i = base + lane;
-    bool flag = false;
-    if (i < total) {
-      const int64_t r = i / E;
-      const int e = (int)(i - r * E);
-      const int b = (int)(r / T), t = (int)(r % T);
-      if (!lens || t < lens[b]) {
-        const float* p = cat + r * 3 * (int64_t)E + 3 * e;
-        float best, mid;
-        int bi;
-        top2_of3(p[0], p[1], p[2], best, mid, bi);
-        flag = !(best - mid >= tie_band(xn2, wn, r, t, T, e, E, best, mid));
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+    if (w == 0) {
+      const int64_t i = base + lane;
+      bool flag = false;
+      if (i < total) {
+        const int64_t r = i / E;
+        const int e = (int)(i - r * E);
+        const int b = (int)(r / T), t = (int)(r % T);
+        if (!lens || t < lens[b]) {
+          const float* p = cat + r * 3 * (int64_t)E + 3 * e;
+          float best, mid;
+          int bi;
+          top2_of3(p[0], p[1], p[2], best, mid, bi);
+          flag = !(best - mid >= tie_band(xn2, wn, r, t, T, e, E, best, mid));
+        }
       }
+      const unsigned m = __ballot_sync(0xffffffffu, flag);
+      if (lane == 0) s_mask = m;
     }
-    unsigned m = __ballot_sync(0xffffffffu, flag);
+    __syncthreads();
+    unsigned m = s_mask;
+    __syncthreads();
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
-      const int64_t ii = base + src;
-      const int64_t r = ii / E;
-      fixup_one(r, (int)(ii - r * E), x, T, w1, w2, w3, b1, b2, b3, out, idx, E);
+      repair(base + src);
     }
   }
 }
@@ -492,7 +497,7 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
   HCA_LAUNCH_K((pool3_fwd_kernel), ew_grid((int64_t)R * E), 256, 0, s, c.cat, lens, out, idx, B, T, E, c.xn2, c.wn, c.tie_list, c.tie_count,
                c.tie_cap);
   HCA_LAUNCHED();
-  HCA_LAUNCH_K((fixup_ties_kernel), 148 * 2, 256, 0, s, c.tie_list, c.tie_count, c.tie_cap, c.cat, lens, c.xn2, c.wn, x, B, T, w1, w2, w3, b1,
+  HCA_LAUNCH_K((fixup_ties_kernel), 148 * 8, 96, 0, s, c.tie_list, c.tie_count, c.tie_cap, c.cat, lens, c.xn2, c.wn, x, B, T, w1, w2, w3, b1,
                b2, b3, out, idx, E, fsaved ? sv.stats : (int*)nullptr);
   HCA_LAUNCHED();
   return 0;
