@@ -497,7 +497,7 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
   HCA_LAUNCH_K((pool3_fwd_kernel), ew_grid((int64_t)R * E), 256, 0, s, c.cat, lens, out, idx, B, T, E, c.xn2, c.wn, c.tie_list, c.tie_count,
                c.tie_cap);
   HCA_LAUNCHED();
-  HCA_LAUNCH_K((fixup_ties_kernel), 148 * 8, 96, 0, s, c.tie_list, c.tie_count, c.tie_cap, c.cat, lens, c.xn2, c.wn, x, B, T, w1, w2, w3, b1,
+  HCA_LAUNCH_K((fixup_ties_kernel), 148 * 20, 96, 0, s, c.tie_list, c.tie_count, c.tie_cap, c.cat, lens, c.xn2, c.wn, x, B, T, w1, w2, w3, b1,
                b2, b3, out, idx, E, fsaved ? sv.stats : (int*)nullptr);
   HCA_LAUNCHED();
   return 0;
