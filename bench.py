@@ -659,14 +659,20 @@ def run_ours(args):
                 "final_loss": final_loss, "grad_allreduce_bytes": st.dp.grad_bytes() if world > 1 else 0}
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
-        # NCCL communicators that were captured into CUDA graphs do not always tear down cleanly (observed: the job
-        # printed its line and then sat in destroy_process_group until the launcher's timeout).  Everything this process
-        # owes the caller has been written: drop the graphs, drain the device and leave without the NCCL destructor.
         for slot in st.slots:
             slot["graph"] = None
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
+        if st.dp.fused and os.environ.get("HCA_BENCH_HARD_EXIT", "0") != "1":
+            # fused transport: no NCCL collective was captured into the graphs, so the process group tears down normally
+            st.dp.close()
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+            return
+        # NCCL transport: communicators that were captured into CUDA graphs do not always tear down cleanly (observed in round 1: the
+        # job printed its line and then sat in destroy_process_group until the launcher's timeout).  Everything this process owes the
+        # caller has been written: leave without the NCCL destructor.
         os._exit(0)
 
 

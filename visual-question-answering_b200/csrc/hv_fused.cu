@@ -437,10 +437,11 @@ int launch(const HvPlanes& C, const HvPlanes& PQ, const HvPlanes& PV, const HvPl
   p.kbl = (T + V_BK - 1) / V_BK;
   p.kbs = BWD ? (3 * T + V_BK - 1) / V_BK : 0;
   const size_t smem = (size_t)V_STAGES * V_STAGE_BYTES + 2 * ((BWD ? 2 : 0) * (size_t)V_STG + V_STG) + 1024;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[BWD ? 1 : 0]) {
+  static bool attr_set[64][2] = {};                  // function attributes are per device
+  bool& attr_done = attr_set[current_device()][BWD ? 1 : 0];
+  if (!attr_done) {
     HCA_CUDA(cudaFuncSetAttribute(hv_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[BWD ? 1 : 0] = true;
+    attr_done = true;
   }
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
