@@ -178,10 +178,8 @@ class Stepper:
                                            fused=fused, early_split="question_encoder." if early_reduce else None)
         self.opt = pkg.optim.FlatAdam(self.dp, lr=1e-4)          # Adam(lr=1e-4), README.md:95-100 / main.py:180
         self.early_end = 0
-        self.side = None
-        if self.dp.fused and early_reduce:
-            self.side = torch.cuda.Stream(device)
-            self.dp.on_early = self._early
+        if early_reduce and self.opt.overlap_early_slice(max_ctas=16):
+            self.early_end = self.dp.buckets[0][1]
         self.criterion = pkg.CrossEntropyLoss(scale=self.dp.loss_scale)   # nn.CrossEntropyLoss(), main.py:179
         self.slots = []
         rank = torch.distributed.get_rank() if world > 1 else 0
@@ -198,12 +196,6 @@ class Stepper:
         self.use_graph = use_graph
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.slots[0]["host"].values())
 
-    def _early(self, end):
-        """Called from inside backward when the gradients of [0, end) are complete (their kernels are enqueued on the main stream)."""
-        self.side.wait_stream(torch.cuda.current_stream())
-        self.opt.step_early(end, self.side, max_ctas=16)
-        self.early_end = end
-
     def _step_body(self, slot):
         d = slot["dev"]
         self.dp.zero_grad()
@@ -211,8 +203,6 @@ class Stepper:
         loss = self.criterion(logits, d["labels"])           # mean CE x 1/world, loss + gradient in one launch
         loss.backward()
         self.dp.finish()
-        if self.side is not None:
-            torch.cuda.current_stream().wait_stream(self.side)
         self.opt.step()
         slot["loss"].copy_(loss.detach())
 

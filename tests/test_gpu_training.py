@@ -222,7 +222,7 @@ def _free_port():
     return port
 
 
-def _dp_worker(rank, world, port, fused, out):
+def _dp_worker(rank, world, port, fused, out, early=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -243,7 +243,8 @@ def _dp_worker(rank, world, port, fused, out):
         ref = h.build_net(p, d, vocab, K, mlp, device=dev)
         ref_opt = torch.optim.Adam([q for n, q in ref.named_parameters() if not n.startswith("co_attention.W_b")], lr=1e-4)
         net = h.build_net(p, d, vocab, K, mlp, device=dev)
-        red = h.PKG.dp.FlatGradAllReduce(net.named_parameters(), None, flat_params=True, fused=fused)
+        red = h.PKG.dp.FlatGradAllReduce(net.named_parameters(), None, flat_params=True, fused=fused,
+                                         early_split="question_encoder." if early else None)
         res["fused"] = bool(red.fused)
         res["multicast"] = bool(red.fused and red._symm.mc)
         crit = h.PKG.CrossEntropyLoss(scale=red.loss_scale)
@@ -268,6 +269,7 @@ def _dp_worker(rank, world, port, fused, out):
         res["grad_err"] = worst
         # (2) three optimizer steps: replicas stay identical and follow the single-rank run
         opt = h.PKG.optim.FlatAdam(red, lr=1e-4)
+        res["early_slice"] = bool(early and opt.overlap_early_slice(max_ctas=16))
         start = red.flat_p.clone()
         for step in range(3):
             xg = to(xs[step % 2])
@@ -304,23 +306,24 @@ def _dp_worker(rank, world, port, fused, out):
         pass
 
 
-@pytest.mark.parametrize("fused", [True, False])
-def test_two_rank_data_parallel_matches_single_rank(fused):
+@pytest.mark.parametrize("fused,early", [(True, False), (True, True), (False, False)])
+def test_two_rank_data_parallel_matches_single_rank(fused, early):
     """SURVEY section 4 item 4 on hardware: the averaged gradients of 2 ranks equal the single-rank gradients of the concatenated
     batch; after 3 optimizer steps the replicas are bit-identical and have moved like the single-rank run.  fused=True is the
-    hand-written NVLink kernel (symmetric memory, multimem when the switch offers multicast), fused=False the NCCL transport."""
+    hand-written NVLink kernel (symmetric memory, multimem when the switch offers multicast), fused=False the NCCL transport; early=True
+    additionally processes the classifier + co-attention slice on a side stream while the encoder's backward is still running."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_dp_worker, args=(world, _free_port(), fused, out), nprocs=world, join=True)
+    mp.spawn(_dp_worker, args=(world, _free_port(), fused, out, early), nprocs=world, join=True)
     res = dict(out)
     print("2-rank DP", "fused" if fused else "nccl", {r: {k: v for k, v in d.items() if k != "error"} for r, d in res.items()})
     for r in range(world):
         assert res[r]["ok"], res[r].get("error")
-        assert res[r]["fused"] == fused
+        assert res[r]["fused"] == fused and res[r]["early_slice"] == early
         assert res[r]["grad_err"] < 1e-4, res[r]
         assert res[r]["replicas_identical"]
         assert res[r]["step_err"] < 3e-2, res[r]

@@ -31,14 +31,36 @@ class FlatAdam:
         self.exp_avg_sq = torch.zeros_like(reducer.flat)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=reducer.flat.device)
         self._coef = torch.zeros(2, dtype=torch.float32, device=reducer.flat.device)
+        self._side = None
+        self._early_ctas = 16
         if reducer.fused:
             reducer._optimizer = self       # finish() leaves the collective to step()
+
+    def overlap_early_slice(self, max_ctas: int = 16):
+        """Fused transport: process the slice of the flat buffers in front of the reducer's ``early_split`` boundary (the classifier and
+        co-attention gradients: complete long before backward ends) on a side stream while the rest of backward is still running, with a
+        grid of at most ``max_ctas`` CTAs (the persistent LSTM kernel leaves 20 of the 148 SMs free).  ``step()`` waits for that stream and
+        covers the rest.  A no-op on one GPU / on the NCCL transport.  Capturable in a CUDA graph (the side stream becomes a branch)."""
+        r = self.reducer
+        if not r.fused or len(r.buckets) < 2:
+            return False
+        self._side = torch.cuda.Stream(r.flat.device)
+        self._early_ctas = int(max_ctas)
+
+        def on_early(end):
+            self._side.wait_stream(torch.cuda.current_stream(r.flat.device))
+            self.step_early(end, self._side, self._early_ctas)
+
+        r.on_early = on_early
+        return True
 
     @torch.no_grad()
     def step(self):
         r = self.reducer
         r.check_aliasing()
         if r.fused:
+            if self._side is not None:
+                torch.cuda.current_stream(r.flat.device).wait_stream(self._side)
             done = self._early_end          # elements [0, done) were already reduced + updated by step_early() this step
             self._early_end = 0
             if done == 0:
