@@ -1003,6 +1003,8 @@ void tc_set_timeline(long long* buf, int nctas, int launch_index) {
   g_timeline_seen = 0;
 }
 
+long long* tc_timeline_buffer() { return g_timeline; }
+
 int launch_split_planes(const float* src, int64_t ld, int64_t rows, int cols, __nv_bfloat16* planes, int64_t ldp,
                         int64_t plane_stride, int P, cudaStream_t s) {
   HCA_CHECK_ARG(src && planes && rows > 0 && cols > 0 && P >= 1 && P <= 3 && (ldp % 8) == 0 && (plane_stride % 8) == 0,

@@ -115,5 +115,6 @@ int tc_make_tmap(void* tm, bool bf16, int rank, const void* base, const uint64_t
 // debug: record per-CTA clock64 stamps of the next gemm_tc launches into buf [nctas][64] (nullptr disables)
 // launch_index >= 0: only that gemm_tc launch (counted from this call) records
 void tc_set_timeline(long long* buf, int nctas, int launch_index = -1);
+long long* tc_timeline_buffer();      // the buffer last handed to tc_set_timeline (the other kernels' debug stamps go there too)
 
 }  // namespace hca
