@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -168,9 +169,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      // one arrival per epilogue warp that drains the buffer: BN = 32 tiles go to ONE group each, wider tiles to all groups
+      // one arrival per epilogue warp that drains the buffer (every group takes part in every tile)
       // (pair mode: the leader's barrier collects the epilogue warps of both CTAs)
-      mbar_init(tmem_empty_bar(a), BN == 32 ? 4 : 4 * p.n_eg * CG);
+      mbar_init(tmem_empty_bar(a), 4 * p.n_eg * CG);
     }
     for (int g = 0; g < NUM_EG; ++g) mbar_init(aux_bar(g), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -338,70 +339,98 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     int tile_it = 0;
     if constexpr (BN == 32) {
       // ------------------------------------------------------------------ transposed epilogue (direct, coalesced global I/O)
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
-        if ((tile_it & (neg - 1)) != eg) continue;
-        const TileCoord tc = decode(t);
-        const int acc = tile_it & 1;
-        const int row = tc.m0 + r;
-        const bool row_ok = row < p.M;
-        mbar_wait(tmem_full_bar(acc), (tile_it >> 1) & 1, 3);
-        tc_fence_after();
-        if (tl && et == 0 && tile_it == 0) tl[4] = clock64();
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN), v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-        const int ncols = min(32, p.N - tc.n0);
-        const int za = (tc.z / p.aux_zd) % p.aux_nb;
-        const __nv_bfloat16* ax0 = p.auxp ? p.auxp + (int64_t)za * p.auxp_sb + (int64_t)tc.n0 * p.auxp_ld + row : nullptr;
-        float* drow = p.D ? p.D + (int64_t)(tc.z / p.d_zd) * p.d_sb + (int64_t)tc.n0 * p.ldd + row : nullptr;
-        __nv_bfloat16* prow = p.P ? p.P + (int64_t)tc.z * p.p_sb + (int64_t)tc.n0 * p.p_ld + row : nullptr;
-        float rsum = 0.f;
-        // transposed tiles: the bias is indexed by the tile ROW m (the output feature: these products put the weight on M)
-        const float bm = (p.bias && row_ok) ? __ldg(p.bias + (int64_t)tc.z * p.bias_sb + row) : 0.f;
-        if (row_ok) {
+      // The groups split the COLUMNS of every tile (CW = 32 / groups each).  A tile's epilogue is one warp per scheduler walking its
+      // columns with nothing to hide a latency behind: per-launch timeline of the classifier products (profiles/timeline_mlp.py):
+      // 7.6 k cycles for the epilogue of ONE 128 x 32 tile with a single group, against 6.5 k for the whole K = 512 mainloop.  (Splitting
+      // that mainloop over a cluster with a DSMEM reduction was built and measured too: no change of the step, removed.)
+      auto run = [&](auto cw_tag) {
+        constexpr int CW = decltype(cw_tag)::value;
+        const int c0 = CW == 32 ? 0 : eg * CW;
+        for (int t = sched0; t < p.total_tiles; t += sched_step, ++tile_it) {
+          const TileCoord tc = decode(t);
+          const int acc = tile_it & 1;
+          const int row = tc.m0 + r;
+          const bool row_ok = row < p.M;
+          mbar_wait(tmem_full_bar(acc), (tile_it >> 1) & 1, 3);
+          tc_fence_after();
+          if (tl && et == 0 && eg == 0 && tile_it == 0) tl[4] = clock64();
+          uint32_t v[CW];
+          __syncwarp();
+          tmem_ld_cols<CW>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+          if (tc.num_kb == 0) {
 #pragma unroll
-          for (int j0 = 0; j0 < 32; j0 += 8) {
-            float ax[8];
-            if (ax0) {
+            for (int j = 0; j < CW; ++j) v[j] = 0u;
+          }
+          const int ncols = min(CW, p.N - tc.n0 - c0);
+          if (!row_ok || ncols <= 0) continue;
+          const int64_t col_first = tc.n0 + c0;
+          // addend / factor tile (bf16 planes, addressed [n][m]): every load of the thread's columns in flight at once
+          float ax[CW];
+          if (p.auxp) {
+            const int za = (tc.z / p.aux_zd) % p.aux_nb;
+            const __nv_bfloat16* a = p.auxp + (int64_t)za * p.auxp_sb + col_first * p.auxp_ld + row;
+            __nv_bfloat16 ah[CW], al[CW];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                ax[j] = 0.f;
-                if (j0 + j < ncols) {
-                  const __nv_bfloat16* a = ax0 + (int64_t)(j0 + j) * p.auxp_ld;
-                  ax[j] = __bfloat162float(a[0]) + __bfloat162float(a[p.auxp_ps]);
-                }
-              }
+            for (int j = 0; j < CW; ++j) {
+              const bool in = j < ncols;
+              ah[j] = in ? a[0] : __float2bfloat16_rn(0.f);
+              al[j] = in ? a[p.auxp_ps] : __float2bfloat16_rn(0.f);
+              a += p.auxp_ld;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (j0 + j < ncols) {
-                float f = ((tc.num_kb != 0) ? __uint_as_float(v[j0 + j]) : 0.f) + bm;
-                if (p.aux_mode == TC_AUX_ADD) f += ax[j];
-                if (p.act_tanh) f = tanh_fast(f);
-                if (p.aux_mode == TC_AUX_MUL_1MX2) f *= (1.f - ax[j] * ax[j]);
-                rsum += f;
-                if (drow) {
-                  float* d = drow + (int64_t)(j0 + j) * p.ldd;
-                  if (p.atomic) atomicAdd(d, f);
-                  else if (p.accumulate) *d += f;
-                  else *d = f;
-                }
-                if (prow) {
-                  const __nv_bfloat16 h = __float2bfloat16_rn(f);
-                  __nv_bfloat16* d = prow + (int64_t)(j0 + j) * p.p_ld;
-                  d[0] = h;
-                  d[p.p_ps] = __float2bfloat16_rn(f - __bfloat162float(h));
-                }
+            for (int j = 0; j < CW; ++j) ax[j] = __bfloat162float(ah[j]) + __bfloat162float(al[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) ax[j] = 0.f;
+          }
+          // transposed tiles: the bias is indexed by the tile ROW m (the output feature: these products put the weight on M)
+          const float bm = p.bias ? __ldg(p.bias + (int64_t)tc.z * p.bias_sb + row) : 0.f;
+          const bool aux_add = p.aux_mode == TC_AUX_ADD, aux_mul = p.aux_mode == TC_AUX_MUL_1MX2, act = p.act_tanh != 0;
+          float f[CW];
+          float rsum = 0.f;
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            float x = __uint_as_float(v[j]) + bm;
+            if (aux_add) x += ax[j];
+            if (act) x = tanh_fast(x);
+            if (aux_mul) x *= (1.f - ax[j] * ax[j]);
+            f[j] = x;
+            rsum += j < ncols ? x : 0.f;
+          }
+          if (p.D) {
+            float* d = p.D + (int64_t)(tc.z / p.d_zd) * p.d_sb + col_first * p.ldd + row;
+            if (p.atomic) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) { if (j < ncols) atomicAdd(d, f[j]); d += p.ldd; }
+            } else if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) { if (j < ncols) *d += f[j]; d += p.ldd; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) { if (j < ncols) *d = f[j]; d += p.ldd; }
+            }
+          }
+          if (p.P) {
+            __nv_bfloat16* d = p.P + (int64_t)tc.z * p.p_sb + col_first * p.p_ld + row;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              if (j < ncols) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
+                d[0] = h;
+                d[p.p_ps] = __float2bfloat16_rn(f[j] - __bfloat162float(h));
               }
+              d += p.p_ld;
             }
           }
           if (p.red_row) atomicAdd(p.red_row + row, rsum);
+          if (tl && et == 0 && eg == 0 && tile_it == 0) tl[5] = clock64();
         }
-        if (tl && et == 0 && tile_it == 0) tl[5] = clock64();
-      }
+      };
+      if (neg == 2) run(std::integral_constant<int, 16>{});
+      else run(std::integral_constant<int, 32>{});
     } else {
       // ------------------------------------------------------------------ standard epilogue
       constexpr bool FULL = (EPI == 1);
