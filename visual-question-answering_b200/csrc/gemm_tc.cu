@@ -31,6 +31,7 @@ struct TcParams {
   uint32_t off_store, off_pstore, off_aux;                   // byte offsets of the epilogue staging areas from the smem base
   int store_nbuf;                                            // staging buffers per output kind and epilogue group (2 = double-buffered)
   int n_eg;                                                  // active epilogue groups: 2 for epilogue-bound products (alternate 32-column chunks)
+  int kwin_ncol, kwin_lo[4], kwin_hi[4];                     // K windows per group of output columns, in k-blocks (kwin_ncol = 0: off)
   // fp32 output
   float* D;
   int64_t ldd, d_sb;
@@ -151,6 +152,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     c.n0 = nt * BN;
     c.kb_begin = ks * p.kb_per_split;
     c.num_kb = min(p.kb_total, c.kb_begin + p.kb_per_split) - c.kb_begin;
+    if (p.kwin_ncol > 0) {            // block-structured contraction: the union of the K windows of the column groups this tile touches
+      const int g0 = c.n0 / p.kwin_ncol, g1 = (min(p.N, c.n0 + BN) - 1) / p.kwin_ncol;
+      int lo = p.kwin_lo[g0], hi = p.kwin_hi[g0];
+      for (int g = g0 + 1; g <= g1; ++g) {
+        lo = min(lo, p.kwin_lo[g]);
+        hi = max(hi, p.kwin_hi[g]);
+      }
+      c.kb_begin = lo;
+      c.num_kb = hi - lo;
+    }
     return c;
   };
 
@@ -1100,7 +1111,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   bool pair_wgrad = pair_epi && splitk > 1 /* the caller has cleared D */ && A.mn_major && B.mn_major && (M % 256) == 0 && (N % 256) == 0 && K >= 2048 && !e.bias && !e.act_tanh &&
                     !e.red_col && !e.P.p && e.D != nullptr && f32_tma_ok(e.D, e.ldd, e.d_batch_stride, 0);
   if (HCA_ENV_INT("HCA_TC_PAIR_WGRAD", 1) == 0) pair_wgrad = false;
-  bool pair = pair_epi && !A.mn_major && !B.mn_major && splitk == 1 && (N % 256) == 0 && M >= 8192 && K >= 256;
+  bool pair = pair_epi && !A.mn_major && !B.mn_major && splitk == 1 && (N % 256) == 0 && M >= 8192 && K >= 256 && e.kwin_ncol == 0;
   if (pair) {
     // wave quantisation: a pair tile is four single tiles of MMA time on two SMs.  Take the pair schedule only when its last,
     // partly filled wave does not cost more than the fabric traffic it saves (PV, M = 31360: 4 pair waves vs 7 single waves;
@@ -1112,7 +1123,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   {
     const int pair_env = HCA_ENV_INT("HCA_TC_PAIR", -1);
     if (pair_env == 0) pair = false;
-    if (pair_env == 1 && !e.transposed && P == 2 && !A.mn_major && !B.mn_major && !A2 && splitk == 1 && batch == 1 && (N % 256) == 0 &&
+    if (pair_env == 1 && e.kwin_ncol == 0 && !e.transposed && P == 2 && !A.mn_major && !B.mn_major && !A2 && splitk == 1 && batch == 1 && (N % 256) == 0 &&
         e.mode == TC_EPI_STORE && e.aux_mode == TC_AUX_NONE && !e.r1col && !e.mulx && e.d_groups <= 1 && A.nbatch <= 1 && B.nbatch <= 1)
       pair = true;
   }
@@ -1244,6 +1255,15 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   p.kb_per_split = (p.kb_total + splitk - 1) / splitk;
   splitk = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;      // no empty split
   p.splitk = splitk;
+  if (e.kwin_ncol > 0) {
+    HCA_CHECK_ARG(splitk == 1 && batch == 1 && !A2 && !pair && (N + e.kwin_ncol - 1) / e.kwin_ncol <= 4, "gemm_tc: K windows are for un-batched, un-split products with at most 4 column groups");
+    p.kwin_ncol = e.kwin_ncol;
+    for (int g = 0; g < 4; ++g) {
+      const int lo = std::max(0, std::min(e.kwin_lo[g], K)), hi = std::max(lo, std::min(e.kwin_hi[g], K));
+      p.kwin_lo[g] = lo / BK;
+      p.kwin_hi[g] = (hi + BK - 1) / BK;
+    }
+  }
   p.tiles_m = (M + BM * CGn - 1) / (BM * CGn);
   p.tiles_n = (N + BN - 1) / BN;
   const int64_t total = (int64_t)p.tiles_m * p.tiles_n * splitk * batch;

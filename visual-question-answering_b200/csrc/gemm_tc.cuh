@@ -77,6 +77,12 @@ struct TcEpilogue {
   // planes P, auxp (ADD / MUL_1MX2), act_tanh, red_row (un-batched: red_row[m] += sum_n f[m][n]) and a bias indexed by the
   // tile ROW (bias[z][m]: these products put the weight matrix on M) are supported, nothing else.
   int transposed = 0;
+  // Block-structured contractions (un-batched, splitk = 1): output columns [g * kwin_ncol, (g + 1) * kwin_ncol) only have non-zero
+  // operand data for k in [kwin_lo[g], kwin_hi[g]) (elements; up to 4 groups; 0 = off).  A tile contracts the union of the windows of
+  // the groups it touches, rounded out to whole k-blocks -- the operand entries outside a group's own window must therefore BE zero in
+  // memory (the windows only skip work, they never change the result).
+  int kwin_ncol = 0;
+  int kwin_lo[4] = {0, 0, 0, 0}, kwin_hi[4] = {0, 0, 0, 0};
 };
 
 // D[z][M,N] (+)= A[z] . B[z]^T (+ A2[z] . B2[z]^T with inner size K2) for z < batch.  splitk >= 1 (un-batched only).

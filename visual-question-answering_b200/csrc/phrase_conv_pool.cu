@@ -282,46 +282,32 @@ __global__ void __launch_bounds__(256) im2col3_planes_kernel(const float4* __res
     for (int pl = 0; pl < P; ++pl) *reinterpret_cast<uint2*>(planes + pl * ps + i * 4) = o[pl];
   }
 }
-// planes [P][E][k*E] of the tap-major weight Wr[o][j*E + c] = w[o][c][j]  (conv layout [C_out][C_in][k])
-template <int P>
-__global__ void __launch_bounds__(256) conv_w_planes_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ planes, int64_t ps, int E,
-                                                            int k) {
-  pdl_enter();
-  const int64_t total = (int64_t)E * E * k;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % E);
-    const int j = (int)((i / E) % k);
-    const int64_t o = i / ((int64_t)E * k);
-    float x = w[(o * E + c) * k + j];
-#pragma unroll
-    for (int pl = 0; pl < P; ++pl) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(x);
-      planes[pl * ps + i] = h;
-      x -= __bfloat162float(h);
-    }
-  }
-}
-// The three weights in one launch (hi/lo planes), which also clears the near-tie counter of the pool kernel.
+// The three weights as ONE block-structured operand, hi/lo planes [2][3E][3E]: row (k-1) E + o holds the taps of output channel o of the k-gram
+// filter at the columns of the Acat taps it multiplies -- unigram: [E, 2E) (the token itself), bigram: [0, 2E), trigram: [0, 3E) -- and ZEROS
+// elsewhere, so that the three convolutions are one product over K = 3E whose zero blocks the GEMM skips (TcEpilogue::kwin_*), and the input
+// gradient is one product with the same matrix as the MN-major operand.  Also: the concatenated bias, and the pool kernel's near-tie counter.
 __global__ void __launch_bounds__(256) conv_w_planes3_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
-                                                             const float* __restrict__ w3, __nv_bfloat16* __restrict__ p1,
-                                                             __nv_bfloat16* __restrict__ p2, __nv_bfloat16* __restrict__ p3, int E,
+                                                             const float* __restrict__ w3, const float* __restrict__ b1,
+                                                             const float* __restrict__ b2, const float* __restrict__ b3,
+                                                             __nv_bfloat16* __restrict__ planes, float* __restrict__ bcat, int E,
                                                              int* __restrict__ tie_count) {
   pdl_enter();
   if (tie_count && blockIdx.x == 0 && threadIdx.x == 0) *tie_count = 0;
-  const int64_t EE = (int64_t)E * E, total = 6 * EE;
+  const int64_t E3 = 3 * (int64_t)E, total = E3 * E3, ps = total;
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-    const int k = g < EE ? 1 : (g < 3 * EE ? 2 : 3);
-    const int64_t i = g - (k == 1 ? 0 : (k == 2 ? EE : 3 * EE));
-    const float* w = k == 1 ? w1 : (k == 2 ? w2 : w3);
-    __nv_bfloat16* planes = k == 1 ? p1 : (k == 2 ? p2 : p3);
-    const int64_t ps = EE * k;
-    const int c = (int)(i % E);
-    const int j = (int)((i / E) % k);
-    const int64_t o = i / ((int64_t)E * k);
-    const float x = w[(o * E + c) * k + j];
+    const int col = (int)(g % E3);
+    const int row = (int)(g / E3);
+    const int k = row / E + 1, o = row - (k - 1) * E;          // k-gram filter, its output channel
+    const int j = col / E - (k == 1 ? 1 : 0), c = col % E;     // tap of that filter at this column (outside [0, k): structural zero)
+    float x = 0.f;
+    if (j >= 0 && j < k) {
+      const float* w = k == 1 ? w1 : (k == 2 ? w2 : w3);
+      x = w[((int64_t)o * E + c) * k + j];
+    }
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    planes[i] = h;
-    planes[ps + i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    planes[g] = h;
+    planes[ps + g] = __float2bfloat16_rn(x - __bfloat162float(h));
+    if (bcat && col == 0) bcat[row] = (k == 1 ? b1 : (k == 2 ? b2 : b3))[o];
   }
 }
 // Pool backward straight into operand planes: dcat[r][3e+j] = (j == idx) ? dout * (1 - out^2) : 0 as bf16 hi/lo planes
@@ -384,7 +370,7 @@ int g_tie_cap_override = 0;      // test hook (hca_set_option("pool_tie_cap", n)
 
 struct ConvWs {
   Workspace w;
-  float *cat, *dA, *dwr2, *dwr3, *xn2, *wn;
+  float *cat, *dA, *dwr2, *dwr3, *xn2, *wn, *bcat;
   int *tie_count, *tie_list;
   int tie_cap;
   bool ok;
@@ -401,6 +387,7 @@ ConvWs carve(void* ws, size_t bytes, int B, int T, int E) {
   c.dwr3 = w.take<float>((size_t)E * 3 * E);
   c.xn2 = w.take<float>(R);
   c.wn = w.take<float>((size_t)3 * E);
+  c.bcat = w.take<float>((size_t)3 * E);
   c.tie_cap = (int)tie_cap_default(R, E);
   c.tie_count = w.take<int>(64);
   c.tie_list = w.take<int>((size_t)c.tie_cap);
@@ -417,31 +404,29 @@ extern "C" size_t hca_phrase_conv_pool_workspace(int B, int T, int E) {
   using hca::align_up;
   const size_t R = (size_t)B * T;
   return 2 * align_up(R * 3 * E * 4) + align_up((size_t)E * 2 * E * 4) + align_up((size_t)E * 3 * E * 4) + align_up(R * 4) +
-         align_up((size_t)3 * E * 4) + 1024 + align_up(hca::tie_cap_default(R, E) * 4) +          // near-tie list
-         2 * 2 * align_up(R * 3 * E * 2) + 2 * align_up((size_t)2 * E * 6 * E * 2) + 8192;          // bf16 planes when no `fsaved` is given
+         2 * align_up((size_t)3 * E * 4) + 1024 + align_up(hca::tie_cap_default(R, E) * 4) +      // near-tie list
+         2 * 2 * align_up(R * 3 * E * 2) + align_up((size_t)2 * 3 * E * 3 * E * 2) + 8192;          // bf16 planes when no `fsaved` is given
 }
 
 namespace hca {
 namespace {
-// operand planes kept from forward to backward: Acat [2][R][3E], W1 [2][E][E], W2 [2][E][2E], W3 [2][E][3E]  (bf16); the last 256
-// bytes hold the tie-repair statistics of the forward call (int32: listed near-ties, list capacity)
+// operand planes kept from forward to backward: Acat [2][R][3E] and the block-structured weight matrix Wcat [2][3E][3E] (bf16); the last
+// 256 bytes hold the tie-repair statistics of the forward call (int32: listed near-ties, list capacity)
 struct ConvSaved {
   __nv_bfloat16* ap = nullptr;
-  __nv_bfloat16* wp[3] = {nullptr, nullptr, nullptr};
+  __nv_bfloat16* wcat = nullptr;
   int* stats = nullptr;
 };
 size_t conv_saved_bytes(int B, int T, int E) {
   const size_t R = (size_t)B * T;
-  size_t n = align_up(2 * R * 3 * E * 2);
-  for (int k = 1; k <= 3; ++k) n += align_up((size_t)2 * E * k * E * 2);
-  return n + 256;
+  return align_up(2 * R * 3 * E * 2) + align_up((size_t)2 * 3 * E * 3 * E * 2) + 256;
 }
 bool carve_saved(ConvSaved& v, void* buf, size_t bytes, int B, int T, int E) {
   if (!buf || (reinterpret_cast<uintptr_t>(buf) & 255) || bytes < conv_saved_bytes(B, T, E)) return false;
   char* p = (char*)buf;
   const size_t R = (size_t)B * T;
   v.ap = (__nv_bfloat16*)p; p += align_up(2 * R * 3 * E * 2);
-  for (int k = 1; k <= 3; ++k) { v.wp[k - 1] = (__nv_bfloat16*)p; p += align_up((size_t)2 * E * k * E * 2); }
+  v.wcat = (__nv_bfloat16*)p; p += align_up((size_t)2 * 3 * E * 3 * E * 2);
   v.stats = (int*)p;
   return true;
 }
@@ -463,7 +448,6 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
   ConvWs c = carve(ws, ws_bytes, B, T, E);
   if (!c.ok) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small (%zu bytes)", ws_bytes);
   const int R = B * T;
-  const float* bs[3] = {b1, b2, b3};
   // tensor cores, bf16x2 operand split (3 MMAs per product): the row-shifted operand Acat and the tap-major weights are written
   // directly as bf16 planes (no fp32 im2col / repack round trip); the three convs read column windows of the Acat planes; bias +
   // tanh fused in the epilogue; near-ties are repaired exactly below
@@ -475,24 +459,24 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
   if (!ap) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for operand planes");
   HCA_LAUNCH_K((im2col3_planes_kernel<2>), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, ap, a_stride, B, T, E / 4);
   HCA_LAUNCHED();
-  __nv_bfloat16* wps[3];
-  for (int k = 1; k <= 3; ++k) {
-    wps[k - 1] = fsaved ? sv.wp[k - 1] : c.w.take<__nv_bfloat16>((size_t)P * E * k * E);
-    if (!wps[k - 1]) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for weight planes");
-  }
-  HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid((int64_t)6 * E * E), 256, 0, s, w1, w2, w3, wps[0], wps[1], wps[2], E, c.tie_count);
+  const int64_t E3 = 3 * (int64_t)E;
+  __nv_bfloat16* wcat = fsaved ? sv.wcat : c.w.take<__nv_bfloat16>((size_t)P * E3 * E3);
+  if (!wcat) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for weight planes");
+  HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid(E3 * E3), 256, 0, s, w1, w2, w3, b1, b2, b3, wcat, c.bcat, E, c.tie_count);
   HCA_LAUNCHED();
   HCA_LAUNCH_K((conv_norms_kernel), std::min(148 * 4, (R + 3 * E + 7) / 8), 256, 0, s, x, w1, w2, w3, c.xn2, c.wn, R, E);
   HCA_LAUNCHED();
-  for (int k = 1; k <= 3; ++k) {
-    const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
-    __nv_bfloat16* wp = wps[k - 1];
+  {  // cat[r][(k-1) E + o] = tanh(conv_k): ONE product over K = 3E, each filter family contracting only the taps it has
     TcOperand A, Bw;
-    A.planes = ap + (k == 1 ? E : 0); A.ld = lda; A.plane_stride = a_stride; A.rows = R; A.cols = k * E;
-    Bw.planes = wp; Bw.ld = ldw; Bw.plane_stride = w_stride; Bw.rows = E; Bw.cols = k * E;
+    A.planes = ap; A.ld = lda; A.plane_stride = a_stride; A.rows = R; A.cols = (int)E3;
+    Bw.planes = wcat; Bw.ld = E3; Bw.plane_stride = E3 * E3; Bw.rows = (int)E3; Bw.cols = (int)E3;
     TcEpilogue ep;
-    ep.D = c.cat + (k - 1) * E; ep.ldd = lda; ep.bias = bs[k - 1]; ep.act_tanh = 1;
-    HCA_TRY(launch_gemm_tc(A, Bw, P, R, E, k * E, ep, 1, s));
+    ep.D = c.cat; ep.ldd = lda; ep.bias = c.bcat; ep.act_tanh = 1;
+    ep.kwin_ncol = E;
+    ep.kwin_lo[0] = E; ep.kwin_hi[0] = 2 * E;          // unigram: the token itself
+    ep.kwin_lo[1] = 0; ep.kwin_hi[1] = 2 * E;          // bigram: previous token, token
+    ep.kwin_lo[2] = 0; ep.kwin_hi[2] = 3 * E;          // trigram
+    HCA_TRY(launch_gemm_tc(A, Bw, P, R, (int)E3, (int)E3, ep, 1, s));
   }
   HCA_LAUNCH_K((pool3_fwd_kernel), ew_grid((int64_t)R * E), 256, 0, s, c.cat, lens, out, idx, B, T, E, c.xn2, c.wn, c.tie_list, c.tie_count,
                c.tie_cap);
@@ -555,23 +539,26 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
   HCA_LAUNCH_K((unpack_conv_w23_kernel), ew_grid((int64_t)E * E * 5), 256, 0, s, c.dwr2, dw2, c.dwr3, dw3, E);
   HCA_LAUNCHED();
   if (dx) {
-    // dA[r][a_off + kk] (+)= sum_o dcat[r][(k-1)E + o] * Wr_k[o][kk]: tri first (covers all 3E columns), bi and uni accumulate
-    const float* ws_[3] = {w1, w2, w3};
-    for (int k = 3; k >= 1; --k) {
-      const int64_t ldw = (int64_t)k * E, w_stride = (int64_t)E * ldw;
-      __nv_bfloat16* wp = fsaved ? sv.wp[k - 1] : c.w.take<__nv_bfloat16>((size_t)2 * w_stride);
-      if (!wp) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for weight planes");
-      if (!fsaved) {
-        HCA_LAUNCH_K((conv_w_planes_kernel<2>), ew_grid((int64_t)E * E * k), 256, 0, s, ws_[k - 1], wp, w_stride, E, k);
-        HCA_LAUNCHED();
-      }
-      TcOperand A, Bm;
-      A.planes = dp + (k - 1) * E; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = E;
-      Bm.planes = wp; Bm.ld = ldw; Bm.plane_stride = w_stride; Bm.rows = E; Bm.cols = k * E; Bm.mn_major = true;
-      TcEpilogue ep;
-      ep.D = c.dA + (k == 1 ? E : 0); ep.ldd = ld3; ep.accumulate = (k != 3);
-      HCA_TRY(launch_gemm_tc(A, Bm, 2, R, k * E, E, ep, 1, s));
+    // dA[r][kk] = sum_oc dcat[r][oc] * Wcat[oc][kk]: ONE product with the block-structured weight matrix as the MN-major operand; tap
+    // block 0 (previous token) only receives from the bigram and trigram filters, block 2 (next token) only from the trigram
+    const int64_t E3 = 3 * (int64_t)E;
+    __nv_bfloat16* wcat = fsaved ? sv.wcat : c.w.take<__nv_bfloat16>((size_t)2 * E3 * E3);
+    if (!wcat) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for weight planes");
+    if (!fsaved) {
+      HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid(E3 * E3), 256, 0, s, w1, w2, w3, (const float*)nullptr, (const float*)nullptr,
+                                                                   (const float*)nullptr, wcat, (float*)nullptr, E, (int*)nullptr);
+      HCA_LAUNCHED();
     }
+    TcOperand A, Bm;
+    A.planes = dp; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = (int)E3;
+    Bm.planes = wcat; Bm.ld = E3; Bm.plane_stride = E3 * E3; Bm.rows = (int)E3; Bm.cols = (int)E3; Bm.mn_major = true;
+    TcEpilogue ep;
+    ep.D = c.dA; ep.ldd = ld3;
+    ep.kwin_ncol = E;
+    ep.kwin_lo[0] = E; ep.kwin_hi[0] = 3 * E;
+    ep.kwin_lo[1] = 0; ep.kwin_hi[1] = 3 * E;
+    ep.kwin_lo[2] = 2 * E; ep.kwin_hi[2] = 3 * E;
+    HCA_TRY(launch_gemm_tc(A, Bm, 2, R, (int)E3, (int)E3, ep, 1, s));
     HCA_LAUNCH_K((col2im3_kernel), ew_grid((int64_t)R * E / 4), 256, 0, s, (const float4*)c.dA, (float4*)dx, B, T, E / 4);
     HCA_LAUNCHED();
   }

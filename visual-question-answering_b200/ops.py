@@ -140,7 +140,7 @@ embedding.register_autograd(_embedding_backward, setup_context=_embedding_setup)
 # ------------------------------------------------------------------------------------------ phrase conv + pool
 def _pcp_saved_bytes(B: int, T: int, E: int) -> int:
     al = lambda n: (n + 255) // 256 * 256
-    return al(2 * B * T * 3 * E * 2) + sum(al(2 * E * k * E * 2) for k in (1, 2, 3)) + 256
+    return al(2 * B * T * 3 * E * 2) + al(2 * 3 * E * 3 * E * 2) + 256      # mirrors hca_phrase_conv_pool_saved_bytes (fake-tensor path)
 
 
 @torch.library.custom_op(f"{NS}::phrase_conv_pool", mutates_args=(), device_types="cuda")
