@@ -407,12 +407,62 @@ TcPlanes plv(const Pl& pl, int64_t row0, int64_t rows_per_entry, int nbatch, int
 }
 
 
+// Question-side backward through tanh: dZq[r][j] = dsq[r] * wq[j] * (1 - Hq[r][j]^2) as bf16 hi/lo planes, dwq[j] += sum_r Hq[r][j] dsq[r].
+// Hq [rows][d] comes as the planes the forward pass saved.  Block = a slab of HQ_ROWS rows x 128 columns: a lane owns 4 columns, the 8 warps
+// take the rows of the slab in turn, and the column sums meet in shared memory -- one atomic per column and block (49 per column at B = 160:
+// with one atomic per column and 16-row slab the 400 k atomics onto 16 cache lines WERE the kernel: 41 us for 50 MB).
+constexpr int HQ_ROWS = 256, HQ_WARPS = 8;
+__global__ void __launch_bounds__(32 * HQ_WARPS) hq_bwd_kernel(const __nv_bfloat16* __restrict__ hq, int64_t ld, int64_t ps,
+                                                               const float* __restrict__ dsq, const float* __restrict__ wq,
+                                                               __nv_bfloat16* __restrict__ dz, int64_t dz_ld, int64_t dz_ps,
+                                                               float* __restrict__ dwq, int64_t rows, int d) {
+  pdl_enter();
+  __shared__ float red[HQ_WARPS][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.y * 128 + 4 * lane;
+  const bool col_ok = c < d;                     // (d % 4 == 0: a lane's 4 columns are inside or outside together)
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (col_ok) {
+    const float4 w = *reinterpret_cast<const float4*>(wq + c);
+    const float wv[4] = {w.x, w.y, w.z, w.w};
+    const int64_t r0 = (int64_t)blockIdx.x * HQ_ROWS, r1 = r0 + HQ_ROWS < rows ? r0 + HQ_ROWS : rows;
+#pragma unroll 8
+    for (int64_t r = r0 + warp; r < r1; r += HQ_WARPS) {
+      const uint2 hh = *reinterpret_cast<const uint2*>(hq + r * ld + c);
+      const uint2 hl = *reinterpret_cast<const uint2*>(hq + ps + r * ld + c);
+      const float ds = __ldg(dsq + r);
+      const float h[4] = {__uint_as_float(hh.x << 16) + __uint_as_float(hl.x << 16), __uint_as_float(hh.x & 0xffff0000u) + __uint_as_float(hl.x & 0xffff0000u),
+                          __uint_as_float(hh.y << 16) + __uint_as_float(hl.y << 16), __uint_as_float(hh.y & 0xffff0000u) + __uint_as_float(hl.y & 0xffff0000u)};
+      __nv_bfloat16 oh[4], ol[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j] = fmaf(h[j], ds, acc[j]);
+        const float g = ds * wv[j] * (1.f - h[j] * h[j]);
+        oh[j] = __float2bfloat16_rn(g);
+        ol[j] = __float2bfloat16_rn(g - __bfloat162float(oh[j]));
+      }
+      *reinterpret_cast<uint2*>(dz + r * dz_ld + c) = *reinterpret_cast<const uint2*>(oh);
+      *reinterpret_cast<uint2*>(dz + dz_ps + r * dz_ld + c) = *reinterpret_cast<const uint2*>(ol);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[warp][4 * lane + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 128 && blockIdx.y * 128 + (int)threadIdx.x < d) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < HQ_WARPS; ++w) sum += red[w][threadIdx.x];
+    atomicAdd(dwq + blockIdx.y * 128 + threadIdx.x, sum);
+  }
+}
+
 struct Saved {
   Pl V, Q, PV, PQ, C;
   float *av, *aq;
+  Pl Hq;          // question-side hidden state tanh(PQ_all + C_all PV) [B][3T][d]: 25 MB saved against one fabric-bound product recomputed
 };
 size_t saved_bytes(int B, int N, int T, int d) {
-  return 2 * pl_bytes((int64_t)B * N, d) + 2 * pl_bytes((int64_t)B * 3 * T, d) + pl_bytes((int64_t)B * 3 * T, N) +
+  return 2 * pl_bytes((int64_t)B * N, d) + 3 * pl_bytes((int64_t)B * 3 * T, d) + pl_bytes((int64_t)B * 3 * T, N) +
          align_up((size_t)B * 3 * N * 4) + align_up((size_t)B * 3 * T * 4) + 256;
 }
 bool carve_saved(Saved& s, void* buf, size_t bytes, int B, int N, int T, int d) {
@@ -425,7 +475,8 @@ bool carve_saved(Saved& s, void* buf, size_t bytes, int B, int N, int T, int d) 
   s.PQ = pl_at(p, BT3, d); p += pl_bytes(BT3, d);
   s.C = pl_at(p, BT3, N); p += pl_bytes(BT3, N);
   s.av = (float*)p; p += align_up((size_t)B * 3 * N * 4);
-  s.aq = (float*)p;
+  s.aq = (float*)p; p += align_up((size_t)B * 3 * T * 4);
+  s.Hq = pl_at(p, BT3, d);                 // (behind the attention weights: hca_coattn_saved_attention's offsets stay put)
   return true;
 }
 Pl take_pl(Workspace& w, int64_t rows, int cols) {
@@ -534,6 +585,7 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
   {  // sq[b][(l,t)] = sum_j tanh(PQ_all + C_all PV)[(l,t)][j] wq[j]
     TcEpilogue e; e.mode = TC_EPI_ROWDOT; e.act_tanh = 1; e.colv = wq; e.red_row = sqs; e.red_row_batch_stride = T3;
     e.auxp = plv(PQp, 0, T3, B); e.aux_mode = TC_AUX_ADD;
+    e.P = plv(sv_.Hq, 0, T3, B);            // Hq itself, for backward
     HCA_TRY(launch_gemm_tc(opv(Cp, 0, T3, T3, B, false), opv(PVp, 0, N, N, B, true), 2, T3, d, N, e, 1, s, B));
   }
   // sv[b][l][n] = sum_j tanh(PV + C_l^T PQ_l)[n][j] wv[j]: the three levels of a tile in one pass over its PV tile (hv_fused.cu)
@@ -595,11 +647,12 @@ extern "C" int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv,
     HCA_LAUNCH_K((attn_bwd_softmax_kernel), B, 192, 0, s, sv_.av, sv_.aq, dav, daq, dsv, dsq, dcv, dcq, N, T);
     HCA_LAUNCHED();
   }
-  {  // dZq_all = (dsq x wq) * (1 - Hq^2), Hq = tanh(PQ_all + C_all PV) recomputed ; dwq += Hq^T dsq
-    TcEpilogue e; e.mode = TC_EPI_DZ; e.act_tanh = 1; e.colv = wq; e.rowv = dsq; e.rowv_batch_stride = T3; e.red_col = dwq;
-    e.auxp = plv(PQp, 0, T3, B); e.aux_mode = TC_AUX_ADD;
-    e.P = plv(dZq, 0, T3, B);
-    HCA_TRY(launch_gemm_tc(opv(Cp, 0, T3, T3, B, false), opv(PVp, 0, N, N, B, true), 2, T3, d, N, e, 1, s, B));
+  {  // dZq_all = (dsq x wq) * (1 - Hq^2) ; dwq += Hq^T dsq      (Hq saved by the forward pass: element-wise, no product)
+    const int64_t rows = BT3;
+    HCA_CHECK_ARG((rows + HQ_ROWS - 1) / HQ_ROWS <= 0x7fffffff && (d + 127) / 128 <= 65535, "coattn_bwd: too many rows / columns for the Hq backward kernel");
+    HCA_LAUNCH_K((hq_bwd_kernel), dim3((unsigned)((rows + HQ_ROWS - 1) / HQ_ROWS), (unsigned)((d + 127) / 128)), 32 * HQ_WARPS, 0, s, sv_.Hq.p, sv_.Hq.ld,
+                                                           sv_.Hq.ps, dsq, wq, dZq.p, dZq.ld, dZq.ps, dwq, rows, d);
+    HCA_LAUNCHED();
   }
   // dZv_l = (dsv_l x wv) * (1 - Hv_l^2) with Hv_l = tanh(PV + C_l^T PQ_l) recomputed, dwv += Hv_l^T dsv_l, and
   // dPV = sum_l dZv_l + C_all^T dZq_all, dbv += sum_n dPV: one kernel, four TMEM accumulators per tile (hv_fused.cu)

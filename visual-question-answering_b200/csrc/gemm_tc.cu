@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const float* const rowv = FULL ? p.rowv : nullptr;
       const float* const colv = FULL ? p.colv : nullptr;
       const bool do_f32 = (p.D != nullptr) && mode != TC_EPI_ROWDOT;
-      const bool do_pl = (p.P != nullptr) && mode != TC_EPI_ROWDOT;
+      const bool do_pl = (p.P != nullptr);          // (ROWDOT may keep f as planes too: the question-side hidden state saved for backward)
       const bool pl_direct = p.pl_direct != 0;
       const bool stage_tma = (do_f32 && p.tma_store) || (do_pl && !pl_direct);
       const bool want_colred = FULL && (p.red_col != nullptr);
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           if (mode == TC_EPI_ROWDOT) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) rowdot = fmaf(f[j], colv_s[c * 32 + j], rowdot);   // colv_s is 0 beyond N
-            continue;
+            if (!do_pl) continue;
           }
           if (mode == TC_EPI_DZ) {
             // column partials of h * rowv over this warp's 32 rows, then dz = rowv * colv * (1 - h^2)
@@ -1166,7 +1166,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   p.M = M; p.N = N; p.K = K; p.K2 = A2 ? K2 : 0;
   const bool rowdot = e.mode == TC_EPI_ROWDOT;
   const bool want_f32 = e.D != nullptr && !rowdot;
-  const bool want_pl = e.P.p != nullptr && !rowdot;
+  const bool want_pl = e.P.p != nullptr;
   HCA_CHECK_ARG(rowdot || want_f32 || want_pl || e.red_col || (e.transposed && e.red_row), "gemm_tc: no output requested");
   const int groups = e.d_groups > 1 ? e.d_groups : 1;
   HCA_CHECK_ARG(groups == 1 || (M % groups == 0 && M <= BM && !e.transposed), "gemm_tc: grouped output rows need M <= 128, M %% groups == 0");

@@ -347,7 +347,7 @@ def _(V, q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq):
     r8 = lambda x: (x + 7) // 8 * 8
     al = lambda x: (x + 255) // 256 * 256
     pl = lambda rows, cols: al(2 * rows * r8(cols) * 2)
-    nbytes = 2 * pl(B * N, d) + 2 * pl(B * 3 * T, d) + pl(B * 3 * T, N) + al(B * 3 * N * 4) + al(B * 3 * T * 4) + 256
+    nbytes = 2 * pl(B * N, d) + 3 * pl(B * 3 * T, d) + pl(B * 3 * T, N) + al(B * 3 * N * 4) + al(B * 3 * T * 4) + 256
     return V.new_empty(3, B, d), V.new_empty(3, B, d), V.new_empty(nbytes, dtype=torch.uint8)
 
 
