@@ -22,6 +22,7 @@ constexpr int NUM_EG = 2;             // epilogue warp groups (4 warps each: one
 constexpr int NUM_THREADS = 64 + 128 * NUM_EG;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 / 6..9 epilogue groups 0 / 1
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr uint32_t CHUNK_BYTES = BM * 128;    // one [128 rows][32 fp32] staging tile = two [128 rows][32 bf16] plane tiles
+constexpr int NWIN_TM_MAX = 32;               // M tiles of a product with N windows (block-structured outputs)
 
 struct TcParams {
   int M, N, K, K2;
@@ -32,6 +33,8 @@ struct TcParams {
   int store_nbuf;                                            // staging buffers per output kind and epilogue group (2 = double-buffered)
   int n_eg;                                                  // active epilogue groups: 2 for epilogue-bound products (alternate 32-column chunks)
   int kwin_ncol, kwin_lo[4], kwin_hi[4];                     // K windows per group of output columns, in k-blocks (kwin_ncol = 0: off)
+  int nwin_on, tiles_mn;                                     // N windows per group of output rows: only tiles_mn (M tile, N tile) pairs exist;
+  short nw_first[NWIN_TM_MAX], nw_pre[NWIN_TM_MAX + 1];      // M tile mt owns the N tiles nw_first[mt] + [0, nw_pre[mt + 1] - nw_pre[mt])
   // fp32 output
   float* D;
   int64_t ldd, d_sb;
@@ -142,10 +145,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   auto b_tile = [&](int s, int pl) { return smem_base + s * stage_bytes + P * A_TILE_BYTES + pl * B_TILE_BYTES; };
   auto decode = [&](int t) {
     TileCoord c;
-    const int nt = t % p.tiles_n;
-    t /= p.tiles_n;
-    const int mt = t % p.tiles_m;
-    t /= p.tiles_m;
+    int nt, mt;
+    if (p.nwin_on) {                  // block-structured output: walk the (M tile, N tile) pairs that exist
+      const int u = t % p.tiles_mn;
+      t /= p.tiles_mn;
+      mt = 0;
+      while (mt + 1 < p.tiles_m && p.nw_pre[mt + 1] <= u) ++mt;
+      nt = p.nw_first[mt] + (u - p.nw_pre[mt]);
+    } else {
+      nt = t % p.tiles_n;
+      t /= p.tiles_n;
+      mt = t % p.tiles_m;
+      t /= p.tiles_m;
+    }
     const int ks = t % p.splitk;
     c.z = t / p.splitk;
     c.m0 = mt * (BM * CG) + rank * BM;
@@ -1006,8 +1018,32 @@ bool planes_ok(const TcPlanes& t) {
 
 bool tc_available() { return get_encoder() != nullptr; }
 
-int tc_splitk(int M, int N, int K) {
-  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+// N-tile range [first, first + count) of the M tile covering rows [m0, m0 + bm) under the N windows of `e`
+static void nwin_range(const TcEpilogue& e, int M, int N, int m0, int bm, int bn, int& first, int& count) {
+  const int tiles_n = (N + bn - 1) / bn;
+  if (e.nwin_nrow <= 0) { first = 0; count = tiles_n; return; }
+  const int g0 = m0 / e.nwin_nrow, g1 = (std::min(M, m0 + bm) - 1) / e.nwin_nrow;
+  int lo = N, hi = 0;
+  for (int g = g0; g <= g1 && g < 4; ++g) {
+    lo = std::min(lo, std::max(0, e.nwin_lo[g]));
+    hi = std::max(hi, std::min(N, e.nwin_hi[g]));
+  }
+  if (g1 >= 4) { lo = 0; hi = N; }
+  if (hi <= lo) { first = 0; count = 0; return; }
+  first = lo / bn;
+  count = std::min(tiles_n, (hi + bn - 1) / bn) - first;
+}
+int tc_count_tiles(int M, int N, const TcEpilogue& e, int bm, int bn) {
+  int total = 0;
+  for (int m0 = 0; m0 < M; m0 += bm) {
+    int first, count;
+    nwin_range(e, M, N, m0, bm, bn, first, count);
+    total += count;
+  }
+  return total;
+}
+int tc_splitk(int M, int N, int K) { return tc_splitk_tiles(((M + 127) / 128) * ((N + 127) / 128), K); }
+int tc_splitk_tiles(int tiles, int K) {
   const int sms = num_sms();
   if (tiles * 3 >= sms * 2) return 1;             // the tiles alone fill most of a wave
   int sk = sms / tiles;                           // floor: one work item per SM at most
@@ -1131,7 +1167,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   if (pair_wgrad) {
     pair = true;
     // the split is chosen for the pair grid: one 256 x 256 tile per pair and wave, at least 4 k-blocks per split
-    const int t2 = (M / 256) * (N / 256), nc = num_sms() / 2, kbt = (K + 63) / 64;
+    const int t2 = std::max(1, tc_count_tiles(M, N, e, 256, 256)), nc = num_sms() / 2, kbt = (K + 63) / 64;
     int sk = nc / t2;                    // ONE wave: tiles * slices <= pairs (a ceil here left 2 of 76 items for a second wave: 2x the time)
     if (sk > kbt / 4) sk = kbt / 4;
     splitk = sk < 1 ? 1 : sk;
@@ -1266,7 +1302,21 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   }
   p.tiles_m = (M + BM * CGn - 1) / (BM * CGn);
   p.tiles_n = (N + BN - 1) / BN;
-  const int64_t total = (int64_t)p.tiles_m * p.tiles_n * splitk * batch;
+  int64_t tiles_mn = (int64_t)p.tiles_m * p.tiles_n;
+  if (e.nwin_nrow > 0 && batch == 1 && p.tiles_m <= NWIN_TM_MAX && p.tiles_n < 32768) {      // (otherwise: every tile, which is always correct)
+    p.nwin_on = 1;
+    p.nw_pre[0] = 0;
+    for (int mt = 0; mt < p.tiles_m; ++mt) {
+      int first, count;
+      nwin_range(e, M, N, mt * BM * CGn, BM * CGn, BN, first, count);
+      p.nw_first[mt] = (short)first;
+      p.nw_pre[mt + 1] = (short)(p.nw_pre[mt] + count);
+    }
+    tiles_mn = p.nw_pre[p.tiles_m];
+    HCA_CHECK_ARG(tiles_mn > 0, "gemm_tc: the N windows leave no tile");
+  }
+  p.tiles_mn = (int)tiles_mn;
+  const int64_t total = tiles_mn * splitk * batch;
   HCA_CHECK_ARG(total < (1LL << 30), "gemm_tc: too many tiles");
   p.total_tiles = (int)total;
   auto nbf = [](int nb) { return nb > 0 ? nb : 1; };

@@ -83,6 +83,11 @@ struct TcEpilogue {
   // memory (the windows only skip work, they never change the result).
   int kwin_ncol = 0;
   int kwin_lo[4] = {0, 0, 0, 0}, kwin_hi[4] = {0, 0, 0, 0};
+  // Block-structured OUTPUTS (un-batched): of the output rows [g * nwin_nrow, (g + 1) * nwin_nrow) only the columns
+  // [nwin_lo[g], nwin_hi[g]) are wanted (up to 4 groups; 0 = off).  Tiles entirely outside are not computed and their part of D is left
+  // untouched; a tile that straddles is computed whole.
+  int nwin_nrow = 0;
+  int nwin_lo[4] = {0, 0, 0, 0}, nwin_hi[4] = {0, 0, 0, 0};
 };
 
 // D[z][M,N] (+)= A[z] . B[z]^T (+ A2[z] . B2[z]^T with inner size K2) for z < batch.  splitk >= 1 (un-batched only).
@@ -112,6 +117,9 @@ struct SplitBatch {
 // (tiles * slices > SMs means a second, nearly empty wave: measured as a 2x longer kernel on the weight gradients) -- with at least
 // 4 k-blocks (256 of K) per slice.
 int tc_splitk(int M, int N, int K);
+int tc_splitk_tiles(int tiles, int K);                       // the same rule for a given number of output tiles
+// 128 x 128 output tiles of an M x N product that the N windows of `e` (if any) leave to be computed
+int tc_count_tiles(int M, int N, const TcEpilogue& e, int bm = 128, int bn = 128);
 
 bool tc_available();   // TMA descriptor encoder resolved from the driver
 // generic tiled TMA descriptor (rank 2..5) for the other hand-written kernels: `tm` points at a CUtensorMap; dims / box in

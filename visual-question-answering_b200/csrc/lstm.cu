@@ -134,7 +134,6 @@ __device__ __forceinline__ void publish_fence() {
   asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_all() { asm volatile("bar.sync 1, 320;" ::: "memory"); }      // the 10 epilogue warps
 __device__ __forceinline__ void reader_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }       // the 4 TMEM-reader warps
 // ---- distributed shared memory (cluster of L_KSPLIT CTAs, backward) ----
@@ -547,19 +546,6 @@ __device__ __forceinline__ int perm_row(int jp, int H) {
   const int ni = jp >> 6, rem = jp & 63;
   return (rem & 3) * H + ni * L_UNITS + (rem >> 2);
 }
-// planes [2][4H][cols] <- W[perm][cols]
-__global__ void __launch_bounds__(256) lstm_split_perm_kernel(const float* __restrict__ W, int H, int cols, __nv_bfloat16* __restrict__ planes,
-                                                              int64_t ps) {
-  pdl_enter();
-  const int64_t total = (int64_t)4 * H * cols;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int jp = (int)(i / cols), c = (int)(i - (int64_t)jp * cols);
-    const float x = W[(int64_t)perm_row(jp, H) * cols + c];
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    planes[i] = h;
-    planes[ps + i] = __float2bfloat16_rn(x - __bfloat162float(h));
-  }
-}
 // planes [2][H][4H] <- W_hh[perm(j')][k] at [k][j']   (the resident operand of the backward recurrence)
 __global__ void __launch_bounds__(256) lstm_split_perm_t_kernel(const float* __restrict__ Whh, int H, __nv_bfloat16* __restrict__ planes,
                                                                 int64_t ps) {
@@ -600,29 +586,6 @@ __global__ void __launch_bounds__(256) lstm_prep_kernel(const float* __restrict_
     }
   }
 }
-__global__ void __launch_bounds__(256) lstm_bias_perm_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, int H,
-                                                             float* __restrict__ out) {
-  pdl_enter();
-  const int jp = blockIdx.x * blockDim.x + threadIdx.x;
-  if (jp < 4 * H) {
-    const int j = perm_row(jp, H);
-    out[jp] = b_ih[j] + b_hh[j];
-  }
-}
-// dst[perm(j')][c] = src[j'][c]   (dst2 optional second destination: b_ih and b_hh receive the same gradient)
-__global__ void __launch_bounds__(256) lstm_unperm_kernel(const float* __restrict__ src, int H, int cols, float* __restrict__ dst,
-                                                          float* __restrict__ dst2) {
-  pdl_enter();
-  const int64_t total = (int64_t)4 * H * cols;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int jp = (int)(i / cols), c = (int)(i - (int64_t)jp * cols);
-    const float v = src[i];
-    const int64_t o = (int64_t)perm_row(jp, H) * cols + c;
-    dst[o] = v;
-    if (dst2) dst2[o] = v;
-  }
-}
-
 // dW_ih, dW_hh and the bias gradient (both b_ih and b_hh receive it) in one launch
 __global__ void __launch_bounds__(256) lstm_unperm3_kernel(const float* __restrict__ dwi, const float* __restrict__ dwh,
                                                            const float* __restrict__ dbp, int H, int E, float* __restrict__ dw_ih,

@@ -350,19 +350,20 @@ __global__ void __launch_bounds__(256) pool3_bwd_planes_kernel(const float* __re
     atomicAdd(db + (c % E), sv[j]);
   }
 }
-// tap-major fp32 weight gradients -> conv layout: w[o][c][j] = wr[o][j*E + c]
-// both in one launch (bigram and trigram weight gradients)
-__global__ void __launch_bounds__(256) unpack_conv_w23_kernel(const float* __restrict__ wr2, float* __restrict__ w2,
-                                                              const float* __restrict__ wr3, float* __restrict__ w3, int E) {
+// block-structured fp32 weight gradient dWcat [3E][3E] (row (k-1) E + o, column = Acat tap column) -> the three conv layouts
+// w_k[o][c][j] = dWcat[(k-1) E + o][(j + (k == 1)) E + c], one launch
+__global__ void __launch_bounds__(256) unpack_conv_w_kernel(const float* __restrict__ dwcat, float* __restrict__ w1, float* __restrict__ w2,
+                                                            float* __restrict__ w3, int E) {
   pdl_enter();
-  const int64_t n2 = (int64_t)E * E * 2, total = n2 + (int64_t)E * E * 3;
+  const int64_t EE = (int64_t)E * E, total = 6 * EE, E3 = 3 * (int64_t)E;
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-    const int k = g < n2 ? 2 : 3;
-    const int64_t i = g < n2 ? g : g - n2;
+    const int k = g < EE ? 1 : (g < 3 * EE ? 2 : 3);
+    const int64_t i = g - (k == 1 ? 0 : (k == 2 ? EE : 3 * EE));
     const int j = (int)(i % k);
     const int c = (int)((i / k) % E);
     const int64_t o = i / ((int64_t)E * k);
-    (k == 2 ? w2 : w3)[i] = (k == 2 ? wr2 : wr3)[(o * k + j) * E + c];
+    const float v = dwcat[((k - 1) * (int64_t)E + o) * E3 + (int64_t)(j + (k == 1 ? 1 : 0)) * E + c];
+    (k == 1 ? w1 : (k == 2 ? w2 : w3))[i] = v;
   }
 }
 
@@ -370,7 +371,7 @@ int g_tie_cap_override = 0;      // test hook (hca_set_option("pool_tie_cap", n)
 
 struct ConvWs {
   Workspace w;
-  float *cat, *dA, *dwr2, *dwr3, *xn2, *wn, *bcat;
+  float *cat, *dA, *dwcat, *xn2, *wn, *bcat;
   int *tie_count, *tie_list;
   int tie_cap;
   bool ok;
@@ -383,8 +384,7 @@ ConvWs carve(void* ws, size_t bytes, int B, int T, int E) {
   const size_t R = (size_t)B * T;
   c.cat = w.take<float>(R * 3 * E);     // fwd: tanh(conv)
   c.dA = w.take<float>(R * 3 * E);
-  c.dwr2 = w.take<float>((size_t)E * 2 * E);
-  c.dwr3 = w.take<float>((size_t)E * 3 * E);
+  c.dwcat = w.take<float>((size_t)9 * E * E);
   c.xn2 = w.take<float>(R);
   c.wn = w.take<float>((size_t)3 * E);
   c.bcat = w.take<float>((size_t)3 * E);
@@ -403,7 +403,7 @@ void set_pool_tie_cap(int n) { g_tie_cap_override = n; }
 extern "C" size_t hca_phrase_conv_pool_workspace(int B, int T, int E) {
   using hca::align_up;
   const size_t R = (size_t)B * T;
-  return 2 * align_up(R * 3 * E * 4) + align_up((size_t)E * 2 * E * 4) + align_up((size_t)E * 3 * E * 4) + align_up(R * 4) +
+  return 2 * align_up(R * 3 * E * 4) + align_up((size_t)9 * E * E * 4) + align_up(R * 4) +
          2 * align_up((size_t)3 * E * 4) + 1024 + align_up(hca::tie_cap_default(R, E) * 4) +      // near-tie list
          2 * 2 * align_up(R * 3 * E * 2) + align_up((size_t)2 * 3 * E * 3 * E * 2) + 8192;          // bf16 planes when no `fsaved` is given
 }
@@ -511,32 +511,34 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
     HCA_LAUNCH_K((im2col3_planes_kernel<2>), ew_grid((int64_t)R * 3 * E / 4), 256, 0, s, (const float4*)x, ap, pstride, B, T, E / 4);
     HCA_LAUNCHED();
   }
-  float* dbs[3] = {db1, db2, db3};
-  float* dwr[3] = {dw1, c.dwr2, c.dwr3};
-  int sks[3];
-  {  // bias gradients and the split-K weight-gradient accumulators cleared by one launch
+  // weight gradients as ONE product: dWcat[oc][kk] = sum_r dcat[r][oc] * Acat[r][kk] (K = R, split-K), of which only the blocks a filter
+  // family has taps in are computed (row group k: the tap columns of its window) -- 6 of the 9 E x E blocks
+  const int64_t E3w = 3 * (int64_t)E;
+  TcEpilogue epw;
+  epw.D = c.dwcat; epw.ldd = E3w;
+  epw.nwin_nrow = E;
+  epw.nwin_lo[0] = E; epw.nwin_hi[0] = 2 * E;
+  epw.nwin_lo[1] = 0; epw.nwin_hi[1] = 2 * E;
+  epw.nwin_lo[2] = 0; epw.nwin_hi[2] = 3 * E;
+  // (split-K: the pair-mode launcher re-sizes the split for its own tile grid when the shape qualifies -- any value > 1 says "D is cleared")
+  int skw = tc_splitk_tiles(tc_count_tiles((int)E3w, (int)E3w, epw), R);
+  if (skw < 2 && R >= 2048) skw = 2;
+  {  // bias gradients and the split-K weight-gradient accumulator cleared by one launch
     ZeroBatch zb(s);
-    for (int k = 1; k <= 3; ++k) {
-      HCA_TRY(zb.add(dbs[k - 1], (size_t)E * 4));
-      sks[k - 1] = tc_splitk(E, k * E, R);
-      if (sks[k - 1] > 1) HCA_TRY(zb.add(dwr[k - 1], (size_t)E * k * E * 4));
-    }
+    HCA_TRY(zb.add(db1, (size_t)E * 4)); HCA_TRY(zb.add(db2, (size_t)E * 4)); HCA_TRY(zb.add(db3, (size_t)E * 4));
+    if (skw > 1) HCA_TRY(zb.add(c.dwcat, (size_t)9 * E * E * 4));
     HCA_TRY(zb.flush());
   }
   HCA_LAUNCH_K((pool3_bwd_planes_kernel), dim3((E + 255) / 256, (R + POOL_BWD_ROWS - 1) / POOL_BWD_ROWS), 256, 0, s, out, idx, dout, lens, dp, pstride, db1,
                                                                                                      db2, db3, B, T, E);
   HCA_LAUNCHED();
-  // weight gradients, tap-major: dWr_k[o][kk] = sum_r dcat[r][(k-1)E + o] * Acat[r][a_off + kk]   (K = R, split-K)
-  for (int k = 1; k <= 3; ++k) {
+  {
     TcOperand A, Bm;
-    A.planes = dp + (k - 1) * E; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = E; A.mn_major = true;
-    Bm.planes = ap + (k == 1 ? E : 0); Bm.ld = ld3; Bm.plane_stride = pstride; Bm.rows = R; Bm.cols = k * E; Bm.mn_major = true;
-    const int sk = sks[k - 1];
-    TcEpilogue ep;
-    ep.D = dwr[k - 1]; ep.ldd = (int64_t)k * E;
-    HCA_TRY(launch_gemm_tc(A, Bm, 2, E, k * E, R, ep, sk, s));
+    A.planes = dp; A.ld = ld3; A.plane_stride = pstride; A.rows = R; A.cols = (int)E3w; A.mn_major = true;
+    Bm.planes = ap; Bm.ld = ld3; Bm.plane_stride = pstride; Bm.rows = R; Bm.cols = (int)E3w; Bm.mn_major = true;
+    HCA_TRY(launch_gemm_tc(A, Bm, 2, (int)E3w, (int)E3w, R, epw, skw, s));
   }
-  HCA_LAUNCH_K((unpack_conv_w23_kernel), ew_grid((int64_t)E * E * 5), 256, 0, s, c.dwr2, dw2, c.dwr3, dw3, E);
+  HCA_LAUNCH_K((unpack_conv_w_kernel), ew_grid((int64_t)E * E * 6), 256, 0, s, c.dwcat, dw1, dw2, dw3, E);
   HCA_LAUNCHED();
   if (dx) {
     // dA[r][kk] = sum_oc dcat[r][oc] * Wcat[oc][kk]: ONE product with the block-structured weight matrix as the MN-major operand; tap
