@@ -558,17 +558,14 @@ extern "C" int hca_coattn_fwd(const float* V, int64_t v_sb, int64_t v_sn, int64_
   float* sqs = sc + (size_t)3 * B * N;      // [B][3][T]
   const Pl &Qp = sv_.Q, &PVp = sv_.PV, &PQp = sv_.PQ, &Cp = sv_.C;
   HCA_TRY(launch_split_planes_stack3(q0, q1, q2, B, T, d, Qp.p, Qp.ld, Qp.ps, s));
-  {  // both projection weights -> operand planes, one launch
+  {  // both projection weights -> operand planes, and the two accumulated outputs (scores, attended image features) cleared: one launch
     SplitBatch sb(s);
     HCA_TRY(sb.add(Wv, d, d, d, Wvp.p, Wvp.ld, Wvp.ps));
     HCA_TRY(sb.add(Wq, d, d, d, Wqp.p, Wqp.ld, Wqp.ps));
-    HCA_TRY(sb.flush());
-  }
-  {  // the two accumulated outputs (scores, attended image features) cleared by one launch
     ZeroBatch zb(s);
     HCA_TRY(zb.add(sc, (size_t)3 * B * (N + T) * 4));
     HCA_TRY(zb.add(vhat, (size_t)3 * B * d * 4));
-    HCA_TRY(zb.flush());
+    HCA_TRY(sb.flush(zb));
   }
   {  // PV = V Wv^T + bv   (once per step: level independent)
     TcEpilogue e; e.bias = bv; e.P = plv(PVp, 0, BN, 1);
@@ -625,17 +622,18 @@ extern "C" int hca_coattn_bwd(const float* Wv, const float* Wq, const float* wv,
   float* dsv = dsc;                        // [B][3][N]
   float* dsq = dsc + (size_t)3 * B * N;    // [B][3][T]
 
-  HCA_TRY(split_to(Wqp, Wq, d, s));
-  if (dV) HCA_TRY(split_to(Wvp, Wv, d, s));
   const int sk_wq = tc_splitk(d, d, (int)BT3), sk_wv = tc_splitk(d, d, (int)BN);
-  {  // every accumulated output of this call (bias / score-vector gradients, split-K weight gradients) cleared by one launch
+  {  // weight planes, and every accumulated output of this call (bias / score-vector gradients, split-K weight gradients) cleared: one launch
+    SplitBatch sb(s);
+    HCA_TRY(sb.add(Wq, d, d, d, Wqp.p, Wqp.ld, Wqp.ps));
+    if (dV) HCA_TRY(sb.add(Wv, d, d, d, Wvp.p, Wvp.ld, Wvp.ps));
     ZeroBatch zb(s);
     HCA_TRY(zb.add(dcv, 4)); HCA_TRY(zb.add(dcq, 4));
     HCA_TRY(zb.add(dwv, (size_t)d * 4)); HCA_TRY(zb.add(dwq, (size_t)d * 4));
     HCA_TRY(zb.add(dbv, (size_t)d * 4)); HCA_TRY(zb.add(dbq, (size_t)d * 4));
     if (sk_wq > 1) HCA_TRY(zb.add(dWq, (size_t)d * d * 4));
     if (sk_wv > 1) HCA_TRY(zb.add(dWv, (size_t)d * d * 4));
-    HCA_TRY(zb.flush());
+    HCA_TRY(sb.flush(zb));
   }
   {
     const size_t smem = (size_t)6 * d * sizeof(float);

@@ -861,8 +861,9 @@ struct SplitJobs {
   long long start[SplitBatch::MAX + 1];      // prefix sums of the jobs' float4 counts
   int count;
 };
-__global__ void __launch_bounds__(256) split_planes_multi_kernel(const SplitJobs jobs) {
+__global__ void __launch_bounds__(256) split_planes_multi_kernel(const SplitJobs jobs, const ZeroJobs zero) {
   pdl_enter();
+  zero_jobs_device(zero);
   const long long total = jobs.start[jobs.count];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int j = 0;
@@ -1102,7 +1103,11 @@ int SplitBatch::add(const float* src, int64_t ld, int64_t rows, int cols, __nv_b
 }
 
 int SplitBatch::flush() {
-  if (count == 0) return 0;
+  ZeroBatch none(stream);
+  return flush(none);
+}
+int SplitBatch::flush(ZeroBatch& also_clear) {
+  if (count == 0) return also_clear.flush();
   SplitJobs jobs;
   memset(&jobs, 0, sizeof(jobs));
   long long total = 0;
@@ -1114,7 +1119,9 @@ int SplitBatch::flush() {
   jobs.start[count] = total;
   jobs.count = count;
   count = 0;
-  HCA_LAUNCH_K((split_planes_multi_kernel), ew_grid(total), 256, 0, stream, jobs);
+  unsigned long long zwords = 0;
+  for (int i = 0; i < also_clear.count; ++i) zwords += also_clear.words[i];
+  HCA_LAUNCH_K((split_planes_multi_kernel), ew_grid(std::max<long long>(total, (long long)(zwords / 4 + 1))), 256, 0, stream, jobs, also_clear.take());
   HCA_LAUNCHED();
   return 0;
 }

@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "util_kernels.cuh"
 
 namespace hca {
 
@@ -111,6 +112,7 @@ struct SplitBatch {
   explicit SplitBatch(cudaStream_t s) : stream(s) {}
   int add(const float* src, int64_t ld, int64_t rows, int cols, __nv_bfloat16* planes, int64_t ldp, int64_t plane_stride);
   int flush();
+  int flush(ZeroBatch& also_clear);    // the same launch also clears the buffers collected in `also_clear` (and empties it)
 };
 
 // Split-K factor for an un-batched product whose output has few tiles: as many K slices as give every SM ONE work item -- never more

@@ -548,8 +548,9 @@ __device__ __forceinline__ int perm_row(int jp, int H) {
 }
 // planes [2][H][4H] <- W_hh[perm(j')][k] at [k][j']   (the resident operand of the backward recurrence)
 __global__ void __launch_bounds__(256) lstm_split_perm_t_kernel(const float* __restrict__ Whh, int H, __nv_bfloat16* __restrict__ planes,
-                                                                int64_t ps) {
+                                                                int64_t ps, const ZeroJobs zero) {
   pdl_enter();
+  zero_jobs_device(zero);          // (the backward call's accumulators and counters: one launch less)
   const int64_t total = (int64_t)4 * H * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i / (4 * H)), jp = (int)(i - (int64_t)k * 4 * H);
@@ -563,8 +564,9 @@ __global__ void __launch_bounds__(256) lstm_split_perm_t_kernel(const float* __r
 __global__ void __launch_bounds__(256) lstm_prep_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                                                         const float* __restrict__ b_ih, const float* __restrict__ b_hh, int H, int E,
                                                         __nv_bfloat16* __restrict__ wip, __nv_bfloat16* __restrict__ whp,
-                                                        float* __restrict__ biasp) {
+                                                        float* __restrict__ biasp, const ZeroJobs zero) {
   pdl_enter();
+  zero_jobs_device(zero);          // (the h planes and the step counters of the forward call: one launch less)
   const int64_t n1 = (int64_t)4 * H * E, n2 = (int64_t)4 * H * H, total = n1 + n2 + 4 * H;
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
     if (g < n1 + n2) {
@@ -843,13 +845,12 @@ extern "C" int hca_lstm_fwd(const float* x, const int64_t* lens, const float* w_
   int* counters = w.take<int>(counter_count(B, T));
   if (!counters) return set_err(HCA_ERR_WORKSPACE, "lstm_fwd: workspace too small (%zu bytes)", ws_bytes);
   HCA_TRY(launch_split_planes(x, E, BT, E, sv.xp, E, BT * E, 2, s));
-  HCA_LAUNCH_K((lstm_prep_kernel), ew_grid((int64_t)H4 * (E + H + 1)), 256, 0, s, w_ih, w_hh, b_ih, b_hh, H, E, wip, whp, biasp);
-  HCA_LAUNCHED();
   {
     ZeroBatch zb(s);
     HCA_TRY(zb.add(sv.hp, (size_t)2 * BT * H * 2));            // slot 0 (h_{-1} = 0) and the slots no step reaches
     HCA_TRY(zb.add(counters, counter_count(B, T) * 4));
-    HCA_TRY(zb.flush());
+    HCA_LAUNCH_K((lstm_prep_kernel), ew_grid((int64_t)H4 * (E + H + 1)), 256, 0, s, w_ih, w_hh, b_ih, b_hh, H, E, wip, whp, biasp, zb.take());
+    HCA_LAUNCHED();
   }
   {  // x-projection of every (b, t), gate columns in [unit][gate] order, biases folded in
     TcEpilogue e;
@@ -893,10 +894,9 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
     HCA_TRY(zb.add(counters, counter_count(B, T) * 4));
     if (sk_wi > 1) HCA_TRY(zb.add(dwi, (size_t)H4 * E * 4));
     if (sk_wh > 1) HCA_TRY(zb.add(dwh, (size_t)H4 * H * 4));
-    HCA_TRY(zb.flush());
+    HCA_LAUNCH_K((lstm_split_perm_t_kernel), ew_grid((int64_t)H4 * H), 256, 0, s, w_hh, H, wtp, (int64_t)H4 * H, zb.take());
+    HCA_LAUNCHED();
   }
-  HCA_LAUNCH_K((lstm_split_perm_t_kernel), ew_grid((int64_t)H4 * H), 256, 0, s, w_hh, H, wtp, (int64_t)H4 * H);
-  HCA_LAUNCHED();
   LstmParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.T = T; p.H = H; p.lens = lens; p.counters = counters;

@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(256) mlp_inputs_planes_kernel(const float4* __
 // planes of X [rows, cols] (leading dim ld) + its column sums: block = 32 columns x 8 row lanes over all rows
 __global__ void __launch_bounds__(256) split_colsum_kernel(const float* __restrict__ X, int64_t ld, int rows, int cols,
                                                            __nv_bfloat16* __restrict__ planes, int64_t ldp, int64_t ps,
-                                                           float* __restrict__ colsum) {
+                                                           float* __restrict__ colsum, const ZeroJobs zero) {
   pdl_enter();
+  zero_jobs_device(zero);          // (the bias gradients the data-gradient products accumulate into: one launch less)
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -227,12 +228,11 @@ extern "C" int hca_mlp_bwd(const float* dlogits, const void* saved, size_t saved
   SideStream side(s);
   cudaStream_t sw = side.stream();
   // W_h: planes of dlogits + db_h in one pass; dW_h; dz_s = (dlogits W_h) * (1 - h_s^2) with db_s
-  HCA_LAUNCH_K((split_colsum_kernel), (K + 31) / 32, 256, 0, s, dlogits, K, B, K, dl.p, dl.ld, dl.ps, dbh);
-  HCA_LAUNCHED();
   {
     ZeroBatch zb(s);
     HCA_TRY(zb.add(dbs, (size_t)mlp * 4)); HCA_TRY(zb.add(dbp, (size_t)d * 4)); HCA_TRY(zb.add(dbw, (size_t)d * 4));
-    HCA_TRY(zb.flush());
+    HCA_LAUNCH_K((split_colsum_kernel), (K + 31) / 32, 256, 0, s, dlogits, K, B, K, dl.p, dl.ld, dl.ps, dbh, zb.take());
+    HCA_LAUNCHED();
   }
   HCA_TRY(side.fork());
   HCA_TRY(bwd_weight(dl, K, sv.hs, mlp, B, dWh, sw));

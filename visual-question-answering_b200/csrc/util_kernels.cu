@@ -31,28 +31,20 @@ int launch_colsum(const float* X, int64_t ld, int64_t rows, int cols, float* out
 }
 
 namespace {
-struct ZeroJobs {
-  void* ptr[ZeroBatch::MAX];
-  unsigned long long words[ZeroBatch::MAX];
-  int count;
-};
 __global__ void __launch_bounds__(256) zero_many_kernel(const ZeroJobs jobs) {
   pdl_enter();
-  const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x, nthr = (unsigned long long)gridDim.x * blockDim.x;
-  for (int j = 0; j < jobs.count; ++j) {
-    uint32_t* p = (uint32_t*)jobs.ptr[j];
-    const unsigned long long n = jobs.words[j];
-    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-      uint4* p4 = (uint4*)p;
-      const unsigned long long n4 = n >> 2;
-      for (unsigned long long i = tid; i < n4; i += nthr) p4[i] = make_uint4(0u, 0u, 0u, 0u);
-      for (unsigned long long i = (n4 << 2) + tid; i < n; i += nthr) p[i] = 0u;
-    } else {
-      for (unsigned long long i = tid; i < n; i += nthr) p[i] = 0u;
-    }
-  }
+  zero_jobs_device(jobs);
 }
 }  // namespace
+
+ZeroJobs ZeroBatch::take() {
+  ZeroJobs jobs;
+  for (int i = 0; i < count; ++i) { jobs.ptr[i] = ptr[i]; jobs.words[i] = words[i]; }
+  for (int i = count; i < MAX; ++i) { jobs.ptr[i] = nullptr; jobs.words[i] = 0; }
+  jobs.count = count;
+  count = 0;
+  return jobs;
+}
 
 int ZeroBatch::add(void* p, size_t bytes) {
   if (!p || bytes == 0) return 0;
@@ -66,12 +58,9 @@ int ZeroBatch::add(void* p, size_t bytes) {
 
 int ZeroBatch::flush() {
   if (count == 0) return 0;
-  ZeroJobs jobs;
   unsigned long long total = 0;
-  for (int i = 0; i < count; ++i) { jobs.ptr[i] = ptr[i]; jobs.words[i] = words[i]; total += words[i]; }
-  for (int i = count; i < MAX; ++i) { jobs.ptr[i] = nullptr; jobs.words[i] = 0; }
-  jobs.count = count;
-  count = 0;
+  for (int i = 0; i < count; ++i) total += words[i];
+  const ZeroJobs jobs = take();
   HCA_LAUNCH_K((zero_many_kernel), ew_grid((int64_t)(total / 4 + 1)), 256, 0, stream, jobs);
   HCA_LAUNCHED();
   return 0;
