@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) conv_w_planes3_kernel(const float* __rest
                                                              const float* __restrict__ w3, const float* __restrict__ b1,
                                                              const float* __restrict__ b2, const float* __restrict__ b3,
                                                              __nv_bfloat16* __restrict__ planes, float* __restrict__ bcat, int E,
-                                                             int* __restrict__ tie_count) {
+                                                             int* __restrict__ tie_count, int write_zeros) {
   pdl_enter();
   if (tie_count && blockIdx.x == 0 && threadIdx.x == 0) *tie_count = 0;
   const int64_t E3 = 3 * (int64_t)E, total = E3 * E3, ps = total;
@@ -303,6 +303,9 @@ __global__ void __launch_bounds__(256) conv_w_planes3_kernel(const float* __rest
     if (j >= 0 && j < k) {
       const float* w = k == 1 ? w1 : (k == 2 ? w2 : w3);
       x = w[((int64_t)o * E + c) * k + j];
+    } else if (!write_zeros) {        // (E % 128 == 0: no tile of the products straddles a block boundary, the zero blocks are never read)
+      if (bcat && col == 0) bcat[row] = (k == 1 ? b1 : (k == 2 ? b2 : b3))[o];
+      continue;
     }
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
     planes[g] = h;
@@ -311,59 +314,84 @@ __global__ void __launch_bounds__(256) conv_w_planes3_kernel(const float* __rest
   }
 }
 // Pool backward straight into operand planes: dcat[r][3e+j] = (j == idx) ? dout * (1 - out^2) : 0 as bf16 hi/lo planes
-// [2][R][3E], plus the three bias gradients (column sums of dcat over r).  Thread <-> one channel triple e, block <-> a slab
-// of rows, so the column sums stay in registers until one atomic per column and block.
+// [2][R][3E], plus the three bias gradients (column sums of dcat over r).  Thread <-> FOUR consecutive channel triples (one float4 of out /
+// dout, 12 consecutive bf16 = three 8-byte stores per plane: a warp writes 768 contiguous bytes), block = 64 such threads x 4 row lanes over
+// a slab of rows; the column sums meet in shared memory: one atomic per column and block.
 constexpr int POOL_BWD_ROWS = 32;
 __global__ void __launch_bounds__(256) pool3_bwd_planes_kernel(const float* __restrict__ out, const uint8_t* __restrict__ idx,
                                                                const float* __restrict__ dout, const int64_t* __restrict__ lens,
                                                                __nv_bfloat16* __restrict__ planes, int64_t ps, float* __restrict__ db1,
                                                                float* __restrict__ db2, float* __restrict__ db3, int B, int T, int E) {
   pdl_enter();
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
+  __shared__ float red[4][64 * 12];
+  const int ct = threadIdx.x & 63, rl = threadIdx.x >> 6;          // column thread, row lane
+  const int e0 = (blockIdx.x * 64 + ct) * 4;                        // first of this thread's 4 channel triples
   const int64_t R = (int64_t)B * T;
   const int64_t r0 = (int64_t)blockIdx.y * POOL_BWD_ROWS, r1 = min(R, r0 + POOL_BWD_ROWS);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll 4                      // four rows' loads in flight per thread (the rows are independent; one at a time is latency-bound)
-  for (int64_t r = r0; r < r1; ++r) {
-    const int b = (int)(r / T), t = (int)(r - (int64_t)b * T);
-    float g = 0.f;
-    int j = 0;
-    if (!lens || t < lens[b]) {
-      const float o = out[r * E + e];
-      g = dout[r * E + e] * (1.f - o * o);
-      j = idx[r * E + e];
-    }
-    const __nv_bfloat16 h = __float2bfloat16_rn(g);
-    const __nv_bfloat16 l = __float2bfloat16_rn(g - __bfloat162float(h));
-    const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
-    __nv_bfloat16* ph = planes + r * 3 * (int64_t)E + 3 * e;
-    ph[0] = j == 0 ? h : z; ph[1] = j == 1 ? h : z; ph[2] = j == 2 ? h : z;
-    ph[ps] = j == 0 ? l : z; ph[ps + 1] = j == 1 ? l : z; ph[ps + 2] = j == 2 ? l : z;
-    s0 += j == 0 ? g : 0.f; s1 += j == 1 ? g : 0.f; s2 += j == 2 ? g : 0.f;
-  }
-  const float sv[3] = {s0, s1, s2};
+  float sum[12];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const int c = 3 * e + j;                    // channel of the concatenated [uni|bi|tri] axis
-    float* db = c < E ? db1 : (c < 2 * E ? db2 : db3);
-    atomicAdd(db + (c % E), sv[j]);
+  for (int j = 0; j < 12; ++j) sum[j] = 0.f;
+  if (e0 < E) {
+#pragma unroll 4                      // several rows' loads in flight per thread (the rows are independent)
+    for (int64_t r = r0 + rl; r < r1; r += 4) {
+      const int b = (int)(r / T), t = (int)(r - (int64_t)b * T);
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      int jj[4] = {0, 0, 0, 0};
+      if (!lens || t < lens[b]) {
+        const float4 o = *reinterpret_cast<const float4*>(out + r * E + e0);
+        const float4 d = *reinterpret_cast<const float4*>(dout + r * E + e0);
+        const uchar4 ix = *reinterpret_cast<const uchar4*>(idx + r * E + e0);
+        g[0] = d.x * (1.f - o.x * o.x); g[1] = d.y * (1.f - o.y * o.y); g[2] = d.z * (1.f - o.z * o.z); g[3] = d.w * (1.f - o.w * o.w);
+        jj[0] = ix.x; jj[1] = ix.y; jj[2] = ix.z; jj[3] = ix.w;
+      }
+      __nv_bfloat16 hi[12], lo[12];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(g[q]);
+        const __nv_bfloat16 l = __float2bfloat16_rn(g[q] - __bfloat162float(h));
+        const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const bool on = jj[q] == j;
+          hi[3 * q + j] = on ? h : z;
+          lo[3 * q + j] = on ? l : z;
+          sum[3 * q + j] += on ? g[q] : 0.f;
+        }
+      }
+      __nv_bfloat16* ph = planes + r * 3 * (int64_t)E + 3 * e0;       // (3 e0 is a multiple of 12: 8-byte aligned)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        reinterpret_cast<uint2*>(ph)[v] = reinterpret_cast<const uint2*>(hi)[v];
+        reinterpret_cast<uint2*>(ph + ps)[v] = reinterpret_cast<const uint2*>(lo)[v];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 12; ++j) red[rl][ct * 12 + j] = sum[j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 12; i += blockDim.x) {
+    const int c = blockIdx.x * 64 * 12 + i;                         // channel of the concatenated [uni|bi|tri] axis
+    if (c < 3 * E) {
+      const float v = red[0][i] + red[1][i] + red[2][i] + red[3][i];
+      float* db = c < E ? db1 : (c < 2 * E ? db2 : db3);
+      atomicAdd(db + (c % E), v);
+    }
   }
 }
 // block-structured fp32 weight gradient dWcat [3E][3E] (row (k-1) E + o, column = Acat tap column) -> the three conv layouts
-// w_k[o][c][j] = dWcat[(k-1) E + o][(j + (k == 1)) E + c], one launch
+// w_k[o][c][j] = dWcat[(k-1) E + o][(j + (k == 1)) E + c], one launch; threads walk dWcat's rows (coalesced reads, stride-k writes)
 __global__ void __launch_bounds__(256) unpack_conv_w_kernel(const float* __restrict__ dwcat, float* __restrict__ w1, float* __restrict__ w2,
                                                             float* __restrict__ w3, int E) {
   pdl_enter();
   const int64_t EE = (int64_t)E * E, total = 6 * EE, E3 = 3 * (int64_t)E;
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
     const int k = g < EE ? 1 : (g < 3 * EE ? 2 : 3);
-    const int64_t i = g - (k == 1 ? 0 : (k == 2 ? EE : 3 * EE));
-    const int j = (int)(i % k);
-    const int c = (int)((i / k) % E);
+    const int64_t i = g - (k == 1 ? 0 : (k == 2 ? EE : 3 * EE));    // = (o * k + j) * E + c
+    const int c = (int)(i % E);
+    const int j = (int)((i / E) % k);
     const int64_t o = i / ((int64_t)E * k);
     const float v = dwcat[((k - 1) * (int64_t)E + o) * E3 + (int64_t)(j + (k == 1 ? 1 : 0)) * E + c];
-    (k == 1 ? w1 : (k == 2 ? w2 : w3))[i] = v;
+    (k == 1 ? w1 : (k == 2 ? w2 : w3))[(o * E + c) * k + j] = v;
   }
 }
 
@@ -462,7 +490,7 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
   const int64_t E3 = 3 * (int64_t)E;
   __nv_bfloat16* wcat = fsaved ? sv.wcat : c.w.take<__nv_bfloat16>((size_t)P * E3 * E3);
   if (!wcat) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for weight planes");
-  HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid(E3 * E3), 256, 0, s, w1, w2, w3, b1, b2, b3, wcat, c.bcat, E, c.tie_count);
+  HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid(E3 * E3), 256, 0, s, w1, w2, w3, b1, b2, b3, wcat, c.bcat, E, c.tie_count, (E % 128) != 0 ? 1 : 0);
   HCA_LAUNCHED();
   HCA_LAUNCH_K((conv_norms_kernel), std::min(148 * 4, (R + 3 * E + 7) / 8), 256, 0, s, x, w1, w2, w3, c.xn2, c.wn, R, E);
   HCA_LAUNCHED();
@@ -529,7 +557,7 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
     if (skw > 1) HCA_TRY(zb.add(c.dwcat, (size_t)9 * E * E * 4));
     HCA_TRY(zb.flush());
   }
-  HCA_LAUNCH_K((pool3_bwd_planes_kernel), dim3((E + 255) / 256, (R + POOL_BWD_ROWS - 1) / POOL_BWD_ROWS), 256, 0, s, out, idx, dout, lens, dp, pstride, db1,
+  HCA_LAUNCH_K((pool3_bwd_planes_kernel), dim3((E / 4 + 63) / 64, (R + POOL_BWD_ROWS - 1) / POOL_BWD_ROWS), 256, 0, s, out, idx, dout, lens, dp, pstride, db1,
                                                                                                      db2, db3, B, T, E);
   HCA_LAUNCHED();
   {
@@ -548,7 +576,7 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
     if (!wcat) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for weight planes");
     if (!fsaved) {
       HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid(E3 * E3), 256, 0, s, w1, w2, w3, (const float*)nullptr, (const float*)nullptr,
-                                                                   (const float*)nullptr, wcat, (float*)nullptr, E, (int*)nullptr);
+                                                                   (const float*)nullptr, wcat, (float*)nullptr, E, (int*)nullptr, (E % 128) != 0 ? 1 : 0);
       HCA_LAUNCHED();
     }
     TcOperand A, Bm;
