@@ -546,18 +546,35 @@ __device__ __forceinline__ int perm_row(int jp, int H) {
   const int ni = jp >> 6, rem = jp & 63;
   return (rem & 3) * H + ni * L_UNITS + (rem >> 2);
 }
-// planes [2][H][4H] <- W_hh[perm(j')][k] at [k][j']   (the resident operand of the backward recurrence)
+// planes [2][H][4H] <- W_hh[perm(j')][k] at [k][j']   (the resident operand of the backward recurrence): 32 x 32 tiles through shared memory,
+// rows of W_hh read along k, plane rows written along j' (both coalesced)
 __global__ void __launch_bounds__(256) lstm_split_perm_t_kernel(const float* __restrict__ Whh, int H, __nv_bfloat16* __restrict__ planes,
                                                                 int64_t ps, const ZeroJobs zero) {
   pdl_enter();
   zero_jobs_device(zero);          // (the backward call's accumulators and counters: one launch less)
-  const int64_t total = (int64_t)4 * H * H;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i / (4 * H)), jp = (int)(i - (int64_t)k * 4 * H);
-    const float x = Whh[(int64_t)perm_row(jp, H) * H + k];
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    planes[i] = h;
-    planes[ps + i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+  const int tiles_j = 4 * H / 32, tiles_k = (H + 31) / 32;
+  for (int t = blockIdx.x; t < tiles_j * tiles_k; t += gridDim.x) {
+    const int j0 = (t % tiles_j) * 32, k0 = (t / tiles_j) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int jp = j0 + ty + 8 * i, k = k0 + tx;
+      tile[ty + 8 * i][tx] = k < H ? Whh[(int64_t)perm_row(jp, H) * H + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + ty + 8 * i, jp = j0 + tx;
+      if (k < H) {
+        const float x = tile[tx][ty + 8 * i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        const int64_t o = (int64_t)k * 4 * H + jp;
+        planes[o] = h;
+        planes[ps + o] = __float2bfloat16_rn(x - __bfloat162float(h));
+      }
+    }
+    __syncthreads();
   }
 }
 // forward prologue in one launch: planes of W_ih and W_hh (gate rows permuted) and the permuted bias sum
@@ -567,22 +584,29 @@ __global__ void __launch_bounds__(256) lstm_prep_kernel(const float* __restrict_
                                                         float* __restrict__ biasp, const ZeroJobs zero) {
   pdl_enter();
   zero_jobs_device(zero);          // (the h planes and the step counters of the forward call: one launch less)
-  const int64_t n1 = (int64_t)4 * H * E, n2 = (int64_t)4 * H * H, total = n1 + n2 + 4 * H;
+  // (four consecutive columns per thread: E % 8 == 0 and H % 16 == 0, so every row is a whole number of float4)
+  const int64_t n1 = (int64_t)4 * H * E, n2 = (int64_t)4 * H * H, v1 = n1 / 4, v2 = n2 / 4, total = v1 + v2 + 4 * H;
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-    if (g < n1 + n2) {
-      const bool first = g < n1;
-      const int64_t i = first ? g : g - n1;
+    if (g < v1 + v2) {
+      const bool first = g < v1;
+      const int64_t i = 4 * (first ? g : g - v1);
       const int cols = first ? E : H;
       const float* W = first ? w_ih : w_hh;
       __nv_bfloat16* planes = first ? wip : whp;
       const int64_t ps = first ? n1 : n2;
       const int jp = (int)(i / cols), c = (int)(i - (int64_t)jp * cols);
-      const float x = W[(int64_t)perm_row(jp, H) * cols + c];
-      const __nv_bfloat16 h = __float2bfloat16_rn(x);
-      planes[i] = h;
-      planes[ps + i] = __float2bfloat16_rn(x - __bfloat162float(h));
+      const float4 x4 = __ldg(reinterpret_cast<const float4*>(W + (int64_t)perm_row(jp, H) * cols + c));
+      const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        hi[q] = __float2bfloat16_rn(x[q]);
+        lo[q] = __float2bfloat16_rn(x[q] - __bfloat162float(hi[q]));
+      }
+      *reinterpret_cast<uint2*>(planes + i) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(planes + ps + i) = *reinterpret_cast<const uint2*>(lo);
     } else {
-      const int jp = (int)(g - n1 - n2);
+      const int jp = (int)(g - v1 - v2);
       const int j = perm_row(jp, H);
       biasp[jp] = b_ih[j] + b_hh[j];
     }
@@ -593,17 +617,18 @@ __global__ void __launch_bounds__(256) lstm_unperm3_kernel(const float* __restri
                                                            const float* __restrict__ dbp, int H, int E, float* __restrict__ dw_ih,
                                                            float* __restrict__ dw_hh, float* __restrict__ db_ih, float* __restrict__ db_hh) {
   pdl_enter();
-  const int64_t n1 = (int64_t)4 * H * E, n2 = (int64_t)4 * H * H, total = n1 + n2 + 4 * H;
+  const int64_t n1 = (int64_t)4 * H * E, n2 = (int64_t)4 * H * H, v1 = n1 / 4, v2 = n2 / 4, total = v1 + v2 + 4 * H;      // (float4 per thread)
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-    if (g < n1) {
-      const int jp = (int)(g / E), c = (int)(g - (int64_t)jp * E);
-      dw_ih[(int64_t)perm_row(jp, H) * E + c] = dwi[g];
-    } else if (g < n1 + n2) {
-      const int64_t i = g - n1;
+    if (g < v1) {
+      const int64_t i = 4 * g;
+      const int jp = (int)(i / E), c = (int)(i - (int64_t)jp * E);
+      *reinterpret_cast<float4*>(dw_ih + (int64_t)perm_row(jp, H) * E + c) = *reinterpret_cast<const float4*>(dwi + i);
+    } else if (g < v1 + v2) {
+      const int64_t i = 4 * (g - v1);
       const int jp = (int)(i / H), c = (int)(i - (int64_t)jp * H);
-      dw_hh[(int64_t)perm_row(jp, H) * H + c] = dwh[i];
+      *reinterpret_cast<float4*>(dw_hh + (int64_t)perm_row(jp, H) * H + c) = *reinterpret_cast<const float4*>(dwh + i);
     } else {
-      const int jp = (int)(g - n1 - n2);
+      const int jp = (int)(g - v1 - v2);
       const float v = dbp[jp];
       const int o = perm_row(jp, H);
       db_ih[o] = v;
@@ -849,7 +874,7 @@ extern "C" int hca_lstm_fwd(const float* x, const int64_t* lens, const float* w_
     ZeroBatch zb(s);
     HCA_TRY(zb.add(sv.hp, (size_t)2 * BT * H * 2));            // slot 0 (h_{-1} = 0) and the slots no step reaches
     HCA_TRY(zb.add(counters, counter_count(B, T) * 4));
-    HCA_LAUNCH_K((lstm_prep_kernel), ew_grid((int64_t)H4 * (E + H + 1)), 256, 0, s, w_ih, w_hh, b_ih, b_hh, H, E, wip, whp, biasp, zb.take());
+    HCA_LAUNCH_K((lstm_prep_kernel), ew_grid((int64_t)H4 * ((E + H) / 4 + 1)), 256, 0, s, w_ih, w_hh, b_ih, b_hh, H, E, wip, whp, biasp, zb.take());
     HCA_LAUNCHED();
   }
   {  // x-projection of every (b, t), gate columns in [unit][gate] order, biases folded in
@@ -894,7 +919,7 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
     HCA_TRY(zb.add(counters, counter_count(B, T) * 4));
     if (sk_wi > 1) HCA_TRY(zb.add(dwi, (size_t)H4 * E * 4));
     if (sk_wh > 1) HCA_TRY(zb.add(dwh, (size_t)H4 * H * 4));
-    HCA_LAUNCH_K((lstm_split_perm_t_kernel), ew_grid((int64_t)H4 * H), 256, 0, s, w_hh, H, wtp, (int64_t)H4 * H, zb.take());
+    HCA_LAUNCH_K((lstm_split_perm_t_kernel), std::min(148 * 8, (H4 / 32) * ((H + 31) / 32)), 256, 0, s, w_hh, H, wtp, (int64_t)H4 * H, zb.take());
     HCA_LAUNCHED();
   }
   LstmParams p;
@@ -914,7 +939,7 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
     HCA_TRY(launch_gemm_tc(dg_mn, operand(sv.hp, H, BT * H, (int)BT, H, true), 2, H4, H, (int)BT, e, sk, s));
   }
   // the three gradients back to PyTorch's gate order, one launch
-  HCA_LAUNCH_K((lstm_unperm3_kernel), ew_grid((int64_t)H4 * (E + H + 1)), 256, 0, s, dwi, dwh, dbp, H, E, dw_ih, dw_hh, db_ih, db_hh);
+  HCA_LAUNCH_K((lstm_unperm3_kernel), ew_grid((int64_t)H4 * ((E + H) / 4 + 1)), 256, 0, s, dwi, dwh, dbp, H, E, dw_ih, dw_hh, db_ih, db_hh);
   HCA_LAUNCHED();
   if (dx) {  // dx = dz W_ih
     TcEpilogue e; e.D = dx; e.ldd = E;
