@@ -1,7 +1,7 @@
 #!/bin/bash
 # checkpoint visit: full GPU suite + a short bench with the per-kernel breakdown
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_headline.py -q -m gpu -x --deselect tests/test_gpu_headline.py::test_argmax_agreement_on_10240_samples 2>&1 | tail -4 | cut -c1-300 | tee gpurun_out/r2m_tests.log
+timeout 1500 python -m pytest tests -q -m gpu -x --deselect tests/test_gpu_headline.py::test_argmax_agreement_on_10240_samples 2>&1 | tail -4 | cut -c1-300 | tee gpurun_out/r2m_tests.log
 timeout 600 python bench.py --steps 60 --warmup 5 --skip-cpu-baseline --skip-gpu-baseline --skip-legs 2>gpurun_out/r2m_bench.err | tee gpurun_out/r2m_bench.json | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
