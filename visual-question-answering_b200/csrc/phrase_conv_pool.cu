@@ -293,24 +293,27 @@ __global__ void __launch_bounds__(256) conv_w_planes3_kernel(const float* __rest
                                                              int* __restrict__ tie_count, int write_zeros) {
   pdl_enter();
   if (tie_count && blockIdx.x == 0 && threadIdx.x == 0) *tie_count = 0;
-  const int64_t E3 = 3 * (int64_t)E, total = E3 * E3, ps = total;
+  // thread <-> (row of Wcat, input channel c): its k taps w[o][c][0..k) are contiguous in the conv layout (coalesced reads) and go to k tap
+  // blocks of the row (each a coalesced stream over c); the row's structural zeros are written by the same thread when a tile may read them
+  const int64_t E3 = 3 * (int64_t)E, total = E3 * E, ps = E3 * E3;
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-    const int col = (int)(g % E3);
-    const int row = (int)(g / E3);
+    const int c = (int)(g % E);
+    const int row = (int)(g / E);
     const int k = row / E + 1, o = row - (k - 1) * E;          // k-gram filter, its output channel
-    const int j = col / E - (k == 1 ? 1 : 0), c = col % E;     // tap of that filter at this column (outside [0, k): structural zero)
-    float x = 0.f;
-    if (j >= 0 && j < k) {
-      const float* w = k == 1 ? w1 : (k == 2 ? w2 : w3);
-      x = w[((int64_t)o * E + c) * k + j];
-    } else if (!write_zeros) {        // (E % 128 == 0: no tile of the products straddles a block boundary, the zero blocks are never read)
-      if (bcat && col == 0) bcat[row] = (k == 1 ? b1 : (k == 2 ? b2 : b3))[o];
-      continue;
+    const float* w = (k == 1 ? w1 : (k == 2 ? w2 : w3)) + ((int64_t)o * E + c) * k;
+    const int first = k == 1 ? 1 : 0;                          // tap block of the filter's tap 0
+#pragma unroll
+    for (int jb = 0; jb < 3; ++jb) {
+      const int j = jb - first;
+      const bool has = j >= 0 && j < k;
+      if (!has && !write_zeros) continue;      // (E % 128 == 0: no tile of the products straddles a block boundary, the zero blocks are never read)
+      const float x = has ? w[j] : 0.f;
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      const int64_t dst = (int64_t)row * E3 + (int64_t)jb * E + c;
+      planes[dst] = h;
+      planes[ps + dst] = __float2bfloat16_rn(x - __bfloat162float(h));
     }
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    planes[g] = h;
-    planes[ps + g] = __float2bfloat16_rn(x - __bfloat162float(h));
-    if (bcat && col == 0) bcat[row] = (k == 1 ? b1 : (k == 2 ? b2 : b3))[o];
+    if (bcat && c == 0) bcat[row] = (k == 1 ? b1 : (k == 2 ? b2 : b3))[o];
   }
 }
 // Pool backward straight into operand planes: dcat[r][3e+j] = (j == idx) ? dout * (1 - out^2) : 0 as bf16 hi/lo planes
@@ -383,15 +386,15 @@ __global__ void __launch_bounds__(256) pool3_bwd_planes_kernel(const float* __re
 __global__ void __launch_bounds__(256) unpack_conv_w_kernel(const float* __restrict__ dwcat, float* __restrict__ w1, float* __restrict__ w2,
                                                             float* __restrict__ w3, int E) {
   pdl_enter();
-  const int64_t EE = (int64_t)E * E, total = 6 * EE, E3 = 3 * (int64_t)E;
+  // thread <-> (row of dWcat, input channel c): k coalesced reads (one per tap block), k contiguous writes in the conv layout
+  const int64_t E3 = 3 * (int64_t)E, total = E3 * E;
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-    const int k = g < EE ? 1 : (g < 3 * EE ? 2 : 3);
-    const int64_t i = g - (k == 1 ? 0 : (k == 2 ? EE : 3 * EE));    // = (o * k + j) * E + c
-    const int c = (int)(i % E);
-    const int j = (int)((i / E) % k);
-    const int64_t o = i / ((int64_t)E * k);
-    const float v = dwcat[((k - 1) * (int64_t)E + o) * E3 + (int64_t)(j + (k == 1 ? 1 : 0)) * E + c];
-    (k == 1 ? w1 : (k == 2 ? w2 : w3))[(o * E + c) * k + j] = v;
+    const int c = (int)(g % E);
+    const int row = (int)(g / E);
+    const int k = row / E + 1, o = row - (k - 1) * E;
+    float* w = (k == 1 ? w1 : (k == 2 ? w2 : w3)) + ((int64_t)o * E + c) * k;
+    const float* src = dwcat + (int64_t)row * E3 + (int64_t)(k == 1 ? 1 : 0) * E + c;
+    for (int j = 0; j < k; ++j) w[j] = src[(int64_t)j * E];
   }
 }
 
@@ -490,7 +493,7 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
   const int64_t E3 = 3 * (int64_t)E;
   __nv_bfloat16* wcat = fsaved ? sv.wcat : c.w.take<__nv_bfloat16>((size_t)P * E3 * E3);
   if (!wcat) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_fwd: workspace too small for weight planes");
-  HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid(E3 * E3), 256, 0, s, w1, w2, w3, b1, b2, b3, wcat, c.bcat, E, c.tie_count, (E % 128) != 0 ? 1 : 0);
+  HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid(E3 * E), 256, 0, s, w1, w2, w3, b1, b2, b3, wcat, c.bcat, E, c.tie_count, (E % 128) != 0 ? 1 : 0);
   HCA_LAUNCHED();
   HCA_LAUNCH_K((conv_norms_kernel), std::min(148 * 4, (R + 3 * E + 7) / 8), 256, 0, s, x, w1, w2, w3, c.xn2, c.wn, R, E);
   HCA_LAUNCHED();
@@ -566,7 +569,7 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
     Bm.planes = ap; Bm.ld = ld3; Bm.plane_stride = pstride; Bm.rows = R; Bm.cols = (int)E3w; Bm.mn_major = true;
     HCA_TRY(launch_gemm_tc(A, Bm, 2, (int)E3w, (int)E3w, R, epw, skw, s));
   }
-  HCA_LAUNCH_K((unpack_conv_w_kernel), ew_grid((int64_t)E * E * 6), 256, 0, s, c.dwcat, dw1, dw2, dw3, E);
+  HCA_LAUNCH_K((unpack_conv_w_kernel), ew_grid((int64_t)E * E * 3), 256, 0, s, c.dwcat, dw1, dw2, dw3, E);
   HCA_LAUNCHED();
   if (dx) {
     // dA[r][kk] = sum_oc dcat[r][oc] * Wcat[oc][kk]: ONE product with the block-structured weight matrix as the MN-major operand; tap
@@ -575,7 +578,7 @@ extern "C" int hca_phrase_conv_pool_bwd(const float* x, const float* w1, const f
     __nv_bfloat16* wcat = fsaved ? sv.wcat : c.w.take<__nv_bfloat16>((size_t)2 * E3 * E3);
     if (!wcat) return set_err(HCA_ERR_WORKSPACE, "phrase_conv_pool_bwd: workspace too small for weight planes");
     if (!fsaved) {
-      HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid(E3 * E3), 256, 0, s, w1, w2, w3, (const float*)nullptr, (const float*)nullptr,
+      HCA_LAUNCH_K((conv_w_planes3_kernel), ew_grid(E3 * E), 256, 0, s, w1, w2, w3, (const float*)nullptr, (const float*)nullptr,
                                                                    (const float*)nullptr, wcat, (float*)nullptr, E, (int*)nullptr, (E % 128) != 0 ? 1 : 0);
       HCA_LAUNCHED();
     }
