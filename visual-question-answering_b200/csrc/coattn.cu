@@ -409,9 +409,9 @@ TcPlanes plv(const Pl& pl, int64_t row0, int64_t rows_per_entry, int nbatch, int
 
 // Question-side backward through tanh: dZq[r][j] = dsq[r] * wq[j] * (1 - Hq[r][j]^2) as bf16 hi/lo planes, dwq[j] += sum_r Hq[r][j] dsq[r].
 // Hq [rows][d] comes as the planes the forward pass saved.  Block = a slab of HQ_ROWS rows x 128 columns: a lane owns 4 columns, the 8 warps
-// take the rows of the slab in turn, and the column sums meet in shared memory -- one atomic per column and block (49 per column at B = 160:
+// take the rows of the slab in turn, and the column sums meet in shared memory -- one atomic per column and block (98 per column at B = 160:
 // with one atomic per column and 16-row slab the 400 k atomics onto 16 cache lines WERE the kernel: 41 us for 50 MB).
-constexpr int HQ_ROWS = 256, HQ_WARPS = 8;
+constexpr int HQ_ROWS = 128, HQ_WARPS = 8;
 __global__ void __launch_bounds__(32 * HQ_WARPS) hq_bwd_kernel(const __nv_bfloat16* __restrict__ hq, int64_t ld, int64_t ps,
                                                                const float* __restrict__ dsq, const float* __restrict__ wq,
                                                                __nv_bfloat16* __restrict__ dz, int64_t dz_ld, int64_t dz_ps,

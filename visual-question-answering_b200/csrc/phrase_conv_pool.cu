@@ -114,29 +114,36 @@ __device__ __forceinline__ void top2_of3(float v0, float v1, float v2, float& be
 }
 
 // cat [R, 3E] (post tanh) -> out [R, E], idx [R, E]; rows t >= len zeroed.  Near-ties go to tie_list (count keeps counting past tie_cap).
+// A thread takes FOUR consecutive channel triples: three float4 of cat (48 contiguous bytes), one float4 of out, one uchar4 of idx (E % 8 == 0).
 __global__ void __launch_bounds__(256) pool3_fwd_kernel(const float* __restrict__ cat, const int64_t* __restrict__ lens,
                                                         float* __restrict__ out, uint8_t* __restrict__ idx, int B, int T, int E,
                                                         const float* __restrict__ xn2, const float* __restrict__ wn,
                                                         int* __restrict__ tie_list, int* __restrict__ tie_count, int tie_cap) {
   pdl_enter();
-  const int64_t total = (int64_t)B * T * E;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / E;
-    const int e = (int)(i - r * E);
+  const int64_t total4 = (int64_t)B * T * (E / 4);
+  const int E4 = E / 4;
+  for (int64_t i4 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i4 < total4; i4 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i4 / E4;
+    const int e0 = (int)(i4 - r * E4) * 4;
     const int b = (int)(r / T), t = (int)(r % T);
-    float best = 0.f;
-    int bi = 0;
+    float best[4] = {0.f, 0.f, 0.f, 0.f};
+    int bi[4] = {0, 0, 0, 0};
     if (!lens || t < lens[b]) {
-      const float* p = cat + r * 3 * (int64_t)E + 3 * e;
-      float mid;
-      top2_of3(p[0], p[1], p[2], best, mid, bi);
-      if (!(best - mid >= tie_band(xn2, wn, r, t, T, e, E, best, mid))) {      // (NaN lands here too)
-        const int slot = atomicAdd(tie_count, 1);
-        if (slot < tie_cap) tie_list[slot] = (int)i;
+      const float4* p4 = reinterpret_cast<const float4*>(cat + r * 3 * (int64_t)E + 3 * e0);
+      const float4 c0 = p4[0], c1 = p4[1], c2 = p4[2];
+      const float v[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float mid;
+        top2_of3(v[3 * q], v[3 * q + 1], v[3 * q + 2], best[q], mid, bi[q]);
+        if (!(best[q] - mid >= tie_band(xn2, wn, r, t, T, e0 + q, E, best[q], mid))) {      // (NaN lands here too)
+          const int slot = atomicAdd(tie_count, 1);
+          if (slot < tie_cap) tie_list[slot] = (int)(r * E + e0 + q);
+        }
       }
     }
-    out[i] = best;
-    idx[i] = (uint8_t)bi;
+    *reinterpret_cast<float4*>(out + r * E + e0) = make_float4(best[0], best[1], best[2], best[3]);
+    *reinterpret_cast<uchar4*>(idx + r * E + e0) = make_uchar4((unsigned char)bi[0], (unsigned char)bi[1], (unsigned char)bi[2], (unsigned char)bi[3]);
   }
 }
 
@@ -509,7 +516,7 @@ extern "C" int hca_phrase_conv_pool_fwd(const float* x, const float* w1, const f
     ep.kwin_lo[2] = 0; ep.kwin_hi[2] = 3 * E;          // trigram
     HCA_TRY(launch_gemm_tc(A, Bw, P, R, (int)E3, (int)E3, ep, 1, s));
   }
-  HCA_LAUNCH_K((pool3_fwd_kernel), ew_grid((int64_t)R * E), 256, 0, s, c.cat, lens, out, idx, B, T, E, c.xn2, c.wn, c.tie_list, c.tie_count,
+  HCA_LAUNCH_K((pool3_fwd_kernel), ew_grid((int64_t)R * E / 4), 256, 0, s, c.cat, lens, out, idx, B, T, E, c.xn2, c.wn, c.tie_list, c.tie_count,
                c.tie_cap);
   HCA_LAUNCHED();
   HCA_LAUNCH_K((fixup_ties_kernel), 148 * 20, 96, 0, s, c.tie_list, c.tie_count, c.tie_cap, c.cat, lens, c.xn2, c.wn, x, B, T, w1, w2, w3, b1,
