@@ -81,7 +81,7 @@ struct LstmParams {
   float* c;               // [B][T][H] cell states
   float* out;             // [B][T][H] (fwd)
   __nv_bfloat16* hp;      // h planes [2][B][T][H]: slot t holds h_{t-1} (slot 0 = 0)
-  int64_t hp_ps;
+  int64_t hp_ps, hp_ld;   // plane stride and row pitch of the h planes (they share rows with the x planes: [x | h] per token)
   const float* dout;      // [B][T][H] (bwd)
   __nv_bfloat16* dgp;     // gate-gradient planes [2][B][T][4H] ([unit][gate] column order) (bwd)
   int64_t dgp_ps;
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_rec_kernel(const __grid_con
         if (row_ok && t < len_b && t + 1 < p.T) {         // (rows past their end keep the zero slot: their h is never used)
           uint32_t hi, lo;
           split2(h[0], h[1], hi, lo);
-          __nv_bfloat16* dst = p.hp + (bt0 + t + 1) * H + u0;
+          __nv_bfloat16* dst = p.hp + (bt0 + t + 1) * p.hp_ld + u0;
           *reinterpret_cast<uint32_t*>(dst) = hi;
           *reinterpret_cast<uint32_t*>(dst + p.hp_ps) = lo;
         }
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(256) lstm_prep_kernel(const float* __restrict_
   }
 }
 // dW_ih, dW_hh and the bias gradient (both b_ih and b_hh receive it) in one launch
-__global__ void __launch_bounds__(256) lstm_unperm3_kernel(const float* __restrict__ dwi, const float* __restrict__ dwh,
+__global__ void __launch_bounds__(256) lstm_unperm3_kernel(const float* __restrict__ dwc /* [4H][E + H]: dW_ih' | dW_hh' */,
                                                            const float* __restrict__ dbp, int H, int E, float* __restrict__ dw_ih,
                                                            float* __restrict__ dw_hh, float* __restrict__ db_ih, float* __restrict__ db_hh) {
   pdl_enter();
@@ -622,11 +622,11 @@ __global__ void __launch_bounds__(256) lstm_unperm3_kernel(const float* __restri
     if (g < v1) {
       const int64_t i = 4 * g;
       const int jp = (int)(i / E), c = (int)(i - (int64_t)jp * E);
-      *reinterpret_cast<float4*>(dw_ih + (int64_t)perm_row(jp, H) * E + c) = *reinterpret_cast<const float4*>(dwi + i);
+      *reinterpret_cast<float4*>(dw_ih + (int64_t)perm_row(jp, H) * E + c) = *reinterpret_cast<const float4*>(dwc + (int64_t)jp * (E + H) + c);
     } else if (g < v1 + v2) {
       const int64_t i = 4 * (g - v1);
       const int jp = (int)(i / H), c = (int)(i - (int64_t)jp * H);
-      *reinterpret_cast<float4*>(dw_hh + (int64_t)perm_row(jp, H) * H + c) = *reinterpret_cast<const float4*>(dwh + i);
+      *reinterpret_cast<float4*>(dw_hh + (int64_t)perm_row(jp, H) * H + c) = *reinterpret_cast<const float4*>(dwc + (int64_t)jp * (E + H) + E + c);
     } else {
       const int jp = (int)(g - v1 - v2);
       const float v = dbp[jp];
@@ -640,14 +640,13 @@ __global__ void __launch_bounds__(256) lstm_unperm3_kernel(const float* __restri
 struct Saved {
   float* act;              // [B][T][4H]
   float* c;                // [B][T][H]
-  __nv_bfloat16* hp;       // [2][B][T][H]
-  __nv_bfloat16* xp;       // [2][B][T][E]
+  __nv_bfloat16* xh;       // [2][B][T][E + H]: x planes in columns [0, E), h planes (slot t = h_{t-1}) in [E, E + H): ONE operand for both
+                           // weight gradients of backward (dW_ih' | dW_hh' = dz^T [x | h])
   __nv_bfloat16* wip;      // [2][4H][E]: gate-permuted planes of w_ih (the input-gradient product of backward reads them again)
 };
 size_t saved_bytes(int B, int T, int E, int H) {
   const size_t BT = (size_t)B * T;
-  return align_up(BT * 4 * H * 4) + align_up(BT * H * 4) + align_up(2 * BT * H * 2) + align_up(2 * BT * E * 2) +
-         align_up((size_t)2 * 4 * H * E * 2) + 256;
+  return align_up(BT * 4 * H * 4) + align_up(BT * H * 4) + align_up(2 * BT * (E + H) * 2) + align_up((size_t)2 * 4 * H * E * 2) + 256;
 }
 bool carve_saved(Saved& s, void* buf, size_t bytes, int B, int T, int E, int H) {
   if (bytes < saved_bytes(B, T, E, H) || (reinterpret_cast<uintptr_t>(buf) & 255) != 0) return false;
@@ -655,8 +654,7 @@ bool carve_saved(Saved& s, void* buf, size_t bytes, int B, int T, int E, int H) 
   char* p = (char*)buf;
   s.act = (float*)p; p += align_up(BT * 4 * H * 4);
   s.c = (float*)p; p += align_up(BT * H * 4);
-  s.hp = (__nv_bfloat16*)p; p += align_up(2 * BT * H * 2);
-  s.xp = (__nv_bfloat16*)p; p += align_up(2 * BT * E * 2);
+  s.xh = (__nv_bfloat16*)p; p += align_up(2 * BT * (E + H) * 2);
   s.wip = (__nv_bfloat16*)p;
   return true;
 }
@@ -747,7 +745,7 @@ bool geometry(Geometry& g, int B, int H) {
 size_t counter_count(int B, int T) { return (size_t)((B + 7) / 8 + 1) * T; }
 
 template <bool BWD>
-int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64_t stream_ps, int stream_cols,
+int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64_t stream_ps, int stream_cols, int64_t stream_ld,
                const __nv_bfloat16* w_planes, int64_t w_ps, int w_rows, int w_cols, cudaStream_t s) {
   Geometry g;
   if (!geometry<BWD>(g, base.B, base.H))
@@ -764,7 +762,7 @@ int launch_rec(const LstmParams& base, const __nv_bfloat16* stream_planes, int64
   {  // streamed operand [2][B][T][cols] as (col, b, plane, t); a box brings one k-block of both planes for the rows of a tile.  Rows
      // beyond B and columns beyond `cols` arrive as zeros (out-of-bounds fill).
     const uint64_t dims[4] = {(uint64_t)stream_cols, (uint64_t)base.B, 2, (uint64_t)base.T};
-    const uint64_t str[3] = {(uint64_t)base.T * stream_cols * 2, (uint64_t)stream_ps * 2, (uint64_t)stream_cols * 2};
+    const uint64_t str[3] = {(uint64_t)base.T * stream_ld * 2, (uint64_t)stream_ps * 2, (uint64_t)stream_ld * 2};
     const uint32_t box[4] = {L_BK, (uint32_t)g.rpt, 2, 1};
     HCA_TRY(tc_make_tmap(&maps.X, true, 4, stream_planes, dims, str, box, 3));
   }
@@ -869,25 +867,27 @@ extern "C" int hca_lstm_fwd(const float* x, const int64_t* lens, const float* w_
   float* biasp = w.take<float>((size_t)H4);
   int* counters = w.take<int>(counter_count(B, T));
   if (!counters) return set_err(HCA_ERR_WORKSPACE, "lstm_fwd: workspace too small (%zu bytes)", ws_bytes);
-  HCA_TRY(launch_split_planes(x, E, BT, E, sv.xp, E, BT * E, 2, s));
+  const int64_t xh_ld = E + H, xh_ps = BT * xh_ld;
+  __nv_bfloat16* const hp = sv.xh + E;
   {
     ZeroBatch zb(s);
-    HCA_TRY(zb.add(sv.hp, (size_t)2 * BT * H * 2));            // slot 0 (h_{-1} = 0) and the slots no step reaches
+    HCA_TRY(zb.add(sv.xh, (size_t)2 * xh_ps * 2));             // the h columns: slot 0 (h_{-1} = 0) and the slots no step reaches (the x columns follow)
     HCA_TRY(zb.add(counters, counter_count(B, T) * 4));
     HCA_LAUNCH_K((lstm_prep_kernel), ew_grid((int64_t)H4 * ((E + H) / 4 + 1)), 256, 0, s, w_ih, w_hh, b_ih, b_hh, H, E, wip, whp, biasp, zb.take());
     HCA_LAUNCHED();
   }
+  HCA_TRY(launch_split_planes(x, E, BT, E, sv.xh, xh_ld, xh_ps, 2, s));
   {  // x-projection of every (b, t), gate columns in [unit][gate] order, biases folded in
     TcEpilogue e;
     e.D = sv.act; e.ldd = H4; e.bias = biasp;
-    HCA_TRY(launch_gemm_tc(operand(sv.xp, E, BT * E, (int)BT, E, false), operand(wip, E, (int64_t)H4 * E, H4, E, false), 2, (int)BT, H4, E,
+    HCA_TRY(launch_gemm_tc(operand(sv.xh, xh_ld, xh_ps, (int)BT, E, false), operand(wip, E, (int64_t)H4 * E, H4, E, false), 2, (int)BT, H4, E,
                            e, 1, s));
   }
   LstmParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.T = T; p.H = H; p.lens = lens; p.counters = counters;
-  p.act = sv.act; p.c = sv.c; p.out = out; p.hp = sv.hp; p.hp_ps = BT * H;
-  return launch_rec<false>(p, sv.hp, BT * H, H, whp, (int64_t)H4 * H, H4, H, s);
+  p.act = sv.act; p.c = sv.c; p.out = out; p.hp = hp; p.hp_ps = xh_ps; p.hp_ld = xh_ld;
+  return launch_rec<false>(p, hp, xh_ps, H, xh_ld, whp, (int64_t)H4 * H, H4, H, s);
 }
 
 extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float* w_hh, const void* saved, size_t saved_sz,
@@ -906,19 +906,17 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
   __nv_bfloat16* dgp = w.take<__nv_bfloat16>((size_t)2 * BT * H4);
   const __nv_bfloat16* wip = sv.wip;                             // written by the forward call
   __nv_bfloat16* wtp = w.take<__nv_bfloat16>((size_t)2 * H4 * H);
-  float* dwi = w.take<float>((size_t)H4 * E);
-  float* dwh = w.take<float>((size_t)H4 * H);
+  float* dwc = w.take<float>((size_t)H4 * (E + H));           // [4H][E + H]: dW_ih' | dW_hh' (gate rows still permuted)
   float* dbp = w.take<float>((size_t)H4);
   int* counters = w.take<int>(counter_count(B, T));
   if (!counters) return set_err(HCA_ERR_WORKSPACE, "lstm_bwd: workspace too small (%zu bytes)", ws_bytes);
-  const int sk_wi = tc_splitk(H4, E, (int)BT), sk_wh = tc_splitk(H4, H, (int)BT);
+  const int sk_w = tc_splitk(H4, E + H, (int)BT);
   {
     ZeroBatch zb(s);
     HCA_TRY(zb.add(dgp, (size_t)2 * BT * H4 * 2));             // rows no step writes must read as zero in the GEMMs below
     HCA_TRY(zb.add(dbp, (size_t)H4 * 4));
     HCA_TRY(zb.add(counters, counter_count(B, T) * 4));
-    if (sk_wi > 1) HCA_TRY(zb.add(dwi, (size_t)H4 * E * 4));
-    if (sk_wh > 1) HCA_TRY(zb.add(dwh, (size_t)H4 * H * 4));
+    if (sk_w > 1) HCA_TRY(zb.add(dwc, (size_t)H4 * (E + H) * 4));
     HCA_LAUNCH_K((lstm_split_perm_t_kernel), std::min(148 * 8, (H4 / 32) * ((H + 31) / 32)), 256, 0, s, w_hh, H, wtp, (int64_t)H4 * H, zb.take());
     HCA_LAUNCHED();
   }
@@ -926,20 +924,14 @@ extern "C" int hca_lstm_bwd(const int64_t* lens, const float* w_ih, const float*
   memset(&p, 0, sizeof(p));
   p.B = B; p.T = T; p.H = H; p.lens = lens; p.counters = counters;
   p.act = sv.act; p.c = sv.c; p.dout = dout; p.dgp = dgp; p.dgp_ps = BT * H4; p.dbias = dbp;
-  HCA_TRY(launch_rec<true>(p, dgp, BT * H4, H4, wtp, (int64_t)H4 * H, H, H4, s));
+  HCA_TRY(launch_rec<true>(p, dgp, BT * H4, H4, H4, wtp, (int64_t)H4 * H, H, H4, s));
   const TcOperand dg_mn = operand(dgp, H4, BT * H4, (int)BT, H4, true);
-  {  // dW_ih' = dz^T x   (K = B*T, split-K)
-    const int sk = sk_wi;
-    TcEpilogue e; e.D = dwi; e.ldd = E;
-    HCA_TRY(launch_gemm_tc(dg_mn, operand(sv.xp, E, BT * E, (int)BT, E, true), 2, H4, E, (int)BT, e, sk, s));
-  }
-  {  // dW_hh' = dz^T h_prev
-    const int sk = sk_wh;
-    TcEpilogue e; e.D = dwh; e.ldd = H;
-    HCA_TRY(launch_gemm_tc(dg_mn, operand(sv.hp, H, BT * H, (int)BT, H, true), 2, H4, H, (int)BT, e, sk, s));
+  {  // [dW_ih' | dW_hh'] = dz^T [x | h_prev]: ONE product (K = B*T, split-K) over the planes the forward pass laid out side by side
+    TcEpilogue e; e.D = dwc; e.ldd = E + H;
+    HCA_TRY(launch_gemm_tc(dg_mn, operand(sv.xh, E + H, BT * (E + H), (int)BT, E + H, true), 2, H4, E + H, (int)BT, e, sk_w, s));
   }
   // the three gradients back to PyTorch's gate order, one launch
-  HCA_LAUNCH_K((lstm_unperm3_kernel), ew_grid((int64_t)H4 * ((E + H) / 4 + 1)), 256, 0, s, dwi, dwh, dbp, H, E, dw_ih, dw_hh, db_ih, db_hh);
+  HCA_LAUNCH_K((lstm_unperm3_kernel), ew_grid((int64_t)H4 * ((E + H) / 4 + 1)), 256, 0, s, dwc, dbp, H, E, dw_ih, dw_hh, db_ih, db_hh);
   HCA_LAUNCHED();
   if (dx) {  // dx = dz W_ih
     TcEpilogue e; e.D = dx; e.ldd = E;

@@ -262,7 +262,7 @@ def _(x, lens, w_ih, w_hh, b_ih, b_hh):
     H = w_hh.shape[1]
     al = lambda n: (n + 255) // 256 * 256
     BT = B * T
-    nbytes = al(BT * 4 * H * 4) + al(BT * H * 4) + al(2 * BT * H * 2) + al(2 * BT * E * 2) + al(2 * 4 * H * E * 2) + 256
+    nbytes = al(BT * 4 * H * 4) + al(BT * H * 4) + al(2 * BT * (E + H) * 2) + al(2 * 4 * H * E * 2) + 256      # mirrors hca_lstm_saved_bytes
     return x.new_empty(B, T, H), x.new_empty(nbytes, dtype=torch.uint8)
 
 
