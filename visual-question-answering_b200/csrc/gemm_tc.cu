@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   __shared__ uint32_t tmem_ptr_smem;
   // per epilogue group: this tile's per-column vectors
   __shared__ __align__(16) float bias_sm[NUM_EG][BNV];      // bias slice (per batch entry)
-  __shared__ __align__(16) float colv_sm[NUM_EG][BNV];      // colv (ROWDOT / DZ)
+  __shared__ __align__(16) float colv_sm[NUM_EG][BNV];      // colv (ROWDOT)
   __shared__ __align__(16) float r1_sm[NUM_EG][CG == 2 ? 1 : 4][BNV];   // rank-1 column vectors, one per row group (not in pair mode)
   __shared__ float colred_sm[NUM_EG][BNV];                  // column partial sums of the group's four warps
 
@@ -669,17 +669,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             for (int j = 0; j < 32; ++j) rowdot = fmaf(f[j], colv_s[c * 32 + j], rowdot);   // colv_s is 0 beyond N
             if (!do_pl) continue;
           }
-          if (mode == TC_EPI_DZ) {
-            // column partials of h * rowv over this warp's 32 rows, then dz = rowv * colv * (1 - h^2)
-            float part[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              part[j] = f[j] * rv;
-              f[j] = rv * colv_s[c * 32 + j] * (1.f - f[j] * f[j]);
-            }
-            const float cs = col_reduce32(part, lane);
-            atomicAdd(&colred_s[c * 32 + lane], cs);
-          } else if (want_colred) {
+          if (want_colred) {
             float part[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) part[j] = row_ok ? f[j] : 0.f;
@@ -1310,7 +1300,7 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   p.tiles_m = (M + BM * CGn - 1) / (BM * CGn);
   p.tiles_n = (N + BN - 1) / BN;
   int64_t tiles_mn = (int64_t)p.tiles_m * p.tiles_n;
-  if (e.nwin_nrow > 0 && batch == 1 && p.tiles_m <= NWIN_TM_MAX && p.tiles_n < 32768) {      // (otherwise: every tile, which is always correct)
+  if (e.nwin_nrow > 0 && batch == 1 && p.tiles_m <= NWIN_TM_MAX && tiles_mn < 32768) {      // (otherwise: every tile, which is always correct)
     p.nwin_on = 1;
     p.nw_pre[0] = 0;
     for (int mt = 0; mt < p.tiles_m; ++mt) {
@@ -1354,7 +1344,6 @@ int launch_gemm_tc(const TcOperand& A, const TcOperand& B, int P, int M, int N, 
   HCA_CHECK_ARG(!(splitk > 1 && (nonlinear || want_pl || e.red_col)), "gemm_tc: split-K needs a linear fp32 epilogue");
   HCA_CHECK_ARG(!(p.d_zd > 1 && !e.accumulate), "gemm_tc: d_zdiv > 1 means several tiles add into one output: set accumulate");
   HCA_CHECK_ARG(e.mode != TC_EPI_ROWDOT || (e.colv && e.red_row), "gemm_tc: ROWDOT needs colv and red_row");
-  HCA_CHECK_ARG(e.mode != TC_EPI_DZ || (e.colv && e.rowv && e.red_col), "gemm_tc: DZ needs rowv, colv and red_col");
   HCA_CHECK_ARG(!e.r1col || (e.rowv && e.mode == TC_EPI_STORE), "gemm_tc: the rank-1 term needs rowv and the STORE mode");
   HCA_CHECK_ARG(!e.r1col || e.r1_rows_per_group <= 0 || (M + e.r1_rows_per_group - 1) / e.r1_rows_per_group <= 4,
                 "gemm_tc: at most 4 rank-1 row groups");

@@ -45,8 +45,7 @@ struct TcPlanes {
 
 enum TcEpiMode : int {
   TC_EPI_STORE = 0,   // D[z] (+)= f  and / or  planes(f)
-  TC_EPI_ROWDOT = 1,  // red_row[z][m] += sum_n f[m][n] * colv[n]                     (nothing stored)
-  TC_EPI_DZ = 2,      // g = rowv[z][m] * colv[n] * (1 - f^2) ; red_col[n] += sum_m f[m][n] * rowv[z][m] ; store g like STORE
+  TC_EPI_ROWDOT = 1,  // red_row[z][m] += sum_n f[m][n] * colv[n]                     (planes P of f may be kept; no fp32 store)
 };
 enum TcAuxMode : int { TC_AUX_NONE = 0, TC_AUX_ADD = 1 /* f = act(acc + aux) */, TC_AUX_MUL_1MX2 = 2 /* f *= 1 - aux^2 */ };
 
@@ -73,7 +72,7 @@ struct TcEpilogue {
   const float* r1col = nullptr; int64_t r1col_batch_stride = 0;     // rank-1 term rowv[z][m] * r1col[z][g][n]
   int r1_rows_per_group = 0;    int64_t r1_group_stride = 0;        // g = m / r1_rows_per_group (0: one group)
   float* red_row = nullptr;     int64_t red_row_batch_stride = 0;
-  float* red_col = nullptr;                                         // DZ: see above.  STORE: red_col[n] += sum_m f[m][n]
+  float* red_col = nullptr;                                         // STORE: red_col[n] += sum_m f[m][n]
   // BN = 32 "transposed" epilogue: outputs and auxp are addressed [z][n][m] (ld = their leading dimension over m); fp32 D,
   // planes P, auxp (ADD / MUL_1MX2), act_tanh, red_row (un-batched: red_row[m] += sum_n f[m][n]) and a bias indexed by the
   // tile ROW (bias[z][m]: these products put the weight matrix on M) are supported, nothing else.
