@@ -13,9 +13,11 @@
 // image-side operand is level independent are one M = 3T (or K = 3T) product per sample instead of three M = T ones,
 // and the products that contract over T per level put the long image axis (N or d) on the 128-row M side of the
 // tensor core and T on a 32-wide N tile (transposed epilogue).  Intermediates are never written as fp32: each GEMM
-// epilogue emits the bf16 hi/lo planes its consumers take as operands.  Hv / Hq are recomputed in backward.
+// epilogue emits the bf16 hi/lo planes its consumers take as operands.  Hv (three levels x [N, d] per sample) is recomputed in
+// backward by hv_fused.cu; Hq ([3T, d] per sample) is saved: recomputing it is a per-sample product with 78 rows that is bound by
+// the L2 -> SM operand stream, not by its arithmetic.
 //
-// Saved for backward (one opaque buffer, hca_coattn_saved_bytes): planes of V, Q_all, PV, PQ_all, C_all; av, aq.
+// Saved for backward (one opaque buffer, hca_coattn_saved_bytes): planes of V, Q_all, PV, PQ_all, C_all; av, aq; planes of Hq.
 #include <algorithm>
 #include "common.cuh"
 #include "gemm_tc.cuh"
