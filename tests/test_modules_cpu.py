@@ -58,6 +58,21 @@ def test_library_exports_every_declared_symbol(pkg):
     assert pkg._lib.get_option("gemm") in ("tc", "ffma")
 
 
+def test_fake_tensor_sizes_mirror_the_library(pkg):
+    """The fake-tensor (meta) implementations of the forward ops size their opaque `saved` buffers in Python; the library sizes the real
+    ones (pure host arithmetic: no CUDA call).  A layout change in the library that is not mirrored makes opcheck / torch.compile tracing
+    disagree with the real op -- twice in round 2 -- so the mirrors are pinned here, on shapes with every kind of padding."""
+    lib = pkg._lib.lib()
+    ops = pkg.ops
+    for B, N, T, d, mlp, K in [(160, 196, 26, 512, 1024, 1001), (3, 576, 64, 512, 1024, 3001), (9, 62, 4, 136, 24, 16), (1, 1, 1, 8, 8, 2),
+                               (5, 47, 9, 16, 72, 22), (7, 13, 3, 40, 136, 35)]:
+        assert ops._pcp_saved_bytes(B, T, d) == lib.hca_phrase_conv_pool_saved_bytes(B, T, d), (B, T, d)
+        assert ops._coattn_saved_bytes(B, N, T, d) == lib.hca_coattn_saved_bytes(B, N, T, d), (B, N, T, d)
+        assert ops._mlp_saved_bytes(B, d, mlp, K) == lib.hca_mlp_saved_bytes(B, d, mlp, K), (B, d, mlp, K)
+        if d % 16 == 0:
+            assert ops._lstm_saved_bytes(B, T, d, d) == lib.hca_lstm_saved_bytes(B, T, d, d), (B, T, d)
+
+
 def test_no_cpu_fallback(pkg):
     net = pkg.HieCoAttnHotPath(50, 32, 7, 16)
     with pytest.raises((NotImplementedError, RuntimeError)):

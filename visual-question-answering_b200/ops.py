@@ -256,14 +256,18 @@ def lstm(x: Tensor, lens: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh
     return out, saved
 
 
+def _lstm_saved_bytes(B: int, T: int, E: int, H: int) -> int:
+    """Mirror of ``hca_lstm_saved_bytes`` for the fake-tensor path (tests/test_modules_cpu.py checks the mirrors against the library)."""
+    al = lambda n: (n + 255) // 256 * 256
+    BT = B * T
+    return al(BT * 4 * H * 4) + al(BT * H * 4) + al(2 * BT * (E + H) * 2) + al(2 * 4 * H * E * 2) + 256
+
+
 @lstm.register_fake
 def _(x, lens, w_ih, w_hh, b_ih, b_hh):
     B, T, E = x.shape
     H = w_hh.shape[1]
-    al = lambda n: (n + 255) // 256 * 256
-    BT = B * T
-    nbytes = al(BT * 4 * H * 4) + al(BT * H * 4) + al(2 * BT * (E + H) * 2) + al(2 * 4 * H * E * 2) + 256      # mirrors hca_lstm_saved_bytes
-    return x.new_empty(B, T, H), x.new_empty(nbytes, dtype=torch.uint8)
+    return x.new_empty(B, T, H), x.new_empty(_lstm_saved_bytes(B, T, E, H), dtype=torch.uint8)
 
 
 @torch.library.custom_op(f"{NS}::lstm_bwd", mutates_args=("dw_ih", "dw_hh", "db_ih", "db_hh"), device_types="cuda")
@@ -340,15 +344,19 @@ def coattn(V: Tensor, q0: Tensor, q1: Tensor, q2: Tensor, Wv: Tensor, bv: Tensor
     return vhat, qhat, saved
 
 
+def _coattn_saved_bytes(B: int, N: int, T: int, d: int) -> int:
+    """Mirror of ``hca_coattn_saved_bytes`` for the fake-tensor path."""
+    r8 = lambda x: (x + 7) // 8 * 8
+    al = lambda x: (x + 255) // 256 * 256
+    pl = lambda rows, cols: al(2 * rows * r8(cols) * 2)
+    return 2 * pl(B * N, d) + 3 * pl(B * 3 * T, d) + pl(B * 3 * T, N) + al(B * 3 * N * 4) + al(B * 3 * T * 4) + 256
+
+
 @coattn.register_fake
 def _(V, q0, q1, q2, Wv, bv, Wq, bq, wv, cv, wq, cq):
     B, N, d = V.shape
     T = q0.shape[1]
-    r8 = lambda x: (x + 7) // 8 * 8
-    al = lambda x: (x + 255) // 256 * 256
-    pl = lambda rows, cols: al(2 * rows * r8(cols) * 2)
-    nbytes = 2 * pl(B * N, d) + 3 * pl(B * 3 * T, d) + pl(B * 3 * T, N) + al(B * 3 * N * 4) + al(B * 3 * T * 4) + 256
-    return V.new_empty(3, B, d), V.new_empty(3, B, d), V.new_empty(nbytes, dtype=torch.uint8)
+    return V.new_empty(3, B, d), V.new_empty(3, B, d), V.new_empty(_coattn_saved_bytes(B, N, T, d), dtype=torch.uint8)
 
 
 @torch.library.custom_op(f"{NS}::coattn_bwd", mutates_args=("dWv", "dbv", "dWq", "dbq", "dwv", "dcv", "dwq", "dcq"),
